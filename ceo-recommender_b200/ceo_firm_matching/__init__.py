@@ -1,0 +1,18 @@
+"""ceo_firm_matching — B200-native build of the CEO-Recommender two-tower hot path.
+
+Drop-in for the reference package's training/scoring surface: ``CEOFirmMatcher``,
+``StructuralDistillationNet``, ``train_model``, ``train_structural_model``, ``contrastive``
+(``ContrastiveCEOFirmMatcher``, ``info_nce_loss``, ``train_contrastive``, ``compute_retrieval_metrics``),
+``scoring.score_topk`` and the ``cli`` / ``structural_cli`` ``--synthetic`` entry points.  The arithmetic
+runs in hand-written sm_100a CUDA kernels (``libcfm_b200.so``) reached through a C ABI
+(``include/cfm_b200.h``); there is no CPU fallback.  Plotting / explainability / WRDS modules of the
+reference are out of scope.
+"""
+from .config import Config
+from .structural_config import StructuralConfig
+from .model import CEOFirmMatcher
+from .structural_model import StructuralDistillationNet
+
+__version__ = "0.4.0+b200"
+
+__all__ = ["Config", "StructuralConfig", "CEOFirmMatcher", "StructuralDistillationNet"]

@@ -1,0 +1,136 @@
+"""ctypes binding of libcfm_b200.so (the C ABI declared in include/cfm_b200.h).
+
+There is NO fallback: if the shared library is missing, or a CUDA device is not
+present when an op is called, the call raises.  Build the library with
+``python __graft_entry__.py`` (or ``make -C ceo-recommender_b200/csrc``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+CFM_MAX_TABLES = 16
+CFM_TOPK_CAND = 256
+CFM_ABI_VERSION = 1
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libcfm_b200.so")
+
+p_f32 = C.c_void_p
+i64 = C.c_int64
+
+
+class Tower(C.Structure):
+    """Mirror of ``cfm_tower_t``."""
+    _fields_ = [
+        ("n_num", i64), ("n_tables", i64), ("emb_dim", i64), ("h1", i64), ("h2", i64), ("d_out", i64),
+        ("bn2", i64), ("drop1", C.c_double), ("drop2", C.c_double), ("tower_id", i64),
+        ("x_num", C.c_void_p), ("x_cat", C.c_void_p),
+        ("tables", C.c_void_p * CFM_MAX_TABLES), ("table_rows", i64 * CFM_MAX_TABLES),
+        ("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p),
+        ("w3", C.c_void_p), ("b3", C.c_void_p),
+        ("bn1_w", C.c_void_p), ("bn1_b", C.c_void_p), ("bn2_w", C.c_void_p), ("bn2_b", C.c_void_p),
+        ("bn1_rm", C.c_void_p), ("bn1_rv", C.c_void_p), ("bn2_rm", C.c_void_p), ("bn2_rv", C.c_void_p),
+        ("bn1_nbt", C.c_void_p), ("bn2_nbt", C.c_void_p),
+        ("h1_raw", C.c_void_p), ("h2_raw", C.c_void_p), ("out", C.c_void_p),
+        ("bn1_stat", C.c_void_p), ("bn2_stat", C.c_void_p), ("scratch", C.c_void_p),
+    ]
+
+
+class TowerGrads(C.Structure):
+    """Mirror of ``cfm_tower_grads_t``."""
+    _fields_ = [
+        ("g_out", C.c_void_p),
+        ("dw1", C.c_void_p), ("db1", C.c_void_p), ("dw2", C.c_void_p), ("db2", C.c_void_p),
+        ("dw3", C.c_void_p), ("db3", C.c_void_p),
+        ("dbn1_w", C.c_void_p), ("dbn1_b", C.c_void_p), ("dbn2_w", C.c_void_p), ("dbn2_b", C.c_void_p),
+        ("dy1", C.c_void_p), ("dy2", C.c_void_p), ("dx_emb", C.c_void_p), ("dx_num", C.c_void_p),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/cfm_b200.h declares
+_V, _I, _D, _U64 = C.c_void_p, i64, C.c_double, C.c_uint64
+PROTOTYPES = {
+    "cfm_abi_version": (C.c_int, []),
+    "cfm_last_error": (C.c_char_p, []),
+    "cfm_device_info": (C.c_int, [C.POINTER(i64)] * 4),
+    "cfm_tower_scratch_floats": (i64, [C.POINTER(Tower)]),
+    "cfm_towers_fwd": (C.c_int, [C.POINTER(Tower), _I, _I, _I, _U64, _U64, _V, _V]),
+    "cfm_towers_bwd": (C.c_int, [C.POINTER(Tower), C.POINTER(TowerGrads), _I, _I, _I, _U64, _U64, _V]),
+    "cfm_dropout_mask": (C.c_int, [_V, _I, _I, _D, _I, _I, _U64, _U64, _V]),
+    "cfm_emb_grad_tmp_bytes": (i64, [_I, _I]),
+    "cfm_emb_grad_segment_reduce": (C.c_int, [_V, _V, _I, _I, _I, C.POINTER(C.c_void_p), C.POINTER(i64),
+                                              _V, _V, _V, _V, _V, _I, _V]),
+    "cfm_emb_grad_rezero": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(i64), _I, _I, _V, _I, _V]),
+    "cfm_cosine_head_fwd": (C.c_int, [_V, _V, _V, _I, _I, _D, _V, _V, _V, _V, _V, _V, _V, _V]),
+    "cfm_cosine_head_bwd": (C.c_int, [_V, _V, _V, _V, _V, _V, _V, _V, _V, _I, _I, _D, _V, _V, _V, _V, _V]),
+    "cfm_structural_head": (C.c_int, [_V, _V, _V, _V, _V, _V, _I, _D, _V, _V, _V, _V, _V, _V]),
+    "cfm_infonce_rowsum": (C.c_int, [_V, _V, _I, _I, _I, _D, _I, _V, _V, _V]),
+    "cfm_infonce_grad": (C.c_int, [_V, _V, _I, _I, _I, _D, _I, _I, _V, _V, _V, _V]),
+    "cfm_allpairs_topk": (C.c_int, [_V, _V, _V, _V, _I, _I, _I, _I, _I, _D, _I, _V, _V, _V, _V, _V, _V]),
+    "cfm_topk_merge": (C.c_int, [_V, _V, _I, _I, _I, _V, _V, _V]),
+    "cfm_allpairs_rank": (C.c_int, [_V, _V, _I, _I, _I, _V, _V, _V]),
+}
+
+_lib: Optional[C.CDLL] = None
+
+
+class CfmError(RuntimeError):
+    """A libcfm_b200 entry point returned a negative status."""
+
+
+def lib() -> C.CDLL:
+    """Load (once) and return the shared library; raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} not found: the CUDA library is not built (run `python __graft_entry__.py` or "
+                f"`make -C ceo-recommender_b200/csrc`). There is no CPU fallback.")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(handle, name)      # AttributeError if the .so lacks a declared symbol
+            fn.restype, fn.argtypes = res, args
+        if handle.cfm_abi_version() != CFM_ABI_VERSION:
+            raise ImportError(f"libcfm_b200 ABI {handle.cfm_abi_version()} != binding {CFM_ABI_VERSION}")
+        _lib = handle
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc == 0:
+        return
+    msg = lib().cfm_last_error().decode("utf-8", "replace")
+    if rc == -4:
+        raise ValueError(msg)      # torch raises ValueError for train-mode BatchNorm with one row
+    raise CfmError(f"libcfm_b200 error {rc}: {msg}")
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    """Raw device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("ceo_firm_matching (B200 build) has no CPU path: tensor is on " + str(t.device))
+    if not t.is_contiguous():
+        raise RuntimeError("libcfm_b200 needs contiguous tensors")
+    return t.data_ptr()
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+_dev_info = {}
+
+
+def device_info() -> dict:
+    dev = torch.cuda.current_device()
+    if dev not in _dev_info:
+        vals = [i64() for _ in range(4)]
+        check(lib().cfm_device_info(*[C.byref(v) for v in vals]))
+        _dev_info[dev] = dict(zip(("sm_count", "cc_major", "cc_minor", "tower_ctas"), (v.value for v in vals)))
+    return _dev_info[dev]

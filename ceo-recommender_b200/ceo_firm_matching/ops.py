@@ -1,0 +1,467 @@
+"""Host side of the fused ops: autograd Functions over the libcfm_b200 C ABI.
+
+torch is used for device memory, streams and autograd bookkeeping only; all
+arithmetic of the hot path runs in the CUDA library (``_native.lib()``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _native as N
+
+
+# ---------------------------------------------------------------------------------------
+# small per-device state
+# ---------------------------------------------------------------------------------------
+class _DeviceState:
+    """Per-device persistent buffers: error flag, reduction partials, dropout counter."""
+
+    def __init__(self, device: torch.device):
+        self.err_flag = torch.zeros(1, dtype=torch.int32, device=device)
+        self.partial = torch.zeros(4096, dtype=torch.float32, device=device)   # last-CTA-reduces scratch
+        self.dropout_offset = 0
+
+
+_states = {}
+
+
+def _state(device: torch.device) -> _DeviceState:
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    if key not in _states:
+        _states[key] = _DeviceState(torch.device("cuda", key))
+    return _states[key]
+
+
+def raise_if_index_error(device: Optional[torch.device] = None) -> None:
+    """Synchronising check of the device-side error word (mirrors torch's IndexError for a
+    categorical index outside its embedding table — model.py:69,74)."""
+    for key, st in list(_states.items()):
+        if device is not None and device.index not in (None, key):
+            continue
+        flag = int(st.err_flag.item())
+        if flag & 1:
+            st.err_flag.zero_()
+            raise IndexError("index out of range in self (categorical index outside its embedding table)")
+
+
+def _require_cuda(*tensors: torch.Tensor) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "ceo_firm_matching (B200 build) runs on CUDA only and has no CPU fallback; got a tensor on "
+                f"{t.device}. Move the module and its inputs to 'cuda'.")
+
+
+def next_dropout_offset(device: torch.device) -> Tuple[int, int]:
+    """(seed, offset) of the next dropout draw: seed follows ``torch.manual_seed``, offset counts calls."""
+    st = _state(device)
+    st.dropout_offset += 1
+    return torch.initial_seed() & 0xFFFFFFFFFFFFFFFF, st.dropout_offset
+
+
+# ---------------------------------------------------------------------------------------
+# towers
+# ---------------------------------------------------------------------------------------
+class TowerHandle:
+    """Binds one tower's nn.Embedding list + nn.Sequential to the ``cfm_tower_t`` layout.
+
+    The sub-modules stay ordinary torch modules (scripts call ``model.firm_tower(x)`` directly —
+    deep_dive.py:80-91); the fused op just reads their parameters.
+    """
+
+    def __init__(self, embeddings: nn.ModuleList, seq: nn.Sequential, lin: Sequence[int],
+                 bn: Sequence[Optional[int]], drop: Sequence[float], tower_id: int):
+        self.embeddings, self.seq = embeddings, seq
+        self.lin, self.bn, self.tower_id = tuple(lin), tuple(bn), tower_id
+        self._drop = tuple(drop)
+        self._scratch = None
+        self.table_grads: Optional["PersistentTableGrads"] = None
+
+    # dims -------------------------------------------------------------------------------
+    @property
+    def n_tables(self) -> int:
+        return len(self.embeddings)
+
+    @property
+    def emb_dim(self) -> int:
+        return self.embeddings[0].embedding_dim if self.n_tables else 0
+
+    def linear(self, i: int) -> nn.Linear:
+        return self.seq[self.lin[i]]
+
+    def batchnorm(self, i: int) -> Optional[nn.BatchNorm1d]:
+        return self.seq[self.bn[i]] if self.bn[i] is not None else None
+
+    def drop_p(self, i: int) -> float:
+        """Dropout probability at site i, read live from the module so ``m.p = 0`` is honoured."""
+        if self._drop[i] is None:
+            return 0.0
+        mod = self.seq[self._drop[i]]
+        return float(mod.p)
+
+    def params(self) -> List[torch.Tensor]:
+        """Differentiable tensors in the canonical order the Function uses."""
+        ps = [e.weight for e in self.embeddings]
+        l1, l2, l3 = self.linear(0), self.linear(1), self.linear(2)
+        b1, b2 = self.batchnorm(0), self.batchnorm(1)
+        ps += [l1.weight, l1.bias, b1.weight, b1.bias, l2.weight, l2.bias]
+        if b2 is not None:
+            ps += [b2.weight, b2.bias]
+        ps += [l3.weight, l3.bias]
+        return ps
+
+    def scratch(self, device: torch.device, floats: int) -> torch.Tensor:
+        if self._scratch is None or self._scratch.numel() < floats or self._scratch.device != device:
+            self._scratch = torch.empty(floats, dtype=torch.float32, device=device)
+        return self._scratch
+
+
+class _TowerCall:
+    """Everything one fwd/bwd pair of a tower shares: the C struct and the tensors keeping it alive."""
+
+    def __init__(self, h: TowerHandle, x_num: torch.Tensor, x_cat: torch.Tensor, B: int):
+        dev = x_num.device
+        l1, l2, l3 = h.linear(0), h.linear(1), h.linear(2)
+        b1, b2 = h.batchnorm(0), h.batchnorm(1)
+        in_dim = l1.in_features
+        n_num = in_dim - h.n_tables * h.emb_dim
+        if x_num.shape != (B, n_num) or (h.n_tables and x_cat.shape != (B, h.n_tables)):
+            raise RuntimeError(f"tower input shapes {tuple(x_num.shape)}, {tuple(x_cat.shape)} do not match "
+                               f"[B,{n_num}] / [B,{h.n_tables}]")
+        self.h = h
+        self.B = B
+        self.x_num, self.x_cat = x_num, x_cat
+        self.h1_raw = torch.empty(B, l1.out_features, device=dev)
+        self.h2_raw = torch.empty(B, l2.out_features, device=dev)
+        self.out = torch.empty(B, l3.out_features, device=dev)
+        self.bn1_stat = torch.empty(4, l1.out_features, device=dev)
+        self.bn2_stat = torch.empty(4, l2.out_features, device=dev)
+        t = N.Tower()
+        t.n_num, t.n_tables, t.emb_dim = n_num, h.n_tables, h.emb_dim
+        t.h1, t.h2, t.d_out = l1.out_features, l2.out_features, l3.out_features
+        t.bn2 = 1 if b2 is not None else 0
+        t.drop1, t.drop2 = h.drop_p(0), h.drop_p(1)
+        t.tower_id = h.tower_id
+        t.x_num, t.x_cat = N.ptr(x_num), N.ptr(x_cat)
+        for i, e in enumerate(h.embeddings):
+            t.tables[i] = N.ptr(e.weight)
+            t.table_rows[i] = e.num_embeddings
+        t.w1, t.b1, t.w2, t.b2, t.w3, t.b3 = (N.ptr(x) for x in (l1.weight, l1.bias, l2.weight, l2.bias,
+                                                                  l3.weight, l3.bias))
+        t.bn1_w, t.bn1_b = N.ptr(b1.weight), N.ptr(b1.bias)
+        t.bn1_rm, t.bn1_rv, t.bn1_nbt = N.ptr(b1.running_mean), N.ptr(b1.running_var), N.ptr(b1.num_batches_tracked)
+        if b2 is not None:
+            t.bn2_w, t.bn2_b = N.ptr(b2.weight), N.ptr(b2.bias)
+            t.bn2_rm, t.bn2_rv, t.bn2_nbt = (N.ptr(b2.running_mean), N.ptr(b2.running_var),
+                                             N.ptr(b2.num_batches_tracked))
+        t.h1_raw, t.h2_raw, t.out = N.ptr(self.h1_raw), N.ptr(self.h2_raw), N.ptr(self.out)
+        t.bn1_stat, t.bn2_stat = N.ptr(self.bn1_stat), N.ptr(self.bn2_stat)
+        per_cta = N.lib().cfm_tower_scratch_floats(C.byref(t))
+        t.scratch = N.ptr(h.scratch(dev, per_cta * N.device_info()["tower_ctas"]))
+        self.struct = t
+
+
+def _as_index(x_cat: torch.Tensor) -> torch.Tensor:
+    # explain.py:53,59 hands categoricals over as float -> .long(); accept any integer/float dtype
+    return x_cat if x_cat.dtype == torch.int64 else x_cat.long()
+
+
+class TowersFunction(torch.autograd.Function):
+    """Forward/backward of one or two towers over the same batch (model.py:69-76; structural_model.py:120-127).
+
+    apply(handles, training, seed, offset, x_num_0, x_cat_0[, x_num_1, x_cat_1], *params) -> out_0[, out_1]
+    """
+
+    @staticmethod
+    def forward(ctx, handles, training, seed, offset, *tensors):
+        n = len(handles)
+        xs = tensors[:2 * n]
+        _require_cuda(*tensors)
+        B = xs[0].shape[0]
+        dev = xs[0].device
+        calls = []
+        with torch.cuda.device(dev):
+            for i, h in enumerate(handles):
+                x_num = xs[2 * i].contiguous().float()
+                x_cat = _as_index(xs[2 * i + 1]).contiguous()
+                calls.append(_TowerCall(h, x_num, x_cat, B))
+            arr = (N.Tower * n)(*[c.struct for c in calls])
+            N.check(N.lib().cfm_towers_fwd(arr, n, B, 1 if training else 0, seed, offset,
+                                           N.ptr(_state(dev).err_flag), N.stream_ptr()))
+        ctx.calls, ctx.arr, ctx.training, ctx.seed, ctx.offset = calls, arr, training, seed, offset
+        ctx.handles = handles
+        ctx.needs_xnum = [xs[2 * i].requires_grad for i in range(n)]
+        outs = tuple(c.out for c in calls)
+        return outs if n > 1 else outs[0]
+
+    @staticmethod
+    def backward(ctx, *g_outs):
+        calls, n = ctx.calls, len(ctx.calls)
+        dev = calls[0].out.device
+        B = calls[0].B
+        per_tower = []
+        grads_arr = (N.TowerGrads * n)()
+        with torch.cuda.device(dev):
+            for i, c in enumerate(calls):
+                h, t = c.h, c.struct
+                g = g_outs[i]
+                g = torch.zeros_like(c.out) if g is None else g.contiguous().float()
+                K_in = t.n_num + t.n_tables * t.emb_dim
+                d = dict(
+                    g_out=g,
+                    dw1=torch.empty(t.h1, K_in, device=dev), db1=torch.empty(t.h1, device=dev),
+                    dw2=torch.empty(t.h2, t.h1, device=dev), db2=torch.empty(t.h2, device=dev),
+                    dw3=torch.empty(t.d_out, t.h2, device=dev), db3=torch.empty(t.d_out, device=dev),
+                    dbn1_w=torch.empty(t.h1, device=dev), dbn1_b=torch.empty(t.h1, device=dev),
+                    dbn2_w=torch.empty(t.h2, device=dev) if t.bn2 else None,
+                    dbn2_b=torch.empty(t.h2, device=dev) if t.bn2 else None,
+                    dy1=torch.empty(B, t.h1, device=dev), dy2=torch.empty(B, t.h2, device=dev),
+                    dx_emb=torch.empty(B, t.n_tables * t.emb_dim, device=dev) if t.n_tables else None,
+                    dx_num=torch.empty(B, t.n_num, device=dev) if ctx.needs_xnum[i] else None,
+                )
+                for k, v in d.items():
+                    setattr(grads_arr[i], k, N.ptr(v))
+                per_tower.append(d)
+            N.check(N.lib().cfm_towers_bwd(ctx.arr, grads_arr, n, B, 1 if ctx.training else 0, ctx.seed, ctx.offset,
+                                           N.stream_ptr()))
+            out: List[Optional[torch.Tensor]] = []
+            for i, (c, d) in enumerate(zip(calls, per_tower)):
+                out += [d["dx_num"], None]
+            for c, d in zip(calls, per_tower):
+                h, t = c.h, c.struct
+                table_grads = embedding_grads(h, c.x_cat, d["dx_emb"], B) if t.n_tables else []
+                out += table_grads
+                out += [d["dw1"], d["db1"], d["dbn1_w"], d["dbn1_b"], d["dw2"], d["db2"]]
+                if t.bn2:
+                    out += [d["dbn2_w"], d["dbn2_b"]]
+                out += [d["dw3"], d["db3"]]
+        return (None, None, None, None, *out)
+
+
+def run_towers(handles: Sequence[TowerHandle], inputs: Sequence[Tuple[torch.Tensor, torch.Tensor]], training: bool):
+    """Convenience wrapper: gathers parameters, draws the dropout (seed, offset) and applies the Function."""
+    dev = inputs[0][0].device
+    _require_cuda(*(t for pair in inputs for t in pair))
+    seed, offset = next_dropout_offset(dev) if training else (0, 0)
+    flat = [t for pair in inputs for t in pair]
+    params = [p for h in handles for p in h.params()]
+    _require_cuda(*params)
+    return TowersFunction.apply(list(handles), training, seed, offset, *flat, *params)
+
+
+# ---------------------------------------------------------------------------------------
+# embedding gradients: sorted-segment reduce into dense [n_i, E] tables
+# ---------------------------------------------------------------------------------------
+class _SortScratch:
+    def __init__(self, n_items: int, n_tables: int, B: int, device: torch.device):
+        self.n_items = n_items
+        self.keys_tmp = torch.empty(n_items, dtype=torch.int64, device=device)
+        self.vals_tmp = torch.empty(n_items, dtype=torch.int32, device=device)
+        self.keys_sorted = [torch.empty(n_items, dtype=torch.int64, device=device) for _ in range(2)]
+        self.vals_sorted = torch.empty(n_items, dtype=torch.int32, device=device)
+        self.tmp_bytes = N.lib().cfm_emb_grad_tmp_bytes(n_tables, B)
+        self.tmp = torch.empty(self.tmp_bytes, dtype=torch.uint8, device=device)
+        self.flip = 0
+
+
+class PersistentTableGrads:
+    """Keeps each table's dense ``.grad`` allocated across steps and re-zeroes only the rows the previous
+    step touched (their sorted keys are kept), so the result is the exact dense gradient torch produces
+    (``nn.Embedding(sparse=False)``, model.py:24-33) without a full-table memset every step."""
+
+    def __init__(self, handle: TowerHandle):
+        self.h = handle
+        self.prev_items = 0
+        self.scratch: Optional[_SortScratch] = None
+        for e in handle.embeddings:
+            e.weight.grad = torch.zeros_like(e.weight)
+
+    def rezero(self) -> None:
+        if self.prev_items == 0 or self.scratch is None:
+            return
+        h = self.h
+        ptrs = (C.c_void_p * h.n_tables)(*[N.ptr(e.weight.grad) for e in h.embeddings])
+        rows = (N.i64 * h.n_tables)(*[e.num_embeddings for e in h.embeddings])
+        prev_keys = self.scratch.keys_sorted[self.scratch.flip ^ 1]
+        N.check(N.lib().cfm_emb_grad_rezero(ptrs, rows, h.n_tables, h.emb_dim, N.ptr(prev_keys), self.prev_items,
+                                            N.stream_ptr()))
+        self.prev_items = 0
+
+
+def _segment_reduce(h: TowerHandle, x_cat: torch.Tensor, dx_emb: torch.Tensor, B: int,
+                    targets: Sequence[torch.Tensor], scratch: _SortScratch) -> None:
+    ptrs = (C.c_void_p * h.n_tables)(*[N.ptr(t) for t in targets])
+    rows = (N.i64 * h.n_tables)(*[e.num_embeddings for e in h.embeddings])
+    N.check(N.lib().cfm_emb_grad_segment_reduce(
+        N.ptr(x_cat), N.ptr(dx_emb), B, h.n_tables, h.emb_dim, ptrs, rows, N.ptr(scratch.keys_tmp),
+        N.ptr(scratch.vals_tmp), N.ptr(scratch.keys_sorted[scratch.flip]), N.ptr(scratch.vals_sorted),
+        N.ptr(scratch.tmp), scratch.tmp_bytes, N.stream_ptr()))
+
+
+def embedding_grads(h: TowerHandle, x_cat: torch.Tensor, dx_emb: torch.Tensor, B: int) -> List[Optional[torch.Tensor]]:
+    """Dense gradient of every table of tower ``h`` (aten::embedding_dense_backward semantics)."""
+    n_items = B * h.n_tables
+    pg = h.table_grads
+    if pg is not None:
+        # fast path: write into the persistent .grad buffers (rows touched last step were re-zeroed by
+        # PersistentTableGrads.rezero(), called from zero_grad), autograd gets no tensor for the tables
+        if pg.scratch is None or pg.scratch.n_items != n_items:
+            pg.rezero()
+            pg.scratch = _SortScratch(n_items, h.n_tables, B, dx_emb.device)
+        _segment_reduce(h, x_cat, dx_emb, B, [e.weight.grad for e in h.embeddings], pg.scratch)
+        pg.prev_items = n_items
+        pg.scratch.flip ^= 1
+        return [None] * h.n_tables
+    scratch = _SortScratch(n_items, h.n_tables, B, dx_emb.device)
+    grads = [torch.zeros_like(e.weight) for e in h.embeddings]
+    _segment_reduce(h, x_cat, dx_emb, B, grads, scratch)
+    return grads
+
+
+# ---------------------------------------------------------------------------------------
+# cosine head (model.py:79-87 / contrastive.py:64-70,92-93) with optional fused weighted MSE (training.py:52)
+# ---------------------------------------------------------------------------------------
+class CosineHeadFunction(torch.autograd.Function):
+    """apply(u, v, logit_scale, eps, want_unit) -> score [B,1] (+ u_hat, v_hat when want_unit)."""
+
+    @staticmethod
+    def forward(ctx, u, v, logit_scale, eps, want_unit):
+        _require_cuda(u, v, logit_scale)
+        u, v = u.contiguous(), v.contiguous()
+        B, D = u.shape
+        score = torch.empty(B, 1, device=u.device)
+        u_hat = torch.empty_like(u) if want_unit else None
+        v_hat = torch.empty_like(v) if want_unit else None
+        with torch.cuda.device(u.device):
+            N.check(N.lib().cfm_cosine_head_fwd(N.ptr(u), N.ptr(v), N.ptr(logit_scale), B, D, eps, N.ptr(score),
+                                                N.ptr(u_hat), N.ptr(v_hat), None, None, None, None, N.stream_ptr()))
+        ctx.save_for_backward(u, v, logit_scale)
+        ctx.eps = eps
+        return (score, u_hat, v_hat) if want_unit else score
+
+    @staticmethod
+    def backward(ctx, d_score, d_uhat=None, d_vhat=None):
+        u, v, logit_scale = ctx.saved_tensors
+        B, D = u.shape
+        du, dv = torch.empty_like(u), torch.empty_like(v)
+        dls = torch.zeros((), device=u.device)
+        d_score = d_score.contiguous() if d_score is not None else None
+        d_uhat = d_uhat.contiguous() if d_uhat is not None else None
+        d_vhat = d_vhat.contiguous() if d_vhat is not None else None
+        with torch.cuda.device(u.device):
+            N.check(N.lib().cfm_cosine_head_bwd(N.ptr(u), N.ptr(v), N.ptr(logit_scale), N.ptr(d_score), N.ptr(d_uhat),
+                                                N.ptr(d_vhat), None, None, None, B, D, ctx.eps, N.ptr(du), N.ptr(dv),
+                                                N.ptr(dls), N.ptr(_state(u.device).partial), N.stream_ptr()))
+        return du, dv, dls, None, None
+
+
+class CosineMSEFunction(torch.autograd.Function):
+    """apply(u, v, logit_scale, target, weights, eps) -> (loss, score): loss = mean(w (s - t)^2)."""
+
+    @staticmethod
+    def forward(ctx, u, v, logit_scale, target, weights, eps):
+        _require_cuda(u, v, logit_scale, target, weights)
+        u, v = u.contiguous(), v.contiguous()
+        target, weights = target.contiguous().float(), weights.contiguous().float()
+        B, D = u.shape
+        score = torch.empty(B, 1, device=u.device)
+        loss = torch.zeros((), device=u.device)
+        with torch.cuda.device(u.device):
+            N.check(N.lib().cfm_cosine_head_fwd(N.ptr(u), N.ptr(v), N.ptr(logit_scale), B, D, eps, N.ptr(score), None,
+                                                None, N.ptr(target), N.ptr(weights), N.ptr(loss),
+                                                N.ptr(_state(u.device).partial), N.stream_ptr()))
+        ctx.save_for_backward(u, v, logit_scale, target, weights)
+        ctx.eps = eps
+        ctx.mark_non_differentiable(score)
+        return loss, score
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_score):
+        u, v, logit_scale, target, weights = ctx.saved_tensors
+        B, D = u.shape
+        du, dv = torch.empty_like(u), torch.empty_like(v)
+        dls = torch.zeros((), device=u.device)
+        g_loss = g_loss.contiguous().float()
+        with torch.cuda.device(u.device):
+            N.check(N.lib().cfm_cosine_head_bwd(N.ptr(u), N.ptr(v), N.ptr(logit_scale), None, None, None,
+                                                N.ptr(target), N.ptr(weights), N.ptr(g_loss), B, D, ctx.eps,
+                                                N.ptr(du), N.ptr(dv), N.ptr(dls), N.ptr(_state(u.device).partial),
+                                                N.stream_ptr()))
+        return du, dv, dls, None, None, None
+
+
+# ---------------------------------------------------------------------------------------
+# structural head (structural_model.py:130-141, structural_training.py:75-77)
+# ---------------------------------------------------------------------------------------
+class StructuralHeadFunction(torch.autograd.Function):
+    """apply(c_logits, f_logits, A) -> expected_match [B,1]."""
+
+    @staticmethod
+    def forward(ctx, c_logits, f_logits, A):
+        _require_cuda(c_logits, f_logits, A)
+        c_logits, f_logits = c_logits.contiguous(), f_logits.contiguous()
+        B = c_logits.shape[0]
+        match = torch.empty(B, 1, device=c_logits.device)
+        with torch.cuda.device(c_logits.device):
+            N.check(N.lib().cfm_structural_head(N.ptr(c_logits), N.ptr(f_logits), N.ptr(A), None, None, None, B, 0.0,
+                                                N.ptr(match), None, None, None,
+                                                N.ptr(_state(c_logits.device).partial), N.stream_ptr()))
+        ctx.save_for_backward(c_logits, f_logits, A)
+        return match
+
+    @staticmethod
+    def backward(ctx, d_match):
+        c_logits, f_logits, A = ctx.saved_tensors
+        B = c_logits.shape[0]
+        dc, df = torch.empty_like(c_logits), torch.empty_like(f_logits)
+        scratch_match = torch.empty(B, device=c_logits.device)
+        d_match = d_match.contiguous().float()
+        with torch.cuda.device(c_logits.device):
+            N.check(N.lib().cfm_structural_head(N.ptr(c_logits), N.ptr(f_logits), N.ptr(A), None, None,
+                                                N.ptr(d_match), B, 0.0, N.ptr(scratch_match), None, N.ptr(dc),
+                                                N.ptr(df), N.ptr(_state(c_logits.device).partial), N.stream_ptr()))
+        return dc, df, None
+
+
+class StructuralKLFunction(torch.autograd.Function):
+    """apply(c_logits, f_logits, A, target_ceo, target_firm) -> loss: KL(batchmean) of both sides, summed.
+    The gradients w.r.t. both logit sets are produced by the same kernel launch as the loss."""
+
+    @staticmethod
+    def forward(ctx, c_logits, f_logits, A, target_ceo, target_firm):
+        _require_cuda(c_logits, f_logits, A, target_ceo, target_firm)
+        c_logits, f_logits = c_logits.contiguous(), f_logits.contiguous()
+        target_ceo, target_firm = target_ceo.contiguous().float(), target_firm.contiguous().float()
+        B = c_logits.shape[0]
+        dev = c_logits.device
+        loss = torch.zeros((), device=dev)
+        match = torch.empty(B, device=dev)
+        need_grad = c_logits.requires_grad or f_logits.requires_grad
+        dc = torch.empty_like(c_logits) if need_grad else None
+        df = torch.empty_like(f_logits) if need_grad else None
+        with torch.cuda.device(dev):
+            N.check(N.lib().cfm_structural_head(N.ptr(c_logits), N.ptr(f_logits), N.ptr(A), N.ptr(target_ceo),
+                                                N.ptr(target_firm), None, B, 1.0, N.ptr(match), N.ptr(loss),
+                                                N.ptr(dc), N.ptr(df), N.ptr(_state(dev).partial), N.stream_ptr()))
+        ctx.dc, ctx.df = dc, df
+        return loss
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        # d loss / d logits was computed with kl_scale = 1; chain with the incoming scalar
+        if ctx.dc is None:
+            return None, None, None, None, None
+        return ctx.dc * g_loss, ctx.df * g_loss, None, None, None
+
+
+def dropout_mask(B: int, width: int, p: float, tower_id: int, site: int, seed: int, offset: int,
+                 device: torch.device) -> torch.Tensor:
+    """Materialise the keep-mask the tower kernels regenerate from (seed, offset) — differential tests only."""
+    mask = torch.empty(B, width, dtype=torch.uint8, device=device)
+    with torch.cuda.device(device):
+        N.check(N.lib().cfm_dropout_mask(N.ptr(mask), B, width, p, tower_id, site, seed, offset, N.stream_ptr()))
+    return mask

@@ -1,0 +1,1026 @@
+// Tower kernels (exact-fp32 path): categorical-embedding gather + numeric concat + 3-layer MLP,
+// forward and backward, one Linear per launch ("stage"), both towers in one grid (blockIdx.y).
+//
+// replaces ceo_firm_matching/model.py:69-76 and structural_model.py:120-127 (+ their autograd).
+//
+// Layout of one stage launch: persistent CTAs (<= one per SM per tower) walk 64-row tiles.  The stage's
+// weight matrix lives in shared memory for the CTA's lifetime; each tile's input activations are
+// (re)built in shared memory (stage 1: gathered embedding rows + numerics; stage >1: BN/ReLU/dropout of the
+// previous stage's raw output) and multiplied with register-tiled FMA loops fed by conflict-free LDS.128.
+// Train-mode BatchNorm needs whole-batch statistics between stages, hence the stage-per-launch split:
+// every CTA writes (count, mean, M2) partials (two-pass per tile, Chan-merged), a 1-CTA finalize kernel
+// merges them in a fixed order -> bitwise reproducible.  Backward mirrors this: per-CTA weight-gradient
+// accumulators stay in registers over all tiles and are written once, then reduced in fixed CTA order.
+#include "common.cuh"
+#include <algorithm>
+
+namespace cfm {
+
+constexpr int TM = 64;    // rows per tile
+constexpr int NT = 256;   // threads per CTA
+constexpr float BN_EPS = 1e-5f;
+constexpr int MAX_SMEM = 227 * 1024;
+
+// ------------------------------------------------------------------------------------------
+// descriptors (plain structs passed by value as kernel parameters)
+// ------------------------------------------------------------------------------------------
+struct GatherSrc {
+    int n_num, n_tab, E;
+    const float* x_num;
+    const long long* x_cat;
+    const float* tab[CFM_MAX_TABLES];
+    long long tab_rows[CFM_MAX_TABLES];
+};
+
+struct ActSrc {           // a = dropout(relu(bn(h)))
+    const float* h;       // [B,K] raw Linear output of the previous stage
+    int bn_mode;          // 0 none, 1 batch stats (mean, istd), 2 running stats (mean, var)
+    const float *mean, *var_or_istd, *gamma, *beta;
+    DropCtx drop;
+};
+
+struct InputDesc {        // how a stage's [TM, K] input tile is built
+    int stage;            // 1: gather, >1: activation of previous stage
+    int K;
+    GatherSrc g;
+    ActSrc a;
+};
+
+struct GemmPlan {         // register tiling of a [TM, n] output: thread (rg, cg) owns rows rg+i*NRG, cols cg+j*NCG
+    int passes, NCG, NRG, RM, wrows;
+};
+
+__host__ __device__ inline GemmPlan make_plan(int n) {
+    GemmPlan p;
+    int n4 = ceil_div(n, 4);
+    p.passes = ceil_div(n4, 32);
+    p.NCG = ceil_div(n4, p.passes);
+    int nrg = NT / p.NCG;
+    if (nrg > TM) nrg = TM;
+    int rm = ceil_div(TM, nrg);
+    p.RM = rm <= 1 ? 1 : rm <= 2 ? 2 : rm <= 4 ? 4 : 8;
+    p.NRG = TM / p.RM;
+    p.wrows = p.passes * 4 * p.NCG;
+    return p;
+}
+
+struct FwdStage {
+    InputDesc in;
+    int N;
+    const float* W;       // [N,K]
+    const float* bias;    // [N]
+    float* hout;          // [B,N]
+    float* stat_part;     // nullable: per-CTA (mean[N], M2[N], count) partials
+};
+struct FwdArgs {
+    FwdStage st[2];
+    long long B;
+    int* err;
+};
+
+struct BwdStage {
+    InputDesc in;         // rebuilds the stage's input tile A
+    int N;
+    const float* W;       // [N,K]
+    int a_bn;             // BN precedes the input activation: keep x-hat tile and emit (sum dy, sum dy*xhat)
+    const float* gin;     // [B,N] incoming gradient (g_out for stage 3, dy_s otherwise)
+    int g_mode;           // 0 as is; 1 train BN: gamma*istd*(dy - c1 - xhat*c2); 2 eval BN: dy*gamma*rsqrt(var+eps)
+    const float* hs;      // [B,N] raw output of this stage (g_mode 1)
+    const float *g_mean, *g_var_or_istd, *g_gamma, *g_c1, *g_c2;
+    float* dW_part;       // per-CTA [N, K+1] (last column = bias gradient), global column order
+    float* dy_out;        // stage>1: [B,K]
+    float* sum_part;      // a_bn: per-CTA [2K]
+    float* dx_emb;        // stage 1, nullable: [B, n_tab*E]
+    float* dx_num;        // stage 1, nullable: [B, n_num]
+    int need_dx;          // run the dX GEMM
+};
+struct BwdArgs {
+    BwdStage st[2];
+    long long B;
+};
+
+// ------------------------------------------------------------------------------------------
+// shared-memory carve-up (same arithmetic on host and device)
+// ------------------------------------------------------------------------------------------
+struct FwdSmem {
+    int lda, ws, as, bn, red, tmean, rmean, rm2, idx, total_floats;
+};
+__host__ __device__ inline FwdSmem fwd_smem(int K, int N, int n_tab, const GemmPlan& gp) {
+    FwdSmem s;
+    s.lda = pad_ld(K + 1);
+    int o = 0;
+    s.ws = o; o += gp.wrows * s.lda;
+    s.as = o; o += TM * s.lda;
+    s.bn = o; o += 4 * ((K + 3) & ~3);
+    s.red = o; o += gp.NRG * 4 * gp.NCG;
+    s.tmean = o; o += 4 * gp.NCG;
+    s.rmean = o; o += gp.wrows;
+    s.rm2 = o; o += gp.wrows;
+    s.idx = o; o += TM * (n_tab > 0 ? n_tab : 1);
+    s.total_floats = (o + 3) & ~3;
+    return s;
+}
+
+struct BwdSmem {
+    int lda, ldg, ldxh, wt, as, gs, xh, bna, bng, red, rs, idx, total_floats;
+};
+__host__ __device__ inline BwdSmem bwd_smem(int K, int N, int n_tab, int a_bn, int need_dx, const GemmPlan& gx) {
+    BwdSmem s;
+    s.lda = pad_ld(K + 1);
+    s.ldg = pad_ld(N);
+    s.ldxh = pad_ld(K);
+    int o = 0;
+    s.wt = o; o += need_dx ? gx.wrows * s.ldg : 0;
+    s.as = o; o += TM * s.lda;
+    s.gs = o; o += TM * s.ldg;
+    s.xh = o; o += a_bn ? TM * s.ldxh : 0;
+    s.bna = o; o += 4 * ((K + 3) & ~3);
+    s.bng = o; o += 5 * ((N + 3) & ~3);
+    s.red = o; o += 2 * gx.NRG * 4 * gx.NCG;
+    s.rs = o; o += 2 * gx.wrows;
+    s.idx = o; o += TM * (n_tab > 0 ? n_tab : 1);
+    s.total_floats = (o + 3) & ~3;
+    return s;
+}
+
+// smem column c' of a stage-1 tile -> column of the torch concat layout [numeric | emb_0 | emb_1 ...]
+// (the tile keeps embeddings first so every gathered row lands 16-byte aligned)
+__device__ __forceinline__ int gcol_stage1(int c, int KE, int n_num) { return c < KE ? n_num + c : c - KE; }
+
+// ------------------------------------------------------------------------------------------
+// input tile builders
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void stage_bn_params(const ActSrc& a, int K, float* sm_bn) {
+    int Kp = (K + 3) & ~3;
+    if (a.bn_mode == 0) return;
+    for (int c = threadIdx.x; c < K; c += NT) {
+        float m = a.mean[c], s = a.var_or_istd[c];
+        sm_bn[c] = m;
+        sm_bn[Kp + c] = a.bn_mode == 2 ? rsqrtf(s + BN_EPS) : s;
+        sm_bn[2 * Kp + c] = a.gamma[c];
+        sm_bn[3 * Kp + c] = a.beta[c];
+    }
+}
+
+// Build the [TM, K] input tile (+ ones column at K, zero pad to lda); optionally the x-hat tile.
+__device__ void build_input_tile(const InputDesc& in, long long row0, int rows_valid, float* As, int lda,
+                                 float* Xh, int ldxh, const float* sm_bn, int* sm_idx, int* err) {
+    const int K = in.K;
+    const int tid = threadIdx.x;
+    if (in.stage == 1) {
+        const GatherSrc& g = in.g;
+        const int KE = g.n_tab * g.E;
+        for (int i = tid; i < TM * g.n_tab; i += NT) {
+            int r = i / g.n_tab, t = i - r * g.n_tab;
+            long long idx = 0;
+            if (r < rows_valid) {
+                idx = g.x_cat[(row0 + r) * g.n_tab + t];
+                if (idx < 0 || idx >= g.tab_rows[t]) {
+                    if (err) atomicOr(err, CFM_FLAG_INDEX_OOB);
+                    idx = 0;
+                }
+            }
+            sm_idx[i] = (int)idx;
+        }
+        __syncthreads();
+        if ((g.E & 3) == 0) {
+            const int E4 = g.E >> 2;
+            const int items = TM * g.n_tab * E4;
+            for (int i = tid; i < items; i += NT) {
+                int q = i % E4;
+                int rt = i / E4;
+                int t = rt % g.n_tab, r = rt / g.n_tab;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r < rows_valid)
+                    v = __ldg(reinterpret_cast<const float4*>(g.tab[t] + (size_t)sm_idx[rt] * g.E) + q);
+                *reinterpret_cast<float4*>(As + r * lda + t * g.E + 4 * q) = v;
+            }
+        } else {
+            const int items = TM * KE;
+            for (int i = tid; i < items; i += NT) {
+                int e = i % g.E;
+                int rt = i / g.E;
+                int t = rt % g.n_tab, r = rt / g.n_tab;
+                float v = 0.f;
+                if (r < rows_valid) v = __ldg(g.tab[t] + (size_t)sm_idx[rt] * g.E + e);
+                As[r * lda + t * g.E + e] = v;
+            }
+        }
+        for (int i = tid; i < TM * g.n_num; i += NT) {
+            int r = i / g.n_num, j = i - r * g.n_num;
+            As[r * lda + KE + j] = r < rows_valid ? g.x_num[(row0 + r) * g.n_num + j] : 0.f;
+        }
+    } else {
+        const ActSrc& a = in.a;
+        const int K4 = (K + 3) >> 2, Kp = K4 << 2;
+        const bool vec = (K & 3) == 0;
+        for (int i = tid; i < TM * K4; i += NT) {
+            int r = i / K4, c4 = i - r * K4;
+            const bool valid = r < rows_valid;
+            float v[4] = {0.f, 0.f, 0.f, 0.f}, xh[4] = {0.f, 0.f, 0.f, 0.f};
+            if (valid) {
+                const float* hp = a.h + (size_t)(row0 + r) * K + 4 * c4;
+                if (vec) {
+                    float4 t4 = *reinterpret_cast<const float4*>(hp);
+                    v[0] = t4.x; v[1] = t4.y; v[2] = t4.z; v[3] = t4.w;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (4 * c4 + e < K) v[e] = hp[e];
+                }
+                Philox4 w = {0, 0, 0, 0};
+                if (a.drop.active) w = drop_words(a.drop, row0 + r, c4);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    int c = 4 * c4 + e;
+                    if (c < K) {
+                        float t = v[e];
+                        if (a.bn_mode) {
+                            xh[e] = (t - sm_bn[c]) * sm_bn[Kp + c];
+                            t = xh[e] * sm_bn[2 * Kp + c] + sm_bn[3 * Kp + c];
+                        }
+                        t = fmaxf(t, 0.f);
+                        if (a.drop.active) t = drop_keep(a.drop, w, e) ? t * a.drop.inv_keep : 0.f;
+                        v[e] = t;
+                    } else {
+                        v[e] = 0.f;
+                    }
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                int c = 4 * c4 + e;
+                if (c < K) {
+                    As[r * lda + c] = v[e];
+                    if (Xh) Xh[r * ldxh + c] = xh[e];
+                }
+            }
+        }
+    }
+    // ones column (folds the bias / bias gradient into the GEMMs) and zero padding
+    for (int i = tid; i < TM * (lda - K); i += NT) {
+        int r = i / (lda - K), c = K + (i - r * (lda - K));
+        As[r * lda + c] = (c == K && r < rows_valid) ? 1.f : 0.f;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// register-tiled GEMMs on shared-memory operands
+// ------------------------------------------------------------------------------------------
+// acc[i][j] = sum_k X[rg + i*NRG][k] * W[pass*4*NCG + cg + j*NCG][k], k over 4*k4n columns
+template <int RM>
+__device__ __forceinline__ void gemm_rows(const float* __restrict__ Xs, int ldx, const float* __restrict__ Ws,
+                                          int ldw, int k4n, int rg, int cg, int NRG, int NCG, int pass,
+                                          float (&acc)[RM][4]) {
+#pragma unroll
+    for (int i = 0; i < RM; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    const float4* xp = reinterpret_cast<const float4*>(Xs + rg * ldx);
+    const float4* wp = reinterpret_cast<const float4*>(Ws + (pass * 4 * NCG + cg) * ldw);
+    const int xs = NRG * (ldx >> 2), ws = NCG * (ldw >> 2);
+#pragma unroll 2
+    for (int k = 0; k < k4n; ++k) {
+        float4 w[4], x[RM];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) w[j] = wp[j * ws + k];
+#pragma unroll
+        for (int i = 0; i < RM; ++i) x[i] = xp[i * xs + k];
+#pragma unroll
+        for (int i = 0; i < RM; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                acc[i][j] = fmaf(x[i].x, w[j].x, acc[i][j]);
+                acc[i][j] = fmaf(x[i].y, w[j].y, acc[i][j]);
+                acc[i][j] = fmaf(x[i].z, w[j].z, acc[i][j]);
+                acc[i][j] = fmaf(x[i].w, w[j].w, acc[i][j]);
+            }
+    }
+}
+
+// dW accumulators: acc[a][b][e][f] += sum_r G[r][4*(ng+a*NG)+e] * A[r][4*(kg+b*KG)+f]
+template <int RN4, int RK4>
+__device__ __forceinline__ void dw_accum(const float* __restrict__ Gs, int ldg, const float* __restrict__ As, int lda,
+                                         const int (&gi)[RN4], const int (&ki)[RK4], float (&acc)[RN4][RK4][4][4]) {
+#pragma unroll 4
+    for (int r = 0; r < TM; ++r) {
+        float4 g[RN4], x[RK4];
+#pragma unroll
+        for (int a = 0; a < RN4; ++a) g[a] = *reinterpret_cast<const float4*>(Gs + r * ldg + 4 * gi[a]);
+#pragma unroll
+        for (int b = 0; b < RK4; ++b) x[b] = *reinterpret_cast<const float4*>(As + r * lda + 4 * ki[b]);
+#pragma unroll
+        for (int a = 0; a < RN4; ++a)
+#pragma unroll
+            for (int b = 0; b < RK4; ++b) {
+                const float ge[4] = {g[a].x, g[a].y, g[a].z, g[a].w};
+                const float xf[4] = {x[b].x, x[b].y, x[b].z, x[b].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+#pragma unroll
+                    for (int f = 0; f < 4; ++f) acc[a][b][e][f] = fmaf(ge[e], xf[f], acc[a][b][e][f]);
+            }
+    }
+}
+
+
+struct FwdCtx {
+    const float *As, *Ws;
+    float *red, *tmean, *rmean, *rm2, *hout;
+    int lda, k4n, rg, cg, NRG, NCG, cpp, N;
+    bool active, stats;
+};
+
+// one column pass of a forward tile: GEMM, store raw output, optional (count, mean, M2) statistics
+template <int RM>
+__device__ __forceinline__ void fwd_pass(const FwdCtx& C, int pass, long long row0, int rows_valid, float run_cnt) {
+    const int tid = threadIdx.x;
+    float acc[RM][4];
+    if (C.active) {
+        gemm_rows<RM>(C.As, C.lda, C.Ws, C.lda, C.k4n, C.rg, C.cg, C.NRG, C.NCG, pass, acc);
+#pragma unroll
+        for (int i = 0; i < RM; ++i) {
+            int r = C.rg + i * C.NRG;
+            if (r < rows_valid) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    int c = pass * C.cpp + C.cg + j * C.NCG;
+                    if (c < C.N) C.hout[(size_t)(row0 + r) * C.N + c] = acc[i][j];
+                }
+            }
+        }
+    }
+    if (!C.stats) return;
+    // pass A: tile mean per column
+    if (C.active) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < RM; ++i)
+                if (C.rg + i * C.NRG < rows_valid) s += acc[i][j];
+            C.red[C.rg * C.cpp + C.cg + j * C.NCG] = s;
+        }
+    }
+    __syncthreads();
+    if (tid < C.cpp) {
+        float t = 0.f;
+        for (int g = 0; g < C.NRG; ++g) t += C.red[g * C.cpp + tid];
+        C.tmean[tid] = t / (float)rows_valid;
+    }
+    __syncthreads();
+    // pass B: tile M2 around the tile mean
+    if (C.active) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float m = C.tmean[C.cg + j * C.NCG], s = 0.f;
+#pragma unroll
+            for (int i = 0; i < RM; ++i)
+                if (C.rg + i * C.NRG < rows_valid) { float d = acc[i][j] - m; s = fmaf(d, d, s); }
+            C.red[C.rg * C.cpp + C.cg + j * C.NCG] = s;
+        }
+    }
+    __syncthreads();
+    if (tid < C.cpp) {
+        float m2 = 0.f;
+        for (int g = 0; g < C.NRG; ++g) m2 += C.red[g * C.cpp + tid];
+        // Chan merge of (run_cnt, rmean, rm2) with (rows_valid, tmean, m2)
+        int c = pass * C.cpp + tid;
+        float na = run_cnt, nb = (float)rows_valid, n = na + nb;
+        float d = C.tmean[tid] - C.rmean[c];
+        C.rmean[c] += d * (nb / n);
+        C.rm2[c] += m2 + d * d * (na * nb / n);
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------
+// forward stage kernel
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT, 1) tower_fwd_stage(const __grid_constant__ FwdArgs args) {
+    const FwdStage& S = args.st[blockIdx.y];
+    extern __shared__ float4 smem4[];
+    float* sm = reinterpret_cast<float*>(smem4);
+    const int K = S.in.K, N = S.N;
+    const GemmPlan gp = make_plan(N);
+    const FwdSmem L = fwd_smem(K, N, S.in.g.n_tab, gp);
+    float *Ws = sm + L.ws, *As = sm + L.as, *sm_bn = sm + L.bn, *red = sm + L.red, *tmean = sm + L.tmean;
+    float *rmean = sm + L.rmean, *rm2 = sm + L.rm2;
+    int* sm_idx = reinterpret_cast<int*>(sm + L.idx);
+    const int tid = threadIdx.x, lda = L.lda;
+    const int KE = S.in.g.n_tab * S.in.g.E;
+    const bool stats = S.stat_part != nullptr;
+
+    // weights -> smem, [wrows][lda] with bias in column K and zeros elsewhere in the padding
+    for (int i = tid; i < gp.wrows * lda; i += NT) {
+        int n = i / lda, c = i - n * lda;
+        float v = 0.f;
+        if (n < N) {
+            if (c < K) v = S.W[(size_t)n * K + (S.in.stage == 1 ? gcol_stage1(c, KE, S.in.g.n_num) : c)];
+            else if (c == K) v = S.bias[n];
+        }
+        Ws[i] = v;
+    }
+    if (S.in.stage > 1) stage_bn_params(S.in.a, K, sm_bn);
+    for (int i = tid; i < gp.wrows; i += NT) { rmean[i] = 0.f; rm2[i] = 0.f; }
+    float run_cnt = 0.f;   // identical in every thread
+    __syncthreads();
+
+    const int cg = tid % gp.NCG, rg = tid / gp.NCG;
+    const bool active = rg < gp.NRG;
+    const int k4n = (K + 1 + 3) >> 2;
+    const int cpp = 4 * gp.NCG;   // columns per pass
+    const long long ntiles = (args.B + TM - 1) / TM;
+    FwdCtx C;
+    C.As = As; C.Ws = Ws; C.red = red; C.tmean = tmean; C.rmean = rmean; C.rm2 = rm2; C.hout = S.hout;
+    C.lda = lda; C.k4n = k4n; C.rg = rg; C.cg = cg; C.NRG = gp.NRG; C.NCG = gp.NCG; C.cpp = cpp; C.N = N;
+    C.active = active; C.stats = stats;
+
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long row0 = tile * TM;
+        const int rows_valid = (int)min((long long)TM, args.B - row0);
+        build_input_tile(S.in, row0, rows_valid, As, lda, nullptr, 0, sm_bn, sm_idx, args.err);
+        __syncthreads();
+        for (int pass = 0; pass < gp.passes; ++pass) {
+            switch (gp.RM) {
+                case 1: fwd_pass<1>(C, pass, row0, rows_valid, run_cnt); break;
+                case 2: fwd_pass<2>(C, pass, row0, rows_valid, run_cnt); break;
+                case 4: fwd_pass<4>(C, pass, row0, rows_valid, run_cnt); break;
+                default: fwd_pass<8>(C, pass, row0, rows_valid, run_cnt); break;
+            }
+        }
+        run_cnt += (float)rows_valid;
+        __syncthreads();   // As is rebuilt next iteration
+    }
+    if (stats) {
+        float* P = S.stat_part + (size_t)blockIdx.x * (2 * N + 4);
+        for (int c = tid; c < N; c += NT) { P[c] = rmean[c]; P[N + c] = rm2[c]; }
+        if (tid == 0) P[2 * N] = run_cnt;
+    }
+}
+
+// merge per-CTA (count, mean, M2) partials in CTA order; write batch mean / istd, update running stats
+struct BnFwdFin {
+    const float* part; int nparts; int N;
+    float* stat;            // [4,N]: mean, istd, (c1, c2 written by the backward finalize)
+    float *rm, *rv; long long* nbt;
+};
+struct BnFwdFinArgs { BnFwdFin t[2]; };
+__global__ void bn_fwd_finalize(const __grid_constant__ BnFwdFinArgs args) {
+    const BnFwdFin& F = args.t[blockIdx.y];
+    const int N = F.N;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < N; c += gridDim.x * blockDim.x) {
+        float n = 0.f, mean = 0.f, m2 = 0.f;
+        for (int p = 0; p < F.nparts; ++p) {
+            const float* P = F.part + (size_t)p * (2 * N + 4);
+            float nb = P[2 * N];
+            if (nb <= 0.f) continue;
+            float d = P[c] - mean, nn = n + nb;
+            mean += d * (nb / nn);
+            m2 += P[N + c] + d * d * (n * nb / nn);
+            n = nn;
+        }
+        float var_b = m2 / n;
+        F.stat[c] = mean;
+        F.stat[N + c] = rsqrtf(var_b + BN_EPS);
+        if (F.rm) {
+            float var_u = n > 1.f ? m2 / (n - 1.f) : var_b;
+            F.rm[c] = 0.9f * F.rm[c] + 0.1f * mean;       // momentum 0.1 (nn.BatchNorm1d default)
+            F.rv[c] = 0.9f * F.rv[c] + 0.1f * var_u;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && F.nbt) *F.nbt += 1;
+}
+
+struct BwdCtx {
+    const float *As, *Gs, *Wt, *Xh;
+    float *red, *rs;
+    int lda, ldg, ldxh, n4n, rg, cg, NRG, NCG, cpp, wrows, K, KE, n_num;
+    float inv_keep;
+    bool active, stage1;
+};
+
+// one column pass of the dX GEMM of a backward tile (+ ReLU/dropout mask, BN-backward sums)
+template <int RM>
+__device__ __forceinline__ void bwd_dx_pass(const BwdStage& S, const BwdCtx& C, int pass, long long row0, int rows_valid) {
+    const int tid = threadIdx.x;
+    float acc[RM][4];
+    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+    if (C.active) {
+        gemm_rows<RM>(C.Gs, C.ldg, C.Wt, C.ldg, C.n4n, C.rg, C.cg, C.NRG, C.NCG, pass, acc);
+#pragma unroll
+        for (int i = 0; i < RM; ++i) {
+            int r = C.rg + i * C.NRG;
+            if (r < rows_valid) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    int c = pass * C.cpp + C.cg + j * C.NCG;
+                    if (c < C.K) {
+                        if (C.stage1) {
+                            if (c < C.KE) { if (S.dx_emb) S.dx_emb[(size_t)(row0 + r) * C.KE + c] = acc[i][j]; }
+                            else if (S.dx_num) S.dx_num[(size_t)(row0 + r) * C.n_num + (c - C.KE)] = acc[i][j];
+                        } else {
+                            float dy = C.As[r * C.lda + c] > 0.f ? acc[i][j] * C.inv_keep : 0.f;
+                            S.dy_out[(size_t)(row0 + r) * C.K + c] = dy;
+                            if (S.a_bn) { s1[j] += dy; s2[j] = fmaf(dy, C.Xh[r * C.ldxh + c], s2[j]); }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (!S.a_bn) return;
+    const int half = C.NRG * C.cpp;
+    if (C.active) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            C.red[C.rg * C.cpp + C.cg + j * C.NCG] = s1[j];
+            C.red[half + C.rg * C.cpp + C.cg + j * C.NCG] = s2[j];
+        }
+    }
+    __syncthreads();
+    if (tid < 2 * C.cpp) {
+        int which = tid / C.cpp, cl = tid - which * C.cpp;
+        float t = 0.f;
+        for (int g = 0; g < C.NRG; ++g) t += C.red[which * half + g * C.cpp + cl];
+        C.rs[which * C.wrows + pass * C.cpp + cl] += t;
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------
+// backward stage kernel
+// ------------------------------------------------------------------------------------------
+template <int RN4, int RK4>
+__device__ void bwd_stage_body(const BwdStage& S, long long B, float* sm) {
+    const int K = S.in.K, N = S.N;
+    const GemmPlan gx = make_plan(K);   // dX: [TM, K] output, reduction over N
+    const BwdSmem L = bwd_smem(K, N, S.in.g.n_tab, S.a_bn, S.need_dx, gx);
+    float *Wt = sm + L.wt, *As = sm + L.as, *Gs = sm + L.gs, *Xh = S.a_bn ? sm + L.xh : nullptr;
+    float *sm_bna = sm + L.bna, *sm_bng = sm + L.bng, *red = sm + L.red, *rs = sm + L.rs;
+    int* sm_idx = reinterpret_cast<int*>(sm + L.idx);
+    const int tid = threadIdx.x, lda = L.lda, ldg = L.ldg, ldxh = L.ldxh;
+    const int KE = S.in.g.n_tab * S.in.g.E, n_num = S.in.g.n_num;
+    const int Np = (N + 3) & ~3;
+    const bool stage1 = S.in.stage == 1;
+
+    // W^T -> smem: Wt[k'][n] (k' in tile column order), zero padded
+    if (S.need_dx) {
+        for (int i = tid; i < gx.wrows * ldg; i += NT) {
+            int k = i / ldg, n = i - k * ldg;
+            float v = 0.f;
+            if (k < K && n < N) v = S.W[(size_t)n * K + (stage1 ? gcol_stage1(k, KE, n_num) : k)];
+            Wt[i] = v;
+        }
+    }
+    if (!stage1) stage_bn_params(S.in.a, K, sm_bna);
+    if (S.g_mode) {
+        for (int c = tid; c < N; c += NT) {
+            float s = S.g_var_or_istd[c];
+            float istd = S.g_mode == 2 ? rsqrtf(s + BN_EPS) : s;
+            sm_bng[c] = S.g_mean[c];
+            sm_bng[Np + c] = istd;
+            sm_bng[2 * Np + c] = S.g_gamma[c] * istd;
+            sm_bng[3 * Np + c] = S.g_mode == 1 ? S.g_c1[c] : 0.f;
+            sm_bng[4 * Np + c] = S.g_mode == 1 ? S.g_c2[c] : 0.f;
+        }
+    }
+    for (int i = tid; i < 2 * gx.wrows; i += NT) rs[i] = 0.f;
+
+    // dW thread layout
+    const int N4 = (N + 3) >> 2, K4 = (K + 1 + 3) >> 2;
+    const int NG = ceil_div(N4, RN4), KG = ceil_div(K4, RK4);
+    const int kg = tid % KG, ng = tid / KG;
+    const bool dw_active = ng < NG;
+    int gi[RN4], ki[RK4];
+#pragma unroll
+    for (int a = 0; a < RN4; ++a) gi[a] = min(ng + a * NG, N4 - 1);
+#pragma unroll
+    for (int b = 0; b < RK4; ++b) ki[b] = min(kg + b * KG, K4 - 1);
+    float dw[RN4][RK4][4][4];
+#pragma unroll
+    for (int a = 0; a < RN4; ++a)
+#pragma unroll
+        for (int b = 0; b < RK4; ++b)
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+#pragma unroll
+                for (int f = 0; f < 4; ++f) dw[a][b][e][f] = 0.f;
+
+    // dX thread layout
+    const int cg = tid % gx.NCG, rg = tid / gx.NCG;
+    const bool dx_active = rg < gx.NRG;
+    const int n4n = (N + 3) >> 2;
+    const int cpp = 4 * gx.NCG;
+    const float inv_keep = (!stage1 && S.in.a.drop.active) ? S.in.a.drop.inv_keep : 1.f;
+    BwdCtx C;
+    C.As = As; C.Gs = Gs; C.Wt = Wt; C.Xh = Xh; C.red = red; C.rs = rs;
+    C.lda = lda; C.ldg = ldg; C.ldxh = ldxh; C.n4n = n4n; C.rg = rg; C.cg = cg; C.NRG = gx.NRG; C.NCG = gx.NCG;
+    C.cpp = cpp; C.wrows = gx.wrows; C.K = K; C.KE = KE; C.n_num = n_num; C.inv_keep = inv_keep;
+    C.active = dx_active; C.stage1 = stage1;
+    __syncthreads();
+
+    const long long ntiles = (B + TM - 1) / TM;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long row0 = tile * TM;
+        const int rows_valid = (int)min((long long)TM, B - row0);
+        build_input_tile(S.in, row0, rows_valid, As, lda, Xh, ldxh, sm_bna, sm_idx, nullptr);
+        // incoming-gradient tile G [TM, N] (zero padded to ldg)
+        for (int i = tid; i < TM * (ldg >> 2); i += NT) {
+            int r = i / (ldg >> 2), c4 = i - r * (ldg >> 2);
+            float g[4] = {0.f, 0.f, 0.f, 0.f};
+            if (r < rows_valid) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    int c = 4 * c4 + e;
+                    if (c < N) {
+                        float dy = S.gin[(size_t)(row0 + r) * N + c];
+                        if (S.g_mode == 1) {
+                            float xh = (S.hs[(size_t)(row0 + r) * N + c] - sm_bng[c]) * sm_bng[Np + c];
+                            dy = sm_bng[2 * Np + c] * (dy - sm_bng[3 * Np + c] - xh * sm_bng[4 * Np + c]);
+                        } else if (S.g_mode == 2) {
+                            dy *= sm_bng[2 * Np + c];
+                        }
+                        g[e] = dy;
+                    }
+                }
+            }
+            *reinterpret_cast<float4*>(Gs + r * ldg + 4 * c4) = make_float4(g[0], g[1], g[2], g[3]);
+        }
+        __syncthreads();
+
+        if (dw_active) dw_accum<RN4, RK4>(Gs, ldg, As, lda, gi, ki, dw);
+
+        if (S.need_dx) {
+            for (int pass = 0; pass < gx.passes; ++pass) {
+                switch (gx.RM) {
+                    case 1: bwd_dx_pass<1>(S, C, pass, row0, rows_valid); break;
+                    case 2: bwd_dx_pass<2>(S, C, pass, row0, rows_valid); break;
+                    case 4: bwd_dx_pass<4>(S, C, pass, row0, rows_valid); break;
+                    default: bwd_dx_pass<8>(S, C, pass, row0, rows_valid); break;
+                }
+            }
+        }
+        __syncthreads();   // tiles are rebuilt next iteration
+    }
+
+    // per-CTA partial outputs
+    if (dw_active) {
+        float* P = S.dW_part + (size_t)blockIdx.x * N * (K + 1);
+#pragma unroll
+        for (int a = 0; a < RN4; ++a) {
+            if (ng + a * NG >= N4) continue;
+#pragma unroll
+            for (int b = 0; b < RK4; ++b) {
+                if (kg + b * KG >= K4) continue;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    int n = 4 * (ng + a * NG) + e;
+                    if (n >= N) continue;
+#pragma unroll
+                    for (int f = 0; f < 4; ++f) {
+                        int k = 4 * (kg + b * KG) + f;
+                        if (k > K) continue;
+                        int kgl = (k < K && stage1) ? gcol_stage1(k, KE, n_num) : k;
+                        P[(size_t)n * (K + 1) + kgl] = dw[a][b][e][f];
+                    }
+                }
+            }
+        }
+    }
+    if (S.a_bn && S.need_dx) {
+        float* P = S.sum_part + (size_t)blockIdx.x * 2 * K;
+        for (int c = tid; c < K; c += NT) { P[c] = rs[c]; P[K + c] = rs[gx.wrows + c]; }
+    }
+}
+
+template <int RN4, int RK4>
+__global__ void __launch_bounds__(NT, 1) tower_bwd_stage(const __grid_constant__ BwdArgs args) {
+    extern __shared__ float4 smem4[];
+    bwd_stage_body<RN4, RK4>(args.st[blockIdx.y], args.B, reinterpret_cast<float*>(smem4));
+}
+
+// dW[n][k] = sum over CTA partials (fixed order), bias gradient from the extra column
+struct ReduceW { const float* part; int nparts; int N, K; float* dW; float* db; };
+struct ReduceWArgs { ReduceW t[2]; };
+__global__ void reduce_dw(const __grid_constant__ ReduceWArgs args) {
+    const ReduceW& R = args.t[blockIdx.y];
+    const int stride = R.N * (R.K + 1);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < stride; i += gridDim.x * blockDim.x) {
+        float s = 0.f;
+        for (int p = 0; p < R.nparts; ++p) s += R.part[(size_t)p * stride + i];
+        int n = i / (R.K + 1), k = i - n * (R.K + 1);
+        if (k < R.K) R.dW[(size_t)n * R.K + k] = s;
+        else if (R.db) R.db[n] = s;
+    }
+}
+
+// sums of dy and dy*xhat over the batch -> BN affine grads and the (c1, c2) coefficients of the BN backward
+struct BnBwdFin { const float* part; int nparts; int K; float B; float* dgamma; float* dbeta; float* stat; };
+struct BnBwdFinArgs { BnBwdFin t[2]; };
+__global__ void bn_bwd_finalize(const __grid_constant__ BnBwdFinArgs args) {
+    const BnBwdFin& F = args.t[blockIdx.y];
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < F.K; c += gridDim.x * blockDim.x) {
+        float s1 = 0.f, s2 = 0.f;
+        for (int p = 0; p < F.nparts; ++p) {
+            s1 += F.part[(size_t)p * 2 * F.K + c];
+            s2 += F.part[(size_t)p * 2 * F.K + F.K + c];
+        }
+        if (F.dbeta) F.dbeta[c] = s1;
+        if (F.dgamma) F.dgamma[c] = s2;
+        F.stat[2 * F.K + c] = s1 / F.B;
+        F.stat[3 * F.K + c] = s2 / F.B;
+    }
+}
+
+__global__ void dropout_mask_kernel(uint8_t* mask, long long B, int width, DropCtx d) {
+    const int W4 = (width + 3) >> 2;
+    long long total = B * W4;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long r = i / W4;
+        int c4 = (int)(i - r * W4);
+        Philox4 w = drop_words(d, r, c4);
+        for (int e = 0; e < 4; ++e) {
+            int c = 4 * c4 + e;
+            if (c < width) mask[r * width + c] = d.active ? (drop_keep(d, w, e) ? 1 : 0) : 1;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static int validate_tower(const cfm_tower_t& t) {
+    CFM_REQUIRE(t.n_tables >= 0 && t.n_tables <= CFM_MAX_TABLES, CFM_ERR_INVALID, "n_tables %lld outside [0,%d]",
+                (long long)t.n_tables, CFM_MAX_TABLES);
+    CFM_REQUIRE(t.n_num >= 0 && t.emb_dim >= 0 && t.h1 > 0 && t.h2 > 0 && t.d_out > 0, CFM_ERR_INVALID,
+                "bad tower dims");
+    CFM_REQUIRE(t.n_num + t.n_tables * t.emb_dim > 0, CFM_ERR_INVALID, "tower has no inputs");
+    CFM_REQUIRE(t.w1 && t.b1 && t.w2 && t.b2 && t.w3 && t.b3 && t.bn1_w && t.bn1_b && t.bn1_rm && t.bn1_rv,
+                CFM_ERR_INVALID, "null tower parameter");
+    CFM_REQUIRE(!t.bn2 || (t.bn2_w && t.bn2_b && t.bn2_rm && t.bn2_rv), CFM_ERR_INVALID, "null bn2 parameter");
+    CFM_REQUIRE(t.h1_raw && t.h2_raw && t.out && t.bn1_stat && t.scratch, CFM_ERR_INVALID, "null tower workspace");
+    CFM_REQUIRE(!t.bn2 || t.bn2_stat, CFM_ERR_INVALID, "null bn2_stat");
+    CFM_REQUIRE(t.drop1 >= 0 && t.drop1 < 1 && t.drop2 >= 0 && t.drop2 < 1, CFM_ERR_INVALID, "dropout p outside [0,1)");
+    for (int i = 0; i < t.n_tables; ++i)
+        CFM_REQUIRE(t.tables[i] && ((uintptr_t)t.tables[i] & 15) == 0, CFM_ERR_INVALID,
+                    "table %d null or not 16-byte aligned", i);
+    return CFM_OK;
+}
+
+static void fill_gather(GatherSrc& g, const cfm_tower_t& t) {
+    g.n_num = (int)t.n_num; g.n_tab = (int)t.n_tables; g.E = (int)t.emb_dim;
+    g.x_num = t.x_num; g.x_cat = (const long long*)t.x_cat;
+    for (int i = 0; i < CFM_MAX_TABLES; ++i) {
+        g.tab[i] = i < t.n_tables ? t.tables[i] : nullptr;
+        g.tab_rows[i] = i < t.n_tables ? t.table_rows[i] : 0;
+    }
+}
+
+// input description of stage s (1..3) of tower t
+static InputDesc input_desc(const cfm_tower_t& t, int s, bool training, uint64_t seed, uint64_t offset) {
+    InputDesc in{};
+    in.stage = s;
+    fill_gather(in.g, t);
+    if (s == 1) {
+        in.K = (int)(t.n_num + t.n_tables * t.emb_dim);
+        in.a.drop = make_drop(0.0, false, 0, 0, 0, 0);
+    } else if (s == 2) {
+        in.K = (int)t.h1;
+        in.a.h = t.h1_raw;
+        in.a.bn_mode = training ? 1 : 2;
+        in.a.mean = training ? t.bn1_stat : t.bn1_rm;
+        in.a.var_or_istd = training ? t.bn1_stat + t.h1 : t.bn1_rv;
+        in.a.gamma = t.bn1_w; in.a.beta = t.bn1_b;
+        in.a.drop = make_drop(t.drop1, training, seed, offset, t.tower_id, 0);
+    } else {
+        in.K = (int)t.h2;
+        in.a.h = t.h2_raw;
+        in.a.bn_mode = t.bn2 ? (training ? 1 : 2) : 0;
+        if (t.bn2) {
+            in.a.mean = training ? t.bn2_stat : t.bn2_rm;
+            in.a.var_or_istd = training ? t.bn2_stat + t.h2 : t.bn2_rv;
+            in.a.gamma = t.bn2_w; in.a.beta = t.bn2_b;
+        }
+        in.a.drop = make_drop(t.drop2, training, seed, offset, t.tower_id, 1);
+    }
+    return in;
+}
+
+static int stage_N(const cfm_tower_t& t, int s) { return (int)(s == 1 ? t.h1 : s == 2 ? t.h2 : t.d_out); }
+static int stage_K(const cfm_tower_t& t, int s) {
+    return (int)(s == 1 ? t.n_num + t.n_tables * t.emb_dim : s == 2 ? t.h1 : t.h2);
+}
+
+static int tower_ctas() { return sm_count(); }
+
+static size_t fwd_smem_bytes(const cfm_tower_t& t, int s) {
+    GemmPlan gp = make_plan(stage_N(t, s));
+    return (size_t)fwd_smem(stage_K(t, s), stage_N(t, s), (int)t.n_tables, gp).total_floats * 4;
+}
+static size_t bwd_smem_bytes(const cfm_tower_t& t, int s, int a_bn, int need_dx) {
+    GemmPlan gx = make_plan(stage_K(t, s));
+    return (size_t)bwd_smem(stage_K(t, s), stage_N(t, s), (int)t.n_tables, a_bn, need_dx, gx).total_floats * 4;
+}
+
+}  // namespace cfm
+
+using namespace cfm;
+
+extern "C" int64_t cfm_tower_scratch_floats(const cfm_tower_t* t) {
+    int64_t m = 0, d = 0;
+    for (int s = 1; s <= 3; ++s) {
+        int64_t n = stage_N(*t, s), k = stage_K(*t, s);
+        m = n * (k + 1) > m ? n * (k + 1) : m;
+        d = n > d ? n : d;
+        d = k > d ? k : d;
+    }
+    return m + 4 * d + 16;
+}
+
+extern "C" int cfm_towers_fwd(const cfm_tower_t* towers, int64_t n_towers, int64_t B, int64_t training,
+                              uint64_t seed, uint64_t offset, int32_t* err_flag, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CFM_REQUIRE(towers && n_towers >= 1 && n_towers <= 2, CFM_ERR_INVALID, "n_towers must be 1 or 2");
+    CFM_REQUIRE(B >= 1, CFM_ERR_INVALID, "B must be >= 1 (got %lld)", (long long)B);
+    CFM_REQUIRE(!(training && B == 1), CFM_ERR_BATCHNORM_B1,
+                "Expected more than 1 value per channel when training (B=1)");
+    for (int i = 0; i < n_towers; ++i) { int rc = validate_tower(towers[i]); if (rc) return rc; }
+    static bool attr_set = false;
+    if (!attr_set) {
+        CFM_CHECK_CUDA(cudaFuncSetAttribute(tower_fwd_stage, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
+        attr_set = true;
+    }
+    const long long ntiles = (B + TM - 1) / TM;
+    const int ctas = (int)std::min<long long>(ntiles, tower_ctas());
+    for (int s = 1; s <= 3; ++s) {
+        FwdArgs a{};
+        a.B = B; a.err = err_flag;
+        size_t smem = 0;
+        bool any_stats = false;
+        for (int i = 0; i < n_towers; ++i) {
+            const cfm_tower_t& t = towers[i];
+            FwdStage& S = a.st[i];
+            S.in = input_desc(t, s, training != 0, seed, offset);
+            S.N = stage_N(t, s);
+            S.W = s == 1 ? t.w1 : s == 2 ? t.w2 : t.w3;
+            S.bias = s == 1 ? t.b1 : s == 2 ? t.b2 : t.b3;
+            S.hout = s == 1 ? t.h1_raw : s == 2 ? t.h2_raw : t.out;
+            bool bn_after = s == 1 || (s == 2 && t.bn2);
+            S.stat_part = (training && bn_after) ? t.scratch : nullptr;
+            any_stats |= S.stat_part != nullptr;
+            size_t need = fwd_smem_bytes(t, s);
+            CFM_REQUIRE(need <= (size_t)MAX_SMEM, CFM_ERR_UNSUPPORTED,
+                        "tower stage %d needs %zu B shared memory (> %d): layer %dx%d too large", s, need, MAX_SMEM,
+                        S.N, S.in.K);
+            smem = std::max(smem, need);
+        }
+        tower_fwd_stage<<<dim3(ctas, (unsigned)n_towers), NT, smem, stream>>>(a);
+        CFM_LAUNCH_CHECK();
+        if (any_stats) {
+            BnFwdFinArgs f{};
+            for (int i = 0; i < n_towers; ++i) {
+                const cfm_tower_t& t = towers[i];
+                bool bn_after = s == 1 || (s == 2 && t.bn2);
+                BnFwdFin& F = f.t[i];
+                F.part = t.scratch; F.nparts = ctas; F.N = bn_after ? stage_N(t, s) : 0;
+                F.stat = s == 1 ? t.bn1_stat : t.bn2_stat;
+                F.rm = s == 1 ? t.bn1_rm : t.bn2_rm;
+                F.rv = s == 1 ? t.bn1_rv : t.bn2_rv;
+                F.nbt = (long long*)(s == 1 ? t.bn1_nbt : t.bn2_nbt);
+                if (!bn_after) F.nbt = nullptr;
+            }
+            bn_fwd_finalize<<<dim3(1, (unsigned)n_towers), 256, 0, stream>>>(f);
+            CFM_LAUNCH_CHECK();
+        }
+    }
+    return CFM_OK;
+}
+
+template <int RN4, int RK4>
+static int launch_bwd(const BwdArgs& a, int ctas, int n_towers, size_t smem, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        CFM_CHECK_CUDA(cudaFuncSetAttribute(tower_bwd_stage<RN4, RK4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            MAX_SMEM));
+        attr_set = true;
+    }
+    tower_bwd_stage<RN4, RK4><<<dim3(ctas, (unsigned)n_towers), NT, smem, stream>>>(a);
+    CFM_LAUNCH_CHECK();
+    return CFM_OK;
+}
+
+extern "C" int cfm_towers_bwd(const cfm_tower_t* towers, const cfm_tower_grads_t* grads, int64_t n_towers, int64_t B,
+                              int64_t training, uint64_t seed, uint64_t offset, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CFM_REQUIRE(towers && grads && n_towers >= 1 && n_towers <= 2, CFM_ERR_INVALID, "n_towers must be 1 or 2");
+    CFM_REQUIRE(B >= 1, CFM_ERR_INVALID, "B must be >= 1");
+    for (int i = 0; i < n_towers; ++i) {
+        int rc = validate_tower(towers[i]);
+        if (rc) return rc;
+        const cfm_tower_grads_t& g = grads[i];
+        CFM_REQUIRE(g.g_out && g.dw1 && g.db1 && g.dw2 && g.db2 && g.dw3 && g.db3 && g.dbn1_w && g.dbn1_b && g.dy1 &&
+                        g.dy2, CFM_ERR_INVALID, "null gradient buffer");
+        CFM_REQUIRE(!towers[i].bn2 || (g.dbn2_w && g.dbn2_b), CFM_ERR_INVALID, "null bn2 gradient buffer");
+    }
+    const long long ntiles = (B + TM - 1) / TM;
+    const int ctas = (int)std::min<long long>(ntiles, tower_ctas());
+    for (int s = 3; s >= 1; --s) {
+        BwdArgs a{};
+        a.B = B;
+        size_t smem = 0;
+        int max_groups = 0;
+        bool any_sums = false;
+        for (int i = 0; i < n_towers; ++i) {
+            const cfm_tower_t& t = towers[i];
+            const cfm_tower_grads_t& g = grads[i];
+            BwdStage& S = a.st[i];
+            S.in = input_desc(t, s, training != 0, seed, offset);
+            S.N = stage_N(t, s);
+            S.W = s == 1 ? t.w1 : s == 2 ? t.w2 : t.w3;
+            S.a_bn = s >= 2 && S.in.a.bn_mode != 0;
+            S.gin = s == 3 ? g.g_out : s == 2 ? g.dy2 : g.dy1;
+            bool bn_s = s == 1 || (s == 2 && t.bn2);
+            S.g_mode = (s < 3 && bn_s) ? (training ? 1 : 2) : 0;
+            if (S.g_mode) {
+                const float* stat = s == 1 ? t.bn1_stat : t.bn2_stat;
+                int h = stage_N(t, s);
+                S.hs = s == 1 ? t.h1_raw : t.h2_raw;
+                S.g_mean = training ? stat : (s == 1 ? t.bn1_rm : t.bn2_rm);
+                S.g_var_or_istd = training ? stat + h : (s == 1 ? t.bn1_rv : t.bn2_rv);
+                S.g_gamma = s == 1 ? t.bn1_w : t.bn2_w;
+                S.g_c1 = stat + 2 * h; S.g_c2 = stat + 3 * h;
+            }
+            S.dW_part = t.scratch;
+            S.dy_out = s == 3 ? g.dy2 : s == 2 ? g.dy1 : nullptr;
+            S.sum_part = t.scratch + (size_t)ctas * S.N * (S.in.K + 1);
+            S.dx_emb = s == 1 ? g.dx_emb : nullptr;
+            S.dx_num = s == 1 ? g.dx_num : nullptr;
+            S.need_dx = s > 1 || g.dx_emb || g.dx_num;
+            any_sums |= S.a_bn != 0;
+            size_t need = bwd_smem_bytes(t, s, S.a_bn, S.need_dx);
+            CFM_REQUIRE(need <= (size_t)MAX_SMEM, CFM_ERR_UNSUPPORTED,
+                        "tower bwd stage %d needs %zu B shared memory (> %d)", s, need, MAX_SMEM);
+            smem = std::max(smem, need);
+            int groups = ceil_div(S.N, 4) * ceil_div(S.in.K + 1, 4);
+            max_groups = std::max(max_groups, groups);
+        }
+        // scratch must hold ctas * (N*(K+1) + 2K) floats: guaranteed by cfm_tower_scratch_floats
+        int rc;
+        auto fits = [&](int rn4, int rk4) {
+            for (int i = 0; i < n_towers; ++i) {
+                const BwdStage& S = a.st[i];
+                if (ceil_div(ceil_div(S.N, 4), rn4) * ceil_div(ceil_div(S.in.K + 1, 4), rk4) > NT) return false;
+            }
+            return true;
+        };
+        if (fits(1, 1)) rc = launch_bwd<1, 1>(a, ctas, (int)n_towers, smem, stream);
+        else if (fits(1, 2)) rc = launch_bwd<1, 2>(a, ctas, (int)n_towers, smem, stream);
+        else if (fits(2, 2)) rc = launch_bwd<2, 2>(a, ctas, (int)n_towers, smem, stream);
+        else {
+            set_error("tower bwd stage %d: layer too large for the register-tiled dW (N*(K+1) > 16384)", s);
+            return CFM_ERR_UNSUPPORTED;
+        }
+        if (rc) return rc;
+        (void)max_groups;
+        // fixed-order reductions of the per-CTA partials
+        ReduceWArgs r{};
+        for (int i = 0; i < n_towers; ++i) {
+            const cfm_tower_t& t = towers[i];
+            const cfm_tower_grads_t& g = grads[i];
+            ReduceW& R = r.t[i];
+            R.part = t.scratch; R.nparts = ctas; R.N = a.st[i].N; R.K = a.st[i].in.K;
+            R.dW = s == 1 ? g.dw1 : s == 2 ? g.dw2 : g.dw3;
+            R.db = s == 1 ? g.db1 : s == 2 ? g.db2 : g.db3;
+        }
+        reduce_dw<<<dim3(32, (unsigned)n_towers), 256, 0, stream>>>(r);
+        CFM_LAUNCH_CHECK();
+        if (any_sums) {
+            BnBwdFinArgs f{};
+            for (int i = 0; i < n_towers; ++i) {
+                const cfm_tower_t& t = towers[i];
+                const cfm_tower_grads_t& g = grads[i];
+                const BwdStage& S = a.st[i];
+                BnBwdFin& F = f.t[i];
+                F.part = S.sum_part; F.nparts = ctas; F.K = S.a_bn ? S.in.K : 0; F.B = (float)B;
+                F.dgamma = s == 3 ? g.dbn2_w : g.dbn1_w;
+                F.dbeta = s == 3 ? g.dbn2_b : g.dbn1_b;
+                F.stat = s == 3 ? t.bn2_stat : t.bn1_stat;
+            }
+            bn_bwd_finalize<<<dim3(1, (unsigned)n_towers), 256, 0, stream>>>(f);
+            CFM_LAUNCH_CHECK();
+        }
+    }
+    return CFM_OK;
+}
+
+extern "C" int cfm_dropout_mask(uint8_t* mask, int64_t B, int64_t width, double p, int64_t tower_id, int64_t site,
+                                uint64_t seed, uint64_t offset, void* stream_) {
+    CFM_REQUIRE(mask && B >= 0 && width > 0, CFM_ERR_INVALID, "bad dropout mask arguments");
+    if (B == 0) return CFM_OK;
+    DropCtx d = make_drop(p, true, seed, offset, tower_id, (int)site);
+    dropout_mask_kernel<<<std::min<long long>(1024, (B * ((width + 3) / 4) + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(
+        mask, B, (int)width, d);
+    CFM_LAUNCH_CHECK();
+    return CFM_OK;
+}

@@ -1,0 +1,194 @@
+/*
+ * cfm_b200.h — C ABI of libcfm_b200.so, the B200 (sm_100a) implementation of the
+ * CEO-Recommender two-tower training + scoring hot path.
+ *
+ * The reference (SMaric93/CEO-Recommender) has no FFI of its own: its hot path is a
+ * chain of PyTorch ATen calls.  Each entry point below names the reference call
+ * sequence it replaces (paths relative to the reference repository root).  Every
+ * pointer is a raw DEVICE pointer unless marked host; buffers are owned by the caller
+ * (torch's caching allocator in the shipped Python host); the library never allocates
+ * device memory.  All work is enqueued on `stream` (a cudaStream_t passed as void*)
+ * and nothing synchronises.  Return value: 0 on success, a negative CFM_ERR_* code
+ * otherwise; cfm_last_error() gives the message of the calling thread's last failure.
+ *
+ * Structs use only int64_t / double / pointers so that any FFI (ctypes, cffi, cgo,
+ * JNI) can mirror them field by field without packing rules.
+ */
+#ifndef CFM_B200_H
+#define CFM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CFM_ABI_VERSION 1
+#define CFM_MAX_TABLES 16
+
+#define CFM_OK 0
+#define CFM_ERR_INVALID (-1)     /* bad dimension / null pointer / misaligned buffer */
+#define CFM_ERR_UNSUPPORTED (-2) /* shape outside what the kernels are built for     */
+#define CFM_ERR_CUDA (-3)        /* a CUDA runtime call failed (message has details) */
+#define CFM_ERR_BATCHNORM_B1 (-4)/* train-mode BatchNorm with a single row (torch raises too) */
+
+/* bits OR-ed by kernels into the caller's device-side `err_flag` word */
+#define CFM_FLAG_INDEX_OOB 1     /* categorical index outside [0, table_rows) — torch raises IndexError */
+#define CFM_FLAG_TOPK_OVERFLOW 2 /* all-pairs candidate list overflowed; row was re-done exactly */
+
+int cfm_abi_version(void);
+const char* cfm_last_error(void);
+/* SM count, compute capability and the number of persistent CTAs the tower kernels launch
+ * per tower (callers size the per-CTA partial buffers with it). */
+int cfm_device_info(int64_t* sm_count, int64_t* cc_major, int64_t* cc_minor, int64_t* tower_ctas);
+
+/* ------------------------------------------------------------------------------------------
+ * Towers.  One tower = categorical embedding gather + numeric concat + 3-layer MLP
+ *   Linear(in,h1) -> BN -> ReLU -> Dropout(p1) -> Linear(h1,h2) -> [BN] -> ReLU -> [Dropout(p2)] -> Linear(h2,d_out)
+ * replaces: ceo_firm_matching/model.py:69-76 (both towers of CEOFirmMatcher, bn2=1) and
+ *           ceo_firm_matching/structural_model.py:120-127 (StructuralDistillationNet, bn2=0).
+ * Layouts are torch's: row-major, Linear weight [out,in], x_num [B,n_num] f32, x_cat [B,n_tables] i64,
+ * table i is [table_rows[i], emb_dim] f32.  Concat order is [x_num | E_0 | E_1 | ...].
+ * ------------------------------------------------------------------------------------------ */
+typedef struct cfm_tower {
+    int64_t n_num, n_tables, emb_dim, h1, h2, d_out;
+    int64_t bn2;                 /* 1: BatchNorm1d after Linear 2 */
+    double drop1, drop2;         /* dropout probability after activation 1 / 2 (0 = none) */
+    int64_t tower_id;            /* distinguishes the dropout streams of the towers in one call */
+    /* inputs */
+    const float* x_num;
+    const int64_t* x_cat;
+    const float* tables[CFM_MAX_TABLES];
+    int64_t table_rows[CFM_MAX_TABLES];
+    /* parameters */
+    const float *w1, *b1, *w2, *b2, *w3, *b3;
+    const float *bn1_w, *bn1_b, *bn2_w, *bn2_b;
+    float *bn1_rm, *bn1_rv, *bn2_rm, *bn2_rv; /* running stats; updated in training mode */
+    int64_t *bn1_nbt, *bn2_nbt;                /* num_batches_tracked; +1 in training mode (nullable) */
+    /* saved activations (written by fwd, read by bwd) */
+    float *h1_raw;               /* [B,h1]  Linear-1 output before BN */
+    float *h2_raw;               /* [B,h2]  Linear-2 output before BN/ReLU */
+    float *out;                  /* [B,d_out] tower output (pre-normalisation latent / logits) */
+    float *bn1_stat, *bn2_stat;  /* [4,h]: batch mean, 1/sqrt(var+eps), and the two BN-backward batch means */
+    float *scratch;              /* per-CTA partials: >= tower_ctas * cfm_tower_scratch_floats() floats */
+} cfm_tower_t;
+
+/* floats of `scratch` needed per persistent CTA for this tower shape (fwd and bwd share it) */
+int64_t cfm_tower_scratch_floats(const cfm_tower_t* t);
+
+/* Forward of `n_towers` towers over the same B rows in one set of launches.
+ * training=1: batch-stat BN (running stats updated), dropout drawn from a counter-based
+ * Philox stream keyed by (seed, offset); training=0: running-stat BN, no dropout. */
+int cfm_towers_fwd(const cfm_tower_t* towers, int64_t n_towers, int64_t B, int64_t training,
+                   uint64_t seed, uint64_t offset, int32_t* err_flag, void* stream);
+
+typedef struct cfm_tower_grads {
+    const float* g_out;          /* [B,d_out] gradient w.r.t. tower output */
+    float *dw1, *db1, *dw2, *db2, *dw3, *db3;   /* parameter gradients (overwritten) */
+    float *dbn1_w, *dbn1_b, *dbn2_w, *dbn2_b;
+    float *dy1, *dy2;            /* scratch [B,h1], [B,h2] */
+    float *dx_emb;               /* [B, n_tables*emb_dim] per-pair embedding-row gradients (nullable) */
+    float *dx_num;               /* [B, n_num] gradient w.r.t. numeric inputs (nullable) */
+} cfm_tower_grads_t;
+
+/* Backward of the towers given the same descriptors (same training flag / seed / offset as fwd).
+ * replaces: the autograd graph torch builds for model.py:69-76 (training.py:54 `loss.backward()`). */
+int cfm_towers_bwd(const cfm_tower_t* towers, const cfm_tower_grads_t* grads, int64_t n_towers, int64_t B,
+                   int64_t training, uint64_t seed, uint64_t offset, void* stream);
+
+/* Keep-mask the towers' dropout uses, materialised for differential tests:
+ * mask[r, c] (uint8) for `site` (0 = after activation 1, 1 = after activation 2). */
+int cfm_dropout_mask(uint8_t* mask, int64_t B, int64_t width, double p, int64_t tower_id, int64_t site,
+                     uint64_t seed, uint64_t offset, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Embedding gradient: deterministic sorted-segment reduce (no atomics).
+ * replaces: aten::embedding_dense_backward for each nn.Embedding of model.py:24-33.
+ * For every table i: grad_table_i[idx] = sum over rows r with x_cat[r,i]==idx of dx_emb[r, i*E:(i+1)*E],
+ * summed in increasing r.  Rows of grad tables not touched are left as they are (caller keeps them zero:
+ * see cfm_emb_grad_rezero).
+ *   keys_tmp/vals_tmp/keys_sorted/vals_sorted: scratch [n_tables*B] (i64 keys, i32 values)
+ *   sort_tmp: sort scratch of sort_tmp_bytes (query with cfm_emb_grad_tmp_bytes)
+ * After the call keys_sorted lists every (table, index) touched (runs of equal keys); handing it to
+ * cfm_emb_grad_rezero before the next step zeroes exactly those rows again, so a persistent dense
+ * gradient buffer stays exact without a full-table memset.
+ * ------------------------------------------------------------------------------------------ */
+int64_t cfm_emb_grad_tmp_bytes(int64_t n_tables, int64_t B);
+int cfm_emb_grad_segment_reduce(const int64_t* x_cat, const float* dx_emb, int64_t B, int64_t n_tables,
+                                int64_t emb_dim, float* const* grad_tables /* host array of device ptrs */,
+                                const int64_t* table_rows /* host */, int64_t* keys_tmp, int32_t* vals_tmp,
+                                int64_t* keys_sorted, int32_t* vals_sorted, void* sort_tmp, int64_t sort_tmp_bytes,
+                                void* stream);
+int cfm_emb_grad_rezero(float* const* grad_tables /* host */, const int64_t* table_rows /* host */, int64_t n_tables,
+                        int64_t emb_dim, const int64_t* keys_sorted, int64_t n_items, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Cosine head: L2-normalise both latents, row-wise dot, times exp(logit_scale).
+ * replaces: model.py:79-87 (eps = 0: plain division) and contrastive.py:64,70,92-93 (eps = 1e-12, F.normalize).
+ * The weighted MSE of training.py:52 can be fused into both directions.
+ * ------------------------------------------------------------------------------------------ */
+/* forward: score [B] (+ unit latents if asked); with target/weights/loss also loss = mean(w (s-t)^2) */
+int cfm_cosine_head_fwd(const float* u, const float* v, const float* logit_scale, int64_t B, int64_t D,
+                        double eps, float* score /* [B] */, float* u_hat /* nullable [B,D] */,
+                        float* v_hat /* nullable [B,D] */, const float* target /* nullable [B] */,
+                        const float* weights /* nullable [B] */, float* loss /* nullable [1] */,
+                        float* partial /* >= 1024 floats, zero on first use; needed with loss */, void* stream);
+/* backward: d_score [B] and/or the weighted-MSE gradient 2 w (s-t) g_loss / B (when target/weights given;
+ * g_loss = device scalar dL/dloss, nullable = 1), plus optional gradients flowing into the unit latents. */
+int cfm_cosine_head_bwd(const float* u, const float* v, const float* logit_scale, const float* d_score /* nullable */,
+                        const float* d_uhat /* nullable [B,D] */, const float* d_vhat /* nullable [B,D] */,
+                        const float* target /* nullable */, const float* weights /* nullable */,
+                        const float* g_loss /* nullable */, int64_t B, int64_t D, double eps, float* du, float* dv,
+                        float* d_logit_scale /* [1] */, float* partial /* >= 1024 floats */, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Structural head: softmax(c_logits) . A . softmax(f_logits) expected match, KL distillation loss and
+ * the gradients w.r.t. both logit sets, one kernel.
+ * replaces: structural_model.py:130-141 + structural_training.py:75-77 (+ autograd of both).
+ *   T == 5 types.  targets nullable (then loss/KL terms are skipped).  d_match nullable (gradient flowing
+ *   into expected_match, e.g. IlluminationEngine structural_explain.py:76-79).  kl_scale = dLoss/d(KL sum),
+ *   the op divides by B itself ('batchmean').
+ * ------------------------------------------------------------------------------------------ */
+int cfm_structural_head(const float* c_logits, const float* f_logits, const float* A /* [5,5] */,
+                        const float* target_ceo, const float* target_firm, const float* d_match,
+                        int64_t B, double kl_scale, float* match /* [B] */, float* loss /* [1] nullable */,
+                        float* d_c_logits /* nullable [B,5] */, float* d_f_logits /* nullable [B,5] */,
+                        float* partial /* >= 1024 floats */, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * InfoNCE (tcgen05/TMEM).  rows/cols are bf16 [R,D] / [C,D] unit vectors (D multiple of 16, <= 256).
+ * replaces: contrastive.py:129-138 (torch.mm + 2x F.cross_entropy) and its autograd.
+ * cfm_infonce_rowsum: out[i] = sum_j exp((x_i . y_j - 1)/T)   (fixed max 1/T, valid for unit vectors)
+ *                     diag[i] = x_i . y_(i + diag_offset)      (fp32 accumulate)  (nullable)
+ * cfm_infonce_grad:   dX[i] = 1/(2 B T) * sum_j E_ij (1/rowsum_x[i] + 1/rowsum_y[j]) y_j - 1/(B T) y_(i+diag_offset)
+ * The symmetric loss and both gradients are two calls each with (X,Y) swapped; S is never written to HBM.
+ * ------------------------------------------------------------------------------------------ */
+int cfm_infonce_rowsum(const void* x_bf16, const void* y_bf16, int64_t R, int64_t C, int64_t D, double temperature,
+                       int64_t diag_offset, float* rowsum, float* diag, void* stream);
+int cfm_infonce_grad(const void* x_bf16, const void* y_bf16, int64_t R, int64_t C, int64_t D, double temperature,
+                     int64_t diag_offset, int64_t B_total, const float* rowsum_x /* [R] */,
+                     const float* rowsum_y /* [C] */, float* dx /* [R,D] f32 */, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * All-pairs scoring with streaming top-k (tcgen05/TMEM filter pass in bf16 + exact fp32 rescoring).
+ * replaces: analytical_extensions.py:471,483 (torch.mm + np.argsort), contrastive.py:307-310 (sim.sort).
+ * rows [R,D] f32, cols [C,D] f32 unit vectors and their bf16 copies [R,Dp]/[C,Dp] (Dp = D padded to 64).
+ * Output per row: the k best columns ordered (score desc, index asc); score = scale * <row, col> in fp32.
+ *   cand_idx/cand_val: scratch [R, CFM_TOPK_CAND]; col_offset is added to emitted indices (column shards).
+ * ------------------------------------------------------------------------------------------ */
+#define CFM_TOPK_CAND 256
+int cfm_allpairs_topk(const float* rows_f32, const float* cols_f32, const void* rows_bf16, const void* cols_bf16,
+                      int64_t R, int64_t C, int64_t D, int64_t Dp, int64_t k, double scale, int64_t col_offset,
+                      float* out_score /* [R,k] */, int64_t* out_idx /* [R,k] */, int32_t* cand_idx,
+                      float* cand_val, int32_t* err_flag, void* stream);
+/* merge `n_parts` per-shard top-k lists [n_parts,R,k] into the global top-k (score desc, index asc) */
+int cfm_topk_merge(const float* part_score, const int64_t* part_idx, int64_t n_parts, int64_t R, int64_t k,
+                   float* out_score, int64_t* out_idx, void* stream);
+/* rank of a given column per row: 1 + #{j : s_ij > s_i,target[i]}  (contrastive.py:312-320) */
+int cfm_allpairs_rank(const float* rows_f32, const float* cols_f32, int64_t R, int64_t C, int64_t D,
+                      const int64_t* target_col /* [R] */, int64_t* rank /* [R] */, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CFM_B200_H */

