@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""Headline benchmark: two-tower training step (fwd + weighted-MSE + bwd) on BASELINE config 4.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+One "step" = one pass of the hot path over one synthetic batch of 65,536 CEO-firm pairs per GPU with
+1M-row categorical embedding tables (4 firm x 48 + 7 CEO x 8 floats), dropout on, dense embedding
+gradients (persistent buffers, rows re-zeroed sparsely).  The optimiser step is NOT part of the metric
+ and is reported separately.  Prints ONE JSON line (see the task contract).
+
+``--impl reference`` times the CPU restatement of the reference (oracle/, torch CPU ops == the reference's
+own ATen path) on the box's host cores for the same config; ``/root/reference`` itself cannot travel.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "ceo-recommender_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+B_PER_GPU = 65_536
+N_PAIRS = 10_000_000
+TABLE_ROWS = 1_000_000
+F_CARDS, C_CARDS = [TABLE_ROWS] * 4, [TABLE_ROWS] * 7
+BYTES_PER_PAIR = 2228          # 1148 fwd + 1080 bwd algorithmic bytes, large-table regime
+BYTES_BWD1_PER_PAIR = 1080     # stage-1 backward kernel: re-read indices (88) + emit embedding-grad rows (992)
+METRIC = "two_tower_train_pairs_per_sec"
+WORKLOAD = "config4: two-tower fwd+loss+bwd, B=65536/GPU, 10M synthetic pairs, 11 tables x 1M rows, fp32"
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            d = json.load(f)
+        return d["hbm_gbs"], "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+# ----------------------------------------------------------------------------------------------
+# synthetic data of config 4's shape
+# ----------------------------------------------------------------------------------------------
+def make_batches(n_batches, B, device, seed):
+    g = torch.Generator(device=device).manual_seed(seed)
+    out = []
+    for _ in range(n_batches):
+        f_num = torch.randn(B, 12, device=device, generator=g)
+        c_num = torch.randn(B, 2, device=device, generator=g)
+        f_cat = torch.randint(0, TABLE_ROWS, (B, 4), device=device, generator=g)
+        c_cat = torch.randint(0, TABLE_ROWS, (B, 7), device=device, generator=g)
+        target = torch.randn(B, 1, device=device, generator=g)
+        sd = torch.rand(B, 1, device=device, generator=g) * 0.9 + 0.1
+        out.append((f_num, f_cat, c_num, c_cat, target, 1.0 / (sd * sd + 1e-6)))
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.12)
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the oracle (torch CPU restatement of the reference) on the host cores
+# ----------------------------------------------------------------------------------------------
+def cpu_step_fn():
+    import oracle
+    torch.set_num_threads(os.cpu_count())
+    p = oracle.init_two_tower_params(12, F_CARDS, 2, C_CARDS, seed=0)
+    names = [k for k, v in p.items() if v.is_floating_point() and "running" not in k]
+    for k in names:
+        p[k].requires_grad_(True)
+    gen = torch.Generator().manual_seed(1234)
+    masks_p = 0.1
+
+    def batch():
+        B = B_PER_GPU
+        return (torch.randn(B, 12, generator=gen), torch.randint(0, TABLE_ROWS, (B, 4), generator=gen),
+                torch.randn(B, 2, generator=gen), torch.randint(0, TABLE_ROWS, (B, 7), generator=gen),
+                torch.randn(B, 1, generator=gen), 1.0 / (torch.rand(B, 1, generator=gen) * 0.9 + 0.1) ** 2)
+
+    data = [batch() for _ in range(2)]
+
+    def step(i):
+        f_num, f_cat, c_num, c_cat, target, weights = data[i % len(data)]
+        for k in names:
+            p[k].grad = None
+        B = f_num.shape[0]
+        masks = {s: [torch.rand(B, w, generator=gen) >= masks_p for w in (64, 32)] for s in ("firm", "ceo")}
+        preds = oracle.two_tower_forward(p, f_num, f_cat, c_num, c_cat, training=True, masks=masks)
+        loss = oracle.weighted_mse(preds, target, weights)
+        loss.backward()
+        return float(loss)
+
+    return step
+
+
+def run_cpu(steps, warmup):
+    step = cpu_step_fn()
+    for i in range(warmup):
+        step(i)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        step(i)
+    dt = time.perf_counter() - t0
+    return B_PER_GPU * steps / dt, dt / steps * 1e3
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    value, ms = run_cpu(args.steps, max(args.warmup, 1))
+    cores = os.cpu_count()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "timing": "host perf_counter, inputs in host memory"},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} steps of one B=65536 batch (fwd+loss+bwd, dense 1M-row table grads), "
+                                   "oracle = torch-CPU restatement of the reference"},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+def build_model(device):
+    from ceo_firm_matching import CEOFirmMatcher, Config
+    torch.manual_seed(0)
+    meta = {"n_firm_numeric": 12, "firm_cat_counts": F_CARDS, "n_ceo_numeric": 2, "ceo_cat_counts": C_CARDS}
+    model = CEOFirmMatcher(meta, Config()).to(device).train()
+    model.use_persistent_table_grads(True)
+    return model
+
+
+def gpu_arm(args):
+    from ceo_firm_matching import _native as N
+    import ctypes as C
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+    lib = N.lib()
+    model = build_model(device)
+    dp = None
+    if world > 1:
+        from ceo_firm_matching.distributed import DataParallelTwoTower
+        dp = DataParallelTwoTower(model)
+
+    n_data = max(8, min(args.steps + args.warmup, N_PAIRS // B_PER_GPU // max(world, 1)))
+    batches = make_batches(n_data, B_PER_GPU, device, seed=1234 + rank)     # ~10 MB each: >> L2 in total
+
+    def step(i):
+        batch = batches[i % n_data]
+        model.zero_grad_fast()
+        loss, _ = model.forward_loss(*batch)
+        loss.backward()
+        if dp is not None:
+            dp.sync_gradients()
+        return loss
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+    lib.cfm_launch_count(1)
+    lib.cfm_profile_enable(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        e0.record()
+        for i in range(args.steps):
+            loss = step(args.warmup + i)
+        e1.record()
+        barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = int(lib.cfm_launch_count(0))
+    prof_ms = (C.c_double * 13)()
+    prof_n = (C.c_int64 * 13)()
+    N.check(lib.cfm_profile_read(prof_ms, prof_n, 13))
+    lib.cfm_profile_enable(0)
+    if dist is not None:
+        tmax = torch.tensor([ms_total], device=device)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms_total = float(tmax.item())
+    ms_step = ms_total / args.steps
+    value = world * B_PER_GPU * args.steps / (ms_total * 1e-3)
+
+    # ---- end-to-end: host (pinned) batches, H2D + step + D2H of the loss inside the timed region ----
+    host = [[t.cpu().pin_memory() for t in b] for b in batches[:4]]
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host[0])
+    copy_stream = torch.cuda.Stream(device)
+    loss_host = torch.zeros(1).pin_memory()
+
+    def upload(i):
+        with torch.cuda.stream(copy_stream):
+            dev_b = [t.to(device, non_blocking=True) for t in host[i % len(host)]]
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return dev_b, ev
+
+    def e2e_loop(n):
+        nxt = upload(0)
+        for i in range(n):
+            dev_b, ev = nxt
+            if i + 1 < n:
+                nxt = upload(i + 1)            # prefetch the next batch while this one computes
+            torch.cuda.current_stream().wait_event(ev)
+            model.zero_grad_fast()
+            loss, _ = model.forward_loss(*dev_b)
+            loss.backward()
+            if dp is not None:
+                dp.sync_gradients()
+            loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+        torch.cuda.synchronize()
+
+    e2e_loop(3)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_loop(args.steps)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        tmax = torch.tensor([e2e_s], device=device)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        e2e_s = float(tmax.item())
+    e2e_value = world * B_PER_GPU * args.steps / e2e_s
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (stage-1 backward: dW1 + dX + embedding-row gradients) ----
+    peak, peak_src = peaks()
+    slots = ["fwd1", "fwd2", "fwd3", "bwd1", "bwd2", "bwd3", "head", "emb_grad", "reduce", "nce_rowsum", "nce_grad",
+             "topk", "topk_post"]
+    per_kernel = {s: (prof_ms[i] / prof_n[i] if prof_n[i] else None) for i, s in enumerate(slots)}
+    shares = {s: round(prof_ms[i] / ms_total, 4) for i, s in enumerate(slots) if prof_n[i]}
+    dom = max((s for s in slots if per_kernel[s]), key=lambda s: prof_ms[slots.index(s)])
+    dom_bytes = {"bwd1": BYTES_BWD1_PER_PAIR, "fwd1": 1148}.get(dom, BYTES_BWD1_PER_PAIR) * B_PER_GPU
+    achieved = dom_bytes / (per_kernel[dom] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "tower_%s_stage" % ("bwd" if dom.startswith("bwd") else "fwd"),
+                "slot": dom, "peak_source": peak_src, "kernel_ms": per_kernel[dom], "kernel_share_of_step": shares,
+                "whole_step_frac": BYTES_PER_PAIR * B_PER_GPU / (ms_step * 1e-3) / 1e9 / peak,
+                "note": "exact-fp32 tower is FMA-issue bound (148 kFLOP/pair), HBM fraction reported as the contract asks"}
+
+    cpu_value, cpu_ms = (None, None)
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        cpu_value, cpu_ms = run_cpu(3, 1)
+        cpu = {"value": cpu_value, "unit": "pairs/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": "3 steps (after 1 warm-up) of one B=65536 batch, fwd+loss+bwd, dense 1M-row table grads"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "global_batch": world * B_PER_GPU,
+                   "parallelism": f"dp{world}" if world > 1 else "single",
+                   "l2": f"{n_data} distinct 10 MB batches cycled + 992 MB tables (inputs >> 126 MB L2)",
+                   "optimizer_step": "excluded from the metric (SURVEY 8d)", "dropout": 0.1},
+        "clocks": clocks.summary(),
+        "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                "note": "pinned host batches, copy stream prefetches batch i+1 during step i, loss read back every step"},
+        "gpu_launches": launches,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (debugging)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

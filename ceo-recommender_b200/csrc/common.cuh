@@ -32,6 +32,7 @@ void set_error(const char* fmt, ...);
 
 #define CFM_LAUNCH_CHECK()                                                                     \
     do {                                                                                       \
+        ::cfm::count_launch();                                                                 \
         cudaError_t _e = cudaGetLastError();                                                   \
         if (_e != cudaSuccess) {                                                               \
             ::cfm::set_error("kernel launch failed at %s:%d: %s", __FILE__, __LINE__,          \
@@ -41,6 +42,19 @@ void set_error(const char* fmt, ...);
     } while (0)
 
 int sm_count();   // cached cudaDevAttrMultiProcessorCount of the current device
+
+// ---- launch accounting + optional per-kernel-family event timing (bench.py's roofline leg) ----
+void count_launch();
+enum ProfSlot {
+    PROF_FWD1 = 0, PROF_FWD2, PROF_FWD3, PROF_BWD1, PROF_BWD2, PROF_BWD3, PROF_HEAD, PROF_EMB, PROF_REDUCE,
+    PROF_NCE_ROWSUM, PROF_NCE_GRAD, PROF_TOPK, PROF_TOPK_POST, PROF_SLOTS
+};
+struct ProfScope {   // records a cudaEvent pair around the launches in its lifetime when profiling is on
+    int idx;
+    cudaStream_t stream;
+    ProfScope(int slot, cudaStream_t s);
+    ~ProfScope();
+};
 
 // ---- device helpers ---------------------------------------------------------------------
 constexpr unsigned FULL = 0xffffffffu;

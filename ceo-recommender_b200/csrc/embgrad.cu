@@ -130,6 +130,7 @@ extern "C" int cfm_emb_grad_segment_reduce(const int64_t* x_cat, const float* dx
     if (rc) return rc;
     const long long n = n_tables * B;
     const int grid = (int)std::min<long long>((n + 255) / 256, 148 * 8);
+    ProfScope prof(PROF_EMB, stream);
     emb_make_keys<<<grid, 256, 0, stream>>>((const long long*)x_cat, B, (int)n_tables, idx_bits,
                                             (unsigned long long*)keys_tmp, vals_tmp, tp);
     CFM_LAUNCH_CHECK();

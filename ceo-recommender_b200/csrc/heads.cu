@@ -141,6 +141,7 @@ __global__ void __launch_bounds__(HEAD_NT) cosine_head_kernel(const CosArgs a) {
 static int launch_cosine(const CosArgs& a, cudaStream_t stream) {
     CFM_REQUIRE(a.B >= 1 && a.D >= 1 && a.D <= 256, CFM_ERR_UNSUPPORTED, "cosine head supports 1 <= D <= 256 (got %d)", a.D);
     int ctas = (int)std::min<long long>((a.B + HEAD_NT / 32 - 1) / (HEAD_NT / 32), HEAD_MAX_CTAS);
+    ProfScope prof(PROF_HEAD, stream);
     if (a.D <= 64) cosine_head_kernel<2><<<ctas, HEAD_NT, 0, stream>>>(a);
     else if (a.D <= 128) cosine_head_kernel<4><<<ctas, HEAD_NT, 0, stream>>>(a);
     else cosine_head_kernel<8><<<ctas, HEAD_NT, 0, stream>>>(a);
@@ -290,6 +291,7 @@ extern "C" int cfm_structural_head(const float* c_logits, const float* f_logits,
     a.d_match = d_match; a.B = B; a.kl_scale = (float)kl_scale; a.match = match; a.loss = loss;
     a.d_c = d_c_logits; a.d_f = d_f_logits; a.partial = partial;
     int ctas = (int)std::min<long long>((B + HEAD_NT - 1) / HEAD_NT, HEAD_MAX_CTAS);
+    ProfScope prof(PROF_HEAD, (cudaStream_t)stream);
     structural_head_kernel<<<ctas, HEAD_NT, 0, (cudaStream_t)stream>>>(a);
     CFM_LAUNCH_CHECK();
     return CFM_OK;

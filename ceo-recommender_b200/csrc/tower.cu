@@ -875,7 +875,10 @@ extern "C" int cfm_towers_fwd(const cfm_tower_t* towers, int64_t n_towers, int64
                         S.N, S.in.K);
             smem = std::max(smem, need);
         }
-        tower_fwd_stage<<<dim3(ctas, (unsigned)n_towers), NT, smem, stream>>>(a);
+        {
+            ProfScope prof(PROF_FWD1 + s - 1, stream);
+            tower_fwd_stage<<<dim3(ctas, (unsigned)n_towers), NT, smem, stream>>>(a);
+        }
         CFM_LAUNCH_CHECK();
         if (any_stats) {
             BnFwdFinArgs f{};
@@ -890,7 +893,10 @@ extern "C" int cfm_towers_fwd(const cfm_tower_t* towers, int64_t n_towers, int64
                 F.nbt = (long long*)(s == 1 ? t.bn1_nbt : t.bn2_nbt);
                 if (!bn_after) F.nbt = nullptr;
             }
-            bn_fwd_finalize<<<dim3(1, (unsigned)n_towers), 256, 0, stream>>>(f);
+            {
+                ProfScope prof(PROF_REDUCE, stream);
+                bn_fwd_finalize<<<dim3(1, (unsigned)n_towers), 256, 0, stream>>>(f);
+            }
             CFM_LAUNCH_CHECK();
         }
     }
@@ -967,6 +973,7 @@ extern "C" int cfm_towers_bwd(const cfm_tower_t* towers, const cfm_tower_grads_t
         }
         // scratch must hold ctas * (N*(K+1) + 2K) floats: guaranteed by cfm_tower_scratch_floats
         int rc;
+        ProfScope* prof = new ProfScope(PROF_BWD1 + s - 1, stream);
         auto fits = [&](int rn4, int rk4) {
             for (int i = 0; i < n_towers; ++i) {
                 const BwdStage& S = a.st[i];
@@ -978,10 +985,13 @@ extern "C" int cfm_towers_bwd(const cfm_tower_t* towers, const cfm_tower_grads_t
         else if (fits(1, 2)) rc = launch_bwd<1, 2>(a, ctas, (int)n_towers, smem, stream);
         else if (fits(2, 2)) rc = launch_bwd<2, 2>(a, ctas, (int)n_towers, smem, stream);
         else {
+            delete prof;
             set_error("tower bwd stage %d: layer too large for the register-tiled dW (N*(K+1) > 16384)", s);
             return CFM_ERR_UNSUPPORTED;
         }
+        delete prof;
         if (rc) return rc;
+        ProfScope prof_red(PROF_REDUCE, stream);
         (void)max_groups;
         // fixed-order reductions of the per-CTA partials
         ReduceWArgs r{};

@@ -42,6 +42,14 @@ const char* cfm_last_error(void);
  * per tower (callers size the per-CTA partial buffers with it). */
 int cfm_device_info(int64_t* sm_count, int64_t* cc_major, int64_t* cc_minor, int64_t* tower_ctas);
 
+/* Bench aids.  cfm_launch_count: kernels this library has launched (optionally reset).
+ * cfm_profile_enable(1): bracket every kernel family with cudaEvents on its stream; cfm_profile_read
+ * synchronises the device and returns summed milliseconds and launch counts per CFM_PROF_* slot. */
+#define CFM_PROF_SLOTS 13
+int64_t cfm_launch_count(int64_t reset);
+int cfm_profile_enable(int64_t on);
+int cfm_profile_read(double* ms /* [CFM_PROF_SLOTS] host */, int64_t* counts /* host */, int64_t n_slots);
+
 /* ------------------------------------------------------------------------------------------
  * Towers.  One tower = categorical embedding gather + numeric concat + 3-layer MLP
  *   Linear(in,h1) -> BN -> ReLU -> Dropout(p1) -> Linear(h1,h2) -> [BN] -> ReLU -> [Dropout(p2)] -> Linear(h2,d_out)

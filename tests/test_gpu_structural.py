@@ -6,7 +6,7 @@ import torch
 import torch.nn.functional as F
 
 import oracle
-from helpers import assert_close_scaled, load_golden, load_into, params_from, t
+from helpers import assert_close_scaled, check_grads, load_golden, load_into, params_from, t
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -56,8 +56,7 @@ def test_matches_reference_golden(name):
     loss.backward()
     assert_close_scaled(loss, g["train_loss"], TOL, "loss (torch KL on fused logits)")
     assert_close_scaled(match, g["train_match"], TOL, "train match")
-    for k, prm in m.named_parameters():
-        assert_close_scaled(prm.grad, g["grad/" + k], 5e-5, "grad " + k)
+    check_grads(m, {k[5:]: v for k, v in g.items() if k.startswith("grad/")}, 5e-5)
     sd = m.state_dict()
     for k, v in g.items():
         if k.startswith("after/"):
@@ -76,8 +75,7 @@ def test_fused_kl_loss_matches_golden(name):
     loss = m.distillation_loss(c_logits, f_logits, tc, tf)       # includes a t == 0 row (xlogy edge case)
     loss.backward()
     assert_close_scaled(loss, g["train_loss"], TOL, "fused KL loss")
-    for k, prm in m.named_parameters():
-        assert_close_scaled(prm.grad, g["grad/" + k], 5e-5, "grad " + k)
+    check_grads(m, {k[5:]: v for k, v in g.items() if k.startswith("grad/")}, 5e-5)
 
 
 def test_reference_known_answer_bilinear():
@@ -123,5 +121,4 @@ def test_batches_vs_oracle(B):
     assert_close_scaled(c_logits, co, TOL, "c_logits")
     assert_close_scaled(match, mo, TOL, "match")
     assert_close_scaled(loss, lo, TOL, "loss")
-    for k, prm in m.named_parameters():
-        assert_close_scaled(prm.grad, po[k].grad, 1e-4, "grad " + k)
+    check_grads(m, {k: po[k].grad for k, _ in m.named_parameters()}, 1e-4)

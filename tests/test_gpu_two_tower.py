@@ -8,7 +8,7 @@ import pytest
 import torch
 
 import oracle
-from helpers import assert_close_scaled, load_golden, load_into, params_from, t
+from helpers import assert_close_scaled, check_grads, load_golden, load_into, params_from, t
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -58,9 +58,7 @@ def test_matches_reference_golden(name):
     assert preds.shape == (ins[0].shape[0], 1)
     assert_close_scaled(preds, g["train_score"], TOL, "train score")
     assert_close_scaled(loss, g["train_loss"], TOL, "train loss")
-    for k, prm in m.named_parameters():
-        assert prm.grad is not None, k
-        assert_close_scaled(prm.grad, g["grad/" + k], 5e-5, "grad " + k)
+    check_grads(m, {k[5:]: v for k, v in g.items() if k.startswith("grad/")}, 5e-5)
     sd = m.state_dict()
     for k, v in g.items():
         if k.startswith("after/"):
@@ -84,8 +82,7 @@ def test_fused_loss_path_matches_golden(name):
         loss.backward()
         assert_close_scaled(loss, g["train_loss"], TOL, "fused loss")
         assert_close_scaled(preds, g["train_score"], TOL, "fused preds")
-        for k, prm in m.named_parameters():
-            assert_close_scaled(prm.grad, g["grad/" + k], 5e-5, f"step {step} grad {k}")
+        check_grads(m, {k[5:]: v for k, v in g.items() if k.startswith("grad/")}, 5e-5)
 
 
 def _rand_inputs(gen, B, f_cards, c_cards):
@@ -115,8 +112,7 @@ def test_ragged_batches_vs_oracle(B):
     loss_o.backward()
     assert_close_scaled(preds, preds_o, TOL, "preds")
     assert_close_scaled(loss, loss_o, TOL, "loss")
-    for k, prm in m.named_parameters():
-        assert_close_scaled(prm.grad, po[k].grad, 1e-4, "grad " + k)
+    check_grads(m, {k: po[k].grad for k, _ in m.named_parameters()}, 1e-4)
 
 
 def test_b1_eval_ok_and_train_raises():
@@ -180,8 +176,7 @@ def test_dropout_mask_parity_and_statistics():
     loss_o = oracle.weighted_mse(preds_o, ins[4], ins[5])
     loss_o.backward()
     assert_close_scaled(preds, preds_o, TOL, "dropout preds")
-    for k, prm in m.named_parameters():
-        assert_close_scaled(prm.grad, po[k].grad, 1e-4, "dropout grad " + k)
+    check_grads(m, {k: po[k].grad for k, _ in m.named_parameters()}, 1e-4)
     # a second call draws a different mask
     loss2, _ = m.forward_loss(*[x.to(DEV) for x in ins])
     assert float(loss2) != float(loss)
@@ -223,8 +218,7 @@ def test_config4_shape_vs_oracle():
     loss_o.backward()
     assert_close_scaled(preds, preds_o, TOL, "preds")
     assert_close_scaled(loss, loss_o, TOL, "loss")
-    for k, prm in m.named_parameters():
-        assert_close_scaled(prm.grad, po[k].grad, 2e-4, "grad " + k)
+    check_grads(m, {k: po[k].grad for k, _ in m.named_parameters()}, 2e-4)
     # size-independent property: every table's gradient rows add up to the column sums of the per-pair rows
     for i, emb in enumerate(m.firm_embeddings):
         nz = (emb.weight.grad.abs().sum(1) > 0).sum().item()
