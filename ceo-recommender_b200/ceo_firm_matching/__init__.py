@@ -10,9 +10,19 @@ reference are out of scope.
 """
 from .config import Config
 from .structural_config import StructuralConfig
+from .data import CEOFirmDataset, DataProcessor
 from .model import CEOFirmMatcher
+from .structural_data import DistillationDataset, StructuralDataProcessor
 from .structural_model import StructuralDistillationNet
+from .structural_training import train_structural_model
+from .synthetic import generate_structural_synthetic_data, generate_synthetic_data
+from .training import train_model
 
 __version__ = "0.4.0+b200"
 
-__all__ = ["Config", "StructuralConfig", "CEOFirmMatcher", "StructuralDistillationNet"]
+__all__ = [
+    "Config", "DataProcessor", "CEOFirmDataset", "CEOFirmMatcher", "train_model",
+    "generate_synthetic_data", "generate_structural_synthetic_data",
+    "StructuralConfig", "StructuralDataProcessor", "DistillationDataset", "StructuralDistillationNet",
+    "train_structural_model",
+]

@@ -58,8 +58,12 @@ PROTOTYPES = {
     "cfm_last_error": (C.c_char_p, []),
     "cfm_device_info": (C.c_int, [C.POINTER(i64)] * 4),
     "cfm_tower_scratch_floats": (i64, [C.POINTER(Tower)]),
-    "cfm_towers_fwd": (C.c_int, [C.POINTER(Tower), _I, _I, _I, _U64, _U64, _V, _V]),
-    "cfm_towers_bwd": (C.c_int, [C.POINTER(Tower), C.POINTER(TowerGrads), _I, _I, _I, _U64, _U64, _V]),
+    "cfm_launch_count": (i64, [_I]),
+    "cfm_profile_enable": (C.c_int, [_I]),
+    "cfm_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(i64), _I]),
+    "cfm_towers_fwd": (C.c_int, [C.POINTER(Tower), _I, _I, _I, _U64, _U64, _V, _V, _V]),
+    "cfm_counter_advance": (C.c_int, [_V, _U64, _V]),
+    "cfm_towers_bwd": (C.c_int, [C.POINTER(Tower), C.POINTER(TowerGrads), _I, _I, _I, _U64, _U64, _V, _V]),
     "cfm_dropout_mask": (C.c_int, [_V, _I, _I, _D, _I, _I, _U64, _U64, _V]),
     "cfm_emb_grad_tmp_bytes": (i64, [_I, _I]),
     "cfm_emb_grad_segment_reduce": (C.c_int, [_V, _V, _I, _I, _I, C.POINTER(C.c_void_p), C.POINTER(i64),

@@ -71,6 +71,12 @@ class CEOFirmMatcher(nn.Module):
         for h in self._handles:
             h.table_grads = ops.PersistentTableGrads(h) if enable else None
 
+    def rezero_table_grads(self) -> None:
+        """Zero the table-gradient rows written by the last backward (call after ``optimizer.step()``)."""
+        for h in self._handles:
+            if h.table_grads is not None:
+                h.table_grads.rezero()
+
     def zero_grad_fast(self) -> None:
         """``optimizer.zero_grad()`` for the fused loop: dense parameters drop their grads, tables re-zero sparsely."""
         tables = set()

@@ -63,6 +63,22 @@ def next_dropout_offset(device: torch.device) -> Tuple[int, int]:
     return torch.initial_seed() & 0xFFFFFFFFFFFFFFFF, st.dropout_offset
 
 
+# While a training step is being captured into a CUDA graph the per-call Python offset would be frozen into the
+# graph; instead the kernels add a device-resident counter (advanced by one graph node per step) to the offset.
+_graph_rng_counter: Optional[torch.Tensor] = None
+
+
+def set_graph_rng_counter(counter: Optional[torch.Tensor]) -> None:
+    global _graph_rng_counter
+    _graph_rng_counter = counter
+
+
+def advance_graph_rng_counter() -> None:
+    if _graph_rng_counter is not None:
+        with torch.cuda.device(_graph_rng_counter.device):
+            N.check(N.lib().cfm_counter_advance(N.ptr(_graph_rng_counter), 1, N.stream_ptr()))
+
+
 # ---------------------------------------------------------------------------------------
 # towers
 # ---------------------------------------------------------------------------------------
@@ -190,9 +206,11 @@ class TowersFunction(torch.autograd.Function):
                 x_cat = _as_index(xs[2 * i + 1]).contiguous()
                 calls.append(_TowerCall(h, x_num, x_cat, B))
             arr = (N.Tower * n)(*[c.struct for c in calls])
-            N.check(N.lib().cfm_towers_fwd(arr, n, B, 1 if training else 0, seed, offset,
+            rng_dev = _graph_rng_counter if training else None
+            N.check(N.lib().cfm_towers_fwd(arr, n, B, 1 if training else 0, seed, offset, N.ptr(rng_dev),
                                            N.ptr(_state(dev).err_flag), N.stream_ptr()))
         ctx.calls, ctx.arr, ctx.training, ctx.seed, ctx.offset = calls, arr, training, seed, offset
+        ctx.rng_dev = rng_dev
         ctx.handles = handles
         ctx.needs_xnum = [xs[2 * i].requires_grad for i in range(n)]
         outs = tuple(c.out for c in calls)
@@ -227,7 +245,7 @@ class TowersFunction(torch.autograd.Function):
                     setattr(grads_arr[i], k, N.ptr(v))
                 per_tower.append(d)
             N.check(N.lib().cfm_towers_bwd(ctx.arr, grads_arr, n, B, 1 if ctx.training else 0, ctx.seed, ctx.offset,
-                                           N.stream_ptr()))
+                                           N.ptr(ctx.rng_dev), N.stream_ptr()))
             out: List[Optional[torch.Tensor]] = []
             for i, (c, d) in enumerate(zip(calls, per_tower)):
                 out += [d["dx_num"], None]
@@ -261,35 +279,41 @@ class _SortScratch:
         self.n_items = n_items
         self.keys_tmp = torch.empty(n_items, dtype=torch.int64, device=device)
         self.vals_tmp = torch.empty(n_items, dtype=torch.int32, device=device)
-        self.keys_sorted = [torch.empty(n_items, dtype=torch.int64, device=device) for _ in range(2)]
+        self.keys_sorted = torch.empty(n_items, dtype=torch.int64, device=device)
         self.vals_sorted = torch.empty(n_items, dtype=torch.int32, device=device)
         self.tmp_bytes = N.lib().cfm_emb_grad_tmp_bytes(n_tables, B)
         self.tmp = torch.empty(self.tmp_bytes, dtype=torch.uint8, device=device)
-        self.flip = 0
 
 
 class PersistentTableGrads:
     """Keeps each table's dense ``.grad`` allocated across steps and re-zeroes only the rows the previous
     step touched (their sorted keys are kept), so the result is the exact dense gradient torch produces
-    (``nn.Embedding(sparse=False)``, model.py:24-33) without a full-table memset every step."""
+    (``nn.Embedding(sparse=False)``, model.py:24-33) without a full-table memset every step.
+    ``rezero()`` reads the sorted keys of the last backward; it runs either at the start of the next step
+    (``zero_grad_fast``) or right after the optimiser step — both orders are CUDA-graph capturable because
+    the keys are consumed before the next sort overwrites them."""
 
     def __init__(self, handle: TowerHandle):
         self.h = handle
-        self.prev_items = 0
-        self.scratch: Optional[_SortScratch] = None
+        self.scratches = {}                      # n_items -> _SortScratch (kept alive: graphs hold raw pointers)
+        self.prev: Optional[_SortScratch] = None
         for e in handle.embeddings:
             e.weight.grad = torch.zeros_like(e.weight)
 
+    def scratch_for(self, n_items: int, B: int, device: torch.device) -> "_SortScratch":
+        if n_items not in self.scratches:
+            self.scratches[n_items] = _SortScratch(n_items, self.h.n_tables, B, device)
+        return self.scratches[n_items]
+
     def rezero(self) -> None:
-        if self.prev_items == 0 or self.scratch is None:
+        if self.prev is None:
             return
         h = self.h
         ptrs = (C.c_void_p * h.n_tables)(*[N.ptr(e.weight.grad) for e in h.embeddings])
         rows = (N.i64 * h.n_tables)(*[e.num_embeddings for e in h.embeddings])
-        prev_keys = self.scratch.keys_sorted[self.scratch.flip ^ 1]
-        N.check(N.lib().cfm_emb_grad_rezero(ptrs, rows, h.n_tables, h.emb_dim, N.ptr(prev_keys), self.prev_items,
-                                            N.stream_ptr()))
-        self.prev_items = 0
+        N.check(N.lib().cfm_emb_grad_rezero(ptrs, rows, h.n_tables, h.emb_dim, N.ptr(self.prev.keys_sorted),
+                                            self.prev.n_items, N.stream_ptr()))
+        self.prev = None
 
 
 def _segment_reduce(h: TowerHandle, x_cat: torch.Tensor, dx_emb: torch.Tensor, B: int,
@@ -298,7 +322,7 @@ def _segment_reduce(h: TowerHandle, x_cat: torch.Tensor, dx_emb: torch.Tensor, B
     rows = (N.i64 * h.n_tables)(*[e.num_embeddings for e in h.embeddings])
     N.check(N.lib().cfm_emb_grad_segment_reduce(
         N.ptr(x_cat), N.ptr(dx_emb), B, h.n_tables, h.emb_dim, ptrs, rows, N.ptr(scratch.keys_tmp),
-        N.ptr(scratch.vals_tmp), N.ptr(scratch.keys_sorted[scratch.flip]), N.ptr(scratch.vals_sorted),
+        N.ptr(scratch.vals_tmp), N.ptr(scratch.keys_sorted), N.ptr(scratch.vals_sorted),
         N.ptr(scratch.tmp), scratch.tmp_bytes, N.stream_ptr()))
 
 
@@ -309,12 +333,11 @@ def embedding_grads(h: TowerHandle, x_cat: torch.Tensor, dx_emb: torch.Tensor, B
     if pg is not None:
         # fast path: write into the persistent .grad buffers (rows touched last step were re-zeroed by
         # PersistentTableGrads.rezero(), called from zero_grad), autograd gets no tensor for the tables
-        if pg.scratch is None or pg.scratch.n_items != n_items:
-            pg.rezero()
-            pg.scratch = _SortScratch(n_items, h.n_tables, B, dx_emb.device)
-        _segment_reduce(h, x_cat, dx_emb, B, [e.weight.grad for e in h.embeddings], pg.scratch)
-        pg.prev_items = n_items
-        pg.scratch.flip ^= 1
+        if pg.prev is not None:
+            raise RuntimeError("persistent table grads: backward ran twice without zero_grad_fast() in between")
+        scratch = pg.scratch_for(n_items, B, dx_emb.device)
+        _segment_reduce(h, x_cat, dx_emb, B, [e.weight.grad for e in h.embeddings], scratch)
+        pg.prev = scratch
         return [None] * h.n_tables
     scratch = _SortScratch(n_items, h.n_tables, B, dx_emb.device)
     grads = [torch.zeros_like(e.weight) for e in h.embeddings]

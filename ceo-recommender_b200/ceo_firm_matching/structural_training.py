@@ -1,0 +1,70 @@
+"""Training loop of the Structural Distillation Network — drop-in for the reference's
+``structural_training.py`` (``ceo_firm_matching/structural_training.py:17-117``): Adam on the sum of the two
+KL(batchmean) distillation losses, a validation pass per epoch, best-validation tracking and the same prints.
+Each step runs the fused towers and the fused softmax.A.softmax + KL head (loss and d/dlogits in one launch).
+"""
+from typing import Optional
+
+import torch
+import torch.optim as optim
+from torch.utils.data import DataLoader
+
+from . import ops
+from .batching import device_batches
+from .structural_config import StructuralConfig
+from .structural_model import StructuralDistillationNet
+
+BATCH_KEYS = ("firm_num", "firm_cat", "ceo_num", "ceo_cat", "target_ceo", "target_firm")
+
+
+def _loss(model: StructuralDistillationNet, batch) -> torch.Tensor:
+    f_num, f_cat, c_num, c_cat, t_ceo, t_firm = batch
+    c_logits, f_logits = model.logits(f_num, f_cat, c_num, c_cat)
+    return model.distillation_loss(c_logits, f_logits, t_ceo, t_firm)
+
+
+def train_structural_model(train_loader: DataLoader, val_loader: DataLoader, metadata: dict,
+                           config: StructuralConfig) -> Optional[StructuralDistillationNet]:
+    device = torch.device(config.DEVICE)
+    if device.type != "cuda":
+        raise RuntimeError("this build trains on CUDA only (config.DEVICE resolved to %s)" % device)
+    model = StructuralDistillationNet(metadata, config).to(device)
+
+    print("Initialized Structural Distillation Network.")
+    print(f"  Device: {config.DEVICE}")
+    print(f"  Interaction Matrix Frozen: {not model.A.requires_grad}")
+    print(f"  CEO Tower Input: {metadata['n_ceo_num']} numeric + {len(metadata['ceo_cat_cards'])} categorical")
+    print(f"  Firm Tower Input: {metadata['n_firm_num']} numeric + {len(metadata['firm_cat_cards'])} categorical")
+
+    optimizer = optim.Adam(model.parameters(), lr=config.LEARNING_RATE)
+    print(f"\nStarting Distillation Training for {config.EPOCHS} epochs...")
+
+    best_val_loss = float("inf")
+    for epoch in range(config.EPOCHS):
+        model.train()
+        train_loss = torch.zeros((), device=device)       # accumulated on the device: one sync per epoch
+        n_train = 0
+        for batch in device_batches(train_loader, BATCH_KEYS, device):
+            optimizer.zero_grad(set_to_none=True)
+            loss = _loss(model, batch)
+            loss.backward()
+            optimizer.step()
+            train_loss += loss.detach()
+            n_train += 1
+
+        model.eval()
+        val_loss = torch.zeros((), device=device)
+        n_val = 0
+        with torch.no_grad():
+            for batch in device_batches(val_loader, BATCH_KEYS, device):
+                val_loss += _loss(model, batch)
+                n_val += 1
+        ops.raise_if_index_error(device)
+        avg_train_loss = float(train_loss) / max(n_train, 1)
+        avg_val_loss = float(val_loss) / max(n_val, 1)
+        best_val_loss = min(best_val_loss, avg_val_loss)
+        if epoch % 10 == 0 or epoch == config.EPOCHS - 1:
+            print(f"  Epoch {epoch:3d}: Train Loss = {avg_train_loss:.4f}, Val Loss = {avg_val_loss:.4f}")
+
+    print(f"\nTraining Complete. Best Validation Loss: {best_val_loss:.4f}")
+    return model

@@ -95,6 +95,7 @@ struct DropCtx {
     float inv_keep;       // 1 / (1 - p)
     uint32_t stream_id;   // tower_id * 4 + site
     bool active;
+    const unsigned long long* dev_off;   // optional device-resident step counter added to the offset (CUDA graphs)
 };
 __host__ __device__ __forceinline__ DropCtx make_drop(double p, bool training, uint64_t seed, uint64_t offset,
                                                       int64_t tower_id, int site) {
@@ -106,6 +107,15 @@ __host__ __device__ __forceinline__ DropCtx make_drop(double p, bool training, u
     d.thresh = t >= 4294967295.0 ? 0xffffffffu : (uint32_t)t;
     d.inv_keep = d.active ? (float)(1.0 / (1.0 - p)) : 1.0f;
     d.stream_id = (uint32_t)(tower_id * 4 + site);
+    d.dev_off = nullptr;
+    return d;
+}
+// fold the device-side counter into the offset (once per thread, at kernel start)
+__device__ __forceinline__ DropCtx resolve_drop(DropCtx d) {
+    if (d.active && d.dev_off) {
+        unsigned long long o = (((unsigned long long)d.o1 << 32) | d.o0) + *d.dev_off;
+        d.o0 = (uint32_t)o; d.o1 = (uint32_t)(o >> 32);
+    }
     return d;
 }
 // words for columns [4*c4, 4*c4+3] of `row`

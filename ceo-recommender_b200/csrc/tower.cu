@@ -163,8 +163,8 @@ __device__ __forceinline__ void stage_bn_params(const ActSrc& a, int K, float* s
 }
 
 // Build the [TM, K] input tile (+ ones column at K, zero pad to lda); optionally the x-hat tile.
-__device__ void build_input_tile(const InputDesc& in, long long row0, int rows_valid, float* As, int lda,
-                                 float* Xh, int ldxh, const float* sm_bn, int* sm_idx, int* err) {
+__device__ void build_input_tile(const InputDesc& in, const DropCtx& drop, long long row0, int rows_valid, float* As,
+                                 int lda, float* Xh, int ldxh, const float* sm_bn, int* sm_idx, int* err) {
     const int K = in.K;
     const int tid = threadIdx.x;
     if (in.stage == 1) {
@@ -229,7 +229,7 @@ __device__ void build_input_tile(const InputDesc& in, long long row0, int rows_v
                         if (4 * c4 + e < K) v[e] = hp[e];
                 }
                 Philox4 w = {0, 0, 0, 0};
-                if (a.drop.active) w = drop_words(a.drop, row0 + r, c4);
+                if (drop.active) w = drop_words(drop, row0 + r, c4);
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     int c = 4 * c4 + e;
@@ -240,7 +240,7 @@ __device__ void build_input_tile(const InputDesc& in, long long row0, int rows_v
                             t = xh[e] * sm_bn[2 * Kp + c] + sm_bn[3 * Kp + c];
                         }
                         t = fmaxf(t, 0.f);
-                        if (a.drop.active) t = drop_keep(a.drop, w, e) ? t * a.drop.inv_keep : 0.f;
+                        if (drop.active) t = drop_keep(drop, w, e) ? t * drop.inv_keep : 0.f;
                         v[e] = t;
                     } else {
                         v[e] = 0.f;
@@ -410,6 +410,7 @@ __global__ void __launch_bounds__(NT, 1) tower_fwd_stage(const __grid_constant__
     const int tid = threadIdx.x, lda = L.lda;
     const int KE = S.in.g.n_tab * S.in.g.E;
     const bool stats = S.stat_part != nullptr;
+    const DropCtx drop = resolve_drop(S.in.a.drop);
 
     // weights -> smem, [wrows][lda] with bias in column K and zeros elsewhere in the padding
     for (int i = tid; i < gp.wrows * lda; i += NT) {
@@ -439,7 +440,7 @@ __global__ void __launch_bounds__(NT, 1) tower_fwd_stage(const __grid_constant__
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long long row0 = tile * TM;
         const int rows_valid = (int)min((long long)TM, args.B - row0);
-        build_input_tile(S.in, row0, rows_valid, As, lda, nullptr, 0, sm_bn, sm_idx, args.err);
+        build_input_tile(S.in, drop, row0, rows_valid, As, lda, nullptr, 0, sm_bn, sm_idx, args.err);
         __syncthreads();
         for (int pass = 0; pass < gp.passes; ++pass) {
             switch (gp.RM) {
@@ -467,11 +468,13 @@ struct BnFwdFin {
 };
 struct BnFwdFinArgs { BnFwdFin t[2]; };
 __global__ void bn_fwd_finalize(const __grid_constant__ BnFwdFinArgs args) {
+    // one warp per column: lanes Chan-merge a strided subset of the CTA partials, then a fixed shuffle tree
     const BnFwdFin& F = args.t[blockIdx.y];
-    const int N = F.N;
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < N; c += gridDim.x * blockDim.x) {
+    const int N = F.N, lane = threadIdx.x & 31;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c < N) {
         float n = 0.f, mean = 0.f, m2 = 0.f;
-        for (int p = 0; p < F.nparts; ++p) {
+        for (int p = lane; p < F.nparts; p += 32) {
             const float* P = F.part + (size_t)p * (2 * N + 4);
             float nb = P[2 * N];
             if (nb <= 0.f) continue;
@@ -480,16 +483,29 @@ __global__ void bn_fwd_finalize(const __grid_constant__ BnFwdFinArgs args) {
             m2 += P[N + c] + d * d * (n * nb / nn);
             n = nn;
         }
-        float var_b = m2 / n;
-        F.stat[c] = mean;
-        F.stat[N + c] = rsqrtf(var_b + BN_EPS);
-        if (F.rm) {
-            float var_u = n > 1.f ? m2 / (n - 1.f) : var_b;
-            F.rm[c] = 0.9f * F.rm[c] + 0.1f * mean;       // momentum 0.1 (nn.BatchNorm1d default)
-            F.rv[c] = 0.9f * F.rv[c] + 0.1f * var_u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            float nb = __shfl_down_sync(FULL, n, o), mb = __shfl_down_sync(FULL, mean, o);
+            float qb = __shfl_down_sync(FULL, m2, o);
+            if (nb > 0.f) {
+                float d = mb - mean, nn = n + nb;
+                mean += d * (nb / nn);
+                m2 += qb + d * d * (n * nb / nn);
+                n = nn;
+            }
+        }
+        if (lane == 0) {
+            float var_b = m2 / n;
+            F.stat[c] = mean;
+            F.stat[N + c] = rsqrtf(var_b + BN_EPS);
+            if (F.rm) {
+                float var_u = n > 1.f ? m2 / (n - 1.f) : var_b;
+                F.rm[c] = 0.9f * F.rm[c] + 0.1f * mean;       // momentum 0.1 (nn.BatchNorm1d default)
+                F.rv[c] = 0.9f * F.rv[c] + 0.1f * var_u;
+            }
         }
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0 && F.nbt) *F.nbt += 1;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && F.nbt && N > 0) *F.nbt += 1;
 }
 
 struct BwdCtx {
@@ -563,6 +579,7 @@ __device__ void bwd_stage_body(const BwdStage& S, long long B, float* sm) {
     const int KE = S.in.g.n_tab * S.in.g.E, n_num = S.in.g.n_num;
     const int Np = (N + 3) & ~3;
     const bool stage1 = S.in.stage == 1;
+    const DropCtx drop = resolve_drop(S.in.a.drop);
 
     // W^T -> smem: Wt[k'][n] (k' in tile column order), zero padded
     if (S.need_dx) {
@@ -624,7 +641,7 @@ __device__ void bwd_stage_body(const BwdStage& S, long long B, float* sm) {
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long long row0 = tile * TM;
         const int rows_valid = (int)min((long long)TM, B - row0);
-        build_input_tile(S.in, row0, rows_valid, As, lda, Xh, ldxh, sm_bna, sm_idx, nullptr);
+        build_input_tile(S.in, drop, row0, rows_valid, As, lda, Xh, ldxh, sm_bna, sm_idx, nullptr);
         // incoming-gradient tile G [TM, N] (zero padded to ldg)
         for (int i = tid; i < TM * (ldg >> 2); i += NT) {
             int r = i / (ldg >> 2), c4 = i - r * (ldg >> 2);
@@ -703,15 +720,31 @@ __global__ void __launch_bounds__(NT, 1) tower_bwd_stage(const __grid_constant__
 // dW[n][k] = sum over CTA partials (fixed order), bias gradient from the extra column
 struct ReduceW { const float* part; int nparts; int N, K; float* dW; float* db; };
 struct ReduceWArgs { ReduceW t[2]; };
-__global__ void reduce_dw(const __grid_constant__ ReduceWArgs args) {
+__global__ void __launch_bounds__(256) reduce_dw(const __grid_constant__ ReduceWArgs args) {
+    // 32 consecutive elements per CTA x 8 partial lanes; lane pl sums partials pl, pl+8, ... then the 8 lane
+    // sums are added in lane order: fixed association, fully coalesced 128-byte reads
     const ReduceW& R = args.t[blockIdx.y];
+    __shared__ float sm[8][33];
     const int stride = R.N * (R.K + 1);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < stride; i += gridDim.x * blockDim.x) {
+    const int el = threadIdx.x & 31, pl = threadIdx.x >> 5;
+    for (int base = blockIdx.x * 32; base < stride; base += gridDim.x * 32) {
+        const int i = base + el;
         float s = 0.f;
-        for (int p = 0; p < R.nparts; ++p) s += R.part[(size_t)p * stride + i];
-        int n = i / (R.K + 1), k = i - n * (R.K + 1);
-        if (k < R.K) R.dW[(size_t)n * R.K + k] = s;
-        else if (R.db) R.db[n] = s;
+        if (i < stride) {
+#pragma unroll 4
+            for (int p = pl; p < R.nparts; p += 8) s += R.part[(size_t)p * stride + i];
+        }
+        sm[pl][el] = s;
+        __syncthreads();
+        if (pl == 0 && i < stride) {
+            float tot = 0.f;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) tot += sm[q][el];
+            int n = i / (R.K + 1), k = i - n * (R.K + 1);
+            if (k < R.K) R.dW[(size_t)n * R.K + k] = tot;
+            else if (R.db) R.db[n] = tot;
+        }
+        __syncthreads();
     }
 }
 
@@ -720,18 +753,28 @@ struct BnBwdFin { const float* part; int nparts; int K; float B; float* dgamma; 
 struct BnBwdFinArgs { BnBwdFin t[2]; };
 __global__ void bn_bwd_finalize(const __grid_constant__ BnBwdFinArgs args) {
     const BnBwdFin& F = args.t[blockIdx.y];
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < F.K; c += gridDim.x * blockDim.x) {
-        float s1 = 0.f, s2 = 0.f;
-        for (int p = 0; p < F.nparts; ++p) {
-            s1 += F.part[(size_t)p * 2 * F.K + c];
-            s2 += F.part[(size_t)p * 2 * F.K + F.K + c];
-        }
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // one warp per column
+    if (c >= F.K) return;
+    float s1 = 0.f, s2 = 0.f;
+    for (int p = lane; p < F.nparts; p += 32) {
+        s1 += F.part[(size_t)p * 2 * F.K + c];
+        s2 += F.part[(size_t)p * 2 * F.K + F.K + c];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s1 += __shfl_down_sync(FULL, s1, o);
+        s2 += __shfl_down_sync(FULL, s2, o);
+    }
+    if (lane == 0) {
         if (F.dbeta) F.dbeta[c] = s1;
         if (F.dgamma) F.dgamma[c] = s2;
         F.stat[2 * F.K + c] = s1 / F.B;
         F.stat[3 * F.K + c] = s2 / F.B;
     }
 }
+
+__global__ void counter_advance_kernel(unsigned long long* c, unsigned long long inc) { *c += inc; }
 
 __global__ void dropout_mask_kernel(uint8_t* mask, long long B, int width, DropCtx d) {
     const int W4 = (width + 3) >> 2;
@@ -778,7 +821,8 @@ static void fill_gather(GatherSrc& g, const cfm_tower_t& t) {
 }
 
 // input description of stage s (1..3) of tower t
-static InputDesc input_desc(const cfm_tower_t& t, int s, bool training, uint64_t seed, uint64_t offset) {
+static InputDesc input_desc(const cfm_tower_t& t, int s, bool training, uint64_t seed, uint64_t offset,
+                            const uint64_t* dev_off) {
     InputDesc in{};
     in.stage = s;
     fill_gather(in.g, t);
@@ -804,6 +848,7 @@ static InputDesc input_desc(const cfm_tower_t& t, int s, bool training, uint64_t
         }
         in.a.drop = make_drop(t.drop2, training, seed, offset, t.tower_id, 1);
     }
+    in.a.drop.dev_off = (const unsigned long long*)dev_off;
     return in;
 }
 
@@ -839,7 +884,8 @@ extern "C" int64_t cfm_tower_scratch_floats(const cfm_tower_t* t) {
 }
 
 extern "C" int cfm_towers_fwd(const cfm_tower_t* towers, int64_t n_towers, int64_t B, int64_t training,
-                              uint64_t seed, uint64_t offset, int32_t* err_flag, void* stream_) {
+                              uint64_t seed, uint64_t offset, const uint64_t* rng_offset_dev, int32_t* err_flag,
+                              void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     CFM_REQUIRE(towers && n_towers >= 1 && n_towers <= 2, CFM_ERR_INVALID, "n_towers must be 1 or 2");
     CFM_REQUIRE(B >= 1, CFM_ERR_INVALID, "B must be >= 1 (got %lld)", (long long)B);
@@ -861,7 +907,7 @@ extern "C" int cfm_towers_fwd(const cfm_tower_t* towers, int64_t n_towers, int64
         for (int i = 0; i < n_towers; ++i) {
             const cfm_tower_t& t = towers[i];
             FwdStage& S = a.st[i];
-            S.in = input_desc(t, s, training != 0, seed, offset);
+            S.in = input_desc(t, s, training != 0, seed, offset, rng_offset_dev);
             S.N = stage_N(t, s);
             S.W = s == 1 ? t.w1 : s == 2 ? t.w2 : t.w3;
             S.bias = s == 1 ? t.b1 : s == 2 ? t.b2 : t.b3;
@@ -895,7 +941,8 @@ extern "C" int cfm_towers_fwd(const cfm_tower_t* towers, int64_t n_towers, int64
             }
             {
                 ProfScope prof(PROF_REDUCE, stream);
-                bn_fwd_finalize<<<dim3(1, (unsigned)n_towers), 256, 0, stream>>>(f);
+                int maxN = 1; for (int i = 0; i < n_towers; ++i) maxN = std::max(maxN, f.t[i].N);
+                bn_fwd_finalize<<<dim3(ceil_div(maxN, 8), (unsigned)n_towers), 256, 0, stream>>>(f);
             }
             CFM_LAUNCH_CHECK();
         }
@@ -917,7 +964,8 @@ static int launch_bwd(const BwdArgs& a, int ctas, int n_towers, size_t smem, cud
 }
 
 extern "C" int cfm_towers_bwd(const cfm_tower_t* towers, const cfm_tower_grads_t* grads, int64_t n_towers, int64_t B,
-                              int64_t training, uint64_t seed, uint64_t offset, void* stream_) {
+                              int64_t training, uint64_t seed, uint64_t offset, const uint64_t* rng_offset_dev,
+                              void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     CFM_REQUIRE(towers && grads && n_towers >= 1 && n_towers <= 2, CFM_ERR_INVALID, "n_towers must be 1 or 2");
     CFM_REQUIRE(B >= 1, CFM_ERR_INVALID, "B must be >= 1");
@@ -941,7 +989,7 @@ extern "C" int cfm_towers_bwd(const cfm_tower_t* towers, const cfm_tower_grads_t
             const cfm_tower_t& t = towers[i];
             const cfm_tower_grads_t& g = grads[i];
             BwdStage& S = a.st[i];
-            S.in = input_desc(t, s, training != 0, seed, offset);
+            S.in = input_desc(t, s, training != 0, seed, offset, rng_offset_dev);
             S.N = stage_N(t, s);
             S.W = s == 1 ? t.w1 : s == 2 ? t.w2 : t.w3;
             S.a_bn = s >= 2 && S.in.a.bn_mode != 0;
@@ -1003,7 +1051,8 @@ extern "C" int cfm_towers_bwd(const cfm_tower_t* towers, const cfm_tower_grads_t
             R.dW = s == 1 ? g.dw1 : s == 2 ? g.dw2 : g.dw3;
             R.db = s == 1 ? g.db1 : s == 2 ? g.db2 : g.db3;
         }
-        reduce_dw<<<dim3(32, (unsigned)n_towers), 256, 0, stream>>>(r);
+        int maxS = 1; for (int i = 0; i < n_towers; ++i) maxS = std::max(maxS, r.t[i].N * (r.t[i].K + 1));
+        reduce_dw<<<dim3(std::min(ceil_div(maxS, 32), 592), (unsigned)n_towers), 256, 0, stream>>>(r);
         CFM_LAUNCH_CHECK();
         if (any_sums) {
             BnBwdFinArgs f{};
@@ -1017,7 +1066,8 @@ extern "C" int cfm_towers_bwd(const cfm_tower_t* towers, const cfm_tower_grads_t
                 F.dbeta = s == 3 ? g.dbn2_b : g.dbn1_b;
                 F.stat = s == 3 ? t.bn2_stat : t.bn1_stat;
             }
-            bn_bwd_finalize<<<dim3(1, (unsigned)n_towers), 256, 0, stream>>>(f);
+            int maxK = 1; for (int i = 0; i < n_towers; ++i) maxK = std::max(maxK, f.t[i].K);
+            bn_bwd_finalize<<<dim3(ceil_div(maxK, 8), (unsigned)n_towers), 256, 0, stream>>>(f);
             CFM_LAUNCH_CHECK();
         }
     }
@@ -1031,6 +1081,13 @@ extern "C" int cfm_dropout_mask(uint8_t* mask, int64_t B, int64_t width, double 
     DropCtx d = make_drop(p, true, seed, offset, tower_id, (int)site);
     dropout_mask_kernel<<<std::min<long long>(1024, (B * ((width + 3) / 4) + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(
         mask, B, (int)width, d);
+    CFM_LAUNCH_CHECK();
+    return CFM_OK;
+}
+
+extern "C" int cfm_counter_advance(uint64_t* counter_dev, uint64_t inc, void* stream_) {
+    CFM_REQUIRE(counter_dev, CFM_ERR_INVALID, "null counter");
+    counter_advance_kernel<<<1, 1, 0, (cudaStream_t)stream_>>>((unsigned long long*)counter_dev, inc);
     CFM_LAUNCH_CHECK();
     return CFM_OK;
 }

@@ -88,7 +88,11 @@ int64_t cfm_tower_scratch_floats(const cfm_tower_t* t);
  * training=1: batch-stat BN (running stats updated), dropout drawn from a counter-based
  * Philox stream keyed by (seed, offset); training=0: running-stat BN, no dropout. */
 int cfm_towers_fwd(const cfm_tower_t* towers, int64_t n_towers, int64_t B, int64_t training,
-                   uint64_t seed, uint64_t offset, int32_t* err_flag, void* stream);
+                   uint64_t seed, uint64_t offset, const uint64_t* rng_offset_dev /* nullable: device counter
+                   added to `offset`, so a captured CUDA graph draws a fresh mask every replay */,
+                   int32_t* err_flag, void* stream);
+/* *counter_dev += inc on the stream (one graph node per step keeps the dropout stream moving) */
+int cfm_counter_advance(uint64_t* counter_dev, uint64_t inc, void* stream);
 
 typedef struct cfm_tower_grads {
     const float* g_out;          /* [B,d_out] gradient w.r.t. tower output */
@@ -102,7 +106,7 @@ typedef struct cfm_tower_grads {
 /* Backward of the towers given the same descriptors (same training flag / seed / offset as fwd).
  * replaces: the autograd graph torch builds for model.py:69-76 (training.py:54 `loss.backward()`). */
 int cfm_towers_bwd(const cfm_tower_t* towers, const cfm_tower_grads_t* grads, int64_t n_towers, int64_t B,
-                   int64_t training, uint64_t seed, uint64_t offset, void* stream);
+                   int64_t training, uint64_t seed, uint64_t offset, const uint64_t* rng_offset_dev, void* stream);
 
 /* Keep-mask the towers' dropout uses, materialised for differential tests:
  * mask[r, c] (uint8) for `site` (0 = after activation 1, 1 = after activation 2). */
