@@ -488,3 +488,93 @@ def dropout_mask(B: int, width: int, p: float, tower_id: int, site: int, seed: i
     with torch.cuda.device(device):
         N.check(N.lib().cfm_dropout_mask(N.ptr(mask), B, width, p, tower_id, site, seed, offset, N.stream_ptr()))
     return mask
+
+
+# ---------------------------------------------------------------------------------------
+# InfoNCE on the tensor cores (contrastive.py:102-138)
+# ---------------------------------------------------------------------------------------
+def padded_width(d: int) -> int:
+    dp = 64 * ((d + 63) // 64)
+    if dp > 128:
+        raise N.CfmError(f"feature width {d} not supported by the tcgen05 similarity kernels (max 128)")
+    return dp
+
+
+def pack_bf16(x: torch.Tensor) -> torch.Tensor:
+    """fp32/bf16 [R, D] -> bf16 [R, Dp] with zero padding to a multiple of 64 features (TMA/UMMA granularity)."""
+    _require_cuda(x)
+    R, D = x.shape
+    dp = padded_width(D)
+    if x.dtype == torch.bfloat16 and dp == D and x.is_contiguous():
+        return x
+    out = torch.empty(R, dp, dtype=torch.bfloat16, device=x.device)
+    xf = x.detach().float().contiguous()
+    with torch.cuda.device(x.device):
+        N.check(N.lib().cfm_pack_rows_bf16(N.ptr(xf), R, D, dp, N.ptr(out), N.stream_ptr()))
+    return out
+
+
+def simtile_scores(xb: torch.Tensor, yb: torch.Tensor) -> torch.Tensor:
+    """Raw tensor-core score tile X . Y^T as fp32 [R, C] (parity/debug aid)."""
+    out = torch.empty(xb.shape[0], yb.shape[0], device=xb.device)
+    with torch.cuda.device(xb.device):
+        N.check(N.lib().cfm_simtile_scores(N.ptr(xb), N.ptr(yb), xb.shape[0], yb.shape[0], xb.shape[1], N.ptr(out),
+                                           N.stream_ptr()))
+    return out
+
+
+def infonce_rowsum(xb: torch.Tensor, yb: torch.Tensor, temperature: float, diag_offset: int = 0, want_diag: bool = True):
+    """rowsum[i] = sum_j exp((x_i.y_j - 1)/T) and diag[i] = x_i . y_(i+diag_offset), S never materialised."""
+    R, C, dp = xb.shape[0], yb.shape[0], xb.shape[1]
+    dev = xb.device
+    chunks = N.lib().cfm_simtile_chunks(R, C)
+    part = torch.empty(chunks * R, device=dev)
+    rowsum = torch.empty(R, device=dev)
+    diag = torch.zeros(R, device=dev) if want_diag else None
+    with torch.cuda.device(dev):
+        N.check(N.lib().cfm_infonce_rowsum(N.ptr(xb), N.ptr(yb), R, C, dp, temperature, diag_offset, N.ptr(rowsum),
+                                           N.ptr(diag), N.ptr(part), N.stream_ptr()))
+    return rowsum, diag
+
+
+def infonce_grad(xb, yb, D, temperature, diag_offset, B_total, rowsum_x, rowsum_y, diag, g_loss):
+    R, C, dp = xb.shape[0], yb.shape[0], xb.shape[1]
+    dev = xb.device
+    chunks = N.lib().cfm_simtile_chunks(R, C)
+    part = torch.empty(chunks * R * dp, device=dev)
+    dx = torch.empty(R, D, device=dev)
+    with torch.cuda.device(dev):
+        N.check(N.lib().cfm_infonce_grad(N.ptr(xb), N.ptr(yb), R, C, D, dp, temperature, diag_offset, B_total,
+                                         N.ptr(rowsum_x), N.ptr(rowsum_y), N.ptr(diag), N.ptr(g_loss), N.ptr(dx), N.ptr(part),
+                                         N.stream_ptr()))
+    return dx
+
+
+class InfoNCEFunction(torch.autograd.Function):
+    """apply(firm_proj [B,D], ceo_proj [B,D], temperature) -> scalar symmetric InfoNCE loss.
+    Four passes of the similarity-tile kernel (row sums of S and of S^T, then dF and dC); the [B,B] matrix only
+    ever exists as 128x128 TMEM accumulators."""
+
+    @staticmethod
+    def forward(ctx, firm_proj, ceo_proj, temperature):
+        _require_cuda(firm_proj, ceo_proj)
+        B, D = firm_proj.shape
+        fb, cb = pack_bf16(firm_proj), pack_bf16(ceo_proj)
+        rs_f, diag = infonce_rowsum(fb, cb, temperature)               # row sums of S  (firm -> ceo)
+        rs_c, _ = infonce_rowsum(cb, fb, temperature, want_diag=False)  # row sums of S^T (ceo -> firm)
+        loss = torch.empty((), device=firm_proj.device)
+        with torch.cuda.device(firm_proj.device):
+            N.check(N.lib().cfm_infonce_loss(N.ptr(rs_f), N.ptr(rs_c), N.ptr(diag), B, temperature, B, N.ptr(loss),
+                                             N.stream_ptr()))
+        ctx.save_for_backward(fb, cb, rs_f, rs_c, diag)
+        ctx.temperature, ctx.D, ctx.in_dtype = temperature, D, firm_proj.dtype
+        return loss
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        fb, cb, rs_f, rs_c, diag = ctx.saved_tensors
+        B = fb.shape[0]
+        g = g_loss.contiguous().float()
+        d_firm = infonce_grad(fb, cb, ctx.D, ctx.temperature, 0, B, rs_f, rs_c, diag, g)
+        d_ceo = infonce_grad(cb, fb, ctx.D, ctx.temperature, 0, B, rs_c, rs_f, diag, g)
+        return d_firm.to(ctx.in_dtype), d_ceo.to(ctx.in_dtype), None

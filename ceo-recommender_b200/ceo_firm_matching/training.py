@@ -31,7 +31,8 @@ class GraphedTwoTowerStep:
     Philox offset counter advanced by a graph node)."""
 
     def __init__(self, model: CEOFirmMatcher, example: Sequence[torch.Tensor],
-                 optimizer: Optional[torch.optim.Optimizer] = None, warmup: int = 3):
+                 optimizer: Optional[torch.optim.Optimizer] = None, warmup: int = 3,
+                 stream: Optional[torch.cuda.Stream] = None):
         dev = next(model.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("GraphedTwoTowerStep needs the model on a CUDA device (no CPU fallback)")
@@ -42,16 +43,18 @@ class GraphedTwoTowerStep:
         self.counter = torch.zeros(1, dtype=torch.int64, device=dev)
         self.graph = torch.cuda.CUDAGraph()
         self.loss = None
+        # Autograd pins each parameter's gradient-accumulation node to the stream of its first use; capture fails
+        # if that is the legacy default stream.  Warm-up, capture and replay therefore share one side stream (the
+        # caller's own non-default stream when it already trains on one).
+        self.stream = stream if stream is not None else torch.cuda.Stream(dev)
         ops.set_graph_rng_counter(self.counter)
         try:
-            side = torch.cuda.Stream(dev)
-            side.wait_stream(torch.cuda.current_stream(dev))
-            with torch.cuda.stream(side):
+            self.stream.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(self.stream):
                 for _ in range(warmup):          # eager warm-up: allocations, func attributes, sort scratch
                     self._body()
-            torch.cuda.current_stream(dev).wait_stream(side)
             torch.cuda.synchronize(dev)
-            with torch.cuda.graph(self.graph):
+            with torch.cuda.graph(self.graph, stream=self.stream):
                 self.loss = self._body()
         finally:
             ops.set_graph_rng_counter(None)
@@ -73,7 +76,7 @@ class GraphedTwoTowerStep:
     def step(self, batch: Optional[Sequence[torch.Tensor]] = None) -> torch.Tensor:
         if batch is not None:
             self.load(batch)
-        self.graph.replay()
+        self.graph.replay()                      # replays on the caller's current stream
         return self.loss
 
 
@@ -108,7 +111,16 @@ def train_model(train_loader: DataLoader, val_loader: DataLoader, metadata: Dict
     model.use_persistent_table_grads(True)
 
     print(f"Starting training on {config.DEVICE} for {config.EPOCHS} epochs...")
+    stream = torch.cuda.Stream(device)           # the whole loop runs on one side stream (see GraphedTwoTowerStep)
+    stream.wait_stream(torch.cuda.current_stream(device))
+    with torch.cuda.stream(stream):
+        _train_epochs(model, optimizer, train_loader, config, device, stream)
+    torch.cuda.current_stream(device).wait_stream(stream)
+    model.use_persistent_table_grads(False)
+    return model
 
+
+def _train_epochs(model, optimizer, train_loader, config, device, stream) -> None:
     # One captured step per distinct batch size.  The first step of a given size runs eagerly (it is a real
     # training step and leaves every buffer allocated); the second occurrence captures the graph.
     graphed: Dict[int, GraphedTwoTowerStep] = {}
@@ -126,7 +138,7 @@ def train_model(train_loader: DataLoader, val_loader: DataLoader, metadata: Dict
                 loss = eager_step(model, optimizer, tensors)
             else:
                 if B not in graphed:
-                    graphed[B] = GraphedTwoTowerStep(model, tensors, optimizer, warmup=0)
+                    graphed[B] = GraphedTwoTowerStep(model, tensors, optimizer, warmup=0, stream=stream)
                 loss = graphed[B].step(tensors)
             total_loss += loss
             n_batches += 1
@@ -134,6 +146,3 @@ def train_model(train_loader: DataLoader, val_loader: DataLoader, metadata: Dict
         avg_loss = float(total_loss) / max(n_batches, 1)
         if epoch % 5 == 0:
             print(f"Epoch {epoch}: Avg Train Loss = {avg_loss:.4f}")
-
-    model.use_persistent_table_grads(False)
-    return model

@@ -1,0 +1,556 @@
+// Similarity-tile kernels on the 5th-gen tensor cores (tcgen05 + TMEM, operands staged by TMA):
+//   S = X . Y^T  tile by tile (128 x 128), never written to HBM, consumed in the epilogue as
+//     * InfoNCE row sums   sum_j exp((s_ij - m)/T) + the diagonal logit          (contrastive.py:129-136)
+//     * InfoNCE gradient   dX = sum_j g_ij y_j with g_ij = E_ij (1/R_i + 1/C_j)/(2BT), second GEMM G . Y on the
+//       same tensor cores with G re-staged through shared memory as bf16           (autograd of the above)
+//     * raw scores (debug/parity mode).
+// One CTA = one 128-row block of X x one chunk of column tiles.  Warp roles: warp 0 TMA producer, warp 1 MMA
+// issuer (one elected thread), warps 2-5 epilogue (thread t <-> TMEM lane t <-> one row).  Pipelines: Y tiles
+// through a 3-stage smem ring (full/empty mbarriers), S accumulators double-buffered in TMEM, G double-buffered
+// in smem.  The fixed maximum m = 1/T (|s| <= 1 for unit rows) makes row and column sums use the same
+// exponentials and makes partial sums directly addable across column chunks and GPUs.
+#include "common.cuh"
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <algorithm>
+
+namespace cfm {
+
+constexpr int ST_M = 128, ST_N = 128, ST_KB = 64;      // tile rows / cols, bf16 elements per 128-byte swizzle row
+constexpr int ST_STAGES = 3;
+constexpr int ST_THREADS = 192;
+constexpr int KB_BYTES = ST_M * 128;                   // one [128 rows x 64 bf16] swizzled block = 16 KB
+constexpr float LOG2E = 1.4426950408889634f;
+
+enum SimMode { SIM_SCORES = 0, SIM_ROWSUM = 1, SIM_GRAD = 2 };
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem], bf16 inputs, fp32 accumulate; issued by ONE thread
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, bool accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"((uint32_t)accumulate)
+        : "memory");
+}
+// mbarrier arrives once every MMA issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Shared-memory matrix descriptors (sm_100 format: version 1 at bit 46, layout type at [61,64), SWIZZLE_128B = 2).
+// K-major operand stored as [rows][64 bf16] 128-byte rows, 8-row groups 1024 B apart (SBO); LBO unused.
+__device__ __forceinline__ uint64_t desc_kmajor_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// MN-major operand: 64 contiguous bf16 along MN per 128-byte row, rows = K; 8-row (K) groups 1024 B apart (SBO),
+// next 64 elements along MN `lbo_bytes` away (LBO).
+__device__ __forceinline__ uint64_t desc_mnmajor_sw128(uint32_t saddr, uint32_t lbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor: fp32 accumulate (c_format=1 @4), bf16 A/B (=1 @7, @10), b_major @16, N>>3 @17, M>>4 @24
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool b_mn_major) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((b_mn_major ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) |
+           ((uint32_t)(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel
+// ------------------------------------------------------------------------------------------
+struct SimArgs {
+    int mode;
+    int R, C, D, Dp;              // rows of X, rows of Y, logical / padded (multiple of 64) feature width
+    int tiles_per_chunk, n_col_tiles;
+    float c1, c2;                 // exp2(s*c1 - c2) == exp((s - m)/T)
+    float alpha;                  // 1 / (2 B_total T)
+    long long diag_offset;        // the positive of row i is column i + diag_offset
+    const float* rowsum_x;        // [R]   (grad)
+    const float* rowsum_y;        // [C]   (grad)
+    float* out_part;              // rowsum: [chunks, R]; grad: [chunks, R, Dp]; scores: [R, C]
+    float* diag;                  // [R] (rowsum, nullable)
+};
+
+struct SimSmem {                  // offsets from the 1024-aligned base
+    int x, y, g, ry, bars, tmem_slot, total;
+};
+__host__ __device__ inline SimSmem sim_smem(int Dp, int mode) {
+    SimSmem s;
+    const int nkb = Dp / ST_KB;
+    int o = 0;
+    s.x = o; o += nkb * KB_BYTES;
+    s.y = o; o += ST_STAGES * nkb * KB_BYTES;
+    s.g = o; o += mode == SIM_GRAD ? 2 * 2 * KB_BYTES : 0;
+    s.ry = o; o += 2 * ST_N * 4;
+    s.bars = o; o += 32 * 8;
+    s.tmem_slot = o; o += 16;
+    s.total = o + 1024;           // slack for the manual 1024-byte alignment
+    return s;
+}
+
+__global__ void __launch_bounds__(ST_THREADS, 1)
+simtile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_y, const SimArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const SimSmem L = sim_smem(a.Dp, a.mode);
+    const int nkb = a.Dp / ST_KB;
+    uint8_t* Xs = sm + L.x;
+    uint8_t* Ys = sm + L.y;
+    uint8_t* Gs = sm + L.g;
+    float* sm_ry = reinterpret_cast<float*>(sm + L.ry);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L.bars);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + L.tmem_slot);
+    uint64_t *x_full = bars + 0, *y_full = bars + 1, *y_empty = bars + 1 + ST_STAGES;
+    uint64_t *s_full = bars + 8, *s_empty = bars + 10, *g_full = bars + 12, *g_empty = bars + 14, *acc_full = bars + 16;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row0 = blockIdx.x * ST_M;
+    const int tile0 = blockIdx.y * a.tiles_per_chunk;
+    const int n_tiles = max(0, min(a.tiles_per_chunk, a.n_col_tiles - tile0));
+    const bool grad = a.mode == SIM_GRAD;
+
+    if (threadIdx.x == 0) {
+        mbar_init(x_full, 1);
+        for (int s = 0; s < ST_STAGES; ++s) { mbar_init(y_full + s, 1); mbar_init(y_empty + s, 1); }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(s_full + b, 1); mbar_init(s_empty + b, 128);
+            mbar_init(g_full + b, 128); mbar_init(g_empty + b, 1);
+        }
+        mbar_init(acc_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm_x); tma_prefetch_desc(&tm_y); }
+    const uint32_t tmem_cols = grad ? 512 : 256;      // 2 S buffers (+ the dX accumulator in grad mode)
+    if (warp == 2) tmem_alloc(tmem_slot, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_s0 = tmem_base, tmem_acc = tmem_base + 256;     // S buffers at columns 0 / 128, dX at 256
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            mbar_expect_tx(x_full, nkb * KB_BYTES);
+            for (int kb = 0; kb < nkb; ++kb) tma_load_2d(Xs + kb * KB_BYTES, &tm_x, x_full, kb * ST_KB, row0);
+            for (int t = 0; t < n_tiles; ++t) {
+                const int s = t % ST_STAGES;
+                mbar_wait(y_empty + s, ((t / ST_STAGES) & 1) ^ 1);
+                mbar_expect_tx(y_full + s, nkb * KB_BYTES);
+                for (int kb = 0; kb < nkb; ++kb)
+                    tma_load_2d(Ys + (s * nkb + kb) * KB_BYTES, &tm_y, y_full + s, kb * ST_KB, (tile0 + t) * ST_N);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc1 = make_idesc(ST_M, ST_N, false);
+            const uint32_t idesc2 = make_idesc(ST_M, a.Dp, true);
+            const uint32_t xs = smem_u32(Xs), ys = smem_u32(Ys), gs = smem_u32(Gs);
+            mbar_wait(x_full, 0);
+            for (int t = 0; t <= n_tiles; ++t) {
+                if (t < n_tiles) {                     // GEMM 1: S[b] = X . Y_t^T
+                    const int s = t % ST_STAGES, b = t & 1;
+                    mbar_wait(y_full + s, (t / ST_STAGES) & 1);
+                    mbar_wait(s_empty + b, ((t >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t yb = ys + s * nkb * KB_BYTES;
+                    for (int ks = 0; ks < a.Dp / 16; ++ks) {
+                        const uint32_t off = (ks >> 2) * KB_BYTES + (ks & 3) * 32;
+                        umma_bf16(tmem_s0 + b * ST_N, desc_kmajor_sw128(xs + off), desc_kmajor_sw128(yb + off), idesc1,
+                                  ks > 0);
+                    }
+                    umma_commit(s_full + b);
+                    if (!grad) umma_commit(y_empty + s);
+                }
+                if (grad && t >= 1) {                  // GEMM 2: dX += G_u . Y_u   (u = t - 1)
+                    const int u = t - 1, s = u % ST_STAGES, g = u & 1;
+                    mbar_wait(g_full + g, (u >> 1) & 1);
+                    tc_fence_after();
+                    const uint32_t yb = ys + s * nkb * KB_BYTES, gb = gs + g * 2 * KB_BYTES;
+                    for (int ks = 0; ks < ST_N / 16; ++ks) {
+                        const uint32_t aoff = (ks >> 2) * KB_BYTES + (ks & 3) * 32;    // K (= j) inside G, K-major
+                        const uint32_t boff = ks * 16 * 128;                           // 16 rows (j) of Y, MN-major
+                        umma_bf16(tmem_acc, desc_kmajor_sw128(gb + aoff), desc_mnmajor_sw128(yb + boff, KB_BYTES),
+                                  idesc2, u > 0 || ks > 0);
+                    }
+                    umma_commit(g_empty + g);
+                    umma_commit(y_empty + s);
+                }
+            }
+            if (grad) umma_commit(acc_full);
+        }
+    } else {
+        // ===================== epilogue: thread <-> TMEM lane <-> row =====================
+        const int q = warp & 3;                        // TMEM lane quadrant this warp may access
+        const int r_loc = 32 * q + lane;
+        const long long row = (long long)row0 + r_loc;
+        const uint32_t lane_addr = (uint32_t)(32 * q) << 16;
+        const bool row_ok = row < a.R;
+        float racc = 0.f, dval = 0.f;
+        bool have_diag = false;
+        const float rx = (grad && row_ok) ? a.alpha / a.rowsum_x[row] : 0.f;
+        for (int t = 0; t < n_tiles; ++t) {
+            const int b = t & 1;
+            const int j0 = (tile0 + t) * ST_N;
+            if (grad) {
+                mbar_wait(g_empty + b, ((t >> 1) & 1) ^ 1);            // G[b] no longer read by GEMM 2 of tile t-2
+                const int col = j0 + r_loc;
+                sm_ry[b * ST_N + r_loc] = col < a.C ? a.alpha / a.rowsum_y[col] : 0.f;
+                named_bar_sync(1, 128);
+            }
+            mbar_wait(s_full + b, (t >> 1) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                float v[32];
+                tmem_ld32(tmem_s0 + b * ST_N + c * 32 + lane_addr, v);
+                const int jc = j0 + c * 32;
+                if (a.mode == SIM_SCORES) {
+                    if (row_ok)
+                        for (int i = 0; i < 32; ++i)
+                            if (jc + i < a.C) a.out_part[row * a.C + jc + i] = v[i];
+                } else if (a.mode == SIM_ROWSUM) {
+                    const long long dcol = row + a.diag_offset;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float e = exp2f(fmaf(v[i], a.c1, -a.c2));
+                        racc += (jc + i < a.C) ? e : 0.f;
+                        if (jc + i == dcol) { dval = v[i]; have_diag = true; }
+                    }
+                } else {
+                    // the positive pair (column row + diag_offset) is left out of the bf16 G tile: its weight is
+                    // O(1/B) while every other entry is O(1/B^2), so it is added in fp32 by the finalize kernel
+                    const long long dcol = row + a.diag_offset;
+                    uint32_t packed[16];
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2) {
+                        float e0 = exp2f(fmaf(v[i], a.c1, -a.c2)), e1 = exp2f(fmaf(v[i + 1], a.c1, -a.c2));
+                        float g0 = (jc + i < a.C && jc + i != dcol) ? e0 * (rx + sm_ry[b * ST_N + c * 32 + i]) : 0.f;
+                        float g1 = (jc + i + 1 < a.C && jc + i + 1 != dcol) ? e1 * (rx + sm_ry[b * ST_N + c * 32 + i + 1]) : 0.f;
+                        __nv_bfloat162 h = __floats2bfloat162_rn(g0, g1);
+                        packed[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
+                    }
+                    // G[b] is the K-major SW128 A operand of GEMM 2: row r_loc, columns c*32 .. c*32+31
+                    uint8_t* grow = Gs + (b * 2 + (c >> 1)) * KB_BYTES + r_loc * 128;
+#pragma unroll
+                    for (int h4 = 0; h4 < 4; ++h4) {
+                        const int chunk = (c & 1) * 4 + h4;                      // 16-byte chunk inside the 128-byte row
+                        uint4 val = make_uint4(packed[4 * h4], packed[4 * h4 + 1], packed[4 * h4 + 2], packed[4 * h4 + 3]);
+                        *reinterpret_cast<uint4*>(grow + ((chunk ^ (r_loc & 7)) << 4)) = val;
+                    }
+                }
+            }
+            tc_fence_before();
+            if (grad) {
+                fence_proxy_async();                   // generic-proxy smem writes -> visible to the tensor core
+                mbar_arrive(g_full + b);
+            }
+            mbar_arrive(s_empty + b);
+        }
+        if (a.mode == SIM_ROWSUM) {
+            if (row_ok) {
+                a.out_part[(long long)blockIdx.y * a.R + row] = racc;
+                if (a.diag && have_diag) a.diag[row] = dval;
+            }
+        } else if (grad) {
+            if (n_tiles > 0) {
+                mbar_wait(acc_full, 0);
+                tc_fence_after();
+            }
+            for (int c = 0; c < a.Dp / 32; ++c) {
+                float v[32];
+                if (n_tiles > 0) tmem_ld32(tmem_acc + c * 32 + lane_addr, v);
+                else
+                    for (int i = 0; i < 32; ++i) v[i] = 0.f;
+                if (row_ok) {
+                    float4* dst = reinterpret_cast<float4*>(a.out_part + ((long long)blockIdx.y * a.R + row) * a.Dp + c * 32);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                }
+            }
+            tc_fence_before();
+        }
+    }
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// small helper kernels
+// ------------------------------------------------------------------------------------------
+__global__ void pack_rows_bf16_kernel(const float* __restrict__ in, long long R, int D, int Dp, __nv_bfloat16* __restrict__ out) {
+    const long long total = R * (Dp / 2);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long r = i / (Dp / 2);
+        int c = (int)(i - r * (Dp / 2)) * 2;
+        float a = c < D ? in[r * D + c] : 0.f, b = c + 1 < D ? in[r * D + c + 1] : 0.f;
+        reinterpret_cast<__nv_bfloat162*>(out)[i] = __floats2bfloat162_rn(a, b);
+    }
+}
+
+__global__ void rowsum_finalize_kernel(const float* __restrict__ part, int chunks, int R, float* __restrict__ out) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < R; i += gridDim.x * blockDim.x) {
+        float s = 0.f;
+        for (int c = 0; c < chunks; ++c) s += part[(long long)c * R + i];
+        out[i] = s;
+    }
+}
+
+// dX[r, d] = g_loss * ( sum_chunks part[c][r][d] + (g_rr - 1/(B T)) * y[r + off][d] ),
+// g_rr = alpha * exp((s_rr - 1)/T) * (1/rowsum_x[r] + 1/rowsum_y[r + off]) : the positive pair, kept in fp32
+__global__ void grad_finalize_kernel(const float* __restrict__ part, int chunks, int R, int D, int Dp, int C,
+                                     const __nv_bfloat16* __restrict__ y, long long diag_offset, float diag_coef,
+                                     float alpha, float c1, const float* __restrict__ diag,
+                                     const float* __restrict__ rowsum_x, const float* __restrict__ rowsum_y,
+                                     const float* __restrict__ g_loss, float* __restrict__ dx) {
+    const float gl = g_loss ? g_loss[0] : 1.f;
+    const long long total = (long long)R * D;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long r = i / D;
+        int d = (int)(i - r * D);
+        float s = 0.f;
+        for (int c = 0; c < chunks; ++c) s += part[((long long)c * R + r) * Dp + d];
+        long long j = r + diag_offset;
+        if (j >= 0 && j < C) {
+            const float g_rr = alpha * exp2f((diag[r] - 1.f) * c1) * (1.f / rowsum_x[r] + 1.f / rowsum_y[j]);
+            s += (g_rr - diag_coef) * __bfloat162float(y[j * Dp + d]);
+        }
+        dx[i] = gl * s;
+    }
+}
+
+// loss = 1/(2 Bt) * sum_i [ log R_i + log C_i + 2 m - 2 s_ii / T ]   (single CTA, fixed order)
+__global__ void infonce_loss_kernel(const float* __restrict__ rs_row, const float* __restrict__ rs_col,
+                                    const float* __restrict__ diag, int n, float inv_T, float inv_2B, float* loss) {
+    __shared__ float red[32];
+    float s = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+        s += logf(rs_row[i]) + logf(rs_col[i]) + 2.f * inv_T - 2.f * diag[i] * inv_T;
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+        loss[0] = t * inv_2B;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// 2-D bf16 tensor [rows, Dp] row-major, box = [64 elements, 128 rows], 128-byte swizzle, OOB rows read as zero
+static int make_tmap(CUtensorMap* tm, const void* base, long long rows, int Dp) {
+    EncodeTiledFn fn = encode_fn();
+    CFM_REQUIRE(fn, CFM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    CFM_REQUIRE(((uintptr_t)base & 15) == 0, CFM_ERR_INVALID, "bf16 operand must be 16-byte aligned");
+    // The encode call is a driver-API entry point: make sure this thread (e.g. an autograd worker) has the
+    // device's primary context current, which runtime calls only do lazily.
+    int dev = 0;
+    CFM_CHECK_CUDA(cudaGetDevice(&dev));
+    CFM_CHECK_CUDA(cudaSetDevice(dev));
+    cuuint64_t dims[2] = {(cuuint64_t)Dp, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)Dp * 2};
+    cuuint32_t box[2] = {ST_KB, ST_M};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CFM_REQUIRE(r == CUDA_SUCCESS, CFM_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d", (int)r);
+    return CFM_OK;
+}
+
+// column chunks per row block: enough CTAs to fill the GPU ~3x, never more chunks than column tiles
+static int sim_chunks(long long R, long long C) {
+    const long long row_blocks = (R + ST_M - 1) / ST_M, col_tiles = (C + ST_N - 1) / ST_N;
+    long long want = (3LL * sm_count() + row_blocks - 1) / row_blocks;
+    want = std::max(1LL, std::min(want, std::min(col_tiles, 16LL)));
+    return (int)want;
+}
+
+static int launch_sim(SimArgs a, const void* x, const void* y, int chunks, cudaStream_t stream) {
+    CFM_REQUIRE(a.Dp % 64 == 0 && a.Dp >= 64 && a.Dp <= 128, CFM_ERR_UNSUPPORTED,
+                "padded feature width %d not in {64,128}", a.Dp);
+    CFM_REQUIRE(a.R >= 1 && a.C >= 1, CFM_ERR_INVALID, "empty operand");
+    CUtensorMap tmx, tmy;
+    int rc = make_tmap(&tmx, x, a.R, a.Dp);
+    if (rc) return rc;
+    rc = make_tmap(&tmy, y, a.C, a.Dp);
+    if (rc) return rc;
+    a.n_col_tiles = (a.C + ST_N - 1) / ST_N;
+    a.tiles_per_chunk = (a.n_col_tiles + chunks - 1) / chunks;
+    const SimSmem L = sim_smem(a.Dp, a.mode);
+    static bool attr = false;
+    if (!attr) {
+        CFM_CHECK_CUDA(cudaFuncSetAttribute(simtile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr = true;
+    }
+    dim3 grid((a.R + ST_M - 1) / ST_M, chunks);
+    simtile_kernel<<<grid, ST_THREADS, L.total, stream>>>(tmx, tmy, a);
+    CFM_LAUNCH_CHECK();
+    return CFM_OK;
+}
+
+}  // namespace cfm
+
+using namespace cfm;
+
+extern "C" int64_t cfm_simtile_chunks(int64_t R, int64_t C) { return sim_chunks(R, C); }
+
+extern "C" int cfm_pack_rows_bf16(const float* in, int64_t R, int64_t D, int64_t Dp, void* out_bf16, void* stream) {
+    CFM_REQUIRE(in && out_bf16 && R >= 0 && D >= 1 && Dp >= D && Dp % 2 == 0, CFM_ERR_INVALID, "bad pack arguments");
+    if (R == 0) return CFM_OK;
+    const long long total = R * (Dp / 2);
+    pack_rows_bf16_kernel<<<(int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
+        in, R, (int)D, (int)Dp, (__nv_bfloat16*)out_bf16);
+    CFM_LAUNCH_CHECK();
+    return CFM_OK;
+}
+
+extern "C" int cfm_simtile_scores(const void* x_bf16, const void* y_bf16, int64_t R, int64_t C, int64_t Dp, float* out,
+                                  void* stream) {
+    CFM_REQUIRE(x_bf16 && y_bf16 && out, CFM_ERR_INVALID, "null pointer");
+    SimArgs a{};
+    a.mode = SIM_SCORES; a.R = (int)R; a.C = (int)C; a.D = (int)Dp; a.Dp = (int)Dp; a.out_part = out;
+    return launch_sim(a, x_bf16, y_bf16, 1, (cudaStream_t)stream);
+}
+
+extern "C" int cfm_infonce_rowsum(const void* x_bf16, const void* y_bf16, int64_t R, int64_t C, int64_t Dp,
+                                  double temperature, int64_t diag_offset, float* rowsum, float* diag, float* part,
+                                  void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CFM_REQUIRE(x_bf16 && y_bf16 && rowsum && part && temperature > 0, CFM_ERR_INVALID, "bad rowsum arguments");
+    const int chunks = sim_chunks(R, C);
+    SimArgs a{};
+    a.mode = SIM_ROWSUM; a.R = (int)R; a.C = (int)C; a.D = (int)Dp; a.Dp = (int)Dp;
+    a.c1 = (float)(LOG2E / temperature); a.c2 = (float)(LOG2E / temperature);
+    a.diag_offset = diag_offset; a.out_part = part; a.diag = diag;
+    ProfScope prof(PROF_NCE_ROWSUM, stream);
+    int rc = launch_sim(a, x_bf16, y_bf16, chunks, stream);
+    if (rc) return rc;
+    rowsum_finalize_kernel<<<(int)std::min<long long>((R + 255) / 256, 592), 256, 0, stream>>>(part, chunks, (int)R, rowsum);
+    CFM_LAUNCH_CHECK();
+    return CFM_OK;
+}
+
+extern "C" int cfm_infonce_grad(const void* x_bf16, const void* y_bf16, int64_t R, int64_t C, int64_t D, int64_t Dp,
+                                double temperature, int64_t diag_offset, int64_t B_total, const float* rowsum_x,
+                                const float* rowsum_y, const float* diag, const float* g_loss, float* dx, float* part,
+                                void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CFM_REQUIRE(x_bf16 && y_bf16 && rowsum_x && rowsum_y && diag && dx && part && temperature > 0 && B_total >= 1 && D <= Dp,
+                CFM_ERR_INVALID, "bad grad arguments");
+    const int chunks = sim_chunks(R, C);
+    SimArgs a{};
+    a.mode = SIM_GRAD; a.R = (int)R; a.C = (int)C; a.D = (int)D; a.Dp = (int)Dp;
+    a.c1 = (float)(LOG2E / temperature); a.c2 = (float)(LOG2E / temperature);
+    a.alpha = (float)(1.0 / (2.0 * (double)B_total * temperature));
+    a.diag_offset = diag_offset; a.rowsum_x = rowsum_x; a.rowsum_y = rowsum_y; a.out_part = part;
+    ProfScope prof(PROF_NCE_GRAD, stream);
+    int rc = launch_sim(a, x_bf16, y_bf16, chunks, stream);
+    if (rc) return rc;
+    const long long total = R * D;
+    grad_finalize_kernel<<<(int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, stream>>>(
+        part, chunks, (int)R, (int)D, (int)Dp, (int)C, (const __nv_bfloat16*)y_bf16, diag_offset,
+        (float)(1.0 / ((double)B_total * temperature)), a.alpha, a.c1, diag, rowsum_x, rowsum_y, g_loss, dx);
+    CFM_LAUNCH_CHECK();
+    return CFM_OK;
+}
+
+extern "C" int cfm_infonce_loss(const float* rowsum_row, const float* rowsum_col, const float* diag, int64_t n,
+                                double temperature, int64_t B_total, float* loss, void* stream) {
+    CFM_REQUIRE(rowsum_row && rowsum_col && diag && loss && n >= 1, CFM_ERR_INVALID, "bad loss arguments");
+    infonce_loss_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(rowsum_row, rowsum_col, diag, (int)n, (float)(1.0 / temperature),
+                                                             (float)(1.0 / (2.0 * (double)B_total)), loss);
+    CFM_LAUNCH_CHECK();
+    return CFM_OK;
+}

@@ -168,18 +168,31 @@ int cfm_structural_head(const float* c_logits, const float* f_logits, const floa
                         float* partial /* >= 1024 floats */, void* stream);
 
 /* ------------------------------------------------------------------------------------------
- * InfoNCE (tcgen05/TMEM).  rows/cols are bf16 [R,D] / [C,D] unit vectors (D multiple of 16, <= 256).
- * replaces: contrastive.py:129-138 (torch.mm + 2x F.cross_entropy) and its autograd.
- * cfm_infonce_rowsum: out[i] = sum_j exp((x_i . y_j - 1)/T)   (fixed max 1/T, valid for unit vectors)
- *                     diag[i] = x_i . y_(i + diag_offset)      (fp32 accumulate)  (nullable)
- * cfm_infonce_grad:   dX[i] = 1/(2 B T) * sum_j E_ij (1/rowsum_x[i] + 1/rowsum_y[j]) y_j - 1/(B T) y_(i+diag_offset)
- * The symmetric loss and both gradients are two calls each with (X,Y) swapped; S is never written to HBM.
+ * InfoNCE (tcgen05 / TMEM / TMA).  Operands are bf16 row-major [rows, Dp], Dp in {64, 128} (features zero-padded
+ * by cfm_pack_rows_bf16), rows of unit L2 norm (what contrastive.py:96-97 feeds info_nce_loss).
+ * replaces: contrastive.py:129-138 (torch.mm + 2x F.cross_entropy) and its autograd; S is never written to HBM.
+ *   cfm_infonce_rowsum: rowsum[i] = sum_j exp((x_i . y_j - 1)/T)  (fixed maximum 1/T), diag[i] = x_i . y_(i+diag_offset)
+ *   cfm_infonce_loss:   loss = 1/(2 B_total) sum_i [log R_i + log C_i + 2/T - 2 diag_i/T]   over the n local rows
+ *   cfm_infonce_grad:   dX[i] = g_loss * ( 1/(2 B T) sum_j E_ij (1/rowsum_x[i] + 1/rowsum_y[j]) y_j - y_(i+off)/(B T) )
+ * The symmetric loss needs two rowsum calls and both gradients two grad calls, each with (X, Y) swapped.
+ * `part` is scratch of cfm_simtile_chunks(R, C) * R floats (rowsum) or * R * Dp floats (grad).
  * ------------------------------------------------------------------------------------------ */
-int cfm_infonce_rowsum(const void* x_bf16, const void* y_bf16, int64_t R, int64_t C, int64_t D, double temperature,
-                       int64_t diag_offset, float* rowsum, float* diag, void* stream);
-int cfm_infonce_grad(const void* x_bf16, const void* y_bf16, int64_t R, int64_t C, int64_t D, double temperature,
-                     int64_t diag_offset, int64_t B_total, const float* rowsum_x /* [R] */,
-                     const float* rowsum_y /* [C] */, float* dx /* [R,D] f32 */, void* stream);
+int64_t cfm_simtile_chunks(int64_t R, int64_t C);
+int cfm_pack_rows_bf16(const float* in /* [R,D] */, int64_t R, int64_t D, int64_t Dp, void* out_bf16 /* [R,Dp] */,
+                       void* stream);
+int cfm_infonce_rowsum(const void* x_bf16, const void* y_bf16, int64_t R, int64_t C, int64_t Dp, double temperature,
+                       int64_t diag_offset, float* rowsum /* [R] */, float* diag /* [R] nullable */, float* part,
+                       void* stream);
+int cfm_infonce_loss(const float* rowsum_row, const float* rowsum_col, const float* diag, int64_t n,
+                     double temperature, int64_t B_total, float* loss /* [1] */, void* stream);
+int cfm_infonce_grad(const void* x_bf16, const void* y_bf16, int64_t R, int64_t C, int64_t D, int64_t Dp,
+                     double temperature, int64_t diag_offset, int64_t B_total, const float* rowsum_x /* [R] */,
+                     const float* rowsum_y /* [C] */, const float* diag /* [R] from cfm_infonce_rowsum */,
+                     const float* g_loss /* device scalar, nullable = 1 */,
+                     float* dx /* [R,D] f32 */, float* part, void* stream);
+/* parity/debug aid: the raw fp32 score tile S = X . Y^T written out as [R, C] */
+int cfm_simtile_scores(const void* x_bf16, const void* y_bf16, int64_t R, int64_t C, int64_t Dp, float* out,
+                       void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * All-pairs scoring with streaming top-k (tcgen05/TMEM filter pass in bf16 + exact fp32 rescoring).

@@ -1,0 +1,92 @@
+"""GPU parity of the tcgen05 similarity-tile kernels: raw score tiles, InfoNCE loss and gradients against the
+reference's golden vectors and the CPU oracle.  bf16 operands, fp32 accumulation -> tolerance 1e-3 (north_star)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+import oracle
+from helpers import assert_close_scaled, load_golden, t
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _unit(R, D, seed):
+    g = torch.Generator().manual_seed(seed)
+    return F.normalize(torch.randn(R, D, generator=g), dim=1)
+
+
+@pytest.mark.parametrize("R,C,D", [(128, 128, 64), (200, 333, 128), (33, 70, 30), (1000, 517, 60), (4096, 1024, 128)])
+def test_score_tiles_match_matmul(R, C, D):
+    """S = X . Y^T through TMA -> smem descriptors -> tcgen05.mma -> TMEM -> tcgen05.ld, incl. ragged edges."""
+    from ceo_firm_matching import ops
+    x, y = _unit(R, D, 1), _unit(C, D, 2)
+    xb, yb = ops.pack_bf16(x.to(DEV)), ops.pack_bf16(y.to(DEV))
+    s = ops.simtile_scores(xb, yb)
+    ref = xb.float().cpu()[:, :D].double() @ yb.float().cpu()[:, :D].double().t()      # same bf16-rounded operands
+    assert_close_scaled(s, ref, 2e-6, f"scores {R}x{C}x{D}", floor=1e-6)              # only fp32 accumulation order
+
+
+@pytest.mark.parametrize("name", ["infonce_b33_d30", "infonce_b200_d128"])
+def test_loss_and_grads_match_reference_golden(name):
+    from ceo_firm_matching.contrastive import info_nce_loss
+    g = load_golden(name)
+    f = t(g["firm_proj"]).to(DEV).requires_grad_(True)
+    c = t(g["ceo_proj"]).to(DEV).requires_grad_(True)
+    loss = info_nce_loss(f, c, float(g["temperature"]))
+    loss.backward()
+    assert loss.shape == ()
+    assert float(loss) == pytest.approx(float(g["loss"]), rel=1e-3)
+    assert_close_scaled(f.grad, g["d_firm"], 4e-3, "d_firm")      # bf16 operands: 2^-9 relative per element
+    assert_close_scaled(c.grad, g["d_ceo"], 4e-3, "d_ceo")
+
+
+@pytest.mark.parametrize("B,D", [(2, 16), (127, 64), (129, 100), (640, 128), (4096, 128)])
+def test_loss_and_grads_vs_oracle(B, D):
+    from ceo_firm_matching.contrastive import info_nce_loss
+    f0, c0 = _unit(B, D, 10 + B), _unit(B, D, 20 + B)
+    # make positives actually similar so the diagonal terms matter
+    c0 = F.normalize(0.6 * f0 + 0.8 * c0, dim=1)
+    f = f0.to(DEV).requires_grad_(True)
+    c = c0.to(DEV).requires_grad_(True)
+    loss = info_nce_loss(f, c, 0.07)
+    (3.0 * loss).backward()                                        # non-unit upstream gradient
+    # oracle on the SAME bf16-rounded operands isolates kernel error from input quantisation
+    fq = f0.bfloat16().float().requires_grad_(True)
+    cq = c0.bfloat16().float().requires_grad_(True)
+    lo = oracle.info_nce(fq, cq, 0.07)
+    (3.0 * lo).backward()
+    assert float(loss) == pytest.approx(float(lo), rel=2e-5, abs=1e-5)
+    assert_close_scaled(f.grad, fq.grad, 6e-3, "d_firm")           # G is re-staged as bf16 for the second GEMM
+    assert_close_scaled(c.grad, cq.grad, 6e-3, "d_ceo")
+    # and against the un-quantised fp32 reference at the bf16 tolerance the north star states
+    lf = oracle.info_nce(f0, c0, 0.07)
+    assert float(loss) == pytest.approx(float(lf), rel=1e-3)
+
+
+def test_b1_returns_zero():
+    from ceo_firm_matching.contrastive import info_nce_loss
+    assert float(info_nce_loss(torch.ones(1, 8, device=DEV), torch.ones(1, 8, device=DEV))) == 0.0
+
+
+def test_rectangular_rowsum_with_offset():
+    """Global-negatives building block: a rank's row block against all columns, positives at i + offset."""
+    from ceo_firm_matching import ops
+    x, y = _unit(300, 128, 5), _unit(1500, 128, 6)
+    xb, yb = ops.pack_bf16(x.to(DEV)), ops.pack_bf16(y.to(DEV))
+    rs, diag = ops.infonce_rowsum(xb, yb, 0.07, diag_offset=600)
+    s = xb.float().cpu().double() @ yb.float().cpu().double().t()
+    assert_close_scaled(rs, torch.exp((s - 1) / 0.07).sum(1), 2e-5, "rowsum")
+    assert_close_scaled(diag, s[torch.arange(300), torch.arange(300) + 600], 2e-6, "diag", floor=1e-6)
+
+
+def test_deterministic():
+    from ceo_firm_matching.contrastive import info_nce_loss
+    f0, c0 = _unit(1000, 128, 1).to(DEV), _unit(1000, 128, 2).to(DEV)
+    outs = []
+    for _ in range(2):
+        f, c = f0.clone().requires_grad_(True), c0.clone().requires_grad_(True)
+        loss = info_nce_loss(f, c, 0.07)
+        loss.backward()
+        outs.append((loss.clone(), f.grad.clone(), c.grad.clone()))
+    assert all(torch.equal(a, b) for a, b in zip(*outs))

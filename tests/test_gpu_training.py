@@ -11,7 +11,7 @@ import torch
 from torch.utils.data import DataLoader
 
 import oracle
-from helpers import assert_close_scaled, check_grads, load_into
+from helpers import assert_close_scaled, check_grads, dead_bias_names, load_into
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -132,8 +132,12 @@ def test_train_model_follows_oracle_trajectory(monkeypatch):
         first_epoch = tot / 4 if first_epoch is None else first_epoch
     assert printed == pytest.approx(first_epoch, rel=2e-4, abs=1e-4)
     sd = model.state_dict()
+    # Biases that feed a train-mode BatchNorm have a mathematically zero gradient; Adam turns the rounding noise
+    # of either implementation into +-lr random walks, and BN cancels them again: not comparable, not relevant.
+    dead = dead_bias_names(model.train())
     for k in names:
-        assert_close_scaled(sd[k], p[k].detach(), 2e-3, "trained " + k, floor=1e-5)
+        if k not in dead:
+            assert_close_scaled(sd[k], p[k].detach(), 2e-3, "trained " + k, floor=1e-5)
     assert int(sd["firm_tower.1.num_batches_tracked"]) == 12
 
 
