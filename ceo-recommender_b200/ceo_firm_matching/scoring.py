@@ -1,0 +1,111 @@
+"""All-pairs CEO x firm scoring with top-k — the public helper the reference's scattered scoring sites map to
+(``analytical_extensions.py:467-483``, ``contrastive.py:296-322``, ``deep_dive.py:277-290`` ...): they all form
+``scores = rows @ cols.T * scale`` and then rank every row.  Here the score matrix is never materialised: a
+tcgen05/TMEM pass over bf16 copies streams the tiles through a per-row candidate filter, and the surviving
+candidates are rescored exactly (fp64 accumulation of the fp32 operands), so the emitted index lists equal the
+exact ranking of the fp32 inputs ordered (score desc, index asc).
+"""
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _native as N
+from . import ops
+
+MAX_K = 128
+
+
+def _exact_rows(rows: torch.Tensor, cols: torch.Tensor, k: int, scale: float, col_offset: int,
+                chunk: int = 65536) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Exact path for the (rare) rows whose candidate set could not be proven complete: fp64 scores, stable
+    ordering.  Plain torch ops on the device; only ever sees flagged rows."""
+    r64 = rows.double()
+    best_s = torch.full((rows.shape[0], 0), 0.0, dtype=torch.float64, device=rows.device)
+    best_i = torch.zeros((rows.shape[0], 0), dtype=torch.int64, device=rows.device)
+    for c0 in range(0, cols.shape[0], chunk):
+        s = r64 @ cols[c0:c0 + chunk].double().t()
+        idx = torch.arange(c0, c0 + s.shape[1], device=rows.device).expand_as(s)
+        s, idx = torch.cat([best_s, s], 1), torch.cat([best_i, idx], 1)
+        order = torch.argsort(-s, dim=1, stable=True)[:, :k]          # earlier (smaller) index wins a tie
+        best_s, best_i = torch.gather(s, 1, order), torch.gather(idx, 1, order)
+    return (best_s * scale).float(), best_i + col_offset
+
+
+def score_topk(rows: torch.Tensor, cols: torch.Tensor, k: int, scale: float = 1.0, col_offset: int = 0,
+               return_flags: bool = False):
+    """Top-``k`` columns of ``rows @ cols.T * scale`` for every row.
+
+    rows [R, D], cols [C, D] float32 on the device (unit-norm tower outputs in the reference's call sites; any
+    norm is handled, the filter margin scales with the largest row norms).  Returns ``(scores [R,k] f32,
+    indices [R,k] i64)`` ordered by (score desc, index asc); if ``C < k`` the tail is ``(-inf, -1)``.
+    Orientation is the caller's choice: pass firms as rows to rank CEOs per firm (analytical_extensions.py:483)
+    or CEOs as rows for "top-100 firms per CEO" (BASELINE config 5).
+    """
+    ops._require_cuda(rows, cols)
+    if not 1 <= k <= MAX_K:
+        raise ValueError(f"k must be in [1, {MAX_K}]")
+    rows, cols = rows.detach().float().contiguous(), cols.detach().float().contiguous()
+    R, D = rows.shape
+    C = cols.shape[0]
+    if cols.shape[1] != D:
+        raise ValueError("rows and cols must have the same feature width")
+    dev = rows.device
+    out_s = torch.empty(R, k, device=dev)
+    out_i = torch.empty(R, k, dtype=torch.int64, device=dev)
+    if R == 0:
+        return (out_s, out_i, torch.zeros(0, dtype=torch.int32, device=dev)) if return_flags else (out_s, out_i)
+    if C == 0:
+        out_s.fill_(float("-inf")); out_i.fill_(-1)
+        return (out_s, out_i, torch.zeros(R, dtype=torch.int32, device=dev)) if return_flags else (out_s, out_i)
+    rb, cb = ops.pack_bf16(rows), ops.pack_bf16(cols)
+    # |bf16-operand score - exact score| <= 2^-8 |row||col| (Cauchy-Schwarz over the per-element roundings), twice
+    # that separates "certainly in" from "certainly out"; the tiny extra covers fp32 accumulation
+    margin = float((2.0 ** -7 + 2.0 ** -16) * rows.norm(dim=1).max() * cols.norm(dim=1).max())
+    chunks = N.lib().cfm_simtile_chunks(R, C)
+    rpad = (R + 127) // 128 * 128
+    cand_val = torch.empty(chunks * rpad * N.CFM_TOPK_CAP, device=dev)
+    cand_idx = torch.empty(chunks * rpad * N.CFM_TOPK_CAP, dtype=torch.int32, device=dev)
+    cand_cnt = torch.empty(chunks * rpad, dtype=torch.int32, device=dev)
+    cand_thr = torch.empty(chunks * rpad, device=dev)
+    flags = torch.empty(R, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        N.check(N.lib().cfm_allpairs_topk(N.ptr(rows), N.ptr(cols), N.ptr(rb), N.ptr(cb), R, C, D, rb.shape[1], k,
+                                          float(scale), margin, col_offset, N.ptr(out_s), N.ptr(out_i), N.ptr(flags),
+                                          N.ptr(cand_val), N.ptr(cand_idx), N.ptr(cand_cnt), N.ptr(cand_thr),
+                                          N.stream_ptr()))
+    bad = torch.nonzero(flags, as_tuple=False).flatten()
+    if bad.numel():                                   # completeness not provable from the filter: redo exactly
+        s, i = _exact_rows(rows[bad], cols, k, float(scale), col_offset)
+        out_s[bad, :s.shape[1]], out_i[bad, :i.shape[1]] = s, i
+    return (out_s, out_i, flags) if return_flags else (out_s, out_i)
+
+
+def merge_topk(part_scores: torch.Tensor, part_indices: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Merge per-shard results ``[n_parts, R, k]`` (each ordered (score desc, index asc), indices already global)
+    into the global top-k with the same ordering — the cross-GPU merge of the row-sharded scoring path."""
+    ops._require_cuda(part_scores, part_indices)
+    n_parts, R, k = part_scores.shape
+    ps, pi = part_scores.float().contiguous(), part_indices.long().contiguous()
+    out_s = torch.empty(R, k, device=ps.device)
+    out_i = torch.empty(R, k, dtype=torch.int64, device=ps.device)
+    with torch.cuda.device(ps.device):
+        N.check(N.lib().cfm_topk_merge(N.ptr(ps), N.ptr(pi), n_parts, R, k, N.ptr(out_s), N.ptr(out_i), N.stream_ptr()))
+    return out_s, out_i
+
+
+def target_ranks(rows: torch.Tensor, cols: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    """1-indexed rank of column ``target[i]`` among all columns for row i (fp64 scores of the fp32 operands)."""
+    ops._require_cuda(rows, cols, target)
+    rows, cols = rows.detach().float().contiguous(), cols.detach().float().contiguous()
+    target = target.long().contiguous()
+    rank = torch.empty(rows.shape[0], dtype=torch.int64, device=rows.device)
+    with torch.cuda.device(rows.device):
+        N.check(N.lib().cfm_allpairs_rank(N.ptr(rows), N.ptr(cols), rows.shape[0], cols.shape[0], rows.shape[1],
+                                          N.ptr(target), N.ptr(rank), N.stream_ptr()))
+    return rank
+
+
+def diagonal_ranks(firm_emb: torch.Tensor, ceo_emb: torch.Tensor) -> torch.Tensor:
+    """Rank of the true CEO (the diagonal) for every firm — contrastive.py:306-322 without the full sort."""
+    n = firm_emb.shape[0]
+    return target_ranks(firm_emb, ceo_emb, torch.arange(n, device=firm_emb.device))

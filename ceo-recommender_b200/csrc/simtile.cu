@@ -22,7 +22,11 @@ constexpr int ST_THREADS = 192;
 constexpr int KB_BYTES = ST_M * 128;                   // one [128 rows x 64 bf16] swizzled block = 16 KB
 constexpr float LOG2E = 1.4426950408889634f;
 
-enum SimMode { SIM_SCORES = 0, SIM_ROWSUM = 1, SIM_GRAD = 2 };
+enum SimMode { SIM_SCORES = 0, SIM_ROWSUM = 1, SIM_GRAD = 2, SIM_TOPK = 3 };
+
+// streaming top-k: per (row, column chunk) candidate buffer of TK_CAP entries; when it fills the warp keeps the
+// TK_KEEP best and raises the row's admission threshold
+constexpr int TK_KEEP = 192, TK_CAP = 384, TK_PER_LANE = TK_CAP / 32;
 
 // ------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -125,6 +129,76 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool b_mn_major)
 }
 
 // ------------------------------------------------------------------------------------------
+// streaming top-k helpers (epilogue of SIM_TOPK)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t float_key(float f) {      // order-preserving map float -> uint32
+    uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float key_float(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
+}
+
+__device__ __noinline__ void topk_append(float* bv, int* bi, int& cnt, float val, int col) {
+    bv[cnt] = val;
+    bi[cnt] = col;
+    ++cnt;
+}
+
+// Warp-cooperative: keep the TK_KEEP largest of the `n` entries of one row's buffer (ties at the cut are kept),
+// returns the new count and the new admission threshold (value of the TK_KEEP-th largest).
+__device__ void topk_compact(float* bv, int* bi, int n, int lane, int& new_cnt, float& new_thr) {
+    float val[TK_PER_LANE];
+    int idx[TK_PER_LANE];
+    uint32_t key[TK_PER_LANE];
+#pragma unroll
+    for (int e = 0; e < TK_PER_LANE; ++e) {
+        int p = e * 32 + lane;
+        bool ok = p < n;
+        val[e] = ok ? bv[p] : 0.f;
+        idx[e] = ok ? bi[p] : 0;
+        key[e] = ok ? float_key(val[e]) : 0u;          // key 0 is below every real float key
+    }
+    __syncwarp();
+    // largest t with #{key >= t} >= TK_KEEP, by bisection over the 32 key bits
+    uint32_t t = 0;
+    for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t cand = t | (1u << bit);
+        int c = 0;
+#pragma unroll
+        for (int e = 0; e < TK_PER_LANE; ++e) c += __popc(__ballot_sync(FULL, key[e] >= cand));
+        if (c >= TK_KEEP) t = cand;
+    }
+    // keep everything above t, and entries equal to t only until TK_KEEP is reached (bounded count even with
+    // massive ties; dropped entries all have score <= the new threshold, which the final selection checks)
+    int n_gt = 0;
+#pragma unroll
+    for (int e = 0; e < TK_PER_LANE; ++e) n_gt += __popc(__ballot_sync(FULL, key[e] > t));
+    int ties_left = TK_KEEP - n_gt;
+    int pos = 0;
+#pragma unroll
+    for (int e = 0; e < TK_PER_LANE; ++e) {
+        const bool valid = e * 32 + lane < n;
+        const bool gt = valid && (key[e] > t || t == 0u);
+        const bool eq = valid && t != 0u && key[e] == t;
+        const unsigned m_eq = __ballot_sync(FULL, eq);
+        const bool eq_keep = eq && __popc(m_eq & ((1u << lane) - 1)) < ties_left;
+        ties_left -= min(ties_left, __popc(m_eq));
+        const bool keep = gt || eq_keep;
+        const unsigned m = __ballot_sync(FULL, keep);
+        if (keep) {
+            int w = pos + __popc(m & ((1u << lane) - 1));
+            bv[w] = val[e];
+            bi[w] = idx[e];
+        }
+        pos += __popc(m);
+    }
+    __syncwarp();
+    new_cnt = pos;
+    new_thr = key_float(t);
+}
+
+// ------------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------------
 struct SimArgs {
@@ -138,6 +212,11 @@ struct SimArgs {
     const float* rowsum_y;        // [C]   (grad)
     float* out_part;              // rowsum: [chunks, R]; grad: [chunks, R, Dp]; scores: [R, C]
     float* diag;                  // [R] (rowsum, nullable)
+    float* cand_val;              // top-k: [chunks * Rpad, TK_CAP] bf16-operand scores
+    int* cand_idx;                // top-k: column of every candidate
+    int* cand_cnt;                // top-k: [chunks * Rpad] entries in use
+    float* cand_thr;              // top-k: [chunks * Rpad] final admission threshold (-inf: nothing was dropped)
+    int Rpad;
 };
 
 struct SimSmem {                  // offsets from the 1024-aligned base
@@ -258,6 +337,12 @@ simtile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
         const bool row_ok = row < a.R;
         float racc = 0.f, dval = 0.f;
         bool have_diag = false;
+        // top-k state of this row: admission threshold, entries in its candidate buffer
+        const long long slot = (long long)blockIdx.y * a.Rpad + row;
+        float* bv = a.mode == SIM_TOPK ? a.cand_val + slot * TK_CAP : nullptr;
+        int* bi = a.mode == SIM_TOPK ? a.cand_idx + slot * TK_CAP : nullptr;
+        float thr = row_ok ? -INFINITY : INFINITY;     // rows past R admit nothing
+        int cnt = 0;
         const float rx = (grad && row_ok) ? a.alpha / a.rowsum_x[row] : 0.f;
         for (int t = 0; t < n_tiles; ++t) {
             const int b = t & 1;
@@ -279,6 +364,27 @@ simtile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
                     if (row_ok)
                         for (int i = 0; i < 32; ++i)
                             if (jc + i < a.C) a.out_part[row * a.C + jc + i] = v[i];
+                } else if (a.mode == SIM_TOPK) {
+                    if (jc + 32 > a.C) {                         // ragged last tile: columns past C never qualify
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (jc + i >= a.C) v[i] = -INFINITY;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (__builtin_expect(v[i] > thr, 0)) topk_append(bv, bi, cnt, v[i], jc + i);
+                    // a buffer that could overflow on the next 32 columns is compacted by the whole warp
+                    unsigned need = __ballot_sync(FULL, cnt > TK_CAP - 32);
+                    while (need) {
+                        const int r = __ffs(need) - 1;
+                        need &= need - 1;
+                        const long long slot_r = (long long)blockIdx.y * a.Rpad + row0 + 32 * q + r;
+                        const int n_r = __shfl_sync(FULL, cnt, r);
+                        int new_cnt;
+                        float new_thr;
+                        topk_compact(a.cand_val + slot_r * TK_CAP, a.cand_idx + slot_r * TK_CAP, n_r, lane, new_cnt, new_thr);
+                        if (lane == r) { cnt = new_cnt; thr = new_thr; }
+                    }
                 } else if (a.mode == SIM_ROWSUM) {
                     const long long dcol = row + a.diag_offset;
 #pragma unroll
@@ -317,7 +423,10 @@ simtile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
             }
             mbar_arrive(s_empty + b);
         }
-        if (a.mode == SIM_ROWSUM) {
+        if (a.mode == SIM_TOPK) {
+            a.cand_cnt[slot] = row_ok ? cnt : 0;
+            a.cand_thr[slot] = thr;
+        } else if (a.mode == SIM_ROWSUM) {
             if (row_ok) {
                 a.out_part[(long long)blockIdx.y * a.R + row] = racc;
                 if (a.diag && have_diag) a.diag[row] = dval;
@@ -551,6 +660,197 @@ extern "C" int cfm_infonce_loss(const float* rowsum_row, const float* rowsum_col
     CFM_REQUIRE(rowsum_row && rowsum_col && diag && loss && n >= 1, CFM_ERR_INVALID, "bad loss arguments");
     infonce_loss_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(rowsum_row, rowsum_col, diag, (int)n, (float)(1.0 / temperature),
                                                              (float)(1.0 / (2.0 * (double)B_total)), loss);
+    CFM_LAUNCH_CHECK();
+    return CFM_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// all-pairs top-k: selection / exact rescoring, k-way merge, diagonal ranks
+// ------------------------------------------------------------------------------------------
+namespace cfm {
+
+constexpr int SEL_MAXC = 1024;      // survivors per row the selection kernel can rescore
+
+// One warp per row.  (1) tau = k-th largest tensor-core score among the row's candidates of all chunks,
+// (2) survivors = candidates with score >= tau - margin (margin bounds |bf16-operand score - exact score| twice),
+// (3) any chunk that dropped entries above tau - margin, or too many survivors -> row flagged for the exact path,
+// (4) survivors are rescored in fp64 from the fp32 operands and ranked (score desc, index asc).
+__global__ void __launch_bounds__(128) topk_select_kernel(const float* __restrict__ rows_f32, const float* __restrict__ cols_f32,
+                                   int R, int C, int D, int k, int chunks, int Rpad, float margin, double scale,
+                                   long long col_offset, const float* __restrict__ cand_val,
+                                   const int* __restrict__ cand_idx, const int* __restrict__ cand_cnt,
+                                   const float* __restrict__ cand_thr, float* __restrict__ out_score,
+                                   long long* __restrict__ out_idx, int* __restrict__ row_flag) {
+    __shared__ int s_idx[4][SEL_MAXC];
+    __shared__ double s_val[4][SEL_MAXC];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 4 + w;
+    if (row >= R) return;
+    // (1) k-th largest key over all candidates (bisection, counting straight from the buffers)
+    int total = 0;
+    for (int c = 0; c < chunks; ++c) total += cand_cnt[(long long)c * Rpad + row];
+    const int kk = min(k, total);
+    uint32_t t = 0;
+    if (kk > 0) {
+        for (int bit = 31; bit >= 0; --bit) {
+            const uint32_t cand = t | (1u << bit);
+            int cnt = 0;
+            for (int c = 0; c < chunks; ++c) {
+                const long long slot = (long long)c * Rpad + row;
+                const int n = cand_cnt[slot];
+                for (int p = lane; p < n; p += 32) cnt += float_key(cand_val[slot * TK_CAP + p]) >= cand;
+            }
+            cnt = __reduce_add_sync(FULL, cnt);
+            if (cnt >= kk) t = cand;
+        }
+    }
+    const float tau = kk > 0 ? key_float(t) : -INFINITY;
+    const float cut = tau - margin;
+    // (2)+(3) survivors into shared memory
+    bool overflow = false;
+    int n_s = 0;
+    for (int c = 0; c < chunks; ++c) {
+        const long long slot = (long long)c * Rpad + row;
+        const int n = cand_cnt[slot];
+        if (cand_thr[slot] >= cut && total >= k) overflow = true;       // this chunk dropped entries that might matter
+        for (int p0 = 0; p0 < n; p0 += 32) {
+            const int p = p0 + lane;
+            const bool keep = p < n && cand_val[slot * TK_CAP + p] >= cut;
+            const unsigned m = __ballot_sync(FULL, keep);
+            const int wpos = n_s + __popc(m & ((1u << lane) - 1));
+            if (keep && wpos < SEL_MAXC) s_idx[w][wpos] = cand_idx[slot * TK_CAP + p];
+            n_s += __popc(m);
+        }
+    }
+    if (n_s > SEL_MAXC) { overflow = true; n_s = SEL_MAXC; }
+    __syncwarp();
+    // (4) exact scores in fp64
+    const float* u = rows_f32 + (long long)row * D;
+    for (int p = lane; p < n_s; p += 32) {
+        const float* v = cols_f32 + (long long)s_idx[w][p] * D;
+        double acc = 0.0;
+        for (int d = 0; d < D; ++d) acc = fma((double)u[d], (double)v[d], acc);
+        s_val[w][p] = acc;
+    }
+    __syncwarp();
+    for (int p = lane; p < n_s; p += 32) {
+        const double mv = s_val[w][p];
+        const int mi = s_idx[w][p];
+        int rank = 0;
+        for (int o = 0; o < n_s; ++o) {
+            const double ov = s_val[w][o];
+            rank += (ov > mv) || (ov == mv && s_idx[w][o] < mi);
+        }
+        if (rank < k) {
+            out_score[(long long)row * k + rank] = (float)(mv * scale);
+            out_idx[(long long)row * k + rank] = (long long)mi + col_offset;
+        }
+    }
+    for (int p = n_s + lane; p < k; p += 32) {          // fewer than k columns exist: pad
+        out_score[(long long)row * k + p] = -INFINITY;
+        out_idx[(long long)row * k + p] = -1;
+    }
+    if (lane == 0) row_flag[row] = overflow ? 1 : 0;
+}
+
+// thread per row: k-way merge of n_parts lists, each sorted (score desc, index asc)
+__global__ void topk_merge_kernel(const float* __restrict__ ps, const long long* __restrict__ pi, int n_parts, long long R,
+                                  int k, float* __restrict__ os, long long* __restrict__ oi) {
+    const long long row = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (row >= R) return;
+    int head[16];
+    for (int p = 0; p < n_parts; ++p) head[p] = 0;
+    for (int o = 0; o < k; ++o) {
+        int best = -1;
+        float bs = 0.f;
+        long long bidx = 0;
+        for (int p = 0; p < n_parts; ++p) {
+            if (head[p] >= k) continue;
+            const long long off = ((long long)p * R + row) * k + head[p];
+            const float sc = ps[off];
+            const long long ix = pi[off];
+            if (ix < 0) { head[p] = k; continue; }                      // padding: list exhausted
+            if (best < 0 || sc > bs || (sc == bs && ix < bidx)) { best = p; bs = sc; bidx = ix; }
+        }
+        if (best < 0) { os[row * k + o] = -INFINITY; oi[row * k + o] = -1; continue; }
+        os[row * k + o] = bs;
+        oi[row * k + o] = bidx;
+        ++head[best];
+    }
+}
+
+// warp per row: rank of column target[row] = 1 + #{j : s_j > s_t  or (s_j == s_t and j < t)}, scores in fp64
+__global__ void __launch_bounds__(128) allpairs_rank_kernel(const float* __restrict__ rows_f32, const float* __restrict__ cols_f32,
+                                     int R, int C, int D, const long long* __restrict__ target,
+                                     long long* __restrict__ rank) {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 4 + w;
+    if (row >= R) return;
+    const float* u = rows_f32 + (long long)row * D;
+    const long long tcol = target[row];
+    double st = 0.0;
+    if (tcol >= 0 && tcol < C) {
+        const float* v = cols_f32 + tcol * D;
+        for (int d = 0; d < D; ++d) st = fma((double)u[d], (double)v[d], st);
+    }
+    int cnt = 0;
+    for (int j = lane; j < C; j += 32) {
+        const float* v = cols_f32 + (long long)j * D;
+        double acc = 0.0;
+        for (int d = 0; d < D; ++d) acc = fma((double)u[d], (double)v[d], acc);
+        cnt += (acc > st) || (acc == st && j < tcol);
+    }
+    cnt = __reduce_add_sync(FULL, cnt);
+    if (lane == 0) rank[row] = (tcol >= 0 && tcol < C) ? cnt + 1 : C;
+}
+
+}  // namespace cfm
+
+extern "C" int cfm_allpairs_topk(const float* rows_f32, const float* cols_f32, const void* rows_bf16, const void* cols_bf16,
+                                 int64_t R, int64_t C, int64_t D, int64_t Dp, int64_t k, double scale, double margin,
+                                 int64_t col_offset, float* out_score, int64_t* out_idx, int32_t* row_flag,
+                                 float* cand_val, int32_t* cand_idx, int32_t* cand_cnt, float* cand_thr, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CFM_REQUIRE(rows_f32 && cols_f32 && rows_bf16 && cols_bf16 && out_score && out_idx && row_flag && cand_val &&
+                    cand_idx && cand_cnt && cand_thr, CFM_ERR_INVALID, "null pointer");
+    CFM_REQUIRE(R >= 1 && C >= 1 && k >= 1 && k <= TK_KEEP / 2 + 32 && D <= Dp && margin >= 0, CFM_ERR_UNSUPPORTED,
+                "top-k supports 1 <= k <= %d (got %lld)", TK_KEEP / 2 + 32, (long long)k);
+    const int chunks = sim_chunks(R, C);
+    SimArgs a{};
+    a.mode = SIM_TOPK; a.R = (int)R; a.C = (int)C; a.D = (int)D; a.Dp = (int)Dp;
+    a.cand_val = cand_val; a.cand_idx = cand_idx; a.cand_cnt = cand_cnt; a.cand_thr = cand_thr;
+    a.Rpad = (int)((R + ST_M - 1) / ST_M) * ST_M;
+    {
+        ProfScope prof(PROF_TOPK, stream);
+        int rc = launch_sim(a, rows_bf16, cols_bf16, chunks, stream);
+        if (rc) return rc;
+    }
+    ProfScope prof(PROF_TOPK_POST, stream);
+    topk_select_kernel<<<(int)((R + 3) / 4), 128, 0, stream>>>(rows_f32, cols_f32, (int)R, (int)C, (int)D, (int)k, chunks,
+                                                             a.Rpad, (float)margin, scale, col_offset, cand_val, cand_idx,
+                                                             cand_cnt, cand_thr, out_score, (long long*)out_idx, row_flag);
+    CFM_LAUNCH_CHECK();
+    return CFM_OK;
+}
+
+extern "C" int cfm_topk_merge(const float* part_score, const int64_t* part_idx, int64_t n_parts, int64_t R, int64_t k,
+                              float* out_score, int64_t* out_idx, void* stream) {
+    CFM_REQUIRE(part_score && part_idx && out_score && out_idx && n_parts >= 1 && n_parts <= 16 && k >= 1,
+                CFM_ERR_INVALID, "bad merge arguments (1 <= n_parts <= 16)");
+    if (R == 0) return CFM_OK;
+    topk_merge_kernel<<<(int)((R + 127) / 128), 128, 0, (cudaStream_t)stream>>>(part_score, (const long long*)part_idx,
+                                                                              (int)n_parts, R, (int)k, out_score,
+                                                                              (long long*)out_idx);
+    CFM_LAUNCH_CHECK();
+    return CFM_OK;
+}
+
+extern "C" int cfm_allpairs_rank(const float* rows_f32, const float* cols_f32, int64_t R, int64_t C, int64_t D,
+                                 const int64_t* target_col, int64_t* rank, void* stream) {
+    CFM_REQUIRE(rows_f32 && cols_f32 && target_col && rank && R >= 1 && C >= 1 && D >= 1, CFM_ERR_INVALID, "bad rank arguments");
+    allpairs_rank_kernel<<<(int)((R + 3) / 4), 128, 0, (cudaStream_t)stream>>>(rows_f32, cols_f32, (int)R, (int)C, (int)D,
+                                                                             (const long long*)target_col, (long long*)rank);
     CFM_LAUNCH_CHECK();
     return CFM_OK;
 }

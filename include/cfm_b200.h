@@ -34,7 +34,6 @@ extern "C" {
 
 /* bits OR-ed by kernels into the caller's device-side `err_flag` word */
 #define CFM_FLAG_INDEX_OOB 1     /* categorical index outside [0, table_rows) — torch raises IndexError */
-#define CFM_FLAG_TOPK_OVERFLOW 2 /* all-pairs candidate list overflowed; row was re-done exactly */
 
 int cfm_abi_version(void);
 const char* cfm_last_error(void);
@@ -195,21 +194,29 @@ int cfm_simtile_scores(const void* x_bf16, const void* y_bf16, int64_t R, int64_
                        void* stream);
 
 /* ------------------------------------------------------------------------------------------
- * All-pairs scoring with streaming top-k (tcgen05/TMEM filter pass in bf16 + exact fp32 rescoring).
+ * All-pairs scoring with streaming top-k.
  * replaces: analytical_extensions.py:471,483 (torch.mm + np.argsort), contrastive.py:307-310 (sim.sort).
- * rows [R,D] f32, cols [C,D] f32 unit vectors and their bf16 copies [R,Dp]/[C,Dp] (Dp = D padded to 64).
- * Output per row: the k best columns ordered (score desc, index asc); score = scale * <row, col> in fp32.
- *   cand_idx/cand_val: scratch [R, CFM_TOPK_CAND]; col_offset is added to emitted indices (column shards).
+ * Pass 1 (tcgen05/TMEM): scores of the bf16 copies, tile by tile; each row keeps the columns whose score beats a
+ * running threshold in a TK_CAP-entry buffer that is compacted to its TK_KEEP best when full.  Pass 2: every
+ * candidate within `margin` of the k-th best is rescored in fp64 from the fp32 operands and the k best are emitted
+ * ordered (score desc, index asc), score = scale * <row, col>.  `margin` must bound twice the error of a
+ * bf16-operand score (2^-7 * max|row| * max|col|); rows whose completeness cannot be proven get row_flag = 1 and
+ * must be redone exactly by the caller.  k <= 128.  The [R,C] score matrix never exists in memory.
+ *   rows [R,D] / cols [C,D] f32 and bf16 copies [R,Dp] / [C,Dp]; col_offset is added to emitted indices (shards)
+ *   scratch: cand_val/cand_idx [chunks*Rpad, CFM_TOPK_CAP], cand_cnt/cand_thr [chunks*Rpad],
+ *            chunks = cfm_simtile_chunks(R, C), Rpad = R rounded up to 128
  * ------------------------------------------------------------------------------------------ */
-#define CFM_TOPK_CAND 256
+#define CFM_TOPK_CAP 384
 int cfm_allpairs_topk(const float* rows_f32, const float* cols_f32, const void* rows_bf16, const void* cols_bf16,
-                      int64_t R, int64_t C, int64_t D, int64_t Dp, int64_t k, double scale, int64_t col_offset,
-                      float* out_score /* [R,k] */, int64_t* out_idx /* [R,k] */, int32_t* cand_idx,
-                      float* cand_val, int32_t* err_flag, void* stream);
-/* merge `n_parts` per-shard top-k lists [n_parts,R,k] into the global top-k (score desc, index asc) */
+                      int64_t R, int64_t C, int64_t D, int64_t Dp, int64_t k, double scale, double margin,
+                      int64_t col_offset, float* out_score /* [R,k] */, int64_t* out_idx /* [R,k] */,
+                      int32_t* row_flag /* [R] */, float* cand_val, int32_t* cand_idx, int32_t* cand_cnt,
+                      float* cand_thr, void* stream);
+/* merge `n_parts` (<= 16) per-shard top-k lists [n_parts,R,k] into the global top-k (score desc, index asc) */
 int cfm_topk_merge(const float* part_score, const int64_t* part_idx, int64_t n_parts, int64_t R, int64_t k,
                    float* out_score, int64_t* out_idx, void* stream);
-/* rank of a given column per row: 1 + #{j : s_ij > s_i,target[i]}  (contrastive.py:312-320) */
+/* 1-indexed rank of column target_col[i] in row i: 1 + #{j : s_ij > s_it or (s_ij == s_it and j < t)}
+ * (contrastive.py:312-320), scores formed in fp64 from the fp32 operands */
 int cfm_allpairs_rank(const float* rows_f32, const float* cols_f32, int64_t R, int64_t C, int64_t D,
                       const int64_t* target_col /* [R] */, int64_t* rank /* [R] */, void* stream);
 
