@@ -297,6 +297,8 @@ class PersistentTableGrads:
         self.h = handle
         self.scratches = {}                      # n_items -> _SortScratch (kept alive: graphs hold raw pointers)
         self.prev: Optional[_SortScratch] = None
+        self.defer = False                       # data parallelism: keep (indices, rows) for the cross-rank reduce
+        self.pending = None
         for e in handle.embeddings:
             e.weight.grad = torch.zeros_like(e.weight)
 
@@ -335,6 +337,9 @@ def embedding_grads(h: TowerHandle, x_cat: torch.Tensor, dx_emb: torch.Tensor, B
         # PersistentTableGrads.rezero(), called from zero_grad), autograd gets no tensor for the tables
         if pg.prev is not None:
             raise RuntimeError("persistent table grads: backward ran twice without zero_grad_fast() in between")
+        if pg.defer:                                  # reduced later over the all-gathered global batch
+            pg.pending = (x_cat, dx_emb)
+            return [None] * h.n_tables
         scratch = pg.scratch_for(n_items, B, dx_emb.device)
         _segment_reduce(h, x_cat, dx_emb, B, [e.weight.grad for e in h.embeddings], scratch)
         pg.prev = scratch
@@ -343,6 +348,16 @@ def embedding_grads(h: TowerHandle, x_cat: torch.Tensor, dx_emb: torch.Tensor, B
     grads = [torch.zeros_like(e.weight) for e in h.embeddings]
     _segment_reduce(h, x_cat, dx_emb, B, grads, scratch)
     return grads
+
+
+def reduce_table_grads(h: TowerHandle, x_cat: torch.Tensor, dx_emb: torch.Tensor) -> None:
+    """Segment-reduce externally supplied (index, gradient-row) pairs — e.g. the all-gathered global batch of a
+    data-parallel step — into the tower's persistent dense table gradients."""
+    pg = h.table_grads
+    B = x_cat.shape[0]
+    scratch = pg.scratch_for(B * h.n_tables, B, dx_emb.device)
+    _segment_reduce(h, x_cat.contiguous(), dx_emb.contiguous(), B, [e.weight.grad for e in h.embeddings], scratch)
+    pg.prev = scratch
 
 
 # ---------------------------------------------------------------------------------------

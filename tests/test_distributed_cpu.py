@@ -1,0 +1,129 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU protocol in ceo_firm_matching.distributed: sharding, bucketed
+all-reduce, ragged gathers, InfoNCE with global negatives and the sharded top-k merge.  The per-rank math is
+injected as a torch reference backend (the CUDA kernels need a GPU); the collectives and bookkeeping are the
+product's own."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+class TorchInfoNCEBackend:
+    """Reference math with the same contract as CudaInfoNCEBackend (fixed maximum 1/T, fp32)."""
+
+    def pack(self, x):
+        return x.detach().float()
+
+    def rowsum(self, xb, yb, temperature, diag_offset, want_diag):
+        s = xb @ yb.t()
+        rs = torch.exp((s - 1) / temperature).sum(1)
+        diag = s[torch.arange(xb.shape[0]), torch.arange(xb.shape[0]) + diag_offset] if want_diag else None
+        return rs, diag
+
+    def local_loss(self, rs_row, rs_col, diag, temperature, b_total):
+        return (torch.log(rs_row) + torch.log(rs_col) + 2 / temperature - 2 * diag / temperature).sum() / (2 * b_total)
+
+    def grad(self, xb, yb, d, temperature, diag_offset, b_total, rs_x, rs_y, diag, g_loss):
+        e = torch.exp((xb @ yb.t() - 1) / temperature)
+        g = e * (1 / rs_x[:, None] + 1 / rs_y[None, :]) / (2 * b_total * temperature)
+        idx = torch.arange(xb.shape[0])
+        g[idx, idx + diag_offset] -= 1 / (b_total * temperature)
+        return g_loss * (g @ yb)[:, :d]
+
+
+class TorchScoringBackend:
+    def topk(self, rows, cols, k, scale, col_offset):
+        s = rows.double() @ cols.double().t()
+        order = torch.argsort(-s, dim=1, stable=True)[:, :k]
+        out_s = torch.full((rows.shape[0], k), float("-inf"))
+        out_i = torch.full((rows.shape[0], k), -1, dtype=torch.int64)
+        out_s[:, :order.shape[1]] = (torch.gather(s, 1, order) * scale).float()
+        out_i[:, :order.shape[1]] = order + col_offset
+        return out_s, out_i
+
+    def merge(self, ps, pi):
+        n_parts, R, k = ps.shape
+        s = ps.permute(1, 0, 2).reshape(R, -1).double()
+        i = pi.permute(1, 0, 2).reshape(R, -1)
+        s = torch.where(i < 0, torch.full_like(s, float("-inf")), s)
+        key = torch.argsort(i, dim=1, stable=True)                           # index asc ...
+        s, i = torch.gather(s, 1, key), torch.gather(i, 1, key)
+        order = torch.argsort(-s, dim=1, stable=True)[:, :k]                  # ... then score desc, stable
+        return torch.gather(s, 1, order).float(), torch.gather(i, 1, order)
+
+
+def _worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "ceo-recommender_b200"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import oracle
+        from ceo_firm_matching import distributed as D
+        res = {}
+        # --- shard bookkeeping + bucketed all-reduce ---
+        assert [D.shard_bounds(10, 4, r) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (8, 10)]
+        a, b = torch.full((3, 2), float(rank + 1)), torch.arange(4.0) * (rank + 1)
+        D.allreduce_flat_([a, None, b], scale=0.5)
+        res["allreduce"] = (a.clone(), b.clone())
+        rag, counts = D.gather_ragged_rows(torch.full((rank + 1, 2), float(rank)))
+        res["ragged"] = (rag.clone(), counts)
+        # --- InfoNCE with global negatives ---
+        gen = torch.Generator().manual_seed(0)
+        Bt, Dm = 12, 16
+        f_all = F.normalize(torch.randn(Bt, Dm, generator=gen), dim=1)
+        c_all = F.normalize(0.5 * f_all + torch.randn(Bt, Dm, generator=gen), dim=1)
+        lo, hi = D.shard_bounds(Bt, world, rank)
+        f = f_all[lo:hi].clone().requires_grad_(True)
+        c = c_all[lo:hi].clone().requires_grad_(True)
+        loss = D.info_nce_loss_global(f, c, 0.07, backend=TorchInfoNCEBackend())
+        (2.0 * loss).backward()
+        fo, co = f_all.clone().requires_grad_(True), c_all.clone().requires_grad_(True)
+        lref = oracle.info_nce(fo, co, 0.07)
+        (2.0 * lref).backward()
+        res["nce"] = (float(loss), float(lref), (f.grad - fo.grad[lo:hi]).abs().max().item(),
+                      (c.grad - co.grad[lo:hi]).abs().max().item())
+        # --- sharded scoring with ragged shards + merge ---
+        rows_all = F.normalize(torch.randn(9, 8, generator=gen), dim=1)
+        cols_all = F.normalize(torch.randn(31, 8, generator=gen), dim=1)
+        cols_all[20] = cols_all[3]                                             # an exact tie across shards
+        rlo, rhi = D.shard_bounds(9, world, rank)
+        clo, chi = (0, 20) if rank == 0 else (20, 31)
+        s, i = D.score_topk_sharded(rows_all[rlo:rhi], cols_all[clo:chi], 7, 3.0, backend=TorchScoringBackend())
+        so, io = oracle.allpairs_topk(rows_all[rlo:rhi], cols_all, 7, 3.0)
+        res["topk"] = (torch.equal(i, io), (s - so).abs().max().item())
+        out[rank] = res
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world2_protocol():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    for rank in range(world):
+        r = out[rank]
+        a, b = r["allreduce"]
+        assert torch.equal(a, torch.full((3, 2), 1.5)) and torch.equal(b, torch.arange(4.0) * 1.5)
+        rag, counts = r["ragged"]
+        assert counts == [1, 2] and torch.equal(rag, torch.tensor([[0., 0.], [1., 1.], [1., 1.]]))
+        loss, lref, ef, ec = r["nce"]
+        assert loss == pytest.approx(lref, rel=1e-5) and ef < 1e-5 and ec < 1e-5
+        same_idx, err = r["topk"]
+        assert same_idx and err < 1e-5
+    assert out[0]["nce"][0] == out[1]["nce"][0]                     # the global loss is identical on every rank
