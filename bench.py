@@ -181,6 +181,84 @@ def build_model(device):
     return model
 
 
+def _time_cuda(fn, reps, dist=None, device=None):
+    """Best-of-`reps` device time of fn() in ms (CUDA events on the current stream; max over ranks)."""
+    best = float("inf")
+    for _ in range(reps):
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        best = min(best, ms)
+    return best
+
+
+def secondary_metrics(device, world, rank, dist):
+    """The other two paths the metric names: in-batch InfoNCE (config 3: global batch 65,536, D=128, bf16) and
+    all-pairs scoring with top-100 (config 5: 1M x 1M, D=60), sharded by rows when world > 1."""
+    import torch.nn.functional as F
+    from ceo_firm_matching.contrastive import info_nce_loss
+    from ceo_firm_matching.scoring import score_topk
+    from ceo_firm_matching import distributed as D
+    try:
+        bf16_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"]
+    except Exception:
+        bf16_peak = 1590.0
+    out = {}
+    g = torch.Generator(device=device).manual_seed(100 + rank)
+    # ---- config 3 ----
+    Bg, Dm = 65_536, 128
+    n = Bg // world
+    f = F.normalize(torch.randn(n, Dm, device=device, generator=g), dim=1).requires_grad_(True)
+    c = F.normalize(torch.randn(n, Dm, device=device, generator=g), dim=1).requires_grad_(True)
+
+    def nce_step():
+        f.grad = c.grad = None
+        loss = info_nce_loss(f, c, 0.07) if world == 1 else D.info_nce_loss_global(f, c, 0.07)
+        loss.backward()
+
+    nce_step()
+    ms = _time_cuda(nce_step, 3, dist, device)
+    flops = 6.0 * Bg * Bg * Dm                       # SURVEY 8(d): fwd 2 B^2 D + bwd 4 B^2 D (recompute not credited)
+    out["infonce_fwd_bwd"] = {"workload": "config3: B=65536 global, D=128, bf16 operands, fp32 accumulate",
+                              "ms": ms, "value": Bg * Bg / (ms * 1e-3), "unit": "scores/s",
+                              "roofline": {"bound": "tensor", "achieved": flops / (ms * 1e-3) / 1e12 / world,
+                                           "peak": bf16_peak, "unit": "TFLOP/s",
+                                           "frac": flops / (ms * 1e-3) / 1e12 / world / bf16_peak}}
+    del f, c
+    # ---- config 5 ----
+    Nall, Dl, k = 1_000_000, 60, 100
+    lo, hi = D.shard_bounds(Nall, world, rank)
+    ceos = F.normalize(torch.randn(hi - lo, Dl, device=device, generator=g), dim=1)
+    firms = F.normalize(torch.randn(hi - lo, Dl, device=device, generator=g), dim=1)
+    scale = 1 / 0.07
+
+    def topk_step():
+        if world == 1:
+            return score_topk(ceos, firms, k, scale)
+        return D.score_topk_sharded(ceos, firms, k, scale)
+
+    warm = score_topk(ceos[:4096], firms[:65536], k, scale)
+    del warm
+    ms = _time_cuda(topk_step, 1, dist, device)
+    flops = 2.0 * Nall * Nall * Dl
+    out["allpairs_top100"] = {"workload": "config5: 1M CEOs x 1M firms, D=60, top-100 per CEO, exact fp64 rescoring",
+                              "ms": ms, "value": float(Nall) * Nall / (ms * 1e-3), "unit": "scores/s",
+                              "roofline": {"bound": "tensor", "achieved": flops / (ms * 1e-3) / 1e12 / world,
+                                           "peak": bf16_peak, "unit": "TFLOP/s",
+                                           "frac": flops / (ms * 1e-3) / 1e12 / world / bf16_peak}}
+    return out
+
+
 def gpu_arm(args):
     from ceo_firm_matching import _native as N
     import ctypes as C
@@ -207,7 +285,8 @@ def gpu_arm(args):
 
     from ceo_firm_matching.training import GraphedTwoTowerStep
     # the whole step (sparse re-zero, fwd, loss, bwd, segment reduce) is captured once and replayed
-    runner = GraphedTwoTowerStep(model, batches[0], optimizer=None, warmup=3)
+    runner = GraphedTwoTowerStep(model, batches[0], optimizer=None, warmup=3,
+                                 loss_scale=dp.loss_scale if dp is not None else 1.0)
 
     def step(i):
         loss = runner.step(batches[i % n_data])      # D2D copy into the graph's static inputs + replay
@@ -300,6 +379,8 @@ def gpu_arm(args):
         e2e_s = float(tmax.item())
     e2e_value = world * B_PER_GPU * args.steps / e2e_s
 
+    secondary = secondary_metrics(device, world, rank, dist)
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -344,6 +425,7 @@ def gpu_arm(args):
         "gpu_launches": launches,
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "secondary": secondary,
     }
     print(json.dumps(line))
     if dist is not None:

@@ -32,11 +32,12 @@ class GraphedTwoTowerStep:
 
     def __init__(self, model: CEOFirmMatcher, example: Sequence[torch.Tensor],
                  optimizer: Optional[torch.optim.Optimizer] = None, warmup: int = 3,
-                 stream: Optional[torch.cuda.Stream] = None):
+                 stream: Optional[torch.cuda.Stream] = None, loss_scale: float = 1.0):
         dev = next(model.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("GraphedTwoTowerStep needs the model on a CUDA device (no CPU fallback)")
         self.model, self.optimizer, self.device = model, optimizer, dev
+        self.loss_scale = loss_scale             # data parallelism: 1/world so gradients are those of the global mean
         self.static = [torch.empty(t.shape, dtype=t.dtype, device=dev) for t in example]
         for s, t in zip(self.static, example):
             s.copy_(t)
@@ -63,7 +64,7 @@ class GraphedTwoTowerStep:
         ops.advance_graph_rng_counter()
         self.model.zero_grad_fast()
         loss, _ = self.model.forward_loss(*self.static)
-        loss.backward()
+        (loss if self.loss_scale == 1.0 else loss * self.loss_scale).backward()
         if self.optimizer is not None:
             self.optimizer.step()
             self.model.rezero_table_grads()      # tables are clean again before any other graph runs
