@@ -18,7 +18,7 @@ namespace cfm {
 
 constexpr int ST_M = 128, ST_N = 128, ST_KB = 64;      // tile rows / cols, bf16 elements per 128-byte swizzle row
 constexpr int ST_STAGES = 3;
-constexpr int ST_THREADS = 192;
+constexpr int ST_THREADS = 64 + 8 * 32;               // TMA warp, MMA warp, 8 epilogue warps
 constexpr int KB_BYTES = ST_M * 128;                   // one [128 rows x 64 bf16] swizzled block = 16 KB
 constexpr float LOG2E = 1.4426950408889634f;
 
@@ -109,6 +109,36 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// 64 consecutive fp32 columns of this thread's TMEM lane (one instruction, one wait)
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
+    uint32_t r[64];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
+        "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+        "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]),
+          "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]),
+          "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]), "=r"(r[48]),
+          "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]),
+          "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
+}
+// 2^x on the SFU (MUFU.EX2), flush-to-zero: one instruction, no denormal fix-up
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 
 // Shared-memory matrix descriptors (sm_100 format: version 1 at bit 46, layout type at [61,64), SWIZZLE_128B = 2).
@@ -261,8 +291,8 @@ simtile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
         mbar_init(x_full, 1);
         for (int s = 0; s < ST_STAGES; ++s) { mbar_init(y_full + s, 1); mbar_init(y_empty + s, 1); }
         for (int b = 0; b < 2; ++b) {
-            mbar_init(s_full + b, 1); mbar_init(s_empty + b, 128);
-            mbar_init(g_full + b, 128); mbar_init(g_empty + b, 1);
+            mbar_init(s_full + b, 1); mbar_init(s_empty + b, 256);
+            mbar_init(g_full + b, 256); mbar_init(g_empty + b, 1);
         }
         mbar_init(acc_full, 1);
         fence_barrier_init();
@@ -329,91 +359,101 @@ simtile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
             if (grad) umma_commit(acc_full);
         }
     } else {
-        // ===================== epilogue: thread <-> TMEM lane <-> row =====================
+        // ===================== epilogue: 8 warps; thread <-> TMEM lane <-> row, warp group <-> column half ======
+        const int half = (warp - 2) >> 2;              // columns [64*half, 64*half+64) of every tile
         const int q = warp & 3;                        // TMEM lane quadrant this warp may access
         const int r_loc = 32 * q + lane;
         const long long row = (long long)row0 + r_loc;
         const uint32_t lane_addr = (uint32_t)(32 * q) << 16;
         const bool row_ok = row < a.R;
-        float racc = 0.f, dval = 0.f;
+        float racc[4] = {0.f, 0.f, 0.f, 0.f}, dval = 0.f;
         bool have_diag = false;
-        // top-k state of this row: admission threshold, entries in its candidate buffer
-        const long long slot = (long long)blockIdx.y * a.Rpad + row;
+        // top-k state of this (row, column half): admission threshold, entries in its candidate buffer
+        const long long list = (long long)blockIdx.y * 2 + half;
+        const long long slot = list * a.Rpad + row;
         float* bv = a.mode == SIM_TOPK ? a.cand_val + slot * TK_CAP : nullptr;
         int* bi = a.mode == SIM_TOPK ? a.cand_idx + slot * TK_CAP : nullptr;
         float thr = row_ok ? -INFINITY : INFINITY;     // rows past R admit nothing
         int cnt = 0;
         const float rx = (grad && row_ok) ? a.alpha / a.rowsum_x[row] : 0.f;
+        const long long dcol = row + a.diag_offset;    // column of this row's positive pair
         for (int t = 0; t < n_tiles; ++t) {
             const int b = t & 1;
-            const int j0 = (tile0 + t) * ST_N;
+            const int j0 = (tile0 + t) * ST_N + 64 * half;
+            float* ry = sm_ry + b * ST_N + 64 * half;
             if (grad) {
                 mbar_wait(g_empty + b, ((t >> 1) & 1) ^ 1);            // G[b] no longer read by GEMM 2 of tile t-2
-                const int col = j0 + r_loc;
-                sm_ry[b * ST_N + r_loc] = col < a.C ? a.alpha / a.rowsum_y[col] : 0.f;
-                named_bar_sync(1, 128);
+                if (r_loc < 64) ry[r_loc] = (j0 + r_loc < a.C) ? a.alpha / a.rowsum_y[j0 + r_loc] : 0.f;
+                named_bar_sync(1 + half, 128);
             }
             mbar_wait(s_full + b, (t >> 1) & 1);
             tc_fence_after();
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                float v[32];
-                tmem_ld32(tmem_s0 + b * ST_N + c * 32 + lane_addr, v);
-                const int jc = j0 + c * 32;
-                if (a.mode == SIM_SCORES) {
-                    if (row_ok)
-                        for (int i = 0; i < 32; ++i)
-                            if (jc + i < a.C) a.out_part[row * a.C + jc + i] = v[i];
-                } else if (a.mode == SIM_TOPK) {
-                    if (jc + 32 > a.C) {                         // ragged last tile: columns past C never qualify
+            float v[64];
+            tmem_ld64(tmem_s0 + b * ST_N + 64 * half + lane_addr, v);
+            if (a.mode == SIM_SCORES) {
+                if (row_ok)
+                    for (int i = 0; i < 64; ++i)
+                        if (j0 + i < a.C) a.out_part[row * a.C + j0 + i] = v[i];
+            } else if (a.mode == SIM_TOPK) {
+                if (j0 + 64 > a.C) {                             // ragged last tile: columns past C never qualify
 #pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (jc + i >= a.C) v[i] = -INFINITY;
-                    }
+                    for (int i = 0; i < 64; ++i)
+                        if (j0 + i >= a.C) v[i] = -INFINITY;
+                }
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i)
-                        if (__builtin_expect(v[i] > thr, 0)) topk_append(bv, bi, cnt, v[i], jc + i);
+                        if (__builtin_expect(v[32 * hh + i] > thr, 0)) topk_append(bv, bi, cnt, v[32 * hh + i], j0 + 32 * hh + i);
                     // a buffer that could overflow on the next 32 columns is compacted by the whole warp
                     unsigned need = __ballot_sync(FULL, cnt > TK_CAP - 32);
                     while (need) {
                         const int r = __ffs(need) - 1;
                         need &= need - 1;
-                        const long long slot_r = (long long)blockIdx.y * a.Rpad + row0 + 32 * q + r;
+                        const long long slot_r = list * a.Rpad + row0 + 32 * q + r;
                         const int n_r = __shfl_sync(FULL, cnt, r);
                         int new_cnt;
                         float new_thr;
                         topk_compact(a.cand_val + slot_r * TK_CAP, a.cand_idx + slot_r * TK_CAP, n_r, lane, new_cnt, new_thr);
                         if (lane == r) { cnt = new_cnt; thr = new_thr; }
                     }
-                } else if (a.mode == SIM_ROWSUM) {
-                    const long long dcol = row + a.diag_offset;
+                }
+            } else if (a.mode == SIM_ROWSUM) {
+                if (j0 + 64 <= a.C) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const float e = exp2f(fmaf(v[i], a.c1, -a.c2));
-                        racc += (jc + i < a.C) ? e : 0.f;
-                        if (jc + i == dcol) { dval = v[i]; have_diag = true; }
-                    }
+                    for (int i = 0; i < 64; ++i) racc[i & 3] += ex2_approx(fmaf(v[i], a.c1, -a.c2));
                 } else {
-                    // the positive pair (column row + diag_offset) is left out of the bf16 G tile: its weight is
-                    // O(1/B) while every other entry is O(1/B^2), so it is added in fp32 by the finalize kernel
-                    const long long dcol = row + a.diag_offset;
-                    uint32_t packed[16];
 #pragma unroll
-                    for (int i = 0; i < 32; i += 2) {
-                        float e0 = exp2f(fmaf(v[i], a.c1, -a.c2)), e1 = exp2f(fmaf(v[i + 1], a.c1, -a.c2));
-                        float g0 = (jc + i < a.C && jc + i != dcol) ? e0 * (rx + sm_ry[b * ST_N + c * 32 + i]) : 0.f;
-                        float g1 = (jc + i + 1 < a.C && jc + i + 1 != dcol) ? e1 * (rx + sm_ry[b * ST_N + c * 32 + i + 1]) : 0.f;
-                        __nv_bfloat162 h = __floats2bfloat162_rn(g0, g1);
-                        packed[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
-                    }
-                    // G[b] is the K-major SW128 A operand of GEMM 2: row r_loc, columns c*32 .. c*32+31
-                    uint8_t* grow = Gs + (b * 2 + (c >> 1)) * KB_BYTES + r_loc * 128;
+                    for (int i = 0; i < 64; ++i) racc[i & 3] += (j0 + i < a.C) ? ex2_approx(fmaf(v[i], a.c1, -a.c2)) : 0.f;
+                }
+                if (dcol >= j0 && dcol < j0 + 64) {
 #pragma unroll
-                    for (int h4 = 0; h4 < 4; ++h4) {
-                        const int chunk = (c & 1) * 4 + h4;                      // 16-byte chunk inside the 128-byte row
-                        uint4 val = make_uint4(packed[4 * h4], packed[4 * h4 + 1], packed[4 * h4 + 2], packed[4 * h4 + 3]);
-                        *reinterpret_cast<uint4*>(grow + ((chunk ^ (r_loc & 7)) << 4)) = val;
+                    for (int i = 0; i < 64; ++i)
+                        if (j0 + i == dcol) dval = v[i];
+                    have_diag = true;
+                }
+            } else {
+                // the positive pair (column row + diag_offset) is left out of the bf16 G tile: its weight is
+                // O(1/B) while every other entry is O(1/B^2), so it is added in fp32 by the finalize kernel
+                const bool edge = j0 + 64 > a.C || (dcol >= j0 && dcol < j0 + 64);
+                uint32_t packed[32];
+#pragma unroll
+                for (int i = 0; i < 64; i += 2) {
+                    float g0 = ex2_approx(fmaf(v[i], a.c1, -a.c2)) * (rx + ry[i]);
+                    float g1 = ex2_approx(fmaf(v[i + 1], a.c1, -a.c2)) * (rx + ry[i + 1]);
+                    if (edge) {
+                        if (j0 + i >= a.C || j0 + i == dcol) g0 = 0.f;
+                        if (j0 + i + 1 >= a.C || j0 + i + 1 == dcol) g1 = 0.f;
                     }
+                    __nv_bfloat162 h2 = __floats2bfloat162_rn(g0, g1);
+                    packed[i >> 1] = *reinterpret_cast<uint32_t*>(&h2);
+                }
+                // G[b] is the K-major SW128 A operand of GEMM 2; this half fills k-block `half` of row r_loc
+                uint8_t* grow = Gs + (b * 2 + half) * KB_BYTES + r_loc * 128;
+#pragma unroll
+                for (int h8 = 0; h8 < 8; ++h8) {
+                    uint4 val = make_uint4(packed[4 * h8], packed[4 * h8 + 1], packed[4 * h8 + 2], packed[4 * h8 + 3]);
+                    *reinterpret_cast<uint4*>(grow + ((h8 ^ (r_loc & 7)) << 4)) = val;
                 }
             }
             tc_fence_before();
@@ -428,7 +468,7 @@ simtile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
             a.cand_thr[slot] = thr;
         } else if (a.mode == SIM_ROWSUM) {
             if (row_ok) {
-                a.out_part[(long long)blockIdx.y * a.R + row] = racc;
+                a.out_part[list * a.R + row] = (racc[0] + racc[1]) + (racc[2] + racc[3]);
                 if (a.diag && have_diag) a.diag[row] = dval;
             }
         } else if (grad) {
@@ -436,15 +476,17 @@ simtile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
                 mbar_wait(acc_full, 0);
                 tc_fence_after();
             }
-            for (int c = 0; c < a.Dp / 32; ++c) {
-                float v[32];
-                if (n_tiles > 0) tmem_ld32(tmem_acc + c * 32 + lane_addr, v);
+            const int cols_half = a.Dp / 2;             // this half drains columns [half*Dp/2, (half+1)*Dp/2) of dX
+            for (int c = 0; c < cols_half / 32; ++c) {
+                float w[32];
+                const int c0 = half * cols_half + c * 32;
+                if (n_tiles > 0) tmem_ld32(tmem_acc + c0 + lane_addr, w);
                 else
-                    for (int i = 0; i < 32; ++i) v[i] = 0.f;
+                    for (int i = 0; i < 32; ++i) w[i] = 0.f;
                 if (row_ok) {
-                    float4* dst = reinterpret_cast<float4*>(a.out_part + ((long long)blockIdx.y * a.R + row) * a.Dp + c * 32);
+                    float4* dst = reinterpret_cast<float4*>(a.out_part + ((long long)blockIdx.y * a.R + row) * a.Dp + c0);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                    for (int i = 0; i < 8; ++i) dst[i] = make_float4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
                 }
             }
             tc_fence_before();
@@ -593,7 +635,8 @@ static int launch_sim(SimArgs a, const void* x, const void* y, int chunks, cudaS
 
 using namespace cfm;
 
-extern "C" int64_t cfm_simtile_chunks(int64_t R, int64_t C) { return sim_chunks(R, C); }
+// partial result lists per row: column chunks x the two column halves the epilogue warp groups own
+extern "C" int64_t cfm_simtile_chunks(int64_t R, int64_t C) { return 2 * sim_chunks(R, C); }
 
 extern "C" int cfm_pack_rows_bf16(const float* in, int64_t R, int64_t D, int64_t Dp, void* out_bf16, void* stream) {
     CFM_REQUIRE(in && out_bf16 && R >= 0 && D >= 1 && Dp >= D && Dp % 2 == 0, CFM_ERR_INVALID, "bad pack arguments");
@@ -626,7 +669,7 @@ extern "C" int cfm_infonce_rowsum(const void* x_bf16, const void* y_bf16, int64_
     ProfScope prof(PROF_NCE_ROWSUM, stream);
     int rc = launch_sim(a, x_bf16, y_bf16, chunks, stream);
     if (rc) return rc;
-    rowsum_finalize_kernel<<<(int)std::min<long long>((R + 255) / 256, 592), 256, 0, stream>>>(part, chunks, (int)R, rowsum);
+    rowsum_finalize_kernel<<<(int)std::min<long long>((R + 255) / 256, 592), 256, 0, stream>>>(part, 2 * chunks, (int)R, rowsum);
     CFM_LAUNCH_CHECK();
     return CFM_OK;
 }
@@ -827,7 +870,7 @@ extern "C" int cfm_allpairs_topk(const float* rows_f32, const float* cols_f32, c
         if (rc) return rc;
     }
     ProfScope prof(PROF_TOPK_POST, stream);
-    topk_select_kernel<<<(int)((R + 3) / 4), 128, 0, stream>>>(rows_f32, cols_f32, (int)R, (int)C, (int)D, (int)k, chunks,
+    topk_select_kernel<<<(int)((R + 3) / 4), 128, 0, stream>>>(rows_f32, cols_f32, (int)R, (int)C, (int)D, (int)k, 2 * chunks,
                                                              a.Rpad, (float)margin, scale, col_offset, cand_val, cand_idx,
                                                              cand_cnt, cand_thr, out_score, (long long*)out_idx, row_flag);
     CFM_LAUNCH_CHECK();
