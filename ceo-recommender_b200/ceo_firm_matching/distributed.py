@@ -113,8 +113,8 @@ class DataParallelTwoTower:
             pg = h.table_grads
             if pg.pending is None:
                 continue
+            # not cleared: inside a replayed CUDA graph the same static buffers are refilled every step
             x_cat, dx_emb = pg.pending
-            pg.pending = None
             x_all = gather_rows(x_cat, self.group)                 # [world*B, K] int64, rank order
             dx_all = gather_rows(dx_emb, self.group)               # [world*B, K*E] f32
             ops.reduce_table_grads(h, x_all, dx_all)               # same inputs, same order -> bitwise equal replicas
@@ -190,7 +190,8 @@ def info_nce_loss_global(firm_proj: torch.Tensor, ceo_proj: torch.Tensor, temper
 class CudaScoringBackend:
     def topk(self, rows, cols, k, scale, col_offset):
         from .scoring import score_topk
-        return score_topk(rows, cols, k, scale, col_offset=col_offset)
+        s, i, s64 = score_topk(rows, cols, k, scale, col_offset=col_offset, return_f64=True)
+        return s64, i                                  # fp64 scores: the merge must order exactly
 
     def merge(self, part_scores, part_indices):
         from .scoring import merge_topk

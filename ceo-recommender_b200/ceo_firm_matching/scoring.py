@@ -28,16 +28,17 @@ def _exact_rows(rows: torch.Tensor, cols: torch.Tensor, k: int, scale: float, co
         s, idx = torch.cat([best_s, s], 1), torch.cat([best_i, idx], 1)
         order = torch.argsort(-s, dim=1, stable=True)[:, :k]          # earlier (smaller) index wins a tie
         best_s, best_i = torch.gather(s, 1, order), torch.gather(idx, 1, order)
-    return (best_s * scale).float(), best_i + col_offset
+    return (best_s * scale).float(), best_i + col_offset, best_s * scale
 
 
 def score_topk(rows: torch.Tensor, cols: torch.Tensor, k: int, scale: float = 1.0, col_offset: int = 0,
-               return_flags: bool = False):
+               return_flags: bool = False, return_f64: bool = False):
     """Top-``k`` columns of ``rows @ cols.T * scale`` for every row.
 
     rows [R, D], cols [C, D] float32 on the device (unit-norm tower outputs in the reference's call sites; any
     norm is handled, the filter margin scales with the largest row norms).  Returns ``(scores [R,k] f32,
     indices [R,k] i64)`` ordered by (score desc, index asc); if ``C < k`` the tail is ``(-inf, -1)``.
+    ``return_f64`` appends the fp64 scores (needed for an exact merge of per-shard lists).
     Orientation is the caller's choice: pass firms as rows to rank CEOs per firm (analytical_extensions.py:483)
     or CEOs as rows for "top-100 firms per CEO" (BASELINE config 5).
     """
@@ -51,12 +52,25 @@ def score_topk(rows: torch.Tensor, cols: torch.Tensor, k: int, scale: float = 1.
         raise ValueError("rows and cols must have the same feature width")
     dev = rows.device
     out_s = torch.empty(R, k, device=dev)
+    out_s64 = torch.empty(R, k, dtype=torch.float64, device=dev) if return_f64 else None
     out_i = torch.empty(R, k, dtype=torch.int64, device=dev)
+    flags = torch.zeros(R, dtype=torch.int32, device=dev)
+
+    def result():
+        out = (out_s, out_i)
+        if return_flags:
+            out += (flags,)
+        if return_f64:
+            out += (out_s64,)
+        return out
+
     if R == 0:
-        return (out_s, out_i, torch.zeros(0, dtype=torch.int32, device=dev)) if return_flags else (out_s, out_i)
+        return result()
     if C == 0:
         out_s.fill_(float("-inf")); out_i.fill_(-1)
-        return (out_s, out_i, torch.zeros(R, dtype=torch.int32, device=dev)) if return_flags else (out_s, out_i)
+        if return_f64:
+            out_s64.fill_(float("-inf"))
+        return result()
     rb, cb = ops.pack_bf16(rows), ops.pack_bf16(cols)
     # |bf16-operand score - exact score| <= 2^-8 |row||col| (Cauchy-Schwarz over the per-element roundings), twice
     # that separates "certainly in" from "certainly out"; the tiny extra covers fp32 accumulation
@@ -67,29 +81,34 @@ def score_topk(rows: torch.Tensor, cols: torch.Tensor, k: int, scale: float = 1.
     cand_idx = torch.empty(chunks * rpad * N.CFM_TOPK_CAP, dtype=torch.int32, device=dev)
     cand_cnt = torch.empty(chunks * rpad, dtype=torch.int32, device=dev)
     cand_thr = torch.empty(chunks * rpad, device=dev)
-    flags = torch.empty(R, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
         N.check(N.lib().cfm_allpairs_topk(N.ptr(rows), N.ptr(cols), N.ptr(rb), N.ptr(cb), R, C, D, rb.shape[1], k,
-                                          float(scale), margin, col_offset, N.ptr(out_s), N.ptr(out_i), N.ptr(flags),
+                                          float(scale), margin, col_offset, N.ptr(out_s), N.ptr(out_s64), N.ptr(out_i), N.ptr(flags),
                                           N.ptr(cand_val), N.ptr(cand_idx), N.ptr(cand_cnt), N.ptr(cand_thr),
                                           N.stream_ptr()))
     bad = torch.nonzero(flags, as_tuple=False).flatten()
     if bad.numel():                                   # completeness not provable from the filter: redo exactly
-        s, i = _exact_rows(rows[bad], cols, k, float(scale), col_offset)
+        s, i, s64 = _exact_rows(rows[bad], cols, k, float(scale), col_offset)
         out_s[bad, :s.shape[1]], out_i[bad, :i.shape[1]] = s, i
-    return (out_s, out_i, flags) if return_flags else (out_s, out_i)
+        if return_f64:
+            out_s64[bad, :s.shape[1]] = s64
+    return result()
 
 
 def merge_topk(part_scores: torch.Tensor, part_indices: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     """Merge per-shard results ``[n_parts, R, k]`` (each ordered (score desc, index asc), indices already global)
-    into the global top-k with the same ordering — the cross-GPU merge of the row-sharded scoring path."""
+    into the global top-k with the same ordering — the cross-GPU merge of the row-sharded scoring path.  Pass the
+    float64 scores (``score_topk(..., return_f64=True)``) for a merge that is exact across shards."""
     ops._require_cuda(part_scores, part_indices)
     n_parts, R, k = part_scores.shape
-    ps, pi = part_scores.float().contiguous(), part_indices.long().contiguous()
+    is64 = part_scores.dtype == torch.float64          # fp64 parts keep the exact cross-shard ordering
+    ps = part_scores.contiguous() if is64 else part_scores.float().contiguous()
+    pi = part_indices.long().contiguous()
     out_s = torch.empty(R, k, device=ps.device)
     out_i = torch.empty(R, k, dtype=torch.int64, device=ps.device)
     with torch.cuda.device(ps.device):
-        N.check(N.lib().cfm_topk_merge(N.ptr(ps), N.ptr(pi), n_parts, R, k, N.ptr(out_s), N.ptr(out_i), N.stream_ptr()))
+        N.check(N.lib().cfm_topk_merge(N.ptr(ps), 1 if is64 else 0, N.ptr(pi), n_parts, R, k, N.ptr(out_s), N.ptr(out_i),
+                                       N.stream_ptr()))
     return out_s, out_i
 
 

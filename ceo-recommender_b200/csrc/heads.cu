@@ -7,7 +7,7 @@
 namespace cfm {
 
 constexpr int HEAD_NT = 256;
-constexpr int HEAD_MAX_CTAS = 240;   // partial buffers are sized for this many CTAs
+constexpr int HEAD_MAX_CTAS = 1184;  // 8 CTAs per SM; partial buffers (>= 4096 floats) are sized for this many
 
 // Sum `nv` per-thread values over the CTA (fixed tree), store as partial of this CTA; the last CTA to
 // arrive sums all partials in CTA order into out[0..nv).  partial[0] is the arrival counter (must be 0 on

@@ -724,7 +724,8 @@ __global__ void __launch_bounds__(128) topk_select_kernel(const float* __restric
                                    long long col_offset, const float* __restrict__ cand_val,
                                    const int* __restrict__ cand_idx, const int* __restrict__ cand_cnt,
                                    const float* __restrict__ cand_thr, float* __restrict__ out_score,
-                                   long long* __restrict__ out_idx, int* __restrict__ row_flag) {
+                                   double* __restrict__ out_score64, long long* __restrict__ out_idx,
+                                   int* __restrict__ row_flag) {
     __shared__ int s_idx[4][SEL_MAXC];
     __shared__ double s_val[4][SEL_MAXC];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -787,18 +788,22 @@ __global__ void __launch_bounds__(128) topk_select_kernel(const float* __restric
         }
         if (rank < k) {
             out_score[(long long)row * k + rank] = (float)(mv * scale);
+            if (out_score64) out_score64[(long long)row * k + rank] = mv * scale;
             out_idx[(long long)row * k + rank] = (long long)mi + col_offset;
         }
     }
     for (int p = n_s + lane; p < k; p += 32) {          // fewer than k columns exist: pad
         out_score[(long long)row * k + p] = -INFINITY;
+        if (out_score64) out_score64[(long long)row * k + p] = -INFINITY;
         out_idx[(long long)row * k + p] = -1;
     }
     if (lane == 0) row_flag[row] = overflow ? 1 : 0;
 }
 
-// thread per row: k-way merge of n_parts lists, each sorted (score desc, index asc)
-__global__ void topk_merge_kernel(const float* __restrict__ ps, const long long* __restrict__ pi, int n_parts, long long R,
+// thread per row: k-way merge of n_parts lists, each sorted (score desc, index asc).  ST = double keeps the exact
+// ordering across shards (two fp64 scores can round to the same fp32 value and would then be ordered by index)
+template <typename ST>
+__global__ void topk_merge_kernel(const ST* __restrict__ ps, const long long* __restrict__ pi, int n_parts, long long R,
                                   int k, float* __restrict__ os, long long* __restrict__ oi) {
     const long long row = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (row >= R) return;
@@ -806,18 +811,18 @@ __global__ void topk_merge_kernel(const float* __restrict__ ps, const long long*
     for (int p = 0; p < n_parts; ++p) head[p] = 0;
     for (int o = 0; o < k; ++o) {
         int best = -1;
-        float bs = 0.f;
+        ST bs = 0;
         long long bidx = 0;
         for (int p = 0; p < n_parts; ++p) {
             if (head[p] >= k) continue;
             const long long off = ((long long)p * R + row) * k + head[p];
-            const float sc = ps[off];
+            const ST sc = ps[off];
             const long long ix = pi[off];
             if (ix < 0) { head[p] = k; continue; }                      // padding: list exhausted
             if (best < 0 || sc > bs || (sc == bs && ix < bidx)) { best = p; bs = sc; bidx = ix; }
         }
         if (best < 0) { os[row * k + o] = -INFINITY; oi[row * k + o] = -1; continue; }
-        os[row * k + o] = bs;
+        os[row * k + o] = (float)bs;
         oi[row * k + o] = bidx;
         ++head[best];
     }
@@ -852,8 +857,9 @@ __global__ void __launch_bounds__(128) allpairs_rank_kernel(const float* __restr
 
 extern "C" int cfm_allpairs_topk(const float* rows_f32, const float* cols_f32, const void* rows_bf16, const void* cols_bf16,
                                  int64_t R, int64_t C, int64_t D, int64_t Dp, int64_t k, double scale, double margin,
-                                 int64_t col_offset, float* out_score, int64_t* out_idx, int32_t* row_flag,
-                                 float* cand_val, int32_t* cand_idx, int32_t* cand_cnt, float* cand_thr, void* stream_) {
+                                 int64_t col_offset, float* out_score, double* out_score64, int64_t* out_idx,
+                                 int32_t* row_flag, float* cand_val, int32_t* cand_idx, int32_t* cand_cnt, float* cand_thr,
+                                 void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     CFM_REQUIRE(rows_f32 && cols_f32 && rows_bf16 && cols_bf16 && out_score && out_idx && row_flag && cand_val &&
                     cand_idx && cand_cnt && cand_thr, CFM_ERR_INVALID, "null pointer");
@@ -872,19 +878,22 @@ extern "C" int cfm_allpairs_topk(const float* rows_f32, const float* cols_f32, c
     ProfScope prof(PROF_TOPK_POST, stream);
     topk_select_kernel<<<(int)((R + 3) / 4), 128, 0, stream>>>(rows_f32, cols_f32, (int)R, (int)C, (int)D, (int)k, 2 * chunks,
                                                              a.Rpad, (float)margin, scale, col_offset, cand_val, cand_idx,
-                                                             cand_cnt, cand_thr, out_score, (long long*)out_idx, row_flag);
+                                                             cand_cnt, cand_thr, out_score, out_score64, (long long*)out_idx, row_flag);
     CFM_LAUNCH_CHECK();
     return CFM_OK;
 }
 
-extern "C" int cfm_topk_merge(const float* part_score, const int64_t* part_idx, int64_t n_parts, int64_t R, int64_t k,
-                              float* out_score, int64_t* out_idx, void* stream) {
+extern "C" int cfm_topk_merge(const void* part_score, int64_t score_is_f64, const int64_t* part_idx, int64_t n_parts,
+                              int64_t R, int64_t k, float* out_score, int64_t* out_idx, void* stream) {
     CFM_REQUIRE(part_score && part_idx && out_score && out_idx && n_parts >= 1 && n_parts <= 16 && k >= 1,
                 CFM_ERR_INVALID, "bad merge arguments (1 <= n_parts <= 16)");
     if (R == 0) return CFM_OK;
-    topk_merge_kernel<<<(int)((R + 127) / 128), 128, 0, (cudaStream_t)stream>>>(part_score, (const long long*)part_idx,
-                                                                              (int)n_parts, R, (int)k, out_score,
-                                                                              (long long*)out_idx);
+    if (score_is_f64)
+        topk_merge_kernel<double><<<(int)((R + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+            (const double*)part_score, (const long long*)part_idx, (int)n_parts, R, (int)k, out_score, (long long*)out_idx);
+    else
+        topk_merge_kernel<float><<<(int)((R + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+            (const float*)part_score, (const long long*)part_idx, (int)n_parts, R, (int)k, out_score, (long long*)out_idx);
     CFM_LAUNCH_CHECK();
     return CFM_OK;
 }

@@ -143,14 +143,14 @@ int cfm_cosine_head_fwd(const float* u, const float* v, const float* logit_scale
                         double eps, float* score /* [B] */, float* u_hat /* nullable [B,D] */,
                         float* v_hat /* nullable [B,D] */, const float* target /* nullable [B] */,
                         const float* weights /* nullable [B] */, float* loss /* nullable [1] */,
-                        float* partial /* >= 1024 floats, zero on first use; needed with loss */, void* stream);
+                        float* partial /* >= 4096 floats, zero on first use; needed with loss */, void* stream);
 /* backward: d_score [B] and/or the weighted-MSE gradient 2 w (s-t) g_loss / B (when target/weights given;
  * g_loss = device scalar dL/dloss, nullable = 1), plus optional gradients flowing into the unit latents. */
 int cfm_cosine_head_bwd(const float* u, const float* v, const float* logit_scale, const float* d_score /* nullable */,
                         const float* d_uhat /* nullable [B,D] */, const float* d_vhat /* nullable [B,D] */,
                         const float* target /* nullable */, const float* weights /* nullable */,
                         const float* g_loss /* nullable */, int64_t B, int64_t D, double eps, float* du, float* dv,
-                        float* d_logit_scale /* [1] */, float* partial /* >= 1024 floats */, void* stream);
+                        float* d_logit_scale /* [1] */, float* partial /* >= 4096 floats */, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Structural head: softmax(c_logits) . A . softmax(f_logits) expected match, KL distillation loss and
@@ -164,7 +164,7 @@ int cfm_structural_head(const float* c_logits, const float* f_logits, const floa
                         const float* target_ceo, const float* target_firm, const float* d_match,
                         int64_t B, double kl_scale, float* match /* [B] */, float* loss /* [1] nullable */,
                         float* d_c_logits /* nullable [B,5] */, float* d_f_logits /* nullable [B,5] */,
-                        float* partial /* >= 1024 floats */, void* stream);
+                        float* partial /* >= 4096 floats */, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * InfoNCE (tcgen05 / TMEM / TMA).  Operands are bf16 row-major [rows, Dp], Dp in {64, 128} (features zero-padded
@@ -209,12 +209,14 @@ int cfm_simtile_scores(const void* x_bf16, const void* y_bf16, int64_t R, int64_
 #define CFM_TOPK_CAP 384
 int cfm_allpairs_topk(const float* rows_f32, const float* cols_f32, const void* rows_bf16, const void* cols_bf16,
                       int64_t R, int64_t C, int64_t D, int64_t Dp, int64_t k, double scale, double margin,
-                      int64_t col_offset, float* out_score /* [R,k] */, int64_t* out_idx /* [R,k] */,
-                      int32_t* row_flag /* [R] */, float* cand_val, int32_t* cand_idx, int32_t* cand_cnt,
-                      float* cand_thr, void* stream);
-/* merge `n_parts` (<= 16) per-shard top-k lists [n_parts,R,k] into the global top-k (score desc, index asc) */
-int cfm_topk_merge(const float* part_score, const int64_t* part_idx, int64_t n_parts, int64_t R, int64_t k,
-                   float* out_score, int64_t* out_idx, void* stream);
+                      int64_t col_offset, float* out_score /* [R,k] */, double* out_score64 /* [R,k] nullable */,
+                      int64_t* out_idx /* [R,k] */, int32_t* row_flag /* [R] */, float* cand_val, int32_t* cand_idx,
+                      int32_t* cand_cnt, float* cand_thr, void* stream);
+/* merge `n_parts` (<= 16) per-shard top-k lists [n_parts,R,k] into the global top-k (score desc, index asc).
+ * Pass the fp64 scores of cfm_allpairs_topk (score_is_f64 = 1) to keep the exact cross-shard ordering: two fp64
+ * scores may round to the same fp32 value. */
+int cfm_topk_merge(const void* part_score, int64_t score_is_f64, const int64_t* part_idx, int64_t n_parts, int64_t R,
+                   int64_t k, float* out_score, int64_t* out_idx, void* stream);
 /* 1-indexed rank of column target_col[i] in row i: 1 + #{j : s_ij > s_it or (s_ij == s_it and j < t)}
  * (contrastive.py:312-320), scores formed in fp64 from the fp32 operands */
 int cfm_allpairs_rank(const float* rows_f32, const float* cols_f32, int64_t R, int64_t C, int64_t D,

@@ -73,9 +73,12 @@ def test_sharded_columns_merge_equals_full():
     from ceo_firm_matching.scoring import merge_topk, score_topk
     u, v = _unit(500, 60, 11).to(DEV), _unit(9000, 60, 12).to(DEV)
     full_s, full_i = score_topk(u, v, 100, SCALE)
-    parts = [score_topk(u, v[a:b], 100, SCALE, col_offset=a) for a, b in ((0, 2000), (2000, 2100), (2100, 9000))]
-    ms, mi = merge_topk(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]))
+    parts = [score_topk(u, v[a:b], 100, SCALE, col_offset=a, return_f64=True)
+             for a, b in ((0, 2000), (2000, 2100), (2100, 9000))]
+    ms, mi = merge_topk(torch.stack([p[2] for p in parts]), torch.stack([p[1] for p in parts]))   # fp64 scores
     assert torch.equal(mi, full_i) and torch.equal(ms, full_s)
+    ms32, mi32 = merge_topk(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]))
+    assert float((mi32 == full_i).float().mean()) > 0.999          # fp32 merge: exact up to fp32-rounding ties
 
 
 def test_diagonal_ranks_and_retrieval_metrics():
