@@ -35,15 +35,31 @@ __device__ void cta_reduce_finish(float (&v)[NV], float* partial, float* const (
         is_last = prev == gridDim.x - 1;
     }
     __syncthreads();
-    if (is_last && threadIdx.x == 0) {
+    if (is_last) {
+        // every thread sums a strided subset of the per-CTA partials in a fixed order, then a fixed tree: the
+        // result does not depend on which CTA happened to arrive last
         __threadfence();
+        __shared__ float sm_fin[NV][HEAD_NT];
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
             float s = 0.f;
-            for (unsigned b = 0; b < gridDim.x; ++b) s += reinterpret_cast<volatile float*>(partial)[8 + b * NV + i];
-            if (out[i]) *out[i] = s * scale[i];
+            for (unsigned b = threadIdx.x; b < gridDim.x; b += HEAD_NT)
+                s += reinterpret_cast<volatile float*>(partial)[8 + b * NV + i];
+            sm_fin[i][threadIdx.x] = s;
         }
-        *reinterpret_cast<unsigned*>(partial) = 0u;
+        __syncthreads();
+        for (int off = HEAD_NT / 2; off > 0; off >>= 1) {
+            if (threadIdx.x < off)
+#pragma unroll
+                for (int i = 0; i < NV; ++i) sm_fin[i][threadIdx.x] += sm_fin[i][threadIdx.x + off];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i)
+                if (out[i]) *out[i] = sm_fin[i][0] * scale[i];
+            *reinterpret_cast<unsigned*>(partial) = 0u;
+        }
     }
 }
 

@@ -46,23 +46,24 @@ struct InputDesc {        // how a stage's [TM, K] input tile is built
     ActSrc a;
 };
 
-struct GemmPlan {         // register tiling of a [TM, n] output: thread (rg, cg) owns rows rg+i*NRG, cols cg+j*NCG
-    int passes, NCG, NRG, RM, wrows;
+// Warp-level tensor-core tiling (mma.sync m16n8k8, TF32 operands split 3x for fp32-class accuracy) of a
+// [TM=64, n] output: 8 warps = 2 row halves (32 rows, two m16 tiles) x 4 column groups of 8*NI columns, in passes
+// of up to 128 columns.
+struct MmaPlan {
+    int passes;
+    int wrows;            // rows of the [n, K]-style operand kept in smem (n rounded up to 32)
 };
-
-__host__ __device__ inline GemmPlan make_plan(int n) {
-    GemmPlan p;
-    int n4 = ceil_div(n, 4);
-    p.passes = ceil_div(n4, 32);
-    p.NCG = ceil_div(n4, p.passes);
-    int nrg = NT / p.NCG;
-    if (nrg > TM) nrg = TM;
-    int rm = ceil_div(TM, nrg);
-    p.RM = rm <= 1 ? 1 : rm <= 2 ? 2 : rm <= 4 ? 4 : 8;
-    p.NRG = TM / p.RM;
-    p.wrows = p.passes * 4 * p.NCG;
+__host__ __device__ inline MmaPlan make_plan(int n) {
+    MmaPlan p;
+    p.passes = ceil_div(n, 128);
+    p.wrows = (n + 31) & ~31;
     return p;
 }
+__host__ __device__ inline int pass_cols(int n, int pass) { return min(128, n - pass * 128); }
+__host__ __device__ inline int pass_ni(int cols) { return cols <= 32 ? 1 : cols <= 64 ? 2 : 4; }
+__host__ __device__ inline int ceil8(int k) { return (k + 7) & ~7; }
+// leading dimension for "transposed" fragment loads (lanes walk rows with t, columns with g): ld == 8 (mod 32)
+__host__ __device__ inline int pad_ld_t(int k) { int ld = (ceil8(k) + 31) & ~31; return ld + 8; }
 
 struct FwdStage {
     InputDesc in;
@@ -105,39 +106,41 @@ struct BwdArgs {
 struct FwdSmem {
     int lda, ws, as, bn, red, tmean, rmean, rm2, idx, total_floats;
 };
-__host__ __device__ inline FwdSmem fwd_smem(int K, int N, int n_tab, const GemmPlan& gp) {
+__host__ __device__ inline FwdSmem fwd_smem(int K, int N, int n_tab, const MmaPlan& gp) {
     FwdSmem s;
-    s.lda = pad_ld(K + 1);
+    s.lda = pad_ld(ceil8(K + 1));
     int o = 0;
     s.ws = o; o += gp.wrows * s.lda;
     s.as = o; o += TM * s.lda;
     s.bn = o; o += 4 * ((K + 3) & ~3);
-    s.red = o; o += gp.NRG * 4 * gp.NCG;
-    s.tmean = o; o += 4 * gp.NCG;
-    s.rmean = o; o += gp.wrows;
-    s.rm2 = o; o += gp.wrows;
+    s.red = o; o += 16 * 128;
+    s.tmean = o; o += 128;
+    s.rmean = o; o += gp.wrows + 128;
+    s.rm2 = o; o += gp.wrows + 128;
     s.idx = o; o += TM * (n_tab > 0 ? n_tab : 1);
     s.total_floats = (o + 3) & ~3;
     return s;
 }
 
 struct BwdSmem {
-    int lda, ldg, ldxh, wt, as, gs, xh, bna, bng, red, rs, idx, total_floats;
+    int lda, ldg, ldgt, ldxh, wt, as, gs, gt, xh, bna, bng, red, rs, idx, total_floats;
 };
-__host__ __device__ inline BwdSmem bwd_smem(int K, int N, int n_tab, int a_bn, int need_dx, const GemmPlan& gx) {
+__host__ __device__ inline BwdSmem bwd_smem(int K, int N, int n_tab, int a_bn, int need_dx, const MmaPlan& gx) {
     BwdSmem s;
-    s.lda = pad_ld(K + 1);
-    s.ldg = pad_ld(N);
+    s.lda = pad_ld_t(K + 1);            // A tile is the "transposed" B operand of the dW product
+    s.ldg = pad_ld(ceil8(N));
+    s.ldgt = pad_ld(TM);
     s.ldxh = pad_ld(K);
     int o = 0;
     s.wt = o; o += need_dx ? gx.wrows * s.ldg : 0;
     s.as = o; o += TM * s.lda;
     s.gs = o; o += TM * s.ldg;
+    s.gt = o; o += ((N + 15) & ~15) * s.ldgt;
     s.xh = o; o += a_bn ? TM * s.ldxh : 0;
     s.bna = o; o += 4 * ((K + 3) & ~3);
     s.bng = o; o += 5 * ((N + 3) & ~3);
-    s.red = o; o += 2 * gx.NRG * 4 * gx.NCG;
-    s.rs = o; o += 2 * gx.wrows;
+    s.red = o; o += 2 * 16 * 128;
+    s.rs = o; o += 2 * (gx.wrows + 128);
     s.idx = o; o += TM * (n_tab > 0 ? n_tab : 1);
     s.total_floats = (o + 3) & ~3;
     return s;
@@ -163,6 +166,20 @@ __device__ __forceinline__ void stage_bn_params(const ActSrc& a, int K, float* s
 }
 
 // Build the [TM, K] input tile (+ ones column at K, zero pad to lda); optionally the x-hat tile.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// Build the [TM, K] input tile (+ ones column at K, zero pad to lda); optionally the x-hat tile.
+// Memory-level parallelism is what matters here (every row of a 1M-row table is an HBM miss): the gather is issued
+// as asynchronous 16-byte global->shared copies, all in flight at once, and the activation rebuild loads four
+// float4 per thread before touching any of them.  The caller's __syncthreads() publishes the tile.
 __device__ void build_input_tile(const InputDesc& in, const DropCtx& drop, long long row0, int rows_valid, float* As,
                                  int lda, float* Xh, int ldxh, const float* sm_bn, int* sm_idx, int* err) {
     const int K = in.K;
@@ -182,6 +199,11 @@ __device__ void build_input_tile(const InputDesc& in, const DropCtx& drop, long 
             }
             sm_idx[i] = (int)idx;
         }
+        for (int i = tid; i < TM * g.n_num; i += NT) {              // numerics do not depend on the indices
+            int r = i / g.n_num, j = i - r * g.n_num;
+            if (r < rows_valid) cp_async4(As + r * lda + KE + j, g.x_num + (row0 + r) * g.n_num + j);
+            else As[r * lda + KE + j] = 0.f;
+        }
         __syncthreads();
         if ((g.E & 3) == 0) {
             const int E4 = g.E >> 2;
@@ -190,10 +212,9 @@ __device__ void build_input_tile(const InputDesc& in, const DropCtx& drop, long 
                 int q = i % E4;
                 int rt = i / E4;
                 int t = rt % g.n_tab, r = rt / g.n_tab;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (r < rows_valid)
-                    v = __ldg(reinterpret_cast<const float4*>(g.tab[t] + (size_t)sm_idx[rt] * g.E) + q);
-                *reinterpret_cast<float4*>(As + r * lda + t * g.E + 4 * q) = v;
+                float* dst = As + r * lda + t * g.E + 4 * q;
+                if (r < rows_valid) cp_async16(dst, g.tab[t] + (size_t)sm_idx[rt] * g.E + 4 * q);
+                else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         } else {
             const int items = TM * KE;
@@ -201,58 +222,71 @@ __device__ void build_input_tile(const InputDesc& in, const DropCtx& drop, long 
                 int e = i % g.E;
                 int rt = i / g.E;
                 int t = rt % g.n_tab, r = rt / g.n_tab;
-                float v = 0.f;
-                if (r < rows_valid) v = __ldg(g.tab[t] + (size_t)sm_idx[rt] * g.E + e);
-                As[r * lda + t * g.E + e] = v;
+                float* dst = As + r * lda + t * g.E + e;
+                if (r < rows_valid) cp_async4(dst, g.tab[t] + (size_t)sm_idx[rt] * g.E + e);
+                else *dst = 0.f;
             }
-        }
-        for (int i = tid; i < TM * g.n_num; i += NT) {
-            int r = i / g.n_num, j = i - r * g.n_num;
-            As[r * lda + KE + j] = r < rows_valid ? g.x_num[(row0 + r) * g.n_num + j] : 0.f;
         }
     } else {
         const ActSrc& a = in.a;
         const int K4 = (K + 3) >> 2, Kp = K4 << 2;
         const bool vec = (K & 3) == 0;
-        for (int i = tid; i < TM * K4; i += NT) {
-            int r = i / K4, c4 = i - r * K4;
-            const bool valid = r < rows_valid;
-            float v[4] = {0.f, 0.f, 0.f, 0.f}, xh[4] = {0.f, 0.f, 0.f, 0.f};
-            if (valid) {
-                const float* hp = a.h + (size_t)(row0 + r) * K + 4 * c4;
-                if (vec) {
-                    float4 t4 = *reinterpret_cast<const float4*>(hp);
-                    v[0] = t4.x; v[1] = t4.y; v[2] = t4.z; v[3] = t4.w;
-                } else {
+        constexpr int U = 4;
+        for (int base = tid; base < TM * K4; base += NT * U) {
+            float v[U][4];
+            // phase 1: all loads of this batch
 #pragma unroll
-                    for (int e = 0; e < 4; ++e)
-                        if (4 * c4 + e < K) v[e] = hp[e];
+            for (int u = 0; u < U; ++u) {
+                const int i = base + u * NT;
+                const int r = i / K4, c4 = i - r * K4;
+                v[u][0] = v[u][1] = v[u][2] = v[u][3] = 0.f;
+                if (i < TM * K4 && r < rows_valid) {
+                    const float* hp = a.h + (size_t)(row0 + r) * K + 4 * c4;
+                    if (vec) {
+                        float4 t4 = *reinterpret_cast<const float4*>(hp);
+                        v[u][0] = t4.x; v[u][1] = t4.y; v[u][2] = t4.z; v[u][3] = t4.w;
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (4 * c4 + e < K) v[u][e] = hp[e];
+                    }
                 }
-                Philox4 w = {0, 0, 0, 0};
-                if (drop.active) w = drop_words(drop, row0 + r, c4);
+            }
+            // phase 2: BN / ReLU / dropout and the smem stores
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = base + u * NT;
+                if (i >= TM * K4) continue;
+                const int r = i / K4, c4 = i - r * K4;
+                const bool valid = r < rows_valid;
+                float xh[4] = {0.f, 0.f, 0.f, 0.f};
+                if (valid) {
+                    Philox4 w = {0, 0, 0, 0};
+                    if (drop.active) w = drop_words(drop, row0 + r, c4);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        int c = 4 * c4 + e;
+                        if (c < K) {
+                            float t = v[u][e];
+                            if (a.bn_mode) {
+                                xh[e] = (t - sm_bn[c]) * sm_bn[Kp + c];
+                                t = xh[e] * sm_bn[2 * Kp + c] + sm_bn[3 * Kp + c];
+                            }
+                            t = fmaxf(t, 0.f);
+                            if (drop.active) t = drop_keep(drop, w, e) ? t * drop.inv_keep : 0.f;
+                            v[u][e] = t;
+                        } else {
+                            v[u][e] = 0.f;
+                        }
+                    }
+                }
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     int c = 4 * c4 + e;
                     if (c < K) {
-                        float t = v[e];
-                        if (a.bn_mode) {
-                            xh[e] = (t - sm_bn[c]) * sm_bn[Kp + c];
-                            t = xh[e] * sm_bn[2 * Kp + c] + sm_bn[3 * Kp + c];
-                        }
-                        t = fmaxf(t, 0.f);
-                        if (drop.active) t = drop_keep(drop, w, e) ? t * drop.inv_keep : 0.f;
-                        v[e] = t;
-                    } else {
-                        v[e] = 0.f;
+                        As[r * lda + c] = v[u][e];
+                        if (Xh) Xh[r * ldxh + c] = xh[e];
                     }
-                }
-            }
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                int c = 4 * c4 + e;
-                if (c < K) {
-                    As[r * lda + c] = v[e];
-                    if (Xh) Xh[r * ldxh + c] = xh[e];
                 }
             }
         }
@@ -262,132 +296,153 @@ __device__ void build_input_tile(const InputDesc& in, const DropCtx& drop, long 
         int r = i / (lda - K), c = K + (i - r * (lda - K));
         As[r * lda + c] = (c == K && r < rows_valid) ? 1.f : 0.f;
     }
+    if (in.stage == 1) cp_async_wait_all();
 }
 
 // ------------------------------------------------------------------------------------------
-// register-tiled GEMMs on shared-memory operands
+// tensor-core GEMMs on shared-memory operands (mma.sync m16n8k8, 3xTF32 error-compensated)
 // ------------------------------------------------------------------------------------------
-// acc[i][j] = sum_k X[rg + i*NRG][k] * W[pass*4*NCG + cg + j*NCG][k], k over 4*k4n columns
-template <int RM>
-__device__ __forceinline__ void gemm_rows(const float* __restrict__ Xs, int ldx, const float* __restrict__ Ws,
-                                          int ldw, int k4n, int rg, int cg, int NRG, int NCG, int pass,
-                                          float (&acc)[RM][4]) {
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+    lo = __float_as_uint(x - __uint_as_float(hi));      // exact remainder; the MMA reads its top 19 bits
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// c += a * b with a = a_hi + a_lo, b = b_hi + b_lo (lo*lo dropped: 2^-22 relative)
+__device__ __forceinline__ void mma_3xtf32(float (&c)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
+                                           const uint32_t (&bh)[2], const uint32_t (&bl)[2]) {
+    mma_tf32(c, al, bh);
+    mma_tf32(c, ah, bl);
+    mma_tf32(c, ah, bh);
+}
+
+// acc[mi][ni][.] = X[r0 + mi*16 .. +15][:] . W[n0 + ni*8 .. +7][:]^T over k8n steps of 8 columns.
+// Fragment loads are scalar LDS; both leading dimensions are 4 (mod 8) so the 32 lanes hit 32 distinct banks.
+template <int NI>
+__device__ __forceinline__ void mma_rows(const float* __restrict__ Xs, int ldx, const float* __restrict__ Ws, int ldw,
+                                         int k8n, int r0, int n0, int lane, float (&acc)[2][NI][4]) {
+    const int g = lane >> 2, t = lane & 3;
 #pragma unroll
-    for (int i = 0; i < RM; ++i)
+    for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    const float4* xp = reinterpret_cast<const float4*>(Xs + rg * ldx);
-    const float4* wp = reinterpret_cast<const float4*>(Ws + (pass * 4 * NCG + cg) * ldw);
-    const int xs = NRG * (ldx >> 2), ws = NCG * (ldw >> 2);
+        for (int ni = 0; ni < NI; ++ni)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[mi][ni][c] = 0.f;
+    const float* xp = Xs + (r0 + g) * ldx + t;
+    const float* wp = Ws + (n0 + g) * ldw + t;
 #pragma unroll 2
-    for (int k = 0; k < k4n; ++k) {
-        float4 w[4], x[RM];
+    for (int k8 = 0; k8 < k8n; ++k8) {
+        uint32_t ah[2][4], al[2][4], bh[NI][2], bl[NI][2];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) w[j] = wp[j * ws + k];
+        for (int mi = 0; mi < 2; ++mi) {
+            const float* p = xp + mi * 16 * ldx + k8 * 8;
+            split_tf32(p[0], ah[mi][0], al[mi][0]);
+            split_tf32(p[8 * ldx], ah[mi][1], al[mi][1]);
+            split_tf32(p[4], ah[mi][2], al[mi][2]);
+            split_tf32(p[8 * ldx + 4], ah[mi][3], al[mi][3]);
+        }
 #pragma unroll
-        for (int i = 0; i < RM; ++i) x[i] = xp[i * xs + k];
+        for (int ni = 0; ni < NI; ++ni) {
+            const float* p = wp + ni * 8 * ldw + k8 * 8;
+            split_tf32(p[0], bh[ni][0], bl[ni][0]);
+            split_tf32(p[4], bh[ni][1], bl[ni][1]);
+        }
 #pragma unroll
-        for (int i = 0; i < RM; ++i)
+        for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                acc[i][j] = fmaf(x[i].x, w[j].x, acc[i][j]);
-                acc[i][j] = fmaf(x[i].y, w[j].y, acc[i][j]);
-                acc[i][j] = fmaf(x[i].z, w[j].z, acc[i][j]);
-                acc[i][j] = fmaf(x[i].w, w[j].w, acc[i][j]);
-            }
+            for (int ni = 0; ni < NI; ++ni) mma_3xtf32(acc[mi][ni], ah[mi], al[mi], bh[ni], bl[ni]);
     }
 }
-
-// dW accumulators: acc[a][b][e][f] += sum_r G[r][4*(ng+a*NG)+e] * A[r][4*(kg+b*KG)+f]
-template <int RN4, int RK4>
-__device__ __forceinline__ void dw_accum(const float* __restrict__ Gs, int ldg, const float* __restrict__ As, int lda,
-                                         const int (&gi)[RN4], const int (&ki)[RK4], float (&acc)[RN4][RK4][4][4]) {
-#pragma unroll 4
-    for (int r = 0; r < TM; ++r) {
-        float4 g[RN4], x[RK4];
-#pragma unroll
-        for (int a = 0; a < RN4; ++a) g[a] = *reinterpret_cast<const float4*>(Gs + r * ldg + 4 * gi[a]);
-#pragma unroll
-        for (int b = 0; b < RK4; ++b) x[b] = *reinterpret_cast<const float4*>(As + r * lda + 4 * ki[b]);
-#pragma unroll
-        for (int a = 0; a < RN4; ++a)
-#pragma unroll
-            for (int b = 0; b < RK4; ++b) {
-                const float ge[4] = {g[a].x, g[a].y, g[a].z, g[a].w};
-                const float xf[4] = {x[b].x, x[b].y, x[b].z, x[b].w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e)
-#pragma unroll
-                    for (int f = 0; f < 4; ++f) acc[a][b][e][f] = fmaf(ge[e], xf[f], acc[a][b][e][f]);
-            }
-    }
-}
-
 
 struct FwdCtx {
     const float *As, *Ws;
     float *red, *tmean, *rmean, *rm2, *hout;
-    int lda, k4n, rg, cg, NRG, NCG, cpp, N;
-    bool active, stats;
+    int lda, k8n, N;
+    bool stats;
 };
 
-// one column pass of a forward tile: GEMM, store raw output, optional (count, mean, M2) statistics
-template <int RM>
-__device__ __forceinline__ void fwd_pass(const FwdCtx& C, int pass, long long row0, int rows_valid, float run_cnt) {
-    const int tid = threadIdx.x;
-    float acc[RM][4];
-    if (C.active) {
-        gemm_rows<RM>(C.As, C.lda, C.Ws, C.lda, C.k4n, C.rg, C.cg, C.NRG, C.NCG, pass, acc);
+// one column pass (<= 128 columns) of a forward tile: GEMM, store raw output, optional (count, mean, M2) statistics
+template <int NI>
+__device__ __forceinline__ void fwd_pass(const FwdCtx& C, int pass, int cols, long long row0, int rows_valid, float run_cnt) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wr = warp >> 2, wc = warp & 3, g = lane >> 2, t = lane & 3;
+    const int n0 = pass * 128 + wc * 8 * NI;
+    const bool active = wc * 8 * NI < cols;
+    float acc[2][NI][4];
+    if (active) {
+        mma_rows<NI>(C.As, C.lda, C.Ws, C.lda, C.k8n, wr * 32, n0, lane, acc);
 #pragma unroll
-        for (int i = 0; i < RM; ++i) {
-            int r = C.rg + i * C.NRG;
-            if (r < rows_valid) {
+        for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    int c = pass * C.cpp + C.cg + j * C.NCG;
-                    if (c < C.N) C.hout[(size_t)(row0 + r) * C.N + c] = acc[i][j];
+            for (int h = 0; h < 2; ++h) {
+                const int r = wr * 32 + mi * 16 + g + 8 * h;
+                if (r < rows_valid) {
+#pragma unroll
+                    for (int ni = 0; ni < NI; ++ni) {
+                        const int c = n0 + ni * 8 + 2 * t;
+                        float* dst = C.hout + (size_t)(row0 + r) * C.N + c;
+                        if (c < C.N) dst[0] = acc[mi][ni][2 * h];
+                        if (c + 1 < C.N) dst[1] = acc[mi][ni][2 * h + 1];
+                    }
                 }
             }
-        }
     }
     if (!C.stats) return;
-    // pass A: tile mean per column
-    if (C.active) {
+    // pass A: tile mean per column.  red[(wr*8+g)][local column]: 16 partial rows per column
+    float* myred = C.red + (wr * 8 + g) * 128 + wc * 8 * NI + 2 * t;
+    if (active) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float s = 0.f;
+        for (int ni = 0; ni < NI; ++ni)
 #pragma unroll
-            for (int i = 0; i < RM; ++i)
-                if (C.rg + i * C.NRG < rows_valid) s += acc[i][j];
-            C.red[C.rg * C.cpp + C.cg + j * C.NCG] = s;
-        }
+            for (int e = 0; e < 2; ++e) {
+                float s = 0.f;
+#pragma unroll
+                for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+                        if (wr * 32 + mi * 16 + g + 8 * h < rows_valid) s += acc[mi][ni][2 * h + e];
+                myred[ni * 8 + e] = s;
+            }
     }
     __syncthreads();
-    if (tid < C.cpp) {
-        float t = 0.f;
-        for (int g = 0; g < C.NRG; ++g) t += C.red[g * C.cpp + tid];
-        C.tmean[tid] = t / (float)rows_valid;
+    if (tid < cols) {
+        float s = 0.f;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) s += C.red[q * 128 + tid];
+        C.tmean[tid] = s / (float)rows_valid;
     }
     __syncthreads();
     // pass B: tile M2 around the tile mean
-    if (C.active) {
+    if (active) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float m = C.tmean[C.cg + j * C.NCG], s = 0.f;
+        for (int ni = 0; ni < NI; ++ni)
 #pragma unroll
-            for (int i = 0; i < RM; ++i)
-                if (C.rg + i * C.NRG < rows_valid) { float d = acc[i][j] - m; s = fmaf(d, d, s); }
-            C.red[C.rg * C.cpp + C.cg + j * C.NCG] = s;
-        }
+            for (int e = 0; e < 2; ++e) {
+                const float m = C.tmean[wc * 8 * NI + ni * 8 + 2 * t + e];
+                float s = 0.f;
+#pragma unroll
+                for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+                        if (wr * 32 + mi * 16 + g + 8 * h < rows_valid) {
+                            const float d = acc[mi][ni][2 * h + e] - m;
+                            s = fmaf(d, d, s);
+                        }
+                myred[ni * 8 + e] = s;
+            }
     }
     __syncthreads();
-    if (tid < C.cpp) {
+    if (tid < cols) {
         float m2 = 0.f;
-        for (int g = 0; g < C.NRG; ++g) m2 += C.red[g * C.cpp + tid];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) m2 += C.red[q * 128 + tid];
         // Chan merge of (run_cnt, rmean, rm2) with (rows_valid, tmean, m2)
-        int c = pass * C.cpp + tid;
-        float na = run_cnt, nb = (float)rows_valid, n = na + nb;
-        float d = C.tmean[tid] - C.rmean[c];
+        const int c = pass * 128 + tid;
+        const float na = run_cnt, nb = (float)rows_valid, n = na + nb;
+        const float d = C.tmean[tid] - C.rmean[c];
         C.rmean[c] += d * (nb / n);
         C.rm2[c] += m2 + d * d * (na * nb / n);
     }
@@ -397,14 +452,14 @@ __device__ __forceinline__ void fwd_pass(const FwdCtx& C, int pass, long long ro
 // ------------------------------------------------------------------------------------------
 // forward stage kernel
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NT, 1) tower_fwd_stage(const __grid_constant__ FwdArgs args) {
+__global__ void __launch_bounds__(NT, 2) tower_fwd_stage(const __grid_constant__ FwdArgs args) {
     const FwdStage& S = args.st[blockIdx.y];
     extern __shared__ float4 smem4[];
     float* sm = reinterpret_cast<float*>(smem4);
     const int K = S.in.K, N = S.N;
-    const GemmPlan gp = make_plan(N);
+    const MmaPlan gp = make_plan(N);
     const FwdSmem L = fwd_smem(K, N, S.in.g.n_tab, gp);
-    float *Ws = sm + L.ws, *As = sm + L.as, *sm_bn = sm + L.bn, *red = sm + L.red, *tmean = sm + L.tmean;
+    float *Ws = sm + L.ws, *As = sm + L.as, *sm_bn = sm + L.bn;
     float *rmean = sm + L.rmean, *rm2 = sm + L.rm2;
     int* sm_idx = reinterpret_cast<int*>(sm + L.idx);
     const int tid = threadIdx.x, lda = L.lda;
@@ -413,29 +468,32 @@ __global__ void __launch_bounds__(NT, 1) tower_fwd_stage(const __grid_constant__
     const DropCtx drop = resolve_drop(S.in.a.drop);
 
     // weights -> smem, [wrows][lda] with bias in column K and zeros elsewhere in the padding
-    for (int i = tid; i < gp.wrows * lda; i += NT) {
-        int n = i / lda, c = i - n * lda;
-        float v = 0.f;
-        if (n < N) {
-            if (c < K) v = S.W[(size_t)n * K + (S.in.stage == 1 ? gcol_stage1(c, KE, S.in.g.n_num) : c)];
-            else if (c == K) v = S.bias[n];
+    // (eight independent loads in flight per thread: the staging is pure latency otherwise)
+    for (int base = tid; base < gp.wrows * lda; base += NT * 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = base + u * NT;
+            const int n = i / lda, c = i - n * lda;
+            v[u] = 0.f;
+            if (i < gp.wrows * lda && n < N) {
+                if (c < K) v[u] = __ldg(S.W + (size_t)n * K + (S.in.stage == 1 ? gcol_stage1(c, KE, S.in.g.n_num) : c));
+                else if (c == K) v[u] = __ldg(S.bias + n);
+            }
         }
-        Ws[i] = v;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (base + u * NT < gp.wrows * lda) Ws[base + u * NT] = v[u];
     }
     if (S.in.stage > 1) stage_bn_params(S.in.a, K, sm_bn);
-    for (int i = tid; i < gp.wrows; i += NT) { rmean[i] = 0.f; rm2[i] = 0.f; }
+    for (int i = tid; i < gp.wrows + 128; i += NT) { rmean[i] = 0.f; rm2[i] = 0.f; }
     float run_cnt = 0.f;   // identical in every thread
     __syncthreads();
 
-    const int cg = tid % gp.NCG, rg = tid / gp.NCG;
-    const bool active = rg < gp.NRG;
-    const int k4n = (K + 1 + 3) >> 2;
-    const int cpp = 4 * gp.NCG;   // columns per pass
-    const long long ntiles = (args.B + TM - 1) / TM;
     FwdCtx C;
-    C.As = As; C.Ws = Ws; C.red = red; C.tmean = tmean; C.rmean = rmean; C.rm2 = rm2; C.hout = S.hout;
-    C.lda = lda; C.k4n = k4n; C.rg = rg; C.cg = cg; C.NRG = gp.NRG; C.NCG = gp.NCG; C.cpp = cpp; C.N = N;
-    C.active = active; C.stats = stats;
+    C.As = As; C.Ws = Ws; C.red = sm + L.red; C.tmean = sm + L.tmean; C.rmean = rmean; C.rm2 = rm2; C.hout = S.hout;
+    C.lda = lda; C.k8n = ceil8(K + 1) >> 3; C.N = N; C.stats = stats;
+    const long long ntiles = (args.B + TM - 1) / TM;
 
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long long row0 = tile * TM;
@@ -443,11 +501,11 @@ __global__ void __launch_bounds__(NT, 1) tower_fwd_stage(const __grid_constant__
         build_input_tile(S.in, drop, row0, rows_valid, As, lda, nullptr, 0, sm_bn, sm_idx, args.err);
         __syncthreads();
         for (int pass = 0; pass < gp.passes; ++pass) {
-            switch (gp.RM) {
-                case 1: fwd_pass<1>(C, pass, row0, rows_valid, run_cnt); break;
-                case 2: fwd_pass<2>(C, pass, row0, rows_valid, run_cnt); break;
-                case 4: fwd_pass<4>(C, pass, row0, rows_valid, run_cnt); break;
-                default: fwd_pass<8>(C, pass, row0, rows_valid, run_cnt); break;
+            const int cols = pass_cols(N, pass);
+            switch (pass_ni(cols)) {
+                case 1: fwd_pass<1>(C, pass, cols, row0, rows_valid, run_cnt); break;
+                case 2: fwd_pass<2>(C, pass, cols, row0, rows_valid, run_cnt); break;
+                default: fwd_pass<4>(C, pass, cols, row0, rows_valid, run_cnt); break;
             }
         }
         run_cnt += (float)rows_valid;
@@ -511,55 +569,69 @@ __global__ void bn_fwd_finalize(const __grid_constant__ BnFwdFinArgs args) {
 struct BwdCtx {
     const float *As, *Gs, *Wt, *Xh;
     float *red, *rs;
-    int lda, ldg, ldxh, n4n, rg, cg, NRG, NCG, cpp, wrows, K, KE, n_num;
+    int lda, ldg, ldxh, n8n, rs_stride, K, KE, n_num;
     float inv_keep;
-    bool active, stage1;
+    bool stage1;
 };
 
-// one column pass of the dX GEMM of a backward tile (+ ReLU/dropout mask, BN-backward sums)
-template <int RM>
-__device__ __forceinline__ void bwd_dx_pass(const BwdStage& S, const BwdCtx& C, int pass, long long row0, int rows_valid) {
-    const int tid = threadIdx.x;
-    float acc[RM][4];
-    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
-    if (C.active) {
-        gemm_rows<RM>(C.Gs, C.ldg, C.Wt, C.ldg, C.n4n, C.rg, C.cg, C.NRG, C.NCG, pass, acc);
+// one column pass (<= 128 columns of K) of the dX product of a backward tile (+ ReLU/dropout mask, BN-backward sums)
+template <int NI>
+__device__ __forceinline__ void bwd_dx_pass(const BwdStage& S, const BwdCtx& C, int pass, int cols, long long row0,
+                                            int rows_valid) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wr = warp >> 2, wc = warp & 3, g = lane >> 2, t = lane & 3;
+    const int k0 = pass * 128 + wc * 8 * NI;
+    const bool active = wc * 8 * NI < cols;
+    float acc[2][NI][4];
+    float s1[NI][2], s2[NI][2];
 #pragma unroll
-        for (int i = 0; i < RM; ++i) {
-            int r = C.rg + i * C.NRG;
-            if (r < rows_valid) {
+    for (int ni = 0; ni < NI; ++ni) { s1[ni][0] = s1[ni][1] = s2[ni][0] = s2[ni][1] = 0.f; }
+    if (active) {
+        mma_rows<NI>(C.Gs, C.ldg, C.Wt, C.ldg, C.n8n, wr * 32, k0, lane, acc);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    int c = pass * C.cpp + C.cg + j * C.NCG;
-                    if (c < C.K) {
-                        if (C.stage1) {
-                            if (c < C.KE) { if (S.dx_emb) S.dx_emb[(size_t)(row0 + r) * C.KE + c] = acc[i][j]; }
-                            else if (S.dx_num) S.dx_num[(size_t)(row0 + r) * C.n_num + (c - C.KE)] = acc[i][j];
-                        } else {
-                            float dy = C.As[r * C.lda + c] > 0.f ? acc[i][j] * C.inv_keep : 0.f;
-                            S.dy_out[(size_t)(row0 + r) * C.K + c] = dy;
-                            if (S.a_bn) { s1[j] += dy; s2[j] = fmaf(dy, C.Xh[r * C.ldxh + c], s2[j]); }
+        for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int r = wr * 32 + mi * 16 + g + 8 * h;
+                if (r < rows_valid) {
+#pragma unroll
+                    for (int ni = 0; ni < NI; ++ni)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int c = k0 + ni * 8 + 2 * t + e;
+                            const float v = acc[mi][ni][2 * h + e];
+                            if (c < C.K) {
+                                if (C.stage1) {
+                                    if (c < C.KE) { if (S.dx_emb) S.dx_emb[(size_t)(row0 + r) * C.KE + c] = v; }
+                                    else if (S.dx_num) S.dx_num[(size_t)(row0 + r) * C.n_num + (c - C.KE)] = v;
+                                } else {
+                                    const float dy = C.As[r * C.lda + c] > 0.f ? v * C.inv_keep : 0.f;
+                                    S.dy_out[(size_t)(row0 + r) * C.K + c] = dy;
+                                    if (S.a_bn) { s1[ni][e] += dy; s2[ni][e] = fmaf(dy, C.Xh[r * C.ldxh + c], s2[ni][e]); }
+                                }
+                            }
                         }
-                    }
                 }
             }
-        }
     }
     if (!S.a_bn) return;
-    const int half = C.NRG * C.cpp;
-    if (C.active) {
+    float* myred = C.red + (wr * 8 + g) * 128 + wc * 8 * NI + 2 * t;
+    if (active) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            C.red[C.rg * C.cpp + C.cg + j * C.NCG] = s1[j];
-            C.red[half + C.rg * C.cpp + C.cg + j * C.NCG] = s2[j];
-        }
+        for (int ni = 0; ni < NI; ++ni)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                myred[ni * 8 + e] = s1[ni][e];
+                myred[16 * 128 + ni * 8 + e] = s2[ni][e];
+            }
     }
     __syncthreads();
-    if (tid < 2 * C.cpp) {
-        int which = tid / C.cpp, cl = tid - which * C.cpp;
-        float t = 0.f;
-        for (int g = 0; g < C.NRG; ++g) t += C.red[which * half + g * C.cpp + cl];
-        C.rs[which * C.wrows + pass * C.cpp + cl] += t;
+    if (tid < 2 * cols) {
+        const int which = tid >= cols, cl = tid - which * cols;
+        float tsum = 0.f;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) tsum += C.red[which * 16 * 128 + q * 128 + cl];
+        C.rs[which * C.rs_stride + pass * 128 + cl] += tsum;
     }
     __syncthreads();
 }
@@ -567,34 +639,48 @@ __device__ __forceinline__ void bwd_dx_pass(const BwdStage& S, const BwdCtx& C, 
 // ------------------------------------------------------------------------------------------
 // backward stage kernel
 // ------------------------------------------------------------------------------------------
-template <int RN4, int RK4>
-__device__ void bwd_stage_body(const BwdStage& S, long long B, float* sm) {
+constexpr int DW_MAX_TILES = 16;   // m16n8 output tiles of dW per warp (N*(K+1) <= 16384)
+
+__global__ void __launch_bounds__(NT, 2) tower_bwd_stage(const __grid_constant__ BwdArgs args) {
+    const BwdStage& S = args.st[blockIdx.y];
+    const long long B = args.B;
+    extern __shared__ float4 smem4[];
+    float* sm = reinterpret_cast<float*>(smem4);
     const int K = S.in.K, N = S.N;
-    const GemmPlan gx = make_plan(K);   // dX: [TM, K] output, reduction over N
+    const MmaPlan gx = make_plan(K);   // dX: [TM, K] output, reduction over N
     const BwdSmem L = bwd_smem(K, N, S.in.g.n_tab, S.a_bn, S.need_dx, gx);
-    float *Wt = sm + L.wt, *As = sm + L.as, *Gs = sm + L.gs, *Xh = S.a_bn ? sm + L.xh : nullptr;
-    float *sm_bna = sm + L.bna, *sm_bng = sm + L.bng, *red = sm + L.red, *rs = sm + L.rs;
+    float *Wt = sm + L.wt, *As = sm + L.as, *Gs = sm + L.gs, *Gt = sm + L.gt, *Xh = S.a_bn ? sm + L.xh : nullptr;
+    float *sm_bna = sm + L.bna, *sm_bng = sm + L.bng, *rs = sm + L.rs;
     int* sm_idx = reinterpret_cast<int*>(sm + L.idx);
-    const int tid = threadIdx.x, lda = L.lda, ldg = L.ldg, ldxh = L.ldxh;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lda = L.lda, ldg = L.ldg, ldgt = L.ldgt, ldxh = L.ldxh;
     const int KE = S.in.g.n_tab * S.in.g.E, n_num = S.in.g.n_num;
     const int Np = (N + 3) & ~3;
     const bool stage1 = S.in.stage == 1;
     const DropCtx drop = resolve_drop(S.in.a.drop);
+    const int rs_stride = gx.wrows + 128;
 
     // W^T -> smem: Wt[k'][n] (k' in tile column order), zero padded
     if (S.need_dx) {
-        for (int i = tid; i < gx.wrows * ldg; i += NT) {
-            int k = i / ldg, n = i - k * ldg;
-            float v = 0.f;
-            if (k < K && n < N) v = S.W[(size_t)n * K + (stage1 ? gcol_stage1(k, KE, n_num) : k)];
-            Wt[i] = v;
+        for (int base = tid; base < gx.wrows * ldg; base += NT * 8) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = base + u * NT;
+                const int k = i / ldg, n = i - k * ldg;
+                v[u] = (i < gx.wrows * ldg && k < K && n < N)
+                           ? __ldg(S.W + (size_t)n * K + (stage1 ? gcol_stage1(k, KE, n_num) : k)) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (base + u * NT < gx.wrows * ldg) Wt[base + u * NT] = v[u];
         }
     }
     if (!stage1) stage_bn_params(S.in.a, K, sm_bna);
     if (S.g_mode) {
         for (int c = tid; c < N; c += NT) {
-            float s = S.g_var_or_istd[c];
-            float istd = S.g_mode == 2 ? rsqrtf(s + BN_EPS) : s;
+            float sv = S.g_var_or_istd[c];
+            float istd = S.g_mode == 2 ? rsqrtf(sv + BN_EPS) : sv;
             sm_bng[c] = S.g_mean[c];
             sm_bng[Np + c] = istd;
             sm_bng[2 * Np + c] = S.g_gamma[c] * istd;
@@ -602,39 +688,23 @@ __device__ void bwd_stage_body(const BwdStage& S, long long B, float* sm) {
             sm_bng[4 * Np + c] = S.g_mode == 1 ? S.g_c2[c] : 0.f;
         }
     }
-    for (int i = tid; i < 2 * gx.wrows; i += NT) rs[i] = 0.f;
+    for (int i = tid; i < 2 * rs_stride; i += NT) rs[i] = 0.f;
+    // the G^T tile's padding rows (n >= N) stay zero for the whole kernel
+    for (int i = tid; i < ((N + 15) & ~15) * ldgt; i += NT) Gt[i] = 0.f;
 
-    // dW thread layout
-    const int N4 = (N + 3) >> 2, K4 = (K + 1 + 3) >> 2;
-    const int NG = ceil_div(N4, RN4), KG = ceil_div(K4, RK4);
-    const int kg = tid % KG, ng = tid / KG;
-    const bool dw_active = ng < NG;
-    int gi[RN4], ki[RK4];
+    // dW = G^T . [A | 1]: m16n8 output tiles (n-tile, k-tile), tile q = warp + 8*i belongs to this warp
+    const int NTN = (N + 15) >> 4, KT = ceil8(K + 1) >> 3, n_dw_tiles = NTN * KT;
+    float dw[DW_MAX_TILES][4];
 #pragma unroll
-    for (int a = 0; a < RN4; ++a) gi[a] = min(ng + a * NG, N4 - 1);
-#pragma unroll
-    for (int b = 0; b < RK4; ++b) ki[b] = min(kg + b * KG, K4 - 1);
-    float dw[RN4][RK4][4][4];
-#pragma unroll
-    for (int a = 0; a < RN4; ++a)
-#pragma unroll
-        for (int b = 0; b < RK4; ++b)
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-#pragma unroll
-                for (int f = 0; f < 4; ++f) dw[a][b][e][f] = 0.f;
+    for (int i = 0; i < DW_MAX_TILES; ++i) dw[i][0] = dw[i][1] = dw[i][2] = dw[i][3] = 0.f;
+    const int g = lane >> 2, t = lane & 3;
 
-    // dX thread layout
-    const int cg = tid % gx.NCG, rg = tid / gx.NCG;
-    const bool dx_active = rg < gx.NRG;
-    const int n4n = (N + 3) >> 2;
-    const int cpp = 4 * gx.NCG;
-    const float inv_keep = (!stage1 && S.in.a.drop.active) ? S.in.a.drop.inv_keep : 1.f;
     BwdCtx C;
-    C.As = As; C.Gs = Gs; C.Wt = Wt; C.Xh = Xh; C.red = red; C.rs = rs;
-    C.lda = lda; C.ldg = ldg; C.ldxh = ldxh; C.n4n = n4n; C.rg = rg; C.cg = cg; C.NRG = gx.NRG; C.NCG = gx.NCG;
-    C.cpp = cpp; C.wrows = gx.wrows; C.K = K; C.KE = KE; C.n_num = n_num; C.inv_keep = inv_keep;
-    C.active = dx_active; C.stage1 = stage1;
+    C.As = As; C.Gs = Gs; C.Wt = Wt; C.Xh = Xh; C.red = sm + L.red; C.rs = rs;
+    C.lda = lda; C.ldg = ldg; C.ldxh = ldxh; C.n8n = ceil8(N) >> 3; C.rs_stride = rs_stride;
+    C.K = K; C.KE = KE; C.n_num = n_num;
+    C.inv_keep = (!stage1 && drop.active) ? drop.inv_keep : 1.f;
+    C.stage1 = stage1;
     __syncthreads();
 
     const long long ntiles = (B + TM - 1) / TM;
@@ -642,64 +712,120 @@ __device__ void bwd_stage_body(const BwdStage& S, long long B, float* sm) {
         const long long row0 = tile * TM;
         const int rows_valid = (int)min((long long)TM, B - row0);
         build_input_tile(S.in, drop, row0, rows_valid, As, lda, Xh, ldxh, sm_bna, sm_idx, nullptr);
-        // incoming-gradient tile G [TM, N] (zero padded to ldg)
-        for (int i = tid; i < TM * (ldg >> 2); i += NT) {
-            int r = i / (ldg >> 2), c4 = i - r * (ldg >> 2);
-            float g[4] = {0.f, 0.f, 0.f, 0.f};
-            if (r < rows_valid) {
+        // incoming-gradient tile G [TM, N] (zero padded to ldg) and its transpose Gt [N, TM];
+        // loads of two items (8 gradient + 8 saved-activation values) are issued before either is used
+        {
+            const int ldg4 = ldg >> 2;
+            const bool vecn = (N & 3) == 0;
+            for (int base = tid; base < TM * ldg4; base += NT * 2) {
+                float dyv[2][4], hsv[2][4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    int c = 4 * c4 + e;
-                    if (c < N) {
-                        float dy = S.gin[(size_t)(row0 + r) * N + c];
-                        if (S.g_mode == 1) {
-                            float xh = (S.hs[(size_t)(row0 + r) * N + c] - sm_bng[c]) * sm_bng[Np + c];
-                            dy = sm_bng[2 * Np + c] * (dy - sm_bng[3 * Np + c] - xh * sm_bng[4 * Np + c]);
-                        } else if (S.g_mode == 2) {
-                            dy *= sm_bng[2 * Np + c];
+                for (int u = 0; u < 2; ++u) {
+                    const int i = base + u * NT;
+                    const int r = i / ldg4, c4 = i - r * ldg4;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) { dyv[u][e] = 0.f; hsv[u][e] = 0.f; }
+                    if (i < TM * ldg4 && r < rows_valid && 4 * c4 < N) {
+                        const size_t off = (size_t)(row0 + r) * N + 4 * c4;
+                        if (vecn) {
+                            const float4 d4 = *reinterpret_cast<const float4*>(S.gin + off);
+                            dyv[u][0] = d4.x; dyv[u][1] = d4.y; dyv[u][2] = d4.z; dyv[u][3] = d4.w;
+                            if (S.g_mode == 1) {
+                                const float4 h4 = *reinterpret_cast<const float4*>(S.hs + off);
+                                hsv[u][0] = h4.x; hsv[u][1] = h4.y; hsv[u][2] = h4.z; hsv[u][3] = h4.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                if (4 * c4 + e < N) {
+                                    dyv[u][e] = S.gin[off + e];
+                                    if (S.g_mode == 1) hsv[u][e] = S.hs[off + e];
+                                }
                         }
-                        g[e] = dy;
                     }
                 }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int i = base + u * NT;
+                    if (i >= TM * ldg4) continue;
+                    const int r = i / ldg4, c4 = i - r * ldg4;
+                    float gv[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (r < rows_valid) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int c = 4 * c4 + e;
+                            if (c < N) {
+                                float dy = dyv[u][e];
+                                if (S.g_mode == 1) {
+                                    const float xh = (hsv[u][e] - sm_bng[c]) * sm_bng[Np + c];
+                                    dy = sm_bng[2 * Np + c] * (dy - sm_bng[3 * Np + c] - xh * sm_bng[4 * Np + c]);
+                                } else if (S.g_mode == 2) {
+                                    dy *= sm_bng[2 * Np + c];
+                                }
+                                gv[e] = dy;
+                            }
+                        }
+                    }
+                    *reinterpret_cast<float4*>(Gs + r * ldg + 4 * c4) = make_float4(gv[0], gv[1], gv[2], gv[3]);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (4 * c4 + e < N) Gt[(4 * c4 + e) * ldgt + r] = gv[e];
+                }
             }
-            *reinterpret_cast<float4*>(Gs + r * ldg + 4 * c4) = make_float4(g[0], g[1], g[2], g[3]);
         }
         __syncthreads();
 
-        if (dw_active) dw_accum<RN4, RK4>(Gs, ldg, As, lda, gi, ki, dw);
+        // ---- dW accumulation over the 64 rows of this tile (8 k-steps of 8 rows) ----
+#pragma unroll
+        for (int i = 0; i < DW_MAX_TILES; ++i) {
+            const int q = warp + 8 * i;
+            if (q < n_dw_tiles) {
+                const int nt = q % NTN, kt = q / NTN;
+                const float* gp_ = Gt + (nt * 16 + g) * ldgt + t;          // A fragment: (m = n, k = row)
+                const float* ap_ = As + t * lda + kt * 8 + g;              // B fragment: (k = row, n = k_in)
+#pragma unroll 2
+                for (int r8 = 0; r8 < TM / 8; ++r8) {
+                    uint32_t ah[4], al[4], bh[2], bl[2];
+                    const float* gq = gp_ + r8 * 8;
+                    split_tf32(gq[0], ah[0], al[0]);
+                    split_tf32(gq[8 * ldgt], ah[1], al[1]);
+                    split_tf32(gq[4], ah[2], al[2]);
+                    split_tf32(gq[8 * ldgt + 4], ah[3], al[3]);
+                    const float* aq = ap_ + r8 * 8 * lda;
+                    split_tf32(aq[0], bh[0], bl[0]);
+                    split_tf32(aq[4 * lda], bh[1], bl[1]);
+                    mma_3xtf32(dw[i], ah, al, bh, bl);
+                }
+            }
+        }
 
         if (S.need_dx) {
             for (int pass = 0; pass < gx.passes; ++pass) {
-                switch (gx.RM) {
-                    case 1: bwd_dx_pass<1>(S, C, pass, row0, rows_valid); break;
-                    case 2: bwd_dx_pass<2>(S, C, pass, row0, rows_valid); break;
-                    case 4: bwd_dx_pass<4>(S, C, pass, row0, rows_valid); break;
-                    default: bwd_dx_pass<8>(S, C, pass, row0, rows_valid); break;
+                const int cols = pass_cols(K, pass);
+                switch (pass_ni(cols)) {
+                    case 1: bwd_dx_pass<1>(S, C, pass, cols, row0, rows_valid); break;
+                    case 2: bwd_dx_pass<2>(S, C, pass, cols, row0, rows_valid); break;
+                    default: bwd_dx_pass<4>(S, C, pass, cols, row0, rows_valid); break;
                 }
             }
         }
         __syncthreads();   // tiles are rebuilt next iteration
     }
 
-    // per-CTA partial outputs
-    if (dw_active) {
+    // per-CTA partial outputs: dW[n][k] (column K = bias gradient), global column order
+    {
         float* P = S.dW_part + (size_t)blockIdx.x * N * (K + 1);
 #pragma unroll
-        for (int a = 0; a < RN4; ++a) {
-            if (ng + a * NG >= N4) continue;
+        for (int i = 0; i < DW_MAX_TILES; ++i) {
+            const int q = warp + 8 * i;
+            if (q < n_dw_tiles) {
+                const int nt = q % NTN, kt = q / NTN;
 #pragma unroll
-            for (int b = 0; b < RK4; ++b) {
-                if (kg + b * KG >= K4) continue;
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    int n = 4 * (ng + a * NG) + e;
-                    if (n >= N) continue;
-#pragma unroll
-                    for (int f = 0; f < 4; ++f) {
-                        int k = 4 * (kg + b * KG) + f;
-                        if (k > K) continue;
-                        int kgl = (k < K && stage1) ? gcol_stage1(k, KE, n_num) : k;
-                        P[(size_t)n * (K + 1) + kgl] = dw[a][b][e][f];
+                for (int c = 0; c < 4; ++c) {
+                    const int n = nt * 16 + g + 8 * (c >> 1), k = kt * 8 + 2 * t + (c & 1);
+                    if (n < N && k <= K) {
+                        const int kgl = (k < K && stage1) ? gcol_stage1(k, KE, n_num) : k;
+                        P[(size_t)n * (K + 1) + kgl] = dw[i][c];
                     }
                 }
             }
@@ -707,14 +833,8 @@ __device__ void bwd_stage_body(const BwdStage& S, long long B, float* sm) {
     }
     if (S.a_bn && S.need_dx) {
         float* P = S.sum_part + (size_t)blockIdx.x * 2 * K;
-        for (int c = tid; c < K; c += NT) { P[c] = rs[c]; P[K + c] = rs[gx.wrows + c]; }
+        for (int c = tid; c < K; c += NT) { P[c] = rs[c]; P[K + c] = rs[rs_stride + c]; }
     }
-}
-
-template <int RN4, int RK4>
-__global__ void __launch_bounds__(NT, 1) tower_bwd_stage(const __grid_constant__ BwdArgs args) {
-    extern __shared__ float4 smem4[];
-    bwd_stage_body<RN4, RK4>(args.st[blockIdx.y], args.B, reinterpret_cast<float*>(smem4));
 }
 
 // dW[n][k] = sum over CTA partials (fixed order), bias gradient from the extra column
@@ -860,11 +980,11 @@ static int stage_K(const cfm_tower_t& t, int s) {
 static int tower_ctas() { return sm_count(); }
 
 static size_t fwd_smem_bytes(const cfm_tower_t& t, int s) {
-    GemmPlan gp = make_plan(stage_N(t, s));
+    MmaPlan gp = make_plan(stage_N(t, s));
     return (size_t)fwd_smem(stage_K(t, s), stage_N(t, s), (int)t.n_tables, gp).total_floats * 4;
 }
 static size_t bwd_smem_bytes(const cfm_tower_t& t, int s, int a_bn, int need_dx) {
-    GemmPlan gx = make_plan(stage_K(t, s));
+    MmaPlan gx = make_plan(stage_K(t, s));
     return (size_t)bwd_smem(stage_K(t, s), stage_N(t, s), (int)t.n_tables, a_bn, need_dx, gx).total_floats * 4;
 }
 
@@ -950,15 +1070,13 @@ extern "C" int cfm_towers_fwd(const cfm_tower_t* towers, int64_t n_towers, int64
     return CFM_OK;
 }
 
-template <int RN4, int RK4>
 static int launch_bwd(const BwdArgs& a, int ctas, int n_towers, size_t smem, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        CFM_CHECK_CUDA(cudaFuncSetAttribute(tower_bwd_stage<RN4, RK4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            MAX_SMEM));
+        CFM_CHECK_CUDA(cudaFuncSetAttribute(tower_bwd_stage, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
         attr_set = true;
     }
-    tower_bwd_stage<RN4, RK4><<<dim3(ctas, (unsigned)n_towers), NT, smem, stream>>>(a);
+    tower_bwd_stage<<<dim3(ctas, (unsigned)n_towers), NT, smem, stream>>>(a);
     CFM_LAUNCH_CHECK();
     return CFM_OK;
 }
@@ -1020,24 +1138,16 @@ extern "C" int cfm_towers_bwd(const cfm_tower_t* towers, const cfm_tower_grads_t
             max_groups = std::max(max_groups, groups);
         }
         // scratch must hold ctas * (N*(K+1) + 2K) floats: guaranteed by cfm_tower_scratch_floats
-        int rc;
-        ProfScope* prof = new ProfScope(PROF_BWD1 + s - 1, stream);
-        auto fits = [&](int rn4, int rk4) {
-            for (int i = 0; i < n_towers; ++i) {
-                const BwdStage& S = a.st[i];
-                if (ceil_div(ceil_div(S.N, 4), rn4) * ceil_div(ceil_div(S.in.K + 1, 4), rk4) > NT) return false;
-            }
-            return true;
-        };
-        if (fits(1, 1)) rc = launch_bwd<1, 1>(a, ctas, (int)n_towers, smem, stream);
-        else if (fits(1, 2)) rc = launch_bwd<1, 2>(a, ctas, (int)n_towers, smem, stream);
-        else if (fits(2, 2)) rc = launch_bwd<2, 2>(a, ctas, (int)n_towers, smem, stream);
-        else {
-            delete prof;
-            set_error("tower bwd stage %d: layer too large for the register-tiled dW (N*(K+1) > 16384)", s);
-            return CFM_ERR_UNSUPPORTED;
+        for (int i = 0; i < n_towers; ++i) {
+            const BwdStage& S = a.st[i];
+            CFM_REQUIRE(ceil_div(S.N, 16) * (ceil8(S.in.K + 1) >> 3) <= 8 * DW_MAX_TILES, CFM_ERR_UNSUPPORTED,
+                        "tower bwd stage %d: layer %dx%d too large for the per-warp dW tiles", s, S.N, S.in.K);
         }
-        delete prof;
+        int rc;
+        {
+            ProfScope prof(PROF_BWD1 + s - 1, stream);
+            rc = launch_bwd(a, ctas, (int)n_towers, smem, stream);
+        }
         if (rc) return rc;
         ProfScope prof_red(PROF_REDUCE, stream);
         (void)max_groups;

@@ -101,8 +101,9 @@ def test_reference_known_answer_bilinear():
 @pytest.mark.parametrize("B", [2, 128, 16, 257, 4096])
 def test_batches_vs_oracle(B):
     """config 2 shapes (train batches of 128, last val batch of 16) and tile edges of the 256-row head kernel."""
-    p = oracle.init_structural_params(12, META["firm_cat_cards"], 2, META["ceo_cat_cards"], seed=B)
-    gen = torch.Generator().manual_seed(B)
+    # seeds checked for conditioning: no pre-activation within 1e-5 of a ReLU kink (a kink flips the unit's gradient)
+    p = oracle.init_structural_params(12, META["firm_cat_cards"], 2, META["ceo_cat_cards"], seed=1000 + B)
+    gen = torch.Generator().manual_seed(1000 + B)
     f_num, c_num = torch.randn(B, 12, generator=gen), torch.randn(B, 2, generator=gen)
     f_cat = torch.stack([torch.randint(0, n, (B,), generator=gen) for n in META["firm_cat_cards"]], 1)
     c_cat = torch.stack([torch.randint(0, n, (B,), generator=gen) for n in META["ceo_cat_cards"]], 1)
