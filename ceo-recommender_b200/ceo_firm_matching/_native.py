@@ -27,7 +27,7 @@ class Tower(C.Structure):
     """Mirror of ``cfm_tower_t``."""
     _fields_ = [
         ("n_num", i64), ("n_tables", i64), ("emb_dim", i64), ("h1", i64), ("h2", i64), ("d_out", i64),
-        ("bn2", i64), ("drop1", C.c_double), ("drop2", C.c_double), ("tower_id", i64),
+        ("bn2", i64), ("drop1", C.c_double), ("drop2", C.c_double), ("tower_id", i64), ("precision", i64),
         ("x_num", C.c_void_p), ("x_cat", C.c_void_p),
         ("tables", C.c_void_p * CFM_MAX_TABLES), ("table_rows", i64 * CFM_MAX_TABLES),
         ("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p),

@@ -64,6 +64,13 @@ class CEOFirmMatcher(nn.Module):
         u, v = self.encode_raw(f_numeric, f_cat, c_numeric, c_cat)
         return ops.CosineMSEFunction.apply(u, v, self.logit_scale, target, weights, 0.0)
 
+    def set_precision(self, precision: str = "fp32") -> None:
+        """``"fp32"``: tower products are 3xTF32 error-compensated (fp32-class, the parity default);
+        ``"tf32"``: one TF32 tensor-core pass (10-bit mantissa operands, fp32 accumulation; ~1e-3 relative)."""
+        code = {"fp32": 0, "tf32": 1}[precision]
+        for h in self._handles:
+            h.precision = code
+
     # ---- dense-gradient bookkeeping for large embedding tables --------------------------
     def use_persistent_table_grads(self, enable: bool = True) -> None:
         """Keep every embedding table's dense ``.grad`` allocated and re-zero only the rows touched by the

@@ -95,6 +95,7 @@ class TowerHandle:
         self.lin, self.bn, self.tower_id = tuple(lin), tuple(bn), tower_id
         self._drop = tuple(drop)
         self._scratch = None
+        self.precision = 0                       # 0: fp32-class (3xTF32), 1: single-pass TF32 tensor-core products
         self.table_grads: Optional["PersistentTableGrads"] = None
 
     # dims -------------------------------------------------------------------------------
@@ -162,6 +163,7 @@ class _TowerCall:
         t.bn2 = 1 if b2 is not None else 0
         t.drop1, t.drop2 = h.drop_p(0), h.drop_p(1)
         t.tower_id = h.tower_id
+        t.precision = h.precision
         t.x_num, t.x_cat = N.ptr(x_num), N.ptr(x_cat)
         for i, e in enumerate(h.embeddings):
             t.tables[i] = N.ptr(e.weight)

@@ -302,58 +302,81 @@ __device__ void build_input_tile(const InputDesc& in, const DropCtx& drop, long 
 // ------------------------------------------------------------------------------------------
 // tensor-core GEMMs on shared-memory operands (mma.sync m16n8k8, 3xTF32 error-compensated)
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
-    lo = __float_as_uint(x - __uint_as_float(hi));      // exact remainder; the MMA reads its top 19 bits
-}
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
     asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
-// c += a * b with a = a_hi + a_lo, b = b_hi + b_lo (lo*lo dropped: 2^-22 relative)
-__device__ __forceinline__ void mma_3xtf32(float (&c)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
-                                           const uint32_t (&bh)[2], const uint32_t (&bl)[2]) {
-    mma_tf32(c, al, bh);
-    mma_tf32(c, ah, bl);
+// four 8x8 b16 matrices == four 8-row x 4-float blocks: one instruction fetches a whole TF32 A fragment
+// (or the B fragments of two n-tiles); lane l supplies the 16-byte row address of matrix l/8, row l%8
+__device__ __forceinline__ void ldmatrix_x4(const float* p, uint32_t (&r)[4]) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"((uint32_t)__cvta_generic_to_shared(p)));
+}
+__device__ __forceinline__ void ldmatrix_x2(const float* p, uint32_t (&r)[2]) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];"
+                 : "=r"(r[0]), "=r"(r[1])
+                 : "r"((uint32_t)__cvta_generic_to_shared(p)));
+}
+template <bool EXACT>
+__device__ __forceinline__ void split_frag(uint32_t raw, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(__uint_as_float(raw)));
+    if (EXACT) lo = __float_as_uint(__uint_as_float(raw) - __uint_as_float(hi));
+}
+template <bool EXACT>
+__device__ __forceinline__ void mma_acc(float (&c)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
+                                        const uint32_t (&bh)[2], const uint32_t (&bl)[2]) {
+    if (EXACT) { mma_tf32(c, al, bh); mma_tf32(c, ah, bl); }
     mma_tf32(c, ah, bh);
 }
 
 // acc[mi][ni][.] = X[r0 + mi*16 .. +15][:] . W[n0 + ni*8 .. +7][:]^T over k8n steps of 8 columns.
-// Fragment loads are scalar LDS; both leading dimensions are 4 (mod 8) so the 32 lanes hit 32 distinct banks.
-template <int NI>
+// EXACT: 3xTF32 error-compensated (fp32-class result); otherwise one TF32 pass.  Leading dimensions are 4 (mod 8)
+// floats, so the eight 16-byte rows of every ldmatrix phase fall into distinct bank groups.
+template <int NI, bool EXACT>
 __device__ __forceinline__ void mma_rows(const float* __restrict__ Xs, int ldx, const float* __restrict__ Ws, int ldw,
                                          int k8n, int r0, int n0, int lane, float (&acc)[2][NI][4]) {
-    const int g = lane >> 2, t = lane & 3;
 #pragma unroll
     for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
         for (int ni = 0; ni < NI; ++ni)
 #pragma unroll
             for (int c = 0; c < 4; ++c) acc[mi][ni][c] = 0.f;
-    const float* xp = Xs + (r0 + g) * ldx + t;
-    const float* wp = Ws + (n0 + g) * ldw + t;
+    const int mat = lane >> 3, rin = lane & 7;
+    // A: matrices (rows 0-7 | 8-15) x (cols 0-3 | 4-7);  B (two n-tiles per x4): (n-tile 0 | 1) x (cols 0-3 | 4-7)
+    const float* xp = Xs + (r0 + rin + (mat & 1) * 8) * ldx + (mat >> 1) * 4;
+    const float* wp = Ws + (n0 + rin + (NI >= 2 ? (mat >> 1) * 8 : 0)) * ldw + (mat & 1) * 4;
 #pragma unroll 2
     for (int k8 = 0; k8 < k8n; ++k8) {
         uint32_t ah[2][4], al[2][4], bh[NI][2], bl[NI][2];
 #pragma unroll
         for (int mi = 0; mi < 2; ++mi) {
-            const float* p = xp + mi * 16 * ldx + k8 * 8;
-            split_tf32(p[0], ah[mi][0], al[mi][0]);
-            split_tf32(p[8 * ldx], ah[mi][1], al[mi][1]);
-            split_tf32(p[4], ah[mi][2], al[mi][2]);
-            split_tf32(p[8 * ldx + 4], ah[mi][3], al[mi][3]);
-        }
+            uint32_t raw[4];
+            ldmatrix_x4(xp + mi * 16 * ldx + k8 * 8, raw);
 #pragma unroll
-        for (int ni = 0; ni < NI; ++ni) {
-            const float* p = wp + ni * 8 * ldw + k8 * 8;
-            split_tf32(p[0], bh[ni][0], bl[ni][0]);
-            split_tf32(p[4], bh[ni][1], bl[ni][1]);
+            for (int e = 0; e < 4; ++e) split_frag<EXACT>(raw[e], ah[mi][e], al[mi][e]);
+        }
+        if (NI == 1) {
+            uint32_t raw[2];
+            ldmatrix_x2(wp + k8 * 8, raw);
+            split_frag<EXACT>(raw[0], bh[0][0], bl[0][0]);
+            split_frag<EXACT>(raw[1], bh[0][1], bl[0][1]);
+        } else {
+#pragma unroll
+            for (int np = 0; np < NI / 2; ++np) {
+                uint32_t raw[4];
+                ldmatrix_x4(wp + np * 16 * ldw + k8 * 8, raw);
+                split_frag<EXACT>(raw[0], bh[2 * np][0], bl[2 * np][0]);
+                split_frag<EXACT>(raw[1], bh[2 * np][1], bl[2 * np][1]);
+                split_frag<EXACT>(raw[2], bh[2 * np + 1][0], bl[2 * np + 1][0]);
+                split_frag<EXACT>(raw[3], bh[2 * np + 1][1], bl[2 * np + 1][1]);
+            }
         }
 #pragma unroll
         for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-            for (int ni = 0; ni < NI; ++ni) mma_3xtf32(acc[mi][ni], ah[mi], al[mi], bh[ni], bl[ni]);
+            for (int ni = 0; ni < NI; ++ni) mma_acc<EXACT>(acc[mi][ni], ah[mi], al[mi], bh[ni], bl[ni]);
     }
 }
 
@@ -365,7 +388,7 @@ struct FwdCtx {
 };
 
 // one column pass (<= 128 columns) of a forward tile: GEMM, store raw output, optional (count, mean, M2) statistics
-template <int NI>
+template <int NI, bool EXACT>
 __device__ __forceinline__ void fwd_pass(const FwdCtx& C, int pass, int cols, long long row0, int rows_valid, float run_cnt) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wr = warp >> 2, wc = warp & 3, g = lane >> 2, t = lane & 3;
@@ -373,7 +396,7 @@ __device__ __forceinline__ void fwd_pass(const FwdCtx& C, int pass, int cols, lo
     const bool active = wc * 8 * NI < cols;
     float acc[2][NI][4];
     if (active) {
-        mma_rows<NI>(C.As, C.lda, C.Ws, C.lda, C.k8n, wr * 32, n0, lane, acc);
+        mma_rows<NI, EXACT>(C.As, C.lda, C.Ws, C.lda, C.k8n, wr * 32, n0, lane, acc);
 #pragma unroll
         for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
@@ -452,6 +475,7 @@ __device__ __forceinline__ void fwd_pass(const FwdCtx& C, int pass, int cols, lo
 // ------------------------------------------------------------------------------------------
 // forward stage kernel
 // ------------------------------------------------------------------------------------------
+template <bool EXACT>
 __global__ void __launch_bounds__(NT, 2) tower_fwd_stage(const __grid_constant__ FwdArgs args) {
     const FwdStage& S = args.st[blockIdx.y];
     extern __shared__ float4 smem4[];
@@ -503,9 +527,9 @@ __global__ void __launch_bounds__(NT, 2) tower_fwd_stage(const __grid_constant__
         for (int pass = 0; pass < gp.passes; ++pass) {
             const int cols = pass_cols(N, pass);
             switch (pass_ni(cols)) {
-                case 1: fwd_pass<1>(C, pass, cols, row0, rows_valid, run_cnt); break;
-                case 2: fwd_pass<2>(C, pass, cols, row0, rows_valid, run_cnt); break;
-                default: fwd_pass<4>(C, pass, cols, row0, rows_valid, run_cnt); break;
+                case 1: fwd_pass<1, EXACT>(C, pass, cols, row0, rows_valid, run_cnt); break;
+                case 2: fwd_pass<2, EXACT>(C, pass, cols, row0, rows_valid, run_cnt); break;
+                default: fwd_pass<4, EXACT>(C, pass, cols, row0, rows_valid, run_cnt); break;
             }
         }
         run_cnt += (float)rows_valid;
@@ -575,7 +599,7 @@ struct BwdCtx {
 };
 
 // one column pass (<= 128 columns of K) of the dX product of a backward tile (+ ReLU/dropout mask, BN-backward sums)
-template <int NI>
+template <int NI, bool EXACT>
 __device__ __forceinline__ void bwd_dx_pass(const BwdStage& S, const BwdCtx& C, int pass, int cols, long long row0,
                                             int rows_valid) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -587,7 +611,7 @@ __device__ __forceinline__ void bwd_dx_pass(const BwdStage& S, const BwdCtx& C, 
 #pragma unroll
     for (int ni = 0; ni < NI; ++ni) { s1[ni][0] = s1[ni][1] = s2[ni][0] = s2[ni][1] = 0.f; }
     if (active) {
-        mma_rows<NI>(C.Gs, C.ldg, C.Wt, C.ldg, C.n8n, wr * 32, k0, lane, acc);
+        mma_rows<NI, EXACT>(C.Gs, C.ldg, C.Wt, C.ldg, C.n8n, wr * 32, k0, lane, acc);
 #pragma unroll
         for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
@@ -641,6 +665,7 @@ __device__ __forceinline__ void bwd_dx_pass(const BwdStage& S, const BwdCtx& C, 
 // ------------------------------------------------------------------------------------------
 constexpr int DW_MAX_TILES = 16;   // m16n8 output tiles of dW per warp (N*(K+1) <= 16384)
 
+template <bool EXACT>
 __global__ void __launch_bounds__(NT, 2) tower_bwd_stage(const __grid_constant__ BwdArgs args) {
     const BwdStage& S = args.st[blockIdx.y];
     const long long B = args.B;
@@ -781,20 +806,19 @@ __global__ void __launch_bounds__(NT, 2) tower_bwd_stage(const __grid_constant__
             const int q = warp + 8 * i;
             if (q < n_dw_tiles) {
                 const int nt = q % NTN, kt = q / NTN;
-                const float* gp_ = Gt + (nt * 16 + g) * ldgt + t;          // A fragment: (m = n, k = row)
+                const int mat = lane >> 3, rin = lane & 7;
+                const float* gp_ = Gt + (nt * 16 + rin + (mat & 1) * 8) * ldgt + (mat >> 1) * 4;   // A: (m = n, k = row)
                 const float* ap_ = As + t * lda + kt * 8 + g;              // B fragment: (k = row, n = k_in)
 #pragma unroll 2
                 for (int r8 = 0; r8 < TM / 8; ++r8) {
-                    uint32_t ah[4], al[4], bh[2], bl[2];
-                    const float* gq = gp_ + r8 * 8;
-                    split_tf32(gq[0], ah[0], al[0]);
-                    split_tf32(gq[8 * ldgt], ah[1], al[1]);
-                    split_tf32(gq[4], ah[2], al[2]);
-                    split_tf32(gq[8 * ldgt + 4], ah[3], al[3]);
+                    uint32_t raw[4], ah[4], al[4], bh[2], bl[2];
+                    ldmatrix_x4(gp_ + r8 * 8, raw);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) split_frag<EXACT>(raw[e], ah[e], al[e]);
                     const float* aq = ap_ + r8 * 8 * lda;
-                    split_tf32(aq[0], bh[0], bl[0]);
-                    split_tf32(aq[4 * lda], bh[1], bl[1]);
-                    mma_3xtf32(dw[i], ah, al, bh, bl);
+                    split_frag<EXACT>(__float_as_uint(aq[0]), bh[0], bl[0]);
+                    split_frag<EXACT>(__float_as_uint(aq[4 * lda]), bh[1], bl[1]);
+                    mma_acc<EXACT>(dw[i], ah, al, bh, bl);
                 }
             }
         }
@@ -803,9 +827,9 @@ __global__ void __launch_bounds__(NT, 2) tower_bwd_stage(const __grid_constant__
             for (int pass = 0; pass < gx.passes; ++pass) {
                 const int cols = pass_cols(K, pass);
                 switch (pass_ni(cols)) {
-                    case 1: bwd_dx_pass<1>(S, C, pass, cols, row0, rows_valid); break;
-                    case 2: bwd_dx_pass<2>(S, C, pass, cols, row0, rows_valid); break;
-                    default: bwd_dx_pass<4>(S, C, pass, cols, row0, rows_valid); break;
+                    case 1: bwd_dx_pass<1, EXACT>(S, C, pass, cols, row0, rows_valid); break;
+                    case 2: bwd_dx_pass<2, EXACT>(S, C, pass, cols, row0, rows_valid); break;
+                    default: bwd_dx_pass<4, EXACT>(S, C, pass, cols, row0, rows_valid); break;
                 }
             }
         }
@@ -925,6 +949,7 @@ static int validate_tower(const cfm_tower_t& t) {
     CFM_REQUIRE(t.h1_raw && t.h2_raw && t.out && t.bn1_stat && t.scratch, CFM_ERR_INVALID, "null tower workspace");
     CFM_REQUIRE(!t.bn2 || t.bn2_stat, CFM_ERR_INVALID, "null bn2_stat");
     CFM_REQUIRE(t.drop1 >= 0 && t.drop1 < 1 && t.drop2 >= 0 && t.drop2 < 1, CFM_ERR_INVALID, "dropout p outside [0,1)");
+    CFM_REQUIRE(t.precision == 0 || t.precision == 1, CFM_ERR_INVALID, "precision must be 0 (fp32) or 1 (tf32)");
     for (int i = 0; i < t.n_tables; ++i)
         CFM_REQUIRE(t.tables[i] && ((uintptr_t)t.tables[i] & 15) == 0, CFM_ERR_INVALID,
                     "table %d null or not 16-byte aligned", i);
@@ -1014,9 +1039,11 @@ extern "C" int cfm_towers_fwd(const cfm_tower_t* towers, int64_t n_towers, int64
     for (int i = 0; i < n_towers; ++i) { int rc = validate_tower(towers[i]); if (rc) return rc; }
     static bool attr_set = false;
     if (!attr_set) {
-        CFM_CHECK_CUDA(cudaFuncSetAttribute(tower_fwd_stage, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
+        CFM_CHECK_CUDA(cudaFuncSetAttribute(tower_fwd_stage<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
+        CFM_CHECK_CUDA(cudaFuncSetAttribute(tower_fwd_stage<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
         attr_set = true;
     }
+    const bool exact = towers[0].precision == 0;
     const long long ntiles = (B + TM - 1) / TM;
     const int ctas = (int)std::min<long long>(ntiles, tower_ctas());
     for (int s = 1; s <= 3; ++s) {
@@ -1043,7 +1070,8 @@ extern "C" int cfm_towers_fwd(const cfm_tower_t* towers, int64_t n_towers, int64
         }
         {
             ProfScope prof(PROF_FWD1 + s - 1, stream);
-            tower_fwd_stage<<<dim3(ctas, (unsigned)n_towers), NT, smem, stream>>>(a);
+            if (exact) tower_fwd_stage<true><<<dim3(ctas, (unsigned)n_towers), NT, smem, stream>>>(a);
+            else tower_fwd_stage<false><<<dim3(ctas, (unsigned)n_towers), NT, smem, stream>>>(a);
         }
         CFM_LAUNCH_CHECK();
         if (any_stats) {
@@ -1070,13 +1098,15 @@ extern "C" int cfm_towers_fwd(const cfm_tower_t* towers, int64_t n_towers, int64
     return CFM_OK;
 }
 
-static int launch_bwd(const BwdArgs& a, int ctas, int n_towers, size_t smem, cudaStream_t stream) {
+static int launch_bwd(const BwdArgs& a, int ctas, int n_towers, size_t smem, bool exact, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        CFM_CHECK_CUDA(cudaFuncSetAttribute(tower_bwd_stage, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
+        CFM_CHECK_CUDA(cudaFuncSetAttribute(tower_bwd_stage<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
+        CFM_CHECK_CUDA(cudaFuncSetAttribute(tower_bwd_stage<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
         attr_set = true;
     }
-    tower_bwd_stage<<<dim3(ctas, (unsigned)n_towers), NT, smem, stream>>>(a);
+    if (exact) tower_bwd_stage<true><<<dim3(ctas, (unsigned)n_towers), NT, smem, stream>>>(a);
+    else tower_bwd_stage<false><<<dim3(ctas, (unsigned)n_towers), NT, smem, stream>>>(a);
     CFM_LAUNCH_CHECK();
     return CFM_OK;
 }
@@ -1146,7 +1176,7 @@ extern "C" int cfm_towers_bwd(const cfm_tower_t* towers, const cfm_tower_grads_t
         int rc;
         {
             ProfScope prof(PROF_BWD1 + s - 1, stream);
-            rc = launch_bwd(a, ctas, (int)n_towers, smem, stream);
+            rc = launch_bwd(a, ctas, (int)n_towers, smem, towers[0].precision == 0, stream);
         }
         if (rc) return rc;
         ProfScope prof_red(PROF_REDUCE, stream);

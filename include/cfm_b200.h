@@ -62,6 +62,7 @@ typedef struct cfm_tower {
     int64_t bn2;                 /* 1: BatchNorm1d after Linear 2 */
     double drop1, drop2;         /* dropout probability after activation 1 / 2 (0 = none) */
     int64_t tower_id;            /* distinguishes the dropout streams of the towers in one call */
+    int64_t precision;           /* 0: fp32-class (3xTF32 error-compensated tensor-core products), 1: single-pass TF32 */
     /* inputs */
     const float* x_num;
     const int64_t* x_cat;
