@@ -78,7 +78,7 @@ PROTOTYPES = {
     "cfm_infonce_loss": (C.c_int, [_V, _V, _V, _I, _D, _I, _V, _V]),
     "cfm_infonce_grad": (C.c_int, [_V, _V, _I, _I, _I, _I, _D, _I, _I, _V, _V, _V, _V, _V, _V, _V]),
     "cfm_simtile_scores": (C.c_int, [_V, _V, _I, _I, _I, _V, _V]),
-    "cfm_allpairs_topk": (C.c_int, [_V, _V, _V, _V, _I, _I, _I, _I, _I, _D, _D, _I, _V, _V, _V, _V, _V, _V, _V, _V, _V]),
+    "cfm_allpairs_topk": (C.c_int, [_V, _V, _V, _V, _I, _I, _I, _I, _I, _D, _D, _I, _V, _V, _V, _V, _V, _V, _V, _V]),
     "cfm_topk_merge": (C.c_int, [_V, _I, _V, _I, _I, _I, _V, _V, _V]),
     "cfm_allpairs_rank": (C.c_int, [_V, _V, _I, _I, _I, _V, _V, _V]),
 }

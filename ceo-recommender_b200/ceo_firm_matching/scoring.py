@@ -76,15 +76,14 @@ def score_topk(rows: torch.Tensor, cols: torch.Tensor, k: int, scale: float = 1.
     # that separates "certainly in" from "certainly out"; the tiny extra covers fp32 accumulation
     margin = float((2.0 ** -7 + 2.0 ** -16) * rows.norm(dim=1).max() * cols.norm(dim=1).max())
     chunks = N.lib().cfm_simtile_chunks(R, C)
-    rpad = (R + 127) // 128 * 128
-    cand_val = torch.empty(chunks * rpad * N.CFM_TOPK_CAP, device=dev)
-    cand_idx = torch.empty(chunks * rpad * N.CFM_TOPK_CAP, dtype=torch.int32, device=dev)
+    rpad = (R + 255) // 256 * 256
+    cand = torch.empty(chunks * rpad * N.CFM_TOPK_CAP, 2, dtype=torch.int32, device=dev)    # (score bits, column)
     cand_cnt = torch.empty(chunks * rpad, dtype=torch.int32, device=dev)
     cand_thr = torch.empty(chunks * rpad, device=dev)
     with torch.cuda.device(dev):
         N.check(N.lib().cfm_allpairs_topk(N.ptr(rows), N.ptr(cols), N.ptr(rb), N.ptr(cb), R, C, D, rb.shape[1], k,
                                           float(scale), margin, col_offset, N.ptr(out_s), N.ptr(out_s64), N.ptr(out_i), N.ptr(flags),
-                                          N.ptr(cand_val), N.ptr(cand_idx), N.ptr(cand_cnt), N.ptr(cand_thr),
+                                          N.ptr(cand), N.ptr(cand_cnt), N.ptr(cand_thr),
                                           N.stream_ptr()))
     bad = torch.nonzero(flags, as_tuple=False).flatten()
     if bad.numel():                                   # completeness not provable from the filter: redo exactly

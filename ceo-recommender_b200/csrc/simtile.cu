@@ -169,25 +169,17 @@ __device__ __forceinline__ float key_float(uint32_t k) {
     return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
 }
 
-__device__ __noinline__ void topk_append(float* bv, int* bi, int& cnt, float val, int col) {
-    bv[cnt] = val;
-    bi[cnt] = col;
-    ++cnt;
-}
-
-// Warp-cooperative: keep the TK_KEEP largest of the `n` entries of one row's buffer (ties at the cut are kept),
-// returns the new count and the new admission threshold (value of the TK_KEEP-th largest).
-__device__ void topk_compact(float* bv, int* bi, int n, int lane, int& new_cnt, float& new_thr) {
-    float val[TK_PER_LANE];
-    int idx[TK_PER_LANE];
+// Warp-cooperative: keep the TK_KEEP largest of the `n` (score, column) entries of one row's buffer (ties at the cut
+// are kept only until TK_KEEP is reached), returns the new count and the new admission threshold.
+__device__ void topk_compact(uint2* buf, int n, int keep_n, int lane, int& new_cnt, float& new_thr) {
+    uint2 ent[TK_PER_LANE];
     uint32_t key[TK_PER_LANE];
 #pragma unroll
     for (int e = 0; e < TK_PER_LANE; ++e) {
         int p = e * 32 + lane;
         bool ok = p < n;
-        val[e] = ok ? bv[p] : 0.f;
-        idx[e] = ok ? bi[p] : 0;
-        key[e] = ok ? float_key(val[e]) : 0u;          // key 0 is below every real float key
+        ent[e] = ok ? buf[p] : make_uint2(0u, 0u);
+        key[e] = ok ? float_key(__uint_as_float(ent[e].x)) : 0u;      // key 0 is below every real float key
     }
     __syncwarp();
     // largest t with #{key >= t} >= TK_KEEP, by bisection over the 32 key bits
@@ -197,14 +189,12 @@ __device__ void topk_compact(float* bv, int* bi, int n, int lane, int& new_cnt, 
         int c = 0;
 #pragma unroll
         for (int e = 0; e < TK_PER_LANE; ++e) c += __popc(__ballot_sync(FULL, key[e] >= cand));
-        if (c >= TK_KEEP) t = cand;
+        if (c >= keep_n) t = cand;
     }
-    // keep everything above t, and entries equal to t only until TK_KEEP is reached (bounded count even with
-    // massive ties; dropped entries all have score <= the new threshold, which the final selection checks)
     int n_gt = 0;
 #pragma unroll
     for (int e = 0; e < TK_PER_LANE; ++e) n_gt += __popc(__ballot_sync(FULL, key[e] > t));
-    int ties_left = TK_KEEP - n_gt;
+    int ties_left = keep_n - n_gt;
     int pos = 0;
 #pragma unroll
     for (int e = 0; e < TK_PER_LANE; ++e) {
@@ -216,11 +206,7 @@ __device__ void topk_compact(float* bv, int* bi, int n, int lane, int& new_cnt, 
         ties_left -= min(ties_left, __popc(m_eq));
         const bool keep = gt || eq_keep;
         const unsigned m = __ballot_sync(FULL, keep);
-        if (keep) {
-            int w = pos + __popc(m & ((1u << lane) - 1));
-            bv[w] = val[e];
-            bi[w] = idx[e];
-        }
+        if (keep) buf[pos + __popc(m & ((1u << lane) - 1))] = ent[e];
         pos += __popc(m);
     }
     __syncwarp();
@@ -228,9 +214,40 @@ __device__ void topk_compact(float* bv, int* bi, int n, int lane, int& new_cnt, 
     new_thr = key_float(t);
 }
 
+__device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+
+// Streaming admission of one row's 64 fresh scores v[] (columns j0 .. j0+63).  Hits are rare once the threshold
+// has tightened, so the common path is a max tree (hierarchical: 8 group maxima) and one warp vote; only groups in
+// which some lane of the warp has a hit are scanned element by element.
+__device__ __forceinline__ void topk_scan64(const float (&v)[64], int j0, float thr, int& cnt, uint2* buf) {
+    float m8[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        m8[k] = fmax3(fmax3(v[8 * k], v[8 * k + 1], v[8 * k + 2]), fmax3(v[8 * k + 3], v[8 * k + 4], v[8 * k + 5]),
+                      fmaxf(v[8 * k + 6], v[8 * k + 7]));
+    const float m = fmax3(fmax3(m8[0], m8[1], m8[2]), fmax3(m8[3], m8[4], m8[5]), fmaxf(m8[6], m8[7]));
+    if (!__any_sync(FULL, m > thr)) return;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        if (__any_sync(FULL, m8[k] > thr)) {              // warp-uniform
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                if (v[8 * k + e] > thr) {
+                    buf[cnt] = make_uint2(__float_as_uint(v[8 * k + e]), (uint32_t)(j0 + 8 * k + e));
+                    ++cnt;
+                }
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------------
+struct SimArgs;
+__device__ __forceinline__ void topk_admit(const SimArgs& a, const float (&v)[64], int j0, long long list, int blk_row0, int q,
+                                           int lane, long long row, float& thr, int& cnt);
+
 struct SimArgs {
     int mode;
     int R, C, D, Dp;              // rows of X, rows of Y, logical / padded (multiple of 64) feature width
@@ -242,21 +259,40 @@ struct SimArgs {
     const float* rowsum_y;        // [C]   (grad)
     float* out_part;              // rowsum: [chunks, R]; grad: [chunks, R, Dp]; scores: [R, C]
     float* diag;                  // [R] (rowsum, nullable)
-    float* cand_val;              // top-k: [chunks * Rpad, TK_CAP] bf16-operand scores
-    int* cand_idx;                // top-k: column of every candidate
-    int* cand_cnt;                // top-k: [chunks * Rpad] entries in use
+    uint2* cand;                  // top-k: [lists * Rpad, TK_CAP] (bf16-operand score bits, column)
+    int keep;                     // top-k: entries kept by a compaction (k + slack for the rescoring margin, <= TK_KEEP)
+    int rb;                       // 128-row blocks per CTA (2 halves the L2->SM traffic of the Y tiles; 1 in grad mode)
+    int* cand_cnt;                // top-k: [lists * Rpad] entries in use
     float* cand_thr;              // top-k: [chunks * Rpad] final admission threshold (-inf: nothing was dropped)
     int Rpad;
 };
 
+// scan 64 fresh scores of one row, then let the warp compact any buffer that could overflow on the next 64 columns
+__device__ __forceinline__ void topk_admit(const SimArgs& a, const float (&v)[64], int j0, long long list, int blk_row0, int q,
+                                           int lane, long long row, float& thr, int& cnt) {
+    uint2* buf = a.cand + (list * a.Rpad + row) * TK_CAP;
+    topk_scan64(v, j0, thr, cnt, buf);
+    unsigned need = __ballot_sync(FULL, cnt > TK_CAP - 64);
+    while (need) {
+        const int r = __ffs(need) - 1;
+        need &= need - 1;
+        const long long slot_r = list * a.Rpad + blk_row0 + 32 * q + r;
+        const int n_r = __shfl_sync(FULL, cnt, r);
+        int new_cnt;
+        float new_thr;
+        topk_compact(a.cand + slot_r * TK_CAP, n_r, a.keep, lane, new_cnt, new_thr);
+        if (lane == r) { cnt = new_cnt; thr = new_thr; }
+    }
+}
+
 struct SimSmem {                  // offsets from the 1024-aligned base
     int x, y, g, ry, bars, tmem_slot, total;
 };
-__host__ __device__ inline SimSmem sim_smem(int Dp, int mode) {
+__host__ __device__ inline SimSmem sim_smem(int Dp, int mode, int rb) {
     SimSmem s;
     const int nkb = Dp / ST_KB;
     int o = 0;
-    s.x = o; o += nkb * KB_BYTES;
+    s.x = o; o += rb * nkb * KB_BYTES;
     s.y = o; o += ST_STAGES * nkb * KB_BYTES;
     s.g = o; o += mode == SIM_GRAD ? 2 * 2 * KB_BYTES : 0;
     s.ry = o; o += 2 * ST_N * 4;
@@ -266,11 +302,12 @@ __host__ __device__ inline SimSmem sim_smem(int Dp, int mode) {
     return s;
 }
 
+template <int MODE, int RB>
 __global__ void __launch_bounds__(ST_THREADS, 1)
 simtile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_y, const SimArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const SimSmem L = sim_smem(a.Dp, a.mode);
+    const SimSmem L = sim_smem(a.Dp, MODE, RB);
     const int nkb = a.Dp / ST_KB;
     uint8_t* Xs = sm + L.x;
     uint8_t* Ys = sm + L.y;
@@ -279,38 +316,41 @@ simtile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L.bars);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + L.tmem_slot);
     uint64_t *x_full = bars + 0, *y_full = bars + 1, *y_empty = bars + 1 + ST_STAGES;
-    uint64_t *s_full = bars + 8, *s_empty = bars + 10, *g_full = bars + 12, *g_empty = bars + 14, *acc_full = bars + 16;
+    uint64_t *s_full = bars + 8, *s_empty = bars + 12;            // [rb * 2 + buffer]
+    uint64_t *g_full = bars + 16, *g_empty = bars + 18, *acc_full = bars + 20;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int row0 = blockIdx.x * ST_M;
+    const int row0 = blockIdx.x * RB * ST_M;
     const int tile0 = blockIdx.y * a.tiles_per_chunk;
     const int n_tiles = max(0, min(a.tiles_per_chunk, a.n_col_tiles - tile0));
-    const bool grad = a.mode == SIM_GRAD;
+    constexpr bool grad = MODE == SIM_GRAD;
 
     if (threadIdx.x == 0) {
         mbar_init(x_full, 1);
         for (int s = 0; s < ST_STAGES; ++s) { mbar_init(y_full + s, 1); mbar_init(y_empty + s, 1); }
-        for (int b = 0; b < 2; ++b) {
-            mbar_init(s_full + b, 1); mbar_init(s_empty + b, 256);
-            mbar_init(g_full + b, 256); mbar_init(g_empty + b, 1);
-        }
+        // an S buffer is drained by all 8 epilogue warps (column halves) except in the top-k RB=2 variant, where
+        // each 128-row block belongs to one warp group that walks both halves (one candidate stream per row)
+        for (int b = 0; b < 4; ++b) { mbar_init(s_full + b, 1); mbar_init(s_empty + b, (MODE == SIM_TOPK && RB == 2) ? 128 : 256); }
+        for (int b = 0; b < 2; ++b) { mbar_init(g_full + b, 256); mbar_init(g_empty + b, 1); }
         mbar_init(acc_full, 1);
         fence_barrier_init();
     }
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm_x); tma_prefetch_desc(&tm_y); }
-    const uint32_t tmem_cols = grad ? 512 : 256;      // 2 S buffers (+ the dX accumulator in grad mode)
+    const uint32_t tmem_cols = (grad || RB == 2) ? 512 : 256;     // S buffers: RB x 2 x 128 columns (+ dX accumulator)
     if (warp == 2) tmem_alloc(tmem_slot, tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_s0 = tmem_base, tmem_acc = tmem_base + 256;     // S buffers at columns 0 / 128, dX at 256
+    const uint32_t tmem_s0 = tmem_base, tmem_acc = tmem_base + 256;     // S(rb, b) at column (rb*2+b)*128, dX at 256
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            mbar_expect_tx(x_full, nkb * KB_BYTES);
-            for (int kb = 0; kb < nkb; ++kb) tma_load_2d(Xs + kb * KB_BYTES, &tm_x, x_full, kb * ST_KB, row0);
+            mbar_expect_tx(x_full, RB * nkb * KB_BYTES);
+            for (int rb = 0; rb < RB; ++rb)
+                for (int kb = 0; kb < nkb; ++kb)
+                    tma_load_2d(Xs + (rb * nkb + kb) * KB_BYTES, &tm_x, x_full, kb * ST_KB, row0 + rb * ST_M);
             for (int t = 0; t < n_tiles; ++t) {
                 const int s = t % ST_STAGES;
                 mbar_wait(y_empty + s, ((t / ST_STAGES) & 1) ^ 1);
@@ -327,18 +367,21 @@ simtile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
             const uint32_t xs = smem_u32(Xs), ys = smem_u32(Ys), gs = smem_u32(Gs);
             mbar_wait(x_full, 0);
             for (int t = 0; t <= n_tiles; ++t) {
-                if (t < n_tiles) {                     // GEMM 1: S[b] = X . Y_t^T
+                if (t < n_tiles) {                     // GEMM 1: S(rb, b) = X_rb . Y_t^T
                     const int s = t % ST_STAGES, b = t & 1;
                     mbar_wait(y_full + s, (t / ST_STAGES) & 1);
-                    mbar_wait(s_empty + b, ((t >> 1) & 1) ^ 1);
-                    tc_fence_after();
                     const uint32_t yb = ys + s * nkb * KB_BYTES;
-                    for (int ks = 0; ks < a.Dp / 16; ++ks) {
-                        const uint32_t off = (ks >> 2) * KB_BYTES + (ks & 3) * 32;
-                        umma_bf16(tmem_s0 + b * ST_N, desc_kmajor_sw128(xs + off), desc_kmajor_sw128(yb + off), idesc1,
-                                  ks > 0);
+                    for (int rb = 0; rb < RB; ++rb) {
+                        mbar_wait(s_empty + rb * 2 + b, ((t >> 1) & 1) ^ 1);
+                        tc_fence_after();
+                        const uint32_t xb = xs + rb * nkb * KB_BYTES;
+                        for (int ks = 0; ks < a.Dp / 16; ++ks) {
+                            const uint32_t off = (ks >> 2) * KB_BYTES + (ks & 3) * 32;
+                            umma_bf16(tmem_s0 + (rb * 2 + b) * ST_N, desc_kmajor_sw128(xb + off), desc_kmajor_sw128(yb + off),
+                                      idesc1, ks > 0);
+                        }
+                        umma_commit(s_full + rb * 2 + b);
                     }
-                    umma_commit(s_full + b);
                     if (!grad) umma_commit(y_empty + s);
                 }
                 if (grad && t >= 1) {                  // GEMM 2: dX += G_u . Y_u   (u = t - 1)
@@ -363,20 +406,55 @@ simtile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
         const int half = (warp - 2) >> 2;              // columns [64*half, 64*half+64) of every tile
         const int q = warp & 3;                        // TMEM lane quadrant this warp may access
         const int r_loc = 32 * q + lane;
-        const long long row = (long long)row0 + r_loc;
         const uint32_t lane_addr = (uint32_t)(32 * q) << 16;
-        const bool row_ok = row < a.R;
-        float racc[4] = {0.f, 0.f, 0.f, 0.f}, dval = 0.f;
-        bool have_diag = false;
-        // top-k state of this (row, column half): admission threshold, entries in its candidate buffer
         const long long list = (long long)blockIdx.y * 2 + half;
-        const long long slot = list * a.Rpad + row;
-        float* bv = a.mode == SIM_TOPK ? a.cand_val + slot * TK_CAP : nullptr;
-        int* bi = a.mode == SIM_TOPK ? a.cand_idx + slot * TK_CAP : nullptr;
-        float thr = row_ok ? -INFINITY : INFINITY;     // rows past R admit nothing
-        int cnt = 0;
-        const float rx = (grad && row_ok) ? a.alpha / a.rowsum_x[row] : 0.f;
-        const long long dcol = row + a.diag_offset;    // column of this row's positive pair
+        // per 128-row block state (RB <= 2)
+        long long row[RB];
+        bool row_ok[RB], have_diag[RB];
+        float racc[RB][4], dval[RB], thr[RB];
+        int cnt[RB];
+#pragma unroll
+        for (int rb = 0; rb < RB; ++rb) {
+            row[rb] = (long long)row0 + rb * ST_M + r_loc;
+            row_ok[rb] = row[rb] < a.R;
+            thr[rb] = row_ok[rb] ? -INFINITY : INFINITY;       // rows past R admit nothing
+            cnt[rb] = 0; dval[rb] = 0.f; have_diag[rb] = false;
+            racc[rb][0] = racc[rb][1] = racc[rb][2] = racc[rb][3] = 0.f;
+        }
+        const float rx = (grad && row_ok[0]) ? a.alpha / a.rowsum_x[row[0]] : 0.f;
+        if (MODE == SIM_TOPK && RB == 2) {
+            // one candidate stream per row: warp group `half` owns row block `half` and walks both column halves
+            const int rbo = half;
+            const long long list0 = (long long)blockIdx.y * 2;
+            const long long myrow = (long long)row0 + rbo * ST_M + r_loc;
+            const bool my_ok = myrow < a.R;
+            float mythr = my_ok ? -INFINITY : INFINITY;
+            int mycnt = 0;
+            for (int t = 0; t < n_tiles; ++t) {
+                const int b = t & 1;
+                mbar_wait(s_full + rbo * 2 + b, (t >> 1) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int j0 = (tile0 + t) * ST_N + 64 * hh;
+                    float v[64];
+                    tmem_ld64(tmem_s0 + (rbo * 2 + b) * ST_N + 64 * hh + lane_addr, v);
+                    if (j0 + 64 > a.C) {
+#pragma unroll
+                        for (int i = 0; i < 64; ++i)
+                            if (j0 + i >= a.C) v[i] = -INFINITY;
+                    }
+                    topk_admit(a, v, j0, list0, row0 + rbo * ST_M, q, lane, myrow, mythr, mycnt);
+                }
+                tc_fence_before();
+                mbar_arrive(s_empty + rbo * 2 + b);
+            }
+            const long long slot = list0 * a.Rpad + myrow;
+            a.cand_cnt[slot] = my_ok ? mycnt : 0;
+            a.cand_thr[slot] = mythr;
+            a.cand_cnt[(list0 + 1) * a.Rpad + myrow] = 0;          // the second list of this chunk stays empty
+            a.cand_thr[(list0 + 1) * a.Rpad + myrow] = -INFINITY;
+        } else
         for (int t = 0; t < n_tiles; ++t) {
             const int b = t & 1;
             const int j0 = (tile0 + t) * ST_N + 64 * half;
@@ -386,90 +464,86 @@ simtile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
                 if (r_loc < 64) ry[r_loc] = (j0 + r_loc < a.C) ? a.alpha / a.rowsum_y[j0 + r_loc] : 0.f;
                 named_bar_sync(1 + half, 128);
             }
-            mbar_wait(s_full + b, (t >> 1) & 1);
-            tc_fence_after();
-            float v[64];
-            tmem_ld64(tmem_s0 + b * ST_N + 64 * half + lane_addr, v);
-            if (a.mode == SIM_SCORES) {
-                if (row_ok)
-                    for (int i = 0; i < 64; ++i)
-                        if (j0 + i < a.C) a.out_part[row * a.C + j0 + i] = v[i];
-            } else if (a.mode == SIM_TOPK) {
-                if (j0 + 64 > a.C) {                             // ragged last tile: columns past C never qualify
 #pragma unroll
-                    for (int i = 0; i < 64; ++i)
-                        if (j0 + i >= a.C) v[i] = -INFINITY;
-                }
+            for (int rb = 0; rb < RB; ++rb) {
+                mbar_wait(s_full + rb * 2 + b, (t >> 1) & 1);
+                tc_fence_after();
+                float v[64];
+                tmem_ld64(tmem_s0 + (rb * 2 + b) * ST_N + 64 * half + lane_addr, v);
+                const long long dcol = row[rb] + a.diag_offset;    // column of this row's positive pair
+                if (MODE == SIM_SCORES) {
+                    if (row_ok[rb])
+                        for (int i = 0; i < 64; ++i)
+                            if (j0 + i < a.C) a.out_part[row[rb] * a.C + j0 + i] = v[i];
+                } else if (MODE == SIM_TOPK) {
+                    // (handled by the dedicated loop below for RB == 2)
+                    if (j0 + 64 > a.C) {                             // ragged last tile: columns past C never qualify
 #pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (__builtin_expect(v[32 * hh + i] > thr, 0)) topk_append(bv, bi, cnt, v[32 * hh + i], j0 + 32 * hh + i);
-                    // a buffer that could overflow on the next 32 columns is compacted by the whole warp
-                    unsigned need = __ballot_sync(FULL, cnt > TK_CAP - 32);
-                    while (need) {
-                        const int r = __ffs(need) - 1;
-                        need &= need - 1;
-                        const long long slot_r = list * a.Rpad + row0 + 32 * q + r;
-                        const int n_r = __shfl_sync(FULL, cnt, r);
-                        int new_cnt;
-                        float new_thr;
-                        topk_compact(a.cand_val + slot_r * TK_CAP, a.cand_idx + slot_r * TK_CAP, n_r, lane, new_cnt, new_thr);
-                        if (lane == r) { cnt = new_cnt; thr = new_thr; }
+                        for (int i = 0; i < 64; ++i)
+                            if (j0 + i >= a.C) v[i] = -INFINITY;
                     }
-                }
-            } else if (a.mode == SIM_ROWSUM) {
-                if (j0 + 64 <= a.C) {
+                    topk_admit(a, v, j0, list, row0 + rb * ST_M, q, lane, row[rb], thr[rb], cnt[rb]);
+                } else if (MODE == SIM_ROWSUM) {
+                    if (j0 + 64 <= a.C) {
 #pragma unroll
-                    for (int i = 0; i < 64; ++i) racc[i & 3] += ex2_approx(fmaf(v[i], a.c1, -a.c2));
+                        for (int i = 0; i < 64; ++i) racc[rb][i & 3] += ex2_approx(fmaf(v[i], a.c1, -a.c2));
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 64; ++i)
+                            racc[rb][i & 3] += (j0 + i < a.C) ? ex2_approx(fmaf(v[i], a.c1, -a.c2)) : 0.f;
+                    }
+                    if (dcol >= j0 && dcol < j0 + 64) {
+#pragma unroll
+                        for (int i = 0; i < 64; ++i)
+                            if (j0 + i == dcol) dval[rb] = v[i];
+                        have_diag[rb] = true;
+                    }
                 } else {
+                    // the positive pair (column row + diag_offset) is left out of the bf16 G tile: its weight is
+                    // O(1/B) while every other entry is O(1/B^2), so it is added in fp32 by the finalize kernel
+                    const bool edge = j0 + 64 > a.C || (dcol >= j0 && dcol < j0 + 64);
+                    uint32_t packed[32];
 #pragma unroll
-                    for (int i = 0; i < 64; ++i) racc[i & 3] += (j0 + i < a.C) ? ex2_approx(fmaf(v[i], a.c1, -a.c2)) : 0.f;
-                }
-                if (dcol >= j0 && dcol < j0 + 64) {
-#pragma unroll
-                    for (int i = 0; i < 64; ++i)
-                        if (j0 + i == dcol) dval = v[i];
-                    have_diag = true;
-                }
-            } else {
-                // the positive pair (column row + diag_offset) is left out of the bf16 G tile: its weight is
-                // O(1/B) while every other entry is O(1/B^2), so it is added in fp32 by the finalize kernel
-                const bool edge = j0 + 64 > a.C || (dcol >= j0 && dcol < j0 + 64);
-                uint32_t packed[32];
-#pragma unroll
-                for (int i = 0; i < 64; i += 2) {
-                    float g0 = ex2_approx(fmaf(v[i], a.c1, -a.c2)) * (rx + ry[i]);
-                    float g1 = ex2_approx(fmaf(v[i + 1], a.c1, -a.c2)) * (rx + ry[i + 1]);
-                    if (edge) {
-                        if (j0 + i >= a.C || j0 + i == dcol) g0 = 0.f;
-                        if (j0 + i + 1 >= a.C || j0 + i + 1 == dcol) g1 = 0.f;
+                    for (int i = 0; i < 64; i += 2) {
+                        float g0 = ex2_approx(fmaf(v[i], a.c1, -a.c2)) * (rx + ry[i]);
+                        float g1 = ex2_approx(fmaf(v[i + 1], a.c1, -a.c2)) * (rx + ry[i + 1]);
+                        if (edge) {
+                            if (j0 + i >= a.C || j0 + i == dcol) g0 = 0.f;
+                            if (j0 + i + 1 >= a.C || j0 + i + 1 == dcol) g1 = 0.f;
+                        }
+                        __nv_bfloat162 h2 = __floats2bfloat162_rn(g0, g1);
+                        packed[i >> 1] = *reinterpret_cast<uint32_t*>(&h2);
                     }
-                    __nv_bfloat162 h2 = __floats2bfloat162_rn(g0, g1);
-                    packed[i >> 1] = *reinterpret_cast<uint32_t*>(&h2);
-                }
-                // G[b] is the K-major SW128 A operand of GEMM 2; this half fills k-block `half` of row r_loc
-                uint8_t* grow = Gs + (b * 2 + half) * KB_BYTES + r_loc * 128;
+                    // G[b] is the K-major SW128 A operand of GEMM 2; this half fills k-block `half` of row r_loc
+                    uint8_t* grow = Gs + (b * 2 + half) * KB_BYTES + r_loc * 128;
 #pragma unroll
-                for (int h8 = 0; h8 < 8; ++h8) {
-                    uint4 val = make_uint4(packed[4 * h8], packed[4 * h8 + 1], packed[4 * h8 + 2], packed[4 * h8 + 3]);
-                    *reinterpret_cast<uint4*>(grow + ((h8 ^ (r_loc & 7)) << 4)) = val;
+                    for (int h8 = 0; h8 < 8; ++h8) {
+                        uint4 val = make_uint4(packed[4 * h8], packed[4 * h8 + 1], packed[4 * h8 + 2], packed[4 * h8 + 3]);
+                        *reinterpret_cast<uint4*>(grow + ((h8 ^ (r_loc & 7)) << 4)) = val;
+                    }
                 }
+                tc_fence_before();
+                if (grad) {
+                    fence_proxy_async();               // generic-proxy smem writes -> visible to the tensor core
+                    mbar_arrive(g_full + b);
+                }
+                mbar_arrive(s_empty + rb * 2 + b);
             }
-            tc_fence_before();
-            if (grad) {
-                fence_proxy_async();                   // generic-proxy smem writes -> visible to the tensor core
-                mbar_arrive(g_full + b);
-            }
-            mbar_arrive(s_empty + b);
         }
-        if (a.mode == SIM_TOPK) {
-            a.cand_cnt[slot] = row_ok ? cnt : 0;
-            a.cand_thr[slot] = thr;
-        } else if (a.mode == SIM_ROWSUM) {
-            if (row_ok) {
-                a.out_part[list * a.R + row] = (racc[0] + racc[1]) + (racc[2] + racc[3]);
-                if (a.diag && have_diag) a.diag[row] = dval;
+        if (MODE == SIM_TOPK && RB == 1) {
+#pragma unroll
+            for (int rb = 0; rb < RB; ++rb) {
+                const long long slot = list * a.Rpad + row[rb];
+                a.cand_cnt[slot] = row_ok[rb] ? cnt[rb] : 0;
+                a.cand_thr[slot] = thr[rb];
+            }
+        } else if (MODE == SIM_ROWSUM) {
+#pragma unroll
+            for (int rb = 0; rb < RB; ++rb) {
+                if (row_ok[rb]) {
+                    a.out_part[list * a.R + row[rb]] = (racc[rb][0] + racc[rb][1]) + (racc[rb][2] + racc[rb][3]);
+                    if (a.diag && have_diag[rb]) a.diag[row[rb]] = dval[rb];
+                }
             }
         } else if (grad) {
             if (n_tiles > 0) {
@@ -483,8 +557,8 @@ simtile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
                 if (n_tiles > 0) tmem_ld32(tmem_acc + c0 + lane_addr, w);
                 else
                     for (int i = 0; i < 32; ++i) w[i] = 0.f;
-                if (row_ok) {
-                    float4* dst = reinterpret_cast<float4*>(a.out_part + ((long long)blockIdx.y * a.R + row) * a.Dp + c0);
+                if (row_ok[0]) {
+                    float4* dst = reinterpret_cast<float4*>(a.out_part + ((long long)blockIdx.y * a.R + row[0]) * a.Dp + c0);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) dst[i] = make_float4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
                 }
@@ -601,14 +675,15 @@ static int make_tmap(CUtensorMap* tm, const void* base, long long rows, int Dp) 
 }
 
 // column chunks per row block: enough CTAs to fill the GPU ~3x, never more chunks than column tiles
-static int sim_chunks(long long R, long long C) {
-    const long long row_blocks = (R + ST_M - 1) / ST_M, col_tiles = (C + ST_N - 1) / ST_N;
+static int sim_chunks(long long R, long long C, int rb = 1) {
+    const long long row_blocks = (R + rb * ST_M - 1) / (rb * ST_M), col_tiles = (C + ST_N - 1) / ST_N;
     long long want = (3LL * sm_count() + row_blocks - 1) / row_blocks;
     want = std::max(1LL, std::min(want, std::min(col_tiles, 16LL)));
     return (int)want;
 }
 
 static int launch_sim(SimArgs a, const void* x, const void* y, int chunks, cudaStream_t stream) {
+    if (a.rb != 2 || a.mode == SIM_GRAD || a.mode == SIM_SCORES) a.rb = 1;
     CFM_REQUIRE(a.Dp % 64 == 0 && a.Dp >= 64 && a.Dp <= 128, CFM_ERR_UNSUPPORTED,
                 "padded feature width %d not in {64,128}", a.Dp);
     CFM_REQUIRE(a.R >= 1 && a.C >= 1, CFM_ERR_INVALID, "empty operand");
@@ -619,14 +694,25 @@ static int launch_sim(SimArgs a, const void* x, const void* y, int chunks, cudaS
     if (rc) return rc;
     a.n_col_tiles = (a.C + ST_N - 1) / ST_N;
     a.tiles_per_chunk = (a.n_col_tiles + chunks - 1) / chunks;
-    const SimSmem L = sim_smem(a.Dp, a.mode);
-    static bool attr = false;
-    if (!attr) {
-        CFM_CHECK_CUDA(cudaFuncSetAttribute(simtile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr = true;
+    const SimSmem L = sim_smem(a.Dp, a.mode, a.rb);
+    typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const SimArgs);
+    KernelFn fn = nullptr;
+    switch (a.mode * 2 + (a.rb - 1)) {
+        case SIM_SCORES * 2: fn = simtile_kernel<SIM_SCORES, 1>; break;
+        case SIM_ROWSUM * 2: fn = simtile_kernel<SIM_ROWSUM, 1>; break;
+        case SIM_ROWSUM * 2 + 1: fn = simtile_kernel<SIM_ROWSUM, 2>; break;
+        case SIM_GRAD * 2: fn = simtile_kernel<SIM_GRAD, 1>; break;
+        case SIM_TOPK * 2: fn = simtile_kernel<SIM_TOPK, 1>; break;
+        case SIM_TOPK * 2 + 1: fn = simtile_kernel<SIM_TOPK, 2>; break;
+        default: set_error("unsupported similarity-kernel variant"); return CFM_ERR_UNSUPPORTED;
     }
-    dim3 grid((a.R + ST_M - 1) / ST_M, chunks);
-    simtile_kernel<<<grid, ST_THREADS, L.total, stream>>>(tmx, tmy, a);
+    static bool attr[8] = {false};
+    if (!attr[a.mode * 2 + (a.rb - 1)]) {
+        CFM_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr[a.mode * 2 + (a.rb - 1)] = true;
+    }
+    dim3 grid((a.R + a.rb * ST_M - 1) / (a.rb * ST_M), chunks);
+    fn<<<grid, ST_THREADS, L.total, stream>>>(tmx, tmy, a);
     CFM_LAUNCH_CHECK();
     return CFM_OK;
 }
@@ -636,7 +722,13 @@ static int launch_sim(SimArgs a, const void* x, const void* y, int chunks, cudaS
 using namespace cfm;
 
 // partial result lists per row: column chunks x the two column halves the epilogue warp groups own
-extern "C" int64_t cfm_simtile_chunks(int64_t R, int64_t C) { return 2 * sim_chunks(R, C); }
+// 128-row blocks per CTA: two blocks share every Y tile (half the L2->SM operand traffic) once there are enough
+// rows to fill the GPU twice over
+static int sim_rb(long long R) { return (R + ST_M - 1) / ST_M >= 4LL * sm_count() ? 2 : 1; }
+
+extern "C" int64_t cfm_simtile_chunks(int64_t R, int64_t C) {
+    return 2 * std::max(sim_chunks(R, C, 1), sim_chunks(R, C, 2));      // upper bound used to size scratch
+}
 
 extern "C" int cfm_pack_rows_bf16(const float* in, int64_t R, int64_t D, int64_t Dp, void* out_bf16, void* stream) {
     CFM_REQUIRE(in && out_bf16 && R >= 0 && D >= 1 && Dp >= D && Dp % 2 == 0, CFM_ERR_INVALID, "bad pack arguments");
@@ -661,8 +753,10 @@ extern "C" int cfm_infonce_rowsum(const void* x_bf16, const void* y_bf16, int64_
                                   void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     CFM_REQUIRE(x_bf16 && y_bf16 && rowsum && part && temperature > 0, CFM_ERR_INVALID, "bad rowsum arguments");
-    const int chunks = sim_chunks(R, C);
+    const int rb = sim_rb(R);
+    const int chunks = sim_chunks(R, C, rb);
     SimArgs a{};
+    a.rb = rb;
     a.mode = SIM_ROWSUM; a.R = (int)R; a.C = (int)C; a.D = (int)Dp; a.Dp = (int)Dp;
     a.c1 = (float)(LOG2E / temperature); a.c2 = (float)(LOG2E / temperature);
     a.diag_offset = diag_offset; a.out_part = part; a.diag = diag;
@@ -721,8 +815,8 @@ constexpr int SEL_MAXC = 1024;      // survivors per row the selection kernel ca
 // (4) survivors are rescored in fp64 from the fp32 operands and ranked (score desc, index asc).
 __global__ void __launch_bounds__(128) topk_select_kernel(const float* __restrict__ rows_f32, const float* __restrict__ cols_f32,
                                    int R, int C, int D, int k, int chunks, int Rpad, float margin, double scale,
-                                   long long col_offset, const float* __restrict__ cand_val,
-                                   const int* __restrict__ cand_idx, const int* __restrict__ cand_cnt,
+                                   long long col_offset, const uint2* __restrict__ cand,
+                                   const int* __restrict__ cand_cnt,
                                    const float* __restrict__ cand_thr, float* __restrict__ out_score,
                                    double* __restrict__ out_score64, long long* __restrict__ out_idx,
                                    int* __restrict__ row_flag) {
@@ -738,15 +832,15 @@ __global__ void __launch_bounds__(128) topk_select_kernel(const float* __restric
     uint32_t t = 0;
     if (kk > 0) {
         for (int bit = 31; bit >= 0; --bit) {
-            const uint32_t cand = t | (1u << bit);
+            const uint32_t cand_key = t | (1u << bit);
             int cnt = 0;
             for (int c = 0; c < chunks; ++c) {
                 const long long slot = (long long)c * Rpad + row;
                 const int n = cand_cnt[slot];
-                for (int p = lane; p < n; p += 32) cnt += float_key(cand_val[slot * TK_CAP + p]) >= cand;
+                for (int p = lane; p < n; p += 32) cnt += float_key(__uint_as_float(cand[slot * TK_CAP + p].x)) >= cand_key;
             }
             cnt = __reduce_add_sync(FULL, cnt);
-            if (cnt >= kk) t = cand;
+            if (cnt >= kk) t = cand_key;
         }
     }
     const float tau = kk > 0 ? key_float(t) : -INFINITY;
@@ -760,10 +854,11 @@ __global__ void __launch_bounds__(128) topk_select_kernel(const float* __restric
         if (cand_thr[slot] >= cut && total >= k) overflow = true;       // this chunk dropped entries that might matter
         for (int p0 = 0; p0 < n; p0 += 32) {
             const int p = p0 + lane;
-            const bool keep = p < n && cand_val[slot * TK_CAP + p] >= cut;
+            const uint2 ent = p < n ? cand[slot * TK_CAP + p] : make_uint2(0u, 0u);
+            const bool keep = p < n && __uint_as_float(ent.x) >= cut;
             const unsigned m = __ballot_sync(FULL, keep);
             const int wpos = n_s + __popc(m & ((1u << lane) - 1));
-            if (keep && wpos < SEL_MAXC) s_idx[w][wpos] = cand_idx[slot * TK_CAP + p];
+            if (keep && wpos < SEL_MAXC) s_idx[w][wpos] = (int)ent.y;
             n_s += __popc(m);
         }
     }
@@ -858,18 +953,20 @@ __global__ void __launch_bounds__(128) allpairs_rank_kernel(const float* __restr
 extern "C" int cfm_allpairs_topk(const float* rows_f32, const float* cols_f32, const void* rows_bf16, const void* cols_bf16,
                                  int64_t R, int64_t C, int64_t D, int64_t Dp, int64_t k, double scale, double margin,
                                  int64_t col_offset, float* out_score, double* out_score64, int64_t* out_idx,
-                                 int32_t* row_flag, float* cand_val, int32_t* cand_idx, int32_t* cand_cnt, float* cand_thr,
-                                 void* stream_) {
+                                 int32_t* row_flag, void* cand, int32_t* cand_cnt, float* cand_thr, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    CFM_REQUIRE(rows_f32 && cols_f32 && rows_bf16 && cols_bf16 && out_score && out_idx && row_flag && cand_val &&
-                    cand_idx && cand_cnt && cand_thr, CFM_ERR_INVALID, "null pointer");
+    CFM_REQUIRE(rows_f32 && cols_f32 && rows_bf16 && cols_bf16 && out_score && out_idx && row_flag && cand && cand_cnt &&
+                    cand_thr, CFM_ERR_INVALID, "null pointer");
     CFM_REQUIRE(R >= 1 && C >= 1 && k >= 1 && k <= TK_KEEP / 2 + 32 && D <= Dp && margin >= 0, CFM_ERR_UNSUPPORTED,
                 "top-k supports 1 <= k <= %d (got %lld)", TK_KEEP / 2 + 32, (long long)k);
-    const int chunks = sim_chunks(R, C);
+    const int rb = sim_rb(R);
+    const int chunks = sim_chunks(R, C, rb);
     SimArgs a{};
+    a.rb = rb;
     a.mode = SIM_TOPK; a.R = (int)R; a.C = (int)C; a.D = (int)D; a.Dp = (int)Dp;
-    a.cand_val = cand_val; a.cand_idx = cand_idx; a.cand_cnt = cand_cnt; a.cand_thr = cand_thr;
-    a.Rpad = (int)((R + ST_M - 1) / ST_M) * ST_M;
+    a.cand = (uint2*)cand; a.cand_cnt = cand_cnt; a.cand_thr = cand_thr;
+    a.keep = (int)std::min<int64_t>(TK_KEEP, ((k + 60 + 31) / 32) * 32);
+    a.Rpad = (int)((R + 2 * ST_M - 1) / (2 * ST_M)) * 2 * ST_M;
     {
         ProfScope prof(PROF_TOPK, stream);
         int rc = launch_sim(a, rows_bf16, cols_bf16, chunks, stream);
@@ -877,8 +974,9 @@ extern "C" int cfm_allpairs_topk(const float* rows_f32, const float* cols_f32, c
     }
     ProfScope prof(PROF_TOPK_POST, stream);
     topk_select_kernel<<<(int)((R + 3) / 4), 128, 0, stream>>>(rows_f32, cols_f32, (int)R, (int)C, (int)D, (int)k, 2 * chunks,
-                                                             a.Rpad, (float)margin, scale, col_offset, cand_val, cand_idx,
-                                                             cand_cnt, cand_thr, out_score, out_score64, (long long*)out_idx, row_flag);
+                                                             a.Rpad, (float)margin, scale, col_offset, (const uint2*)cand,
+                                                             cand_cnt, cand_thr, out_score, out_score64, (long long*)out_idx,
+                                                             row_flag);
     CFM_LAUNCH_CHECK();
     return CFM_OK;
 }

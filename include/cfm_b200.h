@@ -204,15 +204,15 @@ int cfm_simtile_scores(const void* x_bf16, const void* y_bf16, int64_t R, int64_
  * bf16-operand score (2^-7 * max|row| * max|col|); rows whose completeness cannot be proven get row_flag = 1 and
  * must be redone exactly by the caller.  k <= 128.  The [R,C] score matrix never exists in memory.
  *   rows [R,D] / cols [C,D] f32 and bf16 copies [R,Dp] / [C,Dp]; col_offset is added to emitted indices (shards)
- *   scratch: cand_val/cand_idx [chunks*Rpad, CFM_TOPK_CAP], cand_cnt/cand_thr [chunks*Rpad],
- *            chunks = cfm_simtile_chunks(R, C), Rpad = R rounded up to 128
+ *   scratch: cand [lists*Rpad, CFM_TOPK_CAP] 8-byte (score bits, column) entries, cand_cnt/cand_thr [lists*Rpad],
+ *            lists = cfm_simtile_chunks(R, C), Rpad = R rounded up to 256
  * ------------------------------------------------------------------------------------------ */
 #define CFM_TOPK_CAP 384
 int cfm_allpairs_topk(const float* rows_f32, const float* cols_f32, const void* rows_bf16, const void* cols_bf16,
                       int64_t R, int64_t C, int64_t D, int64_t Dp, int64_t k, double scale, double margin,
                       int64_t col_offset, float* out_score /* [R,k] */, double* out_score64 /* [R,k] nullable */,
-                      int64_t* out_idx /* [R,k] */, int32_t* row_flag /* [R] */, float* cand_val, int32_t* cand_idx,
-                      int32_t* cand_cnt, float* cand_thr, void* stream);
+                      int64_t* out_idx /* [R,k] */, int32_t* row_flag /* [R] */, void* cand, int32_t* cand_cnt,
+                      float* cand_thr, void* stream);
 /* merge `n_parts` (<= 16) per-shard top-k lists [n_parts,R,k] into the global top-k (score desc, index asc).
  * Pass the fp64 scores of cfm_allpairs_topk (score_is_f64 = 1) to keep the exact cross-shard ordering: two fp64
  * scores may round to the same fp32 value. */
