@@ -73,12 +73,14 @@ PROTOTYPES = {
     "cfm_cosine_head_bwd": (C.c_int, [_V, _V, _V, _V, _V, _V, _V, _V, _V, _I, _I, _D, _V, _V, _V, _V, _V]),
     "cfm_structural_head": (C.c_int, [_V, _V, _V, _V, _V, _V, _I, _D, _V, _V, _V, _V, _V, _V]),
     "cfm_simtile_chunks": (i64, [_I, _I]),
+    "cfm_simtile_set_rb": (C.c_int, [_I]),
     "cfm_pack_rows_bf16": (C.c_int, [_V, _I, _I, _I, _V, _V]),
     "cfm_infonce_rowsum": (C.c_int, [_V, _V, _I, _I, _I, _D, _I, _V, _V, _V, _V]),
     "cfm_infonce_loss": (C.c_int, [_V, _V, _V, _I, _D, _I, _V, _V]),
     "cfm_infonce_grad": (C.c_int, [_V, _V, _I, _I, _I, _I, _D, _I, _I, _V, _V, _V, _V, _V, _V, _V]),
     "cfm_simtile_scores": (C.c_int, [_V, _V, _I, _I, _I, _V, _V]),
-    "cfm_allpairs_topk": (C.c_int, [_V, _V, _V, _V, _I, _I, _I, _I, _I, _D, _D, _I, _V, _V, _V, _V, _V, _V, _V, _V]),
+    "cfm_pack_rows_f16": (C.c_int, [_V, _I, _I, _I, _V, _V]),
+    "cfm_allpairs_topk": (C.c_int, [_V, _V, _V, _V, _I, _I, _I, _I, _I, _I, _D, _D, _I, _V, _V, _V, _V, _V, _V, _V, _V]),
     "cfm_topk_merge": (C.c_int, [_V, _I, _V, _I, _I, _I, _V, _V, _V]),
     "cfm_allpairs_rank": (C.c_int, [_V, _V, _I, _I, _I, _V, _V, _V]),
 }

@@ -531,6 +531,18 @@ def pack_bf16(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def pack_f16(x: torch.Tensor) -> torch.Tensor:
+    """fp32 [R, D] -> fp16 [R, Dp], zero padded (operands of the all-pairs filter pass when they fit fp16's range)."""
+    _require_cuda(x)
+    R, D = x.shape
+    dp = padded_width(D)
+    out = torch.empty(R, dp, dtype=torch.float16, device=x.device)
+    xf = x.detach().float().contiguous()
+    with torch.cuda.device(x.device):
+        N.check(N.lib().cfm_pack_rows_f16(N.ptr(xf), R, D, dp, N.ptr(out), N.stream_ptr()))
+    return out
+
+
 def simtile_scores(xb: torch.Tensor, yb: torch.Tensor) -> torch.Tensor:
     """Raw tensor-core score tile X . Y^T as fp32 [R, C] (parity/debug aid)."""
     out = torch.empty(xb.shape[0], yb.shape[0], device=xb.device)

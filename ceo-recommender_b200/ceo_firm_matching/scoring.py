@@ -71,17 +71,28 @@ def score_topk(rows: torch.Tensor, cols: torch.Tensor, k: int, scale: float = 1.
         if return_f64:
             out_s64.fill_(float("-inf"))
         return result()
-    rb, cb = ops.pack_bf16(rows), ops.pack_bf16(cols)
-    # |bf16-operand score - exact score| <= 2^-8 |row||col| (Cauchy-Schwarz over the per-element roundings), twice
-    # that separates "certainly in" from "certainly out"; the tiny extra covers fp32 accumulation
-    margin = float((2.0 ** -7 + 2.0 ** -16) * rows.norm(dim=1).max() * cols.norm(dim=1).max())
+    # Filter operands: fp16 copies when the values fit fp16 comfortably (unit-norm tower outputs always do) — 11-bit
+    # mantissas make the filter 8x tighter than bf16 — otherwise bf16 copies (same exponent range as fp32).
+    # |16-bit-operand score - exact score| <= 2u |row||col| (Cauchy-Schwarz over the per-element roundings, u = 2^-11
+    # or 2^-8), twice that separates "certainly in" from "certainly out"; the extra covers fp32 accumulation and
+    # fp16 subnormals.
+    norm_bound = float(rows.norm(dim=1).max() * cols.norm(dim=1).max())
+    amax = float(torch.maximum(rows.abs().max(), cols.abs().max()))
+    use_f16 = 1e-2 < amax < 1e3
+    if use_f16:
+        rb, cb = ops.pack_f16(rows), ops.pack_f16(cols)
+        margin = (2.0 ** -10 + 2.0 ** -16) * norm_bound + 4e-6
+    else:
+        rb, cb = ops.pack_bf16(rows), ops.pack_bf16(cols)
+        margin = (2.0 ** -7 + 2.0 ** -16) * norm_bound
     chunks = N.lib().cfm_simtile_chunks(R, C)
     rpad = (R + 255) // 256 * 256
     cand = torch.empty(chunks * rpad * N.CFM_TOPK_CAP, 2, dtype=torch.int32, device=dev)    # (score bits, column)
     cand_cnt = torch.empty(chunks * rpad, dtype=torch.int32, device=dev)
     cand_thr = torch.empty(chunks * rpad, device=dev)
     with torch.cuda.device(dev):
-        N.check(N.lib().cfm_allpairs_topk(N.ptr(rows), N.ptr(cols), N.ptr(rb), N.ptr(cb), R, C, D, rb.shape[1], k,
+        N.check(N.lib().cfm_allpairs_topk(N.ptr(rows), N.ptr(cols), N.ptr(rb), N.ptr(cb), 1 if use_f16 else 0, R, C, D,
+                                          rb.shape[1], k,
                                           float(scale), margin, col_offset, N.ptr(out_s), N.ptr(out_s64), N.ptr(out_i), N.ptr(flags),
                                           N.ptr(cand), N.ptr(cand_cnt), N.ptr(cand_thr),
                                           N.stream_ptr()))

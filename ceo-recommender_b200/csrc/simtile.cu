@@ -12,12 +12,14 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <algorithm>
 
 namespace cfm {
 
 constexpr int ST_M = 128, ST_N = 128, ST_KB = 64;      // tile rows / cols, bf16 elements per 128-byte swizzle row
 constexpr int ST_STAGES = 3;
+__host__ __device__ constexpr int sim_stages(int mode, int rb) { return (mode == 2 && rb == 2) ? 2 : ST_STAGES; }
 constexpr int ST_THREADS = 64 + 8 * 32;               // TMA warp, MMA warp, 8 epilogue warps
 constexpr int KB_BYTES = ST_M * 128;                   // one [128 rows x 64 bf16] swizzled block = 16 KB
 constexpr float LOG2E = 1.4426950408889634f;
@@ -112,6 +114,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 }
 
 // 64 consecutive fp32 columns of this thread's TMEM lane (one instruction, one wait)
+template <bool WAIT = true>
 __device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
     uint32_t r[64];
     asm volatile(
@@ -130,10 +133,11 @@ __device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
           "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
         : "r"(taddr)
         : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (WAIT) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
     for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // 2^x on the SFU (MUFU.EX2), flush-to-zero: one instruction, no denormal fix-up
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
@@ -153,8 +157,9 @@ __device__ __forceinline__ uint64_t desc_mnmajor_sw128(uint32_t saddr, uint32_t 
            ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 // instruction descriptor: fp32 accumulate (c_format=1 @4), bf16 A/B (=1 @7, @10), b_major @16, N>>3 @17, M>>4 @24
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool b_mn_major) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((b_mn_major ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) |
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool b_mn_major, bool f16 = false) {
+    const uint32_t fmt = f16 ? 0u : 1u;        // kind::f16 operand format: 0 = fp16, 1 = bf16
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((b_mn_major ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) |
            ((uint32_t)(M >> 4) << 24);
 }
 
@@ -260,6 +265,7 @@ struct SimArgs {
     float* out_part;              // rowsum: [chunks, R]; grad: [chunks, R, Dp]; scores: [R, C]
     float* diag;                  // [R] (rowsum, nullable)
     uint2* cand;                  // top-k: [lists * Rpad, TK_CAP] (bf16-operand score bits, column)
+    int f16;                      // operands are fp16 instead of bf16 (top-k with unit-norm rows: 8x tighter filter)
     int keep;                     // top-k: entries kept by a compaction (k + slack for the rescoring margin, <= TK_KEEP)
     int rb;                       // 128-row blocks per CTA (2 halves the L2->SM traffic of the Y tiles; 1 in grad mode)
     int* cand_cnt;                // top-k: [lists * Rpad] entries in use
@@ -293,9 +299,9 @@ __host__ __device__ inline SimSmem sim_smem(int Dp, int mode, int rb) {
     const int nkb = Dp / ST_KB;
     int o = 0;
     s.x = o; o += rb * nkb * KB_BYTES;
-    s.y = o; o += ST_STAGES * nkb * KB_BYTES;
+    s.y = o; o += sim_stages(mode, rb) * nkb * KB_BYTES;
     s.g = o; o += mode == SIM_GRAD ? 2 * 2 * KB_BYTES : 0;
-    s.ry = o; o += 2 * ST_N * 4;
+    s.ry = o; o += 4 * ST_N * 4;
     s.bars = o; o += 32 * 8;
     s.tmem_slot = o; o += 16;
     s.total = o + 1024;           // slack for the manual 1024-byte alignment
@@ -324,14 +330,16 @@ simtile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
     const int tile0 = blockIdx.y * a.tiles_per_chunk;
     const int n_tiles = max(0, min(a.tiles_per_chunk, a.n_col_tiles - tile0));
     constexpr bool grad = MODE == SIM_GRAD;
+    constexpr bool GRAD2 = MODE == SIM_GRAD && RB == 2;    // two row blocks ping-pong on single-buffered S / G
+    constexpr int NSTG = sim_stages(MODE, RB);
 
     if (threadIdx.x == 0) {
         mbar_init(x_full, 1);
-        for (int s = 0; s < ST_STAGES; ++s) { mbar_init(y_full + s, 1); mbar_init(y_empty + s, 1); }
+        for (int s = 0; s < NSTG; ++s) { mbar_init(y_full + s, 1); mbar_init(y_empty + s, 1); }
         // an S buffer is drained by all 8 epilogue warps (column halves) except in the top-k RB=2 variant, where
         // each 128-row block belongs to one warp group that walks both halves (one candidate stream per row)
-        for (int b = 0; b < 4; ++b) { mbar_init(s_full + b, 1); mbar_init(s_empty + b, (MODE == SIM_TOPK && RB == 2) ? 128 : 256); }
-        for (int b = 0; b < 2; ++b) { mbar_init(g_full + b, 256); mbar_init(g_empty + b, 1); }
+        for (int b = 0; b < 4; ++b) { mbar_init(s_full + b, 1); mbar_init(s_empty + b, ((MODE == SIM_TOPK && RB == 2) || GRAD2) ? 128 : 256); }
+        for (int b = 0; b < 2; ++b) { mbar_init(g_full + b, GRAD2 ? 128 : 256); mbar_init(g_empty + b, 1); }
         mbar_init(acc_full, 1);
         fence_barrier_init();
     }
@@ -352,8 +360,8 @@ simtile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
                 for (int kb = 0; kb < nkb; ++kb)
                     tma_load_2d(Xs + (rb * nkb + kb) * KB_BYTES, &tm_x, x_full, kb * ST_KB, row0 + rb * ST_M);
             for (int t = 0; t < n_tiles; ++t) {
-                const int s = t % ST_STAGES;
-                mbar_wait(y_empty + s, ((t / ST_STAGES) & 1) ^ 1);
+                const int s = t % NSTG;
+                mbar_wait(y_empty + s, ((t / NSTG) & 1) ^ 1);
                 mbar_expect_tx(y_full + s, nkb * KB_BYTES);
                 for (int kb = 0; kb < nkb; ++kb)
                     tma_load_2d(Ys + (s * nkb + kb) * KB_BYTES, &tm_y, y_full + s, kb * ST_KB, (tile0 + t) * ST_N);
@@ -362,14 +370,47 @@ simtile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            const uint32_t idesc1 = make_idesc(ST_M, ST_N, false);
+            const uint32_t idesc1 = make_idesc(ST_M, ST_N, false, a.f16 != 0);
             const uint32_t idesc2 = make_idesc(ST_M, a.Dp, true);
             const uint32_t xs = smem_u32(Xs), ys = smem_u32(Ys), gs = smem_u32(Gs);
             mbar_wait(x_full, 0);
+            if (GRAD2) {
+                // per Y tile: S_0, S_1 (GEMM 1 for both row blocks), then dX_0 += G_0 Y, dX_1 += G_1 Y.  While the
+                // epilogue of one row block exponentiates, the tensor core works for the other one.
+                for (int t = 0; t < n_tiles; ++t) {
+                    const int s = t % NSTG;
+                    mbar_wait(y_full + s, (t / NSTG) & 1);
+                    const uint32_t yb = ys + s * nkb * KB_BYTES;
+                    for (int rb = 0; rb < 2; ++rb) {
+                        mbar_wait(s_empty + rb * 2, (t & 1) ^ 1);
+                        tc_fence_after();
+                        const uint32_t xb = xs + rb * nkb * KB_BYTES;
+                        for (int ks = 0; ks < a.Dp / 16; ++ks) {
+                            const uint32_t off = (ks >> 2) * KB_BYTES + (ks & 3) * 32;
+                            umma_bf16(tmem_s0 + rb * ST_N, desc_kmajor_sw128(xb + off), desc_kmajor_sw128(yb + off), idesc1, ks > 0);
+                        }
+                        umma_commit(s_full + rb * 2);
+                    }
+                    for (int rb = 0; rb < 2; ++rb) {
+                        mbar_wait(g_full + rb, t & 1);
+                        tc_fence_after();
+                        const uint32_t gb = gs + rb * 2 * KB_BYTES;
+                        for (int ks = 0; ks < ST_N / 16; ++ks) {
+                            const uint32_t aoff = (ks >> 2) * KB_BYTES + (ks & 3) * 32;
+                            const uint32_t boff = ks * 16 * 128;
+                            umma_bf16(tmem_acc + rb * ST_N, desc_kmajor_sw128(gb + aoff), desc_mnmajor_sw128(yb + boff, KB_BYTES),
+                                      idesc2, t > 0 || ks > 0);
+                        }
+                        umma_commit(g_empty + rb);
+                    }
+                    umma_commit(y_empty + s);
+                }
+                umma_commit(acc_full);
+            } else
             for (int t = 0; t <= n_tiles; ++t) {
                 if (t < n_tiles) {                     // GEMM 1: S(rb, b) = X_rb . Y_t^T
-                    const int s = t % ST_STAGES, b = t & 1;
-                    mbar_wait(y_full + s, (t / ST_STAGES) & 1);
+                    const int s = t % NSTG, b = t & 1;
+                    mbar_wait(y_full + s, (t / NSTG) & 1);
                     const uint32_t yb = ys + s * nkb * KB_BYTES;
                     for (int rb = 0; rb < RB; ++rb) {
                         mbar_wait(s_empty + rb * 2 + b, ((t >> 1) & 1) ^ 1);
@@ -385,7 +426,7 @@ simtile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
                     if (!grad) umma_commit(y_empty + s);
                 }
                 if (grad && t >= 1) {                  // GEMM 2: dX += G_u . Y_u   (u = t - 1)
-                    const int u = t - 1, s = u % ST_STAGES, g = u & 1;
+                    const int u = t - 1, s = u % NSTG, g = u & 1;
                     mbar_wait(g_full + g, (u >> 1) & 1);
                     tc_fence_after();
                     const uint32_t yb = ys + s * nkb * KB_BYTES, gb = gs + g * 2 * KB_BYTES;
@@ -399,7 +440,7 @@ simtile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
                     umma_commit(y_empty + s);
                 }
             }
-            if (grad) umma_commit(acc_full);
+            if (grad && !GRAD2) umma_commit(acc_full);
         }
     } else {
         // ===================== epilogue: 8 warps; thread <-> TMEM lane <-> row, warp group <-> column half ======
@@ -422,7 +463,71 @@ simtile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
             racc[rb][0] = racc[rb][1] = racc[rb][2] = racc[rb][3] = 0.f;
         }
         const float rx = (grad && row_ok[0]) ? a.alpha / a.rowsum_x[row[0]] : 0.f;
-        if (MODE == SIM_TOPK && RB == 2) {
+        if (GRAD2) {
+            // warp group `half` owns row block `half`: 128 threads, one row each, all 128 columns of every tile
+            const int rbo = half;
+            const long long myrow = (long long)row0 + rbo * ST_M + r_loc;
+            const bool my_ok = myrow < a.R;
+            const float myrx = my_ok ? a.alpha / a.rowsum_x[myrow] : 0.f;
+            const long long dcol = myrow + a.diag_offset;
+            uint8_t* grow = Gs + rbo * 2 * KB_BYTES + r_loc * 128;
+            for (int t = 0; t < n_tiles; ++t) {
+                const int jt = (tile0 + t) * ST_N;
+                float* ry = sm_ry + (rbo * 2 + (t & 1)) * ST_N;      // per group, double-buffered by tile parity
+                ry[r_loc] = (jt + r_loc < a.C) ? a.alpha / a.rowsum_y[jt + r_loc] : 0.f;
+                named_bar_sync(1 + rbo, 128);
+                mbar_wait(s_full + rbo * 2, t & 1);
+                tc_fence_after();
+                const bool edge = jt + 128 > a.C || (dcol >= jt && dcol < jt + 128);
+                uint32_t packed[64];
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    float v[64];
+                    tmem_ld64(tmem_s0 + rbo * ST_N + 64 * hh + lane_addr, v);
+#pragma unroll
+                    for (int i = 0; i < 64; i += 2) {
+                        const int c = 64 * hh + i;
+                        float g0 = ex2_approx(fmaf(v[i], a.c1, -a.c2)) * (myrx + ry[c]);
+                        float g1 = ex2_approx(fmaf(v[i + 1], a.c1, -a.c2)) * (myrx + ry[c + 1]);
+                        if (edge) {
+                            if (jt + c >= a.C || jt + c == dcol) g0 = 0.f;
+                            if (jt + c + 1 >= a.C || jt + c + 1 == dcol) g1 = 0.f;
+                        }
+                        __nv_bfloat162 h2 = __floats2bfloat162_rn(g0, g1);
+                        packed[c >> 1] = *reinterpret_cast<uint32_t*>(&h2);
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(s_empty + rbo * 2);                       // S consumed: GEMM 1 of the next tile may run
+                mbar_wait(g_empty + rbo, (t & 1) ^ 1);                // GEMM 2 of the previous tile is done with G
+#pragma unroll
+                for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+                    for (int h8 = 0; h8 < 8; ++h8) {
+                        const int o = kb * 32 + h8 * 4;
+                        uint4 val = make_uint4(packed[o], packed[o + 1], packed[o + 2], packed[o + 3]);
+                        *reinterpret_cast<uint4*>(grow + kb * KB_BYTES + ((h8 ^ (r_loc & 7)) << 4)) = val;
+                    }
+                fence_proxy_async();
+                mbar_arrive(g_full + rbo);
+            }
+            if (n_tiles > 0) {
+                mbar_wait(acc_full, 0);
+                tc_fence_after();
+            }
+            for (int c = 0; c < a.Dp / 32; ++c) {
+                float w[32];
+                if (n_tiles > 0) tmem_ld32(tmem_acc + rbo * ST_N + c * 32 + lane_addr, w);
+                else
+                    for (int i = 0; i < 32; ++i) w[i] = 0.f;
+                if (my_ok) {
+                    float4* dst = reinterpret_cast<float4*>(a.out_part + ((long long)blockIdx.y * a.R + myrow) * a.Dp + c * 32);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) dst[i] = make_float4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+                }
+            }
+            tc_fence_before();
+        } else if (MODE == SIM_TOPK && RB == 2) {
             // one candidate stream per row: warp group `half` owns row block `half` and walks both column halves
             const int rbo = half;
             const long long list0 = (long long)blockIdx.y * 2;
@@ -434,18 +539,22 @@ simtile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
                 const int b = t & 1;
                 mbar_wait(s_full + rbo * 2 + b, (t >> 1) & 1);
                 tc_fence_after();
+                // both 64-column halves are fetched from TMEM before either is examined (one exposed latency, two
+                // independent max trees for the scheduler)
+                float v0[64], v1[64];
+                tmem_ld64<false>(tmem_s0 + (rbo * 2 + b) * ST_N + lane_addr, v0);
+                tmem_ld64<false>(tmem_s0 + (rbo * 2 + b) * ST_N + 64 + lane_addr, v1);
+                tmem_ld_wait();
+                const int jt = (tile0 + t) * ST_N;
+                if (jt + 128 > a.C) {
 #pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                    const int j0 = (tile0 + t) * ST_N + 64 * hh;
-                    float v[64];
-                    tmem_ld64(tmem_s0 + (rbo * 2 + b) * ST_N + 64 * hh + lane_addr, v);
-                    if (j0 + 64 > a.C) {
-#pragma unroll
-                        for (int i = 0; i < 64; ++i)
-                            if (j0 + i >= a.C) v[i] = -INFINITY;
+                    for (int i = 0; i < 64; ++i) {
+                        if (jt + i >= a.C) v0[i] = -INFINITY;
+                        if (jt + 64 + i >= a.C) v1[i] = -INFINITY;
                     }
-                    topk_admit(a, v, j0, list0, row0 + rbo * ST_M, q, lane, myrow, mythr, mycnt);
                 }
+                topk_admit(a, v0, jt, list0, row0 + rbo * ST_M, q, lane, myrow, mythr, mycnt);
+                topk_admit(a, v1, jt + 64, list0, row0 + rbo * ST_M, q, lane, myrow, mythr, mycnt);
                 tc_fence_before();
                 mbar_arrive(s_empty + rbo * 2 + b);
             }
@@ -545,7 +654,7 @@ simtile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
                     if (a.diag && have_diag[rb]) a.diag[row[rb]] = dval[rb];
                 }
             }
-        } else if (grad) {
+        } else if (grad && !GRAD2) {
             if (n_tiles > 0) {
                 mbar_wait(acc_full, 0);
                 tc_fence_after();
@@ -583,6 +692,16 @@ __global__ void pack_rows_bf16_kernel(const float* __restrict__ in, long long R,
         int c = (int)(i - r * (Dp / 2)) * 2;
         float a = c < D ? in[r * D + c] : 0.f, b = c + 1 < D ? in[r * D + c + 1] : 0.f;
         reinterpret_cast<__nv_bfloat162*>(out)[i] = __floats2bfloat162_rn(a, b);
+    }
+}
+
+__global__ void pack_rows_f16_kernel(const float* __restrict__ in, long long R, int D, int Dp, __half* __restrict__ out) {
+    const long long total = R * (Dp / 2);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long r = i / (Dp / 2);
+        int c = (int)(i - r * (Dp / 2)) * 2;
+        float a = c < D ? in[r * D + c] : 0.f, b = c + 1 < D ? in[r * D + c + 1] : 0.f;
+        reinterpret_cast<__half2*>(out)[i] = __floats2half2_rn(a, b);
     }
 }
 
@@ -654,7 +773,7 @@ static EncodeTiledFn encode_fn() {
 }
 
 // 2-D bf16 tensor [rows, Dp] row-major, box = [64 elements, 128 rows], 128-byte swizzle, OOB rows read as zero
-static int make_tmap(CUtensorMap* tm, const void* base, long long rows, int Dp) {
+static int make_tmap(CUtensorMap* tm, const void* base, long long rows, int Dp, bool f16 = false) {
     EncodeTiledFn fn = encode_fn();
     CFM_REQUIRE(fn, CFM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     CFM_REQUIRE(((uintptr_t)base & 15) == 0, CFM_ERR_INVALID, "bf16 operand must be 16-byte aligned");
@@ -667,7 +786,7 @@ static int make_tmap(CUtensorMap* tm, const void* base, long long rows, int Dp) 
     cuuint64_t strides[1] = {(cuuint64_t)Dp * 2};
     cuuint32_t box[2] = {ST_KB, ST_M};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+    CUresult r = fn(tm, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     CFM_REQUIRE(r == CUDA_SUCCESS, CFM_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d", (int)r);
@@ -675,22 +794,33 @@ static int make_tmap(CUtensorMap* tm, const void* base, long long rows, int Dp) 
 }
 
 // column chunks per row block: enough CTAs to fill the GPU ~3x, never more chunks than column tiles
-static int sim_chunks(long long R, long long C, int rb = 1) {
-    const long long row_blocks = (R + rb * ST_M - 1) / (rb * ST_M), col_tiles = (C + ST_N - 1) / ST_N;
-    long long want = (3LL * sm_count() + row_blocks - 1) / row_blocks;
-    want = std::max(1LL, std::min(want, std::min(col_tiles, 16LL)));
-    return (int)want;
+static int sim_chunks(long long R, long long C, int rb = 1, bool few = false) {
+    // column chunks per row-block CTA: at least ~3 waves of CTAs when the problem allows it, and among those the
+    // count that wastes the least of the last wave; never fewer than 4 column tiles per chunk
+    const long long row_ctas = (R + rb * ST_M - 1) / (rb * ST_M), col_tiles = (C + ST_N - 1) / ST_N;
+    const long long sms = sm_count(), max_chunks = std::max(1LL, std::min(16LL, col_tiles / 4));
+    if (few && row_ctas >= 2 * sms) return 1;      // top-k: every extra list costs more admissions than it saves
+    int best = 1;
+    double best_score = -1.0;
+    for (long long c = 1; c <= max_chunks; ++c) {
+        const long long ctas = row_ctas * c, waves = (ctas + sms - 1) / sms;
+        double eff = (double)ctas / (double)(waves * sms);
+        if (ctas < 3 * sms) eff *= (double)ctas / (double)(3 * sms);      // too few CTAs to hide ramp-up/tails
+        eff -= 0.004 * (double)c;                                         // mild preference for fewer partials
+        if (eff > best_score) { best_score = eff; best = (int)c; }
+    }
+    return best;
 }
 
 static int launch_sim(SimArgs a, const void* x, const void* y, int chunks, cudaStream_t stream) {
-    if (a.rb != 2 || a.mode == SIM_GRAD || a.mode == SIM_SCORES) a.rb = 1;
+    if (a.rb != 2 || a.mode == SIM_SCORES) a.rb = 1;
     CFM_REQUIRE(a.Dp % 64 == 0 && a.Dp >= 64 && a.Dp <= 128, CFM_ERR_UNSUPPORTED,
                 "padded feature width %d not in {64,128}", a.Dp);
     CFM_REQUIRE(a.R >= 1 && a.C >= 1, CFM_ERR_INVALID, "empty operand");
     CUtensorMap tmx, tmy;
-    int rc = make_tmap(&tmx, x, a.R, a.Dp);
+    int rc = make_tmap(&tmx, x, a.R, a.Dp, a.f16 != 0);
     if (rc) return rc;
-    rc = make_tmap(&tmy, y, a.C, a.Dp);
+    rc = make_tmap(&tmy, y, a.C, a.Dp, a.f16 != 0);
     if (rc) return rc;
     a.n_col_tiles = (a.C + ST_N - 1) / ST_N;
     a.tiles_per_chunk = (a.n_col_tiles + chunks - 1) / chunks;
@@ -702,6 +832,7 @@ static int launch_sim(SimArgs a, const void* x, const void* y, int chunks, cudaS
         case SIM_ROWSUM * 2: fn = simtile_kernel<SIM_ROWSUM, 1>; break;
         case SIM_ROWSUM * 2 + 1: fn = simtile_kernel<SIM_ROWSUM, 2>; break;
         case SIM_GRAD * 2: fn = simtile_kernel<SIM_GRAD, 1>; break;
+        case SIM_GRAD * 2 + 1: fn = simtile_kernel<SIM_GRAD, 2>; break;
         case SIM_TOPK * 2: fn = simtile_kernel<SIM_TOPK, 1>; break;
         case SIM_TOPK * 2 + 1: fn = simtile_kernel<SIM_TOPK, 2>; break;
         default: set_error("unsupported similarity-kernel variant"); return CFM_ERR_UNSUPPORTED;
@@ -724,7 +855,17 @@ using namespace cfm;
 // partial result lists per row: column chunks x the two column halves the epilogue warp groups own
 // 128-row blocks per CTA: two blocks share every Y tile (half the L2->SM operand traffic) once there are enough
 // rows to fill the GPU twice over
-static int sim_rb(long long R) { return (R + ST_M - 1) / ST_M >= 4LL * sm_count() ? 2 : 1; }
+static int g_force_rb = 0;      // 0 = automatic; 1 / 2 pin the variant (parity tests exercise both on small inputs)
+static int sim_rb(long long R) {
+    if (g_force_rb == 1 || g_force_rb == 2) return g_force_rb;
+    return (R + ST_M - 1) / ST_M >= 2LL * sm_count() ? 2 : 1;
+}
+
+extern "C" int cfm_simtile_set_rb(int64_t rb) {
+    CFM_REQUIRE(rb >= 0 && rb <= 2, CFM_ERR_INVALID, "rb must be 0 (auto), 1 or 2");
+    g_force_rb = (int)rb;
+    return CFM_OK;
+}
 
 extern "C" int64_t cfm_simtile_chunks(int64_t R, int64_t C) {
     return 2 * std::max(sim_chunks(R, C, 1), sim_chunks(R, C, 2));      // upper bound used to size scratch
@@ -736,6 +877,16 @@ extern "C" int cfm_pack_rows_bf16(const float* in, int64_t R, int64_t D, int64_t
     const long long total = R * (Dp / 2);
     pack_rows_bf16_kernel<<<(int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
         in, R, (int)D, (int)Dp, (__nv_bfloat16*)out_bf16);
+    CFM_LAUNCH_CHECK();
+    return CFM_OK;
+}
+
+extern "C" int cfm_pack_rows_f16(const float* in, int64_t R, int64_t D, int64_t Dp, void* out_f16, void* stream) {
+    CFM_REQUIRE(in && out_f16 && R >= 0 && D >= 1 && Dp >= D && Dp % 2 == 0, CFM_ERR_INVALID, "bad pack arguments");
+    if (R == 0) return CFM_OK;
+    const long long total = R * (Dp / 2);
+    pack_rows_f16_kernel<<<(int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
+        in, R, (int)D, (int)Dp, (__half*)out_f16);
     CFM_LAUNCH_CHECK();
     return CFM_OK;
 }
@@ -775,8 +926,12 @@ extern "C" int cfm_infonce_grad(const void* x_bf16, const void* y_bf16, int64_t 
     cudaStream_t stream = (cudaStream_t)stream_;
     CFM_REQUIRE(x_bf16 && y_bf16 && rowsum_x && rowsum_y && diag && dx && part && temperature > 0 && B_total >= 1 && D <= Dp,
                 CFM_ERR_INVALID, "bad grad arguments");
-    const int chunks = sim_chunks(R, C);
+    // two-row-block ping-pong exists (forced with cfm_simtile_set_rb(2)) but measured slower than one block per
+    // CTA on B200: the SS-mode operand fetch of four GEMMs per Y tile saturates shared-memory bandwidth
+    const int rb = g_force_rb == 2 ? 2 : 1;
+    const int chunks = sim_chunks(R, C, rb);
     SimArgs a{};
+    a.rb = rb;
     a.mode = SIM_GRAD; a.R = (int)R; a.C = (int)C; a.D = (int)D; a.Dp = (int)Dp;
     a.c1 = (float)(LOG2E / temperature); a.c2 = (float)(LOG2E / temperature);
     a.alpha = (float)(1.0 / (2.0 * (double)B_total * temperature));
@@ -951,7 +1106,8 @@ __global__ void __launch_bounds__(128) allpairs_rank_kernel(const float* __restr
 }  // namespace cfm
 
 extern "C" int cfm_allpairs_topk(const float* rows_f32, const float* cols_f32, const void* rows_bf16, const void* cols_bf16,
-                                 int64_t R, int64_t C, int64_t D, int64_t Dp, int64_t k, double scale, double margin,
+                                 int64_t operands_f16, int64_t R, int64_t C, int64_t D, int64_t Dp, int64_t k, double scale,
+                                 double margin,
                                  int64_t col_offset, float* out_score, double* out_score64, int64_t* out_idx,
                                  int32_t* row_flag, void* cand, int32_t* cand_cnt, float* cand_thr, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -960,12 +1116,15 @@ extern "C" int cfm_allpairs_topk(const float* rows_f32, const float* cols_f32, c
     CFM_REQUIRE(R >= 1 && C >= 1 && k >= 1 && k <= TK_KEEP / 2 + 32 && D <= Dp && margin >= 0, CFM_ERR_UNSUPPORTED,
                 "top-k supports 1 <= k <= %d (got %lld)", TK_KEEP / 2 + 32, (long long)k);
     const int rb = sim_rb(R);
-    const int chunks = sim_chunks(R, C, rb);
+    const int chunks = sim_chunks(R, C, rb, true);
     SimArgs a{};
     a.rb = rb;
     a.mode = SIM_TOPK; a.R = (int)R; a.C = (int)C; a.D = (int)D; a.Dp = (int)Dp;
     a.cand = (uint2*)cand; a.cand_cnt = cand_cnt; a.cand_thr = cand_thr;
-    a.keep = (int)std::min<int64_t>(TK_KEEP, ((k + 60 + 31) / 32) * 32);
+    a.f16 = operands_f16 != 0;
+    // survivors of the filter = k + the columns within `margin` of the k-th score: ~24 for bf16 operands on
+    // 1M unit-norm columns, ~3 for fp16; the rest of the slack absorbs clustering before the exact fallback kicks in
+    a.keep = (int)std::min<int64_t>(TK_KEEP, ((k + (a.f16 ? 28 : 60) + 31) / 32) * 32);
     a.Rpad = (int)((R + 2 * ST_M - 1) / (2 * ST_M)) * 2 * ST_M;
     {
         ProfScope prof(PROF_TOPK, stream);

@@ -178,6 +178,8 @@ int cfm_structural_head(const float* c_logits, const float* f_logits, const floa
  * `part` is scratch of cfm_simtile_chunks(R, C) * R floats (rowsum) or * R * Dp floats (grad).
  * ------------------------------------------------------------------------------------------ */
 int64_t cfm_simtile_chunks(int64_t R, int64_t C);
+/* test hook: pin the number of 128-row blocks a similarity-kernel CTA owns (0 = automatic, 1, 2) */
+int cfm_simtile_set_rb(int64_t rb);
 int cfm_pack_rows_bf16(const float* in /* [R,D] */, int64_t R, int64_t D, int64_t Dp, void* out_bf16 /* [R,Dp] */,
                        void* stream);
 int cfm_infonce_rowsum(const void* x_bf16, const void* y_bf16, int64_t R, int64_t C, int64_t Dp, double temperature,
@@ -201,14 +203,18 @@ int cfm_simtile_scores(const void* x_bf16, const void* y_bf16, int64_t R, int64_
  * running threshold in a TK_CAP-entry buffer that is compacted to its TK_KEEP best when full.  Pass 2: every
  * candidate within `margin` of the k-th best is rescored in fp64 from the fp32 operands and the k best are emitted
  * ordered (score desc, index asc), score = scale * <row, col>.  `margin` must bound twice the error of a
- * bf16-operand score (2^-7 * max|row| * max|col|); rows whose completeness cannot be proven get row_flag = 1 and
+ * 16-bit-operand score (2^-7 * max|row| * max|col| for bf16 copies, 2^-10 for fp16 copies, which are the better
+ * choice whenever the operands fit fp16's range, e.g. unit-norm tower outputs); rows whose completeness cannot be proven get row_flag = 1 and
  * must be redone exactly by the caller.  k <= 128.  The [R,C] score matrix never exists in memory.
  *   rows [R,D] / cols [C,D] f32 and bf16 copies [R,Dp] / [C,Dp]; col_offset is added to emitted indices (shards)
  *   scratch: cand [lists*Rpad, CFM_TOPK_CAP] 8-byte (score bits, column) entries, cand_cnt/cand_thr [lists*Rpad],
  *            lists = cfm_simtile_chunks(R, C), Rpad = R rounded up to 256
  * ------------------------------------------------------------------------------------------ */
 #define CFM_TOPK_CAP 384
-int cfm_allpairs_topk(const float* rows_f32, const float* cols_f32, const void* rows_bf16, const void* cols_bf16,
+int cfm_pack_rows_f16(const float* in /* [R,D] */, int64_t R, int64_t D, int64_t Dp, void* out_f16 /* [R,Dp] */,
+                      void* stream);
+int cfm_allpairs_topk(const float* rows_f32, const float* cols_f32, const void* rows_16 /* [R,Dp] */,
+                      const void* cols_16 /* [C,Dp] */, int64_t operands_f16 /* 0: bf16 copies, 1: fp16 copies */,
                       int64_t R, int64_t C, int64_t D, int64_t Dp, int64_t k, double scale, double margin,
                       int64_t col_offset, float* out_score /* [R,k] */, double* out_score64 /* [R,k] nullable */,
                       int64_t* out_idx /* [R,k] */, int32_t* row_flag /* [R] */, void* cand, int32_t* cand_cnt,

@@ -95,3 +95,27 @@ def test_deterministic():
         loss.backward()
         outs.append((loss.clone(), f.grad.clone(), c.grad.clone()))
     assert all(torch.equal(a, b) for a, b in zip(*outs))
+
+
+@pytest.mark.parametrize("rb", [1, 2])
+def test_row_block_variants_agree_with_oracle(rb):
+    """The similarity kernel has one- and two-row-block-per-CTA variants (the second is chosen automatically only
+    for >= 37,888 rows); both are pinned here on an input the oracle can handle."""
+    from ceo_firm_matching import _native as N
+    from ceo_firm_matching.contrastive import info_nce_loss
+    B, D = 1500, 128
+    f0 = _unit(B, D, 3)
+    c0 = F.normalize(0.6 * f0 + 0.8 * _unit(B, D, 4), dim=1)
+    N.check(N.lib().cfm_simtile_set_rb(rb))
+    try:
+        f, c = f0.to(DEV).requires_grad_(True), c0.to(DEV).requires_grad_(True)
+        loss = info_nce_loss(f, c, 0.07)
+        loss.backward()
+    finally:
+        N.check(N.lib().cfm_simtile_set_rb(0))
+    fq, cq = f0.bfloat16().float().requires_grad_(True), c0.bfloat16().float().requires_grad_(True)
+    lo = oracle.info_nce(fq, cq, 0.07)
+    lo.backward()
+    assert float(loss) == pytest.approx(float(lo), rel=2e-5, abs=1e-5)
+    assert_close_scaled(f.grad, fq.grad, 6e-3, "d_firm")
+    assert_close_scaled(c.grad, cq.grad, 6e-3, "d_ceo")

@@ -91,3 +91,19 @@ def test_diagonal_ranks_and_retrieval_metrics():
     want = (order == torch.arange(700).unsqueeze(1)).float().argmax(1).numpy() + 1
     np.testing.assert_array_equal(ranks, want)
     assert oracle.retrieval_metrics(ranks)["recall@10"] == oracle.retrieval_metrics(want)["recall@10"]
+
+
+@pytest.mark.parametrize("rb", [1, 2])
+def test_row_block_variants_give_exact_ranking(rb):
+    """Both CTA shapes of the filter kernel (one / two 128-row blocks, i.e. split vs single candidate stream per row)."""
+    from ceo_firm_matching import _native as N
+    from ceo_firm_matching.scoring import score_topk
+    u, v = _unit(700, 60, 31), _unit(30000, 60, 32)
+    N.check(N.lib().cfm_simtile_set_rb(rb))
+    try:
+        s, idx, flags = score_topk(u.to(DEV), v.to(DEV), 100, SCALE, return_flags=True)
+    finally:
+        N.check(N.lib().cfm_simtile_set_rb(0))
+    so, io = oracle.allpairs_topk(u, v, 100, SCALE)
+    np.testing.assert_array_equal(idx.cpu().numpy(), io.numpy())
+    assert int(flags.sum()) == 0
