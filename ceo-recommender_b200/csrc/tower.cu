@@ -12,93 +12,10 @@
 // merges them in a fixed order -> bitwise reproducible.  Backward mirrors this: per-CTA weight-gradient
 // accumulators stay in registers over all tiles and are written once, then reduced in fixed CTA order.
 #include "common.cuh"
+#include "tower_types.cuh"
 #include <algorithm>
 
 namespace cfm {
-
-constexpr int TM = 64;    // rows per tile
-constexpr int NT = 256;   // threads per CTA
-constexpr float BN_EPS = 1e-5f;
-constexpr int MAX_SMEM = 227 * 1024;
-
-// ------------------------------------------------------------------------------------------
-// descriptors (plain structs passed by value as kernel parameters)
-// ------------------------------------------------------------------------------------------
-struct GatherSrc {
-    int n_num, n_tab, E;
-    const float* x_num;
-    const long long* x_cat;
-    const float* tab[CFM_MAX_TABLES];
-    long long tab_rows[CFM_MAX_TABLES];
-};
-
-struct ActSrc {           // a = dropout(relu(bn(h)))
-    const float* h;       // [B,K] raw Linear output of the previous stage
-    int bn_mode;          // 0 none, 1 batch stats (mean, istd), 2 running stats (mean, var)
-    const float *mean, *var_or_istd, *gamma, *beta;
-    DropCtx drop;
-};
-
-struct InputDesc {        // how a stage's [TM, K] input tile is built
-    int stage;            // 1: gather, >1: activation of previous stage
-    int K;
-    GatherSrc g;
-    ActSrc a;
-};
-
-// Warp-level tensor-core tiling (mma.sync m16n8k8, TF32 operands split 3x for fp32-class accuracy) of a
-// [TM=64, n] output: 8 warps = 2 row halves (32 rows, two m16 tiles) x 4 column groups of 8*NI columns, in passes
-// of up to 128 columns.
-struct MmaPlan {
-    int passes;
-    int wrows;            // rows of the [n, K]-style operand kept in smem (n rounded up to 32)
-};
-__host__ __device__ inline MmaPlan make_plan(int n) {
-    MmaPlan p;
-    p.passes = ceil_div(n, 128);
-    p.wrows = (n + 31) & ~31;
-    return p;
-}
-__host__ __device__ inline int pass_cols(int n, int pass) { return min(128, n - pass * 128); }
-__host__ __device__ inline int pass_ni(int cols) { return cols <= 32 ? 1 : cols <= 64 ? 2 : 4; }
-__host__ __device__ inline int ceil8(int k) { return (k + 7) & ~7; }
-// leading dimension for "transposed" fragment loads (lanes walk rows with t, columns with g): ld == 8 (mod 32)
-__host__ __device__ inline int pad_ld_t(int k) { int ld = (ceil8(k) + 31) & ~31; return ld + 8; }
-
-struct FwdStage {
-    InputDesc in;
-    int N;
-    const float* W;       // [N,K]
-    const float* bias;    // [N]
-    float* hout;          // [B,N]
-    float* stat_part;     // nullable: per-CTA (mean[N], M2[N], count) partials
-};
-struct FwdArgs {
-    FwdStage st[2];
-    long long B;
-    int* err;
-};
-
-struct BwdStage {
-    InputDesc in;         // rebuilds the stage's input tile A
-    int N;
-    const float* W;       // [N,K]
-    int a_bn;             // BN precedes the input activation: keep x-hat tile and emit (sum dy, sum dy*xhat)
-    const float* gin;     // [B,N] incoming gradient (g_out for stage 3, dy_s otherwise)
-    int g_mode;           // 0 as is; 1 train BN: gamma*istd*(dy - c1 - xhat*c2); 2 eval BN: dy*gamma*rsqrt(var+eps)
-    const float* hs;      // [B,N] raw output of this stage (g_mode 1)
-    const float *g_mean, *g_var_or_istd, *g_gamma, *g_c1, *g_c2;
-    float* dW_part;       // per-CTA [N, K+1] (last column = bias gradient), global column order
-    float* dy_out;        // stage>1: [B,K]
-    float* sum_part;      // a_bn: per-CTA [2K]
-    float* dx_emb;        // stage 1, nullable: [B, n_tab*E]
-    float* dx_num;        // stage 1, nullable: [B, n_num]
-    int need_dx;          // run the dX GEMM
-};
-struct BwdArgs {
-    BwdStage st[2];
-    long long B;
-};
 
 // ------------------------------------------------------------------------------------------
 // shared-memory carve-up (same arithmetic on host and device)
@@ -145,10 +62,6 @@ __host__ __device__ inline BwdSmem bwd_smem(int K, int N, int n_tab, int a_bn, i
     s.total_floats = (o + 3) & ~3;
     return s;
 }
-
-// smem column c' of a stage-1 tile -> column of the torch concat layout [numeric | emb_0 | emb_1 ...]
-// (the tile keeps embeddings first so every gathered row lands 16-byte aligned)
-__device__ __forceinline__ int gcol_stage1(int c, int KE, int n_num) { return c < KE ? n_num + c : c - KE; }
 
 // ------------------------------------------------------------------------------------------
 // input tile builders
