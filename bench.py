@@ -279,8 +279,11 @@ def gpu_arm(args):
     model = build_model(device)
     dp = None
     if world > 1:
-        from ceo_firm_matching.distributed import DataParallelTwoTower
-        dp = DataParallelTwoTower(model)
+        from ceo_firm_matching import distributed as D
+        # default: towers data-parallel, tables sharded over NVLink peer memory (per-rank exchange independent of
+        # the world size); --tables replicated = the all-gather form SURVEY 8e describes (does not scale)
+        dp = (D.TableShardedTwoTower(model, batch_rows=B_PER_GPU) if args.tables == "sharded"
+              else D.DataParallelTwoTower(model))
 
     n_data = max(8, min(args.steps + args.warmup, N_PAIRS // B_PER_GPU // max(world, 1)))
     batches = make_batches(n_data, B_PER_GPU, device, seed=1234 + rank)     # ~10 MB each: >> L2 in total
@@ -434,7 +437,9 @@ def gpu_arm(args):
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "global_batch": world * B_PER_GPU,
-                   "parallelism": f"dp{world}" if world > 1 else "single",
+                   "parallelism": ("single" if world == 1 else
+                                   f"dp{world} towers + tables {args.tables}" +
+                                   (" over NVLink peer memory" if args.tables == "sharded" else " (all-gather)")),
                    "l2": f"{n_data} distinct 10 MB batches cycled + 992 MB tables (inputs >> 126 MB L2)",
                    "optimizer_step": "excluded from the metric (SURVEY 8d)", "dropout": 0.1,
                    "launch": "one CUDA-graph replay per step"},
@@ -458,6 +463,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (debugging)")
+    ap.add_argument("--tables", default="sharded", choices=["sharded", "replicated"],
+                    help="multi-GPU embedding tables: sharded over NVLink peer memory, or replicated + all-gather")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

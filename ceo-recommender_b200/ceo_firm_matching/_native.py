@@ -13,6 +13,7 @@ from typing import Optional
 import torch
 
 CFM_MAX_TABLES = 16
+CFM_MAX_PEERS = 8
 CFM_TOPK_CAP = 384
 CFM_ABI_VERSION = 1
 
@@ -51,6 +52,14 @@ class TowerGrads(C.Structure):
     ]
 
 
+class PeerTable(C.Structure):
+    """Mirror of ``cfm_peer_table_t`` (one owned table of the NVLink table-sharded mode)."""
+    _fields_ = [
+        ("n_cols", i64), ("col", i64), ("col0", i64), ("rows", i64), ("grad", C.c_void_p),
+        ("x_cat", C.c_void_p * CFM_MAX_PEERS), ("dx_emb", C.c_void_p * CFM_MAX_PEERS),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/cfm_b200.h declares
 _V, _I, _D, _U64 = C.c_void_p, i64, C.c_double, C.c_uint64
 PROTOTYPES = {
@@ -69,6 +78,13 @@ PROTOTYPES = {
     "cfm_emb_grad_segment_reduce": (C.c_int, [_V, _V, _I, _I, _I, C.POINTER(C.c_void_p), C.POINTER(i64),
                                               _V, _V, _V, _V, _V, _I, _V]),
     "cfm_emb_grad_rezero": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(i64), _I, _I, _V, _I, _V]),
+    "cfm_enable_peer_access": (C.c_int, [_I]),
+    "cfm_ipc_export": (C.c_int, [_V, C.c_char_p, C.POINTER(i64)]),
+    "cfm_ipc_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "cfm_ipc_close": (C.c_int, [_V]),
+    "cfm_emb_gather_rows": (C.c_int, [_V, _I, _I, _I, _I, C.POINTER(C.c_void_p), C.POINTER(i64), _V, _V, _V]),
+    "cfm_emb_grad_peer_reduce": (C.c_int, [C.POINTER(PeerTable), _I, _I, _I, _I, _I, _V, _V, _V, _V, _V, _I, _V]),
+    "cfm_emb_grad_peer_rezero": (C.c_int, [C.POINTER(PeerTable), _I, _I, _I, _V, _I, _V]),
     "cfm_cosine_head_fwd": (C.c_int, [_V, _V, _V, _I, _I, _D, _V, _V, _V, _V, _V, _V, _V, _V]),
     "cfm_cosine_head_bwd": (C.c_int, [_V, _V, _V, _V, _V, _V, _V, _V, _V, _I, _I, _D, _V, _V, _V, _V, _V]),
     "cfm_structural_head": (C.c_int, [_V, _V, _V, _V, _V, _V, _I, _D, _V, _V, _V, _V, _V, _V]),
@@ -128,6 +144,25 @@ def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     if not t.is_contiguous():
         raise RuntimeError("libcfm_b200 needs contiguous tensors")
     return t.data_ptr()
+
+
+class PeerView:
+    """A buffer of another process of the node, mapped into this one through CUDA IPC (``cfm_ipc_open``): just
+    enough of the tensor interface for ``ptr()``.  The memory is owned by the exporting process."""
+    is_cuda = True
+
+    def __init__(self, address: int, shape, dtype, owner_rank: int):
+        self._address, self.shape, self.dtype, self.owner_rank = int(address), tuple(shape), dtype, owner_rank
+
+    def data_ptr(self) -> int:
+        return self._address
+
+    def is_contiguous(self) -> bool:
+        return True
+
+    @property
+    def device(self):
+        return f"peer:{self.owner_rank}"
 
 
 def stream_ptr() -> int:

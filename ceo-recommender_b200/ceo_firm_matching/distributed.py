@@ -4,6 +4,11 @@ NVLink; the reference has no distributed code at all — SURVEY.md 8e).
 * ``DataParallelTwoTower``  – batch rows sharded over ranks, replicas kept bit-identical: one flat-buffer all-reduce
   for the dense tower parameters, and the embedding-table gradients rebuilt on every rank from the all-gathered
   (index, per-pair gradient row) pairs with the same deterministic sorted-segment reduce, in rank order.
+* ``TableShardedTwoTower``  – the scalable form of the same step: every embedding table lives on ONE rank, the
+  others map it over NVLink (CUDA IPC).  Rows are pulled peer-to-peer into a local stash, the towers stay data
+  parallel, and each table's owner runs the sorted-segment reduce over every rank's gradient rows, read in place from
+  the peers' buffers.  Per-rank exchange volume is independent of the world size (the replicated form above receives
+  ``world`` times the gradient rows on every rank).
 * ``GlobalInfoNCE``         – in-batch InfoNCE with global negatives: projections are all-gathered (bf16), every
   rank runs the similarity-tile kernels for ITS rows against ALL columns (row sums in both directions, then both
   gradients), so no partial column sums or gradient reduce-scatter are needed; only two tiny all-gathers of the
@@ -118,6 +123,256 @@ class DataParallelTwoTower:
             x_all = gather_rows(x_cat, self.group)                 # [world*B, K] int64, rank order
             dx_all = gather_rows(dx_emb, self.group)               # [world*B, K*E] f32
             ops.reduce_table_grads(h, x_all, dx_all)               # same inputs, same order -> bitwise equal replicas
+
+
+# ---------------------------------------------------------------------------------------------
+# table-sharded two-tower training over NVLink peer memory
+# ---------------------------------------------------------------------------------------------
+def plan_table_slices(towers: Sequence[Tuple[int, int]], world: int, max_pieces: int = 4,
+                      slack: float = 0.05) -> Tuple[List[int], List[Tuple[int, int, int]], List[int]]:
+    """Decide which rank owns what.  ``towers`` = [(n_tables, emb_dim), ...].  Every table is cut into ``pieces``
+    equal column slices (per tower; slice width a multiple of 4 floats so rows stay 16-byte vectors) and the
+    slices are spread over the ranks longest-first onto the least loaded rank, load = slice width (bytes moved per
+    pair).  The smallest ``pieces`` whose worst rank is within ``slack`` of the best achievable plan is kept.
+    Returns (pieces per tower, slices [(tower, table, piece)], owner rank per slice) — identical on every rank."""
+    def options(E):
+        return [S for S in range(1, max_pieces + 1) if E % S == 0 and (E // S) % 4 == 0] or [1]
+
+    def spread(pieces):
+        slices = [(t, k, c) for t, (K, E) in enumerate(towers) for k in range(K) for c in range(pieces[t])]
+        weight = [towers[t][1] // pieces[t] for t, _, _ in slices]
+        load = [0] * world
+        owner = [0] * len(slices)
+        for s in sorted(range(len(slices)), key=lambda s: (-weight[s], s)):
+            r = min(range(world), key=lambda r: (load[r], r))
+            owner[s] = r
+            load[r] += weight[s]
+        return slices, owner, max(load)
+
+    import itertools
+    plans = []
+    for pieces in itertools.product(*[options(E) for _, E in towers]):
+        slices, owner, worst = spread(pieces)
+        plans.append((worst, sum(pieces), list(pieces), slices, owner))
+    best = min(p[0] for p in plans)
+    ok = [p for p in plans if p[0] <= best * (1.0 + slack)]
+    _, _, pieces, slices, owner = min(ok, key=lambda p: (p[1], p[0]))
+    return pieces, slices, owner
+
+
+class CudaIpcPeers:
+    """Maps buffers of the other ranks of the node into this process: every rank exports the cudaMalloc allocation
+    behind each published tensor (``cfm_ipc_export``), the 64-byte handles travel through the process group, and
+    each accessor opens them with its own device current (``cfm_ipc_open``: NVLink peer access is enabled lazily)."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self._opened = {}                          # (rank, handle) -> mapped base address (a handle opens once)
+
+    def share(self, named: dict) -> dict:
+        """name -> per-rank list (None where a rank did not publish that name); own entries are the local
+        tensors, the others ``PeerView``s."""
+        import ctypes as C
+        from . import _native as N
+        payload = {}
+        for k, v in named.items():
+            if not (v.is_cuda and v.is_contiguous()):
+                raise ValueError(f"{k}: only contiguous CUDA tensors can be published")
+            handle, offset = C.create_string_buffer(64), N.i64()
+            N.check(N.lib().cfm_ipc_export(N.ptr(v), handle, C.byref(offset)))
+            payload[k] = (handle.raw, offset.value, tuple(v.shape), v.dtype)
+        gathered: List[Optional[dict]] = [None] * self.world
+        dist.all_gather_object(gathered, payload, group=self.group)
+        out = {}
+        for r in range(self.world):
+            for k, (handle, offset, shape, dtype) in gathered[r].items():
+                if r == self.rank:
+                    view = named[k]
+                else:
+                    if (r, handle) not in self._opened:
+                        base = C.c_void_p()
+                        N.check(N.lib().cfm_ipc_open(handle, C.byref(base)))
+                        self._opened[(r, handle)] = base.value
+                    view = N.PeerView(self._opened[(r, handle)] + offset, shape, dtype, r)
+                out.setdefault(k, [None] * self.world)[r] = view
+        return out
+
+    def close(self) -> None:
+        from . import _native as N
+        for base in self._opened.values():
+            N.lib().cfm_ipc_close(base)
+        self._opened.clear()
+
+
+class CudaTableOps:
+    """Per-rank kernels of the table-sharded step."""
+
+    def make_row_source(self, handle, tables, pieces, dx_emb):
+        from . import ops
+        return ops.StashedRows(handle, tables, pieces, dx_emb)
+
+    def make_scratch(self, n_owned, n_peers, B, device):
+        from . import ops
+        return ops._SortScratch(n_owned * n_peers * B, n_owned * n_peers, B, device)
+
+    @staticmethod
+    def _array(owned, n_peers):
+        from . import _native as N
+        arr = (N.PeerTable * len(owned))()
+        for j, o in enumerate(owned):
+            arr[j].n_cols, arr[j].col, arr[j].col0 = o["n_cols"], o["col"], o["col0"]
+            arr[j].rows, arr[j].grad = o["grad"].shape[0], N.ptr(o["grad"])
+            for r in range(n_peers):
+                arr[j].x_cat[r] = N.ptr(o["x_cat"][r])
+                arr[j].dx_emb[r] = N.ptr(o["dx_emb"][r])
+        return arr
+
+    def peer_reduce(self, owned, n_peers, B, emb_dim, width, scratch):
+        from . import _native as N
+        N.check(N.lib().cfm_emb_grad_peer_reduce(
+            self._array(owned, n_peers), len(owned), n_peers, B, emb_dim, width, N.ptr(scratch.keys_tmp),
+            N.ptr(scratch.vals_tmp), N.ptr(scratch.keys_sorted), N.ptr(scratch.vals_sorted), N.ptr(scratch.tmp),
+            scratch.tmp_bytes, N.stream_ptr()))
+
+    def rezero(self, owned, emb_dim, width, scratch):
+        from . import _native as N
+        N.check(N.lib().cfm_emb_grad_peer_rezero(self._array(owned, 0), len(owned), emb_dim, width,
+                                                 N.ptr(scratch.keys_sorted), scratch.n_items, N.stream_ptr()))
+
+
+class TableShardedTwoTower:
+    """Hybrid parallelism for ``CEOFirmMatcher`` on one NVLink node: towers data-parallel, tables sharded.
+
+    * every embedding table (or column slice of a wide table, ``plan_table_slices``) is owned by one rank; only the
+      owner's copy is read, receives gradients and should be stepped by the optimiser (``owned_parameters()``);
+      ``consolidate()`` broadcasts the owners' slices so that ``state_dict()`` is complete on every rank again;
+    * forward: the rows of the local batch are pulled from the owners over NVLink into a local stash
+      (``cfm_emb_gather_rows``) that both the forward and the stage-1 backward read;
+    * backward: every rank leaves its per-pair gradient rows in a fixed peer-visible buffer; after the dense
+      all-reduce (which is also the barrier that makes those buffers complete) each owner runs the sorted-segment
+      reduce over all ranks' rows, read in place through its peer mappings; a second tiny collective releases the
+      buffers for the next step.
+
+    Usage per step (``batch_rows`` rows per rank, fixed)::
+
+        model.zero_grad_fast()
+        loss, _ = model.forward_loss(*local_batch)
+        (loss * ts.loss_scale).backward()
+        ts.sync_gradients(release=False)
+        optimizer.step()          # optimiser built over ts.owned_parameters()
+        ts.release()              # peers may read the updated tables / overwrite their buffers from here on
+
+    (without an optimiser ``ts.sync_gradients()`` alone does both).  The owner's dense table gradient is bitwise
+    what ``DataParallelTwoTower`` produces on every rank: same items, same (rank, row) order inside each run."""
+
+    def __init__(self, model, batch_rows: int, group=None, peers=None, table_ops=None):
+        self.model, self.group, self.B = model, group, int(batch_rows)
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.loss_scale = 1.0 / self.world
+        self.kernels = table_ops or CudaTableOps()
+        handles = self.handles = model._handles
+        dev = next(model.parameters()).device
+        self.pieces, self.slices, self.owner = plan_table_slices([(h.n_tables, h.emb_dim) for h in handles],
+                                                                 self.world)
+        table_ids = set()
+        for h in handles:
+            if h.table_grads is None:
+                raise RuntimeError("call model.use_persistent_table_grads(True) before sharding the tables")
+            h.table_grads.defer = True
+            h.table_grads.rezero_hook = lambda: None      # the owner re-zeroes inside sync_gradients
+            table_ids.update(id(e.weight) for e in h.embeddings)
+        self.dense = [p for p in model.parameters() if id(p) not in table_ids]
+        dist.barrier(group=group)
+        for p in self.dense:
+            dist.broadcast(p.data, src=0, group=group)
+        for b in model.buffers():
+            dist.broadcast(b.data, src=0, group=group)
+        self.consolidate()                          # every replica starts from the owners' slices
+        # peer-visible buffers of this rank: indices and gradient rows of its batch, per tower
+        self.x_shared = [torch.zeros(self.B, h.n_tables, dtype=torch.int64, device=dev) for h in handles]
+        self.dx_shared = [torch.zeros(self.B, h.n_tables * h.emb_dim, device=dev) for h in handles]
+        named = {}
+        for (t, k, c), r in zip(self.slices, self.owner):
+            if r == self.rank:
+                named[f"table{t}.{k}"] = handles[t].embeddings[k].weight.data
+        for t in range(len(handles)):
+            named[f"x{t}"], named[f"dx{t}"] = self.x_shared[t], self.dx_shared[t]
+        self.peers = peers or CudaIpcPeers(group)
+        self.views = self.peers.share(named)
+        owner_of = dict(zip(self.slices, self.owner))
+        for t, h in enumerate(handles):
+            tables = [self.views[f"table{t}.{k}"][owner_of[(t, k, c)]]
+                      for k in range(h.n_tables) for c in range(self.pieces[t])]
+            h.row_source = self.kernels.make_row_source(h, tables, self.pieces[t], self.dx_shared[t])
+        # owned slices grouped by tower (one reduce per embedding width)
+        self.groups = []
+        for t, h in enumerate(handles):
+            width = h.emb_dim // self.pieces[t]
+            owned = [dict(n_cols=h.n_tables, col=k, col0=c * width, grad=h.embeddings[k].weight.grad,
+                          x_cat=self.views[f"x{t}"], dx_emb=self.views[f"dx{t}"])
+                     for (tt, k, c), r in zip(self.slices, self.owner) if tt == t and r == self.rank]
+            if owned:
+                self.groups.append(dict(owned=owned, emb_dim=h.emb_dim, width=width, dirty=False,
+                                        scratch=self.kernels.make_scratch(len(owned), self.world, self.B, dev)))
+        self._token = torch.zeros(1, device=dev)
+        dist.barrier(group=group)
+
+    # ---- parameter views ----------------------------------------------------------------
+    def owned_parameters(self) -> List[torch.nn.Parameter]:
+        """Dense parameters plus the tables this rank owns a slice of: what this rank's optimiser should step
+        (columns owned by another rank keep zero gradients here)."""
+        mine = []
+        for (t, k, c), r in zip(self.slices, self.owner):
+            w = self.handles[t].embeddings[k].weight
+            if r == self.rank and all(w is not m for m in mine):
+                mine.append(w)
+        return self.dense + mine
+
+    def consolidate(self) -> None:
+        """Broadcast every slice from its owner (start-up, checkpointing: ``state_dict()`` is then complete)."""
+        for (t, k, c), r in zip(self.slices, self.owner):
+            w = self.handles[t].embeddings[k].weight.data
+            width = w.shape[1] // self.pieces[t]
+            part = w[:, c * width:(c + 1) * width].contiguous()
+            dist.broadcast(part, src=r, group=self.group)
+            w[:, c * width:(c + 1) * width] = part
+
+    # ---- per-step protocol --------------------------------------------------------------
+    def sync_gradients(self, release: bool = True) -> None:
+        """After ``backward()``: all-reduce the tower gradients and let every owner reduce its slices' gradients.
+        With an optimiser pass ``release=False`` and call ``release()`` after ``optimizer.step()``."""
+        for t, h in enumerate(self.handles):
+            pg = h.table_grads
+            if pg.pending is None:
+                continue
+            x_cat, dx_emb = pg.pending            # kept: a replayed CUDA graph refills the same buffers
+            self.x_shared[t].copy_(x_cat)
+            if dx_emb.data_ptr() != self.dx_shared[t].data_ptr():
+                self.dx_shared[t].copy_(dx_emb)
+        # one flat all-reduce for the tower parameters; it completes only after every rank has queued it behind its
+        # backward, so it is also the barrier after which all peer buffers are complete
+        allreduce_flat_([p.grad for p in self.dense] + [self._token], self.group)
+        self.rezero()                             # rows of the previous step (its sorted keys are still in scratch)
+        for g in self.groups:
+            self.kernels.peer_reduce(g["owned"], self.world, self.B, g["emb_dim"], g["width"], g["scratch"])
+            g["dirty"] = True
+        if release:
+            self.release()
+
+    def release(self) -> None:
+        """Second rendezvous of the step: after it, every owner has consumed the peers' gradient rows (they may be
+        overwritten) and, with an optimiser, every owner's updated table rows are visible to the next forward."""
+        dist.all_reduce(self._token, group=self.group)
+
+    def rezero(self) -> None:
+        """Zero the owned gradient slices written by the last reduce.  Runs at the start of the next
+        ``sync_gradients`` (not inside ``zero_grad_fast``, which a CUDA graph may have captured before the first
+        reduce existed); call it directly to get clean ``.grad`` tables earlier."""
+        for g in self.groups:
+            if g["dirty"]:
+                self.kernels.rezero(g["owned"], g["emb_dim"], g["width"], g["scratch"])
+                g["dirty"] = False
 
 
 # ---------------------------------------------------------------------------------------------

@@ -97,6 +97,7 @@ class TowerHandle:
         self._scratch = None
         self.precision = 0                       # 0: fp32-class (3xTF32), 1: single-pass TF32 tensor-core products
         self.table_grads: Optional["PersistentTableGrads"] = None
+        self.row_source: Optional["StashedRows"] = None   # table-sharded mode: rows pulled into a local stash first
 
     # dims -------------------------------------------------------------------------------
     @property
@@ -165,9 +166,18 @@ class _TowerCall:
         t.tower_id = h.tower_id
         t.precision = h.precision
         t.x_num, t.x_cat = N.ptr(x_num), N.ptr(x_cat)
-        for i, e in enumerate(h.embeddings):
-            t.tables[i] = N.ptr(e.weight)
-            t.table_rows[i] = e.num_embeddings
+        if h.row_source is not None and h.n_tables:
+            # rows come from (possibly NVLink peer-mapped) tables into a per-call stash [K, B, E]; the tower kernels
+            # then see table k = stash[k] and index = row number, in forward and in the stage-1 backward
+            self.stash, self.stash_index = h.row_source.gather(x_cat, B)
+            t.x_cat = N.ptr(self.stash_index)
+            for i in range(h.n_tables):
+                t.tables[i] = N.ptr(self.stash[i])
+                t.table_rows[i] = B
+        else:
+            for i, e in enumerate(h.embeddings):
+                t.tables[i] = N.ptr(e.weight)
+                t.table_rows[i] = e.num_embeddings
         t.w1, t.b1, t.w2, t.b2, t.w3, t.b3 = (N.ptr(x) for x in (l1.weight, l1.bias, l2.weight, l2.bias,
                                                                   l3.weight, l3.bias))
         t.bn1_w, t.bn1_b = N.ptr(b1.weight), N.ptr(b1.bias)
@@ -240,7 +250,7 @@ class TowersFunction(torch.autograd.Function):
                     dbn2_w=torch.empty(t.h2, device=dev) if t.bn2 else None,
                     dbn2_b=torch.empty(t.h2, device=dev) if t.bn2 else None,
                     dy1=torch.empty(B, t.h1, device=dev), dy2=torch.empty(B, t.h2, device=dev),
-                    dx_emb=torch.empty(B, t.n_tables * t.emb_dim, device=dev) if t.n_tables else None,
+                    dx_emb=_dx_emb_buffer(h, B, t.n_tables * t.emb_dim, dev) if t.n_tables else None,
                     dx_num=torch.empty(B, t.n_num, device=dev) if ctx.needs_xnum[i] else None,
                 )
                 for k, v in d.items():
@@ -274,6 +284,53 @@ def run_towers(handles: Sequence[TowerHandle], inputs: Sequence[Tuple[torch.Tens
 
 
 # ---------------------------------------------------------------------------------------
+# table-sharded mode: embedding rows pulled from local / NVLink peer-mapped tables into a local stash
+# ---------------------------------------------------------------------------------------
+class StashedRows:
+    """Row source of a tower whose tables may live on other GPUs of the node (``distributed.TableShardedTwoTower``).
+
+    ``tables[k * pieces + c]`` is the full ``[rows_k, E]`` weight of table ``k`` as held by the owner of its column
+    slice ``c``: the local parameter, or a CUDA-IPC mapping of the owner's parameter.  ``gather`` copies the rows a batch needs into a fresh ``[K, B, E]`` stash, so a training step
+    crosses NVLink once for the forward AND the stage-1 backward (which rebuilds its input tile from the same stash).
+    ``dx_emb`` (optional) is a fixed ``[B, K*E]`` buffer the backward writes the per-pair gradient rows into; the
+    table owners read it in place through their own peer mappings."""
+
+    def __init__(self, handle: TowerHandle, tables: Sequence[torch.Tensor], pieces: int = 1,
+                 dx_emb: Optional[torch.Tensor] = None):
+        self.h = handle
+        self.tables, self.pieces = list(tables), int(pieces)
+        if len(self.tables) != handle.n_tables * self.pieces:
+            raise ValueError("one (local or peer-mapped) tensor per (table, column slice) is required")
+        self.dx_emb = dx_emb
+        self._index = {}
+
+    def index_for(self, B: int, device: torch.device) -> torch.Tensor:
+        if B not in self._index:
+            self._index[B] = torch.arange(B, dtype=torch.int64, device=device).unsqueeze(1).repeat(
+                1, self.h.n_tables).contiguous()
+        return self._index[B]
+
+    def gather(self, x_cat: torch.Tensor, B: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        h, dev = self.h, x_cat.device
+        stash = torch.empty(h.n_tables, B, h.emb_dim, device=dev)
+        ptrs = (C.c_void_p * len(self.tables))(*[N.ptr(t) for t in self.tables])
+        rows = (N.i64 * h.n_tables)(*[e.num_embeddings for e in h.embeddings])
+        N.check(N.lib().cfm_emb_gather_rows(N.ptr(x_cat), B, h.n_tables, h.emb_dim, self.pieces, ptrs, rows,
+                                            N.ptr(stash), N.ptr(_state(dev).err_flag), N.stream_ptr()))
+        return stash, self.index_for(B, dev)
+
+
+def _dx_emb_buffer(h: TowerHandle, B: int, width: int, dev: torch.device) -> torch.Tensor:
+    rs = h.row_source
+    if rs is not None and rs.dx_emb is not None:
+        if tuple(rs.dx_emb.shape) != (B, width):
+            raise RuntimeError(f"table-sharded mode was set up for batches of {rs.dx_emb.shape[0]} rows per rank, "
+                               f"got {B}")
+        return rs.dx_emb
+    return torch.empty(B, width, device=dev)
+
+
+# ---------------------------------------------------------------------------------------
 # embedding gradients: sorted-segment reduce into dense [n_i, E] tables
 # ---------------------------------------------------------------------------------------
 class _SortScratch:
@@ -301,6 +358,7 @@ class PersistentTableGrads:
         self.prev: Optional[_SortScratch] = None
         self.defer = False                       # data parallelism: keep (indices, rows) for the cross-rank reduce
         self.pending = None
+        self.rezero_hook = None                  # table-sharded mode: the owner re-zeroes its tables itself
         for e in handle.embeddings:
             e.weight.grad = torch.zeros_like(e.weight)
 
@@ -310,6 +368,9 @@ class PersistentTableGrads:
         return self.scratches[n_items]
 
     def rezero(self) -> None:
+        if self.rezero_hook is not None:
+            self.rezero_hook()
+            return
         if self.prev is None:
             return
         h = self.h
@@ -357,6 +418,10 @@ def reduce_table_grads(h: TowerHandle, x_cat: torch.Tensor, dx_emb: torch.Tensor
     data-parallel step — into the tower's persistent dense table gradients."""
     pg = h.table_grads
     B = x_cat.shape[0]
+    if pg.prev is not None:
+        # rows of the previous reduce; done here and not only in zero_grad_fast because a CUDA graph captured
+        # before the first reduce existed has no re-zero node to replay
+        pg.rezero()
     scratch = pg.scratch_for(B * h.n_tables, B, dx_emb.device)
     _segment_reduce(h, x_cat.contiguous(), dx_emb.contiguous(), B, [e.weight.grad for e in h.embeddings], scratch)
     pg.prev = scratch

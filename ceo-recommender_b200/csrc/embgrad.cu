@@ -165,3 +165,300 @@ extern "C" int cfm_emb_grad_rezero(float* const* grad_tables, const int64_t* tab
     CFM_LAUNCH_CHECK();
     return CFM_OK;
 }
+
+// =============================================================================================
+// Table-sharded embeddings over NVLink peer memory (single node, one process per GPU).
+// Every table -- or every column slice ("piece") of a wide table -- lives on ONE rank; the others map it (CUDA IPC)
+// and read rows straight through NVLink:
+//   * emb_gather_rows      pulls the rows a batch needs from local/peer tables into a local stash [K][B][E]
+//   * emb_make_keys_peer / emb_segment_reduce_peer: the owner reduces the per-pair gradient rows of EVERY rank's
+//     batch, reading the peers' dx_emb buffers in place (no staging copy, no all-to-all).
+// Order inside a run of equal keys is (rank, row) ascending == the order of the concatenated global batch,
+// so the result is bitwise the replicated data-parallel one.
+// =============================================================================================
+namespace cfm {
+
+struct GatherPlan {
+    const float* table[CFM_MAX_SLOTS];      // [k * pieces + piece]: base of table k as mapped from that piece's owner
+    long long rows[CFM_MAX_TABLES];
+};
+
+// unit i -> (pair j = b*K + k in x_cat memory order, vector q of the row); U independent loads in flight per thread
+template <int VEC>
+__global__ void emb_gather_rows(const long long* __restrict__ x_cat, long long B, int K, int E, int pieces, int w,
+                                GatherPlan gp, float* __restrict__ stash, int* __restrict__ err) {
+    const int EV = E / VEC;
+    const long long total = B * K * EV;
+    constexpr int U = 4;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += stride * U) {
+        float4 v4[U];
+        float v1[U];
+        long long dst[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long iu = i + u * stride;
+            dst[u] = -1;
+            if (iu < total) {
+                const long long j = iu / EV;
+                const int c = (int)(iu - j * EV) * VEC;          // first column of this vector
+                const long long b = j / K;
+                const int k = (int)(j - b * K);
+                long long idx = x_cat[j];
+                if (idx < 0 || idx >= gp.rows[k]) {
+                    if (c == 0) atomicOr(err, 1);
+                    idx = 0;
+                }
+                const float* src = gp.table[k * pieces + c / w] + (size_t)idx * E + c;
+                if (VEC == 4) v4[u] = *reinterpret_cast<const float4*>(src);
+                else v1[u] = *src;
+                dst[u] = ((long long)k * B + b) * E + c;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (dst[u] >= 0) {
+                if (VEC == 4) *reinterpret_cast<float4*>(stash + dst[u]) = v4[u];
+                else stash[dst[u]] = v1[u];
+            }
+        }
+    }
+}
+
+struct PeerPlan {
+    const long long* x_cat[CFM_MAX_TABLES][CFM_MAX_PEERS];
+    const float* dx[CFM_MAX_TABLES][CFM_MAX_PEERS];
+    int n_cols[CFM_MAX_TABLES];
+    int col[CFM_MAX_TABLES];
+    int col0[CFM_MAX_TABLES];
+};
+
+// slot (j*W + r)*B + b: owned-slice-major, then rank, then row -> a stable sort keeps (rank, row) order per key
+__global__ void emb_make_keys_peer(PeerPlan pp, int n_owned, int W, long long B, int idx_bits, TablePtrs tp,
+                                   unsigned long long* __restrict__ keys, int* __restrict__ vals) {
+    const long long n = (long long)n_owned * W * B;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long jr = i / B;
+        const long long b = i - jr * B;
+        const int j = (int)(jr / W), r = (int)(jr - (long long)j * W);
+        long long idx = pp.x_cat[j][r][b * pp.n_cols[j] + pp.col[j]];
+        if (idx < 0 || idx >= tp.rows[j]) idx = 0;       // the gather already flagged the error
+        keys[i] = ((unsigned long long)j << idx_bits) | (unsigned long long)idx;
+        vals[i] = (int)((long long)r * B + b);
+    }
+}
+
+template <int VEC>
+__global__ void emb_segment_reduce_peer(const unsigned long long* __restrict__ keys, const int* __restrict__ vals,
+                                        long long n, long long B, int E, int w, int idx_bits, PeerPlan pp,
+                                        TablePtrs tp) {
+    const int WV = w / VEC;
+    const long long total = n * WV;
+    const unsigned long long mask = (1ull << idx_bits) - 1;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long p = i / WV;
+        const int q = (int)(i - p * WV);
+        const unsigned long long key = keys[p];
+        if (p > 0 && keys[p - 1] == key) continue;
+        const int j = (int)(key >> idx_bits);
+        const long long idx = (long long)(key & mask);
+        const int ld = pp.n_cols[j] * E, off = pp.col[j] * E + pp.col0[j] + q * VEC;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (long long s = p; s < n && keys[s] == key; ++s) {
+            const int v = vals[s];
+            const int r = (int)(v / B);
+            const long long b = v - (long long)r * B;
+            const float* src = pp.dx[j][r] + (size_t)b * ld + off;
+            if (VEC == 4) {
+                const float4 g = *reinterpret_cast<const float4*>(src);
+                acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
+            } else {
+                acc.x += *src;
+            }
+        }
+        float* dst = tp.p[j] + (size_t)idx * E + pp.col0[j] + q * VEC;
+        if (VEC == 4) *reinterpret_cast<float4*>(dst) = acc;
+        else *dst = acc.x;
+    }
+}
+
+// zero columns [col0, col0 + w) of every row a sorted key names
+__global__ void emb_rezero_peer(const unsigned long long* __restrict__ keys, long long n, int E, int w, int idx_bits,
+                                PeerPlan pp, TablePtrs tp) {
+    const long long total = n * w;
+    const unsigned long long mask = (1ull << idx_bits) - 1;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long p = i / w;
+        const int e = (int)(i - p * w);
+        const unsigned long long key = keys[p];
+        if (p > 0 && keys[p - 1] == key) continue;
+        const int j = (int)(key >> idx_bits);
+        tp.p[j][(size_t)(key & mask) * E + pp.col0[j] + e] = 0.f;
+    }
+}
+
+static int fill_peer_plan(PeerPlan& pp, TablePtrs& tp, const cfm_peer_table_t* owned, int64_t n_owned, int64_t n_peers,
+                          int64_t emb_dim, int64_t width, bool need_peers, int* idx_bits, int* key_bits) {
+    CFM_REQUIRE(owned, CFM_ERR_INVALID, "null pointer");
+    CFM_REQUIRE(n_owned >= 1 && n_owned <= CFM_MAX_TABLES && n_peers >= 1 && n_peers <= CFM_MAX_PEERS, CFM_ERR_INVALID,
+                "n_owned outside [1,%d] or n_peers outside [1,%d]", CFM_MAX_TABLES, CFM_MAX_PEERS);
+    CFM_REQUIRE(emb_dim >= 1 && width >= 1 && width <= emb_dim, CFM_ERR_INVALID, "bad emb_dim / width");
+    float* grads[CFM_MAX_TABLES];
+    int64_t rows[CFM_MAX_TABLES];
+    for (int j = 0; j < CFM_MAX_TABLES; ++j) {
+        pp.n_cols[j] = pp.col[j] = pp.col0[j] = 0;
+        for (int r = 0; r < CFM_MAX_PEERS; ++r) { pp.x_cat[j][r] = nullptr; pp.dx[j][r] = nullptr; }
+        if (j >= n_owned) continue;
+        const cfm_peer_table_t& t = owned[j];
+        CFM_REQUIRE(t.n_cols >= 1 && t.col >= 0 && t.col < t.n_cols && t.grad && t.rows >= 1 && t.col0 >= 0 &&
+                        t.col0 + width <= emb_dim, CFM_ERR_INVALID, "bad owned slice %d", j);
+        pp.n_cols[j] = (int)t.n_cols; pp.col[j] = (int)t.col; pp.col0[j] = (int)t.col0;
+        grads[j] = t.grad; rows[j] = t.rows;
+        for (int r = 0; need_peers && r < n_peers; ++r) {
+            CFM_REQUIRE(t.x_cat[r] && t.dx_emb[r], CFM_ERR_INVALID, "owned slice %d: null peer buffer %d", j, r);
+            pp.x_cat[j][r] = (const long long*)t.x_cat[r];
+            pp.dx[j][r] = t.dx_emb[r];
+        }
+    }
+    return fill_tables(tp, grads, rows, n_owned, idx_bits, key_bits);
+}
+
+}  // namespace cfm
+
+extern "C" int cfm_enable_peer_access(int64_t peer_device) {
+    int dev = 0, can = 0;
+    CFM_CHECK_CUDA(cudaGetDevice(&dev));
+    if (peer_device == dev) return CFM_OK;
+    CFM_CHECK_CUDA(cudaDeviceCanAccessPeer(&can, dev, (int)peer_device));
+    CFM_REQUIRE(can, CFM_ERR_UNSUPPORTED, "device %d cannot access peer device %d", dev, (int)peer_device);
+    cudaError_t e = cudaDeviceEnablePeerAccess((int)peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { (void)cudaGetLastError(); return CFM_OK; }
+    CFM_CHECK_CUDA(e);
+    return CFM_OK;
+}
+
+extern "C" int cfm_emb_gather_rows(const int64_t* x_cat, int64_t B, int64_t n_tables, int64_t emb_dim, int64_t pieces,
+                                   const float* const* tables, const int64_t* table_rows, float* stash,
+                                   int32_t* err_flag, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CFM_REQUIRE(x_cat && tables && table_rows && stash && err_flag, CFM_ERR_INVALID, "null pointer");
+    CFM_REQUIRE(B >= 1 && emb_dim >= 1 && n_tables >= 1 && n_tables <= CFM_MAX_TABLES, CFM_ERR_INVALID, "bad sizes");
+    CFM_REQUIRE(pieces >= 1 && emb_dim % pieces == 0 && n_tables * pieces <= CFM_MAX_SLOTS, CFM_ERR_INVALID,
+                "pieces must divide emb_dim and n_tables*pieces <= %d", CFM_MAX_SLOTS);
+    GatherPlan gp;
+    for (int i = 0; i < CFM_MAX_SLOTS; ++i) {
+        gp.table[i] = i < n_tables * pieces ? tables[i] : nullptr;
+        if (i < n_tables * pieces) CFM_REQUIRE(tables[i], CFM_ERR_INVALID, "null table slice %d", i);
+    }
+    for (int i = 0; i < CFM_MAX_TABLES; ++i) {
+        gp.rows[i] = i < n_tables ? table_rows[i] : 0;
+        if (i < n_tables) CFM_REQUIRE(table_rows[i] >= 1, CFM_ERR_INVALID, "bad table %d", i);
+    }
+    const int w = (int)(emb_dim / pieces);
+    const bool vec = (w & 3) == 0;
+    const long long total = B * n_tables * (vec ? emb_dim / 4 : emb_dim);
+    const int grid = (int)std::max<long long>(1, std::min<long long>((total + 1023) / 1024, (long long)sm_count() * 8));
+    ProfScope prof(PROF_EMB, stream);
+    if (vec) emb_gather_rows<4><<<grid, 256, 0, stream>>>((const long long*)x_cat, B, (int)n_tables, (int)emb_dim,
+                                                         (int)pieces, w, gp, stash, err_flag);
+    else emb_gather_rows<1><<<grid, 256, 0, stream>>>((const long long*)x_cat, B, (int)n_tables, (int)emb_dim,
+                                                      (int)pieces, w, gp, stash, err_flag);
+    CFM_LAUNCH_CHECK();
+    return CFM_OK;
+}
+
+extern "C" int cfm_emb_grad_peer_reduce(const cfm_peer_table_t* owned, int64_t n_owned, int64_t n_peers, int64_t B,
+                                        int64_t emb_dim, int64_t width, int64_t* keys_tmp, int32_t* vals_tmp,
+                                        int64_t* keys_sorted, int32_t* vals_sorted, void* sort_tmp,
+                                        int64_t sort_tmp_bytes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CFM_REQUIRE(keys_tmp && vals_tmp && keys_sorted && vals_sorted && sort_tmp, CFM_ERR_INVALID, "null pointer");
+    PeerPlan pp;
+    TablePtrs tp;
+    int idx_bits, key_bits;
+    int rc = fill_peer_plan(pp, tp, owned, n_owned, n_peers, emb_dim, width, true, &idx_bits, &key_bits);
+    if (rc) return rc;
+    CFM_REQUIRE(B >= 1 && n_owned * n_peers * B < (1ll << 31), CFM_ERR_INVALID, "bad sizes");
+    const long long n = n_owned * n_peers * B;
+    ProfScope prof(PROF_EMB, stream);
+    emb_make_keys_peer<<<(int)std::min<long long>((n + 255) / 256, 148 * 8), 256, 0, stream>>>(
+        pp, (int)n_owned, (int)n_peers, B, idx_bits, tp, (unsigned long long*)keys_tmp, vals_tmp);
+    CFM_LAUNCH_CHECK();
+    size_t bytes = (size_t)sort_tmp_bytes;
+    CFM_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(sort_tmp, bytes, (const unsigned long long*)keys_tmp,
+                                                   (unsigned long long*)keys_sorted, (const int*)vals_tmp,
+                                                   vals_sorted, (int)n, 0, key_bits, stream));
+    if ((width & 3) == 0 && (emb_dim & 3) == 0) {
+        const long long total = n * (width / 4);
+        emb_segment_reduce_peer<4><<<(int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, stream>>>(
+            (const unsigned long long*)keys_sorted, vals_sorted, n, B, (int)emb_dim, (int)width, idx_bits, pp, tp);
+    } else {
+        const long long total = n * width;
+        emb_segment_reduce_peer<1><<<(int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, stream>>>(
+            (const unsigned long long*)keys_sorted, vals_sorted, n, B, (int)emb_dim, (int)width, idx_bits, pp, tp);
+    }
+    CFM_LAUNCH_CHECK();
+    return CFM_OK;
+}
+
+extern "C" int cfm_emb_grad_peer_rezero(const cfm_peer_table_t* owned, int64_t n_owned, int64_t emb_dim, int64_t width,
+                                        const int64_t* keys_sorted, int64_t n_items, void* stream_) {
+    CFM_REQUIRE(keys_sorted, CFM_ERR_INVALID, "null pointer");
+    if (n_items == 0) return CFM_OK;
+    PeerPlan pp;
+    TablePtrs tp;
+    int idx_bits, key_bits;
+    int rc = fill_peer_plan(pp, tp, owned, n_owned, 1, emb_dim, width, false, &idx_bits, &key_bits);
+    if (rc) return rc;
+    const long long total = n_items * width;
+    emb_rezero_peer<<<(int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, (cudaStream_t)stream_>>>(
+        (const unsigned long long*)keys_sorted, n_items, (int)emb_dim, (int)width, idx_bits, pp, tp);
+    CFM_LAUNCH_CHECK();
+    return CFM_OK;
+}
+
+// ---- CUDA IPC plumbing for the peer mappings (export on the owner, open on the accessor's own device) ----
+typedef int (*MemGetAddressRangeFn)(unsigned long long*, size_t*, unsigned long long);
+
+extern "C" int cfm_ipc_export(const void* ptr, uint8_t* handle_out, int64_t* offset_out) {
+    CFM_REQUIRE(ptr && handle_out && offset_out, CFM_ERR_INVALID, "null pointer");
+    static MemGetAddressRangeFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        CFM_CHECK_CUDA(cudaGetDriverEntryPoint("cuMemGetAddressRange", &p, cudaEnableDefault, &q));
+        CFM_REQUIRE(q == cudaDriverEntryPointSuccess && p, CFM_ERR_CUDA, "cuMemGetAddressRange entry point not available");
+        fn = (MemGetAddressRangeFn)p;
+    }
+    unsigned long long base = 0;
+    size_t size = 0;
+    int rc = fn(&base, &size, (unsigned long long)(uintptr_t)ptr);
+    CFM_REQUIRE(rc == 0, CFM_ERR_CUDA, "cuMemGetAddressRange failed (%d)", rc);
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, (void*)(uintptr_t)base);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        CFM_REQUIRE(false, CFM_ERR_CUDA,
+                    "cudaIpcGetMemHandle: %s (the buffer must come from cudaMalloc: expandable segments / "
+                    "cudaMallocAsync pools cannot be exported)", cudaGetErrorString(e));
+    }
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(handle_out, &h, sizeof(h));
+    *offset_out = (int64_t)((unsigned long long)(uintptr_t)ptr - base);
+    return CFM_OK;
+}
+
+extern "C" int cfm_ipc_open(const uint8_t* handle, void** base_out) {
+    CFM_REQUIRE(handle && base_out, CFM_ERR_INVALID, "null pointer");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    // opened from the ACCESSING device's context: peer access to the exporting device is enabled lazily
+    CFM_CHECK_CUDA(cudaIpcOpenMemHandle(base_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return CFM_OK;
+}
+
+extern "C" int cfm_ipc_close(void* base) {
+    CFM_REQUIRE(base, CFM_ERR_INVALID, "null pointer");
+    CFM_CHECK_CUDA(cudaIpcCloseMemHandle(base));
+    return CFM_OK;
+}

@@ -135,6 +135,54 @@ int cfm_emb_grad_rezero(float* const* grad_tables /* host */, const int64_t* tab
                         int64_t emb_dim, const int64_t* keys_sorted, int64_t n_items, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Table-sharded embeddings over NVLink peer memory (one process per GPU, single node; the reference has no
+ * multi-GPU code - SURVEY 8e).  Each table - or each of `pieces` equal column slices of it - is owned by one rank;
+ * the other ranks map the owner's tensor (CUDA IPC) and pass the mapped pointer wherever a table pointer is expected.
+ *   cfm_enable_peer_access  : cudaDeviceEnablePeerAccess from the current device to `peer_device` (idempotent).
+ *   cfm_ipc_export/open/close: see below.
+ *   cfm_emb_gather_rows     : stash[k, b, c] = tables[k*pieces + c/(E/pieces)][x_cat[b, k], c]; tables[] holds, per
+ *                             (table, piece), the base of the FULL [rows, E] tensor as mapped from that piece's
+ *                             owner.  stash is [n_tables, B, E]; the towers then run on it (table k = stash[k],
+ *                             index = b), so forward and stage-1 backward touch NVLink once per step.
+ *                             Out-of-range index: err_flag |= 1.
+ *   cfm_emb_grad_peer_reduce: the owner's sorted-segment reduce over EVERY rank's batch.  For owned slice j the
+ *                             items are (rank r, row b) with index x_cat[r][b*n_cols + col] and gradient columns
+ *                             dx_emb[r][b*n_cols*E + col*E + col0 ... + width); both buffers are read in place
+ *                             through the peer mappings; grad[idx, col0 ... col0+width) is written.  Runs of equal
+ *                             keys are summed in (rank, row) order == the order of the concatenated global batch.
+ *                             Scratch as for cfm_emb_grad_segment_reduce with n_items = n_owned*n_peers*B
+ *                             (cfm_emb_grad_tmp_bytes(n_owned*n_peers, B)).
+ *   cfm_emb_grad_peer_rezero: zero the slices named by keys_sorted of the previous reduce (x_cat/dx_emb ignored).
+ * ------------------------------------------------------------------------------------------ */
+#define CFM_MAX_PEERS 8
+#define CFM_MAX_SLOTS 64
+typedef struct cfm_peer_table {
+    int64_t n_cols;                          /* categorical columns of the tower this table belongs to */
+    int64_t col;                             /* this table's column in that tower's x_cat / dx_emb     */
+    int64_t col0;                            /* first embedding column of the owned slice              */
+    int64_t rows;                            /* rows of the table                                       */
+    float* grad;                             /* [rows, emb_dim] dense gradient, local                   */
+    const int64_t* x_cat[CFM_MAX_PEERS];     /* per rank: [B, n_cols] indices (peer-mapped)             */
+    const float* dx_emb[CFM_MAX_PEERS];      /* per rank: [B, n_cols*emb_dim] gradient rows (peer-mapped) */
+} cfm_peer_table_t;
+int cfm_enable_peer_access(int64_t peer_device);
+/* CUDA IPC plumbing for the mappings: the owner exports the cudaMalloc allocation holding `ptr` (64-byte handle +
+ * byte offset of ptr inside it); every other process opens the handle ONCE, with ITS OWN device current (peer access
+ * to the owner's device is enabled lazily), and addresses the buffer at base + offset. */
+int cfm_ipc_export(const void* ptr, uint8_t* handle_out /* 64 bytes */, int64_t* offset_out);
+int cfm_ipc_open(const uint8_t* handle /* 64 bytes */, void** base_out);
+int cfm_ipc_close(void* base);
+int cfm_emb_gather_rows(const int64_t* x_cat, int64_t B, int64_t n_tables, int64_t emb_dim, int64_t pieces,
+                        const float* const* tables /* host array of n_tables*pieces device ptrs */,
+                        const int64_t* table_rows /* host */, float* stash, int32_t* err_flag, void* stream);
+int cfm_emb_grad_peer_reduce(const cfm_peer_table_t* owned /* host */, int64_t n_owned, int64_t n_peers, int64_t B,
+                             int64_t emb_dim, int64_t width, int64_t* keys_tmp, int32_t* vals_tmp,
+                             int64_t* keys_sorted, int32_t* vals_sorted, void* sort_tmp, int64_t sort_tmp_bytes,
+                             void* stream);
+int cfm_emb_grad_peer_rezero(const cfm_peer_table_t* owned /* host */, int64_t n_owned, int64_t emb_dim, int64_t width,
+                             const int64_t* keys_sorted, int64_t n_items, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Cosine head: L2-normalise both latents, row-wise dot, times exp(logit_scale).
  * replaces: model.py:79-87 (eps = 0: plain division) and contrastive.py:64,70,92-93 (eps = 1e-12, F.normalize).
  * The weighted MSE of training.py:52 can be fused into both directions.

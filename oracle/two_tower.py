@@ -162,6 +162,27 @@ def tower_forward(p: Params, spec: TowerSpec, x_num: torch.Tensor, x_cat: torch.
     return F.linear(h, p[f"{spec.prefix}.{li}.weight"], p[f"{spec.prefix}.{li}.bias"])
 
 
+def min_abs_relu_input(p: Params, specs: Sequence[TowerSpec], inputs: Sequence[Tuple[torch.Tensor, torch.Tensor]]
+                       ) -> float:
+    """Smallest |ReLU input| over all hidden units, rows and towers in train mode (float64).  ReLU has no derivative
+    at 0: when a pre-activation lies within an implementation's rounding error of 0, the sign of the unit - and with
+    it a 1/B share of that column's gradients - is decided by rounding, in torch as much as in any other
+    implementation.  Parity tests draw their inputs so that this margin is far above the arithmetic's resolution."""
+    worst = float("inf")
+    for spec, (x_num, x_cat) in zip(specs, inputs):
+        pd = {k: (v.double() if v.is_floating_point() else v) for k, v in p.items()}
+        h = gather_concat(pd, spec.emb_prefix, x_num.double(), x_cat)
+        for s in range(2):
+            li, bi = spec.lin[s], spec.bn[s]
+            h = F.linear(h, pd[f"{spec.prefix}.{li}.weight"], pd[f"{spec.prefix}.{li}.bias"])
+            if bi is not None:
+                pre = f"{spec.prefix}.{bi}"
+                h = F.batch_norm(h, None, None, pd[pre + ".weight"], pd[pre + ".bias"], True, 0.1, 1e-5)
+            worst = min(worst, float(h.abs().min()))
+            h = F.relu(h)
+    return worst
+
+
 def two_tower_forward(p: Params, f_num, f_cat, c_num, c_cat, training: bool = False,
                       masks: Optional[Dict[str, Sequence[Optional[torch.Tensor]]]] = None,
                       update_stats: bool = True) -> torch.Tensor:
