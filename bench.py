@@ -290,14 +290,13 @@ def gpu_arm(args):
 
     from ceo_firm_matching.training import GraphedTwoTowerStep
     # the whole step (sparse re-zero, fwd, loss, bwd, segment reduce) is captured once and replayed
+    # multi-GPU: the gradient synchronisation (NCCL all-reduce + the owners' peer reduce) is captured with the step
     runner = GraphedTwoTowerStep(model, batches[0], optimizer=None, warmup=3,
-                                 loss_scale=dp.loss_scale if dp is not None else 1.0)
+                                 loss_scale=dp.loss_scale if dp is not None else 1.0,
+                                 after_backward=dp.sync_gradients if dp is not None else None)
 
     def step(i):
-        loss = runner.step(batches[i % n_data])      # D2D copy into the graph's static inputs + replay
-        if dp is not None:
-            dp.sync_gradients()
-        return loss
+        return runner.step(batches[i % n_data])      # D2D copy into the graph's static inputs + replay
 
     def barrier():
         if dist is not None:
@@ -365,8 +364,6 @@ def gpu_arm(args):
                 nxt = upload(i + 1)            # prefetch the next batch while this one computes
             torch.cuda.current_stream().wait_event(ev)
             loss = runner.step(dev_b)
-            if dp is not None:
-                dp.sync_gradients()
             loss_host.copy_(loss.reshape(1), non_blocking=True)
             for t in dev_b:
                 t.record_stream(torch.cuda.current_stream())
@@ -405,8 +402,7 @@ def gpu_arm(args):
         model.zero_grad_fast()
 
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
+        _finish(dist, runner)
         return
 
     # ---- roofline of the dominant kernel (stage-1 backward: dW1 + dX + embedding-row gradients) ----
@@ -452,8 +448,22 @@ def gpu_arm(args):
         "secondary": secondary,
     }
     print(json.dumps(line))
-    if dist is not None:
-        dist.destroy_process_group()
+    _finish(dist, runner)
+
+
+def _finish(dist, runner):
+    """Multi-rank exit: a live CUDA graph that holds captured NCCL kernels makes destroy_process_group() wait
+    forever, so drop the graph, rendezvous once more and leave without NCCL/IPC teardown."""
+    sys.stdout.flush()
+    sys.stderr.flush()
+    if dist is None:
+        return
+    runner.graph.reset()
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    os._exit(0)
 
 
 def main():

@@ -45,11 +45,12 @@ def allreduce_flat_(tensors: Sequence[torch.Tensor], group=None, scale: float = 
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     if scale != 1.0:
         flat.mul_(scale)
-    off = 0
+    views, off = [], 0
     for t in tensors:
         n = t.numel()
-        t.copy_(flat[off:off + n].view_as(t))
+        views.append(flat[off:off + n].view_as(t))
         off += n
+    torch._foreach_copy_(list(tensors), views)       # one multi-tensor kernel instead of one copy per parameter
 
 
 def gather_rows(x: torch.Tensor, group=None) -> torch.Tensor:

@@ -32,12 +32,16 @@ class GraphedTwoTowerStep:
 
     def __init__(self, model: CEOFirmMatcher, example: Sequence[torch.Tensor],
                  optimizer: Optional[torch.optim.Optimizer] = None, warmup: int = 3,
-                 stream: Optional[torch.cuda.Stream] = None, loss_scale: float = 1.0):
+                 stream: Optional[torch.cuda.Stream] = None, loss_scale: float = 1.0,
+                 after_backward=None):
         dev = next(model.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("GraphedTwoTowerStep needs the model on a CUDA device (no CPU fallback)")
         self.model, self.optimizer, self.device = model, optimizer, dev
         self.loss_scale = loss_scale             # data parallelism: 1/world so gradients are those of the global mean
+        # multi-GPU: the gradient synchronisation (e.g. TableShardedTwoTower.sync_gradients) runs right after the
+        # backward INSIDE the captured step, NCCL collectives included, so a step stays one graph launch per rank
+        self.after_backward = after_backward
         self.static = [torch.empty(t.shape, dtype=t.dtype, device=dev) for t in example]
         for s, t in zip(self.static, example):
             s.copy_(t)
@@ -65,6 +69,8 @@ class GraphedTwoTowerStep:
         self.model.zero_grad_fast()
         loss, _ = self.model.forward_loss(*self.static)
         (loss if self.loss_scale == 1.0 else loss * self.loss_scale).backward()
+        if self.after_backward is not None:
+            self.after_backward()
         if self.optimizer is not None:
             self.optimizer.step()
             self.model.rezero_table_grads()      # tables are clean again before any other graph runs
