@@ -199,6 +199,10 @@ class CudaIpcPeers:
                 out.setdefault(k, [None] * self.world)[r] = view
         return out
 
+    def fence(self) -> None:
+        """Called by every rank between the barrier collective and the owners' reads: peer memory is coherent at
+        kernel boundaries, nothing to do (an emulation without shared memory refreshes its copies here)."""
+
     def close(self) -> None:
         from . import _native as N
         for base in self._opened.values():
@@ -354,6 +358,7 @@ class TableShardedTwoTower:
         # one flat all-reduce for the tower parameters; it completes only after every rank has queued it behind its
         # backward, so it is also the barrier after which all peer buffers are complete
         allreduce_flat_([p.grad for p in self.dense] + [self._token], self.group)
+        self.peers.fence()
         self.rezero()                             # rows of the previous step (its sorted keys are still in scratch)
         for g in self.groups:
             self.kernels.peer_reduce(g["owned"], self.world, self.B, g["emb_dim"], g["width"], g["scratch"])

@@ -66,6 +66,99 @@ class TorchScoringBackend:
         return torch.gather(s, 1, order).float(), torch.gather(i, 1, order)
 
 
+class GlooPeers:
+    """Stand-in for CudaIpcPeers on CPU: there is no shared memory, so every rank keeps a copy of each published
+    buffer and ``fence()`` refreshes the copies from their publishers."""
+
+    def share(self, named):
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        metas = [None] * self.world
+        dist.all_gather_object(metas, {k: (tuple(v.shape), v.dtype) for k, v in named.items()})
+        self.views = {}
+        for r in range(self.world):
+            for k, (shape, dtype) in metas[r].items():
+                self.views.setdefault(k, [None] * self.world)[r] = (named[k] if r == self.rank
+                                                                    else torch.zeros(shape, dtype=dtype))
+        self.fence()
+        return self.views
+
+    def fence(self):
+        for k in sorted(self.views):
+            for r, t in enumerate(self.views[k]):
+                if t is not None:
+                    dist.broadcast(t, src=r)
+
+
+class TorchTableOps:
+    """Reference math with the contract of CudaTableOps (the row source is only used by the CUDA forward)."""
+
+    def make_row_source(self, handle, tables, pieces, dx_emb):
+        return ("row-source", len(tables), pieces)
+
+    def make_scratch(self, n_owned, n_peers, B, device):
+        return {"touched": []}
+
+    def peer_reduce(self, owned, n_peers, B, emb_dim, width, scratch):
+        scratch["touched"] = []
+        for o in owned:
+            c0 = o["col0"]
+            for r in range(n_peers):                                   # rank order, then row order
+                idx = o["x_cat"][r][:, o["col"]]
+                rows = o["dx_emb"][r][:, o["col"] * emb_dim + c0:o["col"] * emb_dim + c0 + width]
+                o["grad"][:, c0:c0 + width].index_add_(0, idx, rows)
+                scratch["touched"].append((o, idx.clone()))
+
+    def rezero(self, owned, emb_dim, width, scratch):
+        for o, idx in scratch["touched"]:
+            o["grad"][idx, o["col0"]:o["col0"] + width] = 0.0
+
+
+def _table_sharded_protocol(rank, world):
+    """TableShardedTwoTower bookkeeping end to end with emulated peers: plan, consolidation, dense all-reduce,
+    owner-side reduce over every rank's (index, gradient row) pairs, sparse re-zero on the next step."""
+    from ceo_firm_matching import CEOFirmMatcher, Config
+    from ceo_firm_matching import distributed as D
+    f_cards, c_cards, B = [40, 5, 3, 2], [2, 4, 30, 2, 2, 5, 2], 16
+    meta = {"n_firm_numeric": 12, "firm_cat_counts": f_cards, "n_ceo_numeric": 2, "ceo_cat_counts": c_cards}
+    torch.manual_seed(100 + rank)                                      # replicas start DIFFERENT on purpose
+    model = CEOFirmMatcher(meta, Config())
+    model.use_persistent_table_grads(True)
+    ts = D.TableShardedTwoTower(model, batch_rows=B, peers=GlooPeers(), table_ops=TorchTableOps())
+    hs = model._handles
+    res = {"plan": (ts.pieces, ts.slices, ts.owner)}
+    flat = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+    both = [torch.empty_like(flat) for _ in range(world)]
+    dist.all_gather(both, flat)
+    res["consolidated"] = all(torch.equal(both[0], x) for x in both)    # dense from rank 0, slices from owners
+    expected_steps = []
+    for step in range(2):
+        for p in ts.dense:
+            p.grad = torch.full_like(p, float(rank + 1 + step))
+        gens = [torch.Generator().manual_seed(1000 * step + r) for r in range(world)]
+        data = [[(torch.stack([torch.randint(0, e.num_embeddings, (B,), generator=g) for e in h.embeddings], 1),
+                  torch.randn(B, h.n_tables * h.emb_dim, generator=g)) for h in hs] for g in gens]
+        for t, h in enumerate(hs):
+            h.table_grads.pending = data[rank][t]                       # what the CUDA backward leaves behind
+        ts.sync_gradients()
+        ok = all(torch.equal(p.grad, torch.full_like(p, float(sum(r + 1 + step for r in range(world)))))
+                 for p in ts.dense)
+        for (t, k, c), r in zip(ts.slices, ts.owner):
+            h = hs[t]
+            w = h.emb_dim // ts.pieces[t]
+            exp = torch.zeros(h.embeddings[k].num_embeddings, w)
+            for rr in range(world):
+                x, dx = data[rr][t]
+                exp.index_add_(0, x[:, k], dx[:, k * h.emb_dim + c * w:k * h.emb_dim + (c + 1) * w])
+            got = h.embeddings[k].weight.grad[:, c * w:(c + 1) * w]
+            ok = ok and (torch.equal(got, exp) if r == rank else float(got.abs().sum()) == 0.0)
+        expected_steps.append(ok)
+    res["steps"] = expected_steps
+    owned = {id(p) for p in ts.owned_parameters()}
+    res["owned_ok"] = all((id(hs[t].embeddings[k].weight) in owned) == (r == rank) or ts.pieces[t] > 1
+                          for (t, k, c), r in zip(ts.slices, ts.owner))
+    return res
+
+
 def _worker(rank, world, port, out):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "ceo-recommender_b200"))
@@ -106,6 +199,7 @@ def _worker(rank, world, port, out):
         s, i = D.score_topk_sharded(rows_all[rlo:rhi], cols_all[clo:chi], 7, 3.0, backend=TorchScoringBackend())
         so, io = oracle.allpairs_topk(rows_all[rlo:rhi], cols_all, 7, 3.0)
         res["topk"] = (torch.equal(i, io), (s - so).abs().max().item())
+        res["sharded"] = _table_sharded_protocol(rank, world)
         out[rank] = res
     finally:
         dist.destroy_process_group()
@@ -127,3 +221,22 @@ def test_world2_protocol():
         same_idx, err = r["topk"]
         assert same_idx and err < 1e-5
     assert out[0]["nce"][0] == out[1]["nce"][0]                     # the global loss is identical on every rank
+    for rank in range(world):
+        sh = out[rank]["sharded"]
+        assert sh["plan"] == out[0]["sharded"]["plan"]              # every rank derives the same ownership
+        assert sh["consolidated"] and sh["steps"] == [True, True] and sh["owned_ok"]
+
+
+def test_table_slice_plan_is_balanced():
+    sys.path.insert(0, os.path.join(ROOT, "ceo-recommender_b200"))
+    from ceo_firm_matching.distributed import plan_table_slices
+    towers = [(4, 48), (7, 8)]                                      # BASELINE config 4: 992 B of rows per pair
+    for world in (1, 2, 4, 8):
+        pieces, slices, owner = plan_table_slices(towers, world)
+        load = [0] * world
+        for (t, k, c), r in zip(slices, owner):
+            load[r] += towers[t][1] // pieces[t]
+        assert sum(load) == 4 * 48 + 7 * 8 and len(slices) == 4 * pieces[0] + 7 * pieces[1]
+        assert max(load) <= 1.06 * (sum(load) / world) + 8, (world, pieces, load)
+        assert all((towers[t][1] // pieces[t]) % 4 == 0 for t in range(2))      # rows stay 16-byte vectors
+    assert plan_table_slices(towers, 8)[0] == [2, 1]                # wide firm tables are cut in two at 8 ranks
