@@ -34,8 +34,12 @@ F_CARDS, C_CARDS = [TABLE_ROWS] * 4, [TABLE_ROWS] * 7
 BYTES_PER_PAIR = 2228          # 1148 fwd + 1080 bwd algorithmic bytes, large-table regime
 BYTES_BWD1_PER_PAIR = 1080     # stage-1 backward kernel: re-read indices (88) + emit embedding-grad rows (992)
 METRIC = "two_tower_train_pairs_per_sec"
-WORKLOAD = ("config4: two-tower fwd+loss+bwd, B=65536/GPU, 10M synthetic pairs, 11 tables x 1M rows, "
-            "TF32 tensor-core tower products with fp32 accumulation, everything else fp32")
+WORKLOADS = {
+    "fp32": ("config4: two-tower fwd+loss+bwd, B=65536/GPU, 10M synthetic pairs, 11 tables x 1M rows, fp32 end to end "
+             "(tower products as error-compensated 3xTF32 tensor-core MMAs: fp32-class, parity rtol 2e-5 vs the oracle)"),
+    "tf32": ("config4: two-tower fwd+loss+bwd, B=65536/GPU, 10M synthetic pairs, 11 tables x 1M rows, "
+             "single-pass TF32 tensor-core tower products with fp32 accumulation, everything else fp32"),
+}
 
 
 def peaks():
@@ -65,79 +69,85 @@ def make_batches(n_batches, B, device, seed):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region: an in-process NVML polling thread (2 ms period;
+    the timed region of the default run is ~25 ms, shorter than one `nvidia-smi -lms` tick), nvidia-smi as fallback.
+    `mark()` / `unmark()` bracket the timed region; samples outside it are kept separately."""
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.samples, self.stop, self.timed, self.thread, self.max_mhz = index, [], False, False, None, None
+        self.backend = None
+
+    def _nvml_loop(self, nv, handle):
+        bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown,
+                "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown,
+                "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+        while not self.stop:
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(handle)
+                self.samples.append((self.timed, float(mhz), [k for k, b in bits.items() if mask & b]))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def _smi_loop(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                 "--format=csv,noheader,nounits", "-lms", "50"],
+                                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        self.proc = proc
+        for ln in proc.stdout:
+            f = [x.strip() for x in ln.split(",")]
+            try:
+                self.max_mhz = float(f[1])
+                self.samples.append((self.timed, float(f[0]),
+                                     [n for n, v in zip(names, f[2:6]) if v.lower().startswith("active")]))
+            except Exception:
+                continue
+            if self.stop:
+                break
 
     def __enter__(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
-            self.t.start()
+            import pynvml as nv
+            nv.nvmlInit()
+            try:
+                uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+                handle = nv.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                handle = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM))
+            self.backend = "nvml"
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, handle), daemon=True)
         except Exception:
-            self.proc = None
+            self.backend = "nvidia-smi"
+            self.thread = threading.Thread(target=self._smi_loop, daemon=True)
+        self.thread.start()
         return self
 
+    def mark(self):
+        self.timed = True
+
+    def unmark(self):
+        self.timed = False
+
     def __exit__(self, *a):
-        if self.proc:
-            time.sleep(0.12)
+        self.stop = True
+        if getattr(self, "proc", None) is not None:
             self.proc.terminate()
-            self.t.join(timeout=2)
+        self.thread.join(timeout=2)
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except Exception:
-                continue
-            for n, v in zip(names, f[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
-
-
-# ----------------------------------------------------------------------------------------------
-# CPU arm: the oracle (torch CPU restatement of the reference) on the host cores
-# ----------------------------------------------------------------------------------------------
-def cpu_step_fn():
-    import oracle
-    torch.set_num_threads(os.cpu_count())
-    p = oracle.init_two_tower_params(12, F_CARDS, 2, C_CARDS, seed=0)
-    names = [k for k, v in p.items() if v.is_floating_point() and "running" not in k]
-    for k in names:
-        p[k].requires_grad_(True)
-    gen = torch.Generator().manual_seed(1234)
-    masks_p = 0.1
-
-    def batch():
-        B = B_PER_GPU
-        return (torch.randn(B, 12, generator=gen), torch.randint(0, TABLE_ROWS, (B, 4), generator=gen),
-                torch.randn(B, 2, generator=gen), torch.randint(0, TABLE_ROWS, (B, 7), generator=gen),
-                torch.randn(B, 1, generator=gen), 1.0 / (torch.rand(B, 1, generator=gen) * 0.9 + 0.1) ** 2)
-
-    data = [batch() for _ in range(2)]
-
-    def step(i):
-        f_num, f_cat, c_num, c_cat, target, weights = data[i % len(data)]
-        for k in names:
-            p[k].grad = None
-        B = f_num.shape[0]
-        masks = {s: [torch.rand(B, w, generator=gen) >= masks_p for w in (64, 32)] for s in ("firm", "ceo")}
-        preds = oracle.two_tower_forward(p, f_num, f_cat, c_num, c_cat, training=True, masks=masks)
-        loss = oracle.weighted_mse(preds, target, weights)
-        loss.backward()
-        return float(loss)
-
-    return step
+        timed = [s for s in self.samples if s[0]]
+        use = timed if timed else self.samples            # fallback sampler may tick slower than the timed region
+        sm = [s[1] for s in use]
+        reasons = sorted({r for s in use for r in s[2]})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(sm), "source": self.backend,
+                "window": "timed region" if timed else "step loop around the timed region"}
 
 
 def run_cpu(steps, warmup):
@@ -161,7 +171,7 @@ def reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "timing": "host perf_counter, inputs in host memory"},
+        "config": {"workload": WORKLOADS[args.precision], "timing": "host perf_counter, inputs in host memory"},
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port",
                          "sample": f"{args.steps} steps of one B=65536 batch (fwd+loss+bwd, dense 1M-row table grads), "
                                    "oracle = torch-CPU restatement of the reference"},
@@ -173,7 +183,7 @@ def reference_arm(args):
 # ----------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------
-def build_model(device, precision="tf32"):
+def build_model(device, precision="fp32"):
     from ceo_firm_matching import CEOFirmMatcher, Config
     torch.manual_seed(0)
     meta = {"n_firm_numeric": 12, "firm_cat_counts": F_CARDS, "n_ceo_numeric": 2, "ceo_cat_counts": C_CARDS}
@@ -276,7 +286,7 @@ def gpu_arm(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=device)
     lib = N.lib()
-    model = build_model(device)
+    model = build_model(device, args.precision)
     dp = None
     if world > 1:
         from ceo_firm_matching import distributed as D
@@ -303,17 +313,18 @@ def gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(max(args.warmup, 3)):
-        step(i)
-    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
+        for i in range(max(args.warmup, 3)):
+            step(i)
         barrier()
+        clocks.mark()
         e0.record()
         for i in range(args.steps):
             loss = step(args.warmup + i)
         e1.record()
         barrier()
+        clocks.unmark()
     ms_total = e0.elapsed_time(e1)
 
     # Per-kernel durations: a graph replay hides the individual launches from host-side events, so the same
@@ -383,22 +394,24 @@ def gpu_arm(args):
 
     secondary = secondary_metrics(device, world, rank, dist)
     if world == 1:
-        # the same step with fp32-class tower products (3xTF32 error-compensated): the parity-default precision
-        model.set_precision("fp32")
-        with torch.cuda.stream(runner.stream):
-            for i in range(3):
-                eager_step(model, None, batches[i % n_data])
-            torch.cuda.synchronize()
-            t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
-            t0.record()
-            for i in range(10):
-                eager_step(model, None, batches[i % n_data])
-            t1.record()
-            torch.cuda.synchronize()
-        ms32 = t0.elapsed_time(t1) / 10
-        secondary["two_tower_fp32_class"] = {"workload": "same step, tower products 3xTF32 (fp32-class, rtol 2e-5 vs oracle), eager launches",
-                                             "ms_per_step": ms32, "value": B_PER_GPU / (ms32 * 1e-3), "unit": "pairs/s"}
-        model.set_precision("tf32")
+        # the same step in the other tower-product precision, also as one graph replay per step
+        other = "tf32" if args.precision == "fp32" else "fp32"
+        model.set_precision(other)
+        model.zero_grad_fast()
+        runner2 = GraphedTwoTowerStep(model, batches[0], optimizer=None, warmup=3, stream=runner.stream)
+        for i in range(3):
+            runner2.step(batches[i % n_data])
+        torch.cuda.synchronize()
+        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for i in range(args.steps):
+            runner2.step(batches[i % n_data])
+        t1.record()
+        torch.cuda.synchronize()
+        ms_o = t0.elapsed_time(t1) / args.steps
+        secondary["two_tower_" + other] = {"workload": WORKLOADS[other], "ms_per_step": ms_o,
+                                           "value": B_PER_GPU / (ms_o * 1e-3), "unit": "pairs/s"}
+        model.set_precision(args.precision)
         model.zero_grad_fast()
 
     if rank != 0:
@@ -431,8 +444,8 @@ def gpu_arm(args):
     line = {
         "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "global_batch": world * B_PER_GPU,
+        "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "tf32", "data": "synthetic",
+        "config": {"workload": WORKLOADS[args.precision], "global_batch": world * B_PER_GPU,
                    "parallelism": ("single" if world == 1 else
                                    f"dp{world} towers + tables {args.tables}" +
                                    (" over NVLink peer memory" if args.tables == "sharded" else " (all-gather)")),
@@ -473,6 +486,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (debugging)")
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32"],
+                    help="tower products: fp32-class (3xTF32, the reference's precision; default) or single-pass TF32")
     ap.add_argument("--tables", default="sharded", choices=["sharded", "replicated"],
                     help="multi-GPU embedding tables: sharded over NVLink peer memory, or replicated + all-gather")
     args = ap.parse_args()

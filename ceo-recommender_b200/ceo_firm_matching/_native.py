@@ -52,6 +52,14 @@ class TowerGrads(C.Structure):
     ]
 
 
+class EmbGroup(C.Structure):
+    """Mirror of ``cfm_emb_group_t`` (one tower's tables in the joint embedding-gradient reduce)."""
+    _fields_ = [
+        ("x_cat", C.c_void_p), ("dx_emb", C.c_void_p), ("n_tables", i64), ("emb_dim", i64),
+        ("grad_tables", C.c_void_p * CFM_MAX_TABLES), ("table_rows", i64 * CFM_MAX_TABLES),
+    ]
+
+
 class PeerTable(C.Structure):
     """Mirror of ``cfm_peer_table_t`` (one owned table of the NVLink table-sharded mode)."""
     _fields_ = [
@@ -78,6 +86,8 @@ PROTOTYPES = {
     "cfm_emb_grad_segment_reduce": (C.c_int, [_V, _V, _I, _I, _I, C.POINTER(C.c_void_p), C.POINTER(i64),
                                               _V, _V, _V, _V, _V, _I, _V]),
     "cfm_emb_grad_rezero": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(i64), _I, _I, _V, _I, _V]),
+    "cfm_emb_grad_joint_reduce": (C.c_int, [C.POINTER(EmbGroup), _I, _I, _V, _V, _V, _V, _V, _I, _V]),
+    "cfm_emb_grad_joint_rezero": (C.c_int, [C.POINTER(EmbGroup), _I, _I, _V, _V]),
     "cfm_enable_peer_access": (C.c_int, [_I]),
     "cfm_ipc_export": (C.c_int, [_V, C.c_char_p, C.POINTER(i64)]),
     "cfm_ipc_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),

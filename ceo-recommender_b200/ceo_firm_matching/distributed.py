@@ -460,12 +460,24 @@ class CudaScoringBackend:
 
 
 def score_topk_sharded(rows_local: torch.Tensor, cols_local: torch.Tensor, k: int, scale: float = 1.0, group=None,
-                       backend=None) -> Tuple[torch.Tensor, torch.Tensor]:
-    """Top-``k`` columns (global indices) for this rank's rows when BOTH sides are row-sharded across ranks:
-    column shards are all-gathered (ragged shards allowed), each is scored separately with its global offset, and
-    the ``world`` partial lists are k-way merged — the cross-GPU merge of BASELINE config 5."""
+                       backend=None, merge: str = "fused") -> Tuple[torch.Tensor, torch.Tensor]:
+    """Top-``k`` columns (global indices) for this rank's rows when BOTH sides are row-sharded across ranks
+    (BASELINE config 5).  The column shards are all-gathered (ragged shards allowed; 128 MB at 1M x 64 bf16) and
+
+    * ``merge="fused"``  – the rank's rows are scored against the concatenated columns in ONE pass: the kernel's own
+      candidate lists do the cross-shard merge, and the per-row selection / fp64 rescoring runs once;
+    * ``merge="shards"`` – every shard is scored separately with its global column offset and the ``world`` partial
+      lists go through the exact k-way merge (``cfm_topk_merge``, fp64 scores) — the form to use when the column
+      side does not fit one GPU or arrives shard by shard.
+
+    Both return the same lists (tests pin them against each other and the oracle)."""
     backend = backend or CudaScoringBackend()
     cols_all, counts = gather_ragged_rows(cols_local.contiguous(), group)
+    if merge == "fused":
+        s, i = backend.topk(rows_local, cols_all, k, scale, 0)
+        return s.float(), i
+    if merge != "shards":
+        raise ValueError("merge must be 'fused' or 'shards'")
     parts_s, parts_i = [], []
     off = 0
     for c in counts:
@@ -475,5 +487,5 @@ def score_topk_sharded(rows_local: torch.Tensor, cols_local: torch.Tensor, k: in
             parts_i.append(i)
         off += c
     if len(parts_s) == 1:
-        return parts_s[0], parts_i[0]
+        return parts_s[0].float(), parts_i[0]
     return backend.merge(torch.stack(parts_s), torch.stack(parts_i))

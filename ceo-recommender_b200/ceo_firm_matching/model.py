@@ -77,6 +77,8 @@ class CEOFirmMatcher(nn.Module):
         previous step (exactly the dense gradient torch would produce, without a full-table memset)."""
         for h in self._handles:
             h.table_grads = ops.PersistentTableGrads(h) if enable else None
+        if enable:
+            ops.JointTableGrads(self._handles)   # both towers' gradients go through one radix sort per step
 
     def rezero_table_grads(self) -> None:
         """Zero the table-gradient rows written by the last backward (call after ``optimizer.step()``)."""

@@ -261,9 +261,15 @@ class TowersFunction(torch.autograd.Function):
             out: List[Optional[torch.Tensor]] = []
             for i, (c, d) in enumerate(zip(calls, per_tower)):
                 out += [d["dx_num"], None]
+            joint = _joint_for(calls)
+            if joint is not None:                     # one sort for all towers, straight into the persistent grads
+                joint.reduce([(c.x_cat, d["dx_emb"]) for c, d in zip(calls, per_tower)], B)
             for c, d in zip(calls, per_tower):
                 h, t = c.h, c.struct
-                table_grads = embedding_grads(h, c.x_cat, d["dx_emb"], B) if t.n_tables else []
+                if joint is not None:
+                    table_grads = [None] * t.n_tables
+                else:
+                    table_grads = embedding_grads(h, c.x_cat, d["dx_emb"], B) if t.n_tables else []
                 out += table_grads
                 out += [d["dw1"], d["db1"], d["dbn1_w"], d["dbn1_b"], d["dw2"], d["db2"]]
                 if t.bn2:
@@ -359,6 +365,7 @@ class PersistentTableGrads:
         self.defer = False                       # data parallelism: keep (indices, rows) for the cross-rank reduce
         self.pending = None
         self.rezero_hook = None                  # table-sharded mode: the owner re-zeroes its tables itself
+        self.joint: Optional["JointTableGrads"] = None   # set when all towers of a model reduce in one sort
         for e in handle.embeddings:
             e.weight.grad = torch.zeros_like(e.weight)
 
@@ -371,6 +378,8 @@ class PersistentTableGrads:
         if self.rezero_hook is not None:
             self.rezero_hook()
             return
+        if self.joint is not None:
+            self.joint.rezero()                  # idempotent: the first tower's call does the work
         if self.prev is None:
             return
         h = self.h
@@ -379,6 +388,69 @@ class PersistentTableGrads:
         N.check(N.lib().cfm_emb_grad_rezero(ptrs, rows, h.n_tables, h.emb_dim, N.ptr(self.prev.keys_sorted),
                                             self.prev.n_items, N.stream_ptr()))
         self.prev = None
+
+
+class JointTableGrads:
+    """All towers of one model reduce their embedding gradients with ONE radix sort per step
+    (``cfm_emb_grad_joint_reduce``): at these sizes the sort passes are latency-bound, so one sort over both towers'
+    (table, index) pairs costs about half of two.  Results are bitwise those of the per-tower reduce."""
+
+    def __init__(self, handles: Sequence[TowerHandle]):
+        self.handles = [h for h in handles if h.n_tables]
+        self.total_tables = sum(h.n_tables for h in self.handles)
+        self.scratches = {}
+        self.prev = None                          # (scratch, B) of the last reduce, until re-zeroed
+        for h in self.handles:
+            h.table_grads.joint = self
+
+    def usable(self) -> bool:
+        return (self.total_tables <= N.CFM_MAX_TABLES and
+                all(h.table_grads is not None and h.table_grads.joint is self and not h.table_grads.defer and
+                    h.table_grads.rezero_hook is None for h in self.handles))
+
+    def _groups(self, inputs):
+        arr = (N.EmbGroup * len(self.handles))()
+        for g, h in enumerate(self.handles):
+            if inputs is not None:
+                arr[g].x_cat, arr[g].dx_emb = N.ptr(inputs[g][0]), N.ptr(inputs[g][1])
+            arr[g].n_tables, arr[g].emb_dim = h.n_tables, h.emb_dim
+            for i, e in enumerate(h.embeddings):
+                arr[g].grad_tables[i] = N.ptr(e.weight.grad)
+                arr[g].table_rows[i] = e.num_embeddings
+        return arr
+
+    def reduce(self, inputs, B: int) -> None:
+        if self.prev is not None:
+            raise RuntimeError("persistent table grads: backward ran twice without zero_grad_fast() in between")
+        dev = inputs[0][1].device
+        if B not in self.scratches:
+            self.scratches[B] = _SortScratch(B * self.total_tables, self.total_tables, B, dev)
+        sc = self.scratches[B]
+        N.check(N.lib().cfm_emb_grad_joint_reduce(self._groups(inputs), len(self.handles), B, N.ptr(sc.keys_tmp),
+                                                  N.ptr(sc.vals_tmp), N.ptr(sc.keys_sorted), N.ptr(sc.vals_sorted),
+                                                  N.ptr(sc.tmp), sc.tmp_bytes, N.stream_ptr()))
+        self.prev = (sc, B)
+
+    def rezero(self) -> None:
+        if self.prev is None:
+            return
+        sc, B = self.prev
+        N.check(N.lib().cfm_emb_grad_joint_rezero(self._groups(None), len(self.handles), B, N.ptr(sc.keys_sorted),
+                                                  N.stream_ptr()))
+        self.prev = None
+
+
+def _joint_for(calls) -> Optional[JointTableGrads]:
+    """The joint reducer when every tower of this call belongs to it and nothing defers the reduce."""
+    pgs = [c.h.table_grads for c in calls if c.h.n_tables]
+    if len(pgs) < 2 or any(pg is None or pg.joint is None for pg in pgs):
+        return None
+    joint = pgs[0].joint
+    if any(pg.joint is not joint for pg in pgs) or len(joint.handles) != len(pgs) or not joint.usable():
+        return None
+    if any(a is not b for a, b in zip(joint.handles, [c.h for c in calls if c.h.n_tables])):
+        return None
+    return joint
 
 
 def _segment_reduce(h: TowerHandle, x_cat: torch.Tensor, dx_emb: torch.Tensor, B: int,

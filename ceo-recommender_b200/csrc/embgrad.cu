@@ -462,3 +462,189 @@ extern "C" int cfm_ipc_close(void* base) {
     CFM_CHECK_CUDA(cudaIpcCloseMemHandle(base));
     return CFM_OK;
 }
+
+// =============================================================================================
+// Joint reduce for the towers of one step: ONE key build and ONE radix sort over the (table, index) pairs of every
+// tower (the sort passes are latency-bound at these sizes, so two half-size sorts cost almost twice one), then one
+// segment-reduce launch per tower on its contiguous key range (tables are numbered tower-major, so after the sort
+// tower g owns positions [B * sum_{h<g} K_h, B * sum_{h<=g} K_h)).
+// =============================================================================================
+namespace cfm {
+
+struct JointKeys {
+    const long long* x_cat[CFM_MAX_GROUPS];
+    int n_tab[CFM_MAX_GROUPS];
+    int t0[CFM_MAX_GROUPS];                 // first global table id of the group
+    long long rows[CFM_MAX_TABLES];         // by global table id
+    int n_groups;
+};
+
+__global__ void emb_make_keys_joint(JointKeys jk, long long B, int idx_bits, unsigned long long* __restrict__ keys,
+                                    int* __restrict__ vals) {
+    for (int g = 0; g < jk.n_groups; ++g) {
+        const int K = jk.n_tab[g], t0 = jk.t0[g];
+        const long long n = B * K;
+        const long long* __restrict__ x = jk.x_cat[g];
+        for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+            const long long r = i / K;
+            const int t = (int)(i - r * K);
+            long long idx = x[i];
+            if (idx < 0 || idx >= jk.rows[t0 + t]) idx = 0;   // forward already flagged the error
+            keys[(long long)(t0 + t) * B + r] = ((unsigned long long)(t0 + t) << idx_bits) | (unsigned long long)idx;
+            vals[(long long)(t0 + t) * B + r] = (int)r;
+        }
+    }
+}
+
+// thread (p, q): if sorted position p starts a run, sum float4 slice q of every row in the run (t0: first table id)
+template <int VEC>
+__global__ void emb_segment_reduce_range(const unsigned long long* __restrict__ keys, const int* __restrict__ vals,
+                                         long long n, int n_tab, int E, int idx_bits, int t0,
+                                         const float* __restrict__ dx, TablePtrs tp) {
+    const int EV = E / VEC;
+    const long long total = n * EV;
+    const int KE = n_tab * E;
+    const unsigned long long mask = (1ull << idx_bits) - 1;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long p = i / EV;
+        const int q = (int)(i - p * EV);
+        const unsigned long long key = keys[p];
+        if (p > 0 && keys[p - 1] == key) continue;
+        const int t = (int)(key >> idx_bits) - t0;
+        const long long idx = (long long)(key & mask);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (long long s = p; s < n && keys[s] == key; ++s) {
+            const float* src = dx + (size_t)vals[s] * KE + t * E + q * VEC;
+            if (VEC == 4) {
+                const float4 g = __ldg(reinterpret_cast<const float4*>(src));
+                acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
+            } else {
+                acc.x += __ldg(src);
+            }
+        }
+        float* dst = tp.p[t] + (size_t)idx * E + q * VEC;
+        if (VEC == 4) *reinterpret_cast<float4*>(dst) = acc;
+        else *dst = acc.x;
+    }
+}
+
+template <int VEC>
+__global__ void emb_rezero_range(const unsigned long long* __restrict__ keys, long long n, int E, int idx_bits, int t0,
+                                 TablePtrs tp) {
+    const int EV = E / VEC;
+    const long long total = n * EV;
+    const unsigned long long mask = (1ull << idx_bits) - 1;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long p = i / EV;
+        const int q = (int)(i - p * EV);
+        const unsigned long long key = keys[p];
+        if (p > 0 && keys[p - 1] == key) continue;
+        float* dst = tp.p[(int)(key >> idx_bits) - t0] + (size_t)(key & mask) * E + q * VEC;
+        if (VEC == 4) *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+        else *dst = 0.f;
+    }
+}
+
+// validates the groups; fills per-group table pointers, the joint key plan and the key widths
+static int joint_plan(const cfm_emb_group_t* groups, int64_t n_groups, bool need_inputs, JointKeys& jk,
+                      TablePtrs (&tps)[CFM_MAX_GROUPS], int* idx_bits, int* key_bits, long long* total_tables) {
+    CFM_REQUIRE(groups && n_groups >= 1 && n_groups <= CFM_MAX_GROUPS, CFM_ERR_INVALID, "n_groups outside [1,%d]",
+                CFM_MAX_GROUPS);
+    long long tt = 0, max_rows = 1;
+    jk.n_groups = (int)n_groups;
+    for (int g = 0; g < CFM_MAX_GROUPS; ++g) { jk.x_cat[g] = nullptr; jk.n_tab[g] = 0; jk.t0[g] = 0; }
+    for (int i = 0; i < CFM_MAX_TABLES; ++i) jk.rows[i] = 0;
+    for (int g = 0; g < n_groups; ++g) {
+        const cfm_emb_group_t& G = groups[g];
+        CFM_REQUIRE(G.n_tables >= 1 && G.emb_dim >= 1 && tt + G.n_tables <= CFM_MAX_TABLES, CFM_ERR_INVALID,
+                    "group %d: bad table count / more than %d tables in total", g, CFM_MAX_TABLES);
+        CFM_REQUIRE(!need_inputs || (G.x_cat && G.dx_emb), CFM_ERR_INVALID, "group %d: null input", g);
+        jk.x_cat[g] = (const long long*)G.x_cat; jk.n_tab[g] = (int)G.n_tables; jk.t0[g] = (int)tt;
+        for (int i = 0; i < CFM_MAX_TABLES; ++i) {
+            tps[g].p[i] = i < G.n_tables ? G.grad_tables[i] : nullptr;
+            tps[g].rows[i] = i < G.n_tables ? G.table_rows[i] : 0;
+            if (i < G.n_tables) {
+                CFM_REQUIRE(G.grad_tables[i] && G.table_rows[i] >= 1, CFM_ERR_INVALID, "group %d: bad table %d", g, i);
+                jk.rows[tt + i] = G.table_rows[i];
+                max_rows = std::max<long long>(max_rows, G.table_rows[i]);
+            }
+        }
+        tt += G.n_tables;
+    }
+    *idx_bits = bits_for(max_rows);
+    *key_bits = *idx_bits + bits_for(tt);
+    *total_tables = tt;
+    CFM_REQUIRE(*key_bits <= 62, CFM_ERR_UNSUPPORTED, "tables too large for the 64-bit sort key");
+    return CFM_OK;
+}
+
+}  // namespace cfm
+
+extern "C" int cfm_emb_grad_joint_reduce(const cfm_emb_group_t* groups, int64_t n_groups, int64_t B, int64_t* keys_tmp,
+                                         int32_t* vals_tmp, int64_t* keys_sorted, int32_t* vals_sorted, void* sort_tmp,
+                                         int64_t sort_tmp_bytes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CFM_REQUIRE(keys_tmp && vals_tmp && keys_sorted && vals_sorted && sort_tmp, CFM_ERR_INVALID, "null pointer");
+    JointKeys jk;
+    TablePtrs tps[CFM_MAX_GROUPS];
+    int idx_bits, key_bits;
+    long long tt;
+    int rc = joint_plan(groups, n_groups, true, jk, tps, &idx_bits, &key_bits, &tt);
+    if (rc) return rc;
+    CFM_REQUIRE(B >= 1 && tt * B < (1ll << 31), CFM_ERR_INVALID, "bad sizes");
+    const long long n = tt * B;
+    ProfScope prof(PROF_EMB, stream);
+    emb_make_keys_joint<<<(int)std::min<long long>((n + 255) / 256, 148 * 8), 256, 0, stream>>>(
+        jk, B, idx_bits, (unsigned long long*)keys_tmp, vals_tmp);
+    CFM_LAUNCH_CHECK();
+    size_t bytes = (size_t)sort_tmp_bytes;
+    CFM_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(sort_tmp, bytes, (const unsigned long long*)keys_tmp,
+                                                   (unsigned long long*)keys_sorted, (const int*)vals_tmp,
+                                                   vals_sorted, (int)n, 0, key_bits, stream));
+    for (int g = 0; g < n_groups; ++g) {
+        const cfm_emb_group_t& G = groups[g];
+        const long long off = (long long)jk.t0[g] * B, ng = G.n_tables * B;
+        const unsigned long long* ks = (const unsigned long long*)keys_sorted + off;
+        if ((G.emb_dim & 3) == 0) {
+            const long long total = ng * (G.emb_dim / 4);
+            emb_segment_reduce_range<4><<<(int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, stream>>>(
+                ks, vals_sorted + off, ng, (int)G.n_tables, (int)G.emb_dim, idx_bits, jk.t0[g], G.dx_emb, tps[g]);
+        } else {
+            const long long total = ng * G.emb_dim;
+            emb_segment_reduce_range<1><<<(int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, stream>>>(
+                ks, vals_sorted + off, ng, (int)G.n_tables, (int)G.emb_dim, idx_bits, jk.t0[g], G.dx_emb, tps[g]);
+        }
+        CFM_LAUNCH_CHECK();
+    }
+    return CFM_OK;
+}
+
+extern "C" int cfm_emb_grad_joint_rezero(const cfm_emb_group_t* groups, int64_t n_groups, int64_t B,
+                                         const int64_t* keys_sorted, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CFM_REQUIRE(keys_sorted, CFM_ERR_INVALID, "null pointer");
+    JointKeys jk;
+    TablePtrs tps[CFM_MAX_GROUPS];
+    int idx_bits, key_bits;
+    long long tt;
+    int rc = joint_plan(groups, n_groups, false, jk, tps, &idx_bits, &key_bits, &tt);
+    if (rc) return rc;
+    CFM_REQUIRE(B >= 1, CFM_ERR_INVALID, "bad sizes");
+    ProfScope prof(PROF_EMB, stream);
+    for (int g = 0; g < n_groups; ++g) {
+        const cfm_emb_group_t& G = groups[g];
+        const long long off = (long long)jk.t0[g] * B, ng = G.n_tables * B;
+        const unsigned long long* ks = (const unsigned long long*)keys_sorted + off;
+        if ((G.emb_dim & 3) == 0) {
+            const long long total = ng * (G.emb_dim / 4);
+            emb_rezero_range<4><<<(int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, stream>>>(
+                ks, ng, (int)G.emb_dim, idx_bits, jk.t0[g], tps[g]);
+        } else {
+            const long long total = ng * G.emb_dim;
+            emb_rezero_range<1><<<(int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, stream>>>(
+                ks, ng, (int)G.emb_dim, idx_bits, jk.t0[g], tps[g]);
+        }
+        CFM_LAUNCH_CHECK();
+    }
+    return CFM_OK;
+}

@@ -134,6 +134,26 @@ int cfm_emb_grad_segment_reduce(const int64_t* x_cat, const float* dx_emb, int64
 int cfm_emb_grad_rezero(float* const* grad_tables /* host */, const int64_t* table_rows /* host */, int64_t n_tables,
                         int64_t emb_dim, const int64_t* keys_sorted, int64_t n_items, void* stream);
 
+/* Joint form for the towers of one step (same batch): ONE key build and ONE radix sort over the (table, index)
+ * pairs of every tower, then one segment-reduce launch per tower on its contiguous range of the sorted keys.
+ * Same result, bit for bit, as one cfm_emb_grad_segment_reduce per tower; scratch sized for
+ * n_items = B * (total tables) (cfm_emb_grad_tmp_bytes(total tables, B)).  cfm_emb_grad_joint_rezero zeroes the rows
+ * named by keys_sorted of the previous joint reduce (x_cat / dx_emb of the groups are ignored). */
+#define CFM_MAX_GROUPS 4
+typedef struct cfm_emb_group {
+    const int64_t* x_cat;                    /* [B, n_tables] */
+    const float* dx_emb;                     /* [B, n_tables*emb_dim] */
+    int64_t n_tables;
+    int64_t emb_dim;
+    float* grad_tables[CFM_MAX_TABLES];      /* [rows_i, emb_dim] dense gradients */
+    int64_t table_rows[CFM_MAX_TABLES];
+} cfm_emb_group_t;
+int cfm_emb_grad_joint_reduce(const cfm_emb_group_t* groups /* host */, int64_t n_groups, int64_t B, int64_t* keys_tmp,
+                              int32_t* vals_tmp, int64_t* keys_sorted, int32_t* vals_sorted, void* sort_tmp,
+                              int64_t sort_tmp_bytes, void* stream);
+int cfm_emb_grad_joint_rezero(const cfm_emb_group_t* groups /* host */, int64_t n_groups, int64_t B,
+                              const int64_t* keys_sorted, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Table-sharded embeddings over NVLink peer memory (one process per GPU, single node; the reference has no
  * multi-GPU code - SURVEY 8e).  Each table - or each of `pieces` equal column slices of it - is owned by one rank;

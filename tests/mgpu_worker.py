@@ -136,10 +136,11 @@ def main():
     cols_all = F.normalize(torch.randn(30001, 60, generator=gen), dim=1)       # ragged column shards
     rlo, rhi = D.shard_bounds(2000, world, rank)
     clo, chi = D.shard_bounds(30001, world, rank)
-    s, i = D.score_topk_sharded(rows_all[rlo:rhi].to(dev), cols_all[clo:chi].to(dev), 100, 14.2857)
     so, io = oracle.allpairs_topk(rows_all[rlo:rhi], cols_all, 100, 14.2857)
-    np.testing.assert_array_equal(i.cpu().numpy(), io.numpy())
-    assert_close_scaled(s, so, 2e-6, "sharded scores")
+    for how in ("fused", "shards"):
+        s, i = D.score_topk_sharded(rows_all[rlo:rhi].to(dev), cols_all[clo:chi].to(dev), 100, 14.2857, merge=how)
+        np.testing.assert_array_equal(i.cpu().numpy(), io.numpy())
+        assert_close_scaled(s, so, 2e-6, f"sharded scores ({how})")
 
     dist.barrier()
     if rank == 0:

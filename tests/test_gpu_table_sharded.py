@@ -122,3 +122,26 @@ def test_peer_reduce_equals_segment_reduce_of_concatenated_batch(n_peers, pieces
             assert torch.equal(o["grad"], exp), (hi, o["col"], o["col0"])
         kernels.rezero(owned, h.emb_dim, w, scratch)
         assert all(float(o["grad"].abs().sum()) == 0.0 for o in owned)
+
+
+def test_joint_reduce_is_bitwise_the_per_tower_reduce():
+    """model.use_persistent_table_grads(True) sends both towers' (table, index) pairs through ONE radix sort
+    (cfm_emb_grad_joint_reduce); the dense table gradients must equal the per-tower autograd path bit for bit,
+    also on a second step with other indices (sparse re-zero of the rows the first step touched)."""
+    ma, mb = _model(), _model()
+    for m in (ma, mb):
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.Dropout):
+                mod.p = 0.0
+    ma.use_persistent_table_grads(True)
+    assert ma._handles[0].table_grads.joint is ma._handles[1].table_grads.joint is not None
+    for seed, B in ((6, 300), (7, 300), (8, 77)):
+        batch = _batch(B, seed)
+        ma.zero_grad_fast()
+        mb.zero_grad(set_to_none=True)
+        la, _ = ma.forward_loss(*batch)
+        la.backward()
+        lb, _ = mb.forward_loss(*batch)
+        lb.backward()
+        for (ka, pa), (kb, pb) in zip(ma.named_parameters(), mb.named_parameters()):
+            assert ka == kb and torch.equal(pa.grad, pb.grad), ka
