@@ -303,7 +303,8 @@ def gpu_arm(args):
     # multi-GPU: the gradient synchronisation (NCCL all-reduce + the owners' peer reduce) is captured with the step
     runner = GraphedTwoTowerStep(model, batches[0], optimizer=None, warmup=3,
                                  loss_scale=dp.loss_scale if dp is not None else 1.0,
-                                 after_backward=dp.sync_gradients if dp is not None else None)
+                                 after_backward=dp.sync_gradients if dp is not None else None,
+                                 before_forward=getattr(dp, "begin_step", None))
 
     def step(i):
         return runner.step(batches[i % n_data])      # D2D copy into the graph's static inputs + replay

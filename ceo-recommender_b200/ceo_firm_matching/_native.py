@@ -68,6 +68,11 @@ class PeerTable(C.Structure):
     ]
 
 
+class PeerGroup(C.Structure):
+    """Mirror of ``cfm_peer_group_t``."""
+    _fields_ = [("owned", C.POINTER(PeerTable)), ("n_owned", i64), ("emb_dim", i64), ("width", i64)]
+
+
 # name -> (restype, argtypes); every symbol include/cfm_b200.h declares
 _V, _I, _D, _U64 = C.c_void_p, i64, C.c_double, C.c_uint64
 PROTOTYPES = {
@@ -93,8 +98,8 @@ PROTOTYPES = {
     "cfm_ipc_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
     "cfm_ipc_close": (C.c_int, [_V]),
     "cfm_emb_gather_rows": (C.c_int, [_V, _I, _I, _I, _I, C.POINTER(C.c_void_p), C.POINTER(i64), _V, _V, _V]),
-    "cfm_emb_grad_peer_reduce": (C.c_int, [C.POINTER(PeerTable), _I, _I, _I, _I, _I, _V, _V, _V, _V, _V, _I, _V]),
-    "cfm_emb_grad_peer_rezero": (C.c_int, [C.POINTER(PeerTable), _I, _I, _I, _V, _I, _V]),
+    "cfm_emb_grad_peer_reduce": (C.c_int, [C.POINTER(PeerGroup), _I, _I, _I, _I, _V, _V, _V, _V, _V, _I, _V]),
+    "cfm_emb_grad_peer_rezero": (C.c_int, [C.POINTER(PeerGroup), _I, _I, _I, _V, _V]),
     "cfm_cosine_head_fwd": (C.c_int, [_V, _V, _V, _I, _I, _D, _V, _V, _V, _V, _V, _V, _V, _V]),
     "cfm_cosine_head_bwd": (C.c_int, [_V, _V, _V, _V, _V, _V, _V, _V, _V, _I, _I, _D, _V, _V, _V, _V, _V]),
     "cfm_structural_head": (C.c_int, [_V, _V, _V, _V, _V, _V, _I, _D, _V, _V, _V, _V, _V, _V]),

@@ -222,28 +222,43 @@ class CudaTableOps:
         return ops._SortScratch(n_owned * n_peers * B, n_owned * n_peers, B, device)
 
     @staticmethod
-    def _array(owned, n_peers):
+    def _groups(groups, n_peers):
         from . import _native as N
-        arr = (N.PeerTable * len(owned))()
-        for j, o in enumerate(owned):
-            arr[j].n_cols, arr[j].col, arr[j].col0 = o["n_cols"], o["col"], o["col0"]
-            arr[j].rows, arr[j].grad = o["grad"].shape[0], N.ptr(o["grad"])
-            for r in range(n_peers):
-                arr[j].x_cat[r] = N.ptr(o["x_cat"][r])
-                arr[j].dx_emb[r] = N.ptr(o["dx_emb"][r])
-        return arr
+        keep = []                                    # ctypes arrays referenced by pointer must outlive the call
+        arr = (N.PeerGroup * len(groups))()
+        for g, grp in enumerate(groups):
+            owned = (N.PeerTable * len(grp["owned"]))()
+            for j, o in enumerate(grp["owned"]):
+                owned[j].n_cols, owned[j].col, owned[j].col0 = o["n_cols"], o["col"], o["col0"]
+                owned[j].rows, owned[j].grad = o["grad"].shape[0], N.ptr(o["grad"])
+                for r in range(n_peers):
+                    owned[j].x_cat[r] = N.ptr(o["x_cat"][r])
+                    owned[j].dx_emb[r] = N.ptr(o["dx_emb"][r])
+            keep.append(owned)
+            arr[g].owned, arr[g].n_owned = owned, len(grp["owned"])
+            arr[g].emb_dim, arr[g].width = grp["emb_dim"], grp["width"]
+        return arr, keep
 
-    def peer_reduce(self, owned, n_peers, B, emb_dim, width, scratch):
+    def peer_reduce(self, groups, n_peers, B, scratch, phase=0):
+        """phase 0: keys + sort + reduce; 1: keys + sort (needs only the peers' indices); 2: reduce."""
         from . import _native as N
+        arr, keep = self._groups(groups, n_peers)
         N.check(N.lib().cfm_emb_grad_peer_reduce(
-            self._array(owned, n_peers), len(owned), n_peers, B, emb_dim, width, N.ptr(scratch.keys_tmp),
-            N.ptr(scratch.vals_tmp), N.ptr(scratch.keys_sorted), N.ptr(scratch.vals_sorted), N.ptr(scratch.tmp),
-            scratch.tmp_bytes, N.stream_ptr()))
+            arr, len(groups), n_peers, B, phase, N.ptr(scratch.keys_tmp), N.ptr(scratch.vals_tmp),
+            N.ptr(scratch.keys_sorted), N.ptr(scratch.vals_sorted), N.ptr(scratch.tmp), scratch.tmp_bytes,
+            N.stream_ptr()))
+        del keep
 
-    def rezero(self, owned, emb_dim, width, scratch):
+    def rezero(self, groups, n_peers, B, scratch):
         from . import _native as N
-        N.check(N.lib().cfm_emb_grad_peer_rezero(self._array(owned, 0), len(owned), emb_dim, width,
-                                                 N.ptr(scratch.keys_sorted), scratch.n_items, N.stream_ptr()))
+        arr, keep = self._groups(groups, 0)
+        N.check(N.lib().cfm_emb_grad_peer_rezero(arr, len(groups), n_peers, B, N.ptr(scratch.keys_sorted),
+                                                 N.stream_ptr()))
+        del keep
+
+    def side_stream(self, device):
+        # high priority: the short sort kernels slot in between the CTAs of the long tower kernels
+        return torch.cuda.Stream(device, priority=-1)
 
 
 class TableShardedTwoTower:
@@ -310,7 +325,7 @@ class TableShardedTwoTower:
             tables = [self.views[f"table{t}.{k}"][owner_of[(t, k, c)]]
                       for k in range(h.n_tables) for c in range(self.pieces[t])]
             h.row_source = self.kernels.make_row_source(h, tables, self.pieces[t], self.dx_shared[t])
-        # owned slices grouped by tower (one reduce per embedding width)
+        # owned slices grouped by tower (one embedding width per group); ONE sort covers all groups
         self.groups = []
         for t, h in enumerate(handles):
             width = h.emb_dim // self.pieces[t]
@@ -318,8 +333,12 @@ class TableShardedTwoTower:
                           x_cat=self.views[f"x{t}"], dx_emb=self.views[f"dx{t}"])
                      for (tt, k, c), r in zip(self.slices, self.owner) if tt == t and r == self.rank]
             if owned:
-                self.groups.append(dict(owned=owned, emb_dim=h.emb_dim, width=width, dirty=False,
-                                        scratch=self.kernels.make_scratch(len(owned), self.world, self.B, dev)))
+                self.groups.append(dict(owned=owned, emb_dim=h.emb_dim, width=width))
+        n_owned = sum(len(g["owned"]) for g in self.groups)
+        self.scratch = self.kernels.make_scratch(n_owned, self.world, self.B, dev) if n_owned else None
+        self._dirty = False          # owned gradient rows written by the last reduce, not yet re-zeroed
+        self._presorted = False      # begin_step() already built and sorted this step's keys
+        self._side = self.kernels.side_stream(dev) if dev.type == "cuda" else None
         self._token = torch.zeros(1, device=dev)
         dist.barrier(group=group)
 
@@ -344,41 +363,75 @@ class TableShardedTwoTower:
             w[:, c * width:(c + 1) * width] = part
 
     # ---- per-step protocol --------------------------------------------------------------
-    def sync_gradients(self, release: bool = True) -> None:
+    def begin_step(self, f_cat: torch.Tensor, c_cat: torch.Tensor) -> None:
+        """Optional, before the forward: publish this step's indices right away, rendezvous once, and let every
+        owner build and sort its (slice, index) keys on a side stream WHILE the step computes (the sort needs only
+        indices; it is ~40 % of the owner-side reduce).  ``sync_gradients`` then only runs the segment reduce."""
+        for t, x in enumerate((f_cat, c_cat)):
+            self.x_shared[t].copy_(x)
+        dist.all_reduce(self._token, group=self.group)      # every rank's indices are in place
+        self.peers.fence()
+        self.rezero()                                       # previous keys are consumed before the sort overwrites them
+        if self.groups:
+            if self._side is not None:
+                main = torch.cuda.current_stream()
+                self._side.wait_stream(main)
+                with torch.cuda.stream(self._side):
+                    self.kernels.peer_reduce(self.groups, self.world, self.B, self.scratch, phase=1)
+            else:
+                self.kernels.peer_reduce(self.groups, self.world, self.B, self.scratch, phase=1)
+        self._presorted = True
+
+    def sync_gradients(self, release: Optional[bool] = None) -> None:
         """After ``backward()``: all-reduce the tower gradients and let every owner reduce its slices' gradients.
-        With an optimiser pass ``release=False`` and call ``release()`` after ``optimizer.step()``."""
+        ``release``: run the closing rendezvous here.  Default: only when the step did not start with
+        ``begin_step`` — with it, the next step's opening rendezvous already orders everything (every rank reaches it
+        after its own reduce and optimiser step).  With an optimiser and no ``begin_step`` pass ``release=False`` and
+        call ``release()`` after ``optimizer.step()``."""
+        if release is None:
+            release = not self._presorted
         for t, h in enumerate(self.handles):
             pg = h.table_grads
             if pg.pending is None:
                 continue
             x_cat, dx_emb = pg.pending            # kept: a replayed CUDA graph refills the same buffers
-            self.x_shared[t].copy_(x_cat)
+            if not self._presorted:
+                self.x_shared[t].copy_(x_cat)
             if dx_emb.data_ptr() != self.dx_shared[t].data_ptr():
                 self.dx_shared[t].copy_(dx_emb)
+        if self._presorted and self._side is not None:
+            # joined BEFORE the all-reduce: entering it then implies this rank no longer reads the peers' indices,
+            # so a peer that leaves the all-reduce may publish the next step's
+            torch.cuda.current_stream().wait_stream(self._side)
         # one flat all-reduce for the tower parameters; it completes only after every rank has queued it behind its
         # backward, so it is also the barrier after which all peer buffers are complete
         allreduce_flat_([p.grad for p in self.dense] + [self._token], self.group)
         self.peers.fence()
-        self.rezero()                             # rows of the previous step (its sorted keys are still in scratch)
-        for g in self.groups:
-            self.kernels.peer_reduce(g["owned"], self.world, self.B, g["emb_dim"], g["width"], g["scratch"])
-            g["dirty"] = True
+        if self._presorted:
+            if self.groups:
+                self.kernels.peer_reduce(self.groups, self.world, self.B, self.scratch, phase=2)
+                self._dirty = True
+            self._presorted = False
+        else:
+            self.rezero()                         # rows of the previous step (its sorted keys are still in scratch)
+            if self.groups:
+                self.kernels.peer_reduce(self.groups, self.world, self.B, self.scratch, phase=0)
+                self._dirty = True
         if release:
             self.release()
 
     def release(self) -> None:
-        """Second rendezvous of the step: after it, every owner has consumed the peers' gradient rows (they may be
+        """Last rendezvous of the step: after it, every owner has consumed the peers' gradient rows (they may be
         overwritten) and, with an optimiser, every owner's updated table rows are visible to the next forward."""
         dist.all_reduce(self._token, group=self.group)
 
     def rezero(self) -> None:
-        """Zero the owned gradient slices written by the last reduce.  Runs at the start of the next
-        ``sync_gradients`` (not inside ``zero_grad_fast``, which a CUDA graph may have captured before the first
-        reduce existed); call it directly to get clean ``.grad`` tables earlier."""
-        for g in self.groups:
-            if g["dirty"]:
-                self.kernels.rezero(g["owned"], g["emb_dim"], g["width"], g["scratch"])
-                g["dirty"] = False
+        """Zero the owned gradient slices written by the last reduce.  Runs at the start of the next step's key
+        build (not inside ``zero_grad_fast``, which a CUDA graph may have captured before the first reduce
+        existed); call it directly to get clean ``.grad`` tables earlier."""
+        if self.groups and self._dirty:
+            self.kernels.rezero(self.groups, self.world, self.B, self.scratch)
+        self._dirty = False
 
 
 # ---------------------------------------------------------------------------------------------

@@ -33,7 +33,7 @@ class GraphedTwoTowerStep:
     def __init__(self, model: CEOFirmMatcher, example: Sequence[torch.Tensor],
                  optimizer: Optional[torch.optim.Optimizer] = None, warmup: int = 3,
                  stream: Optional[torch.cuda.Stream] = None, loss_scale: float = 1.0,
-                 after_backward=None):
+                 after_backward=None, before_forward=None):
         dev = next(model.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("GraphedTwoTowerStep needs the model on a CUDA device (no CPU fallback)")
@@ -42,6 +42,7 @@ class GraphedTwoTowerStep:
         # multi-GPU: the gradient synchronisation (e.g. TableShardedTwoTower.sync_gradients) runs right after the
         # backward INSIDE the captured step, NCCL collectives included, so a step stays one graph launch per rank
         self.after_backward = after_backward
+        self.before_forward = before_forward     # e.g. TableShardedTwoTower.begin_step(f_cat, c_cat)
         self.static = [torch.empty(t.shape, dtype=t.dtype, device=dev) for t in example]
         for s, t in zip(self.static, example):
             s.copy_(t)
@@ -67,6 +68,8 @@ class GraphedTwoTowerStep:
     def _body(self) -> torch.Tensor:
         ops.advance_graph_rng_counter()
         self.model.zero_grad_fast()
+        if self.before_forward is not None:
+            self.before_forward(self.static[1], self.static[3])
         loss, _ = self.model.forward_loss(*self.static)
         (loss if self.loss_scale == 1.0 else loss * self.loss_scale).backward()
         if self.after_backward is not None:

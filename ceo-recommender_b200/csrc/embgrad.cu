@@ -231,6 +231,7 @@ struct PeerPlan {
     int n_cols[CFM_MAX_TABLES];
     int col[CFM_MAX_TABLES];
     int col0[CFM_MAX_TABLES];
+    int E[CFM_MAX_TABLES];
 };
 
 // slot (j*W + r)*B + b: owned-slice-major, then rank, then row -> a stable sort keeps (rank, row) order per key
@@ -251,7 +252,7 @@ __global__ void emb_make_keys_peer(PeerPlan pp, int n_owned, int W, long long B,
 template <int VEC>
 __global__ void emb_segment_reduce_peer(const unsigned long long* __restrict__ keys, const int* __restrict__ vals,
                                         long long n, long long B, int E, int w, int idx_bits, PeerPlan pp,
-                                        TablePtrs tp) {
+                                        TablePtrs tp) {   // keys/vals already offset to the group's range
     const int WV = w / VEC;
     const long long total = n * WV;
     const unsigned long long mask = (1ull << idx_bits) - 1;
@@ -283,44 +284,57 @@ __global__ void emb_segment_reduce_peer(const unsigned long long* __restrict__ k
 }
 
 // zero columns [col0, col0 + w) of every row a sorted key names
+template <int VEC>
 __global__ void emb_rezero_peer(const unsigned long long* __restrict__ keys, long long n, int E, int w, int idx_bits,
                                 PeerPlan pp, TablePtrs tp) {
-    const long long total = n * w;
+    const int WV = w / VEC;
+    const long long total = n * WV;
     const unsigned long long mask = (1ull << idx_bits) - 1;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long p = i / w;
-        const int e = (int)(i - p * w);
+        const long long p = i / WV;
+        const int q = (int)(i - p * WV);
         const unsigned long long key = keys[p];
         if (p > 0 && keys[p - 1] == key) continue;
         const int j = (int)(key >> idx_bits);
-        tp.p[j][(size_t)(key & mask) * E + pp.col0[j] + e] = 0.f;
+        float* dst = tp.p[j] + (size_t)(key & mask) * E + pp.col0[j] + q * VEC;
+        if (VEC == 4) *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+        else *dst = 0.f;
     }
 }
 
-static int fill_peer_plan(PeerPlan& pp, TablePtrs& tp, const cfm_peer_table_t* owned, int64_t n_owned, int64_t n_peers,
-                          int64_t emb_dim, int64_t width, bool need_peers, int* idx_bits, int* key_bits) {
-    CFM_REQUIRE(owned, CFM_ERR_INVALID, "null pointer");
-    CFM_REQUIRE(n_owned >= 1 && n_owned <= CFM_MAX_TABLES && n_peers >= 1 && n_peers <= CFM_MAX_PEERS, CFM_ERR_INVALID,
-                "n_owned outside [1,%d] or n_peers outside [1,%d]", CFM_MAX_TABLES, CFM_MAX_PEERS);
-    CFM_REQUIRE(emb_dim >= 1 && width >= 1 && width <= emb_dim, CFM_ERR_INVALID, "bad emb_dim / width");
+// one plan over the owned slices of ALL groups (slice ids are global, group-major)
+static int fill_peer_plan(PeerPlan& pp, TablePtrs& tp, const cfm_peer_group_t* groups, int64_t n_groups, int64_t n_peers,
+                          bool need_peers, int* idx_bits, int* key_bits, int* total_owned) {
+    CFM_REQUIRE(groups && n_groups >= 1 && n_groups <= CFM_MAX_GROUPS, CFM_ERR_INVALID, "n_groups outside [1,%d]",
+                CFM_MAX_GROUPS);
+    CFM_REQUIRE(n_peers >= 1 && n_peers <= CFM_MAX_PEERS, CFM_ERR_INVALID, "n_peers outside [1,%d]", CFM_MAX_PEERS);
     float* grads[CFM_MAX_TABLES];
     int64_t rows[CFM_MAX_TABLES];
     for (int j = 0; j < CFM_MAX_TABLES; ++j) {
-        pp.n_cols[j] = pp.col[j] = pp.col0[j] = 0;
+        pp.n_cols[j] = pp.col[j] = pp.col0[j] = pp.E[j] = 0;
         for (int r = 0; r < CFM_MAX_PEERS; ++r) { pp.x_cat[j][r] = nullptr; pp.dx[j][r] = nullptr; }
-        if (j >= n_owned) continue;
-        const cfm_peer_table_t& t = owned[j];
-        CFM_REQUIRE(t.n_cols >= 1 && t.col >= 0 && t.col < t.n_cols && t.grad && t.rows >= 1 && t.col0 >= 0 &&
-                        t.col0 + width <= emb_dim, CFM_ERR_INVALID, "bad owned slice %d", j);
-        pp.n_cols[j] = (int)t.n_cols; pp.col[j] = (int)t.col; pp.col0[j] = (int)t.col0;
-        grads[j] = t.grad; rows[j] = t.rows;
-        for (int r = 0; need_peers && r < n_peers; ++r) {
-            CFM_REQUIRE(t.x_cat[r] && t.dx_emb[r], CFM_ERR_INVALID, "owned slice %d: null peer buffer %d", j, r);
-            pp.x_cat[j][r] = (const long long*)t.x_cat[r];
-            pp.dx[j][r] = t.dx_emb[r];
+    }
+    int j = 0;
+    for (int g = 0; g < n_groups; ++g) {
+        const cfm_peer_group_t& G = groups[g];
+        CFM_REQUIRE(G.owned && G.n_owned >= 1 && j + G.n_owned <= CFM_MAX_TABLES, CFM_ERR_INVALID,
+                    "group %d: bad slice count / more than %d owned slices", g, CFM_MAX_TABLES);
+        CFM_REQUIRE(G.emb_dim >= 1 && G.width >= 1 && G.width <= G.emb_dim, CFM_ERR_INVALID, "group %d: bad emb_dim / width", g);
+        for (int o = 0; o < G.n_owned; ++o, ++j) {
+            const cfm_peer_table_t& t = G.owned[o];
+            CFM_REQUIRE(t.n_cols >= 1 && t.col >= 0 && t.col < t.n_cols && t.grad && t.rows >= 1 && t.col0 >= 0 &&
+                            t.col0 + G.width <= G.emb_dim, CFM_ERR_INVALID, "group %d: bad owned slice %d", g, o);
+            pp.n_cols[j] = (int)t.n_cols; pp.col[j] = (int)t.col; pp.col0[j] = (int)t.col0; pp.E[j] = (int)G.emb_dim;
+            grads[j] = t.grad; rows[j] = t.rows;
+            for (int r = 0; need_peers && r < n_peers; ++r) {
+                CFM_REQUIRE(t.x_cat[r] && t.dx_emb[r], CFM_ERR_INVALID, "group %d slice %d: null peer buffer %d", g, o, r);
+                pp.x_cat[j][r] = (const long long*)t.x_cat[r];
+                pp.dx[j][r] = t.dx_emb[r];
+            }
         }
     }
-    return fill_tables(tp, grads, rows, n_owned, idx_bits, key_bits);
+    *total_owned = j;
+    return fill_tables(tp, grads, rows, j, idx_bits, key_bits);
 }
 
 }  // namespace cfm
@@ -367,53 +381,74 @@ extern "C" int cfm_emb_gather_rows(const int64_t* x_cat, int64_t B, int64_t n_ta
     return CFM_OK;
 }
 
-extern "C" int cfm_emb_grad_peer_reduce(const cfm_peer_table_t* owned, int64_t n_owned, int64_t n_peers, int64_t B,
-                                        int64_t emb_dim, int64_t width, int64_t* keys_tmp, int32_t* vals_tmp,
-                                        int64_t* keys_sorted, int32_t* vals_sorted, void* sort_tmp,
-                                        int64_t sort_tmp_bytes, void* stream_) {
+extern "C" int cfm_emb_grad_peer_reduce(const cfm_peer_group_t* groups, int64_t n_groups, int64_t n_peers, int64_t B,
+                                        int64_t phase, int64_t* keys_tmp, int32_t* vals_tmp, int64_t* keys_sorted,
+                                        int32_t* vals_sorted, void* sort_tmp, int64_t sort_tmp_bytes, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     CFM_REQUIRE(keys_tmp && vals_tmp && keys_sorted && vals_sorted && sort_tmp, CFM_ERR_INVALID, "null pointer");
+    CFM_REQUIRE(phase >= 0 && phase <= 2, CFM_ERR_INVALID, "phase must be 0 (all), 1 (keys + sort) or 2 (reduce)");
     PeerPlan pp;
     TablePtrs tp;
-    int idx_bits, key_bits;
-    int rc = fill_peer_plan(pp, tp, owned, n_owned, n_peers, emb_dim, width, true, &idx_bits, &key_bits);
+    int idx_bits, key_bits, n_owned;
+    int rc = fill_peer_plan(pp, tp, groups, n_groups, n_peers, true, &idx_bits, &key_bits, &n_owned);
     if (rc) return rc;
-    CFM_REQUIRE(B >= 1 && n_owned * n_peers * B < (1ll << 31), CFM_ERR_INVALID, "bad sizes");
-    const long long n = n_owned * n_peers * B;
+    CFM_REQUIRE(B >= 1 && (long long)n_owned * n_peers * B < (1ll << 31), CFM_ERR_INVALID, "bad sizes");
+    const long long n = (long long)n_owned * n_peers * B;
     ProfScope prof(PROF_EMB, stream);
-    emb_make_keys_peer<<<(int)std::min<long long>((n + 255) / 256, 148 * 8), 256, 0, stream>>>(
-        pp, (int)n_owned, (int)n_peers, B, idx_bits, tp, (unsigned long long*)keys_tmp, vals_tmp);
-    CFM_LAUNCH_CHECK();
-    size_t bytes = (size_t)sort_tmp_bytes;
-    CFM_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(sort_tmp, bytes, (const unsigned long long*)keys_tmp,
-                                                   (unsigned long long*)keys_sorted, (const int*)vals_tmp,
-                                                   vals_sorted, (int)n, 0, key_bits, stream));
-    if ((width & 3) == 0 && (emb_dim & 3) == 0) {
-        const long long total = n * (width / 4);
-        emb_segment_reduce_peer<4><<<(int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, stream>>>(
-            (const unsigned long long*)keys_sorted, vals_sorted, n, B, (int)emb_dim, (int)width, idx_bits, pp, tp);
-    } else {
-        const long long total = n * width;
-        emb_segment_reduce_peer<1><<<(int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, stream>>>(
-            (const unsigned long long*)keys_sorted, vals_sorted, n, B, (int)emb_dim, (int)width, idx_bits, pp, tp);
+    if (phase != 2) {
+        emb_make_keys_peer<<<(int)std::min<long long>((n + 255) / 256, 148 * 8), 256, 0, stream>>>(
+            pp, n_owned, (int)n_peers, B, idx_bits, tp, (unsigned long long*)keys_tmp, vals_tmp);
+        CFM_LAUNCH_CHECK();
+        size_t bytes = (size_t)sort_tmp_bytes;
+        CFM_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(sort_tmp, bytes, (const unsigned long long*)keys_tmp,
+                                                       (unsigned long long*)keys_sorted, (const int*)vals_tmp,
+                                                       vals_sorted, (int)n, 0, key_bits, stream));
     }
-    CFM_LAUNCH_CHECK();
+    if (phase == 1) return CFM_OK;
+    long long off = 0;
+    for (int g = 0; g < n_groups; ++g) {
+        const cfm_peer_group_t& G = groups[g];
+        const long long ng = G.n_owned * n_peers * B;
+        const unsigned long long* ks = (const unsigned long long*)keys_sorted + off;
+        if ((G.width & 3) == 0 && (G.emb_dim & 3) == 0) {
+            const long long total = ng * (G.width / 4);
+            emb_segment_reduce_peer<4><<<(int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, stream>>>(
+                ks, vals_sorted + off, ng, B, (int)G.emb_dim, (int)G.width, idx_bits, pp, tp);
+        } else {
+            const long long total = ng * G.width;
+            emb_segment_reduce_peer<1><<<(int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, stream>>>(
+                ks, vals_sorted + off, ng, B, (int)G.emb_dim, (int)G.width, idx_bits, pp, tp);
+        }
+        CFM_LAUNCH_CHECK();
+        off += ng;
+    }
     return CFM_OK;
 }
 
-extern "C" int cfm_emb_grad_peer_rezero(const cfm_peer_table_t* owned, int64_t n_owned, int64_t emb_dim, int64_t width,
-                                        const int64_t* keys_sorted, int64_t n_items, void* stream_) {
+extern "C" int cfm_emb_grad_peer_rezero(const cfm_peer_group_t* groups, int64_t n_groups, int64_t n_peers, int64_t B,
+                                        const int64_t* keys_sorted, void* stream_) {
     CFM_REQUIRE(keys_sorted, CFM_ERR_INVALID, "null pointer");
-    if (n_items == 0) return CFM_OK;
     PeerPlan pp;
     TablePtrs tp;
-    int idx_bits, key_bits;
-    int rc = fill_peer_plan(pp, tp, owned, n_owned, 1, emb_dim, width, false, &idx_bits, &key_bits);
+    int idx_bits, key_bits, n_owned;
+    int rc = fill_peer_plan(pp, tp, groups, n_groups, n_peers, false, &idx_bits, &key_bits, &n_owned);
     if (rc) return rc;
-    const long long total = n_items * width;
-    emb_rezero_peer<<<(int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, (cudaStream_t)stream_>>>(
-        (const unsigned long long*)keys_sorted, n_items, (int)emb_dim, (int)width, idx_bits, pp, tp);
-    CFM_LAUNCH_CHECK();
+    long long off = 0;
+    for (int g = 0; g < n_groups; ++g) {
+        const cfm_peer_group_t& G = groups[g];
+        const long long ng = G.n_owned * n_peers * B;
+        if ((G.width & 3) == 0 && (G.emb_dim & 3) == 0) {
+            const long long total = ng * (G.width / 4);
+            emb_rezero_peer<4><<<(int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, (cudaStream_t)stream_>>>(
+                (const unsigned long long*)keys_sorted + off, ng, (int)G.emb_dim, (int)G.width, idx_bits, pp, tp);
+        } else {
+            const long long total = ng * G.width;
+            emb_rezero_peer<1><<<(int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, (cudaStream_t)stream_>>>(
+                (const unsigned long long*)keys_sorted + off, ng, (int)G.emb_dim, (int)G.width, idx_bits, pp, tp);
+        }
+        CFM_LAUNCH_CHECK();
+        off += ng;
+    }
     return CFM_OK;
 }
 

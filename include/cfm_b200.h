@@ -165,13 +165,14 @@ int cfm_emb_grad_joint_rezero(const cfm_emb_group_t* groups /* host */, int64_t 
  *                             owner.  stash is [n_tables, B, E]; the towers then run on it (table k = stash[k],
  *                             index = b), so forward and stage-1 backward touch NVLink once per step.
  *                             Out-of-range index: err_flag |= 1.
- *   cfm_emb_grad_peer_reduce: the owner's sorted-segment reduce over EVERY rank's batch.  For owned slice j the
+ *   cfm_emb_grad_peer_reduce: the owner's sorted-segment reduce over EVERY rank's batch: one key build + one radix
+ *                             sort over the owned slices of all groups, one reduce launch per group.  For owned slice j the
  *                             items are (rank r, row b) with index x_cat[r][b*n_cols + col] and gradient columns
  *                             dx_emb[r][b*n_cols*E + col*E + col0 ... + width); both buffers are read in place
  *                             through the peer mappings; grad[idx, col0 ... col0+width) is written.  Runs of equal
  *                             keys are summed in (rank, row) order == the order of the concatenated global batch.
- *                             Scratch as for cfm_emb_grad_segment_reduce with n_items = n_owned*n_peers*B
- *                             (cfm_emb_grad_tmp_bytes(n_owned*n_peers, B)).
+ *                             Scratch as for cfm_emb_grad_segment_reduce with n_items = (total owned)*n_peers*B
+ *                             (cfm_emb_grad_tmp_bytes((total owned)*n_peers, B)).
  *   cfm_emb_grad_peer_rezero: zero the slices named by keys_sorted of the previous reduce (x_cat/dx_emb ignored).
  * ------------------------------------------------------------------------------------------ */
 #define CFM_MAX_PEERS 8
@@ -195,12 +196,19 @@ int cfm_ipc_close(void* base);
 int cfm_emb_gather_rows(const int64_t* x_cat, int64_t B, int64_t n_tables, int64_t emb_dim, int64_t pieces,
                         const float* const* tables /* host array of n_tables*pieces device ptrs */,
                         const int64_t* table_rows /* host */, float* stash, int32_t* err_flag, void* stream);
-int cfm_emb_grad_peer_reduce(const cfm_peer_table_t* owned /* host */, int64_t n_owned, int64_t n_peers, int64_t B,
-                             int64_t emb_dim, int64_t width, int64_t* keys_tmp, int32_t* vals_tmp,
-                             int64_t* keys_sorted, int32_t* vals_sorted, void* sort_tmp, int64_t sort_tmp_bytes,
-                             void* stream);
-int cfm_emb_grad_peer_rezero(const cfm_peer_table_t* owned /* host */, int64_t n_owned, int64_t emb_dim, int64_t width,
-                             const int64_t* keys_sorted, int64_t n_items, void* stream);
+typedef struct cfm_peer_group {              /* the owned slices that share one embedding width (one tower) */
+    const cfm_peer_table_t* owned;           /* host array */
+    int64_t n_owned;
+    int64_t emb_dim;                         /* row width of these tables */
+    int64_t width;                           /* columns per owned slice (emb_dim / pieces) */
+} cfm_peer_group_t;
+/* phase 0: everything; 1: key build + sort only (needs the peers' x_cat: can run on a side stream while the step
+ * computes); 2: segment reduce only (needs the peers' dx_emb; after phase 1 on the same scratch). */
+int cfm_emb_grad_peer_reduce(const cfm_peer_group_t* groups /* host */, int64_t n_groups, int64_t n_peers, int64_t B,
+                             int64_t phase, int64_t* keys_tmp, int32_t* vals_tmp, int64_t* keys_sorted,
+                             int32_t* vals_sorted, void* sort_tmp, int64_t sort_tmp_bytes, void* stream);
+int cfm_emb_grad_peer_rezero(const cfm_peer_group_t* groups /* host */, int64_t n_groups, int64_t n_peers, int64_t B,
+                             const int64_t* keys_sorted, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Cosine head: L2-normalise both latents, row-wise dot, times exp(logit_scale).

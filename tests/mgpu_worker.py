@@ -88,10 +88,13 @@ def main():
             m.p = 0.0
     model2.use_persistent_table_grads(True)
     ts = D.TableShardedTwoTower(model2, batch_rows=B)
-    other = clear_of_relu_kinks(5000)        # a different batch first: touches rows (5000-row table) that the
-    for data in (other, shards):             # second step must have re-zeroed
+    other = clear_of_relu_kinks(5000)        # different batches first: they touch rows (5000-row table) that the
+    for step, data in enumerate((other, other, shards)):     # last step must find re-zeroed
+        local = [t.to(dev) for t in data[rank]]
         model2.zero_grad_fast()
-        loss2, _ = model2.forward_loss(*[t.to(dev) for t in data[rank]])
+        if step > 0:                         # early publish: owners sort on a side stream while the step computes
+            ts.begin_step(local[1], local[3])
+        loss2, _ = model2.forward_loss(*local)
         (loss2 * ts.loss_scale).backward()
         ts.sync_gradients()
     assert torch.equal(loss2, loss), "stash forward differs from the direct gather"

@@ -98,19 +98,28 @@ class TorchTableOps:
     def make_scratch(self, n_owned, n_peers, B, device):
         return {"touched": []}
 
-    def peer_reduce(self, owned, n_peers, B, emb_dim, width, scratch):
+    def peer_reduce(self, groups, n_peers, B, scratch, phase=0):
+        if phase != 2:                                                 # "keys + sort": needs only the indices
+            scratch["idx"] = [[[o["x_cat"][r][:, o["col"]].clone() for r in range(n_peers)] for o in g["owned"]]
+                              for g in groups]
+        if phase == 1:
+            return
         scratch["touched"] = []
-        for o in owned:
-            c0 = o["col0"]
-            for r in range(n_peers):                                   # rank order, then row order
-                idx = o["x_cat"][r][:, o["col"]]
-                rows = o["dx_emb"][r][:, o["col"] * emb_dim + c0:o["col"] * emb_dim + c0 + width]
-                o["grad"][:, c0:c0 + width].index_add_(0, idx, rows)
-                scratch["touched"].append((o, idx.clone()))
+        for g, gi in zip(groups, scratch["idx"]):
+            E, width = g["emb_dim"], g["width"]
+            for o, oi in zip(g["owned"], gi):
+                c0 = o["col0"]
+                for r in range(n_peers):                               # rank order, then row order
+                    rows = o["dx_emb"][r][:, o["col"] * E + c0:o["col"] * E + c0 + width]
+                    o["grad"][:, c0:c0 + width].index_add_(0, oi[r], rows)
+                    scratch["touched"].append((o, oi[r], width))
 
-    def rezero(self, owned, emb_dim, width, scratch):
-        for o, idx in scratch["touched"]:
+    def rezero(self, groups, n_peers, B, scratch):
+        for o, idx, width in scratch["touched"]:
             o["grad"][idx, o["col0"]:o["col0"] + width] = 0.0
+
+    def side_stream(self, device):
+        return None
 
 
 def _table_sharded_protocol(rank, world):
@@ -131,12 +140,14 @@ def _table_sharded_protocol(rank, world):
     dist.all_gather(both, flat)
     res["consolidated"] = all(torch.equal(both[0], x) for x in both)    # dense from rank 0, slices from owners
     expected_steps = []
-    for step in range(2):
+    for step in range(3):
         for p in ts.dense:
             p.grad = torch.full_like(p, float(rank + 1 + step))
         gens = [torch.Generator().manual_seed(1000 * step + r) for r in range(world)]
         data = [[(torch.stack([torch.randint(0, e.num_embeddings, (B,), generator=g) for e in h.embeddings], 1),
                   torch.randn(B, h.n_tables * h.emb_dim, generator=g)) for h in hs] for g in gens]
+        if step == 2:                                                   # early publish + sort, reduce after backward
+            ts.begin_step(data[rank][0][0], data[rank][1][0])
         for t, h in enumerate(hs):
             h.table_grads.pending = data[rank][t]                       # what the CUDA backward leaves behind
         ts.sync_gradients()
@@ -228,7 +239,7 @@ def test_world2_protocol():
     for rank in range(world):
         sh = out[rank]["sharded"]
         assert sh["plan"] == out[0]["sharded"]["plan"]              # every rank derives the same ownership
-        assert sh["consolidated"] and sh["steps"] == [True, True] and sh["owned_ok"]
+        assert sh["consolidated"] and sh["steps"] == [True, True, True] and sh["owned_ok"]
 
 
 def test_table_slice_plan_is_balanced():

@@ -108,20 +108,29 @@ def test_peer_reduce_equals_segment_reduce_of_concatenated_batch(n_peers, pieces
         ops.reduce_table_grads(h, torch.cat([xs[r][hi] for r in range(n_peers)]),
                                torch.cat([dxs[r][hi] for r in range(n_peers)]))
     kernels = D.CudaTableOps()
+    groups = []
     for hi, cols in ((0, [1, 3]), (1, [0, 2, 6])):
         h = hs[hi]
         w = h.emb_dim // pieces
+        if w * pieces != h.emb_dim or w % 4:
+            w = h.emb_dim                                      # this tower keeps whole tables
         owned = [dict(n_cols=h.n_tables, col=k, col0=c * w, grad=torch.zeros_like(h.embeddings[k].weight),
-                      x_cat=[xs[r][hi] for r in range(n_peers)], dx_emb=[dxs[r][hi] for r in range(n_peers)])
-                 for k in cols for c in range(pieces) if (k + c) % 2 == 0 or pieces == 1]
-        scratch = kernels.make_scratch(len(owned), n_peers, B, torch.device(DEV))
-        kernels.peer_reduce(owned, n_peers, B, h.emb_dim, w, scratch)
-        for o in owned:
-            exp = torch.zeros_like(o["grad"])
-            exp[:, o["col0"]:o["col0"] + w] = h.embeddings[o["col"]].weight.grad[:, o["col0"]:o["col0"] + w]
-            assert torch.equal(o["grad"], exp), (hi, o["col"], o["col0"])
-        kernels.rezero(owned, h.emb_dim, w, scratch)
-        assert all(float(o["grad"].abs().sum()) == 0.0 for o in owned)
+                      x_cat=[xs[r][hi] for r in range(n_peers)], dx_emb=[dxs[r][hi] for r in range(n_peers)], tower=hi)
+                 for k in cols for c in range(h.emb_dim // w) if (k + c) % 2 == 0 or w == h.emb_dim]
+        groups.append(dict(owned=owned, emb_dim=h.emb_dim, width=w))
+    n_owned = sum(len(g["owned"]) for g in groups)
+    scratch = kernels.make_scratch(n_owned, n_peers, B, torch.device(DEV))
+    for phases in ((0,), (1, 2)):                               # one call, or sort first and reduce later
+        for ph in phases:
+            kernels.peer_reduce(groups, n_peers, B, scratch, phase=ph)
+        for g in groups:
+            for o in g["owned"]:
+                w = g["width"]
+                exp = torch.zeros_like(o["grad"])
+                exp[:, o["col0"]:o["col0"] + w] = hs[o["tower"]].embeddings[o["col"]].weight.grad[:, o["col0"]:o["col0"] + w]
+                assert torch.equal(o["grad"], exp), (o["tower"], o["col"], o["col0"])
+        kernels.rezero(groups, n_peers, B, scratch)
+        assert all(float(o["grad"].abs().sum()) == 0.0 for g in groups for o in g["owned"])
 
 
 def test_joint_reduce_is_bitwise_the_per_tower_reduce():

@@ -34,7 +34,7 @@ def test_struct_mirrors_match_header_field_order():
             decl = decl.strip()
             if not decl:
                 continue
-            decl = re.sub(r"^(const\s+)?(float|int64_t|double|uint64_t)\s*", "", decl)
+            decl = re.sub(r"^(const\s+)?(float|int64_t|double|uint64_t|cfm_peer_table_t)\s*", "", decl)
             for part in decl.split(","):
                 nm = re.sub(r"[\*\s]|const|\[.*?\]", "", part)
                 if nm:
@@ -45,6 +45,7 @@ def test_struct_mirrors_match_header_field_order():
     assert fields("cfm_tower_grads") == [f[0] for f in _native.TowerGrads._fields_]
     assert fields("cfm_peer_table") == [f[0] for f in _native.PeerTable._fields_]
     assert fields("cfm_emb_group") == [f[0] for f in _native.EmbGroup._fields_]
+    assert fields("cfm_peer_group") == [f[0] for f in _native.PeerGroup._fields_]
 
 
 def test_modules_construct_on_cpu_and_refuse_cpu_forward():
