@@ -91,6 +91,6 @@ extern "C" int cfm_device_info(int64_t* sm, int64_t* cc_major, int64_t* cc_minor
     if (sm) *sm = cfm::sm_count();
     if (cc_major) *cc_major = maj;
     if (cc_minor) *cc_minor = min;
-    if (tower_ctas) *tower_ctas = cfm::sm_count();
+    if (tower_ctas) *tower_ctas = 2 * cfm::sm_count();   // maximum persistent CTAs per tower (32-row tile stages)
     return CFM_OK;
 }

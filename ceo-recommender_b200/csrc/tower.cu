@@ -23,18 +23,18 @@ namespace cfm {
 struct FwdSmem {
     int lda, ws, as, bn, red, tmean, rmean, rm2, idx, total_floats;
 };
-__host__ __device__ inline FwdSmem fwd_smem(int K, int N, int n_tab, const MmaPlan& gp) {
+__host__ __device__ inline FwdSmem fwd_smem(int K, int N, int n_tab, const MmaPlan& gp, int tm, bool stage1) {
     FwdSmem s;
     s.lda = pad_ld(ceil8(K + 1));
     int o = 0;
     s.ws = o; o += gp.wrows * s.lda;
-    s.as = o; o += TM * s.lda;
-    s.bn = o; o += 4 * ((K + 3) & ~3);
-    s.red = o; o += 16 * 128;
+    s.as = o; o += tm * s.lda;
+    s.bn = o; o += stage1 ? 0 : 4 * ((K + 3) & ~3);
+    s.red = o; o += (tm / 4) * 128;
     s.tmean = o; o += 128;
     s.rmean = o; o += gp.wrows + 128;
     s.rm2 = o; o += gp.wrows + 128;
-    s.idx = o; o += TM * (n_tab > 0 ? n_tab : 1);
+    s.idx = o; o += tm * (n_tab > 0 ? n_tab : 1);
     s.total_floats = (o + 3) & ~3;
     return s;
 }
@@ -42,23 +42,24 @@ __host__ __device__ inline FwdSmem fwd_smem(int K, int N, int n_tab, const MmaPl
 struct BwdSmem {
     int lda, ldg, ldgt, ldxh, wt, as, gs, gt, xh, bna, bng, red, rs, idx, total_floats;
 };
-__host__ __device__ inline BwdSmem bwd_smem(int K, int N, int n_tab, int a_bn, int need_dx, const MmaPlan& gx) {
+__host__ __device__ inline BwdSmem bwd_smem(int K, int N, int n_tab, int a_bn, int need_dx, const MmaPlan& gx,
+                                            int tm, bool stage1) {
     BwdSmem s;
     s.lda = pad_ld_t(K + 1);            // A tile is the "transposed" B operand of the dW product
     s.ldg = pad_ld(ceil8(N));
-    s.ldgt = pad_ld(TM);
+    s.ldgt = pad_ld(tm);
     s.ldxh = pad_ld(K);
     int o = 0;
     s.wt = o; o += need_dx ? gx.wrows * s.ldg : 0;
-    s.as = o; o += TM * s.lda;
-    s.gs = o; o += TM * s.ldg;
+    s.as = o; o += tm * s.lda;
+    s.gs = o; o += tm * s.ldg;
     s.gt = o; o += ((N + 15) & ~15) * s.ldgt;
-    s.xh = o; o += a_bn ? TM * s.ldxh : 0;
-    s.bna = o; o += 4 * ((K + 3) & ~3);
+    s.xh = o; o += a_bn ? tm * s.ldxh : 0;
+    s.bna = o; o += stage1 ? 0 : 4 * ((K + 3) & ~3);
     s.bng = o; o += 5 * ((N + 3) & ~3);
-    s.red = o; o += 2 * 16 * 128;
-    s.rs = o; o += 2 * (gx.wrows + 128);
-    s.idx = o; o += TM * (n_tab > 0 ? n_tab : 1);
+    s.red = o; o += a_bn ? 2 * (tm / 4) * 128 : 0;
+    s.rs = o; o += a_bn ? 2 * (gx.wrows + 128) : 0;
+    s.idx = o; o += tm * (n_tab > 0 ? n_tab : 1);
     s.total_floats = (o + 3) & ~3;
     return s;
 }
@@ -93,14 +94,14 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // Memory-level parallelism is what matters here (every row of a 1M-row table is an HBM miss): the gather is issued
 // as asynchronous 16-byte global->shared copies, all in flight at once, and the activation rebuild loads four
 // float4 per thread before touching any of them.  The caller's __syncthreads() publishes the tile.
-__device__ void build_input_tile(const InputDesc& in, const DropCtx& drop, long long row0, int rows_valid, float* As,
-                                 int lda, float* Xh, int ldxh, const float* sm_bn, int* sm_idx, int* err) {
+__device__ void build_input_tile(const InputDesc& in, const DropCtx& drop, long long row0, int rows_valid, int tm,
+                                 float* As, int lda, float* Xh, int ldxh, const float* sm_bn, int* sm_idx, int* err) {
     const int K = in.K;
     const int tid = threadIdx.x;
     if (in.stage == 1) {
         const GatherSrc& g = in.g;
         const int KE = g.n_tab * g.E;
-        for (int i = tid; i < TM * g.n_tab; i += NT) {
+        for (int i = tid; i < tm * g.n_tab; i += NT) {
             int r = i / g.n_tab, t = i - r * g.n_tab;
             long long idx = 0;
             if (r < rows_valid) {
@@ -112,7 +113,7 @@ __device__ void build_input_tile(const InputDesc& in, const DropCtx& drop, long 
             }
             sm_idx[i] = (int)idx;
         }
-        for (int i = tid; i < TM * g.n_num; i += NT) {              // numerics do not depend on the indices
+        for (int i = tid; i < tm * g.n_num; i += NT) {              // numerics do not depend on the indices
             int r = i / g.n_num, j = i - r * g.n_num;
             if (r < rows_valid) cp_async4(As + r * lda + KE + j, g.x_num + (row0 + r) * g.n_num + j);
             else As[r * lda + KE + j] = 0.f;
@@ -120,7 +121,7 @@ __device__ void build_input_tile(const InputDesc& in, const DropCtx& drop, long 
         __syncthreads();
         if ((g.E & 3) == 0) {
             const int E4 = g.E >> 2;
-            const int items = TM * g.n_tab * E4;
+            const int items = tm * g.n_tab * E4;
             for (int i = tid; i < items; i += NT) {
                 int q = i % E4;
                 int rt = i / E4;
@@ -130,7 +131,7 @@ __device__ void build_input_tile(const InputDesc& in, const DropCtx& drop, long 
                 else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         } else {
-            const int items = TM * KE;
+            const int items = tm * KE;
             for (int i = tid; i < items; i += NT) {
                 int e = i % g.E;
                 int rt = i / g.E;
@@ -145,7 +146,7 @@ __device__ void build_input_tile(const InputDesc& in, const DropCtx& drop, long 
         const int K4 = (K + 3) >> 2, Kp = K4 << 2;
         const bool vec = (K & 3) == 0;
         constexpr int U = 4;
-        for (int base = tid; base < TM * K4; base += NT * U) {
+        for (int base = tid; base < tm * K4; base += NT * U) {
             float v[U][4];
             // phase 1: all loads of this batch
 #pragma unroll
@@ -153,7 +154,7 @@ __device__ void build_input_tile(const InputDesc& in, const DropCtx& drop, long 
                 const int i = base + u * NT;
                 const int r = i / K4, c4 = i - r * K4;
                 v[u][0] = v[u][1] = v[u][2] = v[u][3] = 0.f;
-                if (i < TM * K4 && r < rows_valid) {
+                if (i < tm * K4 && r < rows_valid) {
                     const float* hp = a.h + (size_t)(row0 + r) * K + 4 * c4;
                     if (vec) {
                         float4 t4 = *reinterpret_cast<const float4*>(hp);
@@ -169,7 +170,7 @@ __device__ void build_input_tile(const InputDesc& in, const DropCtx& drop, long 
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int i = base + u * NT;
-                if (i >= TM * K4) continue;
+                if (i >= tm * K4) continue;
                 const int r = i / K4, c4 = i - r * K4;
                 const bool valid = r < rows_valid;
                 float xh[4] = {0.f, 0.f, 0.f, 0.f};
@@ -205,7 +206,7 @@ __device__ void build_input_tile(const InputDesc& in, const DropCtx& drop, long 
         }
     }
     // ones column (folds the bias / bias gradient into the GEMMs) and zero padding
-    for (int i = tid; i < TM * (lda - K); i += NT) {
+    for (int i = tid; i < tm * (lda - K); i += NT) {
         int r = i / (lda - K), c = K + (i - r * (lda - K));
         As[r * lda + c] = (c == K && r < rows_valid) ? 1.f : 0.f;
     }
@@ -298,13 +299,15 @@ struct FwdCtx {
     float *red, *tmean, *rmean, *rm2, *hout;
     int lda, k8n, N;
     bool stats;
+    int wcn;              // column groups of warps (4 for 64-row tiles, 8 for 32-row tiles); row groups = 8 / wcn
 };
 
 // one column pass (<= 128 columns) of a forward tile: GEMM, store raw output, optional (count, mean, M2) statistics
-template <int NI, bool EXACT>
+template <int NI, bool EXACT, int WCN>
 __device__ __forceinline__ void fwd_pass(const FwdCtx& C, int pass, int cols, long long row0, int rows_valid, float run_cnt) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wr = warp >> 2, wc = warp & 3, g = lane >> 2, t = lane & 3;
+    const int wr = warp / WCN, wc = warp % WCN, g = lane >> 2, t = lane & 3;
+    constexpr int nred = 8 * (8 / WCN);                   // partial rows per column in `red`
     const int n0 = pass * 128 + wc * 8 * NI;
     const bool active = wc * 8 * NI < cols;
     float acc[2][NI][4];
@@ -347,7 +350,7 @@ __device__ __forceinline__ void fwd_pass(const FwdCtx& C, int pass, int cols, lo
     if (tid < cols) {
         float s = 0.f;
 #pragma unroll
-        for (int q = 0; q < 16; ++q) s += C.red[q * 128 + tid];
+        for (int q = 0; q < nred; ++q) s += C.red[q * 128 + tid];
         C.tmean[tid] = s / (float)rows_valid;
     }
     __syncthreads();
@@ -374,7 +377,7 @@ __device__ __forceinline__ void fwd_pass(const FwdCtx& C, int pass, int cols, lo
     if (tid < cols) {
         float m2 = 0.f;
 #pragma unroll
-        for (int q = 0; q < 16; ++q) m2 += C.red[q * 128 + tid];
+        for (int q = 0; q < nred; ++q) m2 += C.red[q * 128 + tid];
         // Chan merge of (run_cnt, rmean, rm2) with (rows_valid, tmean, m2)
         const int c = pass * 128 + tid;
         const float na = run_cnt, nb = (float)rows_valid, n = na + nb;
@@ -388,14 +391,15 @@ __device__ __forceinline__ void fwd_pass(const FwdCtx& C, int pass, int cols, lo
 // ------------------------------------------------------------------------------------------
 // forward stage kernel
 // ------------------------------------------------------------------------------------------
-template <bool EXACT>
+template <bool EXACT, int TMV>
 __global__ void __launch_bounds__(NT, 2) tower_fwd_stage(const __grid_constant__ FwdArgs args) {
     const FwdStage& S = args.st[blockIdx.y];
     extern __shared__ float4 smem4[];
     float* sm = reinterpret_cast<float*>(smem4);
     const int K = S.in.K, N = S.N;
     const MmaPlan gp = make_plan(N);
-    const FwdSmem L = fwd_smem(K, N, S.in.g.n_tab, gp);
+    constexpr int tm = TMV;
+    const FwdSmem L = fwd_smem(K, N, S.in.g.n_tab, gp, tm, S.in.stage == 1);
     float *Ws = sm + L.ws, *As = sm + L.as, *sm_bn = sm + L.bn;
     float *rmean = sm + L.rmean, *rm2 = sm + L.rm2;
     int* sm_idx = reinterpret_cast<int*>(sm + L.idx);
@@ -429,20 +433,21 @@ __global__ void __launch_bounds__(NT, 2) tower_fwd_stage(const __grid_constant__
 
     FwdCtx C;
     C.As = As; C.Ws = Ws; C.red = sm + L.red; C.tmean = sm + L.tmean; C.rmean = rmean; C.rm2 = rm2; C.hout = S.hout;
-    C.lda = lda; C.k8n = ceil8(K + 1) >> 3; C.N = N; C.stats = stats;
-    const long long ntiles = (args.B + TM - 1) / TM;
+    C.lda = lda; C.k8n = ceil8(K + 1) >> 3; C.N = N; C.stats = stats; C.wcn = tm == 64 ? 4 : 8;
+    const long long ntiles = (args.B + tm - 1) / tm;
 
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const long long row0 = tile * TM;
-        const int rows_valid = (int)min((long long)TM, args.B - row0);
-        build_input_tile(S.in, drop, row0, rows_valid, As, lda, nullptr, 0, sm_bn, sm_idx, args.err);
+        const long long row0 = tile * tm;
+        const int rows_valid = (int)min((long long)tm, args.B - row0);
+        build_input_tile(S.in, drop, row0, rows_valid, tm, As, lda, nullptr, 0, sm_bn, sm_idx, args.err);
         __syncthreads();
         for (int pass = 0; pass < gp.passes; ++pass) {
             const int cols = pass_cols(N, pass);
-            switch (pass_ni(cols)) {
-                case 1: fwd_pass<1, EXACT>(C, pass, cols, row0, rows_valid, run_cnt); break;
-                case 2: fwd_pass<2, EXACT>(C, pass, cols, row0, rows_valid, run_cnt); break;
-                default: fwd_pass<4, EXACT>(C, pass, cols, row0, rows_valid, run_cnt); break;
+            constexpr int WCN = tm == 64 ? 4 : 8;
+            switch (pass_ni(cols, WCN)) {
+                case 1: fwd_pass<1, EXACT, WCN>(C, pass, cols, row0, rows_valid, run_cnt); break;
+                case 2: fwd_pass<2, EXACT, WCN>(C, pass, cols, row0, rows_valid, run_cnt); break;
+                default: if (WCN == 4) fwd_pass<4, EXACT, WCN>(C, pass, cols, row0, rows_valid, run_cnt); break;
             }
         }
         run_cnt += (float)rows_valid;
@@ -509,14 +514,16 @@ struct BwdCtx {
     int lda, ldg, ldxh, n8n, rs_stride, K, KE, n_num;
     float inv_keep;
     bool stage1;
+    int wcn;              // column groups of warps, see FwdCtx
 };
 
 // one column pass (<= 128 columns of K) of the dX product of a backward tile (+ ReLU/dropout mask, BN-backward sums)
-template <int NI, bool EXACT>
+template <int NI, bool EXACT, int WCN>
 __device__ __forceinline__ void bwd_dx_pass(const BwdStage& S, const BwdCtx& C, int pass, int cols, long long row0,
                                             int rows_valid) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wr = warp >> 2, wc = warp & 3, g = lane >> 2, t = lane & 3;
+    const int wr = warp / WCN, wc = warp % WCN, g = lane >> 2, t = lane & 3;
+    constexpr int nred = 8 * (8 / WCN);
     const int k0 = pass * 128 + wc * 8 * NI;
     const bool active = wc * 8 * NI < cols;
     float acc[2][NI][4];
@@ -559,7 +566,7 @@ __device__ __forceinline__ void bwd_dx_pass(const BwdStage& S, const BwdCtx& C, 
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 myred[ni * 8 + e] = s1[ni][e];
-                myred[16 * 128 + ni * 8 + e] = s2[ni][e];
+                myred[nred * 128 + ni * 8 + e] = s2[ni][e];
             }
     }
     __syncthreads();
@@ -567,7 +574,7 @@ __device__ __forceinline__ void bwd_dx_pass(const BwdStage& S, const BwdCtx& C, 
         const int which = tid >= cols, cl = tid - which * cols;
         float tsum = 0.f;
 #pragma unroll
-        for (int q = 0; q < 16; ++q) tsum += C.red[which * 16 * 128 + q * 128 + cl];
+        for (int q = 0; q < nred; ++q) tsum += C.red[which * nred * 128 + q * 128 + cl];
         C.rs[which * C.rs_stride + pass * 128 + cl] += tsum;
     }
     __syncthreads();
@@ -578,7 +585,7 @@ __device__ __forceinline__ void bwd_dx_pass(const BwdStage& S, const BwdCtx& C, 
 // ------------------------------------------------------------------------------------------
 constexpr int DW_MAX_TILES = 16;   // m16n8 output tiles of dW per warp (N*(K+1) <= 16384)
 
-template <bool EXACT>
+template <bool EXACT, int TMV>
 __global__ void __launch_bounds__(NT, 2) tower_bwd_stage(const __grid_constant__ BwdArgs args) {
     const BwdStage& S = args.st[blockIdx.y];
     const long long B = args.B;
@@ -586,7 +593,8 @@ __global__ void __launch_bounds__(NT, 2) tower_bwd_stage(const __grid_constant__
     float* sm = reinterpret_cast<float*>(smem4);
     const int K = S.in.K, N = S.N;
     const MmaPlan gx = make_plan(K);   // dX: [TM, K] output, reduction over N
-    const BwdSmem L = bwd_smem(K, N, S.in.g.n_tab, S.a_bn, S.need_dx, gx);
+    constexpr int tm = TMV;
+    const BwdSmem L = bwd_smem(K, N, S.in.g.n_tab, S.a_bn, S.need_dx, gx, tm, S.in.stage == 1);
     float *Wt = sm + L.wt, *As = sm + L.as, *Gs = sm + L.gs, *Gt = sm + L.gt, *Xh = S.a_bn ? sm + L.xh : nullptr;
     float *sm_bna = sm + L.bna, *sm_bng = sm + L.bng, *rs = sm + L.rs;
     int* sm_idx = reinterpret_cast<int*>(sm + L.idx);
@@ -626,7 +634,7 @@ __global__ void __launch_bounds__(NT, 2) tower_bwd_stage(const __grid_constant__
             sm_bng[4 * Np + c] = S.g_mode == 1 ? S.g_c2[c] : 0.f;
         }
     }
-    for (int i = tid; i < 2 * rs_stride; i += NT) rs[i] = 0.f;
+    for (int i = tid; S.a_bn && i < 2 * rs_stride; i += NT) rs[i] = 0.f;
     // the G^T tile's padding rows (n >= N) stay zero for the whole kernel
     for (int i = tid; i < ((N + 15) & ~15) * ldgt; i += NT) Gt[i] = 0.f;
 
@@ -642,20 +650,20 @@ __global__ void __launch_bounds__(NT, 2) tower_bwd_stage(const __grid_constant__
     C.lda = lda; C.ldg = ldg; C.ldxh = ldxh; C.n8n = ceil8(N) >> 3; C.rs_stride = rs_stride;
     C.K = K; C.KE = KE; C.n_num = n_num;
     C.inv_keep = (!stage1 && drop.active) ? drop.inv_keep : 1.f;
-    C.stage1 = stage1;
+    C.stage1 = stage1; C.wcn = tm == 64 ? 4 : 8;
     __syncthreads();
 
-    const long long ntiles = (B + TM - 1) / TM;
+    const long long ntiles = (B + tm - 1) / tm;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const long long row0 = tile * TM;
-        const int rows_valid = (int)min((long long)TM, B - row0);
-        build_input_tile(S.in, drop, row0, rows_valid, As, lda, Xh, ldxh, sm_bna, sm_idx, nullptr);
+        const long long row0 = tile * tm;
+        const int rows_valid = (int)min((long long)tm, B - row0);
+        build_input_tile(S.in, drop, row0, rows_valid, tm, As, lda, Xh, ldxh, sm_bna, sm_idx, nullptr);
         // incoming-gradient tile G [TM, N] (zero padded to ldg) and its transpose Gt [N, TM];
         // loads of two items (8 gradient + 8 saved-activation values) are issued before either is used
         {
             const int ldg4 = ldg >> 2;
             const bool vecn = (N & 3) == 0;
-            for (int base = tid; base < TM * ldg4; base += NT * 2) {
+            for (int base = tid; base < tm * ldg4; base += NT * 2) {
                 float dyv[2][4], hsv[2][4];
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
@@ -663,7 +671,7 @@ __global__ void __launch_bounds__(NT, 2) tower_bwd_stage(const __grid_constant__
                     const int r = i / ldg4, c4 = i - r * ldg4;
 #pragma unroll
                     for (int e = 0; e < 4; ++e) { dyv[u][e] = 0.f; hsv[u][e] = 0.f; }
-                    if (i < TM * ldg4 && r < rows_valid && 4 * c4 < N) {
+                    if (i < tm * ldg4 && r < rows_valid && 4 * c4 < N) {
                         const size_t off = (size_t)(row0 + r) * N + 4 * c4;
                         if (vecn) {
                             const float4 d4 = *reinterpret_cast<const float4*>(S.gin + off);
@@ -685,7 +693,7 @@ __global__ void __launch_bounds__(NT, 2) tower_bwd_stage(const __grid_constant__
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                     const int i = base + u * NT;
-                    if (i >= TM * ldg4) continue;
+                    if (i >= tm * ldg4) continue;
                     const int r = i / ldg4, c4 = i - r * ldg4;
                     float gv[4] = {0.f, 0.f, 0.f, 0.f};
                     if (r < rows_valid) {
@@ -723,7 +731,7 @@ __global__ void __launch_bounds__(NT, 2) tower_bwd_stage(const __grid_constant__
                 const float* gp_ = Gt + (nt * 16 + rin + (mat & 1) * 8) * ldgt + (mat >> 1) * 4;   // A: (m = n, k = row)
                 const float* ap_ = As + t * lda + kt * 8 + g;              // B fragment: (k = row, n = k_in)
 #pragma unroll 2
-                for (int r8 = 0; r8 < TM / 8; ++r8) {
+                for (int r8 = 0; r8 < tm / 8; ++r8) {
                     uint32_t raw[4], ah[4], al[4], bh[2], bl[2];
                     ldmatrix_x4(gp_ + r8 * 8, raw);
 #pragma unroll
@@ -739,10 +747,11 @@ __global__ void __launch_bounds__(NT, 2) tower_bwd_stage(const __grid_constant__
         if (S.need_dx) {
             for (int pass = 0; pass < gx.passes; ++pass) {
                 const int cols = pass_cols(K, pass);
-                switch (pass_ni(cols)) {
-                    case 1: bwd_dx_pass<1, EXACT>(S, C, pass, cols, row0, rows_valid); break;
-                    case 2: bwd_dx_pass<2, EXACT>(S, C, pass, cols, row0, rows_valid); break;
-                    default: bwd_dx_pass<4, EXACT>(S, C, pass, cols, row0, rows_valid); break;
+                constexpr int WCN = tm == 64 ? 4 : 8;
+                switch (pass_ni(cols, WCN)) {
+                    case 1: bwd_dx_pass<1, EXACT, WCN>(S, C, pass, cols, row0, rows_valid); break;
+                    case 2: bwd_dx_pass<2, EXACT, WCN>(S, C, pass, cols, row0, rows_valid); break;
+                    default: if (WCN == 4) bwd_dx_pass<4, EXACT, WCN>(S, C, pass, cols, row0, rows_valid); break;
                 }
             }
         }
@@ -915,15 +924,22 @@ static int stage_K(const cfm_tower_t& t, int s) {
     return (int)(s == 1 ? t.n_num + t.n_tables * t.emb_dim : s == 2 ? t.h1 : t.h2);
 }
 
-static int tower_ctas() { return sm_count(); }
-
-static size_t fwd_smem_bytes(const cfm_tower_t& t, int s) {
-    MmaPlan gp = make_plan(stage_N(t, s));
-    return (size_t)fwd_smem(stage_K(t, s), stage_N(t, s), (int)t.n_tables, gp).total_floats * 4;
+// persistent CTAs per tower: one per SM, two for 32-row tiles (cfm_device_info reports the maximum: scratch sizing)
+static int tower_ctas(int tm) { return tm == 32 ? 2 * sm_count() : sm_count(); }
+// 32-row tiles exactly when they turn a one-CTA-per-SM stage (weights + tile > half the SM's shared memory) into a
+// two-CTA one: the stage is latency-bound, a second resident CTA is worth more than the larger tile
+static int pick_tm(size_t smem64, size_t smem32) {
+    const size_t two_per_sm = 113 * 1024;
+    return (smem64 > two_per_sm && smem32 <= two_per_sm) ? 32 : 64;
 }
-static size_t bwd_smem_bytes(const cfm_tower_t& t, int s, int a_bn, int need_dx) {
+
+static size_t fwd_smem_bytes(const cfm_tower_t& t, int s, int tm) {
+    MmaPlan gp = make_plan(stage_N(t, s));
+    return (size_t)fwd_smem(stage_K(t, s), stage_N(t, s), (int)t.n_tables, gp, tm, s == 1).total_floats * 4;
+}
+static size_t bwd_smem_bytes(const cfm_tower_t& t, int s, int a_bn, int need_dx, int tm) {
     MmaPlan gx = make_plan(stage_K(t, s));
-    return (size_t)bwd_smem(stage_K(t, s), stage_N(t, s), (int)t.n_tables, a_bn, need_dx, gx).total_floats * 4;
+    return (size_t)bwd_smem(stage_K(t, s), stage_N(t, s), (int)t.n_tables, a_bn, need_dx, gx, tm, s == 1).total_floats * 4;
 }
 
 }  // namespace cfm
@@ -952,18 +968,26 @@ extern "C" int cfm_towers_fwd(const cfm_tower_t* towers, int64_t n_towers, int64
     for (int i = 0; i < n_towers; ++i) { int rc = validate_tower(towers[i]); if (rc) return rc; }
     static bool attr_set = false;
     if (!attr_set) {
-        CFM_CHECK_CUDA(cudaFuncSetAttribute(tower_fwd_stage<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
-        CFM_CHECK_CUDA(cudaFuncSetAttribute(tower_fwd_stage<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
+        CFM_CHECK_CUDA(cudaFuncSetAttribute(tower_fwd_stage<true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
+        CFM_CHECK_CUDA(cudaFuncSetAttribute(tower_fwd_stage<false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
         attr_set = true;
     }
     const bool exact = towers[0].precision == 0;
-    const long long ntiles = (B + TM - 1) / TM;
-    const int ctas = (int)std::min<long long>(ntiles, tower_ctas());
     for (int s = 1; s <= 3; ++s) {
         FwdArgs a{};
         a.B = B; a.err = err_flag;
-        size_t smem = 0;
+        size_t smem = 0, smem32 = 0;
         bool any_stats = false;
+        for (int i = 0; i < n_towers; ++i) {
+            smem = std::max(smem, fwd_smem_bytes(towers[i], s, 64));
+            smem32 = std::max(smem32, fwd_smem_bytes(towers[i], s, 32));
+        }
+        // forward stays at 64-row tiles: with 32 rows every warp would reload the whole A tile for one n-tile of
+        // output (measured: no gain), and the statistics partials would double
+        (void)smem32; (void)pick_tm;
+        a.tm = 64;
+        const long long ntiles = (B + a.tm - 1) / a.tm;
+        const int ctas = (int)std::min<long long>(ntiles, tower_ctas(a.tm));
         for (int i = 0; i < n_towers; ++i) {
             const cfm_tower_t& t = towers[i];
             FwdStage& S = a.st[i];
@@ -975,16 +999,15 @@ extern "C" int cfm_towers_fwd(const cfm_tower_t* towers, int64_t n_towers, int64
             bool bn_after = s == 1 || (s == 2 && t.bn2);
             S.stat_part = (training && bn_after) ? t.scratch : nullptr;
             any_stats |= S.stat_part != nullptr;
-            size_t need = fwd_smem_bytes(t, s);
+            size_t need = fwd_smem_bytes(t, s, a.tm);
             CFM_REQUIRE(need <= (size_t)MAX_SMEM, CFM_ERR_UNSUPPORTED,
                         "tower stage %d needs %zu B shared memory (> %d): layer %dx%d too large", s, need, MAX_SMEM,
                         S.N, S.in.K);
-            smem = std::max(smem, need);
         }
         {
             ProfScope prof(PROF_FWD1 + s - 1, stream);
-            if (exact) tower_fwd_stage<true><<<dim3(ctas, (unsigned)n_towers), NT, smem, stream>>>(a);
-            else tower_fwd_stage<false><<<dim3(ctas, (unsigned)n_towers), NT, smem, stream>>>(a);
+            if (exact) tower_fwd_stage<true, 64><<<dim3(ctas, (unsigned)n_towers), NT, smem, stream>>>(a);
+            else tower_fwd_stage<false, 64><<<dim3(ctas, (unsigned)n_towers), NT, smem, stream>>>(a);
         }
         CFM_LAUNCH_CHECK();
         if (any_stats) {
@@ -1014,12 +1037,20 @@ extern "C" int cfm_towers_fwd(const cfm_tower_t* towers, int64_t n_towers, int64
 static int launch_bwd(const BwdArgs& a, int ctas, int n_towers, size_t smem, bool exact, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        CFM_CHECK_CUDA(cudaFuncSetAttribute(tower_bwd_stage<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
-        CFM_CHECK_CUDA(cudaFuncSetAttribute(tower_bwd_stage<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
+        CFM_CHECK_CUDA(cudaFuncSetAttribute(tower_bwd_stage<true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
+        CFM_CHECK_CUDA(cudaFuncSetAttribute(tower_bwd_stage<false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
+        CFM_CHECK_CUDA(cudaFuncSetAttribute(tower_bwd_stage<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
+        CFM_CHECK_CUDA(cudaFuncSetAttribute(tower_bwd_stage<false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_SMEM));
         attr_set = true;
     }
-    if (exact) tower_bwd_stage<true><<<dim3(ctas, (unsigned)n_towers), NT, smem, stream>>>(a);
-    else tower_bwd_stage<false><<<dim3(ctas, (unsigned)n_towers), NT, smem, stream>>>(a);
+    const dim3 grid(ctas, (unsigned)n_towers);
+    if (a.tm == 32) {
+        if (exact) tower_bwd_stage<true, 32><<<grid, NT, smem, stream>>>(a);
+        else tower_bwd_stage<false, 32><<<grid, NT, smem, stream>>>(a);
+    } else {
+        if (exact) tower_bwd_stage<true, 64><<<grid, NT, smem, stream>>>(a);
+        else tower_bwd_stage<false, 64><<<grid, NT, smem, stream>>>(a);
+    }
     CFM_LAUNCH_CHECK();
     return CFM_OK;
 }
@@ -1038,14 +1069,23 @@ extern "C" int cfm_towers_bwd(const cfm_tower_t* towers, const cfm_tower_grads_t
                         g.dy2, CFM_ERR_INVALID, "null gradient buffer");
         CFM_REQUIRE(!towers[i].bn2 || (g.dbn2_w && g.dbn2_b), CFM_ERR_INVALID, "null bn2 gradient buffer");
     }
-    const long long ntiles = (B + TM - 1) / TM;
-    const int ctas = (int)std::min<long long>(ntiles, tower_ctas());
     for (int s = 3; s >= 1; --s) {
         BwdArgs a{};
         a.B = B;
-        size_t smem = 0;
+        size_t smem = 0, smem32 = 0;
         int max_groups = 0;
         bool any_sums = false;
+        for (int i = 0; i < n_towers; ++i) {
+            const cfm_tower_t& t = towers[i];
+            const bool a_bn_i = s >= 2 && (s == 2 || t.bn2);         // BN precedes this stage's input activation
+            const bool need_dx_i = s > 1 || grads[i].dx_emb || grads[i].dx_num;
+            smem = std::max(smem, bwd_smem_bytes(t, s, a_bn_i, need_dx_i, 64));
+            smem32 = std::max(smem32, bwd_smem_bytes(t, s, a_bn_i, need_dx_i, 32));
+        }
+        a.tm = pick_tm(smem, smem32);
+        const long long ntiles = (B + a.tm - 1) / a.tm;
+        const int ctas = (int)std::min<long long>(ntiles, tower_ctas(a.tm));
+        smem = 0;
         for (int i = 0; i < n_towers; ++i) {
             const cfm_tower_t& t = towers[i];
             const cfm_tower_grads_t& g = grads[i];
@@ -1073,7 +1113,7 @@ extern "C" int cfm_towers_bwd(const cfm_tower_t* towers, const cfm_tower_grads_t
             S.dx_num = s == 1 ? g.dx_num : nullptr;
             S.need_dx = s > 1 || g.dx_emb || g.dx_num;
             any_sums |= S.a_bn != 0;
-            size_t need = bwd_smem_bytes(t, s, S.a_bn, S.need_dx);
+            size_t need = bwd_smem_bytes(t, s, S.a_bn, S.need_dx, a.tm);
             CFM_REQUIRE(need <= (size_t)MAX_SMEM, CFM_ERR_UNSUPPORTED,
                         "tower bwd stage %d needs %zu B shared memory (> %d)", s, need, MAX_SMEM);
             smem = std::max(smem, need);

@@ -4,7 +4,7 @@
 
 namespace cfm {
 
-constexpr int TM = 64;    // rows per tile
+constexpr int TM = 64;    // rows per tile (maximum; the widest stage runs 32-row tiles so two CTAs fit one SM)
 constexpr int NT = 256;   // threads per CTA
 constexpr float BN_EPS = 1e-5f;
 constexpr int MAX_SMEM = 227 * 1024;
@@ -48,7 +48,8 @@ __host__ __device__ inline MmaPlan make_plan(int n) {
     return p;
 }
 __host__ __device__ inline int pass_cols(int n, int pass) { return min(128, n - pass * 128); }
-__host__ __device__ inline int pass_ni(int cols) { return cols <= 32 ? 1 : cols <= 64 ? 2 : 4; }
+// n-tiles of 8 columns per warp so that `wc` column groups of warps cover `cols` (<= 128) columns
+__host__ __device__ inline int pass_ni(int cols, int wc) { return cols <= 8 * wc ? 1 : cols <= 16 * wc ? 2 : 4; }
 __host__ __device__ inline int ceil8(int k) { return (k + 7) & ~7; }
 // leading dimension for "transposed" fragment loads (lanes walk rows with t, columns with g): ld == 8 (mod 32)
 __host__ __device__ inline int pad_ld_t(int k) { int ld = (ceil8(k) + 31) & ~31; return ld + 8; }
@@ -65,6 +66,7 @@ struct FwdArgs {
     FwdStage st[2];
     long long B;
     int* err;
+    int tm;               // rows per tile: 64 (2 row groups x 4 column groups of warps) or 32 (1 x 8)
 };
 
 struct BwdStage {
@@ -86,6 +88,7 @@ struct BwdStage {
 struct BwdArgs {
     BwdStage st[2];
     long long B;
+    int tm;               // rows per tile, see FwdArgs
 };
 
 
