@@ -323,8 +323,12 @@ __device__ __forceinline__ void fwd_pass(const FwdCtx& C, int pass, int cols, lo
                     for (int ni = 0; ni < NI; ++ni) {
                         const int c = n0 + ni * 8 + 2 * t;
                         float* dst = C.hout + (size_t)(row0 + r) * C.N + c;
-                        if (c < C.N) dst[0] = acc[mi][ni][2 * h];
-                        if (c + 1 < C.N) dst[1] = acc[mi][ni][2 * h + 1];
+                        if (c + 1 < C.N && !(C.N & 1)) {
+                            *reinterpret_cast<float2*>(dst) = make_float2(acc[mi][ni][2 * h], acc[mi][ni][2 * h + 1]);
+                        } else {
+                            if (c < C.N) dst[0] = acc[mi][ni][2 * h];
+                            if (c + 1 < C.N) dst[1] = acc[mi][ni][2 * h + 1];
+                        }
                     }
                 }
             }
@@ -539,22 +543,40 @@ __device__ __forceinline__ void bwd_dx_pass(const BwdStage& S, const BwdCtx& C, 
                 const int r = wr * 32 + mi * 16 + g + 8 * h;
                 if (r < rows_valid) {
 #pragma unroll
-                    for (int ni = 0; ni < NI; ++ni)
+                    for (int ni = 0; ni < NI; ++ni) {
+                        // the two columns a thread owns are adjacent: one 8-byte store each, so a warp's store
+                        // instruction fills whole 32-byte sectors (8 rows x 4 lanes x 8 B)
+                        const int c0 = k0 + ni * 8 + 2 * t;
+                        float v0 = acc[mi][ni][2 * h], v1 = acc[mi][ni][2 * h + 1];
+                        if (C.stage1) {
+                            if (c0 + 1 < C.KE && !(C.KE & 1)) {
+                                if (S.dx_emb)
+                                    *reinterpret_cast<float2*>(S.dx_emb + (size_t)(row0 + r) * C.KE + c0) = make_float2(v0, v1);
+                            } else {
 #pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            const int c = k0 + ni * 8 + 2 * t + e;
-                            const float v = acc[mi][ni][2 * h + e];
-                            if (c < C.K) {
-                                if (C.stage1) {
+                                for (int e = 0; e < 2; ++e) {
+                                    const int c = c0 + e;
+                                    const float v = e ? v1 : v0;
+                                    if (c >= C.K) continue;
                                     if (c < C.KE) { if (S.dx_emb) S.dx_emb[(size_t)(row0 + r) * C.KE + c] = v; }
                                     else if (S.dx_num) S.dx_num[(size_t)(row0 + r) * C.n_num + (c - C.KE)] = v;
-                                } else {
-                                    const float dy = C.As[r * C.lda + c] > 0.f ? v * C.inv_keep : 0.f;
-                                    S.dy_out[(size_t)(row0 + r) * C.K + c] = dy;
-                                    if (S.a_bn) { s1[ni][e] += dy; s2[ni][e] = fmaf(dy, C.Xh[r * C.ldxh + c], s2[ni][e]); }
                                 }
                             }
+                        } else {
+                            float dy[2] = {0.f, 0.f};
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const int c = c0 + e;
+                                if (c < C.K) {
+                                    dy[e] = C.As[r * C.lda + c] > 0.f ? (e ? v1 : v0) * C.inv_keep : 0.f;
+                                    if (S.a_bn) { s1[ni][e] += dy[e]; s2[ni][e] = fmaf(dy[e], C.Xh[r * C.ldxh + c], s2[ni][e]); }
+                                }
+                            }
+                            float* dst = S.dy_out + (size_t)(row0 + r) * C.K + c0;
+                            if (c0 + 1 < C.K && !(C.K & 1)) *reinterpret_cast<float2*>(dst) = make_float2(dy[0], dy[1]);
+                            else { if (c0 < C.K) dst[0] = dy[0]; if (c0 + 1 < C.K) dst[1] = dy[1]; }
                         }
+                    }
                 }
             }
     }
