@@ -30,7 +30,10 @@ __host__ __device__ inline FwdSmem fwd_smem(int K, int N, int n_tab, const MmaPl
     s.ws = o; o += gp.wrows * s.lda;
     s.as = o; o += tm * s.lda;
     s.bn = o; o += stage1 ? 0 : 4 * ((K + 3) & ~3);
-    s.red = o; o += (tm / 4) * 128;
+    // single-pass layers: the statistics scratch aliases the input tile (dead once every warp has left the MMAs);
+    // with several column passes the tile is still needed, so the scratch gets its own space
+    if (gp.passes == 1) s.red = s.as;
+    else { s.red = o; o += (tm / 4) * 128; }
     s.tmean = o; o += 128;
     s.rmean = o; o += gp.wrows + 128;
     s.rm2 = o; o += gp.wrows + 128;
@@ -334,6 +337,7 @@ __device__ __forceinline__ void fwd_pass(const FwdCtx& C, int pass, int cols, lo
             }
     }
     if (!C.stats) return;
+    __syncthreads();   // `red` lives in the input tile: every warp must be done reading it
     // pass A: tile mean per column.  red[(wr*8+g)][local column]: 16 partial rows per column
     float* myred = C.red + (wr * 8 + g) * 128 + wc * 8 * NI + 2 * t;
     if (active) {
@@ -1006,10 +1010,13 @@ extern "C" int cfm_towers_fwd(const cfm_tower_t* towers, int64_t n_towers, int64
         }
         // forward stays at 64-row tiles: with 32 rows every warp would reload the whole A tile for one n-tile of
         // output (measured: no gain), and the statistics partials would double
-        (void)smem32; (void)pick_tm;
+        (void)smem32;
         a.tm = 64;
         const long long ntiles = (B + a.tm - 1) / a.tm;
-        const int ctas = (int)std::min<long long>(ntiles, tower_ctas(a.tm));
+        // a stage whose CTAs fit exactly twice per SM gets two persistent CTAs per SM and tower, so that the SM keeps
+        // 16 warps while one tower's CTAs run (both towers' grids are otherwise resident one after the other)
+        const bool two = smem > 76 * 1024 && smem <= 113 * 1024;
+        const int ctas = (int)std::min<long long>(ntiles, two ? tower_ctas(32) : tower_ctas(64));
         for (int i = 0; i < n_towers; ++i) {
             const cfm_tower_t& t = towers[i];
             FwdStage& S = a.st[i];
