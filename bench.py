@@ -295,7 +295,7 @@ def secondary_metrics(device, world, rank, dist):
 
     warm = score_topk(ceos[:4096], firms[:65536], k, scale)
     del warm
-    ms = _time_cuda(topk_step, 1, dist, device)
+    ms = _time_cuda(topk_step, 2, dist, device)      # best of 2: the first full-size call also pays the cudaMallocs
     flops = 2.0 * Nall * Nall * Dl
     out["allpairs_top100"] = {"workload": "config5: 1M CEOs x 1M firms, D=60, top-100 per CEO, exact fp64 rescoring",
                               "ms": ms, "value": float(Nall) * Nall / (ms * 1e-3), "unit": "scores/s",
