@@ -469,7 +469,7 @@ def gpu_arm(args):
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, per launch, from the committed
                 # `ncu --set full` capture at this exact shape (profiles/r01_ncu_full_summary.md)
-                "traffic": {"bwd1": 256.2e6, "fwd1": 141.5e6}.get(dom), "traffic_unit": "bytes per launch",
+                "traffic": {"bwd1": 263.0e6, "fwd1": 141.8e6}.get(dom), "traffic_unit": "bytes per launch",
                 "algorithmic_bytes_per_launch": dom_bytes,
                 "kernel": "tower_%s_stage" % ("bwd" if dom.startswith("bwd") else "fwd"),
                 "slot": dom, "peak_source": peak_src, "kernel_ms": per_kernel[dom], "kernel_share_of_step": shares,
