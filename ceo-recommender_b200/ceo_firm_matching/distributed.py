@@ -469,7 +469,10 @@ class _GlobalInfoNCEFn(torch.autograd.Function):
         b_total = n * world
         off = rank * n
         fb, cb = backend.pack(firm_local), backend.pack(ceo_local)
-        fb_all, cb_all = gather_rows(fb, group), gather_rows(cb, group)
+        # ONE all-gather for both sides (the collectives are latency-bound at these sizes): [world, 2, n, Dp]
+        both = gather_rows(torch.stack([fb, cb]).unsqueeze(0), group)
+        fb_all = both[:, 0].reshape(world * n, -1)
+        cb_all = both[:, 1].reshape(world * n, -1)
         rs_f, diag = backend.rowsum(fb, cb_all, temperature, off, True)        # row sums of S   for my firm rows
         rs_c, _ = backend.rowsum(cb, fb_all, temperature, off, False)          # row sums of S^T for my CEO rows
         loss = backend.local_loss(rs_f, rs_c, diag, temperature, b_total)
@@ -482,7 +485,10 @@ class _GlobalInfoNCEFn(torch.autograd.Function):
     def backward(ctx, g_loss):
         fb, cb, fb_all, cb_all, rs_f, rs_c, diag = ctx.saved
         temperature, d, off, b_total, group, backend, dtype = ctx.meta
-        rs_f_all, rs_c_all = gather_rows(rs_f, group), gather_rows(rs_c, group)
+        world, n = dist.get_world_size(group), rs_f.shape[0]
+        rs_both = gather_rows(torch.stack([rs_f, rs_c]).unsqueeze(0), group)    # one all-gather: [world, 2, n]
+        rs_f_all = rs_both[:, 0].reshape(world * n)
+        rs_c_all = rs_both[:, 1].reshape(world * n)
         g = g_loss.contiguous().float()
         d_firm = backend.grad(fb, cb_all, d, temperature, off, b_total, rs_f, rs_c_all, diag, g)
         d_ceo = backend.grad(cb, fb_all, d, temperature, off, b_total, rs_c, rs_f_all, diag, g)

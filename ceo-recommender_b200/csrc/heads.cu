@@ -154,11 +154,104 @@ __global__ void __launch_bounds__(HEAD_NT) cosine_head_kernel(const CosArgs a) {
     }
 }
 
+// D % 4 == 0, D <= 128: LPR lanes per row (16 for D <= 64, else 32), one float4 per lane, so a warp covers 32/LPR rows
+// with 16-byte accesses and log2(LPR) shuffle steps per reduction.  Same arithmetic as cosine_head_kernel.
+__device__ __forceinline__ float dot4(const float4& a, const float4& b) {
+    return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
+}
+template <int LPR>
+__global__ void __launch_bounds__(HEAD_NT) cosine_head_kernel_v4(const CosArgs a) {
+    constexpr int RPW = 32 / LPR;
+    const int lane = threadIdx.x & 31, sub = lane / LPR, q = lane % LPR;
+    const long long wbase = ((long long)blockIdx.x * (HEAD_NT / 32) + (threadIdx.x >> 5)) * RPW;
+    const long long wstride = (long long)gridDim.x * (HEAD_NT / 32) * RPW;
+    const int D4 = a.D >> 2;
+    const bool on = q < D4;
+    const float scale = expf(a.logit_scale[0]);
+    float acc[2] = {0.f, 0.f};   // [0] loss, [1] d_logit_scale
+    const float gl = (a.mode == 2 && a.g_loss) ? a.g_loss[0] : 1.f;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long long rb = wbase; rb < a.B; rb += wstride) {
+        const long long r = rb + sub;
+        const bool live = r < a.B, ld = live && on;
+        const float4 ue = ld ? *(reinterpret_cast<const float4*>(a.u + r * a.D) + q) : z4;
+        const float4 ve = ld ? *(reinterpret_cast<const float4*>(a.v + r * a.D) + q) : z4;
+        float nu2 = dot4(ue, ue), nv2 = dot4(ve, ve), dot = dot4(ue, ve);
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) {
+            nu2 += __shfl_xor_sync(FULL, nu2, o);
+            nv2 += __shfl_xor_sync(FULL, nv2, o);
+            dot += __shfl_xor_sync(FULL, dot, o);
+        }
+        const float nu = sqrtf(nu2), nv = sqrtf(nv2);
+        const bool cl_u = a.eps > 0.f && nu < a.eps, cl_v = a.eps > 0.f && nv < a.eps;   // F.normalize clamp
+        const float inu = 1.f / (cl_u ? a.eps : nu), inv = 1.f / (cl_v ? a.eps : nv);
+        const float s = scale * (dot * inu * inv);
+        const float4 uh = make_float4(ue.x * inu, ue.y * inu, ue.z * inu, ue.w * inu);
+        const float4 vh = make_float4(ve.x * inv, ve.y * inv, ve.z * inv, ve.w * inv);
+        if (a.mode == 0) {
+            if (live && q == 0) {
+                a.score[r] = s;
+                if (a.target) { float diff = s - a.target[r]; acc[0] += a.weights[r] * diff * diff; }
+            }
+            if (ld) {
+                if (a.u_hat) *(reinterpret_cast<float4*>(a.u_hat + r * a.D) + q) = uh;
+                if (a.v_hat) *(reinterpret_cast<float4*>(a.v_hat + r * a.D) + q) = vh;
+            }
+            continue;
+        }
+        float ds = 0.f;
+        if (live) {
+            if (a.mode == 2) {
+                ds = 2.f * a.weights[r] * (s - a.target[r]) * gl / (float)a.B;   // d mean(w (s-t)^2) / ds
+                if (a.d_score) ds += a.d_score[r];
+            } else {
+                ds = a.d_score ? a.d_score[r] : 0.f;
+            }
+        }
+        if (live && q == 0) acc[1] += ds * s;
+        // g wrt u_hat = ds*scale*v_hat + d_uhat ; du = (g - u_hat (u_hat . g)) / |u|   (or g/eps when clamped)
+        const float k = ds * scale;
+        const float4 eu = (a.d_uhat && ld) ? *(reinterpret_cast<const float4*>(a.d_uhat + r * a.D) + q) : z4;
+        const float4 ev = (a.d_vhat && ld) ? *(reinterpret_cast<const float4*>(a.d_vhat + r * a.D) + q) : z4;
+        const float4 gu = make_float4(fmaf(k, vh.x, eu.x), fmaf(k, vh.y, eu.y), fmaf(k, vh.z, eu.z), fmaf(k, vh.w, eu.w));
+        const float4 gv = make_float4(fmaf(k, uh.x, ev.x), fmaf(k, uh.y, ev.y), fmaf(k, uh.z, ev.z), fmaf(k, uh.w, ev.w));
+        float pu = dot4(uh, gu), pv = dot4(vh, gv);
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) {
+            pu += __shfl_xor_sync(FULL, pu, o);
+            pv += __shfl_xor_sync(FULL, pv, o);
+        }
+        if (ld) {
+            const float4 du = cl_u ? make_float4(gu.x * inu, gu.y * inu, gu.z * inu, gu.w * inu)
+                                   : make_float4((gu.x - uh.x * pu) * inu, (gu.y - uh.y * pu) * inu,
+                                                 (gu.z - uh.z * pu) * inu, (gu.w - uh.w * pu) * inu);
+            const float4 dv = cl_v ? make_float4(gv.x * inv, gv.y * inv, gv.z * inv, gv.w * inv)
+                                   : make_float4((gv.x - vh.x * pv) * inv, (gv.y - vh.y * pv) * inv,
+                                                 (gv.z - vh.z * pv) * inv, (gv.w - vh.w * pv) * inv);
+            *(reinterpret_cast<float4*>(a.du + r * a.D) + q) = du;
+            *(reinterpret_cast<float4*>(a.dv + r * a.D) + q) = dv;
+        }
+    }
+    if (a.mode != 0 || a.loss) {
+        float* const outs[2] = {a.loss, a.d_logit_scale};
+        const float sc[2] = {1.f / (float)a.B, 1.f};
+        cta_reduce_finish<2>(acc, a.partial, outs, sc);
+    }
+}
+
 static int launch_cosine(const CosArgs& a, cudaStream_t stream) {
     CFM_REQUIRE(a.B >= 1 && a.D >= 1 && a.D <= 256, CFM_ERR_UNSUPPORTED, "cosine head supports 1 <= D <= 256 (got %d)", a.D);
     int ctas = (int)std::min<long long>((a.B + HEAD_NT / 32 - 1) / (HEAD_NT / 32), HEAD_MAX_CTAS);
     ProfScope prof(PROF_HEAD, stream);
-    if (a.D <= 64) cosine_head_kernel<2><<<ctas, HEAD_NT, 0, stream>>>(a);
+    const bool al16 = (((uintptr_t)a.u | (uintptr_t)a.v | (uintptr_t)a.du | (uintptr_t)a.dv | (uintptr_t)a.u_hat |
+                        (uintptr_t)a.v_hat | (uintptr_t)a.d_uhat | (uintptr_t)a.d_vhat) & 15) == 0;
+    if ((a.D & 3) == 0 && a.D <= 128 && al16) {
+        const int rpw = a.D <= 64 ? 2 : 1, wpc = HEAD_NT / 32;
+        ctas = (int)std::min<long long>((a.B + (long long)wpc * rpw - 1) / ((long long)wpc * rpw), HEAD_MAX_CTAS);
+        if (a.D <= 64) cosine_head_kernel_v4<16><<<ctas, HEAD_NT, 0, stream>>>(a);
+        else cosine_head_kernel_v4<32><<<ctas, HEAD_NT, 0, stream>>>(a);
+    } else if (a.D <= 64) cosine_head_kernel<2><<<ctas, HEAD_NT, 0, stream>>>(a);
     else if (a.D <= 128) cosine_head_kernel<4><<<ctas, HEAD_NT, 0, stream>>>(a);
     else cosine_head_kernel<8><<<ctas, HEAD_NT, 0, stream>>>(a);
     CFM_LAUNCH_CHECK();
