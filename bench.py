@@ -376,9 +376,9 @@ def gpu_arm(args):
             eager_step(model, None, batches[i % n_data])
         torch.cuda.synchronize()
     launches = int(lib.cfm_launch_count(0)) // n_prof * args.steps
-    prof_ms = (C.c_double * 13)()
-    prof_n = (C.c_int64 * 13)()
-    N.check(lib.cfm_profile_read(prof_ms, prof_n, 13))
+    prof_ms = (C.c_double * 14)()
+    prof_n = (C.c_int64 * 14)()
+    N.check(lib.cfm_profile_read(prof_ms, prof_n, 14))
     lib.cfm_profile_enable(0)
     model.zero_grad_fast()
     prof_step_ms = sum(prof_ms) / n_prof
@@ -460,7 +460,7 @@ def gpu_arm(args):
     # ---- roofline of the dominant kernel (stage-1 backward: dW1 + dX + embedding-row gradients) ----
     peak, peak_src = peaks()
     slots = ["fwd1", "fwd2", "fwd3", "bwd1", "bwd2", "bwd3", "head", "emb_grad", "reduce", "nce_rowsum", "nce_grad",
-             "topk", "topk_post"]
+             "topk", "topk_post", "adam"]
     per_kernel = {s: (prof_ms[i] / prof_n[i] if prof_n[i] else None) for i, s in enumerate(slots)}
     shares = {s: round(prof_ms[i] / n_prof / ms_step, 4) for i, s in enumerate(slots) if prof_n[i]}
     dom = max((s for s in slots if per_kernel[s]), key=lambda s: prof_ms[slots.index(s)])

@@ -68,6 +68,12 @@ class PeerTable(C.Structure):
     ]
 
 
+class AdamTensor(C.Structure):
+    """Mirror of ``cfm_adam_tensor_t``."""
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("numel", i64)]
+
+
 class PeerGroup(C.Structure):
     """Mirror of ``cfm_peer_group_t``."""
     _fields_ = [("owned", C.POINTER(PeerTable)), ("n_owned", i64), ("emb_dim", i64), ("width", i64)]
@@ -100,6 +106,7 @@ PROTOTYPES = {
     "cfm_emb_gather_rows": (C.c_int, [_V, _I, _I, _I, _I, C.POINTER(C.c_void_p), C.POINTER(i64), _V, _V, _V]),
     "cfm_emb_grad_peer_reduce": (C.c_int, [C.POINTER(PeerGroup), _I, _I, _I, _I, _V, _V, _V, _V, _V, _I, _V]),
     "cfm_emb_grad_peer_rezero": (C.c_int, [C.POINTER(PeerGroup), _I, _I, _I, _V, _V]),
+    "cfm_adam_step": (C.c_int, [C.POINTER(AdamTensor), _I, _V, _D, _D, _D, _D, _I, _V]),
     "cfm_cosine_head_fwd": (C.c_int, [_V, _V, _V, _I, _I, _D, _V, _V, _V, _V, _V, _V, _V, _V]),
     "cfm_cosine_head_bwd": (C.c_int, [_V, _V, _V, _V, _V, _V, _V, _V, _V, _I, _I, _D, _V, _V, _V, _V, _V]),
     "cfm_structural_head": (C.c_int, [_V, _V, _V, _V, _V, _V, _I, _D, _V, _V, _V, _V, _V, _V]),

@@ -3,7 +3,8 @@
 ``train_model(train_loader, val_loader, metadata, config)`` keeps the reference signature, prints and
 returned object (``ceo_firm_matching/training.py:15-64``).  Underneath, each step is the fused CUDA path:
 towers forward -> cosine head + weighted MSE -> head backward -> towers backward -> deterministic
-embedding-gradient segment reduce, followed by ``torch.optim.Adam`` (kept as the optimiser surface).
+embedding-gradient segment reduce, followed by the fused Adam step (``optim.FusedAdam``: torch.optim.Adam's state and
+arithmetic in one launch).
 Steps with a fixed batch shape are captured once into a CUDA graph and replayed (``GraphedTwoTowerStep``),
 which removes the per-step Python / launch overhead that dominates at the reference's batch sizes; the
 per-step ``loss.item()`` synchronisation of the reference is replaced by a device-side accumulator read once
@@ -102,9 +103,11 @@ def eager_step(model: CEOFirmMatcher, optimizer: Optional[torch.optim.Optimizer]
     return loss.detach()
 
 
-def _make_optimizer(model: CEOFirmMatcher, lr: float) -> optim.Adam:
-    # capturable=True keeps Adam's step counter on the device so the update can live inside the CUDA graph
-    return optim.Adam(model.parameters(), lr=lr, capturable=True)
+def _make_optimizer(model: CEOFirmMatcher, lr: float) -> optim.Optimizer:
+    # optim.Adam(lr) of training.py:32 as ONE fused launch over all parameter tensors: bit-equal to
+    # torch.optim.Adam(capturable=True), step counter on the device so the update lives inside the CUDA graph
+    from .optim import FusedAdam
+    return FusedAdam(model.parameters(), lr=lr)
 
 
 def train_model(train_loader: DataLoader, val_loader: DataLoader, metadata: Dict[str, int],

@@ -47,7 +47,7 @@ int sm_count();   // cached cudaDevAttrMultiProcessorCount of the current device
 void count_launch();
 enum ProfSlot {
     PROF_FWD1 = 0, PROF_FWD2, PROF_FWD3, PROF_BWD1, PROF_BWD2, PROF_BWD3, PROF_HEAD, PROF_EMB, PROF_REDUCE,
-    PROF_NCE_ROWSUM, PROF_NCE_GRAD, PROF_TOPK, PROF_TOPK_POST, PROF_SLOTS
+    PROF_NCE_ROWSUM, PROF_NCE_GRAD, PROF_TOPK, PROF_TOPK_POST, PROF_ADAM, PROF_SLOTS
 };
 struct ProfScope {   // records a cudaEvent pair around the launches in its lifetime when profiling is on
     int idx;

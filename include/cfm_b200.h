@@ -44,7 +44,7 @@ int cfm_device_info(int64_t* sm_count, int64_t* cc_major, int64_t* cc_minor, int
 /* Bench aids.  cfm_launch_count: kernels this library has launched (optionally reset).
  * cfm_profile_enable(1): bracket every kernel family with cudaEvents on its stream; cfm_profile_read
  * synchronises the device and returns summed milliseconds and launch counts per CFM_PROF_* slot. */
-#define CFM_PROF_SLOTS 13
+#define CFM_PROF_SLOTS 14
 int64_t cfm_launch_count(int64_t reset);
 int cfm_profile_enable(int64_t on);
 int cfm_profile_read(double* ms /* [CFM_PROF_SLOTS] host */, int64_t* counts /* host */, int64_t n_slots);
@@ -209,6 +209,24 @@ int cfm_emb_grad_peer_reduce(const cfm_peer_group_t* groups /* host */, int64_t 
                              int32_t* vals_sorted, void* sort_tmp, int64_t sort_tmp_bytes, void* stream);
 int cfm_emb_grad_peer_rezero(const cfm_peer_group_t* groups /* host */, int64_t n_groups, int64_t n_peers, int64_t B,
                              const int64_t* keys_sorted, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused dense Adam step over all tensors of a model in one launch.
+ * replaces: torch.optim.Adam(capturable=True) as used by training.py:32,55 - same arithmetic, operation by
+ * operation (torch/optim/adam.py::_multi_tensor_adam, capturable branch), one pass instead of ~12.
+ *   tensors: HOST array of records (they travel as kernel parameters: no descriptor memory, graph-capturable)
+ *   step   : device fp32 scalar, incremented by the call before use (torch's state["step"])
+ *   variant: 0 (contraction pattern bit-equal to torch's kernels); 1..3 exist for the differential test
+ * ------------------------------------------------------------------------------------------ */
+typedef struct cfm_adam_tensor {
+    float* param;
+    const float* grad;
+    float* exp_avg;
+    float* exp_avg_sq;
+    int64_t numel;
+} cfm_adam_tensor_t;
+int cfm_adam_step(const cfm_adam_tensor_t* tensors /* host */, int64_t n_tensors, float* step, double lr, double beta1,
+                  double beta2, double eps, int64_t variant, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Cosine head: L2-normalise both latents, row-wise dot, times exp(logit_scale).

@@ -8,8 +8,8 @@ def prof(label, fn, reps=3):
     fn(); torch.cuda.synchronize()
     lib.cfm_profile_enable(1)
     for _ in range(reps): fn()
-    ms = (C.c_double * 13)(); n = (C.c_int64 * 13)()
-    N.check(lib.cfm_profile_read(ms, n, 13)); lib.cfm_profile_enable(0)
+    ms = (C.c_double * 14)(); n = (C.c_int64 * 14)()
+    N.check(lib.cfm_profile_read(ms, n, 14)); lib.cfm_profile_enable(0)
     names = ["fwd1","fwd2","fwd3","bwd1","bwd2","bwd3","head","emb","reduce","nce_rowsum","nce_grad","topk","topk_post"]
     print(label, {names[i]: round(ms[i]/n[i], 3) for i in range(13) if n[i]})
 B, D = 65536, 128

@@ -19,8 +19,8 @@ with torch.cuda.stream(side):
     for i in range(10):
         eager_step(model, None, batches[i % 8])
     torch.cuda.synchronize()
-ms = (C.c_double * 13)(); n = (C.c_int64 * 13)()
-N.check(lib.cfm_profile_read(ms, n, 13)); lib.cfm_profile_enable(0)
+ms = (C.c_double * 14)(); n = (C.c_int64 * 14)()
+N.check(lib.cfm_profile_read(ms, n, 14)); lib.cfm_profile_enable(0)
 print(prec, {k: round(ms[i] / 10, 4) for i, k in enumerate(names)}, "sum", round(sum(ms) / 10, 4))
 model.zero_grad_fast()
 runner = GraphedTwoTowerStep(model, batches[0], optimizer=None, warmup=3)

@@ -14,8 +14,8 @@ def prof(model, batches, side):
         for i in range(len(batches)):
             eager_step(model, None, batches[i])
     torch.cuda.synchronize()
-    ms = (C.c_double * 13)(); n = (C.c_int64 * 13)()
-    N.check(lib.cfm_profile_read(ms, n, 13))
+    ms = (C.c_double * 14)(); n = (C.c_int64 * 14)()
+    N.check(lib.cfm_profile_read(ms, n, 14))
     lib.cfm_profile_enable(0)
     return {k: ms[i] / max(n[i], 1) for i, k in enumerate(names)}
 

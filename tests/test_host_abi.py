@@ -46,6 +46,7 @@ def test_struct_mirrors_match_header_field_order():
     assert fields("cfm_peer_table") == [f[0] for f in _native.PeerTable._fields_]
     assert fields("cfm_emb_group") == [f[0] for f in _native.EmbGroup._fields_]
     assert fields("cfm_peer_group") == [f[0] for f in _native.PeerGroup._fields_]
+    assert fields("cfm_adam_tensor") == [f[0] for f in _native.AdamTensor._fields_]
 
 
 def test_modules_construct_on_cpu_and_refuse_cpu_forward():
