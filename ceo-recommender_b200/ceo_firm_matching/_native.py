@@ -106,7 +106,7 @@ PROTOTYPES = {
     "cfm_emb_gather_rows": (C.c_int, [_V, _I, _I, _I, _I, C.POINTER(C.c_void_p), C.POINTER(i64), _V, _V, _V]),
     "cfm_emb_grad_peer_reduce": (C.c_int, [C.POINTER(PeerGroup), _I, _I, _I, _I, _V, _V, _V, _V, _V, _I, _V]),
     "cfm_emb_grad_peer_rezero": (C.c_int, [C.POINTER(PeerGroup), _I, _I, _I, _V, _V]),
-    "cfm_adam_step": (C.c_int, [C.POINTER(AdamTensor), _I, _V, _D, _D, _D, _D, _I, _V]),
+    "cfm_adam_step": (C.c_int, [C.POINTER(AdamTensor), _I, _V, _I, _D, _D, _D, _D, _I, _V]),
     "cfm_cosine_head_fwd": (C.c_int, [_V, _V, _V, _I, _I, _D, _V, _V, _V, _V, _V, _V, _V, _V]),
     "cfm_cosine_head_bwd": (C.c_int, [_V, _V, _V, _V, _V, _V, _V, _V, _V, _I, _I, _D, _V, _V, _V, _V, _V]),
     "cfm_structural_head": (C.c_int, [_V, _V, _V, _V, _V, _V, _I, _D, _V, _V, _V, _V, _V, _V]),

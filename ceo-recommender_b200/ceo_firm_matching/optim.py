@@ -21,29 +21,37 @@ class FusedAdam(torch.optim.Optimizer):
                         capturable=True, differentiable=False, fused=None, decoupled_weight_decay=False)
         super().__init__(params, defaults)
         self.variant = variant
+        self._steps = {}                                # group index -> fp32 [n params] step counters
 
-    def _state_for(self, group, params: List[torch.Tensor]):
-        step = None
-        for p in group["params"]:                      # one device step counter per group, shared by its parameters
-            st = self.state.get(p)
-            if st and "step" in st:
-                step = st["step"]
-                break
+    def _state_for(self, group, params: List[torch.Tensor]) -> torch.Tensor:
+        """Lazily create the state and return the group's step counters: ONE contiguous fp32 vector, of which every
+        parameter's ``state["step"]`` is a distinct element (torch keeps a separate 0-dim tensor per parameter; after
+        ``load_state_dict`` those copies are packed into one vector again)."""
+        allp = group["params"]
+        gi = next(i for i, g in enumerate(self.param_groups) if g is group)
+        steps = self._steps.get(gi)
+        index = {id(p): i for i, p in enumerate(allp)}
+        packed = steps is not None and steps.numel() == len(allp) and all(
+            "step" not in self.state.get(p, {}) or
+            (self.state[p]["step"].dtype == torch.float32 and self.state[p]["step"].data_ptr() == steps.data_ptr() + 4 * i)
+            for i, p in enumerate(allp))
+        if not packed:
+            dev = params[0].device
+            new = torch.zeros(len(allp), dtype=torch.float32, device=dev)
+            known = [float(self.state[p]["step"]) for p in allp if "step" in self.state.get(p, {})]
+            if known:
+                new.fill_(max(known))
+            self._steps[gi] = steps = new
+            for i, p in enumerate(allp):
+                if "step" in self.state.get(p, {}):
+                    self.state[p]["step"] = steps[i]
         for p in params:
             st = self.state[p]
             if "exp_avg" not in st:
-                if step is None:
-                    step = torch.zeros((), dtype=torch.float32, device=p.device)
-                st["step"] = step
+                st["step"] = steps[index[id(p)]]
                 st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                 st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-            elif st["step"] is not step:                # after load_state_dict: re-alias the per-parameter copies
-                if st["step"].device != p.device or st["step"].dtype != torch.float32:
-                    st["step"] = st["step"].to(device=p.device, dtype=torch.float32)
-                if step is None:
-                    step = st["step"]
-                st["step"] = step
-        return step
+        return steps
 
     def _records(self, params: List[torch.Tensor]):
         arr = (N.AdamTensor * len(params))()
@@ -68,10 +76,10 @@ class FusedAdam(torch.optim.Optimizer):
             params = [p for p in group["params"] if p.grad is not None and p.numel() > 0]
             if not params:
                 continue
-            step = self._state_for(group, params)
+            steps = self._state_for(group, params)
             b1, b2 = group["betas"]
             with torch.cuda.device(params[0].device):
-                N.check(N.lib().cfm_adam_step(self._records(params), len(params), N.ptr(step), float(group["lr"]),
-                                              float(b1), float(b2), float(group["eps"]), self.variant,
-                                              N.stream_ptr()))
+                N.check(N.lib().cfm_adam_step(self._records(params), len(params), N.ptr(steps), steps.numel(),
+                                              float(group["lr"]), float(b1), float(b2), float(group["eps"]),
+                                              self.variant, N.stream_ptr()))
         return loss

@@ -52,7 +52,10 @@ __device__ __forceinline__ void adam_elem(float& p, float g, float& m, float& v,
     p = __fadd_rn(p, __fdiv_rn(m, d));
 }
 
-__global__ void adam_advance_step(float* step) { *step = __fadd_rn(*step, 1.f); }
+__global__ void adam_advance_step(float* step, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) step[i] = __fadd_rn(step[i], 1.f);
+}
 
 template <int VARIANT>
 __global__ void __launch_bounds__(ADAM_NT) adam_kernel(const __grid_constant__ AdamBatch B, const float* __restrict__ step,
@@ -72,10 +75,18 @@ __global__ void __launch_bounds__(ADAM_NT) adam_kernel(const __grid_constant__ A
         float* p = t.p + lo; const float* g = t.g + lo; float* m = t.m + lo; float* v = t.v + lo;
         const bool al = ((((uintptr_t)p) | ((uintptr_t)g) | ((uintptr_t)m) | ((uintptr_t)v)) & 15) == 0;
         const int n4 = al ? cnt >> 2 : 0;
-        for (int i = threadIdx.x; i < n4; i += ADAM_NT) {
+        // two float4 groups per thread and iteration: eight independent 16-byte loads in flight before the first use
+        for (int i = threadIdx.x; i < n4; i += 2 * ADAM_NT) {
+            const int j = i + ADAM_NT;
+            const bool two = j < n4;
             float4 p4 = reinterpret_cast<float4*>(p)[i], m4 = reinterpret_cast<float4*>(m)[i],
                    v4 = reinterpret_cast<float4*>(v)[i];
-            const float4 g4 = __ldg(reinterpret_cast<const float4*>(g) + i);
+            const float4 g4 = __ldcs(reinterpret_cast<const float4*>(g) + i);
+            float4 q4 = p4, n4v = m4, w4 = v4, h4 = g4;
+            if (two) {
+                q4 = reinterpret_cast<float4*>(p)[j]; n4v = reinterpret_cast<float4*>(m)[j];
+                w4 = reinterpret_cast<float4*>(v)[j]; h4 = __ldcs(reinterpret_cast<const float4*>(g) + j);
+            }
             adam_elem<VARIANT>(p4.x, g4.x, m4.x, v4.x, s, step_size, bc2_sqrt);
             adam_elem<VARIANT>(p4.y, g4.y, m4.y, v4.y, s, step_size, bc2_sqrt);
             adam_elem<VARIANT>(p4.z, g4.z, m4.z, v4.z, s, step_size, bc2_sqrt);
@@ -83,6 +94,15 @@ __global__ void __launch_bounds__(ADAM_NT) adam_kernel(const __grid_constant__ A
             reinterpret_cast<float4*>(p)[i] = p4;
             reinterpret_cast<float4*>(m)[i] = m4;
             reinterpret_cast<float4*>(v)[i] = v4;
+            if (two) {
+                adam_elem<VARIANT>(q4.x, h4.x, n4v.x, w4.x, s, step_size, bc2_sqrt);
+                adam_elem<VARIANT>(q4.y, h4.y, n4v.y, w4.y, s, step_size, bc2_sqrt);
+                adam_elem<VARIANT>(q4.z, h4.z, n4v.z, w4.z, s, step_size, bc2_sqrt);
+                adam_elem<VARIANT>(q4.w, h4.w, n4v.w, w4.w, s, step_size, bc2_sqrt);
+                reinterpret_cast<float4*>(p)[j] = q4;
+                reinterpret_cast<float4*>(m)[j] = n4v;
+                reinterpret_cast<float4*>(v)[j] = w4;
+            }
         }
         for (int i = 4 * n4 + threadIdx.x; i < cnt; i += ADAM_NT) {
             float pe = p[i], me = m[i], ve = v[i];
@@ -96,21 +116,21 @@ __global__ void __launch_bounds__(ADAM_NT) adam_kernel(const __grid_constant__ A
 
 using namespace cfm;
 
-// tensors: HOST array of n_tensors records {param, grad, exp_avg, exp_avg_sq, numel}; step: device fp32 scalar,
-// incremented first (torch: state["step"] += 1).  `variant` selects the contraction pattern of the two fused ATen
+// tensors: HOST array of n_tensors records {param, grad, exp_avg, exp_avg_sq, numel}; step: device fp32 [n_steps]
+// (torch keeps one state["step"] per parameter, all equal): every element is incremented first, element 0 is used.  `variant` selects the contraction pattern of the two fused ATen
 // functors (0 = bit-equal to torch 2.11's kernels; 1-3 for the differential test).
-extern "C" int cfm_adam_step(const cfm_adam_tensor_t* tensors, int64_t n_tensors, float* step, double lr, double beta1,
-                             double beta2, double eps, int64_t variant, void* stream_) {
+extern "C" int cfm_adam_step(const cfm_adam_tensor_t* tensors, int64_t n_tensors, float* step, int64_t n_steps, double lr,
+                             double beta1, double beta2, double eps, int64_t variant, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     CFM_REQUIRE(tensors && step, CFM_ERR_INVALID, "null pointer");
-    CFM_REQUIRE(n_tensors >= 1, CFM_ERR_INVALID, "bad sizes");
+    CFM_REQUIRE(n_tensors >= 1 && n_steps >= 1 && n_steps < (1 << 20), CFM_ERR_INVALID, "bad sizes");
     CFM_REQUIRE(lr > 0 && beta1 >= 0 && beta1 < 1 && beta2 >= 0 && beta2 < 1 && eps >= 0, CFM_ERR_INVALID,
                 "bad Adam hyper-parameters");
     CFM_REQUIRE(1.0 - beta1 < 0.5, CFM_ERR_UNSUPPORTED, "beta1 <= 0.5 takes ATen's other lerp branch (not implemented)");
     AdamScalars s;
     s.w1 = (float)(1.0 - beta1); s.beta2 = (float)beta2; s.w2 = (float)(1.0 - beta2); s.eps = (float)eps;
     s.inv_lr = (float)(1.0 / lr); s.beta1 = (float)beta1;
-    adam_advance_step<<<1, 1, 0, stream>>>(step);
+    adam_advance_step<<<(int)((n_steps + 255) / 256), 256, 0, stream>>>(step, (int)n_steps);
     CFM_LAUNCH_CHECK();
     for (int64_t t0 = 0; t0 < n_tensors; t0 += ADAM_MAX_T) {
         AdamBatch B;

@@ -215,7 +215,8 @@ int cfm_emb_grad_peer_rezero(const cfm_peer_group_t* groups /* host */, int64_t 
  * replaces: torch.optim.Adam(capturable=True) as used by training.py:32,55 - same arithmetic, operation by
  * operation (torch/optim/adam.py::_multi_tensor_adam, capturable branch), one pass instead of ~12.
  *   tensors: HOST array of records (they travel as kernel parameters: no descriptor memory, graph-capturable)
- *   step   : device fp32 scalar, incremented by the call before use (torch's state["step"])
+ *   step   : device fp32 [n_steps] (torch keeps one state["step"] per parameter, all equal): every element is
+ *            incremented by the call, element 0 is the step count used
  *   variant: 0 (contraction pattern bit-equal to torch's kernels); 1..3 exist for the differential test
  * ------------------------------------------------------------------------------------------ */
 typedef struct cfm_adam_tensor {
@@ -225,8 +226,8 @@ typedef struct cfm_adam_tensor {
     float* exp_avg_sq;
     int64_t numel;
 } cfm_adam_tensor_t;
-int cfm_adam_step(const cfm_adam_tensor_t* tensors /* host */, int64_t n_tensors, float* step, double lr, double beta1,
-                  double beta2, double eps, int64_t variant, void* stream);
+int cfm_adam_step(const cfm_adam_tensor_t* tensors /* host */, int64_t n_tensors, float* step, int64_t n_steps, double lr,
+                  double beta1, double beta2, double eps, int64_t variant, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Cosine head: L2-normalise both latents, row-wise dot, times exp(logit_scale).
