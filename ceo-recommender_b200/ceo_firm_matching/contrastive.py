@@ -74,7 +74,8 @@ def train_contrastive(train_loader: DataLoader, val_loader: DataLoader, metadata
         raise NotImplementedError("semi-hard triplet mining (contrastive.py:141-194) is out of scope of this build")
     device = torch.device(config.DEVICE)
     model = ContrastiveCEOFirmMatcher(metadata, config).to(device)
-    optimizer = optim.Adam(model.parameters(), lr=config.LEARNING_RATE)
+    from .optim import FusedAdam
+    optimizer = FusedAdam(model.parameters(), lr=config.LEARNING_RATE)   # optim.Adam's state/arithmetic, one launch
     print(f"Training Contrastive Two-Tower on {config.DEVICE}")
     print(f"  Contrastive weight: {contrastive_weight}")
     print(f"  Temperature: {temperature}")

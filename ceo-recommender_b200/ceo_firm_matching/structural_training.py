@@ -36,7 +36,8 @@ def train_structural_model(train_loader: DataLoader, val_loader: DataLoader, met
     print(f"  CEO Tower Input: {metadata['n_ceo_num']} numeric + {len(metadata['ceo_cat_cards'])} categorical")
     print(f"  Firm Tower Input: {metadata['n_firm_num']} numeric + {len(metadata['firm_cat_cards'])} categorical")
 
-    optimizer = optim.Adam(model.parameters(), lr=config.LEARNING_RATE)
+    from .optim import FusedAdam
+    optimizer = FusedAdam(model.parameters(), lr=config.LEARNING_RATE)   # optim.Adam's state/arithmetic, one launch
     print(f"\nStarting Distillation Training for {config.EPOCHS} epochs...")
 
     best_val_loss = float("inf")
