@@ -184,25 +184,28 @@ struct GatherPlan {
 };
 
 // unit i -> (pair j = b*K + k in x_cat memory order, vector q of the row); U independent loads in flight per thread
-template <int VEC>
-__global__ void emb_gather_rows(const long long* __restrict__ x_cat, long long B, int K, int E, int pieces, int w,
+// IDX: unsigned (32-bit index arithmetic: B*K*E/VEC < 2^31, the usual case; 64-bit division costs ~10x more and this
+// kernel issues four per 16 bytes moved) or long long
+template <int VEC, typename IDX>
+__global__ void emb_gather_rows(const long long* __restrict__ x_cat, long long B_, int K_, int E, int pieces, int w,
                                 GatherPlan gp, float* __restrict__ stash, int* __restrict__ err) {
-    const int EV = E / VEC;
-    const long long total = B * K * EV;
+    const IDX B = (IDX)B_, K = (IDX)K_;
+    const IDX EV = (IDX)(E / VEC);
+    const IDX total = B * K * EV;
     constexpr int U = 4;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += stride * U) {
+    const IDX stride = (IDX)gridDim.x * blockDim.x;
+    for (IDX i = (IDX)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride * U) {
         float4 v4[U];
         float v1[U];
         long long dst[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const long long iu = i + u * stride;
+            const IDX iu = i + (IDX)u * stride;
             dst[u] = -1;
-            if (iu < total) {
-                const long long j = iu / EV;
+            if (iu < total && iu >= i) {                         // (iu >= i: no wrap-around in the 32-bit variant)
+                const IDX j = iu / EV;
                 const int c = (int)(iu - j * EV) * VEC;          // first column of this vector
-                const long long b = j / K;
+                const IDX b = j / K;
                 const int k = (int)(j - b * K);
                 long long idx = x_cat[j];
                 if (idx < 0 || idx >= gp.rows[k]) {
@@ -212,7 +215,7 @@ __global__ void emb_gather_rows(const long long* __restrict__ x_cat, long long B
                 const float* src = gp.table[k * pieces + c / w] + (size_t)idx * E + c;
                 if (VEC == 4) v4[u] = *reinterpret_cast<const float4*>(src);
                 else v1[u] = *src;
-                dst[u] = ((long long)k * B + b) * E + c;
+                dst[u] = ((long long)k * (long long)B + (long long)b) * E + c;
             }
         }
 #pragma unroll
@@ -267,8 +270,8 @@ __global__ void emb_segment_reduce_peer(const unsigned long long* __restrict__ k
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         for (long long s = p; s < n && keys[s] == key; ++s) {
             const int v = vals[s];
-            const int r = (int)(v / B);
-            const long long b = v - (long long)r * B;
+            const int r = v / (int)B;                              // n_owned * n_peers * B < 2^31, so B fits an int
+            const long long b = v - r * (int)B;
             const float* src = pp.dx[j][r] + (size_t)b * ld + off;
             if (VEC == 4) {
                 const float4 g = *reinterpret_cast<const float4*>(src);
@@ -373,10 +376,13 @@ extern "C" int cfm_emb_gather_rows(const int64_t* x_cat, int64_t B, int64_t n_ta
     const long long total = B * n_tables * (vec ? emb_dim / 4 : emb_dim);
     const int grid = (int)std::max<long long>(1, std::min<long long>((total + 1023) / 1024, (long long)sm_count() * 8));
     ProfScope prof(PROF_EMB, stream);
-    if (vec) emb_gather_rows<4><<<grid, 256, 0, stream>>>((const long long*)x_cat, B, (int)n_tables, (int)emb_dim,
-                                                         (int)pieces, w, gp, stash, err_flag);
-    else emb_gather_rows<1><<<grid, 256, 0, stream>>>((const long long*)x_cat, B, (int)n_tables, (int)emb_dim,
-                                                      (int)pieces, w, gp, stash, err_flag);
+    // 32-bit index arithmetic unless the unit count (plus the unrolled look-ahead) could overflow it
+    const bool small = total + 4ll * grid * 256 < (1ll << 31);
+    const long long* xc = (const long long*)x_cat;
+    if (vec && small) emb_gather_rows<4, unsigned><<<grid, 256, 0, stream>>>(xc, B, (int)n_tables, (int)emb_dim, (int)pieces, w, gp, stash, err_flag);
+    else if (vec) emb_gather_rows<4, long long><<<grid, 256, 0, stream>>>(xc, B, (int)n_tables, (int)emb_dim, (int)pieces, w, gp, stash, err_flag);
+    else if (small) emb_gather_rows<1, unsigned><<<grid, 256, 0, stream>>>(xc, B, (int)n_tables, (int)emb_dim, (int)pieces, w, gp, stash, err_flag);
+    else emb_gather_rows<1, long long><<<grid, 256, 0, stream>>>(xc, B, (int)n_tables, (int)emb_dim, (int)pieces, w, gp, stash, err_flag);
     CFM_LAUNCH_CHECK();
     return CFM_OK;
 }
