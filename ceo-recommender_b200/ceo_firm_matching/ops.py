@@ -525,7 +525,7 @@ class CosineHeadFunction(torch.autograd.Function):
         u, v, logit_scale = ctx.saved_tensors
         B, D = u.shape
         du, dv = torch.empty_like(u), torch.empty_like(v)
-        dls = torch.zeros((), device=u.device)
+        dls = torch.empty((), device=u.device)            # assigned (not accumulated) by the kernel's last-CTA finish
         d_score = d_score.contiguous() if d_score is not None else None
         d_uhat = d_uhat.contiguous() if d_uhat is not None else None
         d_vhat = d_vhat.contiguous() if d_vhat is not None else None
@@ -546,7 +546,7 @@ class CosineMSEFunction(torch.autograd.Function):
         target, weights = target.contiguous().float(), weights.contiguous().float()
         B, D = u.shape
         score = torch.empty(B, 1, device=u.device)
-        loss = torch.zeros((), device=u.device)
+        loss = torch.empty((), device=u.device)           # assigned by the kernel's last-CTA finish
         with torch.cuda.device(u.device):
             N.check(N.lib().cfm_cosine_head_fwd(N.ptr(u), N.ptr(v), N.ptr(logit_scale), B, D, eps, N.ptr(score), None,
                                                 None, N.ptr(target), N.ptr(weights), N.ptr(loss),
@@ -561,7 +561,7 @@ class CosineMSEFunction(torch.autograd.Function):
         u, v, logit_scale, target, weights = ctx.saved_tensors
         B, D = u.shape
         du, dv = torch.empty_like(u), torch.empty_like(v)
-        dls = torch.zeros((), device=u.device)
+        dls = torch.empty((), device=u.device)
         g_loss = g_loss.contiguous().float()
         with torch.cuda.device(u.device):
             N.check(N.lib().cfm_cosine_head_bwd(N.ptr(u), N.ptr(v), N.ptr(logit_scale), None, None, None,

@@ -48,6 +48,8 @@ class GraphedTwoTowerStep:
         for s, t in zip(self.static, example):
             s.copy_(t)
         self.counter = torch.zeros(1, dtype=torch.int64, device=dev)
+        # seed of the backward pass (dL/dloss = loss_scale): passing it saves autograd's ones_like and the scaling multiply
+        self._grad_seed = torch.full((), float(loss_scale), device=dev)
         self.graph = torch.cuda.CUDAGraph()
         self.loss = None
         # Autograd pins each parameter's gradient-accumulation node to the stream of its first use; capture fails
@@ -72,7 +74,7 @@ class GraphedTwoTowerStep:
         if self.before_forward is not None:
             self.before_forward(self.static[1], self.static[3])
         loss, _ = self.model.forward_loss(*self.static)
-        (loss if self.loss_scale == 1.0 else loss * self.loss_scale).backward()
+        loss.backward(gradient=self._grad_seed)
         if self.after_backward is not None:
             self.after_backward()
         if self.optimizer is not None:
