@@ -482,14 +482,28 @@ __global__ void bn_fwd_finalize(const __grid_constant__ BnFwdFinArgs args) {
     const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c < N) {
         float n = 0.f, mean = 0.f, m2 = 0.f;
-        for (int p = lane; p < F.nparts; p += 32) {
-            const float* P = F.part + (size_t)p * (2 * N + 4);
-            float nb = P[2 * N];
-            if (nb <= 0.f) continue;
-            float d = P[c] - mean, nn = n + nb;
-            mean += d * (nb / nn);
-            m2 += P[N + c] + d * d * (n * nb / nn);
-            n = nn;
+        // the partial reads are strided and latency-bound: issue a batch of them before the dependent merges
+        constexpr int PF = 4;
+        for (int p0 = lane; p0 < F.nparts; p0 += 32 * PF) {
+            float nbv[PF], mbv[PF], qbv[PF];
+#pragma unroll
+            for (int u = 0; u < PF; ++u) {
+                const int p = p0 + 32 * u;
+                nbv[u] = 0.f; mbv[u] = 0.f; qbv[u] = 0.f;
+                if (p < F.nparts) {
+                    const float* P = F.part + (size_t)p * (2 * N + 4);
+                    nbv[u] = P[2 * N]; mbv[u] = P[c]; qbv[u] = P[N + c];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < PF; ++u) {
+                const float nb = nbv[u];
+                if (nb <= 0.f) continue;
+                float d = mbv[u] - mean, nn = n + nb;
+                mean += d * (nb / nn);
+                m2 += qbv[u] + d * d * (n * nb / nn);
+                n = nn;
+            }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
