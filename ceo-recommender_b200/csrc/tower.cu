@@ -1,16 +1,18 @@
-// Tower kernels (exact-fp32 path): categorical-embedding gather + numeric concat + 3-layer MLP,
-// forward and backward, one Linear per launch ("stage"), both towers in one grid (blockIdx.y).
+// Tower kernels: categorical-embedding gather + numeric concat + 3-layer MLP, forward and backward, one Linear per
+// launch ("stage"), both towers in one grid (blockIdx.y).
 //
 // replaces ceo_firm_matching/model.py:69-76 and structural_model.py:120-127 (+ their autograd).
 //
-// Layout of one stage launch: persistent CTAs (<= one per SM per tower) walk 64-row tiles.  The stage's
-// weight matrix lives in shared memory for the CTA's lifetime; each tile's input activations are
-// (re)built in shared memory (stage 1: gathered embedding rows + numerics; stage >1: BN/ReLU/dropout of the
-// previous stage's raw output) and multiplied with register-tiled FMA loops fed by conflict-free LDS.128.
-// Train-mode BatchNorm needs whole-batch statistics between stages, hence the stage-per-launch split:
-// every CTA writes (count, mean, M2) partials (two-pass per tile, Chan-merged), a 1-CTA finalize kernel
-// merges them in a fixed order -> bitwise reproducible.  Backward mirrors this: per-CTA weight-gradient
-// accumulators stay in registers over all tiles and are written once, then reduced in fixed CTA order.
+// Layout of one stage launch: persistent CTAs (two resident per SM) walk row tiles (64 rows; 32 in the stage-1
+// backward so that the weight matrix plus the gathered tile fit twice per SM).  The stage's weight matrix lives in
+// shared memory for the CTA's lifetime; each tile's input activations are (re)built in shared memory (stage 1:
+// embedding rows gathered with cp.async + numerics; stage >1: BN/ReLU/dropout of the previous stage's raw output)
+// and multiplied on the tensor cores: mma.sync.m16n8k8 TF32 with ldmatrix fragment loads, either one pass
+// (precision 1) or three error-compensated passes a_lo*b_hi + a_hi*b_lo + a_hi*b_hi (precision 0, fp32-class).
+// Train-mode BatchNorm needs whole-batch statistics between stages, hence the stage-per-launch split: every CTA
+// writes (count, mean, M2) partials (two-pass per tile, Chan-merged), a finalize kernel merges them in a fixed order
+// -> bitwise reproducible.  Backward mirrors this: per-CTA weight-gradient accumulators stay in registers over all
+// tiles and are written once, then reduced in fixed CTA order.
 #include "common.cuh"
 #include "tower_types.cuh"
 #include <algorithm>

@@ -1,4 +1,4 @@
-// Descriptors shared by the tower kernels (mma.sync path in tower.cu, tcgen05 path in tower_tc.cu).
+// Descriptors of the tower stage kernels (tower.cu).
 #pragma once
 #include "common.cuh"
 
