@@ -76,6 +76,8 @@ class FusedAdam(torch.optim.Optimizer):
             params = [p for p in group["params"] if p.grad is not None and p.numel() > 0]
             if not params:
                 continue
+            if any(not p.is_cuda for p in params):
+                raise RuntimeError("FusedAdam runs on CUDA parameters only (this build has no CPU fallback)")
             steps = self._state_for(group, params)
             b1, b2 = group["betas"]
             with torch.cuda.device(params[0].device):

@@ -80,3 +80,20 @@ def test_state_dict_layout_equals_reference_golden():
     sds = StructuralDistillationNet(smeta, StructuralConfig()).state_dict()
     assert list(sds.keys()) == list(gs.keys())
     assert all(sds[k].shape == gs[k].shape for k in gs)
+
+
+def test_fused_adam_refuses_cpu_parameters_and_bad_hyperparameters():
+    """No CPU fallback in the optimiser either: CPU tensors raise at step(), bad hyper-parameters at construction."""
+    import pytest
+    import torch
+    from ceo_firm_matching.optim import FusedAdam
+    p = torch.nn.Parameter(torch.ones(4))
+    p.grad = torch.ones(4)
+    opt = FusedAdam([p], lr=1e-3)
+    with pytest.raises(RuntimeError):
+        opt.step()
+    for bad in (dict(lr=0.0), dict(betas=(0.5, 0.999)), dict(betas=(0.9, 1.0)), dict(eps=-1.0)):
+        with pytest.raises(ValueError):
+            FusedAdam([p], **{"lr": 1e-3, **bad})
+    # the param_group keys torch.optim.Adam keeps (state_dict interchange)
+    assert {"lr", "betas", "eps", "weight_decay", "amsgrad", "capturable"} <= set(opt.param_groups[0])
