@@ -13,29 +13,35 @@ from .structural_data import StructuralDataProcessor
 from .structural_training import train_structural_model
 
 
-def main(argv=None):
+# (flag, StructuralConfig field it overrides, type, help) — the reference's command line, structural_cli.py:18-31
+_OVERRIDES = (
+    ("--epochs", "EPOCHS", int, "Number of training epochs (default: 50)"),
+    ("--batch-size", "BATCH_SIZE", int, "Batch size for training (default: 256)"),
+    ("--data-path", "DATA_PATH", str, "Path to BLM posteriors CSV file"),
+    ("--output-path", "OUTPUT_PATH", str, "Output directory for results"),
+)
+
+
+def _config_from(argv) -> StructuralConfig:
     parser = argparse.ArgumentParser(description="Train Structural Distillation Network with BLM Priors")
     parser.add_argument("--synthetic", action="store_true", help="Use synthetic data for verification")
-    parser.add_argument("--epochs", type=int, default=50, help="Number of training epochs (default: 50)")
-    parser.add_argument("--batch-size", type=int, default=256, help="Batch size for training (default: 256)")
-    parser.add_argument("--data-path", type=str, default=None, help="Path to BLM posteriors CSV file")
-    parser.add_argument("--output-path", type=str, default=None, help="Output directory for results")
+    for flag, _, kind, text in _OVERRIDES:
+        parser.add_argument(flag, type=kind, default=None, help=text)
     args = parser.parse_args(argv)
-
     config = StructuralConfig()
-    if args.epochs:
-        config.EPOCHS = args.epochs
-    if args.batch_size:
-        config.BATCH_SIZE = args.batch_size
-    if args.data_path:
-        config.DATA_PATH = args.data_path
-    if args.output_path:
-        config.OUTPUT_PATH = args.output_path
+    for flag, name, _, _ in _OVERRIDES:
+        value = getattr(args, flag.lstrip("-").replace("-", "_"))
+        if value:
+            setattr(config, name, value)
     if args.synthetic:
         config.DATA_PATH = "SYNTHETIC_MODE"          # a path that does not exist forces the generator
-    print("=" * 60)
-    print("STRUCTURAL DISTILLATION NETWORK")
-    print("=" * 60)
+    return config
+
+
+def main(argv=None):
+    config = _config_from(argv)
+    banner = "=" * 60
+    print(f"{banner}\nSTRUCTURAL DISTILLATION NETWORK\n{banner}")
     print(f"Device: {config.DEVICE}  Epochs: {config.EPOCHS}  Batch Size: {config.BATCH_SIZE}")
 
     processor = StructuralDataProcessor(config)
