@@ -94,9 +94,13 @@ class ClockSampler:
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                 "--format=csv,noheader,nounits", "-lms", "50"],
-                                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        try:
+            proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                     "--format=csv,noheader,nounits", "-lms", "50"],
+                                    stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.backend = "unavailable"                   # neither NVML nor nvidia-smi: no samples, say so
+            return
         self.proc = proc
         for ln in proc.stdout:
             f = [x.strip() for x in ln.split(",")]

@@ -27,3 +27,15 @@ def test_reference_arm_prints_contract_line(monkeypatch, capsys):
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert line["config"]["workload"] == bench.WORKLOADS["fp32"]
+
+
+def test_clock_sampler_degrades_without_a_gpu():
+    """On a box with neither NVML nor nvidia-smi the sampler must not raise; it reports zero samples."""
+    sys.path.insert(0, ROOT)
+    import bench
+    with bench.ClockSampler(0) as clocks:
+        clocks.mark()
+        clocks.unmark()
+    summary = clocks.summary()
+    assert set(summary) >= {"sm_mhz", "sm_max_mhz", "reasons", "samples", "source", "window"}
+    assert summary["samples"] >= 0 and isinstance(summary["reasons"], list)
