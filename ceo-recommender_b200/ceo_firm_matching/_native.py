@@ -15,7 +15,7 @@ import torch
 CFM_MAX_TABLES = 16
 CFM_MAX_PEERS = 8
 CFM_TOPK_CAP = 384
-CFM_ABI_VERSION = 1
+CFM_ABI_VERSION = 2
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libcfm_b200.so")
@@ -37,7 +37,8 @@ class Tower(C.Structure):
         ("bn1_rm", C.c_void_p), ("bn1_rv", C.c_void_p), ("bn2_rm", C.c_void_p), ("bn2_rv", C.c_void_p),
         ("bn1_nbt", C.c_void_p), ("bn2_nbt", C.c_void_p),
         ("h1_raw", C.c_void_p), ("h2_raw", C.c_void_p), ("out", C.c_void_p),
-        ("bn1_stat", C.c_void_p), ("bn2_stat", C.c_void_p), ("scratch", C.c_void_p),
+        ("bn1_stat", C.c_void_p), ("bn2_stat", C.c_void_p), ("scratch", C.c_void_p), ("wimg", C.c_void_p),
+        ("a1", C.c_void_p), ("a2", C.c_void_p),
     ]
 
 
@@ -86,6 +87,7 @@ PROTOTYPES = {
     "cfm_last_error": (C.c_char_p, []),
     "cfm_device_info": (C.c_int, [C.POINTER(i64)] * 4),
     "cfm_tower_scratch_floats": (i64, [C.POINTER(Tower)]),
+    "cfm_tower_wimg_floats": (i64, [C.POINTER(Tower)]),
     "cfm_launch_count": (i64, [_I]),
     "cfm_profile_enable": (C.c_int, [_I]),
     "cfm_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(i64), _I]),
@@ -121,6 +123,8 @@ PROTOTYPES = {
     "cfm_allpairs_topk": (C.c_int, [_V, _V, _V, _V, _I, _I, _I, _I, _I, _I, _D, _D, _I, _V, _V, _V, _V, _V, _V, _V, _V]),
     "cfm_topk_merge": (C.c_int, [_V, _I, _V, _I, _I, _I, _V, _V, _V]),
     "cfm_allpairs_rank": (C.c_int, [_V, _V, _I, _I, _I, _V, _V, _V]),
+    "cfm_debug_set_trace": (C.c_int, [_V, _I]),
+    "cfm_tc_selftest": (C.c_int, [_V, _V, _V, _I, _I, _I, _I, _I, _V]),
 }
 
 _lib: Optional[C.CDLL] = None

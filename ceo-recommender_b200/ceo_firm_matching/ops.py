@@ -95,6 +95,8 @@ class TowerHandle:
         self.lin, self.bn, self.tower_id = tuple(lin), tuple(bn), tower_id
         self._drop = tuple(drop)
         self._scratch = None
+        self._wimg = None
+        self.use_tc = True                       # tcgen05 stage kernels where the layer shapes allow (False: mma.sync)
         self.precision = 0                       # 0: fp32-class (3xTF32), 1: single-pass TF32 tensor-core products
         self.table_grads: Optional["PersistentTableGrads"] = None
         self.row_source: Optional["StashedRows"] = None   # table-sharded mode: rows pulled into a local stash first
@@ -131,6 +133,12 @@ class TowerHandle:
             ps += [b2.weight, b2.bias]
         ps += [l3.weight, l3.bias]
         return ps
+
+    def weight_images(self, device: torch.device, floats: int) -> torch.Tensor:
+        """(hi, lo)-split swizzled weight images of the tcgen05 stage kernels; rebuilt by every forward call."""
+        if self._wimg is None or self._wimg.numel() < floats or self._wimg.device != device:
+            self._wimg = torch.empty(floats, dtype=torch.float32, device=device)
+        return self._wimg
 
     def scratch(self, device: torch.device, floats: int) -> torch.Tensor:
         if self._scratch is None or self._scratch.numel() < floats or self._scratch.device != device:
@@ -190,6 +198,11 @@ class _TowerCall:
         t.bn1_stat, t.bn2_stat = N.ptr(self.bn1_stat), N.ptr(self.bn2_stat)
         per_cta = N.lib().cfm_tower_scratch_floats(C.byref(t))
         t.scratch = N.ptr(h.scratch(dev, per_cta * N.device_info()["tower_ctas"]))
+        if h.use_tc:
+            t.wimg = N.ptr(h.weight_images(dev, N.lib().cfm_tower_wimg_floats(C.byref(t))))
+            self.a1 = torch.empty(B, l1.out_features, device=dev)
+            self.a2 = torch.empty(B, l2.out_features, device=dev)
+            t.a1, t.a2 = N.ptr(self.a1), N.ptr(self.a2)
         self.struct = t
 
 

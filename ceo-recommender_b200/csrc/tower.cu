@@ -15,6 +15,7 @@
 // tiles and are written once, then reduced in fixed CTA order.
 #include "common.cuh"
 #include "tower_types.cuh"
+#include "tower_tc.cuh"
 #include <algorithm>
 
 namespace cfm {
@@ -1015,9 +1016,16 @@ extern "C" int cfm_towers_fwd(const cfm_tower_t* towers, int64_t n_towers, int64
         attr_set = true;
     }
     const bool exact = towers[0].precision == 0;
+    // layers the tcgen05 stage kernels cover (all towers of the call must qualify); the rest run on mma.sync
+    bool use_tc[4] = {false, false, false, false};
+    for (int s = 1; s <= 3; ++s) {
+        use_tc[s] = true;
+        for (int i = 0; i < n_towers; ++i) use_tc[s] = use_tc[s] && tc_fwd_supported(towers[i], s);
+    }
+    if (towers[0].wimg) { int rc = tc_prep_launch(towers, (int)n_towers, stream); if (rc) return rc; }
     for (int s = 1; s <= 3; ++s) {
         FwdArgs a{};
-        a.B = B; a.err = err_flag;
+        a.B = B; a.err = err_flag; a.exact = exact ? 1 : 0;
         size_t smem = 0, smem32 = 0;
         bool any_stats = false;
         for (int i = 0; i < n_towers; ++i) {
@@ -1032,7 +1040,7 @@ extern "C" int cfm_towers_fwd(const cfm_tower_t* towers, int64_t n_towers, int64
         // a stage whose CTAs fit exactly twice per SM gets two persistent CTAs per SM and tower, so that the SM keeps
         // 16 warps while one tower's CTAs run (both towers' grids are otherwise resident one after the other)
         const bool two = smem > 76 * 1024 && smem <= 113 * 1024;
-        const int ctas = (int)std::min<long long>(ntiles, two ? tower_ctas(32) : tower_ctas(64));
+        int ctas = (int)std::min<long long>(ntiles, two ? tower_ctas(32) : tower_ctas(64));
         for (int i = 0; i < n_towers; ++i) {
             const cfm_tower_t& t = towers[i];
             FwdStage& S = a.st[i];
@@ -1045,16 +1053,20 @@ extern "C" int cfm_towers_fwd(const cfm_tower_t* towers, int64_t n_towers, int64
             S.stat_part = (training && bn_after) ? t.scratch : nullptr;
             any_stats |= S.stat_part != nullptr;
             size_t need = fwd_smem_bytes(t, s, a.tm);
-            CFM_REQUIRE(need <= (size_t)MAX_SMEM, CFM_ERR_UNSUPPORTED,
+            CFM_REQUIRE(use_tc[s] || need <= (size_t)MAX_SMEM, CFM_ERR_UNSUPPORTED,
                         "tower stage %d needs %zu B shared memory (> %d): layer %dx%d too large", s, need, MAX_SMEM,
                         S.N, S.in.K);
         }
-        {
+        if (use_tc[s]) {
+            ProfScope prof(PROF_FWD1 + s - 1, stream);
+            int rc = tc_fwd_launch(a, towers, (int)n_towers, s, &ctas, stream);
+            if (rc) return rc;
+        } else {
             ProfScope prof(PROF_FWD1 + s - 1, stream);
             if (exact) tower_fwd_stage<true, 64><<<dim3(ctas, (unsigned)n_towers), NT, smem, stream>>>(a);
             else tower_fwd_stage<false, 64><<<dim3(ctas, (unsigned)n_towers), NT, smem, stream>>>(a);
+            CFM_LAUNCH_CHECK();
         }
-        CFM_LAUNCH_CHECK();
         if (any_stats) {
             BnFwdFinArgs f{};
             for (int i = 0; i < n_towers; ++i) {
@@ -1128,8 +1140,17 @@ extern "C" int cfm_towers_bwd(const cfm_tower_t* towers, const cfm_tower_grads_t
             smem32 = std::max(smem32, bwd_smem_bytes(t, s, a_bn_i, need_dx_i, 32));
         }
         a.tm = pick_tm(smem, smem32);
+        a.exact = towers[0].precision == 0 ? 1 : 0;
+        bool use_tc = true;                               // tcgen05 stage kernel when every tower of the call qualifies
+        for (int i = 0; i < n_towers; ++i) {
+            const cfm_tower_t& t = towers[i];
+            const bool a_bn_i = s >= 2 && (s == 2 || t.bn2);
+            const bool need_dx_i = s > 1 || grads[i].dx_emb || grads[i].dx_num;
+            use_tc = use_tc && tc_bwd_supported(t, s, a_bn_i, need_dx_i);
+        }
+        if (use_tc) a.tm = 64;
         const long long ntiles = (B + a.tm - 1) / a.tm;
-        const int ctas = (int)std::min<long long>(ntiles, tower_ctas(a.tm));
+        int ctas = (int)std::min<long long>(ntiles, use_tc ? sm_count() : tower_ctas(a.tm));
         smem = 0;
         for (int i = 0; i < n_towers; ++i) {
             const cfm_tower_t& t = towers[i];
@@ -1158,7 +1179,7 @@ extern "C" int cfm_towers_bwd(const cfm_tower_t* towers, const cfm_tower_grads_t
             S.dx_num = s == 1 ? g.dx_num : nullptr;
             S.need_dx = s > 1 || g.dx_emb || g.dx_num;
             any_sums |= S.a_bn != 0;
-            size_t need = bwd_smem_bytes(t, s, S.a_bn, S.need_dx, a.tm);
+            size_t need = use_tc ? 0 : bwd_smem_bytes(t, s, S.a_bn, S.need_dx, a.tm);
             CFM_REQUIRE(need <= (size_t)MAX_SMEM, CFM_ERR_UNSUPPORTED,
                         "tower bwd stage %d needs %zu B shared memory (> %d)", s, need, MAX_SMEM);
             smem = std::max(smem, need);
@@ -1166,7 +1187,7 @@ extern "C" int cfm_towers_bwd(const cfm_tower_t* towers, const cfm_tower_grads_t
             max_groups = std::max(max_groups, groups);
         }
         // scratch must hold ctas * (N*(K+1) + 2K) floats: guaranteed by cfm_tower_scratch_floats
-        for (int i = 0; i < n_towers; ++i) {
+        for (int i = 0; i < n_towers && !use_tc; ++i) {
             const BwdStage& S = a.st[i];
             CFM_REQUIRE(ceil_div(S.N, 16) * (ceil8(S.in.K + 1) >> 3) <= 8 * DW_MAX_TILES, CFM_ERR_UNSUPPORTED,
                         "tower bwd stage %d: layer %dx%d too large for the per-warp dW tiles", s, S.N, S.in.K);
@@ -1174,7 +1195,8 @@ extern "C" int cfm_towers_bwd(const cfm_tower_t* towers, const cfm_tower_grads_t
         int rc;
         {
             ProfScope prof(PROF_BWD1 + s - 1, stream);
-            rc = launch_bwd(a, ctas, (int)n_towers, smem, towers[0].precision == 0, stream);
+            if (use_tc) { int c2 = ctas; rc = tc_bwd_launch(a, towers, (int)n_towers, s, &c2, stream); }
+            else rc = launch_bwd(a, ctas, (int)n_towers, smem, towers[0].precision == 0, stream);
         }
         if (rc) return rc;
         ProfScope prof_red(PROF_REDUCE, stream);

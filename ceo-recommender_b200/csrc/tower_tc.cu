@@ -1,0 +1,1114 @@
+// Tower stage kernels on the 5th-generation tensor cores: tcgen05.mma kind::tf32, accumulators in TMEM.
+//
+// replaces ceo_firm_matching/model.py:69-76 and structural_model.py:120-127 (+ their autograd) for layers up to 64
+// outputs wide; same stage contract as the mma.sync kernels of tower.cu (one Linear per launch, both towers in one
+// grid, identical per-CTA partial formats), so the finalize / reduce kernels and the host orchestration are shared.
+//
+// Every product is an fp32-class "3xTF32" product: each fp32 operand is split ONCE, by the thread that builds its
+// shared-memory image, into hi = tf32(x) and lo = x - hi (tctile.cuh); the tensor core runs a_lo.b_hi + a_hi.b_lo +
+// a_hi.b_hi into one TMEM accumulator (precision 1: the last pass only).  All operands are K-major images; where a
+// product reduces over the batch rows (weight gradients) the builders write the transposed image.
+//
+// One persistent CTA per SM and tower, 21 warps with fixed roles:
+//   warps 0-3   epilogue : TMEM -> registers (thread <-> accumulator row), bias / masks, global stores, the
+//                          cross-row column sums (BatchNorm statistics forward, BatchNorm-backward sums) by
+//                          recursive-halving shuffles, accumulated in registers over all tiles of the CTA
+//   warp  4     MMA      : one thread issues every tcgen05.mma and the tcgen05.commit that releases a buffer
+//   warps 5-20  producers: two groups of eight warps take alternate chunks (32 input columns of a row tile) and
+//                          build their operand images in a shared-memory ring: stage 1 gathers embedding rows
+//                          (16-byte loads), later stages re-apply BatchNorm / ReLU / dropout to the saved
+//                          pre-activations; memory-level parallelism comes from the sixteen warps
+// Rings and accumulators are handed over with mbarriers (full / empty pairs); nothing in the steady state uses a
+// CTA-wide barrier, so gather latency, tensor-core time and the epilogue overlap across tiles.
+#include "common.cuh"
+#include "tower_types.cuh"
+#include "tower_tc.cuh"
+#include "tctile.cuh"
+#include <algorithm>
+
+namespace cfm {
+
+constexpr int TC_EPI_WARPS = 4;
+constexpr int TC_GROUPS = 2;                                             // producer groups, alternating chunks
+constexpr int TC_GROUP_WARPS = 8;
+constexpr int TC_PROD_WARPS = TC_GROUPS * TC_GROUP_WARPS;
+constexpr int TC_MMA_WARP = TC_EPI_WARPS;
+constexpr int TC_PROD_WARP0 = TC_EPI_WARPS + 1;
+constexpr int TC_THREADS = (TC_EPI_WARPS + 1 + TC_PROD_WARPS) * 32;      // 672
+constexpr int TC_GT = TC_GROUP_WARPS * 32;                               // threads of one producer group
+constexpr int TC_PT = TC_PROD_WARPS * 32;                                // all producer threads
+constexpr int TCF_M = 128;                                               // forward tile rows (accumulator M)
+constexpr int TCB_M = 64;                                                // backward tile rows
+constexpr int TC_SMEM_MAX = 227 * 1024;
+
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// optional event trace (debug): cfm_debug_set_trace(buffer of n_ctas * 128 uint64) -> every CTA records
+// globaltimer stamps of its roles; slot layout: [0] start, [1] setup done, [2 + i] producer chunk i arrived (i < 40),
+// [48 + t] MMA tile t committed (t < 16), [64 + t] epilogue tile t done (t < 16), [127] end
+__device__ unsigned long long* g_trace = nullptr;
+__device__ int g_trace_code = 0;                 // 10 * (0 forward, 1 backward) + stage of the launches to record
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void trace(int slot, int code) {
+    if (g_trace && g_trace_code == code) g_trace[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 128 + slot] = gtime();
+}
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void sts4(uint8_t* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
+
+// Column sums over the lanes of a warp by recursive halving: every step a lane keeps one half of its columns and
+// sends the other half to its partner (xor mask), so 32 lanes x NC columns cost NC - NC/32 shuffles instead of
+// 5 * NC.  After masks 16..1 lane l holds the sums of columns (NC/32)*l ... ; with masks 8..1 (16-lane groups, the
+// M = 64 accumulator layout) lane l < 16 holds columns (NC/16)*l ... of its group.
+template <int N, int MASK>
+struct Halve {
+    __device__ static __forceinline__ void run(float (&x)[N], int lane) {
+        const bool up = (lane & MASK) != 0;
+#pragma unroll
+        for (int i = 0; i < N / 2; ++i) {
+            const float keep = up ? x[i + N / 2] : x[i];
+            const float send = up ? x[i] : x[i + N / 2];
+            x[i] = keep + __shfl_xor_sync(FULL, send, MASK);
+        }
+        if constexpr (MASK > 1) Halve<N / 2, MASK / 2>::run(reinterpret_cast<float (&)[N / 2]>(x), lane);
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// weight images
+// ------------------------------------------------------------------------------------------
+struct PrepTower {
+    const float* W[3];
+    int K[3], N[3];
+    int KE, n_num;
+    float* img;
+};
+struct PrepArgs { PrepTower t[2]; };
+
+__global__ void __launch_bounds__(256) tc_prep_weights(const __grid_constant__ PrepArgs a) {
+    const PrepTower& T = a.t[blockIdx.y];
+    if (!T.img) return;
+    const WImgLayout L = wimg_layout(T.K, T.N);
+    for (int s = 0; s < 3; ++s) {
+        const int K = T.K[s], N = T.N[s], npad = tc_npad(N), nch = tc_nch(K), ncolp = tc_nblk(N) * 32;
+        const int kcols = nch * 32;
+        float* wimg = T.img + L.w[s];
+        float* wtimg = T.img + L.wt[s];
+        const int total = ncolp * kcols;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+            const int n = i / kcols, kc = i - n * kcols;
+            float v = 0.f;
+            if (n < N && kc < K) v = __ldg(T.W[s] + (size_t)n * K + (s == 0 ? gcol_stage1(kc, T.KE, T.n_num) : kc));
+            float hi, lo;
+            split_tf32(v, hi, lo);
+            const int j = kc >> 5, c = kc & 31;
+            if (n < npad) {
+                float* ch = wimg + (size_t)j * tc_w_chunk_floats(N);
+                const uint32_t off = sw128_off(n, c, npad) >> 2;
+                ch[off] = hi;
+                ch[npad * 32 + off] = lo;
+            }
+            float* tch = wtimg + (size_t)j * tc_wt_chunk_floats(N);
+            const uint32_t offt = sw128_off(c, n, 32) >> 2;
+            tch[offt] = hi;
+            tch[32 * ncolp + offt] = lo;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// producers: one chunk = 32 input columns of a row tile
+// ------------------------------------------------------------------------------------------
+// a = dropout(relu(bn(h))) for a 4-column quad
+__device__ __forceinline__ float4 act_quad(const float4& h, const float* sm_bn, int Kp, int c0, int bn_mode, const DropCtx& drop,
+                                           long long row) {
+    float t[4] = {h.x, h.y, h.z, h.w};
+    if (bn_mode) {
+        const float4 m = *reinterpret_cast<const float4*>(sm_bn + c0), is = *reinterpret_cast<const float4*>(sm_bn + Kp + c0);
+        const float4 ga = *reinterpret_cast<const float4*>(sm_bn + 2 * Kp + c0), be = *reinterpret_cast<const float4*>(sm_bn + 3 * Kp + c0);
+        t[0] = (t[0] - m.x) * is.x * ga.x + be.x; t[1] = (t[1] - m.y) * is.y * ga.y + be.y;
+        t[2] = (t[2] - m.z) * is.z * ga.z + be.z; t[3] = (t[3] - m.w) * is.w * ga.w + be.w;
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) t[e] = fmaxf(t[e], 0.f);
+    if (drop.active) {
+        const Philox4 w = drop_words(drop, row, c0 >> 2);
+        t[0] = w.x >= drop.thresh ? t[0] * drop.inv_keep : 0.f;
+        t[1] = w.y >= drop.thresh ? t[1] * drop.inv_keep : 0.f;
+        t[2] = w.z >= drop.thresh ? t[2] * drop.inv_keep : 0.f;
+        t[3] = w.w >= drop.thresh ? t[3] * drop.inv_keep : 0.f;
+    }
+    return make_float4(t[0], t[1], t[2], t[3]);
+}
+
+__device__ __forceinline__ void stage_bn_params_tc(const ActSrc& a, int K, float* sm_bn, int tid, int nthreads) {
+    const int Kp = (K + 3) & ~3;
+    if (a.bn_mode == 0) return;
+    for (int c = tid; c < Kp; c += nthreads) {
+        const bool ok = c < K;
+        const float s = ok ? a.var_or_istd[c] : 1.f;
+        sm_bn[c] = ok ? a.mean[c] : 0.f;
+        sm_bn[Kp + c] = a.bn_mode == 2 ? rsqrtf(s + BN_EPS) : s;
+        sm_bn[2 * Kp + c] = ok ? a.gamma[c] : 0.f;
+        sm_bn[3 * Kp + c] = ok ? a.beta[c] : 0.f;
+    }
+}
+
+// Position of a chunk in a producer group's stream: tiles in CTA order, inside a tile the column chunks j == group
+// (mod TC_GROUPS).  Group 0 therefore owns chunk 0 of every tile.  (One chunk per tile: everything goes to group 0.)
+struct ChunkPos {
+    int it, j;
+    __device__ __forceinline__ void next(int nch, int grp) {
+        j += TC_GROUPS;
+        if (j >= nch) { j = grp; ++it; }
+    }
+};
+
+// Software pipeline of a producer thread over its group's chunks: the data loads of the next PD chunks are in flight
+// in registers (NX 16-byte quads per chunk), the index loads they depend on two chunks further ahead.  The functors
+// must treat positions past the end (it >= number of tiles) as no-ops that still define their outputs.
+template <int PD, int NX, int NI, class IssueIdx, class IssueData, class Consume>
+__device__ __forceinline__ void chunk_pipeline(int n_tiles, int nch, int grp, IssueIdx issue_idx, IssueData issue_data,
+                                               Consume consume) {
+    static_assert(PD % 2 == 0, "the two index sets alternate with the unrolled slot");
+    if (grp >= nch) return;
+    ChunkPos pc{0, grp}, pd{0, grp}, pi{0, grp};
+    float4 buf[PD][NX];
+    long long ix[2][NI];
+    {
+        long long ixp[PD][NI];
+#pragma unroll
+        for (int u = 0; u < PD; ++u) { issue_idx(pi, ixp[u]); pi.next(nch, grp); }
+#pragma unroll
+        for (int u = 0; u < PD; ++u) { issue_data(pd, ixp[u], buf[u]); pd.next(nch, grp); }
+    }
+    issue_idx(pi, ix[0]); pi.next(nch, grp);
+    issue_idx(pi, ix[1]); pi.next(nch, grp);
+    while (pc.it < n_tiles) {
+#pragma unroll
+        for (int u = 0; u < PD; ++u) {
+            if (pc.it < n_tiles) {
+                consume(pc, buf[u]); pc.next(nch, grp);
+                issue_data(pd, ix[u & 1], buf[u]); pd.next(nch, grp);
+                issue_idx(pi, ix[u & 1]); pi.next(nch, grp);
+            }
+        }
+    }
+}
+
+// loads of one stage-1 chunk: 4-column quad q of rows sub + 32 * i (tile order: embedding columns, then numerics)
+template <int NX>
+__device__ __forceinline__ void gather_issue_idx(const GatherSrc& g, long long B, long long row0, int j, int q, int sub,
+                                                 long long (&ix)[NX]) {
+    const int c0 = 32 * j + 4 * q;
+    if (c0 < g.n_tab * g.E) {
+        const int t = c0 / g.E;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+            const long long r = row0 + sub + 32 * i;
+            if (r < B) ix[i] = __ldg(g.x_cat + r * g.n_tab + t);
+        }
+    }
+}
+template <int NX>
+__device__ __forceinline__ void gather_issue_data(const GatherSrc& g, long long B, long long row0, int j, int q, int sub,
+                                                  const long long (&ix)[NX], int* err, float4* x) {
+    const int c0 = 32 * j + 4 * q;
+    const int KE = g.n_tab * g.E;
+    if (c0 < KE) {                           // E % 4 == 0: a quad never straddles two tables
+        const int t = c0 / g.E, e = c0 - t * g.E;
+        const float* tb = g.tab[t];
+        const long long trows = g.tab_rows[t];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+            const long long r = row0 + sub + 32 * i;
+            if (r < B) {
+                long long v = ix[i];
+                if (v < 0 || v >= trows) { if (err) atomicOr(err, CFM_FLAG_INDEX_OOB); v = 0; }
+                x[i] = ldg4(tb + (size_t)v * g.E + e);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+            const long long r = row0 + sub + 32 * i;
+            if (r < B) {
+                float v[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int cn = c0 + e - KE;
+                    if (cn < g.n_num) v[e] = __ldg(g.x_num + (size_t)r * g.n_num + cn);
+                }
+                x[i] = make_float4(v[0], v[1], v[2], v[3]);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// forward stage
+// ------------------------------------------------------------------------------------------
+struct TcFwdSmem {
+    int w, ring, bn, bias, piv, wst, bars, tmem, total, nst;
+};
+__host__ __device__ inline TcFwdSmem tcf_smem(int K, int N) {
+    TcFwdSmem s;
+    const int nch = tc_nch(K), Kp = (K + 3) & ~3;
+    int o = 0;
+    s.w = o; o += nch * tc_w_chunk_floats(N) * 4;
+    s.ring = o;
+    int f = 0;                                          // fixed tail (relative)
+    const int bn = f; f += 4 * Kp * 4;
+    const int bias = f; f += 64 * 4;
+    const int piv = f; f += 4 * 64 * 4;
+    const int wst = f; f += 4 * (2 * 64 + 4) * 4;
+    f = (f + 15) & ~15;
+    const int bars = f; f += 32 * 8;
+    const int tmem = f; f += 16;
+    const int stage = 2 * TCF_M * 128;
+    int nst = (TC_SMEM_MAX - 1024 - o - f) / stage;
+    nst = nst > 4 ? 4 : nst;
+    s.nst = nst;
+    o += (nst > 0 ? nst : 0) * stage;
+    s.bn = o + bn; s.bias = o + bias; s.piv = o + piv; s.wst = o + wst; s.bars = o + bars; s.tmem = o + tmem;
+    s.total = o + f + 1024;
+    return s;
+}
+
+template <int NC, bool STAGE1>
+__global__ void __launch_bounds__(TC_THREADS, 1) tower_fwd_tc(const __grid_constant__ FwdArgs args) {
+    const FwdStage& S = args.st[blockIdx.y];
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int K = S.in.K, N = S.N, npad = tc_npad(N), nch = tc_nch(K), Kp = (K + 3) & ~3;
+    const TcFwdSmem L = tcf_smem(K, N);
+    const int nst = L.nst;
+    float* sm_bn = reinterpret_cast<float*>(sm + L.bn);
+    float* sm_bias = reinterpret_cast<float*>(sm + L.bias);
+    float* sm_piv = reinterpret_cast<float*>(sm + L.piv);
+    float* sm_wst = reinterpret_cast<float*>(sm + L.wst);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L.bars);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + L.tmem);
+    uint64_t *w_full = bars, *full = bars + 1, *empty = bars + 5, *d_full = bars + 9, *d_empty = bars + 11;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long B = args.B;
+    const long long ntiles = (B + TCF_M - 1) / TCF_M;
+    const int my_tiles = (long long)blockIdx.x < ntiles ? (int)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+    const bool exact = args.exact != 0;
+    const bool stats = S.stat_part != nullptr;
+    const int chunk_bytes = tc_w_chunk_floats(N) * 4;
+    constexpr int STAGE_BYTES = 2 * TCF_M * 128, IMG_BYTES = TCF_M * 128;
+    const int tcode = S.in.stage;
+
+    if (tid == 0) {
+        trace(0, tcode);
+        mbar_init(w_full, 1);
+        for (int s = 0; s < 4; ++s) { mbar_init(full + s, TC_GT); mbar_init(empty + s, 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(d_full + b, 1); mbar_init(d_empty + b, TC_EPI_WARPS * 32); }
+        fence_barrier_init();
+    }
+    constexpr uint32_t TMEM_COLS = 2 * NC;
+    if (warp == TC_MMA_WARP) tmem_alloc(tmem_slot, TMEM_COLS);
+    if (!STAGE1) stage_bn_params_tc(S.in.a, K, sm_bn, tid, TC_THREADS);
+    for (int c = tid; c < 64; c += TC_THREADS) sm_bias[c] = c < N ? S.bias[c] : 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (tid == 0) trace(1, tcode);
+
+    if (warp == TC_MMA_WARP) {
+        // ===================== MMA issuer =====================
+        if (lane == 0 && my_tiles > 0) {
+            mbar_expect_tx(w_full, (uint32_t)(nch * chunk_bytes));
+            for (int j = 0; j < nch; ++j)
+                bulk_g2s(sm + L.w + j * chunk_bytes, S.wimg + (size_t)j * tc_w_chunk_floats(N), (uint32_t)chunk_bytes, w_full);
+            mbar_wait(w_full, 0);
+            const uint32_t idesc = make_idesc_tf32(TCF_M, npad, false, false);
+            const uint32_t w_s = smem_u32(sm + L.w), ring_s = smem_u32(sm + L.ring);
+            const int ks_last = (K - 32 * (nch - 1) + 7) >> 3;
+            const int p0 = exact ? 0 : 2;
+            uint32_t cnt = 0;
+            for (int it = 0; it < my_tiles; ++it) {
+                const int buf = it & 1;
+                mbar_wait(d_empty + buf, ((it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d = tmem_base + buf * NC;
+                for (int j = 0; j < nch; ++j, ++cnt) {
+                    const int s = cnt % nst;
+                    mbar_wait(full + s, (cnt / nst) & 1);
+                    tc_fence_after();
+                    const uint32_t a_hi = ring_s + s * STAGE_BYTES, a_lo = a_hi + IMG_BYTES;
+                    const uint32_t b_hi = w_s + j * chunk_bytes, b_lo = b_hi + npad * 128;
+                    const int ksn = j == nch - 1 ? ks_last : 4;
+                    for (int p = p0; p < 3; ++p) {
+                        const uint32_t ai = p == 0 ? a_lo : a_hi, bi = p == 1 ? b_lo : b_hi;
+                        for (int ks = 0; ks < ksn; ++ks)
+                            umma_tf32(d, desc_kmajor_sw128(ai + ks * 32), desc_kmajor_sw128(bi + ks * 32), idesc,
+                                      !(j == 0 && p == p0 && ks == 0));
+                    }
+                    umma_commit(empty + s);
+                }
+                umma_commit(d_full + buf);
+                if (it < 16) trace(48 + it, tcode);
+            }
+        }
+    } else if (warp < TC_EPI_WARPS) {
+        // ===================== epilogue: thread <-> row =====================
+        const int q = warp;
+        constexpr int NH = NC / 32;                        // 32-column halves; after the reduction lane l owns
+        float S1[NH], S2[NH];                              // column 32 * h + l of half h
+#pragma unroll
+        for (int k = 0; k < NH; ++k) { S1[k] = 0.f; S2[k] = 0.f; }
+        float cntw = 0.f;
+        bool have_piv = false;
+        float* piv = sm_piv + q * 64;
+        for (int it = 0; it < my_tiles; ++it) {
+            const long long row0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * TCF_M;
+            const int rows_valid = (int)min((long long)TCF_M, B - row0);
+            const int buf = it & 1;
+            const int r = 32 * q + lane;
+            const bool valid = r < rows_valid;
+            const int nvw = max(0, min(32, rows_valid - 32 * q));           // valid rows of this warp (warp-uniform)
+            mbar_wait(d_full + buf, (it >> 1) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int h = 0; h < NH; ++h) {
+                float v[32];
+                tmem_ld32(tmem_base + buf * NC + 32 * h + ((uint32_t)(32 * q) << 16), v);
+                if (h == NH - 1) {                        // accumulator drained: the MMAs of tile it + 2 may start
+                    tc_fence_before();
+                    mbar_arrive(d_empty + buf);
+                }
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(sm_bias + 32 * h + i);
+                    v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+                }
+                if (valid) {
+                    float* dst = S.hout + (size_t)(row0 + r) * N + 32 * h;
+                    if ((N & 3) == 0) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4)
+                            if (32 * h + i < N) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (32 * h + i < N) dst[i] = v[i];
+                    }
+                }
+                if (stats && nvw > 0) {
+                    if (!have_piv) {
+                        // pivot = column means of this warp's first rows: keeps the shifted sums free of cancellation
+                        float t[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) t[i] = valid ? v[i] : 0.f;
+                        Halve<32, 16>::run(t, lane);
+                        piv[32 * h + lane] = t[0] / (float)nvw;
+                        __syncwarp();
+                    }
+                    float e[32];
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        const float4 p4 = *reinterpret_cast<const float4*>(piv + 32 * h + i);
+                        v[i] = valid ? v[i] - p4.x : 0.f; v[i + 1] = valid ? v[i + 1] - p4.y : 0.f;
+                        v[i + 2] = valid ? v[i + 2] - p4.z : 0.f; v[i + 3] = valid ? v[i + 3] - p4.w : 0.f;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) e[i] = v[i] * v[i];
+                    Halve<32, 16>::run(v, lane);
+                    Halve<32, 16>::run(e, lane);
+                    S1[h] += v[0];
+                    S2[h] += e[0];
+                }
+            }
+            if (stats && nvw > 0) { have_piv = true; cntw += (float)nvw; }
+            if (tid == 0 && it < 16) trace(64 + it, tcode);
+        }
+        if (stats) {
+            // per-warp (count, mean, M2) -> Chan merge of the four warps in warp order -> the CTA's partial
+            float* ws = sm_wst + q * (2 * 64 + 4);
+#pragma unroll
+            for (int k = 0; k < NH; ++k) {
+                const int c = 32 * k + lane;
+                const float pv = have_piv ? piv[c] : 0.f;
+                ws[c] = cntw > 0.f ? pv + S1[k] / cntw : 0.f;
+                ws[64 + c] = cntw > 0.f ? fmaxf(S2[k] - S1[k] * S1[k] / cntw, 0.f) : 0.f;
+            }
+            if (lane == 0) ws[128] = cntw;
+            named_bar_sync(1, TC_EPI_WARPS * 32);
+            float* P = S.stat_part + (size_t)blockIdx.x * (2 * N + 4);
+            const int c = tid;
+            if (c < N) {
+                float n = 0.f, mean = 0.f, m2 = 0.f;
+#pragma unroll
+                for (int w = 0; w < TC_EPI_WARPS; ++w) {
+                    const float* o = sm_wst + w * (2 * 64 + 4);
+                    const float nb = o[128];
+                    if (nb > 0.f) {
+                        const float d = o[c] - mean, nn = n + nb;
+                        mean += d * (nb / nn);
+                        m2 += o[64 + c] + d * d * (n * nb / nn);
+                        n = nn;
+                    }
+                }
+                P[c] = mean;
+                P[N + c] = m2;
+                if (c == 0) P[2 * N] = n;
+            }
+        }
+    } else {
+        // ===================== producers =====================
+        const int ptid = tid - TC_PROD_WARP0 * 32;
+        const int grp = ptid / TC_GT, gtid = ptid - grp * TC_GT;
+        const int q = gtid & 7, sub = gtid >> 3;
+        const DropCtx drop = resolve_drop(S.in.a.drop);
+        uint8_t* ring = sm + L.ring;
+        const GatherSrc& g = S.in.g;
+        constexpr int NX = TCF_M / 32;
+        auto tile_row0 = [&](int it) { return ((long long)blockIdx.x + (long long)it * gridDim.x) * TCF_M; };
+        auto issue_idx = [&](const ChunkPos& p, long long (&ix)[NX]) {
+#pragma unroll
+            for (int i = 0; i < NX; ++i) ix[i] = 0;
+            if (STAGE1 && p.it < my_tiles) gather_issue_idx<NX>(g, B, tile_row0(p.it), p.j, q, sub, ix);
+        };
+        auto issue_data = [&](const ChunkPos& p, const long long (&ix)[NX], float4 (&x)[NX]) {
+#pragma unroll
+            for (int i = 0; i < NX; ++i) x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.it >= my_tiles) return;
+            const long long row0 = tile_row0(p.it);
+            if (STAGE1) {
+                gather_issue_data<NX>(g, B, row0, p.j, q, sub, ix, args.err, x);
+            } else {
+                const int c0 = 32 * p.j + 4 * q;
+                if (c0 < K) {
+#pragma unroll
+                    for (int i = 0; i < NX; ++i) {
+                        const long long r = row0 + sub + 32 * i;
+                        if (r < B) x[i] = ldg4(S.in.a.h + (size_t)r * K + c0);
+                    }
+                }
+            }
+        };
+        auto consume = [&](const ChunkPos& p, float4 (&x)[NX]) {
+            const uint32_t cnt = (uint32_t)(p.it * nch + p.j);
+            const int s = cnt % nst;
+            mbar_wait(empty + s, ((cnt / nst) & 1) ^ 1);
+            const long long row0 = tile_row0(p.it);
+            const int c0 = 32 * p.j + 4 * q;
+            uint8_t* hi_img = ring + s * STAGE_BYTES;
+#pragma unroll
+            for (int i = 0; i < NX; ++i) {
+                const int r = sub + 32 * i;
+                float4 a = x[i];
+                if (!STAGE1) {
+                    if (row0 + r < B && c0 < K) {
+                        a = act_quad(a, sm_bn, Kp, c0, S.in.a.bn_mode, drop, row0 + r);
+                        if (S.a_out) *reinterpret_cast<float4*>(S.a_out + (size_t)(row0 + r) * K + c0) = a;
+                    } else {
+                        a = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+                float4 hi, lo;
+                split_tf32x4(a, hi, lo);
+                const uint32_t off = sw128_chunk(r, 0, q, TCF_M);
+                sts4(hi_img + off, hi);
+                if (exact) sts4(hi_img + IMG_BYTES + off, lo);
+            }
+            fence_proxy_async();
+            mbar_arrive(full + s);
+            if (gtid == 0 && cnt < 40) trace(2 + cnt, tcode);
+        };
+        chunk_pipeline<2, NX, NX>(my_tiles, nch, grp, issue_idx, issue_data, consume);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) trace(127, tcode);
+    if (warp == TC_MMA_WARP) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------
+// backward stage: per 64-row tile  dX = G . W  (chunk by chunk of 32 input columns, M = 64 accumulators double
+// buffered in TMEM) and  dW += G^T . [A | 1]  (accumulated in TMEM over ALL tiles of the CTA, written once)
+// ------------------------------------------------------------------------------------------
+struct TcBwdSmem {
+    int g, gt, ones, ring, at, wt, msk, xh, stage, bna, bng, red, bars, tmem, total, nst;
+};
+__host__ __device__ inline TcBwdSmem tcb_smem(int K, int N, bool stage1, bool a_bn) {
+    TcBwdSmem s;
+    const int nbn = tc_nblk(N), Kp = (K + 3) & ~3, Np = (N + 3) & ~3;
+    int o = 0;
+    s.g = o; o += 2 * TCB_M * 128 * nbn;              // G   [64 rows][N]      hi, lo
+    s.gt = o; o += 2 * 64 * 128 * 2;                  // G^T [64 n][64 rows]   hi, lo
+    s.ones = o; o += 8 * 128 * 2;                     // [8][64 rows], row 0 = 1 (bias gradient)
+    s.ring = o;
+    int st = 0;
+    s.at = st; st += 2 * 32 * 128 * 2;                // A^T chunk [32 k][64 rows] hi, lo
+    s.wt = st; st += 2 * 32 * 128 * nbn;              // W^T chunk [32 k][N]       hi, lo
+    s.msk = st; st += stage1 ? 0 : TCB_M * 128;       // activation-derivative tile [64 rows][32 k]
+    s.xh = st; st += a_bn ? TCB_M * 128 : 0;          // x-hat tile                 [64 rows][32 k]
+    s.stage = st;
+    int f = 0;
+    const int bna = f; f += 4 * Kp * 4;
+    const int bng = f; f += 5 * Np * 4;
+    const int red = f; f += 4 * 2 * 64 * 4;
+    f = (f + 15) & ~15;
+    const int bars = f; f += 32 * 8;
+    const int tmem = f; f += 16;
+    int nst = (TC_SMEM_MAX - 1024 - o - f) / st;
+    nst = nst > 4 ? 4 : nst;
+    s.nst = nst;
+    o += (nst > 0 ? nst : 0) * st;
+    s.bna = o + bna; s.bng = o + bng; s.red = o + red; s.bars = o + bars; s.tmem = o + tmem;
+    s.total = o + f + 1024;
+    return s;
+}
+__host__ __device__ inline uint32_t tcb_tmem_cols(int K) {
+    const uint32_t need = tc_nch(K) * 32 + 8 + 64;
+    uint32_t c = 32;
+    while (c < need) c <<= 1;
+    return c;
+}
+
+template <bool STAGE1>
+__global__ void __launch_bounds__(TC_THREADS, 1) tower_bwd_tc(const __grid_constant__ BwdArgs args) {
+    const BwdStage& S = args.st[blockIdx.y];
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int K = S.in.K, N = S.N, npad = tc_npad(N), nbn = tc_nblk(N), nch = tc_nch(K);
+    const int Kp = (K + 3) & ~3, Np = (N + 3) & ~3;
+    const bool a_bn = S.a_bn != 0, need_dx = S.need_dx != 0;
+    const TcBwdSmem L = tcb_smem(K, N, STAGE1, a_bn);
+    const int nst = L.nst;
+    uint8_t *G = sm + L.g, *GT = sm + L.gt, *ONES = sm + L.ones, *ring = sm + L.ring;
+    const int G_IMG = TCB_M * 128 * nbn;
+    constexpr int GT_IMG = 64 * 128 * 2, AT_IMG = 32 * 128 * 2;
+    const int WT_IMG = 32 * 128 * nbn;
+    float* sm_bna = reinterpret_cast<float*>(sm + L.bna);
+    float* sm_bng = reinterpret_cast<float*>(sm + L.bng);
+    float* sm_red = reinterpret_cast<float*>(sm + L.red);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L.bars);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + L.tmem);
+    uint64_t *full = bars, *empty = bars + 4, *g_full = bars + 8, *g_empty = bars + 9, *dx_full = bars + 10, *dx_empty = bars + 12,
+             *dw_full = bars + 14;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long B = args.B;
+    const long long ntiles = (B + TCB_M - 1) / TCB_M;
+    const int my_tiles = (long long)blockIdx.x < ntiles ? (int)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+    const bool exact = args.exact != 0;
+    const int tcode = 10 + S.in.stage;
+    const uint32_t tmem_cols = tcb_tmem_cols(K);
+    const uint32_t col_db = nch * 32, col_dx = nch * 32 + 8;
+
+    if (tid == 0) {
+        trace(0, tcode);
+        for (int s = 0; s < 4; ++s) { mbar_init(full + s, TC_GT + 1); mbar_init(empty + s, 1 + TC_EPI_WARPS); }
+        mbar_init(g_full, TC_GT); mbar_init(g_empty, 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(dx_full + b, 1); mbar_init(dx_empty + b, TC_EPI_WARPS * 32); }
+        mbar_init(dw_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == TC_MMA_WARP) tmem_alloc(tmem_slot, tmem_cols);
+    // G^T rows past N and the ones tile never change: written once
+    for (int i = tid; i < (2 * GT_IMG + 8 * 128 * 2) / 16; i += TC_THREADS) reinterpret_cast<uint4*>(GT)[i] = make_uint4(0, 0, 0, 0);
+    if (!STAGE1) stage_bn_params_tc(S.in.a, K, sm_bna, tid, TC_THREADS);
+    if (S.g_mode) {
+        for (int c = tid; c < Np; c += TC_THREADS) {
+            const bool ok = c < N;
+            const float sv = ok ? S.g_var_or_istd[c] : 1.f;
+            const float istd = S.g_mode == 2 ? rsqrtf(sv + BN_EPS) : sv;
+            sm_bng[c] = ok ? S.g_mean[c] : 0.f;
+            sm_bng[Np + c] = istd;
+            sm_bng[2 * Np + c] = ok ? S.g_gamma[c] * istd : 0.f;
+            sm_bng[3 * Np + c] = (ok && S.g_mode == 1) ? S.g_c1[c] : 0.f;
+            sm_bng[4 * Np + c] = (ok && S.g_mode == 1) ? S.g_c2[c] : 0.f;
+        }
+    }
+    __syncthreads();
+    for (int r = tid; r < 64; r += TC_THREADS) *reinterpret_cast<float*>(ONES + sw128_off(0, r, 8)) = 1.f;
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (tid == 0) trace(1, tcode);
+
+    if (warp == TC_MMA_WARP) {
+        // ===================== MMA issuer =====================
+        if (lane == 0 && my_tiles > 0) {
+            const uint32_t idesc32 = make_idesc_tf32(64, 32, false, false), idesc8 = make_idesc_tf32(64, 8, false, false);
+            const uint32_t g_s = smem_u32(G), gt_s = smem_u32(GT), ones_s = smem_u32(ONES), ring_s = smem_u32(ring);
+            const int p0 = exact ? 0 : 2;
+            const int kn = npad >> 3;                        // K steps of dX (over the layer's outputs)
+            uint32_t cnt = 0;
+            for (int it = 0; it < my_tiles; ++it) {
+                mbar_wait(g_full, it & 1);
+                tc_fence_after();
+                for (int j = 0; j < nch; ++j, ++cnt) {
+                    const int s = cnt % nst;
+                    mbar_wait(full + s, (cnt / nst) & 1);
+                    tc_fence_after();
+                    const uint32_t st = ring_s + s * L.stage;
+                    if (need_dx) {
+                        const int b = cnt & 1;
+                        mbar_wait(dx_empty + b, ((cnt >> 1) & 1) ^ 1);
+                        tc_fence_after();
+                        const uint32_t d = tmem_base + col_dx + 32 * b;
+                        for (int p = p0; p < 3; ++p) {
+                            const uint32_t ai = g_s + (p == 0 ? G_IMG : 0), bi = st + L.wt + (p == 1 ? WT_IMG : 0);
+                            for (int ks = 0; ks < kn; ++ks)
+                                umma_tf32(d, tile_desc_k(ai, TCB_M, ks), tile_desc_k(bi, 32, ks), idesc32, !(p == p0 && ks == 0));
+                        }
+                        umma_commit(dx_full + b);
+                    }
+                    {
+                        const uint32_t d = tmem_base + 32 * j;
+                        for (int p = p0; p < 3; ++p) {
+                            const uint32_t ai = gt_s + (p == 0 ? GT_IMG : 0), bi = st + L.at + (p == 1 ? AT_IMG : 0);
+                            for (int ks = 0; ks < 8; ++ks)
+                                umma_tf32(d, tile_desc_k(ai, 64, ks), tile_desc_k(bi, 32, ks), idesc32, !(it == 0 && p == p0 && ks == 0));
+                        }
+                    }
+                    umma_commit(empty + s);
+                }
+                // bias gradient: column sums of G = G^T . 1
+                for (int p = exact ? 0 : 1; p < 2; ++p) {
+                    const uint32_t ai = gt_s + (p == 0 ? GT_IMG : 0);
+                    for (int ks = 0; ks < 8; ++ks)
+                        umma_tf32(tmem_base + col_db, tile_desc_k(ai, 64, ks), tile_desc_k(ones_s, 8, ks), idesc8,
+                                  !(it == 0 && p == (exact ? 0 : 1) && ks == 0));
+                }
+                umma_commit(g_empty);
+                if (it < 16) trace(48 + it, tcode);
+            }
+            umma_commit(dw_full);
+        }
+    } else if (warp < TC_EPI_WARPS) {
+        // ===================== epilogue: M = 64 accumulators, warp q holds rows 16q .. 16q+15 in its lanes 0-15 ======
+        const int q = warp;
+        const bool act = lane < 16;
+        const uint32_t lane_addr = (uint32_t)(32 * q) << 16;
+        const int KE = S.in.g.n_tab * S.in.g.E, n_num = S.in.g.n_num;
+        const float inv_keep = (!STAGE1 && S.in.a.drop.active) ? S.in.a.drop.inv_keep : 1.f;
+        float s1[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, s2[2][2] = {{0.f, 0.f}, {0.f, 0.f}};   // [chunk][owned column], stage > 1: K <= 64
+        uint32_t cnt = 0;
+        for (int it = 0; it < my_tiles; ++it) {
+            const long long row0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * TCB_M;
+            const long long row = row0 + 16 * q + lane;
+            const bool valid = act && row < B;
+            for (int j = 0; j < nch; ++j, ++cnt) {
+                const int s = cnt % nst;
+                const uint8_t* st = ring + s * L.stage;
+                float v[32];
+                if (need_dx) {
+                    const int b = cnt & 1;
+                    mbar_wait(dx_full + b, (cnt >> 1) & 1);
+                    tc_fence_after();
+                    tmem_ld32(tmem_base + col_dx + 32 * b + lane_addr, v);
+                    tc_fence_before();
+                    mbar_arrive(dx_empty + b);
+                    if (STAGE1) {
+                        if (valid) {
+#pragma unroll
+                            for (int i = 0; i < 32; i += 4) {
+                                const int c = 32 * j + i;
+                                if (c + 3 < KE) {
+                                    if (S.dx_emb) *reinterpret_cast<float4*>(S.dx_emb + (size_t)row * KE + c) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                                } else {
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) {
+                                        const int ce = c + e;
+                                        if (ce < KE) { if (S.dx_emb) S.dx_emb[(size_t)row * KE + ce] = v[i + e]; }
+                                        else if (ce < K && S.dx_num) S.dx_num[(size_t)row * n_num + (ce - KE)] = v[i + e];
+                                    }
+                                }
+                            }
+                        }
+                    } else {
+                        // dy = dX * d(act)/d(pre-activation); the producers left that factor (and x-hat) in the ring stage
+                        const int rl = 16 * q + (lane & 15);
+                        float xs[32];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float4 m4 = *reinterpret_cast<const float4*>(st + L.msk + sw128_chunk(rl, 0, i, TCB_M));
+                            v[4 * i] *= m4.x; v[4 * i + 1] *= m4.y; v[4 * i + 2] *= m4.z; v[4 * i + 3] *= m4.w;
+                        }
+                        if (a_bn) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const float4 x4 = *reinterpret_cast<const float4*>(st + L.xh + sw128_chunk(rl, 0, i, TCB_M));
+                                xs[4 * i] = x4.x; xs[4 * i + 1] = x4.y; xs[4 * i + 2] = x4.z; xs[4 * i + 3] = x4.w;
+                            }
+                        }
+                        if (valid) {
+                            float* dst = S.dy_out + (size_t)row * K + 32 * j;
+#pragma unroll
+                            for (int i = 0; i < 32; i += 4)
+                                if (32 * j + i < K) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                        }
+                        if (a_bn) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) {
+                                v[i] = valid ? v[i] : 0.f;
+                                xs[i] = v[i] * xs[i];
+                            }
+                            Halve<32, 8>::run(v, lane);
+                            Halve<32, 8>::run(xs, lane);
+                            if (j == 0) { s1[0][0] += v[0]; s1[0][1] += v[1]; s2[0][0] += xs[0]; s2[0][1] += xs[1]; }
+                            else { s1[1][0] += v[0]; s1[1][1] += v[1]; s2[1][0] += xs[0]; s2[1][1] += xs[1]; }
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty + s);       // this warp no longer reads the stage's mask / x-hat tiles
+            }
+            if (tid == 0 && it < 16) trace(64 + it, tcode);
+        }
+        // ---- BatchNorm-backward sums of this CTA: four warps (16 rows each) added in warp order ----
+        if (a_bn && need_dx) {
+            if (act) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        sm_red[(q * 2 + 0) * 64 + 32 * j + 2 * lane + k] = s1[j][k];
+                        sm_red[(q * 2 + 1) * 64 + 32 * j + 2 * lane + k] = s2[j][k];
+                    }
+            }
+            named_bar_sync(1, TC_EPI_WARPS * 32);
+            float* P = S.sum_part + (size_t)blockIdx.x * 2 * K;
+            if (tid < 2 * K) {
+                const int which = tid >= K, c = tid - which * K;
+                float t = 0.f;
+#pragma unroll
+                for (int w = 0; w < TC_EPI_WARPS; ++w) t += sm_red[(w * 2 + which) * 64 + c];
+                P[which * K + c] = t;
+            }
+        }
+        // ---- weight-gradient partial of this CTA: TMEM [64 n][K (+ bias column)] -> global, layer column order ----
+        {
+            float* P = S.dW_part + (size_t)blockIdx.x * N * (K + 1);
+            const int n = 16 * q + lane;
+            if (my_tiles > 0) {
+                mbar_wait(dw_full, 0);
+                tc_fence_after();
+            }
+            for (int j = 0; j <= nch; ++j) {
+                float v[32];
+                if (my_tiles > 0) {
+                    if (j < nch) tmem_ld32(tmem_base + 32 * j + lane_addr, v);
+                    else {
+                        float w8[16];
+                        tmem_ld16(tmem_base + col_db + lane_addr, w8);      // 8 columns used; 16 is the narrowest helper
+                        v[0] = w8[0];
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = 0.f;
+                }
+                if (act && n < N) {
+                    if (j < nch) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const int c = 32 * j + i;
+                            if (c < K) P[(size_t)n * (K + 1) + (STAGE1 ? gcol_stage1(c, KE, n_num) : c)] = v[i];
+                        }
+                    } else {
+                        P[(size_t)n * (K + 1) + K] = v[0];
+                    }
+                }
+            }
+            tc_fence_before();
+        }
+    } else {
+        // ===================== producers =====================
+        const int ptid = tid - TC_PROD_WARP0 * 32;
+        const int grp = ptid / TC_GT, gtid = ptid - grp * TC_GT;
+        const int q = gtid & 7, sub = gtid >> 3;
+        const GatherSrc& g = S.in.g;
+        const float inv_keep = (!STAGE1 && S.in.a.drop.active) ? S.in.a.drop.inv_keep : 1.f;
+        constexpr int NXR = TCB_M / 32;                        // rows per thread and chunk
+        constexpr int NX = STAGE1 ? NXR : 2 * NXR;             // stage > 1 also loads the pre-activation (x-hat)
+        auto tile_row0 = [&](int it) { return ((long long)blockIdx.x + (long long)it * gridDim.x) * TCB_M; };
+
+        // G and G^T of tile `it` (group 0 only: it owns chunk 0 of every tile).  g = incoming gradient, through the
+        // BatchNorm backward of this layer's output when there is one.
+        const int qpr = npad >> 2;                            // quads per G row
+        auto build_g = [&](int it) {
+            const long long row0 = tile_row0(it);
+            const int nq = TCB_M * qpr;                        // <= 1024: at most four quads per thread
+            float4 gq[4], hq[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int id = gtid + u * TC_GT;
+                gq[u] = make_float4(0.f, 0.f, 0.f, 0.f); hq[u] = gq[u];
+                if (id < nq) {
+                    const int r = id / qpr, c0 = 4 * (id - r * qpr);
+                    if (row0 + r < B && c0 < N) {
+                        gq[u] = ldg4(S.gin + (size_t)(row0 + r) * N + c0);
+                        if (S.g_mode == 1) hq[u] = ldg4(S.hs + (size_t)(row0 + r) * N + c0);
+                    }
+                }
+            }
+            if (it > 0) mbar_wait(g_empty, (it - 1) & 1);      // the MMAs of the previous tile have read G / G^T
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int id = gtid + u * TC_GT;
+                if (id < nq) {
+                    const int r = id / qpr, qq = id - r * qpr, c0 = 4 * qq;
+                    float gv[4] = {gq[u].x, gq[u].y, gq[u].z, gq[u].w};
+                    if (row0 + r < B && c0 < N) {
+                        if (S.g_mode == 1) {
+                            const float hv[4] = {hq[u].x, hq[u].y, hq[u].z, hq[u].w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const int c = c0 + e;
+                                const float xh = (hv[e] - sm_bng[c]) * sm_bng[Np + c];
+                                gv[e] = sm_bng[2 * Np + c] * (gv[e] - sm_bng[3 * Np + c] - xh * sm_bng[4 * Np + c]);
+                            }
+                        } else if (S.g_mode == 2) {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) gv[e] *= sm_bng[2 * Np + c0 + e];
+                        }
+                    }
+                    float4 hi, lo;
+                    split_tf32x4(make_float4(gv[0], gv[1], gv[2], gv[3]), hi, lo);
+                    const uint32_t off = sw128_chunk(r, qq >> 3, qq & 7, TCB_M);
+                    sts4(G + off, hi);
+                    sts4(G + G_IMG + off, lo);
+                }
+            }
+            named_bar_sync(2, TC_GT);
+            // transpose through shared memory: lane <-> batch row, so the scattered 4-byte stores of one instruction
+            // fall into one 128-byte row of G^T (conflict-free)
+            {
+                const int r = gtid & 63;
+                for (int qq = gtid >> 6; qq < qpr; qq += TC_GT / 64) {
+                    const uint32_t off = sw128_chunk(r, qq >> 3, qq & 7, TCB_M);
+                    const float4 hi = *reinterpret_cast<const float4*>(G + off), lo = *reinterpret_cast<const float4*>(G + G_IMG + off);
+                    const float h4[4] = {hi.x, hi.y, hi.z, hi.w}, l4[4] = {lo.x, lo.y, lo.z, lo.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const uint32_t o2 = sw128_off(4 * qq + e, r, 64);
+                        *reinterpret_cast<float*>(GT + o2) = h4[e];
+                        *reinterpret_cast<float*>(GT + GT_IMG + o2) = l4[e];
+                    }
+                }
+            }
+            fence_proxy_async();
+            mbar_arrive(g_full);
+        };
+
+        auto issue_idx = [&](const ChunkPos& p, long long (&ix)[NXR]) {
+#pragma unroll
+            for (int i = 0; i < NXR; ++i) ix[i] = 0;
+            if (STAGE1 && p.it < my_tiles) gather_issue_idx<NXR>(g, B, tile_row0(p.it), p.j, q, sub, ix);
+        };
+        auto issue_data = [&](const ChunkPos& p, const long long (&ix)[NXR], float4 (&x)[NX]) {
+#pragma unroll
+            for (int i = 0; i < NX; ++i) x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.it >= my_tiles) return;
+            const long long row0 = tile_row0(p.it);
+            if (STAGE1) {
+                gather_issue_data<NXR>(g, B, row0, p.j, q, sub, ix, nullptr, x);
+            } else {
+                const int c0 = 32 * p.j + 4 * q;
+                if (c0 < K) {
+#pragma unroll
+                    for (int i = 0; i < NXR; ++i) {
+                        const long long r = row0 + sub + 32 * i;
+                        if (r < B) {
+                            x[i] = ldg4(S.in.a.a_post + (size_t)r * K + c0);
+                            if (a_bn) x[NXR + i] = ldg4(S.in.a.h + (size_t)r * K + c0);
+                        }
+                    }
+                }
+            }
+        };
+        auto consume = [&](const ChunkPos& p, float4 (&x)[NX]) {
+            if (grp == 0 && p.j == 0) build_g(p.it);
+            const uint32_t cnt = (uint32_t)(p.it * nch + p.j);
+            const int s = cnt % nst;
+            mbar_wait(empty + s, ((cnt / nst) & 1) ^ 1);
+            uint8_t* st = ring + s * L.stage;
+            if (gtid == 0) {
+                if (need_dx) {
+                    mbar_expect_tx(full + s, (uint32_t)(2 * WT_IMG));
+                    bulk_g2s(st + L.wt, S.wtimg + (size_t)p.j * tc_wt_chunk_floats(N), (uint32_t)(2 * WT_IMG), full + s);
+                } else {
+                    mbar_arrive(full + s);
+                }
+            }
+            const int c0 = 32 * p.j + 4 * q;
+#pragma unroll
+            for (int i = 0; i < NXR; ++i) {
+                const int r = sub + 32 * i;
+                const float4 a = x[i];
+                if (!STAGE1) {
+                    // derivative of a = dropout(relu(.)) w.r.t. its argument, and x-hat, for the epilogue
+                    const float4 m4 = make_float4(a.x > 0.f ? inv_keep : 0.f, a.y > 0.f ? inv_keep : 0.f, a.z > 0.f ? inv_keep : 0.f,
+                                                  a.w > 0.f ? inv_keep : 0.f);
+                    sts4(st + L.msk + sw128_chunk(r, 0, q, TCB_M), m4);
+                    if (a_bn) {
+                        const float4 h = x[NXR + i];
+                        float4 xh = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (c0 < K) {
+                            const float4 m = *reinterpret_cast<const float4*>(sm_bna + c0), is = *reinterpret_cast<const float4*>(sm_bna + Kp + c0);
+                            xh = make_float4((h.x - m.x) * is.x, (h.y - m.y) * is.y, (h.z - m.z) * is.z, (h.w - m.w) * is.w);
+                        }
+                        sts4(st + L.xh + sw128_chunk(r, 0, q, TCB_M), xh);
+                    }
+                }
+                float4 hi, lo;
+                split_tf32x4(a, hi, lo);
+                const float h4[4] = {hi.x, hi.y, hi.z, hi.w}, l4[4] = {lo.x, lo.y, lo.z, lo.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const uint32_t o2 = sw128_off(4 * q + e, r, 32);
+                    *reinterpret_cast<float*>(st + L.at + o2) = h4[e];
+                    if (exact) *reinterpret_cast<float*>(st + L.at + AT_IMG + o2) = l4[e];
+                }
+            }
+            fence_proxy_async();
+            mbar_arrive(full + s);
+            if (gtid == 0 && cnt < 40) trace(2 + cnt, tcode);
+        };
+        chunk_pipeline<2, NX, NXR>(my_tiles, nch, grp, issue_idx, issue_data, consume);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) trace(127, tcode);
+    if (warp == TC_MMA_WARP) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static int st_N(const cfm_tower_t& t, int s) { return (int)(s == 1 ? t.h1 : s == 2 ? t.h2 : t.d_out); }
+static int st_K(const cfm_tower_t& t, int s) { return (int)(s == 1 ? t.n_num + t.n_tables * t.emb_dim : s == 2 ? t.h1 : t.h2); }
+static void tower_dims(const cfm_tower_t& t, int (&K)[3], int (&N)[3]) {
+    for (int s = 1; s <= 3; ++s) { K[s - 1] = st_K(t, s); N[s - 1] = st_N(t, s); }
+}
+
+bool tc_fwd_supported(const cfm_tower_t& t, int s) {
+    if (!t.wimg || !t.a1 || !t.a2) return false;
+    const int K = st_K(t, s), N = st_N(t, s);
+    if (N > 64 || K > 256) return false;
+    if (s == 1) {
+        if (t.n_tables > 0 && (t.emb_dim & 3)) return false;
+    } else if (K & 3) return false;
+    return tcf_smem(K, N).nst >= 2;
+}
+
+bool tc_bwd_supported(const cfm_tower_t& t, int s, bool a_bn, bool need_dx) {
+    if (!tc_fwd_supported(t, s)) return false;            // the forward of this layer saved what the backward reads
+    const int K = st_K(t, s), N = st_N(t, s);
+    if (N & 3) return false;
+    if (s > 1 && K > 64) return false;
+    (void)need_dx;
+    return tcb_smem(K, N, s == 1, a_bn).nst >= 2;
+}
+
+int tc_prep_launch(const cfm_tower_t* towers, int n_towers, cudaStream_t stream) {
+    PrepArgs a{};
+    bool any = false;
+    for (int i = 0; i < n_towers; ++i) {
+        const cfm_tower_t& t = towers[i];
+        PrepTower& P = a.t[i];
+        P.W[0] = t.w1; P.W[1] = t.w2; P.W[2] = t.w3;
+        tower_dims(t, P.K, P.N);
+        P.KE = (int)(t.n_tables * t.emb_dim); P.n_num = (int)t.n_num;
+        P.img = t.wimg;
+        any |= t.wimg != nullptr;
+    }
+    if (!any) return CFM_OK;
+    tc_prep_weights<<<dim3(16, (unsigned)n_towers), 256, 0, stream>>>(a);
+    CFM_LAUNCH_CHECK();
+    return CFM_OK;
+}
+
+int tc_fwd_launch(FwdArgs& a, const cfm_tower_t* towers, int n_towers, int s, int* ctas_out, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        CFM_CHECK_CUDA(cudaFuncSetAttribute(tower_fwd_tc<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX));
+        CFM_CHECK_CUDA(cudaFuncSetAttribute(tower_fwd_tc<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX));
+        CFM_CHECK_CUDA(cudaFuncSetAttribute(tower_fwd_tc<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX));
+        CFM_CHECK_CUDA(cudaFuncSetAttribute(tower_fwd_tc<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX));
+        attr_set = true;
+    }
+    size_t smem = 0;
+    int nc = 32;
+    for (int i = 0; i < n_towers; ++i) {
+        const cfm_tower_t& t = towers[i];
+        int K[3], N[3];
+        tower_dims(t, K, N);
+        const WImgLayout L = wimg_layout(K, N);
+        a.st[i].wimg = t.wimg + L.w[s - 1];
+        a.st[i].a_out = s == 2 ? t.a1 : s == 3 ? t.a2 : nullptr;
+        smem = std::max(smem, (size_t)tcf_smem(K[s - 1], N[s - 1]).total);
+        if (tc_npad(N[s - 1]) > 32) nc = 64;
+    }
+    const long long ntiles = (a.B + TCF_M - 1) / TCF_M;
+    const int ctas = (int)std::min<long long>(ntiles, sm_count());
+    *ctas_out = ctas;
+    const dim3 grid(ctas, (unsigned)n_towers);
+    if (s == 1) {
+        if (nc == 64) tower_fwd_tc<64, true><<<grid, TC_THREADS, smem, stream>>>(a);
+        else tower_fwd_tc<32, true><<<grid, TC_THREADS, smem, stream>>>(a);
+    } else {
+        if (nc == 64) tower_fwd_tc<64, false><<<grid, TC_THREADS, smem, stream>>>(a);
+        else tower_fwd_tc<32, false><<<grid, TC_THREADS, smem, stream>>>(a);
+    }
+    CFM_LAUNCH_CHECK();
+    return CFM_OK;
+}
+
+int tc_bwd_launch(BwdArgs& a, const cfm_tower_t* towers, int n_towers, int s, int* ctas_out, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        CFM_CHECK_CUDA(cudaFuncSetAttribute(tower_bwd_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX));
+        CFM_CHECK_CUDA(cudaFuncSetAttribute(tower_bwd_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX));
+        attr_set = true;
+    }
+    size_t smem = 0;
+    for (int i = 0; i < n_towers; ++i) {
+        const cfm_tower_t& t = towers[i];
+        int K[3], N[3];
+        tower_dims(t, K, N);
+        const WImgLayout L = wimg_layout(K, N);
+        a.st[i].wtimg = t.wimg + L.wt[s - 1];
+        a.st[i].in.a.a_post = s == 2 ? t.a1 : s == 3 ? t.a2 : nullptr;
+        smem = std::max(smem, (size_t)tcb_smem(K[s - 1], N[s - 1], s == 1, a.st[i].a_bn != 0).total);
+    }
+    const long long ntiles = (a.B + TCB_M - 1) / TCB_M;
+    const int ctas = (int)std::min<long long>(ntiles, sm_count());
+    *ctas_out = ctas;
+    const dim3 grid(ctas, (unsigned)n_towers);
+    if (s == 1) tower_bwd_tc<true><<<grid, TC_THREADS, smem, stream>>>(a);
+    else tower_bwd_tc<false><<<grid, TC_THREADS, smem, stream>>>(a);
+    CFM_LAUNCH_CHECK();
+    return CFM_OK;
+}
+
+}  // namespace cfm
+
+extern "C" int cfm_debug_set_trace(uint64_t* buf, int64_t code) {
+    const int c = (int)code;
+    CFM_CHECK_CUDA(cudaMemcpyToSymbol(cfm::g_trace, &buf, sizeof(buf)));
+    CFM_CHECK_CUDA(cudaMemcpyToSymbol(cfm::g_trace_code, &c, sizeof(c)));
+    return CFM_OK;
+}
+
+extern "C" int64_t cfm_tower_wimg_floats(const cfm_tower_t* t) {
+    int K[3], N[3];
+    cfm::tower_dims(*t, K, N);
+    return cfm::wimg_layout(K, N).total;
+}

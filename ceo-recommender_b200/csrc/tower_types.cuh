@@ -25,6 +25,7 @@ struct ActSrc {           // a = dropout(relu(bn(h)))
     int bn_mode;          // 0 none, 1 batch stats (mean, istd), 2 running stats (mean, var)
     const float *mean, *var_or_istd, *gamma, *beta;
     DropCtx drop;
+    const float* a_post;  // tcgen05 backward: a itself as saved by the forward stage (nullable)
 };
 
 struct InputDesc {        // how a stage's [TM, K] input tile is built
@@ -61,12 +62,15 @@ struct FwdStage {
     const float* bias;    // [N]
     float* hout;          // [B,N]
     float* stat_part;     // nullable: per-CTA (mean[N], M2[N], count) partials
+    const float* wimg;    // tcgen05 path: forward weight image of this layer (tower_tc.cuh)
+    float* a_out;         // tcgen05 path, stage > 1: where the producers save the input activation a (nullable)
 };
 struct FwdArgs {
     FwdStage st[2];
     long long B;
     int* err;
     int tm;               // rows per tile: 64 (2 row groups x 4 column groups of warps) or 32 (1 x 8)
+    int exact;            // tcgen05 path: 1 = three (hi, lo) passes, 0 = single TF32 pass
 };
 
 struct BwdStage {
@@ -84,11 +88,13 @@ struct BwdStage {
     float* dx_emb;        // stage 1, nullable: [B, n_tab*E]
     float* dx_num;        // stage 1, nullable: [B, n_num]
     int need_dx;          // run the dX GEMM
+    const float* wtimg;   // tcgen05 path: transposed weight image of this layer (tower_tc.cuh)
 };
 struct BwdArgs {
     BwdStage st[2];
     long long B;
     int tm;               // rows per tile, see FwdArgs
+    int exact;            // see FwdArgs
 };
 
 

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define CFM_ABI_VERSION 1
+#define CFM_ABI_VERSION 2
 #define CFM_MAX_TABLES 16
 
 #define CFM_OK 0
@@ -79,10 +79,18 @@ typedef struct cfm_tower {
     float *out;                  /* [B,d_out] tower output (pre-normalisation latent / logits) */
     float *bn1_stat, *bn2_stat;  /* [4,h]: batch mean, 1/sqrt(var+eps), and the two BN-backward batch means */
     float *scratch;              /* per-CTA partials: >= tower_ctas * cfm_tower_scratch_floats() floats */
+    float *wimg;                 /* cfm_tower_wimg_floats() floats: (hi, lo)-split, swizzled images of the three weight
+                                    matrices for the tcgen05 stage kernels, rebuilt by every cfm_towers_fwd call and read
+                                    by the cfm_towers_bwd call that follows it.  NULL: the mma.sync stage kernels run. */
+    float *a1, *a2;              /* [B,h1], [B,h2]: post-activation inputs of Linear 2 / 3 (dropout applied), written by the
+                                    tcgen05 forward stages so that the backward needs neither BatchNorm nor the dropout
+                                    stream again; required (non-NULL) together with wimg */
 } cfm_tower_t;
 
 /* floats of `scratch` needed per persistent CTA for this tower shape (fwd and bwd share it) */
 int64_t cfm_tower_scratch_floats(const cfm_tower_t* t);
+/* floats of `wimg` for this tower shape */
+int64_t cfm_tower_wimg_floats(const cfm_tower_t* t);
 
 /* Forward of `n_towers` towers over the same B rows in one set of launches.
  * training=1: batch-stat BN (running stats updated), dropout drawn from a counter-based
@@ -323,6 +331,19 @@ int cfm_topk_merge(const void* part_score, int64_t score_is_f64, const int64_t* 
  * (contrastive.py:312-320), scores formed in fp64 from the fp32 operands */
 int cfm_allpairs_rank(const float* rows_f32, const float* cols_f32, int64_t R, int64_t C, int64_t D,
                       const int64_t* target_col /* [R] */, int64_t* rank /* [R] */, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Self-test of the tensor-core building blocks of the tower kernels (tcgen05 kind::tf32 on (hi, lo)-split fp32
+ * operands in 128-byte-swizzled shared-memory column blocks).  One CTA computes
+ *   mode 0: D[M,N] = A[M,K] . B[N,K]^T    mode 1: D[M,N] = A[K,M]^T . B[K,N]    mode 2: D[M,N] = A[M,K] . B[K,N]
+ * (A, B row-major fp32 in global memory; M in {64,128}; passes 3 = fp32-class, 1 = single TF32 pass) and dumps the
+ * raw TMEM accumulator as out[128 lanes][cols], cols = N rounded up to a power of two >= 32.
+ * ------------------------------------------------------------------------------------------ */
+/* debug: per-CTA globaltimer trace of the tcgen05 tower kernels (buffer of n_ctas * 128 uint64, NULL = off);
+ * code = 10 * (0 forward, 1 backward) + stage selects the launches that record */
+int cfm_debug_set_trace(uint64_t* buf, int64_t code);
+int cfm_tc_selftest(const float* A, const float* B, float* out, int64_t mode, int64_t M, int64_t N, int64_t K,
+                    int64_t passes, void* stream);
 
 #ifdef __cplusplus
 }
