@@ -124,6 +124,7 @@ PROTOTYPES = {
     "cfm_topk_merge": (C.c_int, [_V, _I, _V, _I, _I, _I, _V, _V, _V]),
     "cfm_allpairs_rank": (C.c_int, [_V, _V, _I, _I, _I, _V, _V, _V]),
     "cfm_debug_set_trace": (C.c_int, [_V, _I]),
+    "cfm_tc_mma_probe": (C.c_int, [_V, _I, _I, _I, _I, _V]),
     "cfm_tc_selftest": (C.c_int, [_V, _V, _V, _I, _I, _I, _I, _I, _V]),
 }
 

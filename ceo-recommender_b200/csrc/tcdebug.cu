@@ -96,3 +96,52 @@ extern "C" int cfm_tc_selftest(const float* A, const float* B, float* out, int64
     CFM_LAUNCH_CHECK();
     return CFM_OK;
 }
+
+// Timing probe: `reps` back-to-back tcgen05.mma kind::tf32 (M x N x 8 each, operands = whatever is in shared memory)
+// rotating over `nacc` TMEM accumulators; out[0] = cycles from first issue to completion (one thread's clock64).
+namespace cfm {
+__global__ void __launch_bounds__(128, 1) tc_mma_probe(long long* out, int M, int N, int reps, int nacc) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < 48 * 1024 / 16; i += 128) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0, 0, 0, 0);
+    if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+    if (warp == 0) tmem_alloc(&tmem_slot, 512);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    if (warp == 0) {
+        // whole warp walks the loop (uniform control flow); one elected lane issues
+        const uint32_t idesc = make_idesc_tf32(M, N, false, false);
+        const uint32_t a = smem_u32(sm), b = smem_u32(sm) + 16384;
+        const long long t0 = clock64();
+        int acc = 0;
+        for (int r = 0; r < reps; ++r) {
+            if (elect_one())
+                umma_tf32(tmem + (uint32_t)acc * (uint32_t)N, desc_kmajor_sw128(a + (r & 3) * 32), desc_kmajor_sw128(b + (r & 3) * 32), idesc, r >= nacc);
+            __syncwarp();
+            if (++acc == nacc) acc = 0;
+        }
+        const long long t1 = clock64();
+        if (elect_one()) umma_commit(&bar);
+        __syncwarp();
+        mbar_wait(&bar, 0);
+        const long long t2 = clock64();
+        if (tid == 0) { out[0] = t2 - t0; out[1] = t1 - t0; }
+    }
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+}  // namespace cfm
+
+extern "C" int cfm_tc_mma_probe(long long* out, int64_t M, int64_t N, int64_t reps, int64_t nacc, void* stream_) {
+    CFM_REQUIRE(out && (M == 64 || M == 128) && N >= 8 && N <= 256 && nacc >= 1 && nacc * N <= 512, CFM_ERR_INVALID, "bad probe shape");
+    CFM_CHECK_CUDA(cudaFuncSetAttribute(cfm::tc_mma_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 50 * 1024));
+    cfm::tc_mma_probe<<<1, 128, 50 * 1024, (cudaStream_t)stream_>>>(out, (int)M, (int)N, (int)reps, (int)nacc);
+    CFM_LAUNCH_CHECK();
+    return CFM_OK;
+}

@@ -326,10 +326,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tower_fwd_tc(const __grid_const
 
     if (warp == TC_MMA_WARP) {
         // ===================== MMA issuer =====================
-        if (lane == 0 && my_tiles > 0) {
-            mbar_expect_tx(w_full, (uint32_t)(nch * chunk_bytes));
-            for (int j = 0; j < nch; ++j)
-                bulk_g2s(sm + L.w + j * chunk_bytes, S.wimg + (size_t)j * tc_w_chunk_floats(N), (uint32_t)chunk_bytes, w_full);
+        // The whole warp walks the loops (warp-uniform control flow keeps descriptors in uniform registers); one
+        // elected lane issues the tcgen05 instructions.
+        if (my_tiles > 0) {
+            if (elect_one()) {
+                mbar_expect_tx(w_full, (uint32_t)(nch * chunk_bytes));
+                for (int j = 0; j < nch; ++j)
+                    bulk_g2s(sm + L.w + j * chunk_bytes, S.wimg + (size_t)j * tc_w_chunk_floats(N), (uint32_t)chunk_bytes, w_full);
+            }
+            __syncwarp();
             mbar_wait(w_full, 0);
             const uint32_t idesc = make_idesc_tf32(TCF_M, npad, false, false);
             const uint32_t w_s = smem_u32(sm + L.w), ring_s = smem_u32(sm + L.ring);
@@ -348,16 +353,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tower_fwd_tc(const __grid_const
                     const uint32_t a_hi = ring_s + s * STAGE_BYTES, a_lo = a_hi + IMG_BYTES;
                     const uint32_t b_hi = w_s + j * chunk_bytes, b_lo = b_hi + npad * 128;
                     const int ksn = j == nch - 1 ? ks_last : 4;
-                    for (int p = p0; p < 3; ++p) {
-                        const uint32_t ai = p == 0 ? a_lo : a_hi, bi = p == 1 ? b_lo : b_hi;
-                        for (int ks = 0; ks < ksn; ++ks)
-                            umma_tf32(d, desc_kmajor_sw128(ai + ks * 32), desc_kmajor_sw128(bi + ks * 32), idesc,
-                                      !(j == 0 && p == p0 && ks == 0));
+                    if (elect_one()) {
+                        for (int p = p0; p < 3; ++p) {
+                            const uint32_t ai = p == 0 ? a_lo : a_hi, bi = p == 1 ? b_lo : b_hi;
+                            for (int ks = 0; ks < ksn; ++ks)
+                                umma_tf32(d, desc_kmajor_sw128(ai + ks * 32), desc_kmajor_sw128(bi + ks * 32), idesc,
+                                          !(j == 0 && p == p0 && ks == 0));
+                        }
+                        umma_commit(empty + s);
+                        if (j == nch - 1) umma_commit(d_full + buf);
                     }
-                    umma_commit(empty + s);
+                    __syncwarp();
                 }
-                umma_commit(d_full + buf);
-                if (it < 16) trace(48 + it, tcode);
+                if (lane == 0 && it < 16) trace(48 + it, tcode);
             }
         }
     } else if (warp < TC_EPI_WARPS) {
@@ -642,8 +650,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tower_bwd_tc(const __grid_const
     if (tid == 0) trace(1, tcode);
 
     if (warp == TC_MMA_WARP) {
-        // ===================== MMA issuer =====================
-        if (lane == 0 && my_tiles > 0) {
+        // ===================== MMA issuer (whole warp in the loops, one elected lane issues) =====================
+        if (my_tiles > 0) {
             const uint32_t idesc32 = make_idesc_tf32(64, 32, false, false), idesc8 = make_idesc_tf32(64, 8, false, false);
             const uint32_t g_s = smem_u32(G), gt_s = smem_u32(GT), ones_s = smem_u32(ONES), ring_s = smem_u32(ring);
             const int p0 = exact ? 0 : 2;
@@ -657,39 +665,44 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tower_bwd_tc(const __grid_const
                     mbar_wait(full + s, (cnt / nst) & 1);
                     tc_fence_after();
                     const uint32_t st = ring_s + s * L.stage;
+                    const int b = cnt & 1;
                     if (need_dx) {
-                        const int b = cnt & 1;
                         mbar_wait(dx_empty + b, ((cnt >> 1) & 1) ^ 1);
                         tc_fence_after();
-                        const uint32_t d = tmem_base + col_dx + 32 * b;
-                        for (int p = p0; p < 3; ++p) {
-                            const uint32_t ai = g_s + (p == 0 ? G_IMG : 0), bi = st + L.wt + (p == 1 ? WT_IMG : 0);
-                            for (int ks = 0; ks < kn; ++ks)
-                                umma_tf32(d, tile_desc_k(ai, TCB_M, ks), tile_desc_k(bi, 32, ks), idesc32, !(p == p0 && ks == 0));
-                        }
-                        umma_commit(dx_full + b);
                     }
-                    {
+                    if (elect_one()) {
+                        if (need_dx) {
+                            const uint32_t d = tmem_base + col_dx + 32 * b;
+                            for (int p = p0; p < 3; ++p) {
+                                const uint32_t ai = g_s + (p == 0 ? G_IMG : 0), bi = st + L.wt + (p == 1 ? WT_IMG : 0);
+                                for (int ks = 0; ks < kn; ++ks)
+                                    umma_tf32(d, tile_desc_k(ai, TCB_M, ks), tile_desc_k(bi, 32, ks), idesc32, !(p == p0 && ks == 0));
+                            }
+                            umma_commit(dx_full + b);
+                        }
                         const uint32_t d = tmem_base + 32 * j;
                         for (int p = p0; p < 3; ++p) {
                             const uint32_t ai = gt_s + (p == 0 ? GT_IMG : 0), bi = st + L.at + (p == 1 ? AT_IMG : 0);
                             for (int ks = 0; ks < 8; ++ks)
                                 umma_tf32(d, tile_desc_k(ai, 64, ks), tile_desc_k(bi, 32, ks), idesc32, !(it == 0 && p == p0 && ks == 0));
                         }
+                        umma_commit(empty + s);
+                        if (j == nch - 1) {
+                            // bias gradient: column sums of G = G^T . 1
+                            for (int p = exact ? 0 : 1; p < 2; ++p) {
+                                const uint32_t ai = gt_s + (p == 0 ? GT_IMG : 0);
+                                for (int ks = 0; ks < 8; ++ks)
+                                    umma_tf32(tmem_base + col_db, tile_desc_k(ai, 64, ks), tile_desc_k(ones_s, 8, ks), idesc8,
+                                              !(it == 0 && p == (exact ? 0 : 1) && ks == 0));
+                            }
+                            umma_commit(g_empty);
+                            if (it == my_tiles - 1) umma_commit(dw_full);
+                        }
                     }
-                    umma_commit(empty + s);
+                    __syncwarp();
                 }
-                // bias gradient: column sums of G = G^T . 1
-                for (int p = exact ? 0 : 1; p < 2; ++p) {
-                    const uint32_t ai = gt_s + (p == 0 ? GT_IMG : 0);
-                    for (int ks = 0; ks < 8; ++ks)
-                        umma_tf32(tmem_base + col_db, tile_desc_k(ai, 64, ks), tile_desc_k(ones_s, 8, ks), idesc8,
-                                  !(it == 0 && p == (exact ? 0 : 1) && ks == 0));
-                }
-                umma_commit(g_empty);
-                if (it < 16) trace(48 + it, tcode);
+                if (lane == 0 && it < 16) trace(48 + it, tcode);
             }
-            umma_commit(dw_full);
         }
     } else if (warp < TC_EPI_WARPS) {
         // ===================== epilogue: M = 64 accumulators, warp q holds rows 16q .. 16q+15 in its lanes 0-15 ======

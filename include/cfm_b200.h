@@ -342,6 +342,8 @@ int cfm_allpairs_rank(const float* rows_f32, const float* cols_f32, int64_t R, i
 /* debug: per-CTA globaltimer trace of the tcgen05 tower kernels (buffer of n_ctas * 128 uint64, NULL = off);
  * code = 10 * (0 forward, 1 backward) + stage selects the launches that record */
 int cfm_debug_set_trace(uint64_t* buf, int64_t code);
+/* timing probe: reps back-to-back M x N x 8 tcgen05.mma over nacc accumulators; out[0] = cycles to completion, out[1] = issue cycles */
+int cfm_tc_mma_probe(long long* out, int64_t M, int64_t N, int64_t reps, int64_t nacc, void* stream);
 int cfm_tc_selftest(const float* A, const float* B, float* out, int64_t mode, int64_t M, int64_t N, int64_t K,
                     int64_t passes, void* stream);
 
