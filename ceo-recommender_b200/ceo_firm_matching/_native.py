@@ -99,7 +99,7 @@ PROTOTYPES = {
     "cfm_emb_grad_segment_reduce": (C.c_int, [_V, _V, _I, _I, _I, C.POINTER(C.c_void_p), C.POINTER(i64),
                                               _V, _V, _V, _V, _V, _I, _V]),
     "cfm_emb_grad_rezero": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(i64), _I, _I, _V, _I, _V]),
-    "cfm_emb_grad_joint_reduce": (C.c_int, [C.POINTER(EmbGroup), _I, _I, _V, _V, _V, _V, _V, _I, _V]),
+    "cfm_emb_grad_joint_reduce": (C.c_int, [C.POINTER(EmbGroup), _I, _I, _I, _V, _V, _V, _V, _V, _I, _V]),
     "cfm_emb_grad_joint_rezero": (C.c_int, [C.POINTER(EmbGroup), _I, _I, _V, _V]),
     "cfm_enable_peer_access": (C.c_int, [_I]),
     "cfm_ipc_export": (C.c_int, [_V, C.c_char_p, C.POINTER(i64)]),

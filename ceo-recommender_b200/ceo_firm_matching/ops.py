@@ -232,6 +232,9 @@ class TowersFunction(torch.autograd.Function):
                 calls.append(_TowerCall(h, x_num, x_cat, B))
             arr = (N.Tower * n)(*[c.struct for c in calls])
             rng_dev = _graph_rng_counter if training else None
+            joint = _joint_for(calls) if (training and any(ctx.needs_input_grad)) else None
+            if joint is not None and all(c.h.row_source is None for c in calls):
+                joint.presort([c.x_cat for c in calls if c.h.n_tables], B)
             N.check(N.lib().cfm_towers_fwd(arr, n, B, 1 if training else 0, seed, offset, N.ptr(rng_dev),
                                            N.ptr(_state(dev).err_flag), N.stream_ptr()))
         ctx.calls, ctx.arr, ctx.training, ctx.seed, ctx.offset = calls, arr, training, seed, offset
@@ -413,6 +416,8 @@ class JointTableGrads:
         self.total_tables = sum(h.n_tables for h in self.handles)
         self.scratches = {}
         self.prev = None                          # (scratch, B) of the last reduce, until re-zeroed
+        self.presorted = None                     # (index tensor addresses, B) whose sorted keys are in the scratch
+        self._side: Optional[torch.cuda.Stream] = None
         for h in self.handles:
             h.table_grads.joint = self
 
@@ -432,16 +437,49 @@ class JointTableGrads:
                 arr[g].table_rows[i] = e.num_embeddings
         return arr
 
+    def _scratch(self, B: int, dev: torch.device) -> "_SortScratch":
+        if B not in self.scratches:
+            self.scratches[B] = _SortScratch(B * self.total_tables, self.total_tables, B, dev)
+        return self.scratches[B]
+
+    def _call(self, inputs, B: int, phase: int, sc: "_SortScratch") -> None:
+        N.check(N.lib().cfm_emb_grad_joint_reduce(self._groups(inputs), len(self.handles), B, phase, N.ptr(sc.keys_tmp),
+                                                  N.ptr(sc.vals_tmp), N.ptr(sc.keys_sorted), N.ptr(sc.vals_sorted),
+                                                  N.ptr(sc.tmp), sc.tmp_bytes, N.stream_ptr()))
+
+    def presort(self, x_cats: Sequence[torch.Tensor], B: int) -> None:
+        """Key build + radix sort of this step's (table, index) pairs on a side stream, started by the forward: the
+        sort needs the indices only, so it runs beside the towers instead of after the backward (under graph capture
+        the fork and the join become graph edges).  Skipped while the rows of an earlier backward still await their
+        re-zeroing: that needs the previous sorted keys."""
+        if self.prev is not None:
+            return
+        dev = x_cats[0].device
+        sc = self._scratch(B, dev)
+        main = torch.cuda.current_stream(dev)
+        if self._side is None or self._side.device != dev:
+            self._side = torch.cuda.Stream(dev)
+        side = self._side
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            self._call([(x, None) for x in x_cats], B, 1, sc)
+        for x in x_cats:
+            x.record_stream(side)
+        self.presorted = (tuple(x.data_ptr() for x in x_cats), B)
+
     def reduce(self, inputs, B: int) -> None:
         if self.prev is not None:
             raise RuntimeError("persistent table grads: backward ran twice without zero_grad_fast() in between")
         dev = inputs[0][1].device
-        if B not in self.scratches:
-            self.scratches[B] = _SortScratch(B * self.total_tables, self.total_tables, B, dev)
-        sc = self.scratches[B]
-        N.check(N.lib().cfm_emb_grad_joint_reduce(self._groups(inputs), len(self.handles), B, N.ptr(sc.keys_tmp),
-                                                  N.ptr(sc.vals_tmp), N.ptr(sc.keys_sorted), N.ptr(sc.vals_sorted),
-                                                  N.ptr(sc.tmp), sc.tmp_bytes, N.stream_ptr()))
+        sc = self._scratch(B, dev)
+        if self.presorted == (tuple(x.data_ptr() for x, _ in inputs), B):
+            torch.cuda.current_stream(dev).wait_stream(self._side)
+            self._call(inputs, B, 2, sc)
+        else:
+            if self._side is not None:               # a sort for other inputs may still be running on the scratch
+                torch.cuda.current_stream(dev).wait_stream(self._side)
+            self._call(inputs, B, 0, sc)
+        self.presorted = None
         self.prev = (sc, B)
 
     def rezero(self) -> None:

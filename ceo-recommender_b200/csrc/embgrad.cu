@@ -587,7 +587,7 @@ __global__ void emb_rezero_range(const unsigned long long* __restrict__ keys, lo
 }
 
 // validates the groups; fills per-group table pointers, the joint key plan and the key widths
-static int joint_plan(const cfm_emb_group_t* groups, int64_t n_groups, bool need_inputs, JointKeys& jk,
+static int joint_plan(const cfm_emb_group_t* groups, int64_t n_groups, bool need_x, bool need_dx, JointKeys& jk,
                       TablePtrs (&tps)[CFM_MAX_GROUPS], int* idx_bits, int* key_bits, long long* total_tables) {
     CFM_REQUIRE(groups && n_groups >= 1 && n_groups <= CFM_MAX_GROUPS, CFM_ERR_INVALID, "n_groups outside [1,%d]",
                 CFM_MAX_GROUPS);
@@ -599,7 +599,7 @@ static int joint_plan(const cfm_emb_group_t* groups, int64_t n_groups, bool need
         const cfm_emb_group_t& G = groups[g];
         CFM_REQUIRE(G.n_tables >= 1 && G.emb_dim >= 1 && tt + G.n_tables <= CFM_MAX_TABLES, CFM_ERR_INVALID,
                     "group %d: bad table count / more than %d tables in total", g, CFM_MAX_TABLES);
-        CFM_REQUIRE(!need_inputs || (G.x_cat && G.dx_emb), CFM_ERR_INVALID, "group %d: null input", g);
+        CFM_REQUIRE((!need_x || G.x_cat) && (!need_dx || G.dx_emb), CFM_ERR_INVALID, "group %d: null input", g);
         jk.x_cat[g] = (const long long*)G.x_cat; jk.n_tab[g] = (int)G.n_tables; jk.t0[g] = (int)tt;
         for (int i = 0; i < CFM_MAX_TABLES; ++i) {
             tps[g].p[i] = i < G.n_tables ? G.grad_tables[i] : nullptr;
@@ -621,27 +621,31 @@ static int joint_plan(const cfm_emb_group_t* groups, int64_t n_groups, bool need
 
 }  // namespace cfm
 
-extern "C" int cfm_emb_grad_joint_reduce(const cfm_emb_group_t* groups, int64_t n_groups, int64_t B, int64_t* keys_tmp,
-                                         int32_t* vals_tmp, int64_t* keys_sorted, int32_t* vals_sorted, void* sort_tmp,
-                                         int64_t sort_tmp_bytes, void* stream_) {
+extern "C" int cfm_emb_grad_joint_reduce(const cfm_emb_group_t* groups, int64_t n_groups, int64_t B, int64_t phase,
+                                         int64_t* keys_tmp, int32_t* vals_tmp, int64_t* keys_sorted, int32_t* vals_sorted,
+                                         void* sort_tmp, int64_t sort_tmp_bytes, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     CFM_REQUIRE(keys_tmp && vals_tmp && keys_sorted && vals_sorted && sort_tmp, CFM_ERR_INVALID, "null pointer");
     JointKeys jk;
     TablePtrs tps[CFM_MAX_GROUPS];
     int idx_bits, key_bits;
     long long tt;
-    int rc = joint_plan(groups, n_groups, true, jk, tps, &idx_bits, &key_bits, &tt);
+    CFM_REQUIRE(phase >= 0 && phase <= 2, CFM_ERR_INVALID, "phase must be 0, 1 or 2");
+    int rc = joint_plan(groups, n_groups, phase != 2, phase != 1, jk, tps, &idx_bits, &key_bits, &tt);
     if (rc) return rc;
     CFM_REQUIRE(B >= 1 && tt * B < (1ll << 31), CFM_ERR_INVALID, "bad sizes");
     const long long n = tt * B;
     ProfScope prof(PROF_EMB, stream);
-    emb_make_keys_joint<<<(int)std::min<long long>((n + 255) / 256, 148 * 8), 256, 0, stream>>>(
-        jk, B, idx_bits, (unsigned long long*)keys_tmp, vals_tmp);
-    CFM_LAUNCH_CHECK();
-    size_t bytes = (size_t)sort_tmp_bytes;
-    CFM_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(sort_tmp, bytes, (const unsigned long long*)keys_tmp,
-                                                   (unsigned long long*)keys_sorted, (const int*)vals_tmp,
-                                                   vals_sorted, (int)n, 0, key_bits, stream));
+    if (phase != 2) {
+        emb_make_keys_joint<<<(int)std::min<long long>((n + 255) / 256, 148 * 8), 256, 0, stream>>>(
+            jk, B, idx_bits, (unsigned long long*)keys_tmp, vals_tmp);
+        CFM_LAUNCH_CHECK();
+        size_t bytes = (size_t)sort_tmp_bytes;
+        CFM_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(sort_tmp, bytes, (const unsigned long long*)keys_tmp,
+                                                       (unsigned long long*)keys_sorted, (const int*)vals_tmp,
+                                                       vals_sorted, (int)n, 0, key_bits, stream));
+    }
+    if (phase == 1) return CFM_OK;
     for (int g = 0; g < n_groups; ++g) {
         const cfm_emb_group_t& G = groups[g];
         const long long off = (long long)jk.t0[g] * B, ng = G.n_tables * B;
@@ -668,7 +672,7 @@ extern "C" int cfm_emb_grad_joint_rezero(const cfm_emb_group_t* groups, int64_t 
     TablePtrs tps[CFM_MAX_GROUPS];
     int idx_bits, key_bits;
     long long tt;
-    int rc = joint_plan(groups, n_groups, false, jk, tps, &idx_bits, &key_bits, &tt);
+    int rc = joint_plan(groups, n_groups, false, false, jk, tps, &idx_bits, &key_bits, &tt);
     if (rc) return rc;
     CFM_REQUIRE(B >= 1, CFM_ERR_INVALID, "bad sizes");
     ProfScope prof(PROF_EMB, stream);

@@ -989,15 +989,48 @@ static size_t bwd_smem_bytes(const cfm_tower_t& t, int s, int a_bn, int need_dx,
 
 using namespace cfm;
 
+// Per-CTA floats of a tower's scratch: one weight-gradient partial region per layer (so that the reduction of layer s
+// can run beside the backward of layer s - 1) followed by the small BatchNorm partials (forward statistics, backward
+// sums).  Regions are laid out for the maximum CTA count cfm_device_info reports.
+static int64_t dw_region_floats(const cfm_tower_t& t, int s) { return (int64_t)stage_N(t, s) * (stage_K(t, s) + 1); }
+static int64_t max_ctas() { return 2 * (int64_t)sm_count(); }
+static float* dw_region(const cfm_tower_t& t, int s) {
+    int64_t off = 0;
+    for (int q = 3; q > s; --q) off += dw_region_floats(t, q);
+    return t.scratch + max_ctas() * off;
+}
+static float* misc_region(const cfm_tower_t& t) {
+    return t.scratch + max_ctas() * (dw_region_floats(t, 1) + dw_region_floats(t, 2) + dw_region_floats(t, 3));
+}
 extern "C" int64_t cfm_tower_scratch_floats(const cfm_tower_t* t) {
     int64_t m = 0, d = 0;
     for (int s = 1; s <= 3; ++s) {
         int64_t n = stage_N(*t, s), k = stage_K(*t, s);
-        m = n * (k + 1) > m ? n * (k + 1) : m;
+        m += n * (k + 1);
         d = n > d ? n : d;
         d = k > d ? k : d;
     }
     return m + 4 * d + 16;
+}
+
+// Side stream of the library (one per device): work that is off the critical path of a step (the fixed-order
+// reduction of the per-CTA weight-gradient partials) is forked onto it and joined at the end of the call; under
+// stream capture the fork / join events become graph edges.
+struct SideStream {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork[4] = {nullptr, nullptr, nullptr, nullptr}, join = nullptr;
+};
+static SideStream* side_stream() {
+    static SideStream side[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    SideStream& S = side[dev];
+    if (!S.stream) {
+        if (cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        for (int i = 0; i < 4; ++i) cudaEventCreateWithFlags(&S.fork[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&S.join, cudaEventDisableTiming);
+    }
+    return &S;
 }
 
 extern "C" int cfm_towers_fwd(const cfm_tower_t* towers, int64_t n_towers, int64_t B, int64_t training,
@@ -1050,7 +1083,7 @@ extern "C" int cfm_towers_fwd(const cfm_tower_t* towers, int64_t n_towers, int64
             S.bias = s == 1 ? t.b1 : s == 2 ? t.b2 : t.b3;
             S.hout = s == 1 ? t.h1_raw : s == 2 ? t.h2_raw : t.out;
             bool bn_after = s == 1 || (s == 2 && t.bn2);
-            S.stat_part = (training && bn_after) ? t.scratch : nullptr;
+            S.stat_part = (training && bn_after) ? misc_region(t) : nullptr;
             any_stats |= S.stat_part != nullptr;
             size_t need = fwd_smem_bytes(t, s, a.tm);
             CFM_REQUIRE(use_tc[s] || need <= (size_t)MAX_SMEM, CFM_ERR_UNSUPPORTED,
@@ -1073,7 +1106,7 @@ extern "C" int cfm_towers_fwd(const cfm_tower_t* towers, int64_t n_towers, int64
                 const cfm_tower_t& t = towers[i];
                 bool bn_after = s == 1 || (s == 2 && t.bn2);
                 BnFwdFin& F = f.t[i];
-                F.part = t.scratch; F.nparts = ctas; F.N = bn_after ? stage_N(t, s) : 0;
+                F.part = misc_region(t); F.nparts = ctas; F.N = bn_after ? stage_N(t, s) : 0;
                 F.stat = s == 1 ? t.bn1_stat : t.bn2_stat;
                 F.rm = s == 1 ? t.bn1_rm : t.bn2_rm;
                 F.rv = s == 1 ? t.bn1_rv : t.bn2_rv;
@@ -1126,6 +1159,7 @@ extern "C" int cfm_towers_bwd(const cfm_tower_t* towers, const cfm_tower_grads_t
                         g.dy2, CFM_ERR_INVALID, "null gradient buffer");
         CFM_REQUIRE(!towers[i].bn2 || (g.dbn2_w && g.dbn2_b), CFM_ERR_INVALID, "null bn2 gradient buffer");
     }
+    SideStream* side = side_stream();
     for (int s = 3; s >= 1; --s) {
         BwdArgs a{};
         a.B = B;
@@ -1172,9 +1206,9 @@ extern "C" int cfm_towers_bwd(const cfm_tower_t* towers, const cfm_tower_grads_t
                 S.g_gamma = s == 1 ? t.bn1_w : t.bn2_w;
                 S.g_c1 = stat + 2 * h; S.g_c2 = stat + 3 * h;
             }
-            S.dW_part = t.scratch;
+            S.dW_part = dw_region(t, s);
             S.dy_out = s == 3 ? g.dy2 : s == 2 ? g.dy1 : nullptr;
-            S.sum_part = t.scratch + (size_t)ctas * S.N * (S.in.K + 1);
+            S.sum_part = misc_region(t);
             S.dx_emb = s == 1 ? g.dx_emb : nullptr;
             S.dx_num = s == 1 ? g.dx_num : nullptr;
             S.need_dx = s > 1 || g.dx_emb || g.dx_num;
@@ -1199,21 +1233,31 @@ extern "C" int cfm_towers_bwd(const cfm_tower_t* towers, const cfm_tower_grads_t
             else rc = launch_bwd(a, ctas, (int)n_towers, smem, towers[0].precision == 0, stream);
         }
         if (rc) return rc;
-        ProfScope prof_red(PROF_REDUCE, stream);
         (void)max_groups;
-        // fixed-order reductions of the per-CTA partials
-        ReduceWArgs r{};
-        for (int i = 0; i < n_towers; ++i) {
-            const cfm_tower_t& t = towers[i];
-            const cfm_tower_grads_t& g = grads[i];
-            ReduceW& R = r.t[i];
-            R.part = t.scratch; R.nparts = ctas; R.N = a.st[i].N; R.K = a.st[i].in.K;
-            R.dW = s == 1 ? g.dw1 : s == 2 ? g.dw2 : g.dw3;
-            R.db = s == 1 ? g.db1 : s == 2 ? g.db2 : g.db3;
+        // fixed-order reduction of the per-CTA weight-gradient partials: nothing downstream in this call needs it,
+        // so it runs on the side stream while the next layer's backward proceeds
+        {
+            ReduceWArgs r{};
+            for (int i = 0; i < n_towers; ++i) {
+                const cfm_tower_t& t = towers[i];
+                const cfm_tower_grads_t& g = grads[i];
+                ReduceW& R = r.t[i];
+                R.part = dw_region(t, s); R.nparts = ctas; R.N = a.st[i].N; R.K = a.st[i].in.K;
+                R.dW = s == 1 ? g.dw1 : s == 2 ? g.dw2 : g.dw3;
+                R.db = s == 1 ? g.db1 : s == 2 ? g.db2 : g.db3;
+            }
+            int maxS = 1; for (int i = 0; i < n_towers; ++i) maxS = std::max(maxS, r.t[i].N * (r.t[i].K + 1));
+            cudaStream_t rs = stream;
+            if (side) {
+                CFM_CHECK_CUDA(cudaEventRecord(side->fork[s], stream));
+                CFM_CHECK_CUDA(cudaStreamWaitEvent(side->stream, side->fork[s], 0));
+                rs = side->stream;
+            }
+            ProfScope prof_red(PROF_REDUCE, rs);
+            reduce_dw<<<dim3(std::min(ceil_div(maxS, 32), 592), (unsigned)n_towers), 256, 0, rs>>>(r);
+            CFM_LAUNCH_CHECK();
         }
-        int maxS = 1; for (int i = 0; i < n_towers; ++i) maxS = std::max(maxS, r.t[i].N * (r.t[i].K + 1));
-        reduce_dw<<<dim3(std::min(ceil_div(maxS, 32), 592), (unsigned)n_towers), 256, 0, stream>>>(r);
-        CFM_LAUNCH_CHECK();
+        ProfScope prof_red(PROF_REDUCE, stream);
         if (any_sums) {
             BnBwdFinArgs f{};
             for (int i = 0; i < n_towers; ++i) {
@@ -1230,6 +1274,10 @@ extern "C" int cfm_towers_bwd(const cfm_tower_t* towers, const cfm_tower_grads_t
             bn_bwd_finalize<<<dim3(ceil_div(maxK, 8), (unsigned)n_towers), 256, 0, stream>>>(f);
             CFM_LAUNCH_CHECK();
         }
+    }
+    if (side) {
+        CFM_CHECK_CUDA(cudaEventRecord(side->join, side->stream));
+        CFM_CHECK_CUDA(cudaStreamWaitEvent(stream, side->join, 0));
     }
     return CFM_OK;
 }

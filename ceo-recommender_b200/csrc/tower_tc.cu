@@ -871,7 +871,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tower_bwd_tc(const __grid_const
                     }
                 }
             }
+            if (gtid == 0 && it < 6) trace(80 + 4 * it, tcode);
             if (it > 0) mbar_wait(g_empty, (it - 1) & 1);      // the MMAs of the previous tile have read G / G^T
+            if (gtid == 0 && it < 6) trace(81 + 4 * it, tcode);
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int id = gtid + u * TC_GT;
@@ -900,6 +902,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tower_bwd_tc(const __grid_const
                 }
             }
             named_bar_sync(2, TC_GT);
+            if (gtid == 0 && it < 6) trace(82 + 4 * it, tcode);
             // transpose through shared memory: lane <-> batch row, so the scattered 4-byte stores of one instruction
             // fall into one 128-byte row of G^T (conflict-free)
             {
@@ -918,6 +921,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tower_bwd_tc(const __grid_const
             }
             fence_proxy_async();
             mbar_arrive(g_full);
+            if (gtid == 0 && it < 6) trace(83 + 4 * it, tcode);
         };
 
         auto issue_idx = [&](const ChunkPos& p, long long (&ix)[NXR]) {

@@ -156,9 +156,11 @@ typedef struct cfm_emb_group {
     float* grad_tables[CFM_MAX_TABLES];      /* [rows_i, emb_dim] dense gradients */
     int64_t table_rows[CFM_MAX_TABLES];
 } cfm_emb_group_t;
-int cfm_emb_grad_joint_reduce(const cfm_emb_group_t* groups /* host */, int64_t n_groups, int64_t B, int64_t* keys_tmp,
-                              int32_t* vals_tmp, int64_t* keys_sorted, int32_t* vals_sorted, void* sort_tmp,
-                              int64_t sort_tmp_bytes, void* stream);
+/* phase 0: everything; 1: key build + sort only (needs x_cat only: can run on a side stream beside the forward);
+ * 2: segment reduce only (needs dx_emb; after phase 1 on the same scratch). */
+int cfm_emb_grad_joint_reduce(const cfm_emb_group_t* groups /* host */, int64_t n_groups, int64_t B, int64_t phase,
+                              int64_t* keys_tmp, int32_t* vals_tmp, int64_t* keys_sorted, int32_t* vals_sorted,
+                              void* sort_tmp, int64_t sort_tmp_bytes, void* stream);
 int cfm_emb_grad_joint_rezero(const cfm_emb_group_t* groups /* host */, int64_t n_groups, int64_t B,
                               const int64_t* keys_sorted, void* stream);
 
