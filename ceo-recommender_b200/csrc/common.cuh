@@ -118,10 +118,12 @@ __device__ __forceinline__ DropCtx resolve_drop(DropCtx d) {
     }
     return d;
 }
-// words for columns [4*c4, 4*c4+3] of `row`
+// words for columns [4*c4, 4*c4+3] of `row`.  Counter = (row, dropout site, column group, step offset), each in
+// its own word: masks of different steps are independent draws (no word is shared between the column group and the
+// step offset, so one step's mask is never a column permutation of another's); the offset's high half goes to the key.
 __host__ __device__ __forceinline__ Philox4 drop_words(const DropCtx& d, long long row, int c4) {
     return philox4x32_10((uint32_t)row, (uint32_t)((unsigned long long)row >> 32) ^ (d.stream_id << 24),
-                         (uint32_t)c4 ^ d.o0, d.o1, d.k0, d.k1);
+                         (uint32_t)c4, d.o0, d.k0, d.k1 ^ d.o1);
 }
 __host__ __device__ __forceinline__ bool drop_keep(const DropCtx& d, const Philox4& w, int lane4) {
     uint32_t v = lane4 == 0 ? w.x : lane4 == 1 ? w.y : lane4 == 2 ? w.z : w.w;

@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(256) tc_prep_weights(const __grid_constant__ P
     const WImgLayout L = wimg_layout(T.K, T.N);
     for (int s = 0; s < 3; ++s) {
         const int K = T.K[s], N = T.N[s], npad = tc_npad(N), nch = tc_nch(K), ncolp = tc_nblk(N) * 32;
-        const int kcols = nch * 32;
+        const int kcols = max(nch * 32, tcb_nch(K) * tcb_cw(K));
         float* wimg = T.img + L.w[s];
         float* wtimg = T.img + L.wt[s];
         const int total = ncolp * kcols;
@@ -108,16 +108,17 @@ __global__ void __launch_bounds__(256) tc_prep_weights(const __grid_constant__ P
             float hi, lo;
             split_tf32(v, hi, lo);
             const int j = kc >> 5, c = kc & 31;
-            if (n < npad) {
+            if (n < npad && kc < nch * 32) {
                 float* ch = wimg + (size_t)j * tc_w_chunk_floats(N);
                 const uint32_t off = sw128_off(n, c, npad) >> 2;
                 ch[off] = hi;
                 ch[npad * 32 + off] = lo;
             }
-            float* tch = wtimg + (size_t)j * tc_wt_chunk_floats(N);
-            const uint32_t offt = sw128_off(c, n, 32) >> 2;
+            const int cw = tcb_cw(K);
+            float* tch = wtimg + (size_t)(kc / cw) * tc_wt_chunk_floats(K, N);
+            const uint32_t offt = sw128_off(kc % cw, n, cw) >> 2;
             tch[offt] = hi;
-            tch[32 * ncolp + offt] = lo;
+            tch[cw * ncolp + offt] = lo;
         }
     }
 }
@@ -160,43 +161,45 @@ __device__ __forceinline__ void stage_bn_params_tc(const ActSrc& a, int K, float
     }
 }
 
-// Position of a chunk in a producer group's stream: tiles in CTA order, inside a tile the column chunks j == group
-// (mod TC_GROUPS).  Group 0 therefore owns chunk 0 of every tile.  (One chunk per tile: everything goes to group 0.)
+// Position of a chunk in a producer group's stream.  The CTA's chunks, numbered tile-major (c = it * nch + j), go to
+// the groups in turn: group g takes c = g, g + TC_GROUPS, ...
 struct ChunkPos {
     int it, j;
-    __device__ __forceinline__ void next(int nch, int grp) {
-        j += TC_GROUPS;
-        if (j >= nch) { j = grp; ++it; }
+    __device__ __forceinline__ void start(int grp, int nch) { it = grp / nch; j = grp - it * nch; }
+    template <int GROUPS>
+    __device__ __forceinline__ void next(int nch) {
+        j += GROUPS;
+        while (j >= nch) { j -= nch; ++it; }
     }
 };
 
 // Software pipeline of a producer thread over its group's chunks: the data loads of the next PD chunks are in flight
 // in registers (NX 16-byte quads per chunk), the index loads they depend on two chunks further ahead.  The functors
 // must treat positions past the end (it >= number of tiles) as no-ops that still define their outputs.
-template <int PD, int NX, int NI, class IssueIdx, class IssueData, class Consume>
+template <int GROUPS, int PD, int NX, int NI, class IssueIdx, class IssueData, class Consume>
 __device__ __forceinline__ void chunk_pipeline(int n_tiles, int nch, int grp, IssueIdx issue_idx, IssueData issue_data,
                                                Consume consume) {
     static_assert(PD % 2 == 0, "the two index sets alternate with the unrolled slot");
-    if (grp >= nch) return;
-    ChunkPos pc{0, grp}, pd{0, grp}, pi{0, grp};
+    ChunkPos pc, pd, pi;
+    pc.start(grp, nch); pd = pc; pi = pc;
     float4 buf[PD][NX];
     long long ix[2][NI];
     {
         long long ixp[PD][NI];
 #pragma unroll
-        for (int u = 0; u < PD; ++u) { issue_idx(pi, ixp[u]); pi.next(nch, grp); }
+        for (int u = 0; u < PD; ++u) { issue_idx(pi, ixp[u]); pi.template next<GROUPS>(nch); }
 #pragma unroll
-        for (int u = 0; u < PD; ++u) { issue_data(pd, ixp[u], buf[u]); pd.next(nch, grp); }
+        for (int u = 0; u < PD; ++u) { issue_data(pd, ixp[u], buf[u]); pd.template next<GROUPS>(nch); }
     }
-    issue_idx(pi, ix[0]); pi.next(nch, grp);
-    issue_idx(pi, ix[1]); pi.next(nch, grp);
+    issue_idx(pi, ix[0]); pi.template next<GROUPS>(nch);
+    issue_idx(pi, ix[1]); pi.template next<GROUPS>(nch);
     while (pc.it < n_tiles) {
 #pragma unroll
         for (int u = 0; u < PD; ++u) {
             if (pc.it < n_tiles) {
-                consume(pc, buf[u]); pc.next(nch, grp);
-                issue_data(pd, ix[u & 1], buf[u]); pd.next(nch, grp);
-                issue_idx(pi, ix[u & 1]); pi.next(nch, grp);
+                consume(pc, buf[u]); pc.template next<GROUPS>(nch);
+                issue_data(pd, ix[u & 1], buf[u]); pd.template next<GROUPS>(nch);
+                issue_idx(pi, ix[u & 1]); pi.template next<GROUPS>(nch);
             }
         }
     }
@@ -534,7 +537,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tower_fwd_tc(const __grid_const
             mbar_arrive(full + s);
             if (gtid == 0 && cnt < 40) trace(2 + cnt, tcode);
         };
-        chunk_pipeline<2, NX, NX>(my_tiles, nch, grp, issue_idx, issue_data, consume);
+        chunk_pipeline<TC_GROUPS, 2, NX, NX>(my_tiles, nch, grp, issue_idx, issue_data, consume);
     }
     tc_fence_before();
     __syncthreads();
@@ -543,25 +546,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tower_fwd_tc(const __grid_const
 }
 
 // ------------------------------------------------------------------------------------------
-// backward stage: per 64-row tile  dX = G . W  (chunk by chunk of 32 input columns, M = 64 accumulators double
-// buffered in TMEM) and  dW += G^T . [A | 1]  (accumulated in TMEM over ALL tiles of the CTA, written once)
+// backward stage: per 64-row tile  dX = G . W  (chunk by chunk of CW = 64 input columns; M = 64 accumulators double
+// buffered in TMEM) and  dW += G^T . [A | 1]  (accumulated in TMEM over ALL tiles of the CTA, written once).
+// Every tcgen05.mma costs about 60 cycles to issue whatever its shape, so the chunks are as wide as shared memory
+// allows, and the bias gradient rides in the last chunk's product as a ninth row group (a constant row of ones).
+// Producer threads own one batch row each (lane <-> row), so the transposed images G^T and A^T are written straight
+// from registers, one 128-byte row per store instruction.
 // ------------------------------------------------------------------------------------------
 struct TcBwdSmem {
-    int g, gt, ones, ring, at, wt, msk, xh, stage, bna, bng, red, bars, tmem, total, nst;
+    int g, gt, ring, at, wt, msk, xh, stage, bna, bng, red, bars, tmem, total, nst, at_img;
 };
 __host__ __device__ inline TcBwdSmem tcb_smem(int K, int N, bool stage1, bool a_bn) {
     TcBwdSmem s;
-    const int nbn = tc_nblk(N), Kp = (K + 3) & ~3, Np = (N + 3) & ~3;
+    const int nbn = tc_nblk(N), Kp = (K + 3) & ~3, Np = (N + 3) & ~3, cw = tcb_cw(K);
     int o = 0;
     s.g = o; o += 2 * TCB_M * 128 * nbn;              // G   [64 rows][N]      hi, lo
     s.gt = o; o += 2 * 64 * 128 * 2;                  // G^T [64 n][64 rows]   hi, lo
-    s.ones = o; o += 8 * 128 * 2;                     // [8][64 rows], row 0 = 1 (bias gradient)
     s.ring = o;
     int st = 0;
-    s.at = st; st += 2 * 32 * 128 * 2;                // A^T chunk [32 k][64 rows] hi, lo
-    s.wt = st; st += 2 * 32 * 128 * nbn;              // W^T chunk [32 k][N]       hi, lo
-    s.msk = st; st += stage1 ? 0 : TCB_M * 128;       // activation-derivative tile [64 rows][32 k]
-    s.xh = st; st += a_bn ? TCB_M * 128 : 0;          // x-hat tile                 [64 rows][32 k]
+    s.at_img = (cw + 8) * 128 * 2;                    // A^T chunk [cw k + 8][64 rows]: row cw = ones (bias gradient)
+    s.at = st; st += 2 * s.at_img;
+    s.wt = st; st += 2 * cw * 128 * nbn;              // W^T chunk [cw k][N]       hi, lo
+    s.msk = st; st += stage1 ? 0 : TCB_M * cw * 4;    // activation-derivative tile [64 rows][cw k]
+    s.xh = st; st += a_bn ? TCB_M * cw * 4 : 0;       // x-hat tile                 [64 rows][cw k]
     s.stage = st;
     int f = 0;
     const int bna = f; f += 4 * Kp * 4;
@@ -579,26 +586,26 @@ __host__ __device__ inline TcBwdSmem tcb_smem(int K, int N, bool stage1, bool a_
     return s;
 }
 __host__ __device__ inline uint32_t tcb_tmem_cols(int K) {
-    const uint32_t need = tc_nch(K) * 32 + 8 + 64;
+    const uint32_t need = tcb_nch(K) * tcb_cw(K) + 8 + 2 * tcb_cw(K);
     uint32_t c = 32;
     while (c < need) c <<= 1;
     return c;
 }
 
-template <bool STAGE1>
+template <bool STAGE1, int CW>
 __global__ void __launch_bounds__(TC_THREADS, 1) tower_bwd_tc(const __grid_constant__ BwdArgs args) {
     const BwdStage& S = args.st[blockIdx.y];
     extern __shared__ uint8_t smem_raw[];
     uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const int K = S.in.K, N = S.N, npad = tc_npad(N), nbn = tc_nblk(N), nch = tc_nch(K);
+    const int K = S.in.K, N = S.N, npad = tc_npad(N), nbn = tc_nblk(N), nch = tcb_nch(K);
     const int Kp = (K + 3) & ~3, Np = (N + 3) & ~3;
     const bool a_bn = S.a_bn != 0, need_dx = S.need_dx != 0;
     const TcBwdSmem L = tcb_smem(K, N, STAGE1, a_bn);
     const int nst = L.nst;
-    uint8_t *G = sm + L.g, *GT = sm + L.gt, *ONES = sm + L.ones, *ring = sm + L.ring;
+    uint8_t *G = sm + L.g, *GT = sm + L.gt, *ring = sm + L.ring;
     const int G_IMG = TCB_M * 128 * nbn;
-    constexpr int GT_IMG = 64 * 128 * 2, AT_IMG = 32 * 128 * 2;
-    const int WT_IMG = 32 * 128 * nbn;
+    constexpr int GT_IMG = 64 * 128 * 2, AT_IMG = (CW + 8) * 128 * 2, ATR = CW + 8;
+    const int WT_IMG = CW * 128 * nbn;
     float* sm_bna = reinterpret_cast<float*>(sm + L.bna);
     float* sm_bng = reinterpret_cast<float*>(sm + L.bng);
     float* sm_red = reinterpret_cast<float*>(sm + L.red);
@@ -614,19 +621,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tower_bwd_tc(const __grid_const
     const bool exact = args.exact != 0;
     const int tcode = 10 + S.in.stage;
     const uint32_t tmem_cols = tcb_tmem_cols(K);
-    const uint32_t col_db = nch * 32, col_dx = nch * 32 + 8;
+    const uint32_t col_db = nch * CW, col_dx = nch * CW + 8;
 
     if (tid == 0) {
         trace(0, tcode);
-        for (int s = 0; s < 4; ++s) { mbar_init(full + s, TC_GT + 1); mbar_init(empty + s, 1 + TC_EPI_WARPS); }
-        mbar_init(g_full, TC_GT); mbar_init(g_empty, 1);
+        for (int s = 0; s < 4; ++s) { mbar_init(full + s, TC_PT + 1); mbar_init(empty + s, 1 + TC_EPI_WARPS); }
+        mbar_init(g_full, TC_PT); mbar_init(g_empty, 1);
         for (int b = 0; b < 2; ++b) { mbar_init(dx_full + b, 1); mbar_init(dx_empty + b, TC_EPI_WARPS * 32); }
         mbar_init(dw_full, 1);
         fence_barrier_init();
     }
     if (warp == TC_MMA_WARP) tmem_alloc(tmem_slot, tmem_cols);
-    // G^T rows past N and the ones tile never change: written once
-    for (int i = tid; i < (2 * GT_IMG + 8 * 128 * 2) / 16; i += TC_THREADS) reinterpret_cast<uint4*>(GT)[i] = make_uint4(0, 0, 0, 0);
+    // written once: G^T rows past N (zero), and in every ring stage the eight extra A^T rows (ones, zeros)
+    for (int i = tid; i < 2 * GT_IMG / 16; i += TC_THREADS) reinterpret_cast<uint4*>(GT)[i] = make_uint4(0, 0, 0, 0);
+    for (int s = 0; s < nst; ++s) {
+        uint8_t* at = ring + s * L.stage + L.at;
+        for (int i = tid; i < 2 * 8 * 64; i += TC_THREADS) {
+            const int img = i >> 9, rr = (i >> 6) & 7, c = i & 63;
+            *reinterpret_cast<float*>(at + img * AT_IMG + sw128_off(CW + rr, c, ATR)) = (img == 0 && rr == 0) ? 1.f : 0.f;
+        }
+    }
     if (!STAGE1) stage_bn_params_tc(S.in.a, K, sm_bna, tid, TC_THREADS);
     if (S.g_mode) {
         for (int c = tid; c < Np; c += TC_THREADS) {
@@ -640,8 +654,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tower_bwd_tc(const __grid_const
             sm_bng[4 * Np + c] = (ok && S.g_mode == 1) ? S.g_c2[c] : 0.f;
         }
     }
-    __syncthreads();
-    for (int r = tid; r < 64; r += TC_THREADS) *reinterpret_cast<float*>(ONES + sw128_off(0, r, 8)) = 1.f;
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -652,8 +664,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tower_bwd_tc(const __grid_const
     if (warp == TC_MMA_WARP) {
         // ===================== MMA issuer (whole warp in the loops, one elected lane issues) =====================
         if (my_tiles > 0) {
-            const uint32_t idesc32 = make_idesc_tf32(64, 32, false, false), idesc8 = make_idesc_tf32(64, 8, false, false);
-            const uint32_t g_s = smem_u32(G), gt_s = smem_u32(GT), ones_s = smem_u32(ONES), ring_s = smem_u32(ring);
+            const uint32_t idesc_x = make_idesc_tf32(64, CW, false, false), idesc_w = idesc_x, idesc_wb = make_idesc_tf32(64, CW + 8, false, false);
+            const uint32_t g_s = smem_u32(G), gt_s = smem_u32(GT), ring_s = smem_u32(ring);
             const int p0 = exact ? 0 : 2;
             const int kn = npad >> 3;                        // K steps of dX (over the layer's outputs)
             uint32_t cnt = 0;
@@ -672,29 +684,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tower_bwd_tc(const __grid_const
                     }
                     if (elect_one()) {
                         if (need_dx) {
-                            const uint32_t d = tmem_base + col_dx + 32 * b;
+                            const uint32_t d = tmem_base + col_dx + CW * b;
                             for (int p = p0; p < 3; ++p) {
                                 const uint32_t ai = g_s + (p == 0 ? G_IMG : 0), bi = st + L.wt + (p == 1 ? WT_IMG : 0);
                                 for (int ks = 0; ks < kn; ++ks)
-                                    umma_tf32(d, tile_desc_k(ai, TCB_M, ks), tile_desc_k(bi, 32, ks), idesc32, !(p == p0 && ks == 0));
+                                    umma_tf32(d, tile_desc_k(ai, TCB_M, ks), tile_desc_k(bi, CW, ks), idesc_x, !(p == p0 && ks == 0));
                             }
                             umma_commit(dx_full + b);
                         }
-                        const uint32_t d = tmem_base + 32 * j;
+                        const uint32_t d = tmem_base + CW * j;
+                        const uint32_t idw = j == nch - 1 ? idesc_wb : idesc_w;     // last chunk: + the row of ones
                         for (int p = p0; p < 3; ++p) {
                             const uint32_t ai = gt_s + (p == 0 ? GT_IMG : 0), bi = st + L.at + (p == 1 ? AT_IMG : 0);
                             for (int ks = 0; ks < 8; ++ks)
-                                umma_tf32(d, tile_desc_k(ai, 64, ks), tile_desc_k(bi, 32, ks), idesc32, !(it == 0 && p == p0 && ks == 0));
+                                umma_tf32(d, tile_desc_k(ai, 64, ks), tile_desc_k(bi, ATR, ks), idw, !(it == 0 && p == p0 && ks == 0));
                         }
                         umma_commit(empty + s);
                         if (j == nch - 1) {
-                            // bias gradient: column sums of G = G^T . 1
-                            for (int p = exact ? 0 : 1; p < 2; ++p) {
-                                const uint32_t ai = gt_s + (p == 0 ? GT_IMG : 0);
-                                for (int ks = 0; ks < 8; ++ks)
-                                    umma_tf32(tmem_base + col_db, tile_desc_k(ai, 64, ks), tile_desc_k(ones_s, 8, ks), idesc8,
-                                              !(it == 0 && p == (exact ? 0 : 1) && ks == 0));
-                            }
                             umma_commit(g_empty);
                             if (it == my_tiles - 1) umma_commit(dw_full);
                         }
@@ -710,73 +716,79 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tower_bwd_tc(const __grid_const
         const bool act = lane < 16;
         const uint32_t lane_addr = (uint32_t)(32 * q) << 16;
         const int KE = S.in.g.n_tab * S.in.g.E, n_num = S.in.g.n_num;
-        const float inv_keep = (!STAGE1 && S.in.a.drop.active) ? S.in.a.drop.inv_keep : 1.f;
-        float s1[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, s2[2][2] = {{0.f, 0.f}, {0.f, 0.f}};   // [chunk][owned column], stage > 1: K <= 64
+        float s1[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, s2[2][2] = {{0.f, 0.f}, {0.f, 0.f}};   // [32-column half][owned column] (stage > 1: K <= 64)
         uint32_t cnt = 0;
         for (int it = 0; it < my_tiles; ++it) {
             const long long row0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * TCB_M;
             const long long row = row0 + 16 * q + lane;
             const bool valid = act && row < B;
+            const int rl = 16 * q + (lane & 15);
             for (int j = 0; j < nch; ++j, ++cnt) {
                 const int s = cnt % nst;
                 const uint8_t* st = ring + s * L.stage;
-                float v[32];
                 if (need_dx) {
                     const int b = cnt & 1;
                     mbar_wait(dx_full + b, (cnt >> 1) & 1);
                     tc_fence_after();
-                    tmem_ld32(tmem_base + col_dx + 32 * b + lane_addr, v);
-                    tc_fence_before();
-                    mbar_arrive(dx_empty + b);
-                    if (STAGE1) {
-                        if (valid) {
 #pragma unroll
-                            for (int i = 0; i < 32; i += 4) {
-                                const int c = 32 * j + i;
-                                if (c + 3 < KE) {
-                                    if (S.dx_emb) *reinterpret_cast<float4*>(S.dx_emb + (size_t)row * KE + c) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                                } else {
+                    for (int hf = 0; hf < CW / 32; ++hf) {
+                        float v[32];
+                        tmem_ld32(tmem_base + col_dx + CW * b + 32 * hf + lane_addr, v);
+                        if (hf == CW / 32 - 1) {
+                            tc_fence_before();
+                            mbar_arrive(dx_empty + b);
+                        }
+                        const int cb = CW * j + 32 * hf;          // first input column of this half
+                        if (STAGE1) {
+                            if (valid) {
 #pragma unroll
-                                    for (int e = 0; e < 4; ++e) {
-                                        const int ce = c + e;
-                                        if (ce < KE) { if (S.dx_emb) S.dx_emb[(size_t)row * KE + ce] = v[i + e]; }
-                                        else if (ce < K && S.dx_num) S.dx_num[(size_t)row * n_num + (ce - KE)] = v[i + e];
+                                for (int i = 0; i < 32; i += 4) {
+                                    const int c = cb + i;
+                                    if (c + 3 < KE) {
+                                        if (S.dx_emb) *reinterpret_cast<float4*>(S.dx_emb + (size_t)row * KE + c) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                                    } else if (c < K) {
+#pragma unroll
+                                        for (int e = 0; e < 4; ++e) {
+                                            const int ce = c + e;
+                                            if (ce < KE) { if (S.dx_emb) S.dx_emb[(size_t)row * KE + ce] = v[i + e]; }
+                                            else if (ce < K && S.dx_num) S.dx_num[(size_t)row * n_num + (ce - KE)] = v[i + e];
+                                        }
                                     }
                                 }
                             }
-                        }
-                    } else {
-                        // dy = dX * d(act)/d(pre-activation); the producers left that factor (and x-hat) in the ring stage
-                        const int rl = 16 * q + (lane & 15);
-                        float xs[32];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const float4 m4 = *reinterpret_cast<const float4*>(st + L.msk + sw128_chunk(rl, 0, i, TCB_M));
-                            v[4 * i] *= m4.x; v[4 * i + 1] *= m4.y; v[4 * i + 2] *= m4.z; v[4 * i + 3] *= m4.w;
-                        }
-                        if (a_bn) {
+                        } else {
+                            // dy = dX * d(act)/d(pre-activation); the producers left that factor (and x-hat) in the ring stage
+                            float xs[32];
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
-                                const float4 x4 = *reinterpret_cast<const float4*>(st + L.xh + sw128_chunk(rl, 0, i, TCB_M));
-                                xs[4 * i] = x4.x; xs[4 * i + 1] = x4.y; xs[4 * i + 2] = x4.z; xs[4 * i + 3] = x4.w;
+                                const float4 m4 = *reinterpret_cast<const float4*>(st + L.msk + sw128_chunk(rl, hf, i, TCB_M));
+                                v[4 * i] *= m4.x; v[4 * i + 1] *= m4.y; v[4 * i + 2] *= m4.z; v[4 * i + 3] *= m4.w;
                             }
-                        }
-                        if (valid) {
-                            float* dst = S.dy_out + (size_t)row * K + 32 * j;
+                            if (a_bn) {
 #pragma unroll
-                            for (int i = 0; i < 32; i += 4)
-                                if (32 * j + i < K) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                        }
-                        if (a_bn) {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) {
-                                v[i] = valid ? v[i] : 0.f;
-                                xs[i] = v[i] * xs[i];
+                                for (int i = 0; i < 8; ++i) {
+                                    const float4 x4 = *reinterpret_cast<const float4*>(st + L.xh + sw128_chunk(rl, hf, i, TCB_M));
+                                    xs[4 * i] = x4.x; xs[4 * i + 1] = x4.y; xs[4 * i + 2] = x4.z; xs[4 * i + 3] = x4.w;
+                                }
                             }
-                            Halve<32, 8>::run(v, lane);
-                            Halve<32, 8>::run(xs, lane);
-                            if (j == 0) { s1[0][0] += v[0]; s1[0][1] += v[1]; s2[0][0] += xs[0]; s2[0][1] += xs[1]; }
-                            else { s1[1][0] += v[0]; s1[1][1] += v[1]; s2[1][0] += xs[0]; s2[1][1] += xs[1]; }
+                            if (valid) {
+                                float* dst = S.dy_out + (size_t)row * K + cb;
+#pragma unroll
+                                for (int i = 0; i < 32; i += 4)
+                                    if (cb + i < K) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                            }
+                            if (a_bn) {
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) {
+                                    v[i] = valid ? v[i] : 0.f;
+                                    xs[i] = v[i] * xs[i];
+                                }
+                                Halve<32, 8>::run(v, lane);
+                                Halve<32, 8>::run(xs, lane);
+                                const int hh = (cb >> 5) & 1;       // K <= 64: at most two halves in all
+                                if (hh == 0) { s1[0][0] += v[0]; s1[0][1] += v[1]; s2[0][0] += xs[0]; s2[0][1] += xs[1]; }
+                                else { s1[1][0] += v[0]; s1[1][1] += v[1]; s2[1][0] += xs[0]; s2[1][1] += xs[1]; }
+                            }
                         }
                     }
                 }
@@ -814,108 +826,99 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tower_bwd_tc(const __grid_const
                 mbar_wait(dw_full, 0);
                 tc_fence_after();
             }
-            for (int j = 0; j <= nch; ++j) {
+            const int ngrp = (int)(col_db + 8 + 31) / 32;    // 32-column groups covering the weight and bias columns
+            for (int gidx = 0; gidx < ngrp; ++gidx) {
                 float v[32];
                 if (my_tiles > 0) {
-                    if (j < nch) tmem_ld32(tmem_base + 32 * j + lane_addr, v);
+                    if (32 * gidx + 32 <= (int)tmem_cols) tmem_ld32(tmem_base + 32 * gidx + lane_addr, v);
                     else {
                         float w8[16];
-                        tmem_ld16(tmem_base + col_db + lane_addr, w8);      // 8 columns used; 16 is the narrowest helper
-                        v[0] = w8[0];
+                        tmem_ld16(tmem_base + 32 * gidx + lane_addr, w8);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = i < 16 ? w8[i] : 0.f;
                     }
                 } else {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = 0.f;
                 }
                 if (act && n < N) {
-                    if (j < nch) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const int c = 32 * j + i;
-                            if (c < K) P[(size_t)n * (K + 1) + (STAGE1 ? gcol_stage1(c, KE, n_num) : c)] = v[i];
-                        }
-                    } else {
-                        P[(size_t)n * (K + 1) + K] = v[0];
+                    for (int i = 0; i < 32; ++i) {
+                        const int c = 32 * gidx + i;
+                        if (c < K) P[(size_t)n * (K + 1) + (STAGE1 ? gcol_stage1(c, KE, n_num) : c)] = v[i];
+                        else if (c == (int)col_db) P[(size_t)n * (K + 1) + K] = v[i];
                     }
                 }
             }
             tc_fence_before();
         }
     } else {
-        // ===================== producers =====================
-        const int ptid = tid - TC_PROD_WARP0 * 32;
-        const int grp = ptid / TC_GT, gtid = ptid - grp * TC_GT;
-        const int q = gtid & 7, sub = gtid >> 3;
+        // ===================== producers: thread <-> batch row =====================
+        // all sixteen warps work on one chunk at a time: eight threads per batch row
+        const int gtid = tid - TC_PROD_WARP0 * 32;
+        constexpr int QS = TC_PT / 64;                        // quad stride of a thread (8)
+        const int r = gtid & 63, qb = gtid >> 6;              // row of the tile; quads qb, qb + QS, ...
         const GatherSrc& g = S.in.g;
+        const int KE = g.n_tab * g.E;
         const float inv_keep = (!STAGE1 && S.in.a.drop.active) ? S.in.a.drop.inv_keep : 1.f;
-        constexpr int NXR = TCB_M / 32;                        // rows per thread and chunk
+        constexpr int NXR = CW / (4 * QS);                    // quads per thread and chunk
         constexpr int NX = STAGE1 ? NXR : 2 * NXR;             // stage > 1 also loads the pre-activation (x-hat)
         auto tile_row0 = [&](int it) { return ((long long)blockIdx.x + (long long)it * gridDim.x) * TCB_M; };
 
-        // G and G^T of tile `it` (group 0 only: it owns chunk 0 of every tile).  g = incoming gradient, through the
-        // BatchNorm backward of this layer's output when there is one.
-        const int qpr = npad >> 2;                            // quads per G row
+        // G and G^T of tile `it`, built by the group that owns the tile's first chunk.  g = incoming gradient, through
+        // the BatchNorm backward of this layer's output when there is one.
+        const int qpr = npad >> 2;                            // quads per G row (<= 16)
         auto build_g = [&](int it) {
-            const long long row0 = tile_row0(it);
-            const int nq = TCB_M * qpr;                        // <= 1024: at most four quads per thread
-            float4 gq[4], hq[4];
+            const long long row = tile_row0(it) + r;
+            constexpr int GQ = 16 / QS;                         // at most 16 quads per G row
+            float4 gq[GQ], hq[GQ];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int id = gtid + u * TC_GT;
+            for (int u = 0; u < GQ; ++u) {
+                const int c0 = 4 * (qb + QS * u);
                 gq[u] = make_float4(0.f, 0.f, 0.f, 0.f); hq[u] = gq[u];
-                if (id < nq) {
-                    const int r = id / qpr, c0 = 4 * (id - r * qpr);
-                    if (row0 + r < B && c0 < N) {
-                        gq[u] = ldg4(S.gin + (size_t)(row0 + r) * N + c0);
-                        if (S.g_mode == 1) hq[u] = ldg4(S.hs + (size_t)(row0 + r) * N + c0);
+                if (row < B && c0 < N) {
+                    gq[u] = ldg4(S.gin + (size_t)row * N + c0);
+                    if (S.g_mode == 1) hq[u] = ldg4(S.hs + (size_t)row * N + c0);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < GQ; ++u) {
+                const int c0 = 4 * (qb + QS * u);
+                if (row < B && c0 < N) {
+                    float gv[4] = {gq[u].x, gq[u].y, gq[u].z, gq[u].w};
+                    if (S.g_mode == 1) {
+                        const float hv[4] = {hq[u].x, hq[u].y, hq[u].z, hq[u].w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int c = c0 + e;
+                            const float xh = (hv[e] - sm_bng[c]) * sm_bng[Np + c];
+                            gv[e] = sm_bng[2 * Np + c] * (gv[e] - sm_bng[3 * Np + c] - xh * sm_bng[4 * Np + c]);
+                        }
+                    } else if (S.g_mode == 2) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) gv[e] *= sm_bng[2 * Np + c0 + e];
                     }
+                    gq[u] = make_float4(gv[0], gv[1], gv[2], gv[3]);
                 }
             }
             if (gtid == 0 && it < 6) trace(80 + 4 * it, tcode);
             if (it > 0) mbar_wait(g_empty, (it - 1) & 1);      // the MMAs of the previous tile have read G / G^T
             if (gtid == 0 && it < 6) trace(81 + 4 * it, tcode);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int id = gtid + u * TC_GT;
-                if (id < nq) {
-                    const int r = id / qpr, qq = id - r * qpr, c0 = 4 * qq;
-                    float gv[4] = {gq[u].x, gq[u].y, gq[u].z, gq[u].w};
-                    if (row0 + r < B && c0 < N) {
-                        if (S.g_mode == 1) {
-                            const float hv[4] = {hq[u].x, hq[u].y, hq[u].z, hq[u].w};
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const int c = c0 + e;
-                                const float xh = (hv[e] - sm_bng[c]) * sm_bng[Np + c];
-                                gv[e] = sm_bng[2 * Np + c] * (gv[e] - sm_bng[3 * Np + c] - xh * sm_bng[4 * Np + c]);
-                            }
-                        } else if (S.g_mode == 2) {
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) gv[e] *= sm_bng[2 * Np + c0 + e];
-                        }
-                    }
+            for (int u = 0; u < GQ; ++u) {
+                const int qq = qb + QS * u;
+                if (qq < qpr) {
                     float4 hi, lo;
-                    split_tf32x4(make_float4(gv[0], gv[1], gv[2], gv[3]), hi, lo);
+                    split_tf32x4(gq[u], hi, lo);
                     const uint32_t off = sw128_chunk(r, qq >> 3, qq & 7, TCB_M);
                     sts4(G + off, hi);
-                    sts4(G + G_IMG + off, lo);
-                }
-            }
-            named_bar_sync(2, TC_GT);
-            if (gtid == 0 && it < 6) trace(82 + 4 * it, tcode);
-            // transpose through shared memory: lane <-> batch row, so the scattered 4-byte stores of one instruction
-            // fall into one 128-byte row of G^T (conflict-free)
-            {
-                const int r = gtid & 63;
-                for (int qq = gtid >> 6; qq < qpr; qq += TC_GT / 64) {
-                    const uint32_t off = sw128_chunk(r, qq >> 3, qq & 7, TCB_M);
-                    const float4 hi = *reinterpret_cast<const float4*>(G + off), lo = *reinterpret_cast<const float4*>(G + G_IMG + off);
+                    if (exact) sts4(G + G_IMG + off, lo);
                     const float h4[4] = {hi.x, hi.y, hi.z, hi.w}, l4[4] = {lo.x, lo.y, lo.z, lo.w};
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const uint32_t o2 = sw128_off(4 * qq + e, r, 64);
                         *reinterpret_cast<float*>(GT + o2) = h4[e];
-                        *reinterpret_cast<float*>(GT + GT_IMG + o2) = l4[e];
+                        if (exact) *reinterpret_cast<float*>(GT + GT_IMG + o2) = l4[e];
                     }
                 }
             }
@@ -927,53 +930,69 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tower_bwd_tc(const __grid_const
         auto issue_idx = [&](const ChunkPos& p, long long (&ix)[NXR]) {
 #pragma unroll
             for (int i = 0; i < NXR; ++i) ix[i] = 0;
-            if (STAGE1 && p.it < my_tiles) gather_issue_idx<NXR>(g, B, tile_row0(p.it), p.j, q, sub, ix);
+            if (STAGE1 && p.it < my_tiles) {
+                const long long row = tile_row0(p.it) + r;
+                if (row < B) {
+#pragma unroll
+                    for (int i = 0; i < NXR; ++i) {
+                        const int c0 = CW * p.j + 4 * (qb + QS * i);
+                        if (c0 < KE) ix[i] = __ldg(g.x_cat + row * g.n_tab + c0 / g.E);
+                    }
+                }
+            }
         };
         auto issue_data = [&](const ChunkPos& p, const long long (&ix)[NXR], float4 (&x)[NX]) {
 #pragma unroll
             for (int i = 0; i < NX; ++i) x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (p.it >= my_tiles) return;
-            const long long row0 = tile_row0(p.it);
-            if (STAGE1) {
-                gather_issue_data<NXR>(g, B, row0, p.j, q, sub, ix, nullptr, x);
-            } else {
-                const int c0 = 32 * p.j + 4 * q;
-                if (c0 < K) {
+            const long long row = tile_row0(p.it) + r;
+            if (row >= B) return;
 #pragma unroll
-                    for (int i = 0; i < NXR; ++i) {
-                        const long long r = row0 + sub + 32 * i;
-                        if (r < B) {
-                            x[i] = ldg4(S.in.a.a_post + (size_t)r * K + c0);
-                            if (a_bn) x[NXR + i] = ldg4(S.in.a.h + (size_t)r * K + c0);
-                        }
+            for (int i = 0; i < NXR; ++i) {
+                const int c0 = CW * p.j + 4 * (qb + QS * i);
+                if (STAGE1) {
+                    if (c0 < KE) {                       // E % 4 == 0: a quad never straddles two tables
+                        const int t = c0 / g.E, e = c0 - t * g.E;
+                        long long v = ix[i];
+                        if (v < 0 || v >= g.tab_rows[t]) v = 0;      // reported by the forward
+                        x[i] = ldg4(g.tab[t] + (size_t)v * g.E + e);
+                    } else if (c0 < K) {
+                        float v[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (c0 + e < K) v[e] = __ldg(g.x_num + (size_t)row * g.n_num + (c0 + e - KE));
+                        x[i] = make_float4(v[0], v[1], v[2], v[3]);
                     }
+                } else if (c0 < K) {
+                    x[i] = ldg4(S.in.a.a_post + (size_t)row * K + c0);
+                    if (a_bn) x[NXR + i] = ldg4(S.in.a.h + (size_t)row * K + c0);
                 }
             }
         };
         auto consume = [&](const ChunkPos& p, float4 (&x)[NX]) {
-            if (grp == 0 && p.j == 0) build_g(p.it);
             const uint32_t cnt = (uint32_t)(p.it * nch + p.j);
+            if (p.j == 0) build_g(p.it);
             const int s = cnt % nst;
             mbar_wait(empty + s, ((cnt / nst) & 1) ^ 1);
             uint8_t* st = ring + s * L.stage;
             if (gtid == 0) {
                 if (need_dx) {
                     mbar_expect_tx(full + s, (uint32_t)(2 * WT_IMG));
-                    bulk_g2s(st + L.wt, S.wtimg + (size_t)p.j * tc_wt_chunk_floats(N), (uint32_t)(2 * WT_IMG), full + s);
+                    bulk_g2s(st + L.wt, S.wtimg + (size_t)p.j * tc_wt_chunk_floats(K, N), (uint32_t)(2 * WT_IMG), full + s);
                 } else {
                     mbar_arrive(full + s);
                 }
             }
-            const int c0 = 32 * p.j + 4 * q;
 #pragma unroll
             for (int i = 0; i < NXR; ++i) {
-                const int r = sub + 32 * i;
+                const int q = qb + QS * i;
+                const int c0 = CW * p.j + 4 * q;
                 const float4 a = x[i];
                 if (!STAGE1) {
                     // derivative of a = dropout(relu(.)) w.r.t. its argument, and x-hat, for the epilogue
                     const float4 m4 = make_float4(a.x > 0.f ? inv_keep : 0.f, a.y > 0.f ? inv_keep : 0.f, a.z > 0.f ? inv_keep : 0.f,
                                                   a.w > 0.f ? inv_keep : 0.f);
-                    sts4(st + L.msk + sw128_chunk(r, 0, q, TCB_M), m4);
+                    sts4(st + L.msk + sw128_chunk(r, q >> 3, q & 7, TCB_M), m4);
                     if (a_bn) {
                         const float4 h = x[NXR + i];
                         float4 xh = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -981,7 +1000,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tower_bwd_tc(const __grid_const
                             const float4 m = *reinterpret_cast<const float4*>(sm_bna + c0), is = *reinterpret_cast<const float4*>(sm_bna + Kp + c0);
                             xh = make_float4((h.x - m.x) * is.x, (h.y - m.y) * is.y, (h.z - m.z) * is.z, (h.w - m.w) * is.w);
                         }
-                        sts4(st + L.xh + sw128_chunk(r, 0, q, TCB_M), xh);
+                        sts4(st + L.xh + sw128_chunk(r, q >> 3, q & 7, TCB_M), xh);
                     }
                 }
                 float4 hi, lo;
@@ -989,7 +1008,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tower_bwd_tc(const __grid_const
                 const float h4[4] = {hi.x, hi.y, hi.z, hi.w}, l4[4] = {lo.x, lo.y, lo.z, lo.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    const uint32_t o2 = sw128_off(4 * q + e, r, 32);
+                    const uint32_t o2 = sw128_off(4 * q + e, r, ATR);
                     *reinterpret_cast<float*>(st + L.at + o2) = h4[e];
                     if (exact) *reinterpret_cast<float*>(st + L.at + AT_IMG + o2) = l4[e];
                 }
@@ -998,7 +1017,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tower_bwd_tc(const __grid_const
             mbar_arrive(full + s);
             if (gtid == 0 && cnt < 40) trace(2 + cnt, tcode);
         };
-        chunk_pipeline<2, NX, NXR>(my_tiles, nch, grp, issue_idx, issue_data, consume);
+        chunk_pipeline<1, 2, NX, NXR>(my_tiles, nch, 0, issue_idx, issue_data, consume);
     }
     tc_fence_before();
     __syncthreads();
@@ -1091,8 +1110,10 @@ int tc_fwd_launch(FwdArgs& a, const cfm_tower_t* towers, int n_towers, int s, in
 int tc_bwd_launch(BwdArgs& a, const cfm_tower_t* towers, int n_towers, int s, int* ctas_out, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        CFM_CHECK_CUDA(cudaFuncSetAttribute(tower_bwd_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX));
-        CFM_CHECK_CUDA(cudaFuncSetAttribute(tower_bwd_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX));
+        CFM_CHECK_CUDA(cudaFuncSetAttribute(tower_bwd_tc<true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX));
+        CFM_CHECK_CUDA(cudaFuncSetAttribute(tower_bwd_tc<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX));
+        CFM_CHECK_CUDA(cudaFuncSetAttribute(tower_bwd_tc<false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX));
+        CFM_CHECK_CUDA(cudaFuncSetAttribute(tower_bwd_tc<false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX));
         attr_set = true;
     }
     size_t smem = 0;
@@ -1109,8 +1130,14 @@ int tc_bwd_launch(BwdArgs& a, const cfm_tower_t* towers, int n_towers, int s, in
     const int ctas = (int)std::min<long long>(ntiles, sm_count());
     *ctas_out = ctas;
     const dim3 grid(ctas, (unsigned)n_towers);
-    if (s == 1) tower_bwd_tc<true><<<grid, TC_THREADS, smem, stream>>>(a);
-    else tower_bwd_tc<false><<<grid, TC_THREADS, smem, stream>>>(a);
+    const int cw = tcb_cw(st_K(towers[0], s));
+    if (s == 1) {
+        if (cw == 64) tower_bwd_tc<true, 64><<<grid, TC_THREADS, smem, stream>>>(a);
+        else tower_bwd_tc<true, 32><<<grid, TC_THREADS, smem, stream>>>(a);
+    } else {
+        if (cw == 64) tower_bwd_tc<false, 64><<<grid, TC_THREADS, smem, stream>>>(a);
+        else tower_bwd_tc<false, 32><<<grid, TC_THREADS, smem, stream>>>(a);
+    }
     CFM_LAUNCH_CHECK();
     return CFM_OK;
 }

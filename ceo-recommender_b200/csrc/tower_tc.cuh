@@ -8,14 +8,17 @@ namespace cfm {
 // Per tower and Linear layer, rebuilt once per forward call by tc_prep_weights (the weights change every step):
 //   forward image   : W [Npad rows][K columns] cut into chunks of 32 input columns; chunk j = hi image then lo
 //                     image, each [Npad][32 floats] 128-byte swizzled (the K-major B operand of  H = X . W^T)
-//   transposed image: W^T [K rows][N columns] cut into chunks of 32 rows (input columns); chunk j = hi then lo,
-//                     each [32][nblk * 32 floats] (the K-major B operand of  dX[:, chunk j] = G . W[:, chunk j])
+//   transposed image: W^T [K rows][N columns] cut into chunks of 64 rows (input columns); chunk j = hi then lo,
+//                     each [64][nblk * 32 floats] (the K-major B operand of  dX[:, chunk j] = G . W[:, chunk j])
 // Stage-1 input columns are in tile order [embedding columns | numeric columns] (gcol_stage1 maps back).
 __host__ __device__ inline int tc_npad(int N) { return (N + 15) & ~15; }
 __host__ __device__ inline int tc_nch(int K) { return (K + 31) >> 5; }
 __host__ __device__ inline int tc_nblk(int N) { return (tc_npad(N) + 31) >> 5; }
 __host__ __device__ inline int tc_w_chunk_floats(int N) { return 2 * tc_npad(N) * 32; }
-__host__ __device__ inline int tc_wt_chunk_floats(int N) { return 2 * 32 * tc_nblk(N) * 32; }
+// the backward walks the input columns in chunks of 64 (32 for layers with at most 32 inputs)
+__host__ __device__ inline int tcb_cw(int K) { return K <= 32 ? 32 : 64; }
+__host__ __device__ inline int tcb_nch(int K) { return (K + tcb_cw(K) - 1) / tcb_cw(K); }
+__host__ __device__ inline int tc_wt_chunk_floats(int K, int N) { return 2 * tcb_cw(K) * tc_nblk(N) * 32; }
 struct WImgLayout {
     int w[3], wt[3];      // float offsets of the forward / transposed images of layers 1..3
     int total;
@@ -25,7 +28,7 @@ __host__ __device__ inline WImgLayout wimg_layout(const int (&K)[3], const int (
     int o = 0;
     for (int s = 0; s < 3; ++s) {
         L.w[s] = o;  o += tc_nch(K[s]) * tc_w_chunk_floats(N[s]);
-        L.wt[s] = o; o += tc_nch(K[s]) * tc_wt_chunk_floats(N[s]);
+        L.wt[s] = o; o += tcb_nch(K[s]) * tc_wt_chunk_floats(K[s], N[s]);
     }
     L.total = o;
     return L;

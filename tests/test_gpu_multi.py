@@ -1,4 +1,6 @@
-"""Multi-GPU parity (needs >= 2 GPUs on the box; skipped otherwise): one process per GPU over NCCL."""
+"""Multi-GPU parity: one process per GPU over NCCL (tests/mgpu_worker.py).  The full-width run needs >= 2 GPUs; the
+single-rank run drives the SAME protocol code (NCCL process group, gradient all-reduce, table-sharded step through the
+owner-side peer reduce, global-negative InfoNCE, sharded top-k merge) on any one-GPU box."""
 import os
 import socket
 import subprocess
@@ -24,3 +26,10 @@ def test_multi_gpu_paths_match_oracle():
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), os.path.join(HERE, "mgpu_worker.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0 and "MULTIGPU_OK" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
+
+
+def test_distributed_protocol_single_rank_nccl():
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=1",
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), os.path.join(HERE, "mgpu_worker.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=420)
+    assert res.returncode == 0 and "MULTIGPU_OK world=1" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]

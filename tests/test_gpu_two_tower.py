@@ -182,6 +182,25 @@ def test_dropout_mask_parity_and_statistics():
     assert float(loss2) != float(loss)
 
 
+def test_dropout_masks_of_consecutive_steps_are_independent():
+    """nn.Dropout draws an independent mask every step (model.py:41,45).  With the step offset and the column group in
+    different Philox counter words, consecutive offsets must not give column-permuted copies of one mask: per-row
+    keep counts differ between steps and are uncorrelated."""
+    from ceo_firm_matching import ops
+    dev = torch.device(DEV, torch.cuda.current_device())
+    B, W = 4096, 64
+    counts = []
+    for offset in range(1, 9):
+        mask = ops.dropout_mask(B, W, 0.1, 0, 0, 1234, offset, dev).cpu().float()
+        counts.append(mask.sum(1))
+    c = torch.stack(counts)                                  # [steps, rows]
+    for a in range(8):
+        for b in range(a + 1, 8):
+            assert not torch.equal(c[a], c[b]), f"offsets {a + 1} and {b + 1} keep the same number of units in every row"
+            corr = torch.corrcoef(torch.stack([c[a], c[b]]))[0, 1].item()
+            assert abs(corr) < 0.08, f"per-row keep counts of offsets {a + 1}, {b + 1} are correlated ({corr:.3f})"
+
+
 def test_bitwise_deterministic():
     f_cards, c_cards = [50, 5, 3, 2], [2, 4, 3, 2, 2, 5, 2]
     B = 5000
