@@ -126,26 +126,53 @@ __global__ void __launch_bounds__(256) tc_prep_weights(const __grid_constant__ P
 // ------------------------------------------------------------------------------------------
 // producers: one chunk = 32 input columns of a row tile
 // ------------------------------------------------------------------------------------------
-// a = dropout(relu(bn(h))) for a 4-column quad
+// a = dropout(relu(bn(h))) for a 4-column quad.  `code` is what the forward saves for the backward: the normalised
+// pre-activation x-hat (the raw pre-activation when no BatchNorm precedes) where the unit is active and kept, NaN
+// elsewhere - one tensor from which the backward recovers a, the activation derivative and x-hat (act_decode).
 __device__ __forceinline__ float4 act_quad(const float4& h, const float* sm_bn, int Kp, int c0, int bn_mode, const DropCtx& drop,
-                                           long long row) {
-    float t[4] = {h.x, h.y, h.z, h.w};
+                                           long long row, float4* code) {
+    float t[4] = {h.x, h.y, h.z, h.w}, u[4] = {h.x, h.y, h.z, h.w};
     if (bn_mode) {
         const float4 m = *reinterpret_cast<const float4*>(sm_bn + c0), is = *reinterpret_cast<const float4*>(sm_bn + Kp + c0);
         const float4 ga = *reinterpret_cast<const float4*>(sm_bn + 2 * Kp + c0), be = *reinterpret_cast<const float4*>(sm_bn + 3 * Kp + c0);
-        t[0] = (t[0] - m.x) * is.x * ga.x + be.x; t[1] = (t[1] - m.y) * is.y * ga.y + be.y;
-        t[2] = (t[2] - m.z) * is.z * ga.z + be.z; t[3] = (t[3] - m.w) * is.w * ga.w + be.w;
+        u[0] = (t[0] - m.x) * is.x; u[1] = (t[1] - m.y) * is.y; u[2] = (t[2] - m.z) * is.z; u[3] = (t[3] - m.w) * is.w;
+        t[0] = u[0] * ga.x + be.x; t[1] = u[1] * ga.y + be.y; t[2] = u[2] * ga.z + be.z; t[3] = u[3] * ga.w + be.w;
     }
-#pragma unroll
-    for (int e = 0; e < 4; ++e) t[e] = fmaxf(t[e], 0.f);
+    bool keep[4] = {true, true, true, true};
     if (drop.active) {
         const Philox4 w = drop_words(drop, row, c0 >> 2);
-        t[0] = w.x >= drop.thresh ? t[0] * drop.inv_keep : 0.f;
-        t[1] = w.y >= drop.thresh ? t[1] * drop.inv_keep : 0.f;
-        t[2] = w.z >= drop.thresh ? t[2] * drop.inv_keep : 0.f;
-        t[3] = w.w >= drop.thresh ? t[3] * drop.inv_keep : 0.f;
+        keep[0] = w.x >= drop.thresh; keep[1] = w.y >= drop.thresh; keep[2] = w.z >= drop.thresh; keep[3] = w.w >= drop.thresh;
     }
+    const float nanv = __int_as_float(0x7fc00000);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const bool on = t[e] > 0.f && keep[e];
+        t[e] = on ? t[e] * drop.inv_keep : 0.f;
+        u[e] = on ? u[e] : nanv;
+    }
+    if (code) *code = make_float4(u[0], u[1], u[2], u[3]);
     return make_float4(t[0], t[1], t[2], t[3]);
+}
+// backward side of act_quad: from the saved code, a (for the weight gradient), d a / d pre-activation and x-hat
+__device__ __forceinline__ void act_decode(const float4& code, const float* sm_bn, int Kp, int c0, int bn_mode, float inv_keep,
+                                           float4& a, float4& dact, float4& xhat) {
+    const float u[4] = {code.x, code.y, code.z, code.w};
+    float t[4] = {u[0], u[1], u[2], u[3]};
+    if (bn_mode) {
+        const float4 ga = *reinterpret_cast<const float4*>(sm_bn + 2 * Kp + c0), be = *reinterpret_cast<const float4*>(sm_bn + 3 * Kp + c0);
+        t[0] = u[0] * ga.x + be.x; t[1] = u[1] * ga.y + be.y; t[2] = u[2] * ga.z + be.z; t[3] = u[3] * ga.w + be.w;
+    }
+    float av[4], dv[4], xv[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const bool on = u[e] == u[e];                 // not NaN
+        av[e] = on ? t[e] * inv_keep : 0.f;
+        dv[e] = on ? inv_keep : 0.f;
+        xv[e] = on ? u[e] : 0.f;
+    }
+    a = make_float4(av[0], av[1], av[2], av[3]);
+    dact = make_float4(dv[0], dv[1], dv[2], dv[3]);
+    xhat = make_float4(xv[0], xv[1], xv[2], xv[3]);
 }
 
 __device__ __forceinline__ void stage_bn_params_tc(const ActSrc& a, int K, float* sm_bn, int tid, int nthreads) {
@@ -521,8 +548,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tower_fwd_tc(const __grid_const
                 float4 a = x[i];
                 if (!STAGE1) {
                     if (row0 + r < B && c0 < K) {
-                        a = act_quad(a, sm_bn, Kp, c0, S.in.a.bn_mode, drop, row0 + r);
-                        if (S.a_out) *reinterpret_cast<float4*>(S.a_out + (size_t)(row0 + r) * K + c0) = a;
+                        float4 code;
+                        a = act_quad(a, sm_bn, Kp, c0, S.in.a.bn_mode, drop, row0 + r, &code);
+                        if (S.a_out) *reinterpret_cast<float4*>(S.a_out + (size_t)(row0 + r) * K + c0) = code;
                     } else {
                         a = make_float4(0.f, 0.f, 0.f, 0.f);
                     }
@@ -862,7 +890,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tower_bwd_tc(const __grid_const
         const int KE = g.n_tab * g.E;
         const float inv_keep = (!STAGE1 && S.in.a.drop.active) ? S.in.a.drop.inv_keep : 1.f;
         constexpr int NXR = CW / (4 * QS);                    // quads per thread and chunk
-        constexpr int NX = STAGE1 ? NXR : 2 * NXR;             // stage > 1 also loads the pre-activation (x-hat)
+        constexpr int NX = NXR;
         auto tile_row0 = [&](int it) { return ((long long)blockIdx.x + (long long)it * gridDim.x) * TCB_M; };
 
         // G and G^T of tile `it`, built by the group that owns the tile's first chunk.  g = incoming gradient, through
@@ -964,8 +992,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tower_bwd_tc(const __grid_const
                         x[i] = make_float4(v[0], v[1], v[2], v[3]);
                     }
                 } else if (c0 < K) {
-                    x[i] = ldg4(S.in.a.a_post + (size_t)row * K + c0);
-                    if (a_bn) x[NXR + i] = ldg4(S.in.a.h + (size_t)row * K + c0);
+                    x[i] = ldg4(S.in.a.a_post + (size_t)row * K + c0);       // the forward's saved code (act_quad)
                 }
             }
         };
@@ -987,21 +1014,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tower_bwd_tc(const __grid_const
             for (int i = 0; i < NXR; ++i) {
                 const int q = qb + QS * i;
                 const int c0 = CW * p.j + 4 * q;
-                const float4 a = x[i];
+                float4 a = x[i];
                 if (!STAGE1) {
-                    // derivative of a = dropout(relu(.)) w.r.t. its argument, and x-hat, for the epilogue
-                    const float4 m4 = make_float4(a.x > 0.f ? inv_keep : 0.f, a.y > 0.f ? inv_keep : 0.f, a.z > 0.f ? inv_keep : 0.f,
-                                                  a.w > 0.f ? inv_keep : 0.f);
+                    // a, its derivative w.r.t. the pre-activation and x-hat from the saved code; the last two go to the
+                    // epilogue through the ring stage
+                    float4 m4 = make_float4(0.f, 0.f, 0.f, 0.f), xh = m4;
+                    if (c0 < K && tile_row0(p.it) + r < B) act_decode(x[i], sm_bna, Kp, c0, S.in.a.bn_mode, inv_keep, a, m4, xh);
+                    else a = m4;
                     sts4(st + L.msk + sw128_chunk(r, q >> 3, q & 7, TCB_M), m4);
-                    if (a_bn) {
-                        const float4 h = x[NXR + i];
-                        float4 xh = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (c0 < K) {
-                            const float4 m = *reinterpret_cast<const float4*>(sm_bna + c0), is = *reinterpret_cast<const float4*>(sm_bna + Kp + c0);
-                            xh = make_float4((h.x - m.x) * is.x, (h.y - m.y) * is.y, (h.z - m.z) * is.z, (h.w - m.w) * is.w);
-                        }
-                        sts4(st + L.xh + sw128_chunk(r, q >> 3, q & 7, TCB_M), xh);
-                    }
+                    if (a_bn) sts4(st + L.xh + sw128_chunk(r, q >> 3, q & 7, TCB_M), xh);
                 }
                 float4 hi, lo;
                 split_tf32x4(a, hi, lo);

@@ -82,9 +82,10 @@ typedef struct cfm_tower {
     float *wimg;                 /* cfm_tower_wimg_floats() floats: (hi, lo)-split, swizzled images of the three weight
                                     matrices for the tcgen05 stage kernels, rebuilt by every cfm_towers_fwd call and read
                                     by the cfm_towers_bwd call that follows it.  NULL: the mma.sync stage kernels run. */
-    float *a1, *a2;              /* [B,h1], [B,h2]: post-activation inputs of Linear 2 / 3 (dropout applied), written by the
-                                    tcgen05 forward stages so that the backward needs neither BatchNorm nor the dropout
-                                    stream again; required (non-NULL) together with wimg */
+    float *a1, *a2;              /* [B,h1], [B,h2]: activation codes of the inputs of Linear 2 / 3, written by the tcgen05
+                                    forward stages: x-hat (the raw pre-activation without BatchNorm) where the unit is active
+                                    and kept by dropout, NaN elsewhere - the backward recovers the activation, its derivative
+                                    and x-hat from this one tensor; required (non-NULL) together with wimg */
 } cfm_tower_t;
 
 /* floats of `scratch` needed per persistent CTA for this tower shape (fwd and bwd share it) */

@@ -29,6 +29,7 @@ for code in [int(a) for a in sys.argv[1:]] or [1]:
             print("  mma :", [rel(x) for x in r[48:56] if int(x)])
             print("  epi :", [rel(x) for x in r[64:72] if int(x)])
             print("  gbld:", [rel(x) for x in r[80:104] if int(x)])
+            print("  cons:", [rel(x) for x in r[104:124] if int(x)])
     st = t[:, :, 0]
     t0all = int(st[st > 0].min())
     print("tower0 starts [%.2f, %.2f] ends [%.2f, %.2f]; tower1 starts [%.2f, %.2f] ends [%.2f, %.2f] us" % (
