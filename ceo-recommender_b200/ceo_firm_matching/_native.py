@@ -38,7 +38,7 @@ class Tower(C.Structure):
         ("bn1_nbt", C.c_void_p), ("bn2_nbt", C.c_void_p),
         ("h1_raw", C.c_void_p), ("h2_raw", C.c_void_p), ("out", C.c_void_p),
         ("bn1_stat", C.c_void_p), ("bn2_stat", C.c_void_p), ("scratch", C.c_void_p), ("wimg", C.c_void_p),
-        ("a1", C.c_void_p), ("a2", C.c_void_p),
+        ("a1", C.c_void_p), ("a2", C.c_void_p), ("xstash", C.c_void_p),
     ]
 
 
@@ -88,6 +88,7 @@ PROTOTYPES = {
     "cfm_device_info": (C.c_int, [C.POINTER(i64)] * 4),
     "cfm_tower_scratch_floats": (i64, [C.POINTER(Tower)]),
     "cfm_tower_wimg_floats": (i64, [C.POINTER(Tower)]),
+    "cfm_tower_xstash_floats": (i64, [C.POINTER(Tower), _I]),
     "cfm_launch_count": (i64, [_I]),
     "cfm_profile_enable": (C.c_int, [_I]),
     "cfm_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(i64), _I]),

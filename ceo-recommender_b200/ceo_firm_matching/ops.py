@@ -149,7 +149,7 @@ class TowerHandle:
 class _TowerCall:
     """Everything one fwd/bwd pair of a tower shares: the C struct and the tensors keeping it alive."""
 
-    def __init__(self, h: TowerHandle, x_num: torch.Tensor, x_cat: torch.Tensor, B: int):
+    def __init__(self, h: TowerHandle, x_num: torch.Tensor, x_cat: torch.Tensor, B: int, training: bool = False):
         dev = x_num.device
         l1, l2, l3 = h.linear(0), h.linear(1), h.linear(2)
         b1, b2 = h.batchnorm(0), h.batchnorm(1)
@@ -203,6 +203,10 @@ class _TowerCall:
             self.a1 = torch.empty(B, l1.out_features, device=dev)
             self.a2 = torch.empty(B, l2.out_features, device=dev)
             t.a1, t.a2 = N.ptr(self.a1), N.ptr(self.a2)
+            if training and h.n_tables:
+                # gathered stage-1 inputs, kept for the backward (sequential re-read instead of a second random gather)
+                self.xstash = torch.empty(N.lib().cfm_tower_xstash_floats(C.byref(t), B), device=dev)
+                t.xstash = N.ptr(self.xstash)
         self.struct = t
 
 
@@ -229,7 +233,7 @@ class TowersFunction(torch.autograd.Function):
             for i, h in enumerate(handles):
                 x_num = xs[2 * i].contiguous().float()
                 x_cat = _as_index(xs[2 * i + 1]).contiguous()
-                calls.append(_TowerCall(h, x_num, x_cat, B))
+                calls.append(_TowerCall(h, x_num, x_cat, B, training))
             arr = (N.Tower * n)(*[c.struct for c in calls])
             rng_dev = _graph_rng_counter if training else None
             joint = _joint_for(calls) if (training and any(ctx.needs_input_grad)) else None

@@ -546,6 +546,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tower_fwd_tc(const __grid_const
             for (int i = 0; i < NX; ++i) {
                 const int r = sub + 32 * i;
                 float4 a = x[i];
+                if (STAGE1 && S.x_out && row0 + r < B) {
+                    // input stash for the backward: 16 KB blocks [64-row tile][64-column chunk], rows of 16 quads with
+                    // the quad index XOR-ed by the row (the backward reads it lane <-> row without bank conflicts)
+                    const long long gr = row0 + r;
+                    const int q16 = (c0 & 63) >> 2, r64 = (int)(gr & 63);
+                    float* blk = S.x_out + ((gr >> 6) * tcb_nch(K) + (c0 >> 6)) * 4096;
+                    *reinterpret_cast<float4*>(blk + r64 * 64 + ((q16 ^ (r64 & 15)) << 2)) = a;
+                }
                 if (!STAGE1) {
                     if (row0 + r < B && c0 < K) {
                         float4 code;
@@ -582,14 +590,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tower_fwd_tc(const __grid_const
 // from registers, one 128-byte row per store instruction.
 // ------------------------------------------------------------------------------------------
 struct TcBwdSmem {
-    int g, gt, ring, at, wt, msk, xh, stage, bna, bng, red, bars, tmem, total, nst, at_img;
+    int g, gt, raw, ring, at, wt, msk, xh, stage, bna, bng, red, bars, tmem, total, nst, at_img;
 };
-__host__ __device__ inline TcBwdSmem tcb_smem(int K, int N, bool stage1, bool a_bn) {
+__host__ __device__ inline TcBwdSmem tcb_smem(int K, int N, bool stage1, bool a_bn, bool stash = false) {
     TcBwdSmem s;
     const int nbn = tc_nblk(N), Kp = (K + 3) & ~3, Np = (N + 3) & ~3, cw = tcb_cw(K);
     int o = 0;
     s.g = o; o += 2 * TCB_M * 128 * nbn;              // G   [64 rows][N]      hi, lo
     s.gt = o; o += 2 * 64 * 128 * 2;                  // G^T [64 n][64 rows]   hi, lo
+    s.raw = o; o += stash ? 64 * 64 * 4 : 0;          // one block of the forward's input stash (bulk copy target)
     s.ring = o;
     int st = 0;
     s.at_img = (cw + 8) * 128 * 2;                    // A^T chunk [cw k + 8][64 rows]: row cw = ones (bias gradient)
@@ -628,7 +637,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tower_bwd_tc(const __grid_const
     const int K = S.in.K, N = S.N, npad = tc_npad(N), nbn = tc_nblk(N), nch = tcb_nch(K);
     const int Kp = (K + 3) & ~3, Np = (N + 3) & ~3;
     const bool a_bn = S.a_bn != 0, need_dx = S.need_dx != 0;
-    const TcBwdSmem L = tcb_smem(K, N, STAGE1, a_bn);
+    const bool stash = STAGE1 && S.x_in != nullptr;
+    const TcBwdSmem L = tcb_smem(K, N, STAGE1, a_bn, stash);
     const int nst = L.nst;
     uint8_t *G = sm + L.g, *GT = sm + L.gt, *ring = sm + L.ring;
     const int G_IMG = TCB_M * 128 * nbn;
@@ -640,7 +650,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tower_bwd_tc(const __grid_const
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L.bars);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + L.tmem);
     uint64_t *full = bars, *empty = bars + 4, *g_full = bars + 8, *g_empty = bars + 9, *dx_full = bars + 10, *dx_empty = bars + 12,
-             *dw_full = bars + 14;
+             *dw_full = bars + 14, *raw_full = bars + 15;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long B = args.B;
@@ -657,6 +667,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tower_bwd_tc(const __grid_const
         mbar_init(g_full, TC_PT); mbar_init(g_empty, 1);
         for (int b = 0; b < 2; ++b) { mbar_init(dx_full + b, 1); mbar_init(dx_empty + b, TC_EPI_WARPS * 32); }
         mbar_init(dw_full, 1);
+        mbar_init(raw_full, 1);
         fence_barrier_init();
     }
     if (warp == TC_MMA_WARP) tmem_alloc(tmem_slot, tmem_cols);
@@ -955,10 +966,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tower_bwd_tc(const __grid_const
             if (gtid == 0 && it < 6) trace(83 + 4 * it, tcode);
         };
 
+        uint8_t* raw = sm + L.raw;
+        auto stash_block = [&](const ChunkPos& p) {
+            return S.x_in + ((tile_row0(p.it) >> 6) * nch + p.j) * 4096;
+        };
+        if (stash && gtid == 0 && my_tiles > 0) {       // block of the first chunk
+            mbar_expect_tx(raw_full, 16384u);
+            bulk_g2s(raw, S.x_in + (tile_row0(0) >> 6) * nch * 4096, 16384u, raw_full);
+        }
         auto issue_idx = [&](const ChunkPos& p, long long (&ix)[NXR]) {
 #pragma unroll
             for (int i = 0; i < NXR; ++i) ix[i] = 0;
-            if (STAGE1 && p.it < my_tiles) {
+            if (STAGE1 && !stash && p.it < my_tiles) {
                 const long long row = tile_row0(p.it) + r;
                 if (row < B) {
 #pragma unroll
@@ -972,7 +991,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tower_bwd_tc(const __grid_const
         auto issue_data = [&](const ChunkPos& p, const long long (&ix)[NXR], float4 (&x)[NX]) {
 #pragma unroll
             for (int i = 0; i < NX; ++i) x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.it >= my_tiles) return;
+            if (p.it >= my_tiles || stash) return;
             const long long row = tile_row0(p.it) + r;
             if (row >= B) return;
 #pragma unroll
@@ -998,6 +1017,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tower_bwd_tc(const __grid_const
         };
         auto consume = [&](const ChunkPos& p, float4 (&x)[NX]) {
             const uint32_t cnt = (uint32_t)(p.it * nch + p.j);
+            if (STAGE1 && stash) {
+                // this chunk's block of the forward's input stash has been travelling since the previous chunk
+                mbar_wait(raw_full, cnt & 1);
+                const bool rv = tile_row0(p.it) + r < B;
+#pragma unroll
+                for (int i = 0; i < NXR; ++i) {
+                    const int q = qb + QS * i;
+                    x[i] = (rv && CW * p.j + 4 * q < K) ? *reinterpret_cast<const float4*>(raw + r * 256 + ((q ^ (r & 15)) << 4))
+                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                fence_proxy_async();
+                named_bar_sync(2, TC_PT);                      // every thread holds its quads: the buffer is free again
+                ChunkPos nx = p;
+                nx.template next<1>(nch);
+                if (gtid == 0 && nx.it < my_tiles) {
+                    mbar_expect_tx(raw_full, 16384u);
+                    bulk_g2s(raw, stash_block(nx), 16384u, raw_full);
+                }
+            }
             if (p.j == 0) build_g(p.it);
             const int s = cnt % nst;
             mbar_wait(empty + s, ((cnt / nst) & 1) ^ 1);
@@ -1071,7 +1109,7 @@ bool tc_bwd_supported(const cfm_tower_t& t, int s, bool a_bn, bool need_dx) {
     if (N & 3) return false;
     if (s > 1 && K > 64) return false;
     (void)need_dx;
-    return tcb_smem(K, N, s == 1, a_bn).nst >= 2;
+    return tcb_smem(K, N, s == 1, a_bn, s == 1 && t.xstash).nst >= 2;
 }
 
 int tc_prep_launch(const cfm_tower_t* towers, int n_towers, cudaStream_t stream) {
@@ -1110,6 +1148,7 @@ int tc_fwd_launch(FwdArgs& a, const cfm_tower_t* towers, int n_towers, int s, in
         const WImgLayout L = wimg_layout(K, N);
         a.st[i].wimg = t.wimg + L.w[s - 1];
         a.st[i].a_out = s == 2 ? t.a1 : s == 3 ? t.a2 : nullptr;
+        a.st[i].x_out = s == 1 ? t.xstash : nullptr;
         smem = std::max(smem, (size_t)tcf_smem(K[s - 1], N[s - 1]).total);
         if (tc_npad(N[s - 1]) > 32) nc = 64;
     }
@@ -1145,7 +1184,8 @@ int tc_bwd_launch(BwdArgs& a, const cfm_tower_t* towers, int n_towers, int s, in
         const WImgLayout L = wimg_layout(K, N);
         a.st[i].wtimg = t.wimg + L.wt[s - 1];
         a.st[i].in.a.a_post = s == 2 ? t.a1 : s == 3 ? t.a2 : nullptr;
-        smem = std::max(smem, (size_t)tcb_smem(K[s - 1], N[s - 1], s == 1, a.st[i].a_bn != 0).total);
+        a.st[i].x_in = s == 1 ? t.xstash : nullptr;
+        smem = std::max(smem, (size_t)tcb_smem(K[s - 1], N[s - 1], s == 1, a.st[i].a_bn != 0, s == 1 && t.xstash).total);
     }
     const long long ntiles = (a.B + TCB_M - 1) / TCB_M;
     const int ctas = (int)std::min<long long>(ntiles, sm_count());
@@ -1170,6 +1210,11 @@ extern "C" int cfm_debug_set_trace(uint64_t* buf, int64_t code) {
     CFM_CHECK_CUDA(cudaMemcpyToSymbol(cfm::g_trace, &buf, sizeof(buf)));
     CFM_CHECK_CUDA(cudaMemcpyToSymbol(cfm::g_trace_code, &c, sizeof(c)));
     return CFM_OK;
+}
+
+extern "C" int64_t cfm_tower_xstash_floats(const cfm_tower_t* t, int64_t B) {
+    const int K = cfm::st_K(*t, 1);
+    return ((B + 63) / 64) * cfm::tcb_nch(K) * 4096;
 }
 
 extern "C" int64_t cfm_tower_wimg_floats(const cfm_tower_t* t) {

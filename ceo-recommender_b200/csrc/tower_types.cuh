@@ -64,6 +64,7 @@ struct FwdStage {
     float* stat_part;     // nullable: per-CTA (mean[N], M2[N], count) partials
     const float* wimg;    // tcgen05 path: forward weight image of this layer (tower_tc.cuh)
     float* a_out;         // tcgen05 path, stage > 1: where the producers save the input activation a (nullable)
+    float* x_out;         // tcgen05 path, stage 1: stash of the gathered input tiles (nullable; tower_tc.cu)
 };
 struct FwdArgs {
     FwdStage st[2];
@@ -89,6 +90,7 @@ struct BwdStage {
     float* dx_num;        // stage 1, nullable: [B, n_num]
     int need_dx;          // run the dX GEMM
     const float* wtimg;   // tcgen05 path: transposed weight image of this layer (tower_tc.cuh)
+    const float* x_in;    // tcgen05 path, stage 1: the forward's stash of input tiles (nullable: gather again)
 };
 struct BwdArgs {
     BwdStage st[2];

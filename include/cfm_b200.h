@@ -86,12 +86,18 @@ typedef struct cfm_tower {
                                     forward stages: x-hat (the raw pre-activation without BatchNorm) where the unit is active
                                     and kept by dropout, NaN elsewhere - the backward recovers the activation, its derivative
                                     and x-hat from this one tensor; required (non-NULL) together with wimg */
+    float *xstash;               /* cfm_tower_xstash_floats(t, B) floats, nullable: the tcgen05 stage-1 forward saves its
+                                    gathered input tiles here (16 KB blocks of 64 rows x 64 columns) and the stage-1
+                                    backward streams them back with bulk copies instead of gathering every embedding
+                                    row from HBM a second time */
 } cfm_tower_t;
 
 /* floats of `scratch` needed per persistent CTA for this tower shape (fwd and bwd share it) */
 int64_t cfm_tower_scratch_floats(const cfm_tower_t* t);
 /* floats of `wimg` for this tower shape */
 int64_t cfm_tower_wimg_floats(const cfm_tower_t* t);
+/* floats of `xstash` for this tower shape and batch */
+int64_t cfm_tower_xstash_floats(const cfm_tower_t* t, int64_t B);
 
 /* Forward of `n_towers` towers over the same B rows in one set of launches.
  * training=1: batch-stat BN (running stats updated), dropout drawn from a counter-based
