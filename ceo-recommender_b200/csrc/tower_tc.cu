@@ -1036,7 +1036,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tower_bwd_tc(const __grid_const
                     bulk_g2s(raw, stash_block(nx), 16384u, raw_full);
                 }
             }
-            if (p.j == 0) build_g(p.it);
             const int s = cnt % nst;
             mbar_wait(empty + s, ((cnt / nst) & 1) ^ 1);
             uint8_t* st = ring + s * L.stage;
@@ -1075,6 +1074,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tower_bwd_tc(const __grid_const
             fence_proxy_async();
             mbar_arrive(full + s);
             if (gtid == 0 && cnt < 40) trace(2 + cnt, tcode);
+            // G / G^T of the tile are single-buffered and can only be rewritten when the previous tile's MMAs are done;
+            // the tile's first chunk (which only needs a free ring stage) is therefore staged BEFORE G is rebuilt, so
+            // the tensor core finds work the moment G arrives
+            if (p.j == 0) build_g(p.it);
         };
         chunk_pipeline<1, 2, NX, NXR>(my_tiles, nch, 0, issue_idx, issue_data, consume);
     }
