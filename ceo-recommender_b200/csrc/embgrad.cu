@@ -3,9 +3,13 @@
 //
 // 1. keys = (table << idx_bits) | index for every (row, table) pair, values = row          (1 kernel)
 // 2. stable LSD radix sort of (key, row) over the minimal number of key bits (cub)          (library sort)
-// 3. one thread group per segment head walks its run of equal keys in row order, sums the
-//    [E]-wide slices of dx_emb and writes the dense gradient row once                         (1 kernel)
-// Equal keys keep increasing row order (stable sort), so the floating-point sum order is fixed.
+// 3. every run of equal keys is cut into chunks of SEG_CHUNK positions counted from the run's first position; one
+//    thread per (chunk, 16-byte slice) sums its chunk in position order; a run that fits one chunk is written
+//    straight to the dense gradient row, longer runs leave per-chunk partials that a second kernel adds in chunk
+//    order                                                                                       (2 kernels)
+// Equal keys keep increasing row order (stable sort) and the chunk grid hangs on the run itself, so the
+// floating-point sum order is fixed whatever the launch geometry - and a low-cardinality column (runs of tens of
+// thousands of rows: data.py:120-126 has tables of 2-4 classes) is reduced by hundreds of threads instead of one.
 #include "common.cuh"
 #include <cub/device/device_radix_sort.cuh>
 #include <algorithm>
@@ -13,6 +17,138 @@
 namespace cfm {
 
 struct TablePtrs { float* p[CFM_MAX_TABLES]; long long rows[CFM_MAX_TABLES]; };
+
+// ------------------------------------------------------------------------------------------
+// two-level fixed-order segment reduce shared by the single-tower, joint and peer variants
+// ------------------------------------------------------------------------------------------
+constexpr int SEG_CHUNK = 64;
+constexpr int SEG_MAX_WIDTH = 256;            // floats per destination row slice the partial scratch is sized for
+
+// Is sorted position p the first position of a chunk of its run?  `start` = first position of the run.
+__device__ __forceinline__ bool seg_chunk_head(const unsigned long long* __restrict__ keys, long long p, unsigned long long key,
+                                               long long& start) {
+    if (p == 0 || keys[p - 1] != key) { start = p; return true; }
+    if (p < SEG_CHUNK || keys[p - SEG_CHUNK] != key) return false;      // less than a chunk into its run
+    long long lo = 0, hi = p - SEG_CHUNK;                                // keys[hi] == key: lower bound of key
+    while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        if (keys[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    start = lo;
+    return ((p - start) % SEG_CHUNK) == 0;
+}
+// Partial slot of the chunk at position p of a run starting at `start`.  A window of SEG_CHUNK positions holds at most
+// two heads of multi-chunk runs: one of a run that began before the window, one of a run that begins inside it.
+__device__ __forceinline__ long long seg_slot(long long p, long long start) {
+    const long long w = p / SEG_CHUNK;
+    return 2 * w + (start >= w * SEG_CHUNK ? 1 : 0);
+}
+
+// level 1: thread (p, q) sums slice q of the chunk that starts at p
+template <int VEC, class Acc>
+__global__ void seg_reduce_chunks(const unsigned long long* __restrict__ keys, const int* __restrict__ vals, long long n, Acc acc,
+                                  float* __restrict__ part, int* __restrict__ any_long) {
+    const int W = acc.slices();
+    const long long total = n * W;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long p = i / W;
+        const int q = (int)(i - p * W);
+        const unsigned long long key = keys[p];
+        long long start;
+        if (!seg_chunk_head(keys, p, key, start)) continue;
+        const long long end = min(n, p + SEG_CHUNK);
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (long long s = p; s < end && keys[s] == key; ++s) {
+            const float* src = acc.src(key, vals[s], q);
+            if (VEC == 4) {
+                const float4 g = *reinterpret_cast<const float4*>(src);
+                a.x += g.x; a.y += g.y; a.z += g.z; a.w += g.w;
+            } else {
+                a.x += *src;
+            }
+        }
+        const bool single = start == p && (p + SEG_CHUNK >= n || keys[p + SEG_CHUNK] != key);
+        float* dst = single ? acc.dst(key, q) : part + (seg_slot(p, start) * W + q) * VEC;
+        if (VEC == 4) *reinterpret_cast<float4*>(dst) = a;
+        else *dst = a.x;
+        if (!single && start == p && q == 0) *any_long = 1;
+    }
+}
+// level 2: thread (p, q), p the first position of a multi-chunk run, adds the run's chunk partials in chunk order
+template <int VEC, class Acc>
+__global__ void seg_reduce_long_runs(const unsigned long long* __restrict__ keys, long long n, Acc acc,
+                                     const float* __restrict__ part, const int* __restrict__ any_long) {
+    if (*any_long == 0) return;
+    const int W = acc.slices();
+    const long long total = n * W;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long p = i / W;
+        const int q = (int)(i - p * W);
+        const unsigned long long key = keys[p];
+        if (p > 0 && keys[p - 1] == key) continue;
+        if (p + SEG_CHUNK >= n || keys[p + SEG_CHUNK] != key) continue;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (long long c = p; c < n && keys[c] == key; c += SEG_CHUNK) {
+            const float* src = part + (seg_slot(c, p) * W + q) * VEC;
+            if (VEC == 4) {
+                const float4 g = *reinterpret_cast<const float4*>(src);
+                a.x += g.x; a.y += g.y; a.z += g.z; a.w += g.w;
+            } else {
+                a.x += *src;
+            }
+        }
+        float* dst = acc.dst(key, q);
+        if (VEC == 4) *reinterpret_cast<float4*>(dst) = a;
+        else *dst = a.x;
+    }
+}
+
+// sources / destinations of the dense case: rows of dx [*, n_tab * E], tables t0 .. of `tp`
+template <int VEC>
+struct DenseAcc {
+    const float* dx;
+    TablePtrs tp;
+    int KE, E, idx_bits, t0;
+    __device__ int slices() const { return E / VEC; }
+    __device__ const float* src(unsigned long long key, int val, int q) const {
+        return dx + (size_t)val * KE + ((int)(key >> idx_bits) - t0) * E + q * VEC;
+    }
+    __device__ float* dst(unsigned long long key, int q) const {
+        return tp.p[(int)(key >> idx_bits) - t0] + (size_t)(key & ((1ull << idx_bits) - 1)) * E + q * VEC;
+    }
+};
+
+// scratch behind cub's temporary storage: chunk partials + the "some run is long" flag
+static size_t cub_sort_bytes(long long n) {
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const unsigned long long*)nullptr, (unsigned long long*)nullptr,
+                                    (const int*)nullptr, (int*)nullptr, (int)n, 0, 64, (cudaStream_t)0);
+    return (bytes + 255) & ~(size_t)255;
+}
+static size_t seg_part_bytes(long long n) { return (size_t)(n / SEG_CHUNK + 2) * 2 * SEG_MAX_WIDTH * sizeof(float); }
+struct SegScratch { float* part; int* flag; size_t cub_bytes; };
+static int seg_scratch(void* sort_tmp, int64_t sort_tmp_bytes, long long n, SegScratch* out) {
+    const size_t cb = cub_sort_bytes(n), pb = seg_part_bytes(n);
+    CFM_REQUIRE((size_t)sort_tmp_bytes >= cb + pb + 256, CFM_ERR_INVALID,
+                "sort scratch of %lld bytes is too small (cfm_emb_grad_tmp_bytes gives the size)", (long long)sort_tmp_bytes);
+    out->cub_bytes = cb;
+    out->part = reinterpret_cast<float*>(static_cast<char*>(sort_tmp) + cb);
+    out->flag = reinterpret_cast<int*>(static_cast<char*>(sort_tmp) + cb + pb);
+    return CFM_OK;
+}
+template <int VEC, class Acc>
+static int seg_reduce_launch(const unsigned long long* keys, const int* vals, long long n, const Acc& acc, int width,
+                             const SegScratch& sc, cudaStream_t stream) {
+    CFM_REQUIRE(width <= SEG_MAX_WIDTH, CFM_ERR_UNSUPPORTED, "embedding slices wider than %d floats are not supported", SEG_MAX_WIDTH);
+    CFM_CHECK_CUDA(cudaMemsetAsync(sc.flag, 0, sizeof(int), stream));
+    const long long total = n * (width / VEC);
+    const int grid = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+    seg_reduce_chunks<VEC, Acc><<<grid, 256, 0, stream>>>(keys, vals, n, acc, sc.part, sc.flag);
+    CFM_LAUNCH_CHECK();
+    seg_reduce_long_runs<VEC, Acc><<<grid, 256, 0, stream>>>(keys, n, acc, sc.part, sc.flag);
+    CFM_LAUNCH_CHECK();
+    return CFM_OK;
+}
 
 __global__ void emb_make_keys(const long long* __restrict__ x_cat, long long B, int n_tab, int idx_bits,
                               unsigned long long* __restrict__ keys, int* __restrict__ vals, TablePtrs tp) {
@@ -25,50 +161,6 @@ __global__ void emb_make_keys(const long long* __restrict__ x_cat, long long B, 
         if (idx < 0 || idx >= tp.rows[t]) idx = 0;   // forward already flagged the error
         keys[(long long)t * B + r] = ((unsigned long long)t << idx_bits) | (unsigned long long)idx;
         vals[(long long)t * B + r] = (int)r;
-    }
-}
-
-// thread (p, q): if sorted position p starts a run, sum float4 slice q of every row in the run
-__global__ void emb_segment_reduce(const unsigned long long* __restrict__ keys, const int* __restrict__ vals,
-                                   long long n, int n_tab, int E, int idx_bits, const float* __restrict__ dx,
-                                   TablePtrs tp) {
-    const int E4 = E >> 2;
-    const long long total = n * E4;
-    const int KE = n_tab * E;
-    const unsigned long long mask = (1ull << idx_bits) - 1;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        long long p = i / E4;
-        int q = (int)(i - p * E4);
-        unsigned long long key = keys[p];
-        if (p > 0 && keys[p - 1] == key) continue;
-        int t = (int)(key >> idx_bits);
-        long long idx = (long long)(key & mask);
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (long long s = p; s < n && keys[s] == key; ++s) {
-            const float4 g = __ldg(reinterpret_cast<const float4*>(dx + (size_t)vals[s] * KE + t * E) + q);
-            acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
-        }
-        reinterpret_cast<float4*>(tp.p[t] + (size_t)idx * E)[q] = acc;
-    }
-}
-
-// scalar variant for E % 4 != 0
-__global__ void emb_segment_reduce_scalar(const unsigned long long* __restrict__ keys, const int* __restrict__ vals,
-                                          long long n, int n_tab, int E, int idx_bits, const float* __restrict__ dx,
-                                          TablePtrs tp) {
-    const long long total = n * E;
-    const int KE = n_tab * E;
-    const unsigned long long mask = (1ull << idx_bits) - 1;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        long long p = i / E;
-        int e = (int)(i - p * E);
-        unsigned long long key = keys[p];
-        if (p > 0 && keys[p - 1] == key) continue;
-        int t = (int)(key >> idx_bits);
-        long long idx = (long long)(key & mask);
-        float acc = 0.f;
-        for (long long s = p; s < n && keys[s] == key; ++s) acc += dx[(size_t)vals[s] * KE + t * E + e];
-        tp.p[t][(size_t)idx * E + e] = acc;
     }
 }
 
@@ -109,10 +201,8 @@ static int fill_tables(TablePtrs& tp, float* const* grad_tables, const int64_t* 
 using namespace cfm;
 
 extern "C" int64_t cfm_emb_grad_tmp_bytes(int64_t n_tables, int64_t B) {
-    size_t bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const unsigned long long*)nullptr, (unsigned long long*)nullptr,
-                                    (const int*)nullptr, (int*)nullptr, (int)(n_tables * B), 0, 64, (cudaStream_t)0);
-    return (int64_t)bytes + 256;
+    const long long n = n_tables * B;
+    return (int64_t)(cub_sort_bytes(n) + seg_part_bytes(n) + 256);
 }
 
 extern "C" int cfm_emb_grad_segment_reduce(const int64_t* x_cat, const float* dx_emb, int64_t B, int64_t n_tables,
@@ -134,21 +224,20 @@ extern "C" int cfm_emb_grad_segment_reduce(const int64_t* x_cat, const float* dx
     emb_make_keys<<<grid, 256, 0, stream>>>((const long long*)x_cat, B, (int)n_tables, idx_bits,
                                             (unsigned long long*)keys_tmp, vals_tmp, tp);
     CFM_LAUNCH_CHECK();
-    size_t bytes = (size_t)sort_tmp_bytes;
+    SegScratch sc;
+    rc = seg_scratch(sort_tmp, sort_tmp_bytes, n, &sc);
+    if (rc) return rc;
+    size_t bytes = sc.cub_bytes;
     CFM_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(sort_tmp, bytes, (const unsigned long long*)keys_tmp,
                                                    (unsigned long long*)keys_sorted, (const int*)vals_tmp,
                                                    vals_sorted, (int)n, 0, key_bits, stream));
+    const unsigned long long* ks = (const unsigned long long*)keys_sorted;
     if ((emb_dim & 3) == 0) {
-        const long long total = n * (emb_dim / 4);
-        emb_segment_reduce<<<(int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, stream>>>(
-            (const unsigned long long*)keys_sorted, vals_sorted, n, (int)n_tables, (int)emb_dim, idx_bits, dx_emb, tp);
-    } else {
-        const long long total = n * emb_dim;
-        emb_segment_reduce_scalar<<<(int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, stream>>>(
-            (const unsigned long long*)keys_sorted, vals_sorted, n, (int)n_tables, (int)emb_dim, idx_bits, dx_emb, tp);
+        DenseAcc<4> acc{dx_emb, tp, (int)(n_tables * emb_dim), (int)emb_dim, idx_bits, 0};
+        return seg_reduce_launch<4>(ks, vals_sorted, n, acc, (int)emb_dim, sc, stream);
     }
-    CFM_LAUNCH_CHECK();
-    return CFM_OK;
+    DenseAcc<1> acc{dx_emb, tp, (int)(n_tables * emb_dim), (int)emb_dim, idx_bits, 0};
+    return seg_reduce_launch<1>(ks, vals_sorted, n, acc, (int)emb_dim, sc, stream);
 }
 
 extern "C" int cfm_emb_grad_rezero(float* const* grad_tables, const int64_t* table_rows, int64_t n_tables,
@@ -252,39 +341,25 @@ __global__ void emb_make_keys_peer(PeerPlan pp, int n_owned, int W, long long B,
     }
 }
 
+// sources / destinations of the owner-side reduce: item value = rank * B + row, gradient rows read in place from the
+// rank's (peer-mapped) buffer, destination = columns [col0, col0 + w) of the owned table
 template <int VEC>
-__global__ void emb_segment_reduce_peer(const unsigned long long* __restrict__ keys, const int* __restrict__ vals,
-                                        long long n, long long B, int E, int w, int idx_bits, PeerPlan pp,
-                                        TablePtrs tp) {   // keys/vals already offset to the group's range
-    const int WV = w / VEC;
-    const long long total = n * WV;
-    const unsigned long long mask = (1ull << idx_bits) - 1;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long p = i / WV;
-        const int q = (int)(i - p * WV);
-        const unsigned long long key = keys[p];
-        if (p > 0 && keys[p - 1] == key) continue;
+struct PeerAcc {
+    PeerPlan pp;
+    TablePtrs tp;
+    int B, E, w, idx_bits;
+    __device__ int slices() const { return w / VEC; }
+    __device__ const float* src(unsigned long long key, int val, int q) const {
         const int j = (int)(key >> idx_bits);
-        const long long idx = (long long)(key & mask);
-        const int ld = pp.n_cols[j] * E, off = pp.col[j] * E + pp.col0[j] + q * VEC;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (long long s = p; s < n && keys[s] == key; ++s) {
-            const int v = vals[s];
-            const int r = v / (int)B;                              // n_owned * n_peers * B < 2^31, so B fits an int
-            const long long b = v - r * (int)B;
-            const float* src = pp.dx[j][r] + (size_t)b * ld + off;
-            if (VEC == 4) {
-                const float4 g = *reinterpret_cast<const float4*>(src);
-                acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
-            } else {
-                acc.x += *src;
-            }
-        }
-        float* dst = tp.p[j] + (size_t)idx * E + pp.col0[j] + q * VEC;
-        if (VEC == 4) *reinterpret_cast<float4*>(dst) = acc;
-        else *dst = acc.x;
+        const int r = val / B;                                  // n_owned * n_peers * B < 2^31, so B fits an int
+        const long long b = val - r * B;
+        return pp.dx[j][r] + (size_t)b * (pp.n_cols[j] * E) + pp.col[j] * E + pp.col0[j] + q * VEC;
     }
-}
+    __device__ float* dst(unsigned long long key, int q) const {
+        const int j = (int)(key >> idx_bits);
+        return tp.p[j] + (size_t)(key & ((1ull << idx_bits) - 1)) * E + pp.col0[j] + q * VEC;
+    }
+};
 
 // zero columns [col0, col0 + w) of every row a sorted key names
 template <int VEC>
@@ -401,11 +476,14 @@ extern "C" int cfm_emb_grad_peer_reduce(const cfm_peer_group_t* groups, int64_t 
     CFM_REQUIRE(B >= 1 && (long long)n_owned * n_peers * B < (1ll << 31), CFM_ERR_INVALID, "bad sizes");
     const long long n = (long long)n_owned * n_peers * B;
     ProfScope prof(PROF_EMB, stream);
+    SegScratch sc;
+    rc = seg_scratch(sort_tmp, sort_tmp_bytes, n, &sc);
+    if (rc) return rc;
     if (phase != 2) {
         emb_make_keys_peer<<<(int)std::min<long long>((n + 255) / 256, 148 * 8), 256, 0, stream>>>(
             pp, n_owned, (int)n_peers, B, idx_bits, tp, (unsigned long long*)keys_tmp, vals_tmp);
         CFM_LAUNCH_CHECK();
-        size_t bytes = (size_t)sort_tmp_bytes;
+        size_t bytes = sc.cub_bytes;
         CFM_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(sort_tmp, bytes, (const unsigned long long*)keys_tmp,
                                                        (unsigned long long*)keys_sorted, (const int*)vals_tmp,
                                                        vals_sorted, (int)n, 0, key_bits, stream));
@@ -417,15 +495,13 @@ extern "C" int cfm_emb_grad_peer_reduce(const cfm_peer_group_t* groups, int64_t 
         const long long ng = G.n_owned * n_peers * B;
         const unsigned long long* ks = (const unsigned long long*)keys_sorted + off;
         if ((G.width & 3) == 0 && (G.emb_dim & 3) == 0) {
-            const long long total = ng * (G.width / 4);
-            emb_segment_reduce_peer<4><<<(int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, stream>>>(
-                ks, vals_sorted + off, ng, B, (int)G.emb_dim, (int)G.width, idx_bits, pp, tp);
+            PeerAcc<4> acc{pp, tp, (int)B, (int)G.emb_dim, (int)G.width, idx_bits};
+            rc = seg_reduce_launch<4>(ks, vals_sorted + off, ng, acc, (int)G.width, sc, stream);
         } else {
-            const long long total = ng * G.width;
-            emb_segment_reduce_peer<1><<<(int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, stream>>>(
-                ks, vals_sorted + off, ng, B, (int)G.emb_dim, (int)G.width, idx_bits, pp, tp);
+            PeerAcc<1> acc{pp, tp, (int)B, (int)G.emb_dim, (int)G.width, idx_bits};
+            rc = seg_reduce_launch<1>(ks, vals_sorted + off, ng, acc, (int)G.width, sc, stream);
         }
-        CFM_LAUNCH_CHECK();
+        if (rc) return rc;
         off += ng;
     }
     return CFM_OK;
@@ -537,38 +613,6 @@ __global__ void emb_make_keys_joint(JointKeys jk, long long B, int idx_bits, uns
     }
 }
 
-// thread (p, q): if sorted position p starts a run, sum float4 slice q of every row in the run (t0: first table id)
-template <int VEC>
-__global__ void emb_segment_reduce_range(const unsigned long long* __restrict__ keys, const int* __restrict__ vals,
-                                         long long n, int n_tab, int E, int idx_bits, int t0,
-                                         const float* __restrict__ dx, TablePtrs tp) {
-    const int EV = E / VEC;
-    const long long total = n * EV;
-    const int KE = n_tab * E;
-    const unsigned long long mask = (1ull << idx_bits) - 1;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long p = i / EV;
-        const int q = (int)(i - p * EV);
-        const unsigned long long key = keys[p];
-        if (p > 0 && keys[p - 1] == key) continue;
-        const int t = (int)(key >> idx_bits) - t0;
-        const long long idx = (long long)(key & mask);
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (long long s = p; s < n && keys[s] == key; ++s) {
-            const float* src = dx + (size_t)vals[s] * KE + t * E + q * VEC;
-            if (VEC == 4) {
-                const float4 g = __ldg(reinterpret_cast<const float4*>(src));
-                acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
-            } else {
-                acc.x += __ldg(src);
-            }
-        }
-        float* dst = tp.p[t] + (size_t)idx * E + q * VEC;
-        if (VEC == 4) *reinterpret_cast<float4*>(dst) = acc;
-        else *dst = acc.x;
-    }
-}
-
 template <int VEC>
 __global__ void emb_rezero_range(const unsigned long long* __restrict__ keys, long long n, int E, int idx_bits, int t0,
                                  TablePtrs tp) {
@@ -636,11 +680,14 @@ extern "C" int cfm_emb_grad_joint_reduce(const cfm_emb_group_t* groups, int64_t 
     CFM_REQUIRE(B >= 1 && tt * B < (1ll << 31), CFM_ERR_INVALID, "bad sizes");
     const long long n = tt * B;
     ProfScope prof(PROF_EMB, stream);
+    SegScratch sc;
+    rc = seg_scratch(sort_tmp, sort_tmp_bytes, n, &sc);
+    if (rc) return rc;
     if (phase != 2) {
         emb_make_keys_joint<<<(int)std::min<long long>((n + 255) / 256, 148 * 8), 256, 0, stream>>>(
             jk, B, idx_bits, (unsigned long long*)keys_tmp, vals_tmp);
         CFM_LAUNCH_CHECK();
-        size_t bytes = (size_t)sort_tmp_bytes;
+        size_t bytes = sc.cub_bytes;
         CFM_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(sort_tmp, bytes, (const unsigned long long*)keys_tmp,
                                                        (unsigned long long*)keys_sorted, (const int*)vals_tmp,
                                                        vals_sorted, (int)n, 0, key_bits, stream));
@@ -651,15 +698,13 @@ extern "C" int cfm_emb_grad_joint_reduce(const cfm_emb_group_t* groups, int64_t 
         const long long off = (long long)jk.t0[g] * B, ng = G.n_tables * B;
         const unsigned long long* ks = (const unsigned long long*)keys_sorted + off;
         if ((G.emb_dim & 3) == 0) {
-            const long long total = ng * (G.emb_dim / 4);
-            emb_segment_reduce_range<4><<<(int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, stream>>>(
-                ks, vals_sorted + off, ng, (int)G.n_tables, (int)G.emb_dim, idx_bits, jk.t0[g], G.dx_emb, tps[g]);
+            DenseAcc<4> acc{G.dx_emb, tps[g], (int)(G.n_tables * G.emb_dim), (int)G.emb_dim, idx_bits, jk.t0[g]};
+            rc = seg_reduce_launch<4>(ks, vals_sorted + off, ng, acc, (int)G.emb_dim, sc, stream);
         } else {
-            const long long total = ng * G.emb_dim;
-            emb_segment_reduce_range<1><<<(int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, stream>>>(
-                ks, vals_sorted + off, ng, (int)G.n_tables, (int)G.emb_dim, idx_bits, jk.t0[g], G.dx_emb, tps[g]);
+            DenseAcc<1> acc{G.dx_emb, tps[g], (int)(G.n_tables * G.emb_dim), (int)G.emb_dim, idx_bits, jk.t0[g]};
+            rc = seg_reduce_launch<1>(ks, vals_sorted + off, ng, acc, (int)G.emb_dim, sc, stream);
         }
-        CFM_LAUNCH_CHECK();
+        if (rc) return rc;
     }
     return CFM_OK;
 }
