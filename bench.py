@@ -309,6 +309,209 @@ def secondary_metrics(device, world, rank, dist):
     return out
 
 
+def _zipf_indices(n, rows, s_exp, device, gen):
+    """Zipf(s) over [0, rows) by inverse-CDF sampling (rank r has weight (r + 1)^-s), SURVEY 8(d) config 4(b)."""
+    w = torch.arange(1, rows + 1, dtype=torch.float64, device=device).pow(-s_exp)
+    cdf = torch.cumsum(w, 0)
+    u = torch.rand(n, dtype=torch.float64, device=device, generator=gen) * cdf[-1]
+    return torch.searchsorted(cdf, u).clamp_(max=rows - 1)
+
+
+def _graph_ms(model, batches, steps, stream=None):
+    """ms per step of the graph-captured train step (fwd + loss + bwd) over `batches`."""
+    from ceo_firm_matching.training import GraphedTwoTowerStep
+    runner = GraphedTwoTowerStep(model, batches[0], optimizer=None, warmup=3, stream=stream)
+    for i in range(3):
+        runner.step(batches[i % len(batches)])
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for i in range(steps):
+        runner.step(batches[i % len(batches)])
+    t1.record()
+    torch.cuda.synchronize()
+    return t0.elapsed_time(t1) / steps, runner
+
+
+def index_distribution_legs(device, batches, steps, uniform_ms):
+    """Config 4 under the other index distributions SURVEY 8(d) names: Zipf(1.05) over the 1M-row tables, and the
+    reference's real cardinalities (2-4 classes per table, data.py:120-126) at the same batch size: both stress the
+    embedding-gradient reduce with long runs of equal keys."""
+    from ceo_firm_matching import CEOFirmMatcher, Config
+    out = {}
+    g = torch.Generator(device=device).manual_seed(77)
+    B = B_PER_GPU
+    zb = []
+    for b in batches[:4]:
+        f_cat = torch.stack([_zipf_indices(B, TABLE_ROWS, 1.05, device, g) for _ in range(4)], 1)
+        c_cat = torch.stack([_zipf_indices(B, TABLE_ROWS, 1.05, device, g) for _ in range(7)], 1)
+        zb.append((b[0], f_cat, b[2], c_cat, b[4], b[5]))
+    model = build_model(device, "fp32")
+    ms, runner = _graph_ms(model, zb, steps)
+    out["config4_zipf"] = {"workload": "config4 with Zipf(s=1.05) categorical indices over the 1M-row tables",
+                           "ms_per_step": ms, "value": B / (ms * 1e-3), "unit": "pairs/s",
+                           "vs_uniform_indices": ms / uniform_ms}
+    del runner, model
+    torch.cuda.empty_cache()
+    f_cards, c_cards = [4, 4, 2, 2], [2, 4, 2, 2, 2, 2, 2]
+    torch.manual_seed(0)
+    meta = {"n_firm_numeric": 12, "firm_cat_counts": f_cards, "n_ceo_numeric": 2, "ceo_cat_counts": c_cards}
+    model = CEOFirmMatcher(meta, Config()).to(device).train()
+    model.use_persistent_table_grads(True)
+    rb = []
+    for b in batches[:4]:
+        f_cat = torch.stack([torch.randint(0, n, (B,), device=device, generator=g) for n in f_cards], 1)
+        c_cat = torch.stack([torch.randint(0, n, (B,), device=device, generator=g) for n in c_cards], 1)
+        rb.append((b[0], f_cat, b[2], c_cat, b[4], b[5]))
+    ms, runner = _graph_ms(model, rb, steps)
+    out["config4_reference_cardinalities"] = {
+        "workload": "config4 batch shape with the reference's table sizes [4,4,2,2] / [2,4,2,2,2,2,2] (runs of 16k-32k equal keys)",
+        "ms_per_step": ms, "value": B / (ms * 1e-3), "unit": "pairs/s", "vs_uniform_indices": ms / uniform_ms}
+    del runner, model
+    torch.cuda.empty_cache()
+    return out
+
+
+def small_config_legs(device, with_cpu):
+    """BASELINE configs 1 and 2 (the reference's own CLI runs): device time of one train step and wall-clock of the
+    whole training loop, beside a CPU loop of the same structure (the product's CPU data pipeline, which is the
+    reference's, + the oracle's torch-CPU step + torch.optim.Adam) on the host cores."""
+    import contextlib
+    import io
+    from sklearn.model_selection import train_test_split
+    from torch.utils.data import DataLoader
+    import oracle
+    from ceo_firm_matching import Config, StructuralConfig
+    from ceo_firm_matching.data import CEOFirmDataset, DataProcessor
+    from ceo_firm_matching.synthetic import generate_synthetic_data
+    from ceo_firm_matching.training import train_model, GraphedTwoTowerStep, BATCH_KEYS
+    from ceo_firm_matching.optim import FusedAdam
+    from ceo_firm_matching import CEOFirmMatcher
+    out = {}
+    quiet = contextlib.redirect_stdout(io.StringIO())
+    # ---------------- config 1: python -m ceo_firm_matching.cli --synthetic (cli.py:29-59) ----------------
+    cfg = Config()
+    proc = DataProcessor(cfg)
+    with quiet:
+        df = proc.prepare_features(generate_synthetic_data(1000))
+    train_df, val_df = train_test_split(df, test_size=0.2, random_state=42)
+    with quiet:
+        proc.fit(train_df)
+        train_data, val_data = proc.transform(train_df), proc.transform(val_df)
+    train_loader = DataLoader(CEOFirmDataset(train_data), batch_size=256, shuffle=True)
+    val_loader = DataLoader(CEOFirmDataset(val_data), batch_size=256, shuffle=False)
+    with quiet:
+        train_model(train_loader, val_loader, train_data, cfg)              # warm-up: library load, allocator, graphs
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    with quiet:
+        model = train_model(train_loader, val_loader, train_data, cfg)
+    torch.cuda.synchronize()
+    loop_s = time.perf_counter() - t0
+    # one step (fwd + loss + bwd + Adam) at B = 256 as a graph replay
+    batch = [train_data[k][:256].to(device) for k in BATCH_KEYS]
+    model.train()
+    model.use_persistent_table_grads(True)
+    opt = FusedAdam(model.parameters(), lr=cfg.LEARNING_RATE)
+    st = torch.cuda.Stream(device)
+    with torch.cuda.stream(st):
+        from ceo_firm_matching.training import eager_step
+        eager_step(model, opt, batch)
+        torch.cuda.synchronize()
+    runner = GraphedTwoTowerStep(model, batch, optimizer=opt, warmup=1, stream=st)
+    for _ in range(5):
+        runner.step(batch)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(200):
+        runner.step(batch)
+    e1.record()
+    torch.cuda.synchronize()
+    step_us = e0.elapsed_time(e1) / 200 * 1e3
+    steps_per_loop = cfg.EPOCHS * len(train_loader)
+    out["config1_cli_synthetic"] = {
+        "workload": "config1: cli --synthetic (800 train rows, batch 256, %d epochs, Adam), tables of 2-4 classes" % cfg.EPOCHS,
+        "step_us": step_us, "value": 256 / (step_us * 1e-6), "unit": "pairs/s",
+        "train_loop_seconds": loop_s, "train_loop_pairs_per_sec": cfg.EPOCHS * len(train_df) / loop_s,
+        "steps_per_loop": steps_per_loop}
+    del runner
+    if with_cpu:
+        torch.set_num_threads(os.cpu_count())
+        p = oracle.init_two_tower_params(train_data["n_firm_numeric"], train_data["firm_cat_counts"],
+                                         train_data["n_ceo_numeric"], train_data["ceo_cat_counts"], seed=0)
+        names = [k for k, v in p.items() if v.is_floating_point() and "running" not in k]
+        for k in names:
+            p[k].requires_grad_(True)
+        copt = torch.optim.Adam([p[k] for k in names], lr=cfg.LEARNING_RATE)
+        t0 = time.perf_counter()
+        n_steps = 0
+        for epoch in range(cfg.EPOCHS):
+            for b in train_loader:                                   # the reference's per-sample Dataset + collate path
+                copt.zero_grad()
+                preds = oracle.two_tower_forward(p, b["firm_numeric"], b["firm_cat"], b["ceo_numeric"], b["ceo_cat"],
+                                                 training=True)
+                oracle.weighted_mse(preds, b["target"], b["weights"]).backward()
+                copt.step()
+                n_steps += 1
+        cpu_s = time.perf_counter() - t0
+        out["config1_cli_synthetic"]["cpu_loop"] = {
+            "train_loop_seconds": cpu_s, "step_us": cpu_s / n_steps * 1e6, "cores": os.cpu_count(), "kind": "port",
+            "sample": "the whole loop: %d steps (DataLoader over CEOFirmDataset + oracle step + torch Adam, dropout off)" % n_steps}
+    # ---------------- config 2: structural_cli --synthetic --epochs 100 --batch-size 128 ----------------
+    from ceo_firm_matching.structural_data import StructuralDataProcessor
+    from ceo_firm_matching.structural_training import train_structural_model
+    scfg = StructuralConfig()
+    scfg.EPOCHS, scfg.BATCH_SIZE, scfg.DATA_PATH = 100, 128, "SYNTHETIC_MODE"
+    sproc = StructuralDataProcessor(scfg)
+    with quiet:
+        train_ds, val_ds, _ = sproc.load_and_prep()
+    s_train = DataLoader(train_ds, batch_size=128, shuffle=True, drop_last=True)
+    s_val = DataLoader(val_ds, batch_size=128, shuffle=False)
+    warm = StructuralConfig()
+    warm.EPOCHS, warm.BATCH_SIZE, warm.DATA_PATH = 2, 128, "SYNTHETIC_MODE"
+    with quiet:
+        train_structural_model(s_train, s_val, sproc.get_metadata(), warm)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    with quiet:
+        smodel = train_structural_model(s_train, s_val, sproc.get_metadata(), scfg)
+    torch.cuda.synchronize()
+    s_loop = time.perf_counter() - t0
+    n_train_steps = scfg.EPOCHS * len(s_train)
+    out["config2_structural_cli"] = {
+        "workload": "config2: structural_cli --synthetic --epochs 100 --batch-size 128 (1600 train / 400 val rows, KL distillation, Adam)",
+        "train_loop_seconds": s_loop, "train_steps": n_train_steps,
+        "step_us_incl_validation_share": s_loop / n_train_steps * 1e6,
+        "value": scfg.EPOCHS * len(train_ds) / s_loop, "unit": "train pairs/s (whole loop incl. the validation pass)"}
+    del smodel
+    if with_cpu:
+        meta = sproc.get_metadata()
+        ps = oracle.init_structural_params(meta["n_firm_num"], meta["firm_cat_cards"], meta["n_ceo_num"], meta["ceo_cat_cards"], seed=0)
+        names = [k for k, v in ps.items() if v.is_floating_point() and "running" not in k and k != "A"]
+        for k in names:
+            ps[k].requires_grad_(True)
+        copt = torch.optim.Adam([ps[k] for k in names], lr=scfg.LEARNING_RATE)
+        t0 = time.perf_counter()
+        n_steps = 0
+        for epoch in range(20):                                      # 20 of the 100 epochs: bounded sample
+            for b in s_train:
+                copt.zero_grad()
+                cl, fl, _ = oracle.structural_forward(ps, b["firm_num"], b["firm_cat"], b["ceo_num"], b["ceo_cat"], training=True)
+                oracle.structural_kl_loss(cl, fl, b["target_ceo"], b["target_firm"]).backward()
+                copt.step()
+                n_steps += 1
+            with torch.no_grad():
+                for b in s_val:
+                    cl, fl, _ = oracle.structural_forward(ps, b["firm_num"], b["firm_cat"], b["ceo_num"], b["ceo_cat"], training=False)
+                    oracle.structural_kl_loss(cl, fl, b["target_ceo"], b["target_firm"])
+        cpu_s = (time.perf_counter() - t0) * (scfg.EPOCHS / 20)
+        out["config2_structural_cli"]["cpu_loop"] = {
+            "train_loop_seconds": cpu_s, "cores": os.cpu_count(), "kind": "port",
+            "sample": "20 of the 100 epochs timed (DataLoader + oracle step + torch Adam + validation pass), scaled x5"}
+    return out
+
+
 def gpu_arm(args):
     from ceo_firm_matching import _native as N
     import ctypes as C
@@ -448,6 +651,9 @@ def gpu_arm(args):
     e2e_value = world * B_PER_GPU * args.steps / e2e_s
 
     secondary = secondary_metrics(device, world, rank, dist)
+    if world == 1 and not args.headline_only:
+        secondary.update(index_distribution_legs(device, batches, args.steps, ms_step))
+        secondary.update(small_config_legs(device, with_cpu=not args.no_cpu))
     if world == 1:
         # the same step in the other tower-product precision, also as one graph replay per step
         other = "tf32" if args.precision == "fp32" else "fp32"
@@ -511,19 +717,27 @@ def gpu_arm(args):
 
     # ---- roofline of the dominant kernel (stage-1 backward: dW1 + dX + embedding-row gradients) ----
     peak, peak_src = peaks()
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")) as f:
+            ncu_traffic = json.load(f)
+    except Exception:
+        ncu_traffic = {}
     slots = ["fwd1", "fwd2", "fwd3", "bwd1", "bwd2", "bwd3", "head", "emb_grad", "reduce", "nce_rowsum", "nce_grad",
              "topk", "topk_post", "adam"]
     per_kernel = {s: (prof_ms[i] / prof_n[i] if prof_n[i] else None) for i, s in enumerate(slots)}
     shares = {s: round(prof_ms[i] / n_prof / ms_step, 4) for i, s in enumerate(slots) if prof_n[i]}
-    dom = max((s for s in slots if per_kernel[s]), key=lambda s: prof_ms[slots.index(s)])
+    # dominant kernel = the tower stage kernel with the largest share (the embedding-gradient and reduction slots sum
+    # several small launches, some of them on the library's side stream)
+    dom = max((s for s in slots[:6] if per_kernel[s]), key=lambda s: prof_ms[slots.index(s)])
     dom_bytes = {"bwd1": BYTES_BWD1_PER_PAIR, "fwd1": 1148}.get(dom, BYTES_BWD1_PER_PAIR) * B_PER_GPU
     achieved = dom_bytes / (per_kernel[dom] * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, per launch, from the committed
-                # `ncu --set full` capture at this exact shape (profiles/r01_ncu_full_summary.md)
-                "traffic": {"bwd1": 263.0e6, "fwd1": 141.8e6}.get(dom), "traffic_unit": "bytes per launch",
+                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, per launch, read from the summary of this
+                # round's `ncu --set full` capture at this exact shape (written by scratch/ncu_traffic.py)
+                "traffic": ncu_traffic.get(dom), "traffic_unit": "bytes per launch",
+                "traffic_source": ncu_traffic.get("source"),
                 "algorithmic_bytes_per_launch": dom_bytes,
-                "kernel": "tower_%s_stage" % ("bwd" if dom.startswith("bwd") else "fwd"),
+                "kernel": "tower_%s_tc (tcgen05 kind::tf32, TMEM accumulators)" % ("bwd" if dom.startswith("bwd") else "fwd"),
                 "slot": dom, "peak_source": peak_src, "kernel_ms": per_kernel[dom], "kernel_share_of_step": shares,
                 "whole_step_frac": BYTES_PER_PAIR * B_PER_GPU / (ms_step * 1e-3) / 1e9 / peak,
                 "kernel_sum_ms_per_step": prof_step_ms,
@@ -545,7 +759,7 @@ def gpu_arm(args):
                                    f"dp{world} towers + tables {args.tables}" +
                                    (" over NVLink peer memory" if args.tables == "sharded" else " (all-gather)")),
                    "l2": f"{n_data} distinct 10 MB batches cycled + 992 MB tables (inputs >> 126 MB L2)",
-                   "arithmetic": ("tower products as error-compensated 3xTF32 tensor-core MMAs (fp32-class: parity "
+                   "arithmetic": ("tower products as error-compensated 3xTF32 tcgen05 MMAs (fp32-class: parity "
                                   "rtol 2e-5 vs the oracle), everything else fp32" if args.precision == "fp32" else
                                   "tower products single-pass TF32 (fp32 accumulate), everything else fp32"),
                    "optimizer_step": "excluded from the metric (SURVEY 8d)", "dropout": 0.1,
@@ -580,10 +794,12 @@ def _finish(dist, runner):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (debugging)")
+    ap.add_argument("--headline-only", action="store_true",
+                    help="skip the index-distribution and config 1/2 secondary legs (profiling runs)")
     ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32"],
                     help="tower products: fp32-class (3xTF32, the reference's precision; default) or single-pass TF32")
     ap.add_argument("--tables", default="sharded", choices=["sharded", "replicated"],

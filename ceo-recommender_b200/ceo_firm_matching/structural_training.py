@@ -23,6 +23,45 @@ def _loss(model: StructuralDistillationNet, batch) -> torch.Tensor:
     return model.distillation_loss(c_logits, f_logits, t_ceo, t_firm)
 
 
+class GraphedStructuralStep:
+    """One distillation step (zero-grad, towers, KL head, backward, Adam) for a fixed batch size, captured into a CUDA
+    graph: at the shipped batch size (128, ``structural_cli.py:87-97``) the ~40 launches of a step are pure launch
+    latency, so a replay is several times faster than re-issuing them.  Dropout masks differ per replay (device-side
+    Philox offset counter advanced by a graph node), exactly as in ``training.GraphedTwoTowerStep``."""
+
+    def __init__(self, model: StructuralDistillationNet, optimizer, example, stream: torch.cuda.Stream):
+        dev = example[0].device
+        self.model, self.optimizer, self.stream = model, optimizer, stream
+        self.static = [torch.empty(t.shape, dtype=t.dtype, device=dev) for t in example]
+        for s, t in zip(self.static, example):
+            s.copy_(t)
+        self.counter = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.graph = torch.cuda.CUDAGraph()
+        ops.set_graph_rng_counter(self.counter)
+        # No eager warm-up here: it would be an extra optimiser step.  The caller has already run one eager step of
+        # this batch size (optimiser state, scratch buffers and kernel attributes exist), as train_model does.
+        try:
+            torch.cuda.synchronize(dev)
+            with torch.cuda.graph(self.graph, stream=stream):
+                self.loss = self._body()
+        finally:
+            ops.set_graph_rng_counter(None)
+
+    def _body(self) -> torch.Tensor:
+        ops.advance_graph_rng_counter()
+        self.optimizer.zero_grad(set_to_none=True)
+        loss = _loss(self.model, self.static)
+        loss.backward()
+        self.optimizer.step()
+        return loss.detach()
+
+    def step(self, batch) -> torch.Tensor:
+        for s, t in zip(self.static, batch):
+            s.copy_(t, non_blocking=True)
+        self.graph.replay()
+        return self.loss
+
+
 def train_structural_model(train_loader: DataLoader, val_loader: DataLoader, metadata: dict,
                            config: StructuralConfig) -> Optional[StructuralDistillationNet]:
     device = torch.device(config.DEVICE)
@@ -41,17 +80,32 @@ def train_structural_model(train_loader: DataLoader, val_loader: DataLoader, met
     print(f"\nStarting Distillation Training for {config.EPOCHS} epochs...")
 
     best_val_loss = float("inf")
+    # One captured step per distinct train batch size (the first step of a size runs eagerly and leaves the optimiser
+    # state allocated; the loop runs on one side stream, see training.GraphedTwoTowerStep).
+    stream = torch.cuda.Stream(device)
+    stream.wait_stream(torch.cuda.current_stream(device))
+    graphed, seen = {}, {}
     for epoch in range(config.EPOCHS):
         model.train()
         train_loss = torch.zeros((), device=device)       # accumulated on the device: one sync per epoch
         n_train = 0
-        for batch in device_batches(train_loader, BATCH_KEYS, device):
-            optimizer.zero_grad(set_to_none=True)
-            loss = _loss(model, batch)
-            loss.backward()
-            optimizer.step()
-            train_loss += loss.detach()
-            n_train += 1
+        with torch.cuda.stream(stream):
+            for batch in device_batches(train_loader, BATCH_KEYS, device):
+                B = batch[0].shape[0]
+                seen[B] = seen.get(B, 0) + 1
+                if seen[B] == 1:
+                    optimizer.zero_grad(set_to_none=True)
+                    loss = _loss(model, batch)
+                    loss.backward()
+                    optimizer.step()
+                    loss = loss.detach()
+                else:
+                    if B not in graphed:
+                        graphed[B] = GraphedStructuralStep(model, optimizer, batch, stream)
+                    loss = graphed[B].step(batch)
+                train_loss += loss
+                n_train += 1
+        torch.cuda.current_stream(device).wait_stream(stream)
 
         model.eval()
         val_loss = torch.zeros((), device=device)

@@ -5,13 +5,14 @@
 // 2. stable LSD radix sort of (key, row) over the minimal number of key bits (cub)          (library sort)
 // 3. every run of equal keys is cut into chunks of SEG_CHUNK positions counted from the run's first position; one
 //    thread per (chunk, 16-byte slice) sums its chunk in position order; a run that fits one chunk is written
-//    straight to the dense gradient row, longer runs leave per-chunk partials that a second kernel adds in chunk
-//    order                                                                                       (2 kernels)
+//    straight to the dense gradient row, longer runs leave per-chunk partials that a second kernel adds in a fixed
+//    order (one warp per run: lane l takes chunks l, l + 32, ..., then a shuffle tree)            (2 kernels)
 // Equal keys keep increasing row order (stable sort) and the chunk grid hangs on the run itself, so the
 // floating-point sum order is fixed whatever the launch geometry - and a low-cardinality column (runs of tens of
 // thousands of rows: data.py:120-126 has tables of 2-4 classes) is reduced by hundreds of threads instead of one.
 #include "common.cuh"
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #include <algorithm>
 
 namespace cfm {
@@ -24,17 +25,17 @@ struct TablePtrs { float* p[CFM_MAX_TABLES]; long long rows[CFM_MAX_TABLES]; };
 constexpr int SEG_CHUNK = 64;
 constexpr int SEG_MAX_WIDTH = 256;            // floats per destination row slice the partial scratch is sized for
 
-// Is sorted position p the first position of a chunk of its run?  `start` = first position of the run.
-__device__ __forceinline__ bool seg_chunk_head(const unsigned long long* __restrict__ keys, long long p, unsigned long long key,
-                                               long long& start) {
+// starts[p] = first sorted position of the run p belongs to: run heads marked with their own position, then an inclusive
+// max-scan (cub).  Computed once per sort, beside it (it only needs the sorted keys).
+__global__ void seg_mark_heads(const unsigned long long* __restrict__ keys, long long n, int* __restrict__ starts) {
+    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x)
+        starts[p] = (p > 0 && keys[p - 1] == keys[p]) ? 0 : (int)p;
+}
+// Is position p (local to a range that begins at global position `base`) the first position of a chunk of its run?
+__device__ __forceinline__ bool seg_chunk_head(const unsigned long long* __restrict__ keys, const int* __restrict__ starts,
+                                               long long base, long long p, unsigned long long key, long long& start) {
     if (p == 0 || keys[p - 1] != key) { start = p; return true; }
-    if (p < SEG_CHUNK || keys[p - SEG_CHUNK] != key) return false;      // less than a chunk into its run
-    long long lo = 0, hi = p - SEG_CHUNK;                                // keys[hi] == key: lower bound of key
-    while (lo < hi) {
-        const long long mid = (lo + hi) >> 1;
-        if (keys[mid] < key) lo = mid + 1; else hi = mid;
-    }
-    start = lo;
+    start = (long long)starts[p] - base;
     return ((p - start) % SEG_CHUNK) == 0;
 }
 // Partial slot of the chunk at position p of a run starting at `start`.  A window of SEG_CHUNK positions holds at most
@@ -47,7 +48,8 @@ __device__ __forceinline__ long long seg_slot(long long p, long long start) {
 // level 1: thread (p, q) sums slice q of the chunk that starts at p
 template <int VEC, class Acc>
 __global__ void seg_reduce_chunks(const unsigned long long* __restrict__ keys, const int* __restrict__ vals, long long n, Acc acc,
-                                  float* __restrict__ part, int* __restrict__ any_long) {
+                                  float* __restrict__ part, int* __restrict__ any_long, const int* __restrict__ starts,
+                                  long long base) {
     const int W = acc.slices();
     const long long total = n * W;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -55,10 +57,38 @@ __global__ void seg_reduce_chunks(const unsigned long long* __restrict__ keys, c
         const int q = (int)(i - p * W);
         const unsigned long long key = keys[p];
         long long start;
-        if (!seg_chunk_head(keys, p, key, start)) continue;
-        const long long end = min(n, p + SEG_CHUNK);
+        if (!seg_chunk_head(keys, starts, base, p, key, start)) continue;
+        // end of the chunk: a full chunk unless the run stops inside it (then a 6-step bisection finds where), so the
+        // summation loop below carries no key test and its loads are independent of one another
+        long long end = min(n, p + SEG_CHUNK);
+        if (keys[end - 1] != key) {
+            long long lo = p, hi = end - 1;                    // keys[lo] == key, keys[hi] != key
+            while (hi - lo > 1) {
+                const long long mid = (lo + hi) >> 1;
+                if (keys[mid] == key) lo = mid; else hi = mid;
+            }
+            end = hi;
+        }
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (long long s = p; s < end && keys[s] == key; ++s) {
+        long long s = p;
+        for (; s + 4 <= end; s += 4) {                         // four rows in flight, added in position order
+            const float* s0 = acc.src(key, vals[s], q);
+            const float* s1 = acc.src(key, vals[s + 1], q);
+            const float* s2 = acc.src(key, vals[s + 2], q);
+            const float* s3 = acc.src(key, vals[s + 3], q);
+            if (VEC == 4) {
+                const float4 g0 = *reinterpret_cast<const float4*>(s0), g1 = *reinterpret_cast<const float4*>(s1);
+                const float4 g2 = *reinterpret_cast<const float4*>(s2), g3 = *reinterpret_cast<const float4*>(s3);
+                a.x += g0.x; a.y += g0.y; a.z += g0.z; a.w += g0.w;
+                a.x += g1.x; a.y += g1.y; a.z += g1.z; a.w += g1.w;
+                a.x += g2.x; a.y += g2.y; a.z += g2.z; a.w += g2.w;
+                a.x += g3.x; a.y += g3.y; a.z += g3.z; a.w += g3.w;
+            } else {
+                const float g0 = *s0, g1 = *s1, g2 = *s2, g3 = *s3;
+                a.x += g0; a.x += g1; a.x += g2; a.x += g3;
+            }
+        }
+        for (; s < end; ++s) {
             const float* src = acc.src(key, vals[s], q);
             if (VEC == 4) {
                 const float4 g = *reinterpret_cast<const float4*>(src);
@@ -74,32 +104,50 @@ __global__ void seg_reduce_chunks(const unsigned long long* __restrict__ keys, c
         if (!single && start == p && q == 0) *any_long = 1;
     }
 }
-// level 2: thread (p, q), p the first position of a multi-chunk run, adds the run's chunk partials in chunk order
+// level 2: one WARP per sorted position; if it is the first position of a multi-chunk run, lane l adds the run's chunk
+// partials l, l + 32, ... in increasing order and the 32 lane sums are added in lane order (a fixed tree), slice by slice
 template <int VEC, class Acc>
 __global__ void seg_reduce_long_runs(const unsigned long long* __restrict__ keys, long long n, Acc acc,
                                      const float* __restrict__ part, const int* __restrict__ any_long) {
     if (*any_long == 0) return;
-    const int W = acc.slices();
-    const long long total = n * W;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long p = i / W;
-        const int q = (int)(i - p * W);
+    const int W = acc.slices(), lane = threadIdx.x & 31;
+    const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long p = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; p < n; p += warps) {
         const unsigned long long key = keys[p];
         if (p > 0 && keys[p - 1] == key) continue;
         if (p + SEG_CHUNK >= n || keys[p + SEG_CHUNK] != key) continue;
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (long long c = p; c < n && keys[c] == key; c += SEG_CHUNK) {
-            const float* src = part + (seg_slot(c, p) * W + q) * VEC;
-            if (VEC == 4) {
-                const float4 g = *reinterpret_cast<const float4*>(src);
-                a.x += g.x; a.y += g.y; a.z += g.z; a.w += g.w;
-            } else {
-                a.x += *src;
+        long long lo = p + SEG_CHUNK, hi = n;                  // keys[lo] == key; first position past the run in (lo, hi]
+        while (hi - lo > 1) {
+            const long long mid = (lo + hi) >> 1;
+            if (keys[mid] == key) lo = mid; else hi = mid;
+        }
+        const long long nchunks = (hi - p + SEG_CHUNK - 1) / SEG_CHUNK;
+        for (int q = 0; q < W; ++q) {
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (long long c = lane; c < nchunks; c += 32) {
+                const float* src = part + (seg_slot(p + c * SEG_CHUNK, p) * W + q) * VEC;
+                if (VEC == 4) {
+                    const float4 g = *reinterpret_cast<const float4*>(src);
+                    a.x += g.x; a.y += g.y; a.z += g.z; a.w += g.w;
+                } else {
+                    a.x += *src;
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                a.x += __shfl_down_sync(FULL, a.x, o);
+                if (VEC == 4) {
+                    a.y += __shfl_down_sync(FULL, a.y, o);
+                    a.z += __shfl_down_sync(FULL, a.z, o);
+                    a.w += __shfl_down_sync(FULL, a.w, o);
+                }
+            }
+            if (lane == 0) {
+                float* dst = acc.dst(key, q);
+                if (VEC == 4) *reinterpret_cast<float4*>(dst) = a;
+                else *dst = a.x;
             }
         }
-        float* dst = acc.dst(key, q);
-        if (VEC == 4) *reinterpret_cast<float4*>(dst) = a;
-        else *dst = a.x;
     }
 }
 
@@ -123,29 +171,46 @@ static size_t cub_sort_bytes(long long n) {
     size_t bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const unsigned long long*)nullptr, (unsigned long long*)nullptr,
                                     (const int*)nullptr, (int*)nullptr, (int)n, 0, 64, (cudaStream_t)0);
+    size_t scan = 0;                                   // the run-start scan reuses the region after the sort
+    cub::DeviceScan::InclusiveScan(nullptr, scan, (int*)nullptr, (int*)nullptr, cub::Max(), (int)n, (cudaStream_t)0);
+    bytes = std::max(bytes, scan);
     return (bytes + 255) & ~(size_t)255;
 }
 static size_t seg_part_bytes(long long n) { return (size_t)(n / SEG_CHUNK + 2) * 2 * SEG_MAX_WIDTH * sizeof(float); }
-struct SegScratch { float* part; int* flag; size_t cub_bytes; };
+struct SegScratch { float* part; int* flag; int* starts; size_t cub_bytes; };
+static size_t seg_scratch_bytes(long long n) { return cub_sort_bytes(n) + seg_part_bytes(n) + 256 + (size_t)n * sizeof(int) + 256; }
 static int seg_scratch(void* sort_tmp, int64_t sort_tmp_bytes, long long n, SegScratch* out) {
     const size_t cb = cub_sort_bytes(n), pb = seg_part_bytes(n);
-    CFM_REQUIRE((size_t)sort_tmp_bytes >= cb + pb + 256, CFM_ERR_INVALID,
+    CFM_REQUIRE((size_t)sort_tmp_bytes >= seg_scratch_bytes(n), CFM_ERR_INVALID,
                 "sort scratch of %lld bytes is too small (cfm_emb_grad_tmp_bytes gives the size)", (long long)sort_tmp_bytes);
     out->cub_bytes = cb;
     out->part = reinterpret_cast<float*>(static_cast<char*>(sort_tmp) + cb);
     out->flag = reinterpret_cast<int*>(static_cast<char*>(sort_tmp) + cb + pb);
+    out->starts = reinterpret_cast<int*>(static_cast<char*>(sort_tmp) + cb + pb + 256);
+    return CFM_OK;
+}
+// run starts of the freshly sorted keys (uses cub's temporary storage again: the sort is done with it)
+static int seg_run_starts(const unsigned long long* keys_sorted, long long n, void* sort_tmp, const SegScratch& sc, cudaStream_t stream) {
+    seg_mark_heads<<<(int)std::min<long long>((n + 255) / 256, 148 * 8), 256, 0, stream>>>(keys_sorted, n, sc.starts);
+    CFM_LAUNCH_CHECK();
+    size_t need = 0;
+    cub::DeviceScan::InclusiveScan(nullptr, need, sc.starts, sc.starts, cub::Max(), (int)n, stream);
+    CFM_REQUIRE(need <= sc.cub_bytes, CFM_ERR_INVALID, "scan scratch larger than the sort scratch");
+    size_t bytes = sc.cub_bytes;
+    CFM_CHECK_CUDA(cub::DeviceScan::InclusiveScan(sort_tmp, bytes, sc.starts, sc.starts, cub::Max(), (int)n, stream));
     return CFM_OK;
 }
 template <int VEC, class Acc>
 static int seg_reduce_launch(const unsigned long long* keys, const int* vals, long long n, const Acc& acc, int width,
-                             const SegScratch& sc, cudaStream_t stream) {
+                             const SegScratch& sc, long long base, cudaStream_t stream) {
     CFM_REQUIRE(width <= SEG_MAX_WIDTH, CFM_ERR_UNSUPPORTED, "embedding slices wider than %d floats are not supported", SEG_MAX_WIDTH);
     CFM_CHECK_CUDA(cudaMemsetAsync(sc.flag, 0, sizeof(int), stream));
     const long long total = n * (width / VEC);
     const int grid = (int)std::min<long long>((total + 255) / 256, 148 * 16);
-    seg_reduce_chunks<VEC, Acc><<<grid, 256, 0, stream>>>(keys, vals, n, acc, sc.part, sc.flag);
+    seg_reduce_chunks<VEC, Acc><<<grid, 256, 0, stream>>>(keys, vals, n, acc, sc.part, sc.flag, sc.starts + base, base);
     CFM_LAUNCH_CHECK();
-    seg_reduce_long_runs<VEC, Acc><<<grid, 256, 0, stream>>>(keys, n, acc, sc.part, sc.flag);
+    const int grid2 = (int)std::min<long long>((n * 32 + 255) / 256, 148 * 64);
+    seg_reduce_long_runs<VEC, Acc><<<grid2, 256, 0, stream>>>(keys, n, acc, sc.part, sc.flag);
     CFM_LAUNCH_CHECK();
     return CFM_OK;
 }
@@ -201,8 +266,7 @@ static int fill_tables(TablePtrs& tp, float* const* grad_tables, const int64_t* 
 using namespace cfm;
 
 extern "C" int64_t cfm_emb_grad_tmp_bytes(int64_t n_tables, int64_t B) {
-    const long long n = n_tables * B;
-    return (int64_t)(cub_sort_bytes(n) + seg_part_bytes(n) + 256);
+    return (int64_t)seg_scratch_bytes(n_tables * B);
 }
 
 extern "C" int cfm_emb_grad_segment_reduce(const int64_t* x_cat, const float* dx_emb, int64_t B, int64_t n_tables,
@@ -232,12 +296,14 @@ extern "C" int cfm_emb_grad_segment_reduce(const int64_t* x_cat, const float* dx
                                                    (unsigned long long*)keys_sorted, (const int*)vals_tmp,
                                                    vals_sorted, (int)n, 0, key_bits, stream));
     const unsigned long long* ks = (const unsigned long long*)keys_sorted;
+    rc = seg_run_starts(ks, n, sort_tmp, sc, stream);
+    if (rc) return rc;
     if ((emb_dim & 3) == 0) {
         DenseAcc<4> acc{dx_emb, tp, (int)(n_tables * emb_dim), (int)emb_dim, idx_bits, 0};
-        return seg_reduce_launch<4>(ks, vals_sorted, n, acc, (int)emb_dim, sc, stream);
+        return seg_reduce_launch<4>(ks, vals_sorted, n, acc, (int)emb_dim, sc, 0, stream);
     }
     DenseAcc<1> acc{dx_emb, tp, (int)(n_tables * emb_dim), (int)emb_dim, idx_bits, 0};
-    return seg_reduce_launch<1>(ks, vals_sorted, n, acc, (int)emb_dim, sc, stream);
+    return seg_reduce_launch<1>(ks, vals_sorted, n, acc, (int)emb_dim, sc, 0, stream);
 }
 
 extern "C" int cfm_emb_grad_rezero(float* const* grad_tables, const int64_t* table_rows, int64_t n_tables,
@@ -487,6 +553,8 @@ extern "C" int cfm_emb_grad_peer_reduce(const cfm_peer_group_t* groups, int64_t 
         CFM_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(sort_tmp, bytes, (const unsigned long long*)keys_tmp,
                                                        (unsigned long long*)keys_sorted, (const int*)vals_tmp,
                                                        vals_sorted, (int)n, 0, key_bits, stream));
+        rc = seg_run_starts((const unsigned long long*)keys_sorted, n, sort_tmp, sc, stream);
+        if (rc) return rc;
     }
     if (phase == 1) return CFM_OK;
     long long off = 0;
@@ -496,10 +564,10 @@ extern "C" int cfm_emb_grad_peer_reduce(const cfm_peer_group_t* groups, int64_t 
         const unsigned long long* ks = (const unsigned long long*)keys_sorted + off;
         if ((G.width & 3) == 0 && (G.emb_dim & 3) == 0) {
             PeerAcc<4> acc{pp, tp, (int)B, (int)G.emb_dim, (int)G.width, idx_bits};
-            rc = seg_reduce_launch<4>(ks, vals_sorted + off, ng, acc, (int)G.width, sc, stream);
+            rc = seg_reduce_launch<4>(ks, vals_sorted + off, ng, acc, (int)G.width, sc, off, stream);
         } else {
             PeerAcc<1> acc{pp, tp, (int)B, (int)G.emb_dim, (int)G.width, idx_bits};
-            rc = seg_reduce_launch<1>(ks, vals_sorted + off, ng, acc, (int)G.width, sc, stream);
+            rc = seg_reduce_launch<1>(ks, vals_sorted + off, ng, acc, (int)G.width, sc, off, stream);
         }
         if (rc) return rc;
         off += ng;
@@ -691,6 +759,8 @@ extern "C" int cfm_emb_grad_joint_reduce(const cfm_emb_group_t* groups, int64_t 
         CFM_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(sort_tmp, bytes, (const unsigned long long*)keys_tmp,
                                                        (unsigned long long*)keys_sorted, (const int*)vals_tmp,
                                                        vals_sorted, (int)n, 0, key_bits, stream));
+        rc = seg_run_starts((const unsigned long long*)keys_sorted, n, sort_tmp, sc, stream);
+        if (rc) return rc;
     }
     if (phase == 1) return CFM_OK;
     for (int g = 0; g < n_groups; ++g) {
@@ -699,10 +769,10 @@ extern "C" int cfm_emb_grad_joint_reduce(const cfm_emb_group_t* groups, int64_t 
         const unsigned long long* ks = (const unsigned long long*)keys_sorted + off;
         if ((G.emb_dim & 3) == 0) {
             DenseAcc<4> acc{G.dx_emb, tps[g], (int)(G.n_tables * G.emb_dim), (int)G.emb_dim, idx_bits, jk.t0[g]};
-            rc = seg_reduce_launch<4>(ks, vals_sorted + off, ng, acc, (int)G.emb_dim, sc, stream);
+            rc = seg_reduce_launch<4>(ks, vals_sorted + off, ng, acc, (int)G.emb_dim, sc, off, stream);
         } else {
             DenseAcc<1> acc{G.dx_emb, tps[g], (int)(G.n_tables * G.emb_dim), (int)G.emb_dim, idx_bits, jk.t0[g]};
-            rc = seg_reduce_launch<1>(ks, vals_sorted + off, ng, acc, (int)G.emb_dim, sc, stream);
+            rc = seg_reduce_launch<1>(ks, vals_sorted + off, ng, acc, (int)G.emb_dim, sc, off, stream);
         }
         if (rc) return rc;
     }

@@ -107,3 +107,54 @@ def test_row_block_variants_give_exact_ranking(rb):
     so, io = oracle.allpairs_topk(u, v, 100, SCALE)
     np.testing.assert_array_equal(idx.cpu().numpy(), io.numpy())
     assert int(flags.sum()) == 0
+
+
+def test_generate_counterfactuals_matches_a_full_sort_restatement():
+    """analytical_extensions.py:405-523 routed to score_topk / target_ranks: the table equals what the reference's
+    torch.mm + np.argsort loop gives on the same (device-computed) unit latents."""
+    import contextlib
+    import io
+    import pandas as pd
+    import oracle
+    from ceo_firm_matching import CEOFirmMatcher, Config
+    from ceo_firm_matching.analytical_extensions import generate_counterfactuals, _unit_latents
+    from helpers import load_into
+    f_cards, c_cards = [9, 5, 3, 2], [2, 4, 3, 2, 2, 5, 2]
+    n = 600
+    gen = torch.Generator().manual_seed(21)
+    p = oracle.init_two_tower_params(12, f_cards, 2, c_cards, seed=8)
+    meta = {"n_firm_numeric": 12, "firm_cat_counts": f_cards, "n_ceo_numeric": 2, "ceo_cat_counts": c_cards}
+    model = load_into(CEOFirmMatcher(meta, Config()), p).to(DEV)
+    data = {"firm_numeric": torch.randn(n, 12, generator=gen),
+            "firm_cat": torch.stack([torch.randint(0, c, (n,), generator=gen) for c in f_cards], 1),
+            "ceo_numeric": torch.randn(n, 2, generator=gen),
+            "ceo_cat": torch.stack([torch.randint(0, c, (n,), generator=gen) for c in c_cards], 1)}
+    rng = np.random.default_rng(3)
+    df = pd.DataFrame({"gvkey": rng.integers(0, 150, n), "match_exec_id": rng.integers(0, 400, n),
+                       "fiscalyear": rng.integers(2000, 2020, n), "match_means": rng.normal(size=n)})
+    with contextlib.redirect_stdout(io.StringIO()):
+        cf = generate_counterfactuals(model, data, df, device=DEV)
+    # restatement of the reference's loop on the same latents
+    with torch.no_grad():
+        model.eval()
+        u, v = _unit_latents(model, data, torch.device(DEV))
+    u, v = u.cpu().double(), v.cpu().double()
+    scale = float(model.logit_scale.exp())
+    d = df.reset_index(drop=True)
+    firm_idx = d.loc[d.groupby("gvkey")["fiscalyear"].idxmax()].index.values[:200]
+    ceo_idx = d.drop_duplicates(subset="match_exec_id", keep="last").index.values[:1000]
+    scores = (u[firm_idx] @ v[ceo_idx].t()).numpy() * scale
+    assert len(cf) == len(firm_idx)
+    for i, fi in enumerate(firm_idx):
+        order = np.argsort(-scores[i], kind="stable")
+        row = cf.iloc[i]
+        assert row["firm_id"] == d.loc[fi, "gvkey"]
+        assert row["best_ceo"] == d.loc[ceo_idx[order[0]], "match_exec_id"]
+        assert row["worst_ceo"] == d.loc[ceo_idx[order[-1]], "match_exec_id"]
+        assert row["best_score"] == pytest.approx(scores[i, order[0]], rel=2e-6, abs=1e-6)
+        assert row["worst_score"] == pytest.approx(scores[i, order[-1]], rel=2e-6, abs=1e-6)
+        hit = (d.loc[ceo_idx, "match_exec_id"] == d.loc[fi, "match_exec_id"]).values
+        if hit.any():
+            assert row["actual_rank"] == int((order == hit.argmax()).argmax()) + 1
+        else:
+            assert row["actual_rank"] is None or np.isnan(row["actual_rank"])
