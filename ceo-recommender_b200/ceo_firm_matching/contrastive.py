@@ -59,10 +59,21 @@ class ContrastiveCEOFirmMatcher(nn.Module):
 def info_nce_loss(firm_proj: torch.Tensor, ceo_proj: torch.Tensor, temperature: float = 0.07) -> torch.Tensor:
     """Symmetric InfoNCE over in-batch negatives (contrastive.py:102-138): rows of ``firm_proj`` / ``ceo_proj`` are
     unit vectors, positives sit on the diagonal of ``S = F C^T / T``; returns 0 for ``B <= 1``.
-    Computed in bf16 on the tensor cores with fp32 accumulation (tolerance: 1e-3 relative on the loss)."""
+    Computed in bf16 on the tensor cores with fp32 accumulation (tolerance: 1e-3 relative on the loss).
+    Inputs must be unit rows and ``temperature >= 0.012`` (both checked): the kernels subtract the fixed maximum 1/T."""
     B = firm_proj.size(0)
     if B <= 1:
         return torch.tensor(0.0, device=firm_proj.device)
+    # The kernels use the fixed softmax shift 1/T (|s| <= 1 for unit rows), which makes partial sums addable across
+    # column chunks and GPUs; rows that are not unit vectors would overflow it, and a temperature below ~0.012 lets
+    # exp((s - 1)/T) underflow fp32 for s < 0.  Checked here (one small reduction + host read) unless a CUDA graph is
+    # being captured.
+    if not 0.012 <= float(temperature):
+        raise ValueError("info_nce_loss: temperature must be >= 0.012 for the fixed-shift softmax (reference default 0.07)")
+    if not torch.cuda.is_current_stream_capturing():
+        nmax = float(torch.maximum(firm_proj.detach().norm(dim=1).max(), ceo_proj.detach().norm(dim=1).max()))
+        if not nmax <= 1.0 + 1e-3:
+            raise ValueError(f"info_nce_loss expects L2-normalised rows (contrastive.py:96-97); largest row norm is {nmax:.4f}")
     return ops.InfoNCEFunction.apply(firm_proj, ceo_proj, float(temperature))
 
 

@@ -429,7 +429,8 @@ class TableShardedTwoTower:
         """Zero the owned gradient slices written by the last reduce.  Runs at the start of the next step's key
         build (not inside ``zero_grad_fast``, which a CUDA graph may have captured before the first reduce
         existed); call it directly to get clean ``.grad`` tables earlier."""
-        if self.groups and self._dirty:
+        capturing = torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
+        if self.groups and (self._dirty or capturing):    # idempotent: a captured step always carries the re-zero node
             self.kernels.rezero(self.groups, self.world, self.B, self.scratch)
         self._dirty = False
 

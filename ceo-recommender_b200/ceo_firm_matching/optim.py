@@ -73,9 +73,17 @@ class FusedAdam(torch.optim.Optimizer):
             with torch.enable_grad():
                 loss = closure()
         for group in self.param_groups:
+            if group.get("weight_decay", 0) or group.get("amsgrad") or group.get("maximize"):
+                raise NotImplementedError("FusedAdam implements torch.optim.Adam with weight_decay=0, amsgrad=False, "
+                                          "maximize=False (the reference's optimiser, training.py:32)")
             params = [p for p in group["params"] if p.grad is not None and p.numel() > 0]
             if not params:
                 continue
+            if len(params) != sum(1 for p in group["params"] if p.numel() > 0 and p.requires_grad) and self._steps:
+                # one step counter drives the bias correction of the whole group (they advance together): a
+                # parameter that skips steps would need torch's per-parameter count
+                raise NotImplementedError("FusedAdam: every parameter of a group must receive a gradient at every step "
+                                          "(per-parameter step counts are not tracked)")
             if any(not p.is_cuda for p in params):
                 raise RuntimeError("FusedAdam runs on CUDA parameters only (this build has no CPU fallback)")
             steps = self._state_for(group, params)

@@ -56,6 +56,11 @@ class GraphedTwoTowerStep:
         # if that is the legacy default stream.  Warm-up, capture and replay therefore share one side stream (the
         # caller's own non-default stream when it already trains on one).
         self.stream = stream if stream is not None else torch.cuda.Stream(dev)
+        if warmup == 0 and optimizer is not None and any(
+                p.requires_grad and "exp_avg" not in optimizer.state.get(p, {}) for g in optimizer.param_groups for p in g["params"]):
+            # the optimiser would create (zero-fill) its moments INSIDE the capture and every replay would reset them
+            raise RuntimeError("GraphedTwoTowerStep(warmup=0) needs the optimiser state to exist: run one eager step of this "
+                               "batch size first (train_model does), or pass warmup >= 1")
         ops.set_graph_rng_counter(self.counter)
         try:
             self.stream.wait_stream(torch.cuda.current_stream(dev))
