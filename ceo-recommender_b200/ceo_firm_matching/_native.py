@@ -115,6 +115,7 @@ PROTOTYPES = {
     "cfm_structural_head": (C.c_int, [_V, _V, _V, _V, _V, _V, _I, _D, _V, _V, _V, _V, _V, _V]),
     "cfm_simtile_chunks": (i64, [_I, _I]),
     "cfm_simtile_set_rb": (C.c_int, [_I]),
+    "cfm_simtile_set_poly": (C.c_int, [_I]),
     "cfm_pack_rows_bf16": (C.c_int, [_V, _I, _I, _I, _V, _V]),
     "cfm_infonce_rowsum": (C.c_int, [_V, _V, _I, _I, _I, _D, _I, _V, _V, _V, _V]),
     "cfm_infonce_loss": (C.c_int, [_V, _V, _V, _I, _D, _I, _V, _V]),

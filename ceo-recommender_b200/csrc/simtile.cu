@@ -20,8 +20,8 @@ namespace cfm {
 
 constexpr int ST_M = 128, ST_N = 128, ST_KB = 64;      // tile rows / cols, bf16 elements per 128-byte swizzle row
 constexpr int ST_STAGES = 3;
-__host__ __device__ constexpr int sim_stages(int mode, int rb) { return (mode == 2 && rb == 2) ? 2 : ST_STAGES; }
-constexpr int ST_THREADS = 64 + 8 * 32;               // TMA warp, MMA warp, 8 epilogue warps
+// TMA warp, MMA warp, then 16 epilogue warps in the InfoNCE modes (row sums, gradients), 8 otherwise
+__host__ __device__ constexpr int sim_threads(int mode) { return 64 + ((mode == 1 || mode == 2) ? 16 : 8) * 32; }
 constexpr int KB_BYTES = ST_M * 128;                   // one [128 rows x 64 bf16] swizzled block = 16 KB
 constexpr float LOG2E = 1.4426950408889634f;
 
@@ -139,7 +139,44 @@ struct SimArgs {
     int* cand_cnt;                // top-k: [lists * Rpad] entries in use
     float* cand_thr;              // top-k: [chunks * Rpad] final admission threshold (-inf: nothing was dropped)
     int Rpad;
+    int poly;                     // InfoNCE: a quarter of the exponentials on the FMA pipe (needs 2*c1 <= 120)
 };
+
+// InfoNCE epilogue strips: N fresh scores of one row -> exponentials, in batches of 16 (see exp16)
+template <bool POLY, int N>
+__device__ __forceinline__ void rowsum_strip(const float (&v)[N], float c1, float c2, float (&acc)[4]) {
+#pragma unroll
+    for (int i0 = 0; i0 < N; i0 += 16) {
+        float e[16];
+        exp16<POLY>(v + i0, c1, c2, e);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i & 3] += e[i];
+    }
+}
+// ry: alpha / column sums of the N columns (shared memory, 16-byte aligned); dst16(i0 / 8) receives eight bf16 values
+template <bool POLY, int N, class Store>
+__device__ __forceinline__ void grad_strip(const float (&v)[N], const float* ry, float rx, float c1, float c2, Store&& store16) {
+#pragma unroll
+    for (int i0 = 0; i0 < N; i0 += 16) {
+        float e[16], w[16];
+        exp16<POLY>(v + i0, c1, c2, e);
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+            const float4 r4 = *reinterpret_cast<const float4*>(ry + i0 + i);
+            w[i] = rx + r4.x; w[i + 1] = rx + r4.y; w[i + 2] = rx + r4.z; w[i + 3] = rx + r4.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) e[i] *= w[i];
+        uint32_t pk[8];
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(e[i], e[i + 1]);
+            pk[i >> 1] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+        store16(i0 / 8, make_uint4(pk[0], pk[1], pk[2], pk[3]));
+        store16(i0 / 8 + 1, make_uint4(pk[4], pk[5], pk[6], pk[7]));
+    }
+}
 
 // scan 64 fresh scores of one row, then let the warp compact any buffer that could overflow on the next 64 columns
 __device__ __forceinline__ void topk_admit(const SimArgs& a, const float (&v)[64], int j0, long long list, int blk_row0, int q,
@@ -167,7 +204,7 @@ __host__ __device__ inline SimSmem sim_smem(int Dp, int mode, int rb) {
     const int nkb = Dp / ST_KB;
     int o = 0;
     s.x = o; o += rb * nkb * KB_BYTES;
-    s.y = o; o += sim_stages(mode, rb) * nkb * KB_BYTES;
+    s.y = o; o += ST_STAGES * nkb * KB_BYTES;
     s.g = o; o += mode == SIM_GRAD ? 2 * 2 * KB_BYTES : 0;
     s.ry = o; o += 4 * ST_N * 4;
     s.bars = o; o += 32 * 8;
@@ -177,7 +214,7 @@ __host__ __device__ inline SimSmem sim_smem(int Dp, int mode, int rb) {
 }
 
 template <int MODE, int RB>
-__global__ void __launch_bounds__(ST_THREADS, 1)
+__global__ void __launch_bounds__(sim_threads(MODE), 1)
 simtile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_y, const SimArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -198,16 +235,17 @@ simtile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
     const int tile0 = blockIdx.y * a.tiles_per_chunk;
     const int n_tiles = max(0, min(a.tiles_per_chunk, a.n_col_tiles - tile0));
     constexpr bool grad = MODE == SIM_GRAD;
-    constexpr bool GRAD2 = MODE == SIM_GRAD && RB == 2;    // two row blocks ping-pong on single-buffered S / G
-    constexpr int NSTG = sim_stages(MODE, RB);
+    constexpr bool NCE = MODE == SIM_ROWSUM || MODE == SIM_GRAD;      // 16 epilogue warps
+    constexpr int NSTG = ST_STAGES;
+    // threads that hand an S buffer back: every buffer is drained by two four-warp groups (column halves), except in
+    // the top-k variant with two row blocks, where one group walks a whole buffer (one candidate stream per row)
+    constexpr int S_DRAIN = (MODE == SIM_TOPK && RB == 2) ? 128 : 256;
 
     if (threadIdx.x == 0) {
         mbar_init(x_full, 1);
         for (int s = 0; s < NSTG; ++s) { mbar_init(y_full + s, 1); mbar_init(y_empty + s, 1); }
-        // an S buffer is drained by all 8 epilogue warps (column halves) except in the top-k RB=2 variant, where
-        // each 128-row block belongs to one warp group that walks both halves (one candidate stream per row)
-        for (int b = 0; b < 4; ++b) { mbar_init(s_full + b, 1); mbar_init(s_empty + b, ((MODE == SIM_TOPK && RB == 2) || GRAD2) ? 128 : 256); }
-        for (int b = 0; b < 2; ++b) { mbar_init(g_full + b, GRAD2 ? 128 : 256); mbar_init(g_empty + b, 1); }
+        for (int b = 0; b < 4; ++b) { mbar_init(s_full + b, 1); mbar_init(s_empty + b, S_DRAIN); }
+        for (int b = 0; b < 2; ++b) { mbar_init(g_full + b, 256); mbar_init(g_empty + b, 1); }
         mbar_init(acc_full, 1);
         fence_barrier_init();
     }
@@ -242,39 +280,6 @@ simtile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
             const uint32_t idesc2 = make_idesc(ST_M, a.Dp, true);
             const uint32_t xs = smem_u32(Xs), ys = smem_u32(Ys), gs = smem_u32(Gs);
             mbar_wait(x_full, 0);
-            if (GRAD2) {
-                // per Y tile: S_0, S_1 (GEMM 1 for both row blocks), then dX_0 += G_0 Y, dX_1 += G_1 Y.  While the
-                // epilogue of one row block exponentiates, the tensor core works for the other one.
-                for (int t = 0; t < n_tiles; ++t) {
-                    const int s = t % NSTG;
-                    mbar_wait(y_full + s, (t / NSTG) & 1);
-                    const uint32_t yb = ys + s * nkb * KB_BYTES;
-                    for (int rb = 0; rb < 2; ++rb) {
-                        mbar_wait(s_empty + rb * 2, (t & 1) ^ 1);
-                        tc_fence_after();
-                        const uint32_t xb = xs + rb * nkb * KB_BYTES;
-                        for (int ks = 0; ks < a.Dp / 16; ++ks) {
-                            const uint32_t off = (ks >> 2) * KB_BYTES + (ks & 3) * 32;
-                            umma_bf16(tmem_s0 + rb * ST_N, desc_kmajor_sw128(xb + off), desc_kmajor_sw128(yb + off), idesc1, ks > 0);
-                        }
-                        umma_commit(s_full + rb * 2);
-                    }
-                    for (int rb = 0; rb < 2; ++rb) {
-                        mbar_wait(g_full + rb, t & 1);
-                        tc_fence_after();
-                        const uint32_t gb = gs + rb * 2 * KB_BYTES;
-                        for (int ks = 0; ks < ST_N / 16; ++ks) {
-                            const uint32_t aoff = (ks >> 2) * KB_BYTES + (ks & 3) * 32;
-                            const uint32_t boff = ks * 16 * 128;
-                            umma_bf16(tmem_acc + rb * ST_N, desc_kmajor_sw128(gb + aoff), desc_mnmajor_sw128(yb + boff, KB_BYTES),
-                                      idesc2, t > 0 || ks > 0);
-                        }
-                        umma_commit(g_empty + rb);
-                    }
-                    umma_commit(y_empty + s);
-                }
-                umma_commit(acc_full);
-            } else
             for (int t = 0; t <= n_tiles; ++t) {
                 if (t < n_tiles) {                     // GEMM 1: S(rb, b) = X_rb . Y_t^T
                     const int s = t % NSTG, b = t & 1;
@@ -308,94 +313,169 @@ simtile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
                     umma_commit(y_empty + s);
                 }
             }
-            if (grad && !GRAD2) umma_commit(acc_full);
+            if (grad) umma_commit(acc_full);
         }
-    } else {
-        // ===================== epilogue: 8 warps; thread <-> TMEM lane <-> row, warp group <-> column half ======
-        const int half = (warp - 2) >> 2;              // columns [64*half, 64*half+64) of every tile
+    } else if constexpr (NCE) {
+        // ===================== InfoNCE epilogues: 16 warps = 4 groups of 4 (thread <-> TMEM lane <-> row) ============
+        // Group g takes the column half `ch` of the S buffers of its `slot`: slot <-> row block when the CTA has two,
+        // else slot <-> tile parity.  The two slots run decoupled on different S buffers, four warps per scheduler:
+        // TMEM-load, barrier and MUFU latencies of one warp are covered by the others.
+        const int g = (warp - 2) >> 2, ch = g >> 1, slot = g & 1;
         const int q = warp & 3;                        // TMEM lane quadrant this warp may access
         const int r_loc = 32 * q + lane;
         const uint32_t lane_addr = (uint32_t)(32 * q) << 16;
-        const long long list = (long long)blockIdx.y * 2 + half;
-        // per 128-row block state (RB <= 2)
-        long long row[RB];
-        bool row_ok[RB], have_diag[RB];
-        float racc[RB][4], dval[RB], thr[RB];
-        int cnt[RB];
-#pragma unroll
-        for (int rb = 0; rb < RB; ++rb) {
-            row[rb] = (long long)row0 + rb * ST_M + r_loc;
-            row_ok[rb] = row[rb] < a.R;
-            thr[rb] = row_ok[rb] ? -INFINITY : INFINITY;       // rows past R admit nothing
-            cnt[rb] = 0; dval[rb] = 0.f; have_diag[rb] = false;
-            racc[rb][0] = racc[rb][1] = racc[rb][2] = racc[rb][3] = 0.f;
-        }
-        const float rx = (grad && row_ok[0]) ? a.alpha / a.rowsum_x[row[0]] : 0.f;
-        if (GRAD2) {
-            // warp group `half` owns row block `half`: 128 threads, one row each, all 128 columns of every tile
-            const int rbo = half;
-            const long long myrow = (long long)row0 + rbo * ST_M + r_loc;
-            const bool my_ok = myrow < a.R;
-            const float myrx = my_ok ? a.alpha / a.rowsum_x[myrow] : 0.f;
-            const long long dcol = myrow + a.diag_offset;
-            uint8_t* grow = Gs + rbo * 2 * KB_BYTES + r_loc * 128;
-            for (int t = 0; t < n_tiles; ++t) {
-                const int jt = (tile0 + t) * ST_N;
-                float* ry = sm_ry + (rbo * 2 + (t & 1)) * ST_N;      // per group, double-buffered by tile parity
-                ry[r_loc] = (jt + r_loc < a.C) ? a.alpha / a.rowsum_y[jt + r_loc] : 0.f;
-                named_bar_sync(1 + rbo, 128);
-                mbar_wait(s_full + rbo * 2, t & 1);
+        const int rbo = RB == 2 ? slot : 0;
+        const int t_first = RB == 2 ? 0 : slot, t_step = RB == 2 ? 1 : 2;
+        const long long myrow = (long long)row0 + rbo * ST_M + r_loc;
+        const bool my_ok = myrow < a.R;
+        const long long dcol = myrow + a.diag_offset;  // column of this row's positive pair
+        if constexpr (MODE == SIM_ROWSUM) {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f}, dv = 0.f;
+            bool hd = false;
+            for (int t = t_first; t < n_tiles; t += t_step) {
+                const int b = t & 1, sb = rbo * 2 + b;
+                const int j0 = (tile0 + t) * ST_N + 64 * ch;
+                const uint32_t taddr = tmem_s0 + sb * ST_N + 64 * ch + lane_addr;
+                mbar_wait(s_full + sb, (t >> 1) & 1);
                 tc_fence_after();
-                const bool edge = jt + 128 > a.C || (dcol >= jt && dcol < jt + 128);
-                uint32_t packed[64];
+                const bool diag_here = dcol >= j0 && dcol < j0 + 64;
+                auto piece = [&](const float (&v)[32], int jp) {       // 32 columns from jp on
+                    if (jp + 32 <= a.C) {
+                        if (a.poly) rowsum_strip<true, 32>(v, a.c1, a.c2, acc);
+                        else rowsum_strip<false, 32>(v, a.c1, a.c2, acc);
+                    } else {
 #pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                    float v[64];
-                    tmem_ld64(tmem_s0 + rbo * ST_N + 64 * hh + lane_addr, v);
-#pragma unroll
-                    for (int i = 0; i < 64; i += 2) {
-                        const int c = 64 * hh + i;
-                        float g0 = ex2_approx(fmaf(v[i], a.c1, -a.c2)) * (myrx + ry[c]);
-                        float g1 = ex2_approx(fmaf(v[i + 1], a.c1, -a.c2)) * (myrx + ry[c + 1]);
-                        if (edge) {
-                            if (jt + c >= a.C || jt + c == dcol) g0 = 0.f;
-                            if (jt + c + 1 >= a.C || jt + c + 1 == dcol) g1 = 0.f;
-                        }
-                        __nv_bfloat162 h2 = __floats2bfloat162_rn(g0, g1);
-                        packed[c >> 1] = *reinterpret_cast<uint32_t*>(&h2);
+                        for (int i = 0; i < 32; ++i) acc[i & 3] += (jp + i < a.C) ? ex2_approx(fmaf(v[i], a.c1, -a.c2)) : 0.f;
                     }
+                    if (diag_here && dcol >= jp && dcol < jp + 32) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (jp + i == dcol) dv = v[i];
+                        hd = true;
+                    }
+                };
+                {
+                    float va[32];
+                    tmem_ld32(taddr, va);
+                    piece(va, j0);
                 }
-                tc_fence_before();
-                mbar_arrive(s_empty + rbo * 2);                       // S consumed: GEMM 1 of the next tile may run
-                mbar_wait(g_empty + rbo, (t & 1) ^ 1);                // GEMM 2 of the previous tile is done with G
+                {
+                    float vb[32];
+                    tmem_ld32(taddr + 32, vb);
+                    tc_fence_before();
+                    mbar_arrive(s_empty + sb);         // the buffer is in registers: it may be refilled
+                    piece(vb, j0 + 32);
+                }
+            }
+            float sum = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+            if (RB == 1) {                             // the two tile parities of a row meet in shared memory
+                if (slot == 1) sm_ry[ch * ST_M + r_loc] = sum;
+                named_bar_sync(3, 512);
+                if (slot == 0) sum += sm_ry[ch * ST_M + r_loc];
+            }
+            if (my_ok) {
+                if (RB == 2 || slot == 0) a.out_part[((long long)blockIdx.y * 2 + ch) * a.R + myrow] = sum;
+                if (a.diag && hd) a.diag[myrow] = dv;
+            }
+        } else {
+            // gradient: G = E * (1/R_i + 1/C_j) * alpha re-staged as the bf16 A operand of GEMM 2.  The positive pair
+            // is left out of the bf16 tile (its weight is O(1/B), every other entry O(1/B^2)); the finalize kernel adds
+            // it in fp32.  Only the ragged last tile and the tile holding the positives need per-element tests.
+            const float rx = my_ok ? a.alpha / a.rowsum_x[myrow] : 0.f;
+            auto load_ry = [&](int t) {                // threads r_loc < 64 of a group stage its 64 column factors
+                const long long j = (long long)(tile0 + t) * ST_N + 64 * ch + r_loc;
+                return (r_loc < 64 && t < n_tiles && j < a.C) ? __ldg(a.rowsum_y + j) : 0.f;
+            };
+            float ry_raw = load_ry(t_first);
+            for (int t = t_first; t < n_tiles; t += 2) {
+                const int b = slot, u = t >> 1;                      // b == t & 1; u-th tile of this slot
+                const int j0 = (tile0 + t) * ST_N + 64 * ch;
+                float* ry = sm_ry + ((slot * 2 + (u & 1)) * 2 + ch) * 64;   // double-buffered per slot
+                if (r_loc < 64) ry[r_loc] = ry_raw > 0.f ? a.alpha / ry_raw : 0.f;
+                ry_raw = load_ry(t + 2);                             // in flight while this tile is worked on
+                named_bar_sync(1 + g, 128);
+                mbar_wait(s_full + b, u & 1);
+                tc_fence_after();
+                const uint32_t taddr = tmem_s0 + b * ST_N + 64 * ch + lane_addr;
+                const bool edge = __any_sync(FULL, j0 + 64 > a.C || (dcol >= j0 && dcol < j0 + 64));
+                mbar_wait(g_empty + b, (u & 1) ^ 1);                 // GEMM 2 of tile t-2 no longer reads G[b]
+                // G[b] is the K-major SW128 A operand of GEMM 2; this group fills k-block `ch` of row r_loc, one
+                // 32-column piece (four 16-byte chunks) at a time
+                uint8_t* grow = Gs + (b * 2 + ch) * KB_BYTES + r_loc * 128;
+                auto piece = [&](const float (&v)[32], int pc) {
+                    auto store16 = [&](int c16, const uint4& val) {          // 16-byte chunk c16 of this piece
+                        *reinterpret_cast<uint4*>(grow + (((4 * pc + c16) ^ (r_loc & 7)) << 4)) = val;
+                    };
+                    if (!edge) {
+                        if (a.poly) grad_strip<true, 32>(v, ry + 32 * pc, rx, a.c1, a.c2, store16);
+                        else grad_strip<false, 32>(v, ry + 32 * pc, rx, a.c1, a.c2, store16);
+                    } else {
+                        uint32_t pk[16];
 #pragma unroll
-                for (int kb = 0; kb < 2; ++kb)
+                        for (int i = 0; i < 32; i += 2) {
+                            const int j = j0 + 32 * pc + i;
+                            float g0 = ex2_approx(fmaf(v[i], a.c1, -a.c2)) * (rx + ry[32 * pc + i]);
+                            float g1 = ex2_approx(fmaf(v[i + 1], a.c1, -a.c2)) * (rx + ry[32 * pc + i + 1]);
+                            if (j >= a.C || j == dcol) g0 = 0.f;
+                            if (j + 1 >= a.C || j + 1 == dcol) g1 = 0.f;
+                            __nv_bfloat162 h2 = __floats2bfloat162_rn(g0, g1);
+                            pk[i >> 1] = *reinterpret_cast<uint32_t*>(&h2);
+                        }
 #pragma unroll
-                    for (int h8 = 0; h8 < 8; ++h8) {
-                        const int o = kb * 32 + h8 * 4;
-                        uint4 val = make_uint4(packed[o], packed[o + 1], packed[o + 2], packed[o + 3]);
-                        *reinterpret_cast<uint4*>(grow + kb * KB_BYTES + ((h8 ^ (r_loc & 7)) << 4)) = val;
+                        for (int h = 0; h < 4; ++h) store16(h, make_uint4(pk[4 * h], pk[4 * h + 1], pk[4 * h + 2], pk[4 * h + 3]));
                     }
-                fence_proxy_async();
-                mbar_arrive(g_full + rbo);
+                };
+                {
+                    float va[32];
+                    tmem_ld32(taddr, va);
+                    piece(va, 0);
+                }
+                {
+                    float vb[32];
+                    tmem_ld32(taddr + 32, vb);
+                    tc_fence_before();
+                    mbar_arrive(s_empty + b);                        // S is in registers: GEMM 1 of tile t+2 may run
+                    piece(vb, 1);
+                }
+                fence_proxy_async();                                 // generic-proxy smem writes -> visible to the tensor core
+                mbar_arrive(g_full + b);
             }
             if (n_tiles > 0) {
                 mbar_wait(acc_full, 0);
                 tc_fence_after();
             }
-            for (int c = 0; c < a.Dp / 32; ++c) {
+            // group g drains columns [g * Dp/4, (g+1) * Dp/4) of dX (32 or 16 columns)
+            if (a.Dp == 128) {
                 float w[32];
-                if (n_tiles > 0) tmem_ld32(tmem_acc + rbo * ST_N + c * 32 + lane_addr, w);
+                if (n_tiles > 0) tmem_ld32(tmem_acc + 32 * g + lane_addr, w);
                 else
                     for (int i = 0; i < 32; ++i) w[i] = 0.f;
                 if (my_ok) {
-                    float4* dst = reinterpret_cast<float4*>(a.out_part + ((long long)blockIdx.y * a.R + myrow) * a.Dp + c * 32);
+                    float4* dst = reinterpret_cast<float4*>(a.out_part + ((long long)blockIdx.y * a.R + myrow) * a.Dp + 32 * g);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) dst[i] = make_float4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
                 }
+            } else {
+                float w[16];
+                if (n_tiles > 0) tmem_ld16(tmem_acc + 16 * g + lane_addr, w);
+                else
+                    for (int i = 0; i < 16; ++i) w[i] = 0.f;
+                if (my_ok) {
+                    float4* dst = reinterpret_cast<float4*>(a.out_part + ((long long)blockIdx.y * a.R + myrow) * a.Dp + 16 * g);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) dst[i] = make_float4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+                }
             }
             tc_fence_before();
-        } else if (MODE == SIM_TOPK && RB == 2) {
+        }
+    } else {
+        // ===================== scores / top-k epilogue: 8 warps; thread <-> TMEM lane <-> row ======================
+        const int half = (warp - 2) >> 2;              // columns [64*half, 64*half+64) of every tile
+        const int q = warp & 3;                        // TMEM lane quadrant this warp may access
+        const int r_loc = 32 * q + lane;
+        const uint32_t lane_addr = (uint32_t)(32 * q) << 16;
+        const long long list = (long long)blockIdx.y * 2 + half;
+        if (MODE == SIM_TOPK && RB == 2) {
             // one candidate stream per row: warp group `half` owns row block `half` and walks both column halves
             const int rbo = half;
             const long long list0 = (long long)blockIdx.y * 2;
@@ -431,116 +511,52 @@ simtile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
             a.cand_thr[slot] = mythr;
             a.cand_cnt[(list0 + 1) * a.Rpad + myrow] = 0;          // the second list of this chunk stays empty
             a.cand_thr[(list0 + 1) * a.Rpad + myrow] = -INFINITY;
-        } else
-        for (int t = 0; t < n_tiles; ++t) {
-            const int b = t & 1;
-            const int j0 = (tile0 + t) * ST_N + 64 * half;
-            float* ry = sm_ry + b * ST_N + 64 * half;
-            if (grad) {
-                mbar_wait(g_empty + b, ((t >> 1) & 1) ^ 1);            // G[b] no longer read by GEMM 2 of tile t-2
-                if (r_loc < 64) ry[r_loc] = (j0 + r_loc < a.C) ? a.alpha / a.rowsum_y[j0 + r_loc] : 0.f;
-                named_bar_sync(1 + half, 128);
-            }
+        } else {
+            // per 128-row block state (RB <= 2)
+            long long row[RB];
+            bool row_ok[RB];
+            float thr[RB];
+            int cnt[RB];
 #pragma unroll
             for (int rb = 0; rb < RB; ++rb) {
-                mbar_wait(s_full + rb * 2 + b, (t >> 1) & 1);
-                tc_fence_after();
-                float v[64];
-                tmem_ld64(tmem_s0 + (rb * 2 + b) * ST_N + 64 * half + lane_addr, v);
-                const long long dcol = row[rb] + a.diag_offset;    // column of this row's positive pair
-                if (MODE == SIM_SCORES) {
-                    if (row_ok[rb])
-                        for (int i = 0; i < 64; ++i)
-                            if (j0 + i < a.C) a.out_part[row[rb] * a.C + j0 + i] = v[i];
-                } else if (MODE == SIM_TOPK) {
-                    // (handled by the dedicated loop below for RB == 2)
-                    if (j0 + 64 > a.C) {                             // ragged last tile: columns past C never qualify
+                row[rb] = (long long)row0 + rb * ST_M + r_loc;
+                row_ok[rb] = row[rb] < a.R;
+                thr[rb] = row_ok[rb] ? -INFINITY : INFINITY;       // rows past R admit nothing
+                cnt[rb] = 0;
+            }
+            for (int t = 0; t < n_tiles; ++t) {
+                const int b = t & 1;
+                const int j0 = (tile0 + t) * ST_N + 64 * half;
 #pragma unroll
-                        for (int i = 0; i < 64; ++i)
-                            if (j0 + i >= a.C) v[i] = -INFINITY;
-                    }
-                    topk_admit(a, v, j0, list, row0 + rb * ST_M, q, lane, row[rb], thr[rb], cnt[rb]);
-                } else if (MODE == SIM_ROWSUM) {
-                    if (j0 + 64 <= a.C) {
-#pragma unroll
-                        for (int i = 0; i < 64; ++i) racc[rb][i & 3] += ex2_approx(fmaf(v[i], a.c1, -a.c2));
+                for (int rb = 0; rb < RB; ++rb) {
+                    mbar_wait(s_full + rb * 2 + b, (t >> 1) & 1);
+                    tc_fence_after();
+                    float v[64];
+                    tmem_ld64(tmem_s0 + (rb * 2 + b) * ST_N + 64 * half + lane_addr, v);
+                    if (MODE == SIM_SCORES) {
+                        if (row_ok[rb])
+                            for (int i = 0; i < 64; ++i)
+                                if (j0 + i < a.C) a.out_part[row[rb] * a.C + j0 + i] = v[i];
                     } else {
+                        if (j0 + 64 > a.C) {                             // ragged last tile: columns past C never qualify
 #pragma unroll
-                        for (int i = 0; i < 64; ++i)
-                            racc[rb][i & 3] += (j0 + i < a.C) ? ex2_approx(fmaf(v[i], a.c1, -a.c2)) : 0.f;
-                    }
-                    if (dcol >= j0 && dcol < j0 + 64) {
-#pragma unroll
-                        for (int i = 0; i < 64; ++i)
-                            if (j0 + i == dcol) dval[rb] = v[i];
-                        have_diag[rb] = true;
-                    }
-                } else {
-                    // the positive pair (column row + diag_offset) is left out of the bf16 G tile: its weight is
-                    // O(1/B) while every other entry is O(1/B^2), so it is added in fp32 by the finalize kernel
-                    const bool edge = j0 + 64 > a.C || (dcol >= j0 && dcol < j0 + 64);
-                    uint32_t packed[32];
-#pragma unroll
-                    for (int i = 0; i < 64; i += 2) {
-                        float g0 = ex2_approx(fmaf(v[i], a.c1, -a.c2)) * (rx + ry[i]);
-                        float g1 = ex2_approx(fmaf(v[i + 1], a.c1, -a.c2)) * (rx + ry[i + 1]);
-                        if (edge) {
-                            if (j0 + i >= a.C || j0 + i == dcol) g0 = 0.f;
-                            if (j0 + i + 1 >= a.C || j0 + i + 1 == dcol) g1 = 0.f;
+                            for (int i = 0; i < 64; ++i)
+                                if (j0 + i >= a.C) v[i] = -INFINITY;
                         }
-                        __nv_bfloat162 h2 = __floats2bfloat162_rn(g0, g1);
-                        packed[i >> 1] = *reinterpret_cast<uint32_t*>(&h2);
+                        topk_admit(a, v, j0, list, row0 + rb * ST_M, q, lane, row[rb], thr[rb], cnt[rb]);
                     }
-                    // G[b] is the K-major SW128 A operand of GEMM 2; this half fills k-block `half` of row r_loc
-                    uint8_t* grow = Gs + (b * 2 + half) * KB_BYTES + r_loc * 128;
-#pragma unroll
-                    for (int h8 = 0; h8 < 8; ++h8) {
-                        uint4 val = make_uint4(packed[4 * h8], packed[4 * h8 + 1], packed[4 * h8 + 2], packed[4 * h8 + 3]);
-                        *reinterpret_cast<uint4*>(grow + ((h8 ^ (r_loc & 7)) << 4)) = val;
-                    }
-                }
-                tc_fence_before();
-                if (grad) {
-                    fence_proxy_async();               // generic-proxy smem writes -> visible to the tensor core
-                    mbar_arrive(g_full + b);
-                }
-                mbar_arrive(s_empty + rb * 2 + b);
-            }
-        }
-        if (MODE == SIM_TOPK && RB == 1) {
-#pragma unroll
-            for (int rb = 0; rb < RB; ++rb) {
-                const long long slot = list * a.Rpad + row[rb];
-                a.cand_cnt[slot] = row_ok[rb] ? cnt[rb] : 0;
-                a.cand_thr[slot] = thr[rb];
-            }
-        } else if (MODE == SIM_ROWSUM) {
-#pragma unroll
-            for (int rb = 0; rb < RB; ++rb) {
-                if (row_ok[rb]) {
-                    a.out_part[list * a.R + row[rb]] = (racc[rb][0] + racc[rb][1]) + (racc[rb][2] + racc[rb][3]);
-                    if (a.diag && have_diag[rb]) a.diag[row[rb]] = dval[rb];
+                    tc_fence_before();
+                    mbar_arrive(s_empty + rb * 2 + b);
                 }
             }
-        } else if (grad && !GRAD2) {
-            if (n_tiles > 0) {
-                mbar_wait(acc_full, 0);
-                tc_fence_after();
-            }
-            const int cols_half = a.Dp / 2;             // this half drains columns [half*Dp/2, (half+1)*Dp/2) of dX
-            for (int c = 0; c < cols_half / 32; ++c) {
-                float w[32];
-                const int c0 = half * cols_half + c * 32;
-                if (n_tiles > 0) tmem_ld32(tmem_acc + c0 + lane_addr, w);
-                else
-                    for (int i = 0; i < 32; ++i) w[i] = 0.f;
-                if (row_ok[0]) {
-                    float4* dst = reinterpret_cast<float4*>(a.out_part + ((long long)blockIdx.y * a.R + row[0]) * a.Dp + c0);
+            if (MODE == SIM_TOPK) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) dst[i] = make_float4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+                for (int rb = 0; rb < RB; ++rb) {
+                    const long long slot = list * a.Rpad + row[rb];
+                    a.cand_cnt[slot] = row_ok[rb] ? cnt[rb] : 0;
+                    a.cand_thr[slot] = thr[rb];
                 }
             }
-            tc_fence_before();
         }
     }
     __syncthreads();
@@ -700,7 +716,6 @@ static int launch_sim(SimArgs a, const void* x, const void* y, int chunks, cudaS
         case SIM_ROWSUM * 2: fn = simtile_kernel<SIM_ROWSUM, 1>; break;
         case SIM_ROWSUM * 2 + 1: fn = simtile_kernel<SIM_ROWSUM, 2>; break;
         case SIM_GRAD * 2: fn = simtile_kernel<SIM_GRAD, 1>; break;
-        case SIM_GRAD * 2 + 1: fn = simtile_kernel<SIM_GRAD, 2>; break;
         case SIM_TOPK * 2: fn = simtile_kernel<SIM_TOPK, 1>; break;
         case SIM_TOPK * 2 + 1: fn = simtile_kernel<SIM_TOPK, 2>; break;
         default: set_error("unsupported similarity-kernel variant"); return CFM_ERR_UNSUPPORTED;
@@ -711,7 +726,7 @@ static int launch_sim(SimArgs a, const void* x, const void* y, int chunks, cudaS
         attr[a.mode * 2 + (a.rb - 1)] = true;
     }
     dim3 grid((a.R + a.rb * ST_M - 1) / (a.rb * ST_M), chunks);
-    fn<<<grid, ST_THREADS, L.total, stream>>>(tmx, tmy, a);
+    fn<<<grid, sim_threads(a.mode), L.total, stream>>>(tmx, tmy, a);
     CFM_LAUNCH_CHECK();
     return CFM_OK;
 }
@@ -723,6 +738,7 @@ using namespace cfm;
 // partial result lists per row: column chunks x the two column halves the epilogue warp groups own
 // 128-row blocks per CTA: two blocks share every Y tile (half the L2->SM operand traffic) once there are enough
 // rows to fill the GPU twice over
+static int g_poly_mask = 0;     // bit 0: row sums, bit 1: gradients take a quarter of their exponentials as polynomials
 static int g_force_rb = 0;      // 0 = automatic; 1 / 2 pin the variant (parity tests exercise both on small inputs)
 static int sim_rb(long long R) {
     if (g_force_rb == 1 || g_force_rb == 2) return g_force_rb;
@@ -732,6 +748,11 @@ static int sim_rb(long long R) {
 extern "C" int cfm_simtile_set_rb(int64_t rb) {
     CFM_REQUIRE(rb >= 0 && rb <= 2, CFM_ERR_INVALID, "rb must be 0 (auto), 1 or 2");
     g_force_rb = (int)rb;
+    return CFM_OK;
+}
+
+extern "C" int cfm_simtile_set_poly(int64_t mask) {
+    g_poly_mask = (int)mask & 3;
     return CFM_OK;
 }
 
@@ -779,6 +800,7 @@ extern "C" int cfm_infonce_rowsum(const void* x_bf16, const void* y_bf16, int64_
     a.mode = SIM_ROWSUM; a.R = (int)R; a.C = (int)C; a.D = (int)Dp; a.Dp = (int)Dp;
     a.c1 = (float)(LOG2E / temperature); a.c2 = (float)(LOG2E / temperature);
     a.diag_offset = diag_offset; a.out_part = part; a.diag = diag;
+    a.poly = (g_poly_mask & 1) && 2.f * a.c1 <= 120.f;      // exponents stay inside the normal range of ex2_poly
     ProfScope prof(PROF_NCE_ROWSUM, stream);
     int rc = launch_sim(a, x_bf16, y_bf16, chunks, stream);
     if (rc) return rc;
@@ -794,9 +816,8 @@ extern "C" int cfm_infonce_grad(const void* x_bf16, const void* y_bf16, int64_t 
     cudaStream_t stream = (cudaStream_t)stream_;
     CFM_REQUIRE(x_bf16 && y_bf16 && rowsum_x && rowsum_y && diag && dx && part && temperature > 0 && B_total >= 1 && D <= Dp,
                 CFM_ERR_INVALID, "bad grad arguments");
-    // two-row-block ping-pong exists (forced with cfm_simtile_set_rb(2)) but measured slower than one block per
-    // CTA on B200: the SS-mode operand fetch of four GEMMs per Y tile saturates shared-memory bandwidth
-    const int rb = g_force_rb == 2 ? 2 : 1;
+    // one row block per CTA: with two, the SS-mode operand fetch of four GEMMs per Y tile saturates shared memory
+    const int rb = 1;
     const int chunks = sim_chunks(R, C, rb);
     SimArgs a{};
     a.rb = rb;
@@ -804,6 +825,7 @@ extern "C" int cfm_infonce_grad(const void* x_bf16, const void* y_bf16, int64_t 
     a.c1 = (float)(LOG2E / temperature); a.c2 = (float)(LOG2E / temperature);
     a.alpha = (float)(1.0 / (2.0 * (double)B_total * temperature));
     a.diag_offset = diag_offset; a.rowsum_x = rowsum_x; a.rowsum_y = rowsum_y; a.out_part = part;
+    a.poly = (g_poly_mask & 2) && 2.f * a.c1 <= 120.f;
     ProfScope prof(PROF_NCE_GRAD, stream);
     int rc = launch_sim(a, x_bf16, y_bf16, chunks, stream);
     if (rc) return rc;

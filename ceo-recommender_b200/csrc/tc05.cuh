@@ -99,7 +99,8 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, bool a_mn_m
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// 32 consecutive fp32 columns of this thread's TMEM lane
+// 32 consecutive fp32 columns of this thread's TMEM lane (WAIT = false: the caller issues tmem_ld_wait() later)
+template <bool WAIT = true>
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     uint32_t r[32];
     asm volatile(
@@ -112,7 +113,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr)
         : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (WAIT) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
@@ -156,11 +157,91 @@ __device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
     for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// Pins 32 values behind the preceding volatile statements (a tmem_ld_wait): arithmetic on the results of an
+// un-waited TMEM load must not be scheduled above the wait.
+__device__ __forceinline__ void reg_fence32(float (&v)[32]) {
+    asm volatile("" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]),
+                      "+f"(v[8]), "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15]),
+                      "+f"(v[16]), "+f"(v[17]), "+f"(v[18]), "+f"(v[19]), "+f"(v[20]), "+f"(v[21]), "+f"(v[22]), "+f"(v[23]),
+                      "+f"(v[24]), "+f"(v[25]), "+f"(v[26]), "+f"(v[27]), "+f"(v[28]), "+f"(v[29]), "+f"(v[30]), "+f"(v[31])
+                 :: "memory");
+}
+// Streams the 128 fp32 columns of this thread's TMEM lane through registers in four 32-column pieces: piece k + 1 is
+// in flight while f(k, piece) runs; released() is called as soon as the last piece has landed (the accumulator
+// buffer may be handed back to the MMA issuer while the last piece is still being worked on).
+template <class F, class R>
+__device__ __forceinline__ void tmem_stream128(uint32_t taddr, F&& f, R&& released) {
+    float va[32], vb[32];
+    tmem_ld32<false>(taddr, va);
+    tmem_ld_wait(); reg_fence32(va);
+    tmem_ld32<false>(taddr + 32, vb);
+    f(0, va);
+    tmem_ld_wait(); reg_fence32(vb);
+    tmem_ld32<false>(taddr + 64, va);
+    f(1, vb);
+    tmem_ld_wait(); reg_fence32(va);
+    tmem_ld32<false>(taddr + 96, vb);
+    f(2, va);
+    tmem_ld_wait(); reg_fence32(vb);
+    released();
+    f(3, vb);
+}
 // 2^x on the SFU (MUFU.EX2), flush-to-zero: one instruction, no denormal fix-up
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+}
+
+// 2^x on the FMA/ALU pipes for x in [-125, 0]: round-to-nearest split x = n + f (f in [-0.5, 0.5]) through the
+// 1.5*2^23 magic constant, degree-4 minimax polynomial for 2^f (relative error 2.7e-6), n added into the exponent
+// field.  Used for a fixed quarter of the exponentials of the similarity epilogues, which are otherwise bound by the
+// 16/clk/SM MUFU pipe.
+__device__ __forceinline__ float ex2_poly(float x) {
+    const float t = x + 12582912.f;
+    const float f = x - (t - 12582912.f);
+    float p = fmaf(f, 0.00957009382545948f, 0.05591785907745361f);
+    p = fmaf(p, f, 0.240247443318367f);
+    p = fmaf(p, f, 0.6931217908859253f);
+    p = fmaf(p, f, 0.9999992847442627f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+// 16 exponentials e[i] = 2^(v[i] * c1 - c2), written phase by phase so that the instruction stream carries the
+// parallelism itself (ptxas keeps source order under register pressure: an element-at-a-time loop becomes one long
+// dependent chain).  POLY: elements 3, 7, 11, 15 take the polynomial, four chains interleaved with the twelve MUFUs.
+template <bool POLY>
+__device__ __forceinline__ void exp16(const float* v, float c1, float c2, float (&e)[16]) {
+    float x[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) x[i] = fmaf(v[i], c1, -c2);
+    if (!POLY) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) e[i] = ex2_approx(x[i]);
+        return;
+    }
+    float t[4], f[4], p[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) t[k] = x[4 * k + 3] + 12582912.f;
+    e[0] = ex2_approx(x[0]); e[1] = ex2_approx(x[1]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) f[k] = t[k] - 12582912.f;
+    e[2] = ex2_approx(x[2]); e[4] = ex2_approx(x[4]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) f[k] = x[4 * k + 3] - f[k];
+    e[5] = ex2_approx(x[5]); e[6] = ex2_approx(x[6]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) p[k] = fmaf(f[k], 0.00957009382545948f, 0.05591785907745361f);
+    e[8] = ex2_approx(x[8]); e[9] = ex2_approx(x[9]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) p[k] = fmaf(p[k], f[k], 0.240247443318367f);
+    e[10] = ex2_approx(x[10]); e[12] = ex2_approx(x[12]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) p[k] = fmaf(p[k], f[k], 0.6931217908859253f);
+    e[13] = ex2_approx(x[13]); e[14] = ex2_approx(x[14]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) p[k] = fmaf(p[k], f[k], 0.9999992847442627f);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) e[4 * k + 3] = __int_as_float(__float_as_int(p[k]) + (__float_as_int(t[k]) << 23));
 }
 
 // Shared-memory matrix descriptors (sm_100 format: version 1 at bit 46, layout type at [61,64), SWIZZLE_128B = 2).
