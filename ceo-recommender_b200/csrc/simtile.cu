@@ -170,8 +170,12 @@ __device__ __forceinline__ void grad_strip(const float (&v)[N], const float* ry,
         uint32_t pk[8];
 #pragma unroll
         for (int i = 0; i < 16; i += 2) {
+#ifdef CFM_EXP_TRUNC
+            pk[i >> 1] = __byte_perm(__float_as_uint(e[i]), __float_as_uint(e[i + 1]), 0x7632);
+#else
             __nv_bfloat162 h2 = __floats2bfloat162_rn(e[i], e[i + 1]);
             pk[i >> 1] = *reinterpret_cast<uint32_t*>(&h2);
+#endif
         }
         store16(i0 / 8, make_uint4(pk[0], pk[1], pk[2], pk[3]));
         store16(i0 / 8 + 1, make_uint4(pk[4], pk[5], pk[6], pk[7]));
@@ -217,7 +221,7 @@ template <int MODE, int RB>
 __global__ void __launch_bounds__(sim_threads(MODE), 1)
 simtile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_y, const SimArgs a) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic on the __shared__ array: accesses compile to LDS/STS (a uintptr_t round trip makes them generic LD/ST)
     const SimSmem L = sim_smem(a.Dp, MODE, RB);
     const int nkb = a.Dp / ST_KB;
     uint8_t* Xs = sm + L.x;

@@ -1074,6 +1074,7 @@ extern "C" int cfm_towers_fwd(const cfm_tower_t* towers, int64_t n_towers, int64
         // 16 warps while one tower's CTAs run (both towers' grids are otherwise resident one after the other)
         const bool two = smem > 76 * 1024 && smem <= 113 * 1024;
         int ctas = (int)std::min<long long>(ntiles, two ? tower_ctas(32) : tower_ctas(64));
+        int ctas_t[2] = {ctas, ctas};                    // per-tower CTA (= partial) counts
         for (int i = 0; i < n_towers; ++i) {
             const cfm_tower_t& t = towers[i];
             FwdStage& S = a.st[i];
@@ -1092,7 +1093,7 @@ extern "C" int cfm_towers_fwd(const cfm_tower_t* towers, int64_t n_towers, int64
         }
         if (use_tc[s]) {
             ProfScope prof(PROF_FWD1 + s - 1, stream);
-            int rc = tc_fwd_launch(a, towers, (int)n_towers, s, &ctas, stream);
+            int rc = tc_fwd_launch(a, towers, (int)n_towers, s, ctas_t, stream);   // the towers share the SMs side by side
             if (rc) return rc;
         } else {
             ProfScope prof(PROF_FWD1 + s - 1, stream);
@@ -1106,7 +1107,7 @@ extern "C" int cfm_towers_fwd(const cfm_tower_t* towers, int64_t n_towers, int64
                 const cfm_tower_t& t = towers[i];
                 bool bn_after = s == 1 || (s == 2 && t.bn2);
                 BnFwdFin& F = f.t[i];
-                F.part = misc_region(t); F.nparts = ctas; F.N = bn_after ? stage_N(t, s) : 0;
+                F.part = misc_region(t); F.nparts = ctas_t[i]; F.N = bn_after ? stage_N(t, s) : 0;
                 F.stat = s == 1 ? t.bn1_stat : t.bn2_stat;
                 F.rm = s == 1 ? t.bn1_rm : t.bn2_rm;
                 F.rv = s == 1 ? t.bn1_rv : t.bn2_rv;
@@ -1185,6 +1186,7 @@ extern "C" int cfm_towers_bwd(const cfm_tower_t* towers, const cfm_tower_grads_t
         if (use_tc) a.tm = 64;
         const long long ntiles = (B + a.tm - 1) / a.tm;
         int ctas = (int)std::min<long long>(ntiles, use_tc ? sm_count() : tower_ctas(a.tm));
+        int ctas_t[2] = {ctas, ctas};                    // per-tower CTA (= partial) counts
         smem = 0;
         for (int i = 0; i < n_towers; ++i) {
             const cfm_tower_t& t = towers[i];
@@ -1229,7 +1231,7 @@ extern "C" int cfm_towers_bwd(const cfm_tower_t* towers, const cfm_tower_grads_t
         int rc;
         {
             ProfScope prof(PROF_BWD1 + s - 1, stream);
-            if (use_tc) { int c2 = ctas; rc = tc_bwd_launch(a, towers, (int)n_towers, s, &c2, stream); }
+            if (use_tc) rc = tc_bwd_launch(a, towers, (int)n_towers, s, ctas_t, stream);      // the towers share the SMs side by side
             else rc = launch_bwd(a, ctas, (int)n_towers, smem, towers[0].precision == 0, stream);
         }
         if (rc) return rc;
@@ -1242,7 +1244,7 @@ extern "C" int cfm_towers_bwd(const cfm_tower_t* towers, const cfm_tower_grads_t
                 const cfm_tower_t& t = towers[i];
                 const cfm_tower_grads_t& g = grads[i];
                 ReduceW& R = r.t[i];
-                R.part = dw_region(t, s); R.nparts = ctas; R.N = a.st[i].N; R.K = a.st[i].in.K;
+                R.part = dw_region(t, s); R.nparts = ctas_t[i]; R.N = a.st[i].N; R.K = a.st[i].in.K;
                 R.dW = s == 1 ? g.dw1 : s == 2 ? g.dw2 : g.dw3;
                 R.db = s == 1 ? g.db1 : s == 2 ? g.db2 : g.db3;
             }
@@ -1265,7 +1267,7 @@ extern "C" int cfm_towers_bwd(const cfm_tower_t* towers, const cfm_tower_grads_t
                 const cfm_tower_grads_t& g = grads[i];
                 const BwdStage& S = a.st[i];
                 BnBwdFin& F = f.t[i];
-                F.part = S.sum_part; F.nparts = ctas; F.K = S.a_bn ? S.in.K : 0; F.B = (float)B;
+                F.part = S.sum_part; F.nparts = ctas_t[i]; F.K = S.a_bn ? S.in.K : 0; F.B = (float)B;
                 F.dgamma = s == 3 ? g.dbn2_w : g.dbn1_w;
                 F.dbeta = s == 3 ? g.dbn2_b : g.dbn1_b;
                 F.stat = s == 3 ? t.bn2_stat : t.bn1_stat;

@@ -57,7 +57,7 @@ __device__ __forceinline__ unsigned long long gtime() {
     return t;
 }
 __device__ __forceinline__ void trace(int slot, int code) {
-    if (g_trace && g_trace_code == code) g_trace[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 128 + slot] = gtime();
+    if (g_trace && g_trace_code == code) g_trace[(size_t)blockIdx.x * 128 + slot] = gtime();
 }
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void sts4(uint8_t* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
@@ -313,9 +313,13 @@ __host__ __device__ inline TcFwdSmem tcf_smem(int K, int N) {
 
 template <int NC, bool STAGE1>
 __global__ void __launch_bounds__(TC_THREADS, 1) tower_fwd_tc(const __grid_constant__ FwdArgs args) {
-    const FwdStage& S = args.st[blockIdx.y];
+    // the towers share the SMs side by side: CTAs [0, cta_split) belong to tower 0, the others to tower 1
+    const int tower = (int)blockIdx.x >= args.cta_split;
+    const int cta = tower ? (int)blockIdx.x - args.cta_split : (int)blockIdx.x;
+    const int nctas = tower ? (int)gridDim.x - args.cta_split : args.cta_split;
+    const FwdStage& S = args.st[tower];
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic on the __shared__ array: accesses compile to LDS/STS (a uintptr_t round trip makes them generic LD/ST)
     const int K = S.in.K, N = S.N, npad = tc_npad(N), nch = tc_nch(K), Kp = (K + 3) & ~3;
     const TcFwdSmem L = tcf_smem(K, N);
     const int nst = L.nst;
@@ -330,7 +334,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tower_fwd_tc(const __grid_const
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long B = args.B;
     const long long ntiles = (B + TCF_M - 1) / TCF_M;
-    const int my_tiles = (long long)blockIdx.x < ntiles ? (int)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+    const int my_tiles = (long long)cta < ntiles ? (int)((ntiles - cta + nctas - 1) / nctas) : 0;
     const bool exact = args.exact != 0;
     const bool stats = S.stat_part != nullptr;
     const int chunk_bytes = tc_w_chunk_floats(N) * 4;
@@ -409,7 +413,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tower_fwd_tc(const __grid_const
         bool have_piv = false;
         float* piv = sm_piv + q * 64;
         for (int it = 0; it < my_tiles; ++it) {
-            const long long row0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * TCF_M;
+            const long long row0 = ((long long)cta + (long long)it * nctas) * TCF_M;
             const int rows_valid = (int)min((long long)TCF_M, B - row0);
             const int buf = it & 1;
             const int r = 32 * q + lane;
@@ -482,7 +486,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tower_fwd_tc(const __grid_const
             }
             if (lane == 0) ws[128] = cntw;
             named_bar_sync(1, TC_EPI_WARPS * 32);
-            float* P = S.stat_part + (size_t)blockIdx.x * (2 * N + 4);
+            float* P = S.stat_part + (size_t)cta * (2 * N + 4);
             const int c = tid;
             if (c < N) {
                 float n = 0.f, mean = 0.f, m2 = 0.f;
@@ -511,7 +515,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tower_fwd_tc(const __grid_const
         uint8_t* ring = sm + L.ring;
         const GatherSrc& g = S.in.g;
         constexpr int NX = TCF_M / 32;
-        auto tile_row0 = [&](int it) { return ((long long)blockIdx.x + (long long)it * gridDim.x) * TCF_M; };
+        auto tile_row0 = [&](int it) { return ((long long)cta + (long long)it * nctas) * TCF_M; };
         auto issue_idx = [&](const ChunkPos& p, long long (&ix)[NX]) {
 #pragma unroll
             for (int i = 0; i < NX; ++i) ix[i] = 0;
@@ -631,9 +635,12 @@ __host__ __device__ inline uint32_t tcb_tmem_cols(int K) {
 
 template <bool STAGE1, int CW>
 __global__ void __launch_bounds__(TC_THREADS, 1) tower_bwd_tc(const __grid_constant__ BwdArgs args) {
-    const BwdStage& S = args.st[blockIdx.y];
+    const int tower = (int)blockIdx.x >= args.cta_split;       // see tower_fwd_tc
+    const int cta = tower ? (int)blockIdx.x - args.cta_split : (int)blockIdx.x;
+    const int nctas = tower ? (int)gridDim.x - args.cta_split : args.cta_split;
+    const BwdStage& S = args.st[tower];
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic on the __shared__ array: accesses compile to LDS/STS (a uintptr_t round trip makes them generic LD/ST)
     const int K = S.in.K, N = S.N, npad = tc_npad(N), nbn = tc_nblk(N), nch = tcb_nch(K);
     const int Kp = (K + 3) & ~3, Np = (N + 3) & ~3;
     const bool a_bn = S.a_bn != 0, need_dx = S.need_dx != 0;
@@ -655,7 +662,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tower_bwd_tc(const __grid_const
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long B = args.B;
     const long long ntiles = (B + TCB_M - 1) / TCB_M;
-    const int my_tiles = (long long)blockIdx.x < ntiles ? (int)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+    const int my_tiles = (long long)cta < ntiles ? (int)((ntiles - cta + nctas - 1) / nctas) : 0;
     const bool exact = args.exact != 0;
     const int tcode = 10 + S.in.stage;
     const uint32_t tmem_cols = tcb_tmem_cols(K);
@@ -758,7 +765,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tower_bwd_tc(const __grid_const
         float s1[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, s2[2][2] = {{0.f, 0.f}, {0.f, 0.f}};   // [32-column half][owned column] (stage > 1: K <= 64)
         uint32_t cnt = 0;
         for (int it = 0; it < my_tiles; ++it) {
-            const long long row0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * TCB_M;
+            const long long row0 = ((long long)cta + (long long)it * nctas) * TCB_M;
             const long long row = row0 + 16 * q + lane;
             const bool valid = act && row < B;
             const int rl = 16 * q + (lane & 15);
@@ -848,7 +855,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tower_bwd_tc(const __grid_const
                     }
             }
             named_bar_sync(1, TC_EPI_WARPS * 32);
-            float* P = S.sum_part + (size_t)blockIdx.x * 2 * K;
+            float* P = S.sum_part + (size_t)cta * 2 * K;
             if (tid < 2 * K) {
                 const int which = tid >= K, c = tid - which * K;
                 float t = 0.f;
@@ -859,7 +866,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tower_bwd_tc(const __grid_const
         }
         // ---- weight-gradient partial of this CTA: TMEM [64 n][K (+ bias column)] -> global, layer column order ----
         {
-            float* P = S.dW_part + (size_t)blockIdx.x * N * (K + 1);
+            float* P = S.dW_part + (size_t)cta * N * (K + 1);
             const int n = 16 * q + lane;
             if (my_tiles > 0) {
                 mbar_wait(dw_full, 0);
@@ -902,24 +909,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tower_bwd_tc(const __grid_const
         const float inv_keep = (!STAGE1 && S.in.a.drop.active) ? S.in.a.drop.inv_keep : 1.f;
         constexpr int NXR = CW / (4 * QS);                    // quads per thread and chunk
         constexpr int NX = NXR;
-        auto tile_row0 = [&](int it) { return ((long long)blockIdx.x + (long long)it * gridDim.x) * TCB_M; };
+        auto tile_row0 = [&](int it) { return ((long long)cta + (long long)it * nctas) * TCB_M; };
 
         // G and G^T of tile `it`, built by the group that owns the tile's first chunk.  g = incoming gradient, through
         // the BatchNorm backward of this layer's output when there is one.
         const int qpr = npad >> 2;                            // quads per G row (<= 16)
-        auto build_g = [&](int it) {
+        // The incoming-gradient quads of a tile are requested one tile ahead (right after the previous G was staged), so
+        // that build_g finds them in registers instead of waiting an HBM round trip per tile.
+        constexpr int GQ = 16 / QS;                           // at most 16 quads per G row
+        float4 gq[GQ], hq[GQ];
+        auto issue_g = [&](int it) {
             const long long row = tile_row0(it) + r;
-            constexpr int GQ = 16 / QS;                         // at most 16 quads per G row
-            float4 gq[GQ], hq[GQ];
 #pragma unroll
             for (int u = 0; u < GQ; ++u) {
                 const int c0 = 4 * (qb + QS * u);
                 gq[u] = make_float4(0.f, 0.f, 0.f, 0.f); hq[u] = gq[u];
-                if (row < B && c0 < N) {
+                if (it < my_tiles && row < B && c0 < N) {
                     gq[u] = ldg4(S.gin + (size_t)row * N + c0);
                     if (S.g_mode == 1) hq[u] = ldg4(S.hs + (size_t)row * N + c0);
                 }
             }
+        };
+        auto build_g = [&](int it) {
+            const long long row = tile_row0(it) + r;
 #pragma unroll
             for (int u = 0; u < GQ; ++u) {
                 const int c0 = 4 * (qb + QS * u);
@@ -964,7 +976,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tower_bwd_tc(const __grid_const
             fence_proxy_async();
             mbar_arrive(g_full);
             if (gtid == 0 && it < 6) trace(83 + 4 * it, tcode);
+            issue_g(it + 1);
         };
+        issue_g(0);
 
         uint8_t* raw = sm + L.raw;
         auto stash_block = [&](const ChunkPos& p) {
@@ -1133,6 +1147,19 @@ int tc_prep_launch(const cfm_tower_t* towers, int n_towers, cudaStream_t stream)
     return CFM_OK;
 }
 
+// Shares the SMs between the towers in proportion to their work per tile (chunks of the stage + a fixed part for the
+// G / statistics / epilogue work every tile carries), at most one CTA per tile; returns the per-tower CTA counts.
+static void tc_split_ctas(const int (&nch)[2], int n_towers, long long ntiles, int (&ctas)[2]) {
+    const int sms = sm_count();
+    ctas[0] = ctas[1] = 0;
+    if (n_towers == 1) { ctas[0] = (int)std::min<long long>(ntiles, sms); return; }
+    const double w0 = nch[0] + 1.5, w1 = nch[1] + 1.5;
+    int c0 = (int)(sms * w0 / (w0 + w1) + 0.5);
+    c0 = std::max(1, std::min(sms - 1, c0));
+    ctas[0] = (int)std::min<long long>(ntiles, c0);
+    ctas[1] = (int)std::min<long long>(ntiles, sms - c0);
+}
+
 int tc_fwd_launch(FwdArgs& a, const cfm_tower_t* towers, int n_towers, int s, int* ctas_out, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
@@ -1144,11 +1171,13 @@ int tc_fwd_launch(FwdArgs& a, const cfm_tower_t* towers, int n_towers, int s, in
     }
     size_t smem = 0;
     int nc = 32;
+    int nchs[2] = {1, 1};
     for (int i = 0; i < n_towers; ++i) {
         const cfm_tower_t& t = towers[i];
         int K[3], N[3];
         tower_dims(t, K, N);
         const WImgLayout L = wimg_layout(K, N);
+        nchs[i] = tc_nch(K[s - 1]);
         a.st[i].wimg = t.wimg + L.w[s - 1];
         a.st[i].a_out = s == 2 ? t.a1 : s == 3 ? t.a2 : nullptr;
         a.st[i].x_out = s == 1 ? t.xstash : nullptr;
@@ -1156,9 +1185,11 @@ int tc_fwd_launch(FwdArgs& a, const cfm_tower_t* towers, int n_towers, int s, in
         if (tc_npad(N[s - 1]) > 32) nc = 64;
     }
     const long long ntiles = (a.B + TCF_M - 1) / TCF_M;
-    const int ctas = (int)std::min<long long>(ntiles, sm_count());
-    *ctas_out = ctas;
-    const dim3 grid(ctas, (unsigned)n_towers);
+    int ctas[2];
+    tc_split_ctas(nchs, n_towers, ntiles, ctas);
+    ctas_out[0] = ctas[0]; ctas_out[1] = ctas[1];
+    a.cta_split = ctas[0];
+    const dim3 grid(ctas[0] + ctas[1]);
     if (s == 1) {
         if (nc == 64) tower_fwd_tc<64, true><<<grid, TC_THREADS, smem, stream>>>(a);
         else tower_fwd_tc<32, true><<<grid, TC_THREADS, smem, stream>>>(a);
@@ -1180,20 +1211,24 @@ int tc_bwd_launch(BwdArgs& a, const cfm_tower_t* towers, int n_towers, int s, in
         attr_set = true;
     }
     size_t smem = 0;
+    int nchs[2] = {1, 1};
     for (int i = 0; i < n_towers; ++i) {
         const cfm_tower_t& t = towers[i];
         int K[3], N[3];
         tower_dims(t, K, N);
         const WImgLayout L = wimg_layout(K, N);
+        nchs[i] = tcb_nch(K[s - 1]);
         a.st[i].wtimg = t.wimg + L.wt[s - 1];
         a.st[i].in.a.a_post = s == 2 ? t.a1 : s == 3 ? t.a2 : nullptr;
         a.st[i].x_in = s == 1 ? t.xstash : nullptr;
         smem = std::max(smem, (size_t)tcb_smem(K[s - 1], N[s - 1], s == 1, a.st[i].a_bn != 0, s == 1 && t.xstash).total);
     }
     const long long ntiles = (a.B + TCB_M - 1) / TCB_M;
-    const int ctas = (int)std::min<long long>(ntiles, sm_count());
-    *ctas_out = ctas;
-    const dim3 grid(ctas, (unsigned)n_towers);
+    int ctas[2];
+    tc_split_ctas(nchs, n_towers, ntiles, ctas);
+    ctas_out[0] = ctas[0]; ctas_out[1] = ctas[1];
+    a.cta_split = ctas[0];
+    const dim3 grid(ctas[0] + ctas[1]);
     const int cw = tcb_cw(st_K(towers[0], s));
     if (s == 1) {
         if (cw == 64) tower_bwd_tc<true, 64><<<grid, TC_THREADS, smem, stream>>>(a);

@@ -72,6 +72,7 @@ struct FwdArgs {
     int* err;
     int tm;               // rows per tile: 64 (2 row groups x 4 column groups of warps) or 32 (1 x 8)
     int exact;            // tcgen05 path: 1 = three (hi, lo) passes, 0 = single TF32 pass
+    int cta_split;        // tcgen05 path: 1-D grid, CTAs [0, cta_split) work on tower 0, the rest on tower 1
 };
 
 struct BwdStage {
@@ -97,6 +98,7 @@ struct BwdArgs {
     long long B;
     int tm;               // rows per tile, see FwdArgs
     int exact;            // see FwdArgs
+    int cta_split;        // see FwdArgs
 };
 
 
