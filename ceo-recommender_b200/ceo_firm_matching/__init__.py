@@ -3,7 +3,8 @@
 Drop-in for the reference package's training/scoring surface: ``CEOFirmMatcher``,
 ``StructuralDistillationNet``, ``train_model``, ``train_structural_model``, ``contrastive``
 (``ContrastiveCEOFirmMatcher``, ``info_nce_loss``, ``train_contrastive``, ``compute_retrieval_metrics``),
-``scoring.score_topk`` and the ``cli`` / ``structural_cli`` ``--synthetic`` entry points.  The arithmetic
+``scoring.score_topk``, ``encode.encode`` / ``encode.score_grid`` (the tower encoder for any module with the reference's
+tower layout, batched heat-map scoring) and the ``cli`` / ``structural_cli`` ``--synthetic`` entry points.  The arithmetic
 runs in hand-written sm_100a CUDA kernels (``libcfm_b200.so``) reached through a C ABI
 (``include/cfm_b200.h``); there is no CPU fallback.  Plotting / explainability / WRDS modules of the
 reference are out of scope.

@@ -76,8 +76,9 @@ def score_topk(rows: torch.Tensor, cols: torch.Tensor, k: int, scale: float = 1.
     # |16-bit-operand score - exact score| <= 2u |row||col| (Cauchy-Schwarz over the per-element roundings, u = 2^-11
     # or 2^-8), twice that separates "certainly in" from "certainly out"; the extra covers fp32 accumulation and
     # fp16 subnormals.
-    norm_bound = float(rows.norm(dim=1).max() * cols.norm(dim=1).max())
-    amax = float(torch.maximum(rows.abs().max(), cols.abs().max()))
+    # (one host read for both statistics; the launch parameters below depend on them)
+    norm_bound, amax = torch.stack([rows.norm(dim=1).max() * cols.norm(dim=1).max(),
+                                    torch.maximum(rows.abs().max(), cols.abs().max())]).tolist()
     use_f16 = 1e-2 < amax < 1e3
     if use_f16:
         rb, cb = ops.pack_f16(rows), ops.pack_f16(cols)

@@ -20,6 +20,8 @@ namespace cfm {
 
 constexpr int ST_M = 128, ST_N = 128, ST_KB = 64;      // tile rows / cols, bf16 elements per 128-byte swizzle row
 constexpr int ST_STAGES = 3;
+// Y-tile ring: the gradient kernel keeps four tiles (tiles t .. t+2 are in use by GEMM 1 / GEMM 2, t+3 is in flight)
+__host__ __device__ constexpr int sim_stages(int mode) { return mode == 2 ? 4 : ST_STAGES; }
 // TMA warp, MMA warp, then 16 epilogue warps in the InfoNCE modes (row sums, gradients), 8 otherwise
 __host__ __device__ constexpr int sim_threads(int mode) { return 64 + ((mode == 1 || mode == 2) ? 16 : 8) * 32; }
 constexpr int KB_BYTES = ST_M * 128;                   // one [128 rows x 64 bf16] swizzled block = 16 KB
@@ -170,12 +172,8 @@ __device__ __forceinline__ void grad_strip(const float (&v)[N], const float* ry,
         uint32_t pk[8];
 #pragma unroll
         for (int i = 0; i < 16; i += 2) {
-#ifdef CFM_EXP_TRUNC
-            pk[i >> 1] = __byte_perm(__float_as_uint(e[i]), __float_as_uint(e[i + 1]), 0x7632);
-#else
             __nv_bfloat162 h2 = __floats2bfloat162_rn(e[i], e[i + 1]);
             pk[i >> 1] = *reinterpret_cast<uint32_t*>(&h2);
-#endif
         }
         store16(i0 / 8, make_uint4(pk[0], pk[1], pk[2], pk[3]));
         store16(i0 / 8 + 1, make_uint4(pk[4], pk[5], pk[6], pk[7]));
@@ -208,12 +206,14 @@ __host__ __device__ inline SimSmem sim_smem(int Dp, int mode, int rb) {
     const int nkb = Dp / ST_KB;
     int o = 0;
     s.x = o; o += rb * nkb * KB_BYTES;
-    s.y = o; o += ST_STAGES * nkb * KB_BYTES;
+    s.y = o; o += sim_stages(mode) * nkb * KB_BYTES;
     s.g = o; o += mode == SIM_GRAD ? 2 * 2 * KB_BYTES : 0;
     s.ry = o; o += 4 * ST_N * 4;
     s.bars = o; o += 32 * 8;
     s.tmem_slot = o; o += 16;
-    s.total = o + 1024;           // slack for the manual 1024-byte alignment
+    // slack for the manual 1024-byte alignment; the gradient kernel fills shared memory to the last kilobyte and
+    // instead requires (and checks) that the dynamic region starts 1024-aligned
+    s.total = o + (mode == 2 ? 0 : 1024);
     return s;
 }
 
@@ -223,6 +223,7 @@ simtile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
     extern __shared__ uint8_t smem_raw[];
     uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic on the __shared__ array: accesses compile to LDS/STS (a uintptr_t round trip makes them generic LD/ST)
     const SimSmem L = sim_smem(a.Dp, MODE, RB);
+    if (MODE == SIM_GRAD && sm != smem_raw) __trap();      // no alignment slack in this mode (sim_smem)
     const int nkb = a.Dp / ST_KB;
     uint8_t* Xs = sm + L.x;
     uint8_t* Ys = sm + L.y;
@@ -230,9 +231,9 @@ simtile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
     float* sm_ry = reinterpret_cast<float*>(sm + L.ry);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L.bars);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + L.tmem_slot);
-    uint64_t *x_full = bars + 0, *y_full = bars + 1, *y_empty = bars + 1 + ST_STAGES;
-    uint64_t *s_full = bars + 8, *s_empty = bars + 12;            // [rb * 2 + buffer]
-    uint64_t *g_full = bars + 16, *g_empty = bars + 18, *acc_full = bars + 20;
+    uint64_t *x_full = bars + 0, *y_full = bars + 1, *y_empty = bars + 5;
+    uint64_t *s_full = bars + 9, *s_empty = bars + 13;            // [rb * 2 + buffer]
+    uint64_t *g_full = bars + 17, *g_empty = bars + 19, *acc_full = bars + 21;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row0 = blockIdx.x * RB * ST_M;
@@ -240,7 +241,7 @@ simtile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
     const int n_tiles = max(0, min(a.tiles_per_chunk, a.n_col_tiles - tile0));
     constexpr bool grad = MODE == SIM_GRAD;
     constexpr bool NCE = MODE == SIM_ROWSUM || MODE == SIM_GRAD;      // 16 epilogue warps
-    constexpr int NSTG = ST_STAGES;
+    constexpr int NSTG = sim_stages(MODE);
     // threads that hand an S buffer back: every buffer is drained by two four-warp groups (column halves), except in
     // the top-k variant with two row blocks, where one group walks a whole buffer (one candidate stream per row)
     constexpr int S_DRAIN = (MODE == SIM_TOPK && RB == 2) ? 128 : 256;
@@ -279,45 +280,70 @@ simtile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // The whole warp walks the loops and waits on the barriers (warp-uniform control flow keeps the descriptors in
+        // uniform registers); one elected lane issues the tcgen05 instructions.  Issued from a divergent `lane == 0`
+        // branch every tcgen05.mma cost ~140 cycles - more than the 64 cycles the tensor core needs to execute it.
+        {
             const uint32_t idesc1 = make_idesc(ST_M, ST_N, false, a.f16 != 0);
             const uint32_t idesc2 = make_idesc(ST_M, a.Dp, true);
             const uint32_t xs = smem_u32(Xs), ys = smem_u32(Ys), gs = smem_u32(Gs);
+            const int nks = a.Dp / 16;
             mbar_wait(x_full, 0);
-            for (int t = 0; t <= n_tiles; ++t) {
-                if (t < n_tiles) {                     // GEMM 1: S(rb, b) = X_rb . Y_t^T
-                    const int s = t % NSTG, b = t & 1;
-                    mbar_wait(y_full + s, (t / NSTG) & 1);
-                    const uint32_t yb = ys + s * nkb * KB_BYTES;
-                    for (int rb = 0; rb < RB; ++rb) {
-                        mbar_wait(s_empty + rb * 2 + b, ((t >> 1) & 1) ^ 1);
-                        tc_fence_after();
-                        const uint32_t xb = xs + rb * nkb * KB_BYTES;
-                        for (int ks = 0; ks < a.Dp / 16; ++ks) {
-                            const uint32_t off = (ks >> 2) * KB_BYTES + (ks & 3) * 32;
-                            umma_bf16(tmem_s0 + (rb * 2 + b) * ST_N, desc_kmajor_sw128(xb + off), desc_kmajor_sw128(yb + off),
-                                      idesc1, ks > 0);
+            auto gemm1 = [&](int t) {                  // S(rb, t & 1) = X_rb . Y_t^T
+                const int s = t % NSTG, b = t & 1;
+                mbar_wait(y_full + s, (t / NSTG) & 1);
+                const uint32_t yb = ys + s * nkb * KB_BYTES;
+#pragma unroll
+                for (int rb = 0; rb < RB; ++rb) {
+                    mbar_wait(s_empty + rb * 2 + b, ((t >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t xb = xs + rb * nkb * KB_BYTES;
+                    if (elect_one()) {
+                        const uint64_t dx = desc_kmajor_sw128(xb), dy = desc_kmajor_sw128(yb);
+                        const uint32_t d = tmem_s0 + (rb * 2 + b) * ST_N;
+                        // descriptor start addresses advance in 16-byte units: +2 per 32-byte K step, +KB_BYTES/16
+                        // per 64-column block (constant offsets added to one base descriptor: no per-step rebuild)
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) umma_bf16(d, dx + 2 * ks, dy + 2 * ks, idesc1, ks > 0);
+                        if (nks == 8) {
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks)
+                                umma_bf16(d, dx + KB_BYTES / 16 + 2 * ks, dy + KB_BYTES / 16 + 2 * ks, idesc1, true);
                         }
                         umma_commit(s_full + rb * 2 + b);
+                        if (!grad && rb == RB - 1) umma_commit(y_empty + s);
                     }
-                    if (!grad) umma_commit(y_empty + s);
+                    __syncwarp();
                 }
-                if (grad && t >= 1) {                  // GEMM 2: dX += G_u . Y_u   (u = t - 1)
-                    const int u = t - 1, s = u % NSTG, g = u & 1;
+            };
+            if (!grad) {
+                for (int t = 0; t < n_tiles; ++t) gemm1(t);
+            } else {
+                // GEMM 1 runs two tiles ahead of GEMM 2: S(t+2) is issued as soon as the epilogue has copied S(t) into
+                // registers, so a warp group finds its next tile ready when it hands G(t) over, and dX += G_t . Y_t
+                // executes behind it.
+                for (int t = 0; t < 2 && t < n_tiles; ++t) gemm1(t);
+                for (int u = 0; u < n_tiles; ++u) {
+                    if (u + 2 < n_tiles) gemm1(u + 2);
+                    const int s = u % NSTG, g = u & 1;
                     mbar_wait(g_full + g, (u >> 1) & 1);
                     tc_fence_after();
                     const uint32_t yb = ys + s * nkb * KB_BYTES, gb = gs + g * 2 * KB_BYTES;
-                    for (int ks = 0; ks < ST_N / 16; ++ks) {
-                        const uint32_t aoff = (ks >> 2) * KB_BYTES + (ks & 3) * 32;    // K (= j) inside G, K-major
-                        const uint32_t boff = ks * 16 * 128;                           // 16 rows (j) of Y, MN-major
-                        umma_bf16(tmem_acc, desc_kmajor_sw128(gb + aoff), desc_mnmajor_sw128(yb + boff, KB_BYTES),
-                                  idesc2, u > 0 || ks > 0);
+                    if (elect_one()) {
+                        const uint64_t dg = desc_kmajor_sw128(gb), dyt = desc_mnmajor_sw128(yb, KB_BYTES);
+#pragma unroll
+                        for (int ks = 0; ks < ST_N / 16; ++ks) {
+                            const uint32_t aoff = (ks >> 2) * KB_BYTES + (ks & 3) * 32;    // K (= j) inside G, K-major
+                            const uint32_t boff = ks * 16 * 128;                           // 16 rows (j) of Y, MN-major
+                            umma_bf16(tmem_acc, dg + aoff / 16, dyt + boff / 16, idesc2, u > 0 || ks > 0);
+                        }
+                        umma_commit(g_empty + g);
+                        umma_commit(y_empty + s);
+                        if (u == n_tiles - 1) umma_commit(acc_full);
                     }
-                    umma_commit(g_empty + g);
-                    umma_commit(y_empty + s);
+                    __syncwarp();
                 }
             }
-            if (grad) umma_commit(acc_full);
         }
     } else if constexpr (NCE) {
         // ===================== InfoNCE epilogues: 16 warps = 4 groups of 4 (thread <-> TMEM lane <-> row) ============
