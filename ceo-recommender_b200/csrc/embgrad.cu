@@ -209,7 +209,7 @@ static int seg_reduce_launch(const unsigned long long* keys, const int* vals, lo
     const int grid = (int)std::min<long long>((total + 255) / 256, 148 * 16);
     seg_reduce_chunks<VEC, Acc><<<grid, 256, 0, stream>>>(keys, vals, n, acc, sc.part, sc.flag, sc.starts + base, base);
     CFM_LAUNCH_CHECK();
-    const int grid2 = (int)std::min<long long>((n * 32 + 255) / 256, 148 * 64);
+    const int grid2 = (int)std::min<long long>((n * 32 + 255) / 256, 148 * 8);     // normally a no-op (no long runs): keep its launch cheap
     seg_reduce_long_runs<VEC, Acc><<<grid2, 256, 0, stream>>>(keys, n, acc, sc.part, sc.flag);
     CFM_LAUNCH_CHECK();
     return CFM_OK;
@@ -733,6 +733,25 @@ static int joint_plan(const cfm_emb_group_t* groups, int64_t n_groups, bool need
 
 }  // namespace cfm
 
+namespace cfm {
+// Second stream of the embedding-gradient reduce (one per device): the two towers' segment reductions write disjoint
+// tables and read disjoint key ranges, so the second group runs beside the first; under stream capture the fork / join
+// events become graph edges.
+struct EmbSide { cudaStream_t stream = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+static EmbSide* emb_side() {
+    static EmbSide side[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    EmbSide& S = side[dev];
+    if (!S.stream) {
+        if (cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        cudaEventCreateWithFlags(&S.fork, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&S.join, cudaEventDisableTiming);
+    }
+    return &S;
+}
+}  // namespace cfm
+
 extern "C" int cfm_emb_grad_joint_reduce(const cfm_emb_group_t* groups, int64_t n_groups, int64_t B, int64_t phase,
                                          int64_t* keys_tmp, int32_t* vals_tmp, int64_t* keys_sorted, int32_t* vals_sorted,
                                          void* sort_tmp, int64_t sort_tmp_bytes, void* stream_) {
@@ -763,18 +782,34 @@ extern "C" int cfm_emb_grad_joint_reduce(const cfm_emb_group_t* groups, int64_t 
         if (rc) return rc;
     }
     if (phase == 1) return CFM_OK;
+    // group g > 0 gets its own slice of the partial scratch and its own flag, and runs on the second stream
+    size_t part_off[CFM_MAX_GROUPS + 1] = {0};
+    for (int g = 0; g < n_groups; ++g)
+        part_off[g + 1] = part_off[g] + (size_t)(groups[g].n_tables * B / SEG_CHUNK + 2) * 2 * (size_t)groups[g].emb_dim;
+    EmbSide* side = n_groups == 2 && part_off[n_groups] * sizeof(float) <= seg_part_bytes(n) ? emb_side() : nullptr;
+    if (side) {
+        CFM_CHECK_CUDA(cudaEventRecord(side->fork, stream));
+        CFM_CHECK_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+    }
     for (int g = 0; g < n_groups; ++g) {
         const cfm_emb_group_t& G = groups[g];
         const long long off = (long long)jk.t0[g] * B, ng = G.n_tables * B;
         const unsigned long long* ks = (const unsigned long long*)keys_sorted + off;
+        SegScratch scg = sc;
+        cudaStream_t st = stream;
+        if (side) { scg.part = sc.part + part_off[g]; scg.flag = sc.flag + g; if (g == 1) st = side->stream; }
         if ((G.emb_dim & 3) == 0) {
             DenseAcc<4> acc{G.dx_emb, tps[g], (int)(G.n_tables * G.emb_dim), (int)G.emb_dim, idx_bits, jk.t0[g]};
-            rc = seg_reduce_launch<4>(ks, vals_sorted + off, ng, acc, (int)G.emb_dim, sc, off, stream);
+            rc = seg_reduce_launch<4>(ks, vals_sorted + off, ng, acc, (int)G.emb_dim, scg, off, st);
         } else {
             DenseAcc<1> acc{G.dx_emb, tps[g], (int)(G.n_tables * G.emb_dim), (int)G.emb_dim, idx_bits, jk.t0[g]};
-            rc = seg_reduce_launch<1>(ks, vals_sorted + off, ng, acc, (int)G.emb_dim, sc, off, stream);
+            rc = seg_reduce_launch<1>(ks, vals_sorted + off, ng, acc, (int)G.emb_dim, scg, off, st);
         }
         if (rc) return rc;
+    }
+    if (side) {
+        CFM_CHECK_CUDA(cudaEventRecord(side->join, side->stream));
+        CFM_CHECK_CUDA(cudaStreamWaitEvent(stream, side->join, 0));
     }
     return CFM_OK;
 }

@@ -1142,7 +1142,7 @@ int tc_prep_launch(const cfm_tower_t* towers, int n_towers, cudaStream_t stream)
         any |= t.wimg != nullptr;
     }
     if (!any) return CFM_OK;
-    tc_prep_weights<<<dim3(16, (unsigned)n_towers), 256, 0, stream>>>(a);
+    tc_prep_weights<<<dim3(64, (unsigned)n_towers), 256, 0, stream>>>(a);      // ~60 k elements per tower: latency-bound, spread wide
     CFM_LAUNCH_CHECK();
     return CFM_OK;
 }

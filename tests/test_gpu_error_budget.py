@@ -4,9 +4,10 @@ fp32 everywhere else) the same oracle in float32 — i.e. stock ATen fp32 — is
 says how far two honest fp32 evaluations of this network are from each other.
 
 Two figures per tensor, both relative:  max|a - e| / max|e|  (error against the tensor's scale, what the parity tests
-bound) and the relative L2 error  ||a - e|| / ||e||.  The test asserts that the CUDA path stays within 4x of torch
-fp32's own error (plus a floor of 2e-6), and within the absolute bar 1e-5 for scores / loss and 5e-5 for gradients; the
-table is written to ``gpurun_out/r02_error_budget.md`` (copied to ``profiles/``)."""
+bound) and the relative L2 error  ||a - e|| / ||e||.  The test asserts the north-star's fp32 bar, 1e-5 relative to the
+tensor's scale, for the scores, the loss and EVERY gradient (measured on B200: <= 2.7e-6, torch fp32 itself <= 1.4e-6),
+and that the CUDA path stays within 4x of torch fp32's own error (plus a floor of 2e-6); the table is written to
+``gpurun_out/r02_error_budget.md`` (copied to ``profiles/``)."""
 import os
 
 import numpy as np
@@ -87,6 +88,6 @@ def test_error_budget_vs_float64(B):
         f.write("\n".join(lines) + "\n")
 
     for name, (a_max, a_l2), (t_max, t_l2) in rows:
-        bar = 1e-5 if name in ("scores", "loss") else 5e-5
+        bar = 1e-5
         assert a_max <= bar, f"{name}: max error / scale {a_max:.2e} above the fp32 bar {bar:.0e}"
         assert a_max <= 4 * t_max + 2e-6, f"{name}: CUDA {a_max:.2e} vs torch fp32's own {t_max:.2e}"
