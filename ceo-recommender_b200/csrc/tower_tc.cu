@@ -60,6 +60,22 @@ __device__ __forceinline__ void trace(int slot, int code) {
     if (g_trace && g_trace_code == code) g_trace[(size_t)blockIdx.x * 128 + slot] = gtime();
 }
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+// Asynchronous global -> shared copies (LDGSTS).  Register loads all land on one hardware scoreboard in these kernels
+// (ptxas gives every LDG.128 of the producer loops barrier 5), so waiting for the oldest of several software-
+// pipelined loads waits for the youngest too and the pipeline collapses to one load latency per chunk.  cp.async
+// groups complete in order and `wait_group N` waits for exactly the groups it names.  bytes < size zero-fills.
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, int bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* dst, const void* src, int bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* dst, const void* src, int bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void sts4(uint8_t* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
 
 // Column sums over the lanes of a warp by recursive halving: every step a lane keeps one half of its columns and
@@ -284,15 +300,20 @@ __device__ __forceinline__ void gather_issue_data(const GatherSrc& g, long long 
 // ------------------------------------------------------------------------------------------
 // forward stage
 // ------------------------------------------------------------------------------------------
+constexpr int TCF_PD = 2;                                // chunks of input a producer group keeps in flight
+constexpr int TCF_NIS = TCF_PD + 1;                      // index slots (stage 1): one being read, TCF_PD in flight
+constexpr int TCF_RAW_SLOT = (TCF_M / 32) * TC_GT * 16;  // one chunk of one group: NX quads per thread, 16 KB
+constexpr int TCF_IDX_SLOT = (TCF_M / 32) * TC_GT * 8;   // its embedding indices, 8 KB
 struct TcFwdSmem {
-    int w, ring, bn, bias, piv, wst, bars, tmem, total, nst;
+    int w, raw, idx, ring, bn, bias, piv, wst, bars, tmem, total, nst, stage, wstream;
 };
-__host__ __device__ inline TcFwdSmem tcf_smem(int K, int N) {
+// Shared-memory plan of the forward stage.  `stage1`: the input is gathered (index staging needed).  The weight image
+// stays resident when at least two ring stages fit beside it; otherwise (wide stage-1 inputs: 7 chunks x 16 KB for the
+// firm tower of config 4) every ring stage carries its own weight chunk, re-streamed from L2 per tile.
+__host__ __device__ inline TcFwdSmem tcf_smem(int K, int N, bool stage1) {
     TcFwdSmem s;
     const int nch = tc_nch(K), Kp = (K + 3) & ~3;
-    int o = 0;
-    s.w = o; o += nch * tc_w_chunk_floats(N) * 4;
-    s.ring = o;
+    const int chunk_bytes = tc_w_chunk_floats(N) * 4, img = 2 * TCF_M * 128;
     int f = 0;                                          // fixed tail (relative)
     const int bn = f; f += 4 * Kp * 4;
     const int bias = f; f += 64 * 4;
@@ -301,11 +322,19 @@ __host__ __device__ inline TcFwdSmem tcf_smem(int K, int N) {
     f = (f + 15) & ~15;
     const int bars = f; f += 32 * 8;
     const int tmem = f; f += 16;
-    const int stage = 2 * TCF_M * 128;
-    int nst = (TC_SMEM_MAX - 1024 - o - f) / stage;
+    const int raw_bytes = TC_GROUPS * TCF_PD * TCF_RAW_SLOT, idx_bytes = stage1 ? TC_GROUPS * TCF_NIS * TCF_IDX_SLOT : 0;
+    const int avail = TC_SMEM_MAX - 1024 - raw_bytes - idx_bytes - f;
+    int nst = (avail - nch * chunk_bytes) / img;
+    s.wstream = nst < 2;
+    s.stage = s.wstream ? img + chunk_bytes : img;
+    if (s.wstream) nst = avail / s.stage;
     nst = nst > 4 ? 4 : nst;
     s.nst = nst;
-    o += (nst > 0 ? nst : 0) * stage;
+    int o = 0;
+    s.w = o; o += s.wstream ? 0 : nch * chunk_bytes;
+    s.raw = o; o += raw_bytes;
+    s.idx = o; o += idx_bytes;
+    s.ring = o; o += (nst > 0 ? nst : 0) * s.stage;
     s.bn = o + bn; s.bias = o + bias; s.piv = o + piv; s.wst = o + wst; s.bars = o + bars; s.tmem = o + tmem;
     s.total = o + f + 1024;
     return s;
@@ -321,8 +350,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tower_fwd_tc(const __grid_const
     extern __shared__ uint8_t smem_raw[];
     uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic on the __shared__ array: accesses compile to LDS/STS (a uintptr_t round trip makes them generic LD/ST)
     const int K = S.in.K, N = S.N, npad = tc_npad(N), nch = tc_nch(K), Kp = (K + 3) & ~3;
-    const TcFwdSmem L = tcf_smem(K, N);
+    const TcFwdSmem L = tcf_smem(K, N, STAGE1);
     const int nst = L.nst;
+    const bool wstream = L.wstream != 0;
     float* sm_bn = reinterpret_cast<float*>(sm + L.bn);
     float* sm_bias = reinterpret_cast<float*>(sm + L.bias);
     float* sm_piv = reinterpret_cast<float*>(sm + L.piv);
@@ -338,13 +368,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tower_fwd_tc(const __grid_const
     const bool exact = args.exact != 0;
     const bool stats = S.stat_part != nullptr;
     const int chunk_bytes = tc_w_chunk_floats(N) * 4;
-    constexpr int STAGE_BYTES = 2 * TCF_M * 128, IMG_BYTES = TCF_M * 128;
+    constexpr int IMG_BYTES = TCF_M * 128;
+    const int STAGE_BYTES = L.stage;                       // (hi, lo) input images [+ the chunk's weight image]
     const int tcode = S.in.stage;
 
     if (tid == 0) {
         trace(0, tcode);
         mbar_init(w_full, 1);
-        for (int s = 0; s < 4; ++s) { mbar_init(full + s, TC_GT); mbar_init(empty + s, 1); }
+        // a stage is full when the group's 256 threads have written the images and its weight chunk is in place
+        for (int s = 0; s < 4; ++s) { mbar_init(full + s, TC_GT + 1); mbar_init(empty + s, 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(d_full + b, 1); mbar_init(d_empty + b, TC_EPI_WARPS * 32); }
         fence_barrier_init();
     }
@@ -363,13 +395,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tower_fwd_tc(const __grid_const
         // The whole warp walks the loops (warp-uniform control flow keeps descriptors in uniform registers); one
         // elected lane issues the tcgen05 instructions.
         if (my_tiles > 0) {
-            if (elect_one()) {
-                mbar_expect_tx(w_full, (uint32_t)(nch * chunk_bytes));
-                for (int j = 0; j < nch; ++j)
-                    bulk_g2s(sm + L.w + j * chunk_bytes, S.wimg + (size_t)j * tc_w_chunk_floats(N), (uint32_t)chunk_bytes, w_full);
+            if (!wstream) {
+                if (elect_one()) {
+                    mbar_expect_tx(w_full, (uint32_t)(nch * chunk_bytes));
+                    for (int j = 0; j < nch; ++j)
+                        bulk_g2s(sm + L.w + j * chunk_bytes, S.wimg + (size_t)j * tc_w_chunk_floats(N), (uint32_t)chunk_bytes, w_full);
+                }
+                __syncwarp();
+                mbar_wait(w_full, 0);
             }
-            __syncwarp();
-            mbar_wait(w_full, 0);
             const uint32_t idesc = make_idesc_tf32(TCF_M, npad, false, false);
             const uint32_t w_s = smem_u32(sm + L.w), ring_s = smem_u32(sm + L.ring);
             const int ks_last = (K - 32 * (nch - 1) + 7) >> 3;
@@ -385,7 +419,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tower_fwd_tc(const __grid_const
                     mbar_wait(full + s, (cnt / nst) & 1);
                     tc_fence_after();
                     const uint32_t a_hi = ring_s + s * STAGE_BYTES, a_lo = a_hi + IMG_BYTES;
-                    const uint32_t b_hi = w_s + j * chunk_bytes, b_lo = b_hi + npad * 128;
+                    const uint32_t b_hi = wstream ? a_hi + 2 * IMG_BYTES : w_s + j * chunk_bytes, b_lo = b_hi + npad * 128;
                     const int ksn = j == nch - 1 ? ks_last : 4;
                     if (elect_one()) {
                         for (int p = p0; p < 3; ++p) {
@@ -508,6 +542,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tower_fwd_tc(const __grid_const
         }
     } else {
         // ===================== producers =====================
+        // Per group and chunk: (A) request the chunk's embedding indices, (B) TCF_PD chunks later read them and request
+        // the data quads, (C) TCF_PD chunks later read the quads back, build the (hi, lo) images, hand the stage over.
+        // Everything in flight sits in thread-private shared-memory slots filled by cp.async; every iteration commits
+        // exactly two groups (indices, then data), so a constant `wait_group` count names the group each step needs.
+        // Order inside an iteration: A, C, B - the data slot (B) refills is the one (C) has just read.
         const int ptid = tid - TC_PROD_WARP0 * 32;
         const int grp = ptid / TC_GT, gtid = ptid - grp * TC_GT;
         const int q = gtid & 7, sub = gtid >> 3;
@@ -515,41 +554,78 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tower_fwd_tc(const __grid_const
         uint8_t* ring = sm + L.ring;
         const GatherSrc& g = S.in.g;
         constexpr int NX = TCF_M / 32;
+        const int KE = STAGE1 ? g.n_tab * g.E : 0;
+        uint8_t* raw = sm + L.raw + grp * TCF_PD * TCF_RAW_SLOT + gtid * 16;        // + (slot * NX + i) * TC_GT * 16
+        uint8_t* ixs = sm + L.idx + grp * TCF_NIS * TCF_IDX_SLOT + gtid * 8;        // + (slot * NX + i) * TC_GT * 8
         auto tile_row0 = [&](int it) { return ((long long)cta + (long long)it * nctas) * TCF_M; };
-        auto issue_idx = [&](const ChunkPos& p, long long (&ix)[NX]) {
+        auto issue_idx = [&](const ChunkPos& p, int slot) {
+            if (!STAGE1 || p.it >= my_tiles) return;
+            const int c0 = 32 * p.j + 4 * q;
+            if (c0 >= KE) return;                        // numeric columns need no index
+            const long long row0 = tile_row0(p.it);
+            const int t = c0 / g.E;
 #pragma unroll
-            for (int i = 0; i < NX; ++i) ix[i] = 0;
-            if (STAGE1 && p.it < my_tiles) gather_issue_idx<NX>(g, B, tile_row0(p.it), p.j, q, sub, ix);
+            for (int i = 0; i < NX; ++i) {
+                const long long r = row0 + sub + 32 * i;
+                cp_async8(ixs + (slot * NX + i) * TC_GT * 8, g.x_cat + (r < B ? r : 0) * g.n_tab + t, r < B ? 8 : 0);
+            }
         };
-        auto issue_data = [&](const ChunkPos& p, const long long (&ix)[NX], float4 (&x)[NX]) {
-#pragma unroll
-            for (int i = 0; i < NX; ++i) x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        auto issue_data = [&](const ChunkPos& p, int islot, int dslot) {
             if (p.it >= my_tiles) return;
             const long long row0 = tile_row0(p.it);
-            if (STAGE1) {
-                gather_issue_data<NX>(g, B, row0, p.j, q, sub, ix, args.err, x);
-            } else {
-                const int c0 = 32 * p.j + 4 * q;
-                if (c0 < K) {
+            const int c0 = 32 * p.j + 4 * q;
+            uint8_t* dst = raw + dslot * NX * TC_GT * 16;
+            if (!STAGE1) {
 #pragma unroll
-                    for (int i = 0; i < NX; ++i) {
-                        const long long r = row0 + sub + 32 * i;
-                        if (r < B) x[i] = ldg4(S.in.a.h + (size_t)r * K + c0);
+                for (int i = 0; i < NX; ++i) {
+                    const long long r = row0 + sub + 32 * i;
+                    const bool ok = r < B && c0 < K;
+                    cp_async16(dst + i * TC_GT * 16, S.in.a.h + (ok ? (size_t)r * K + c0 : 0), ok ? 16 : 0);
+                }
+            } else if (c0 < KE) {                        // E % 4 == 0: a quad never straddles two tables
+                const int t = c0 / g.E, e = c0 - t * g.E;
+                const float* tb = g.tab[t];
+                const long long trows = g.tab_rows[t];
+#pragma unroll
+                for (int i = 0; i < NX; ++i) {
+                    const long long r = row0 + sub + 32 * i;
+                    long long v = *reinterpret_cast<const long long*>(ixs + (islot * NX + i) * TC_GT * 8);
+                    if (r < B && (v < 0 || v >= trows)) { if (args.err) atomicOr(args.err, CFM_FLAG_INDEX_OOB); v = 0; }
+                    cp_async16(dst + i * TC_GT * 16, tb + (r < B ? (size_t)v * g.E + e : 0), r < B ? 16 : 0);
+                }
+            } else {                                     // numeric columns (possibly a ragged quad): 4-byte pieces
+#pragma unroll
+                for (int i = 0; i < NX; ++i) {
+                    const long long r = row0 + sub + 32 * i;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int cn = c0 + e - KE;
+                        const bool ok = r < B && cn < g.n_num;
+                        cp_async4(dst + i * TC_GT * 16 + 4 * e, g.x_num + (ok ? (size_t)r * g.n_num + cn : 0), ok ? 4 : 0);
                     }
                 }
             }
         };
-        auto consume = [&](const ChunkPos& p, float4 (&x)[NX]) {
+        auto consume = [&](const ChunkPos& p, int dslot) {
             const uint32_t cnt = (uint32_t)(p.it * nch + p.j);
             const int s = cnt % nst;
             mbar_wait(empty + s, ((cnt / nst) & 1) ^ 1);
             const long long row0 = tile_row0(p.it);
             const int c0 = 32 * p.j + 4 * q;
             uint8_t* hi_img = ring + s * STAGE_BYTES;
+            if (gtid == 0) {                             // the stage's 257th arrival: its weight chunk (or nothing)
+                if (wstream) {
+                    mbar_expect_tx(full + s, (uint32_t)chunk_bytes);
+                    bulk_g2s(hi_img + 2 * IMG_BYTES, S.wimg + (size_t)p.j * tc_w_chunk_floats(N), (uint32_t)chunk_bytes, full + s);
+                } else {
+                    mbar_arrive(full + s);
+                }
+            }
+            const uint8_t* src = raw + dslot * NX * TC_GT * 16;
 #pragma unroll
             for (int i = 0; i < NX; ++i) {
                 const int r = sub + 32 * i;
-                float4 a = x[i];
+                float4 a = *reinterpret_cast<const float4*>(src + i * TC_GT * 16);
                 if (STAGE1 && S.x_out && row0 + r < B) {
                     // input stash for the backward: 16 KB blocks [64-row tile][64-column chunk], rows of 16 quads with
                     // the quad index XOR-ed by the row (the backward reads it lane <-> row without bank conflicts)
@@ -577,7 +653,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tower_fwd_tc(const __grid_const
             mbar_arrive(full + s);
             if (gtid == 0 && cnt < 40) trace(2 + cnt, tcode);
         };
-        chunk_pipeline<TC_GROUPS, 2, NX, NX>(my_tiles, nch, grp, issue_idx, issue_data, consume);
+        ChunkPos pi, pd, pc;
+        pi.start(grp, nch); pd = pi; pc = pi;
+        int si = 0, sd_i = 0, sd_d = 0, sc_d = 0;        // slot counters: index write / index read / data write / data read
+        for (int jj = -2 * TCF_PD;; ++jj) {
+            if (jj >= 0 && pc.it >= my_tiles) break;
+            issue_idx(pi, si); cp_async_commit();                                        // (A) indices of chunk jj + 2 PD
+            pi.template next<TC_GROUPS>(nch); si = si + 1 == TCF_NIS ? 0 : si + 1;
+            if (jj >= 0) {
+                cp_async_wait<2 * TCF_PD - 1>();         // (C) the data of chunk jj have landed (and every older group)
+                consume(pc, sc_d);
+                pc.template next<TC_GROUPS>(nch); sc_d = sc_d + 1 == TCF_PD ? 0 : sc_d + 1;
+            } else if (jj >= -TCF_PD) {
+                cp_async_wait<2 * TCF_PD>();             // start-up: the indices of chunk jj + PD have landed
+            }
+            if (jj >= -TCF_PD) {                         // (B) data of chunk jj + PD, into the slot (C) just drained
+                issue_data(pd, sd_i, sd_d);
+                pd.template next<TC_GROUPS>(nch);
+                sd_i = sd_i + 1 == TCF_NIS ? 0 : sd_i + 1; sd_d = sd_d + 1 == TCF_PD ? 0 : sd_d + 1;
+            }
+            cp_async_commit();
+        }
+        cp_async_wait<0>();
     }
     tc_fence_before();
     __syncthreads();
@@ -1117,7 +1214,7 @@ bool tc_fwd_supported(const cfm_tower_t& t, int s) {
     if (s == 1) {
         if (t.n_tables > 0 && (t.emb_dim & 3)) return false;
     } else if (K & 3) return false;
-    return tcf_smem(K, N).nst >= 2;
+    return tcf_smem(K, N, s == 1).nst >= 2;
 }
 
 bool tc_bwd_supported(const cfm_tower_t& t, int s, bool a_bn, bool need_dx) {
@@ -1181,7 +1278,7 @@ int tc_fwd_launch(FwdArgs& a, const cfm_tower_t* towers, int n_towers, int s, in
         a.st[i].wimg = t.wimg + L.w[s - 1];
         a.st[i].a_out = s == 2 ? t.a1 : s == 3 ? t.a2 : nullptr;
         a.st[i].x_out = s == 1 ? t.xstash : nullptr;
-        smem = std::max(smem, (size_t)tcf_smem(K[s - 1], N[s - 1]).total);
+        smem = std::max(smem, (size_t)tcf_smem(K[s - 1], N[s - 1], s == 1).total);
         if (tc_npad(N[s - 1]) > 32) nc = 64;
     }
     const long long ntiles = (a.B + TCF_M - 1) / TCF_M;
