@@ -528,6 +528,25 @@ extern "C" int cfm_emb_gather_rows(const int64_t* x_cat, int64_t B, int64_t n_ta
     return CFM_OK;
 }
 
+namespace cfm {
+// Second stream of the embedding-gradient reduce (one per device): the two towers' segment reductions write disjoint
+// tables and read disjoint key ranges, so the second group runs beside the first; under stream capture the fork / join
+// events become graph edges.
+struct EmbSide { cudaStream_t stream = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+static EmbSide* emb_side() {
+    static EmbSide side[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    EmbSide& S = side[dev];
+    if (!S.stream) {
+        if (cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        cudaEventCreateWithFlags(&S.fork, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&S.join, cudaEventDisableTiming);
+    }
+    return &S;
+}
+}  // namespace cfm
+
 extern "C" int cfm_emb_grad_peer_reduce(const cfm_peer_group_t* groups, int64_t n_groups, int64_t n_peers, int64_t B,
                                         int64_t phase, int64_t* keys_tmp, int32_t* vals_tmp, int64_t* keys_sorted,
                                         int32_t* vals_sorted, void* sort_tmp, int64_t sort_tmp_bytes, void* stream_) {
@@ -557,20 +576,38 @@ extern "C" int cfm_emb_grad_peer_reduce(const cfm_peer_group_t* groups, int64_t 
         if (rc) return rc;
     }
     if (phase == 1) return CFM_OK;
+    // the second group reduces beside the first (own slice of the partial scratch, own flag, second stream)
+    size_t part_off[CFM_MAX_GROUPS + 1] = {0};
+    for (int g = 0; g < n_groups; ++g)
+        part_off[g + 1] = part_off[g] + (size_t)(groups[g].n_owned * n_peers * B / SEG_CHUNK + 2) * 2 * (size_t)groups[g].width;
+    EmbSide* side = n_groups == 2 && part_off[n_groups] * sizeof(float) <= seg_part_bytes(n) ? emb_side() : nullptr;
+    if (side) {
+        CFM_CHECK_CUDA(cudaEventRecord(side->fork, stream));
+        CFM_CHECK_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+    }
     long long off = 0;
     for (int g = 0; g < n_groups; ++g) {
         const cfm_peer_group_t& G = groups[g];
         const long long ng = G.n_owned * n_peers * B;
         const unsigned long long* ks = (const unsigned long long*)keys_sorted + off;
-        if ((G.width & 3) == 0 && (G.emb_dim & 3) == 0) {
-            PeerAcc<4> acc{pp, tp, (int)B, (int)G.emb_dim, (int)G.width, idx_bits};
-            rc = seg_reduce_launch<4>(ks, vals_sorted + off, ng, acc, (int)G.width, sc, off, stream);
-        } else {
-            PeerAcc<1> acc{pp, tp, (int)B, (int)G.emb_dim, (int)G.width, idx_bits};
-            rc = seg_reduce_launch<1>(ks, vals_sorted + off, ng, acc, (int)G.width, sc, off, stream);
+        SegScratch scg = sc;
+        cudaStream_t st = stream;
+        if (side) { scg.part = sc.part + part_off[g]; scg.flag = sc.flag + g; if (g == 1) st = side->stream; }
+        if (ng > 0) {
+            if ((G.width & 3) == 0 && (G.emb_dim & 3) == 0) {
+                PeerAcc<4> acc{pp, tp, (int)B, (int)G.emb_dim, (int)G.width, idx_bits};
+                rc = seg_reduce_launch<4>(ks, vals_sorted + off, ng, acc, (int)G.width, scg, off, st);
+            } else {
+                PeerAcc<1> acc{pp, tp, (int)B, (int)G.emb_dim, (int)G.width, idx_bits};
+                rc = seg_reduce_launch<1>(ks, vals_sorted + off, ng, acc, (int)G.width, scg, off, st);
+            }
+            if (rc) return rc;
         }
-        if (rc) return rc;
         off += ng;
+    }
+    if (side) {
+        CFM_CHECK_CUDA(cudaEventRecord(side->join, side->stream));
+        CFM_CHECK_CUDA(cudaStreamWaitEvent(stream, side->join, 0));
     }
     return CFM_OK;
 }
@@ -731,25 +768,6 @@ static int joint_plan(const cfm_emb_group_t* groups, int64_t n_groups, bool need
     return CFM_OK;
 }
 
-}  // namespace cfm
-
-namespace cfm {
-// Second stream of the embedding-gradient reduce (one per device): the two towers' segment reductions write disjoint
-// tables and read disjoint key ranges, so the second group runs beside the first; under stream capture the fork / join
-// events become graph edges.
-struct EmbSide { cudaStream_t stream = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
-static EmbSide* emb_side() {
-    static EmbSide side[64];
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-    EmbSide& S = side[dev];
-    if (!S.stream) {
-        if (cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-        cudaEventCreateWithFlags(&S.fork, cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&S.join, cudaEventDisableTiming);
-    }
-    return &S;
-}
 }  // namespace cfm
 
 extern "C" int cfm_emb_grad_joint_reduce(const cfm_emb_group_t* groups, int64_t n_groups, int64_t B, int64_t phase,
