@@ -691,7 +691,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tower_fwd_tc(const __grid_const
 // from registers, one 128-byte row per store instruction.
 // ------------------------------------------------------------------------------------------
 struct TcBwdSmem {
-    int g, gt, raw, ring, at, wt, msk, xh, stage, bna, bng, red, bars, tmem, total, nst, at_img;
+    int g, gt, raw, slots, ring, at, wt, msk, stage, bna, bng, red, bars, tmem, total, nst, at_img;
 };
 __host__ __device__ inline TcBwdSmem tcb_smem(int K, int N, bool stage1, bool a_bn, bool stash = false) {
     TcBwdSmem s;
@@ -700,13 +700,14 @@ __host__ __device__ inline TcBwdSmem tcb_smem(int K, int N, bool stage1, bool a_
     s.g = o; o += 2 * TCB_M * 128 * nbn;              // G   [64 rows][N]      hi, lo
     s.gt = o; o += 2 * 64 * 128 * 2;                  // G^T [64 n][64 rows]   hi, lo
     s.raw = o; o += stash ? 64 * 64 * 4 : 0;          // one block of the forward's input stash (bulk copy target)
+    s.slots = o; o += stage1 ? 0 : 2 * (cw / 32) * TC_PT * 16;   // stage > 1: two chunks of saved codes in flight (cp.async)
     s.ring = o;
     int st = 0;
     s.at_img = (cw + 8) * 128 * 2;                    // A^T chunk [cw k + 8][64 rows]: row cw = ones (bias gradient)
     s.at = st; st += 2 * s.at_img;
     s.wt = st; st += 2 * cw * 128 * nbn;              // W^T chunk [cw k][N]       hi, lo
-    s.msk = st; st += stage1 ? 0 : TCB_M * cw * 4;    // activation-derivative tile [64 rows][cw k]
-    s.xh = st; st += a_bn ? TCB_M * cw * 4 : 0;       // x-hat tile                 [64 rows][cw k]
+    s.msk = st; st += stage1 ? 0 : TCB_M * cw * 4;    // the chunk's activation codes [64 rows][cw k]: the epilogue decodes
+    (void)a_bn;                                       // d(act)/d(pre-activation) and x-hat from them (act_quad)
     s.stage = st;
     int f = 0;
     const int bna = f; f += 4 * Kp * 4;
@@ -860,6 +861,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tower_bwd_tc(const __grid_const
         const uint32_t lane_addr = (uint32_t)(32 * q) << 16;
         const int KE = S.in.g.n_tab * S.in.g.E, n_num = S.in.g.n_num;
         float s1[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, s2[2][2] = {{0.f, 0.f}, {0.f, 0.f}};   // [32-column half][owned column] (stage > 1: K <= 64)
+        const float inv_keep_e = (!STAGE1 && S.in.a.drop.active) ? S.in.a.drop.inv_keep : 1.f;
         uint32_t cnt = 0;
         for (int it = 0; it < my_tiles; ++it) {
             const long long row0 = ((long long)cta + (long long)it * nctas) * TCB_M;
@@ -904,14 +906,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tower_bwd_tc(const __grid_const
                             float xs[32];
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
-                                const float4 m4 = *reinterpret_cast<const float4*>(st + L.msk + sw128_chunk(rl, hf, i, TCB_M));
-                                v[4 * i] *= m4.x; v[4 * i + 1] *= m4.y; v[4 * i + 2] *= m4.z; v[4 * i + 3] *= m4.w;
-                            }
-                            if (a_bn) {
+                                // saved code: x-hat where the unit was active and kept, NaN elsewhere
+                                const float4 c4 = *reinterpret_cast<const float4*>(st + L.msk + sw128_chunk(rl, hf, i, TCB_M));
+                                const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
 #pragma unroll
-                                for (int i = 0; i < 8; ++i) {
-                                    const float4 x4 = *reinterpret_cast<const float4*>(st + L.xh + sw128_chunk(rl, hf, i, TCB_M));
-                                    xs[4 * i] = x4.x; xs[4 * i + 1] = x4.y; xs[4 * i + 2] = x4.z; xs[4 * i + 3] = x4.w;
+                                for (int e = 0; e < 4; ++e) {
+                                    const bool on = cc[e] == cc[e];
+                                    v[4 * i + e] *= on ? inv_keep_e : 0.f;
+                                    xs[4 * i + e] = on ? cc[e] : 0.f;
                                 }
                             }
                             if (valid) {
@@ -1164,13 +1166,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tower_bwd_tc(const __grid_const
                 const int c0 = CW * p.j + 4 * q;
                 float4 a = x[i];
                 if (!STAGE1) {
-                    // a, its derivative w.r.t. the pre-activation and x-hat from the saved code; the last two go to the
-                    // epilogue through the ring stage
+                    // a from the saved code; the code itself goes to the epilogue through the ring stage (it decodes
+                    // the derivative w.r.t. the pre-activation and x-hat)
                     float4 m4 = make_float4(0.f, 0.f, 0.f, 0.f), xh = m4;
-                    if (c0 < K && tile_row0(p.it) + r < B) act_decode(x[i], sm_bna, Kp, c0, S.in.a.bn_mode, inv_keep, a, m4, xh);
+                    const float nanv = __int_as_float(0x7fc00000);
+                    float4 code = make_float4(nanv, nanv, nanv, nanv);      // padding decodes to zeros
+                    if (c0 < K && tile_row0(p.it) + r < B) { act_decode(x[i], sm_bna, Kp, c0, S.in.a.bn_mode, inv_keep, a, m4, xh); code = x[i]; }
                     else a = m4;
-                    sts4(st + L.msk + sw128_chunk(r, q >> 3, q & 7, TCB_M), m4);
-                    if (a_bn) sts4(st + L.xh + sw128_chunk(r, q >> 3, q & 7, TCB_M), xh);
+                    sts4(st + L.msk + sw128_chunk(r, q >> 3, q & 7, TCB_M), code);
                 }
                 float4 hi, lo;
                 split_tf32x4(a, hi, lo);
@@ -1190,7 +1193,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tower_bwd_tc(const __grid_const
             // the tensor core finds work the moment G arrives
             if (p.j == 0) build_g(p.it);
         };
-        chunk_pipeline<1, 2, NX, NXR>(my_tiles, nch, 0, issue_idx, issue_data, consume);
+        if constexpr (STAGE1) {
+            chunk_pipeline<1, 2, NX, NXR>(my_tiles, nch, 0, issue_idx, issue_data, consume);
+        } else {
+            // saved codes through thread-private cp.async slots, two chunks in flight (exact wait_group waits; register
+            // loads of a software pipeline all share one hardware scoreboard in these kernels, see tower_fwd_tc)
+            constexpr int PD = 2;
+            uint8_t* slots = sm + L.slots + gtid * 16;                  // + (slot * NXR + i) * TC_PT * 16
+            ChunkPos pd, pc;
+            pd.start(0, nch); pc = pd;
+            int sd = 0, scs = 0;
+            for (int jj = -PD;; ++jj) {
+                if (jj >= 0 && pc.it >= my_tiles) break;
+                if (jj >= 0) {
+                    cp_async_wait<PD - 1>();
+                    float4 x[NX];
+#pragma unroll
+                    for (int i = 0; i < NXR; ++i) x[i] = *reinterpret_cast<const float4*>(slots + (scs * NXR + i) * TC_PT * 16);
+                    consume(pc, x);
+                    pc.template next<1>(nch); scs ^= 1;
+                }
+                if (pd.it < my_tiles) {
+                    const long long row = tile_row0(pd.it) + r;
+#pragma unroll
+                    for (int i = 0; i < NXR; ++i) {
+                        const int c0 = CW * pd.j + 4 * (qb + QS * i);
+                        const bool ok = row < B && c0 < K;
+                        cp_async16(slots + (sd * NXR + i) * TC_PT * 16, S.in.a.a_post + (ok ? (size_t)row * K + c0 : 0), ok ? 16 : 0);
+                    }
+                }
+                cp_async_commit();
+                pd.template next<1>(nch); sd ^= 1;
+            }
+            cp_async_wait<0>();
+        }
     }
     tc_fence_before();
     __syncthreads();
