@@ -46,6 +46,65 @@ __device__ __forceinline__ long long seg_slot(long long p, long long start) {
 }
 
 // level 1: thread (p, q) sums slice q of the chunk that starts at p
+// general item: any run length (chunk heads only), bisection for the chunk end, four rows in flight
+template <int VEC, class Acc>
+__device__ __forceinline__ void seg_item(const unsigned long long* __restrict__ keys, const int* __restrict__ vals, long long n,
+                                         const Acc& acc, float* __restrict__ part, int* __restrict__ any_long,
+                                         const int* __restrict__ starts, long long base, int W, long long p, int q,
+                                         unsigned long long key, unsigned long long kprev, unsigned long long knext) {
+    long long start;
+    if (kprev != key) start = p;
+    else {
+        start = (long long)starts[p] - base;
+        if (((p - start) % SEG_CHUNK) != 0) return;              // not the first position of a chunk of its run
+    }
+    // end of the chunk: a full chunk unless the run stops inside it (then a 6-step bisection finds where), so the
+    // summation loop below carries no key test and its loads are independent of one another
+    long long end = min(n, p + SEG_CHUNK);
+    if (knext != key) end = p + 1;
+    else if (keys[end - 1] != key) {
+        long long lo = p, hi = end - 1;                    // keys[lo] == key, keys[hi] != key
+        while (hi - lo > 1) {
+            const long long mid = (lo + hi) >> 1;
+            if (keys[mid] == key) lo = mid; else hi = mid;
+        }
+        end = hi;
+    }
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    long long s = p;
+    for (; s + 4 <= end; s += 4) {                         // four rows in flight, added in position order
+        const float* s0 = acc.src(key, vals[s], q);
+        const float* s1 = acc.src(key, vals[s + 1], q);
+        const float* s2 = acc.src(key, vals[s + 2], q);
+        const float* s3 = acc.src(key, vals[s + 3], q);
+        if (VEC == 4) {
+            const float4 g0 = *reinterpret_cast<const float4*>(s0), g1 = *reinterpret_cast<const float4*>(s1);
+            const float4 g2 = *reinterpret_cast<const float4*>(s2), g3 = *reinterpret_cast<const float4*>(s3);
+            a.x += g0.x; a.y += g0.y; a.z += g0.z; a.w += g0.w;
+            a.x += g1.x; a.y += g1.y; a.z += g1.z; a.w += g1.w;
+            a.x += g2.x; a.y += g2.y; a.z += g2.z; a.w += g2.w;
+            a.x += g3.x; a.y += g3.y; a.z += g3.z; a.w += g3.w;
+        } else {
+            const float g0 = *s0, g1 = *s1, g2 = *s2, g3 = *s3;
+            a.x += g0; a.x += g1; a.x += g2; a.x += g3;
+        }
+    }
+    for (; s < end; ++s) {
+        const float* src = acc.src(key, vals[s], q);
+        if (VEC == 4) {
+            const float4 g = *reinterpret_cast<const float4*>(src);
+            a.x += g.x; a.y += g.y; a.z += g.z; a.w += g.w;
+        } else {
+            a.x += *src;
+        }
+    }
+    // the run is this one chunk: it starts here and ends inside the chunk (or exactly at its end)
+    const bool single = start == p && (end < p + SEG_CHUNK || p + SEG_CHUNK >= n || keys[p + SEG_CHUNK] != key);
+    float* dst = single ? acc.dst(key, q) : part + (seg_slot(p, start) * W + q) * VEC;
+    if (VEC == 4) *reinterpret_cast<float4*>(dst) = a;
+    else *dst = a.x;
+    if (!single && start == p && q == 0) *any_long = 1;
+}
 template <int VEC, class Acc>
 __global__ void seg_reduce_chunks(const unsigned long long* __restrict__ keys, const int* __restrict__ vals, long long n, Acc acc,
                                   float* __restrict__ part, int* __restrict__ any_long, const int* __restrict__ starts,
@@ -55,53 +114,12 @@ __global__ void seg_reduce_chunks(const unsigned long long* __restrict__ keys, c
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long p = i / W;
         const int q = (int)(i - p * W);
+        // the three neighbouring keys are requested together: with large tables most runs have ONE position (previous
+        // and next key both differ) and the item needs no further key traffic - one load latency instead of a chain of
+        // eight (head test, end test, six bisection steps)
         const unsigned long long key = keys[p];
-        long long start;
-        if (!seg_chunk_head(keys, starts, base, p, key, start)) continue;
-        // end of the chunk: a full chunk unless the run stops inside it (then a 6-step bisection finds where), so the
-        // summation loop below carries no key test and its loads are independent of one another
-        long long end = min(n, p + SEG_CHUNK);
-        if (keys[end - 1] != key) {
-            long long lo = p, hi = end - 1;                    // keys[lo] == key, keys[hi] != key
-            while (hi - lo > 1) {
-                const long long mid = (lo + hi) >> 1;
-                if (keys[mid] == key) lo = mid; else hi = mid;
-            }
-            end = hi;
-        }
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-        long long s = p;
-        for (; s + 4 <= end; s += 4) {                         // four rows in flight, added in position order
-            const float* s0 = acc.src(key, vals[s], q);
-            const float* s1 = acc.src(key, vals[s + 1], q);
-            const float* s2 = acc.src(key, vals[s + 2], q);
-            const float* s3 = acc.src(key, vals[s + 3], q);
-            if (VEC == 4) {
-                const float4 g0 = *reinterpret_cast<const float4*>(s0), g1 = *reinterpret_cast<const float4*>(s1);
-                const float4 g2 = *reinterpret_cast<const float4*>(s2), g3 = *reinterpret_cast<const float4*>(s3);
-                a.x += g0.x; a.y += g0.y; a.z += g0.z; a.w += g0.w;
-                a.x += g1.x; a.y += g1.y; a.z += g1.z; a.w += g1.w;
-                a.x += g2.x; a.y += g2.y; a.z += g2.z; a.w += g2.w;
-                a.x += g3.x; a.y += g3.y; a.z += g3.z; a.w += g3.w;
-            } else {
-                const float g0 = *s0, g1 = *s1, g2 = *s2, g3 = *s3;
-                a.x += g0; a.x += g1; a.x += g2; a.x += g3;
-            }
-        }
-        for (; s < end; ++s) {
-            const float* src = acc.src(key, vals[s], q);
-            if (VEC == 4) {
-                const float4 g = *reinterpret_cast<const float4*>(src);
-                a.x += g.x; a.y += g.y; a.z += g.z; a.w += g.w;
-            } else {
-                a.x += *src;
-            }
-        }
-        const bool single = start == p && (p + SEG_CHUNK >= n || keys[p + SEG_CHUNK] != key);
-        float* dst = single ? acc.dst(key, q) : part + (seg_slot(p, start) * W + q) * VEC;
-        if (VEC == 4) *reinterpret_cast<float4*>(dst) = a;
-        else *dst = a.x;
-        if (!single && start == p && q == 0) *any_long = 1;
+        const unsigned long long kprev = p > 0 ? keys[p - 1] : ~key, knext = p + 1 < n ? keys[p + 1] : ~key;
+        seg_item<VEC, Acc>(keys, vals, n, acc, part, any_long, starts, base, W, p, q, key, kprev, knext);
     }
 }
 // level 2: one WARP per sorted position; if it is the first position of a multi-chunk run, lane l adds the run's chunk
