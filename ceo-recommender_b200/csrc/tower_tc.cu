@@ -1038,11 +1038,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tower_bwd_tc(const __grid_const
                     float gv[4] = {gq[u].x, gq[u].y, gq[u].z, gq[u].w};
                     if (S.g_mode == 1) {
                         const float hv[4] = {hq[u].x, hq[u].y, hq[u].z, hq[u].w};
+                        // five parameter rows of the quad's columns (N % 4 == 0: 16-byte loads)
+                        const float4 p0 = *reinterpret_cast<const float4*>(sm_bng + c0), p1 = *reinterpret_cast<const float4*>(sm_bng + Np + c0);
+                        const float4 p2 = *reinterpret_cast<const float4*>(sm_bng + 2 * Np + c0), p3 = *reinterpret_cast<const float4*>(sm_bng + 3 * Np + c0);
+                        const float4 p4 = *reinterpret_cast<const float4*>(sm_bng + 4 * Np + c0);
+                        const float mu[4] = {p0.x, p0.y, p0.z, p0.w}, is[4] = {p1.x, p1.y, p1.z, p1.w}, gi[4] = {p2.x, p2.y, p2.z, p2.w};
+                        const float k1[4] = {p3.x, p3.y, p3.z, p3.w}, k2[4] = {p4.x, p4.y, p4.z, p4.w};
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            const int c = c0 + e;
-                            const float xh = (hv[e] - sm_bng[c]) * sm_bng[Np + c];
-                            gv[e] = sm_bng[2 * Np + c] * (gv[e] - sm_bng[3 * Np + c] - xh * sm_bng[4 * Np + c]);
+                            const float xh = (hv[e] - mu[e]) * is[e];
+                            gv[e] = gi[e] * (gv[e] - k1[e] - xh * k2[e]);
                         }
                     } else if (S.g_mode == 2) {
 #pragma unroll
