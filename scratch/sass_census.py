@@ -3,11 +3,12 @@ mnemonics each translation unit contains.  Usage: python scratch/sass_census.py 
 import collections, glob, os, re, subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 WANT = ["UTCHMMA", "UTCQMMA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "HMMA", "LDSM", "LDGSTS", "SYNCS",
-        "ELECT", "SHFL", "MUFU.EX2", "STL", "LDL"]
+        "ELECT", "SHFL", "MUFU.EX2", "LDS", "STS", "LD.E", "ST.E", "STL", "LDL"]
 print("# SASS census of libcfm_b200 (sm_100a), round 2\n")
 print("`cuobjdump -sass` of every object under `ceo-recommender_b200/lib/`; counts of instructions whose mnemonic starts")
 print("with the column name.  UTCHMMA = tcgen05.mma, LDTM = tcgen05.ld, UTMALDG = TMA tensor load, UBLKCP = cp.async.bulk,")
-print("HMMA/LDSM = legacy mma.sync / ldmatrix, LDGSTS = cp.async, STL/LDL = register spills.\n")
+print("HMMA/LDSM = legacy mma.sync / ldmatrix, LDGSTS = cp.async, LDS/STS = shared-memory accesses, LD.E/ST.E = GENERIC")
+print("accesses (should be ~0: a generic access to shared memory is what round 2 found and removed), STL/LDL = register spills.\n")
 print("| object | kernel | " + " | ".join(WANT) + " |")
 print("|---|---|" + "---:|" * len(WANT))
 for obj in sorted(glob.glob(os.path.join(ROOT, "ceo-recommender_b200", "lib", "*.o"))):
