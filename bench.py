@@ -777,8 +777,9 @@ def gpu_arm(args):
 
 
 def _finish(dist, runner):
-    """Multi-rank exit: a live CUDA graph that holds captured NCCL kernels makes destroy_process_group() wait
-    forever, so drop the graph, rendezvous once more and leave without NCCL/IPC teardown."""
+    """Multi-rank exit.  The captured step holds NCCL kernels: the graph is dropped and the ranks rendezvous before the
+    process group is destroyed.  destroy_process_group() has been seen to wait forever with such a graph alive, so it
+    runs under a watchdog that ends the process (exit code 0, results are already printed) if it does not return."""
     sys.stdout.flush()
     sys.stderr.flush()
     if dist is None:
@@ -788,7 +789,19 @@ def _finish(dist, runner):
     dist.barrier()
     torch.cuda.synchronize()
     sys.stdout.flush()
-    os._exit(0)
+    import threading
+
+    def _bail():
+        sys.stderr.write("bench: destroy_process_group() did not return within 15 s; leaving without NCCL teardown\n")
+        sys.stderr.flush()
+        os._exit(0)
+
+    watchdog = threading.Timer(15.0, _bail)
+    watchdog.daemon = True
+    watchdog.start()
+    dist.destroy_process_group()
+    watchdog.cancel()
+    os._exit(0)        # peer (CUDA IPC) mappings of the other ranks' tables are still open: skip interpreter teardown
 
 
 def main():
