@@ -292,9 +292,10 @@ int cfm_structural_head(const float* c_logits, const float* f_logits, const floa
 int64_t cfm_simtile_chunks(int64_t R, int64_t C);
 /* test hook: pin the number of 128-row blocks a similarity-kernel CTA owns (0 = automatic, 1, 2) */
 int cfm_simtile_set_rb(int64_t rb);
-/* Tuning knob: bit 0 / bit 1 = the row-sum / gradient kernels evaluate every fourth exponential as a polynomial on the
-   FMA pipe instead of MUFU.EX2 (results agree to 3e-6 relative).  Default 0: measured 5-14 % slower on B200, where
-   the epilogues are bound by instruction issue, not by the MUFU pipe. */
+/* Tuning knob: bit 0 / bit 1 = the row-sum / gradient kernels evaluate every fourth exponential as a degree-4 polynomial
+   on the FMA pipe instead of MUFU.EX2 (results agree to 3e-6 relative).  Default 1: the row-sum pass is bound by the
+   MUFU pipe (XU 85 % busy) and gains 12 %; the gradient pass is bound by instruction issue and the tensor pipe and
+   loses 13 % with it (profiles/r02_notes.md). */
 int cfm_simtile_set_poly(int64_t mask);
 int cfm_pack_rows_bf16(const float* in /* [R,D] */, int64_t R, int64_t D, int64_t Dp, void* out_bf16 /* [R,Dp] */,
                        void* stream);
