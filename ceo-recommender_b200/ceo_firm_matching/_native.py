@@ -15,7 +15,7 @@ import torch
 CFM_MAX_TABLES = 16
 CFM_MAX_PEERS = 8
 CFM_TOPK_CAP = 384
-CFM_ABI_VERSION = 2
+CFM_ABI_VERSION = 3
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libcfm_b200.so")
@@ -69,6 +69,19 @@ class PeerTable(C.Structure):
     ]
 
 
+class Projector(C.Structure):
+    """Mirror of ``cfm_projector_t``."""
+    _fields_ = [("d_in", i64), ("d_hid", i64), ("d_out", i64),
+                ("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p),
+                ("x", C.c_void_p), ("hid", C.c_void_p), ("raw", C.c_void_p), ("out", C.c_void_p)]
+
+
+class ProjectorGrads(C.Structure):
+    """Mirror of ``cfm_projector_grads_t``."""
+    _fields_ = [("g_out", C.c_void_p), ("dx", C.c_void_p), ("dw1", C.c_void_p), ("db1", C.c_void_p),
+                ("dw2", C.c_void_p), ("db2", C.c_void_p), ("scratch", C.c_void_p)]
+
+
 class AdamTensor(C.Structure):
     """Mirror of ``cfm_adam_tensor_t``."""
     _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
@@ -112,6 +125,9 @@ PROTOTYPES = {
     "cfm_adam_step": (C.c_int, [C.POINTER(AdamTensor), _I, _V, _I, _D, _D, _D, _D, _I, _V]),
     "cfm_cosine_head_fwd": (C.c_int, [_V, _V, _V, _I, _I, _D, _V, _V, _V, _V, _V, _V, _V, _V]),
     "cfm_cosine_head_bwd": (C.c_int, [_V, _V, _V, _V, _V, _V, _V, _V, _V, _I, _I, _D, _V, _V, _V, _V, _V]),
+    "cfm_projector_scratch_floats": (i64, [C.POINTER(Projector), _I]),
+    "cfm_projector_fwd": (C.c_int, [C.POINTER(Projector), _I, _I, _D, _V]),
+    "cfm_projector_bwd": (C.c_int, [C.POINTER(Projector), C.POINTER(ProjectorGrads), _I, _I, _D, _V]),
     "cfm_structural_head": (C.c_int, [_V, _V, _V, _V, _V, _V, _I, _D, _V, _V, _V, _V, _V, _V]),
     "cfm_simtile_chunks": (i64, [_I, _I]),
     "cfm_simtile_set_rb": (C.c_int, [_I]),
@@ -125,6 +141,7 @@ PROTOTYPES = {
     "cfm_allpairs_topk": (C.c_int, [_V, _V, _V, _V, _I, _I, _I, _I, _I, _I, _D, _D, _I, _V, _V, _V, _V, _V, _V, _V, _V]),
     "cfm_topk_merge": (C.c_int, [_V, _I, _V, _I, _I, _I, _V, _V, _V]),
     "cfm_allpairs_rank": (C.c_int, [_V, _V, _I, _I, _I, _V, _V, _V]),
+    "cfm_allpairs_diag_rank": (C.c_int, [_V, _V, _V, _V, _I, _I, _I, _I, _I, _I, _D, _V, _V, _V, _V, _V, _V, _V, _I, _V, _V]),
     "cfm_debug_set_trace": (C.c_int, [_V, _I]),
     "cfm_tc_mma_probe": (C.c_int, [_V, _I, _I, _I, _I, _V]),
     "cfm_tc_selftest": (C.c_int, [_V, _V, _V, _I, _I, _I, _I, _I, _V]),

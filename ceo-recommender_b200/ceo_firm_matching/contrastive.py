@@ -10,7 +10,6 @@ from typing import Dict, Tuple
 import numpy as np
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 import torch.optim as optim
 from torch.utils.data import DataLoader
 
@@ -49,10 +48,10 @@ class ContrastiveCEOFirmMatcher(nn.Module):
     def forward(self, f_numeric, f_cat, c_numeric, c_cat):
         """``(match_score [B,1], firm_proj [B,D//2], ceo_proj [B,D//2])`` (contrastive.py:74-99)."""
         score, u_hat, v_hat = self._unit_latents(f_numeric, f_cat, c_numeric, c_cat)
-        # The projection heads are two small dense layers per side; they run as stock torch ops on the device
-        # (the sub-modules stay ordinary nn.Sequential, like the towers, and are not part of the fused path yet).
-        firm_proj = F.normalize(self.firm_projector(u_hat), dim=1)
-        ceo_proj = F.normalize(self.ceo_projector(v_hat), dim=1)
+        # Both projection heads (Linear - ReLU - Linear) and the F.normalize that follows them run as ONE launch of
+        # the library's projector kernel; the nn.Sequential sub-modules stay in place for state_dict / direct callers
+        # and only hand over their parameters, like the towers.
+        firm_proj, ceo_proj = ops.projector_heads([(u_hat, self.firm_projector), (v_hat, self.ceo_projector)], 1e-12)
         return score, firm_proj, ceo_proj
 
 

@@ -627,6 +627,77 @@ class CosineMSEFunction(torch.autograd.Function):
 
 
 # ---------------------------------------------------------------------------------------
+# projection heads of the contrastive model (contrastive.py:41-50, 96-97)
+# ---------------------------------------------------------------------------------------
+class ProjectorHeadsFunction(torch.autograd.Function):
+    """apply(eps, x_0, w1_0, b1_0, w2_0, b2_0, x_1, ...) -> (out_0, out_1, ...):
+    out_i = normalize(W2_i relu(W1_i x_i + b1_i) + b2_i), all heads over the same B rows in one launch."""
+
+    @staticmethod
+    def forward(ctx, eps, *tensors):
+        _require_cuda(*tensors)
+        assert len(tensors) % 5 == 0 and tensors
+        n = len(tensors) // 5
+        tensors = [t.contiguous().float() for t in tensors]
+        B, dev = tensors[0].shape[0], tensors[0].device
+        heads = (N.Projector * n)()
+        outs, saved = [], []
+        for i in range(n):
+            x, w1, b1, w2, b2 = tensors[5 * i:5 * i + 5]
+            if x.shape != (B, w1.shape[1]) or w2.shape[1] != w1.shape[0] or b1.shape != (w1.shape[0],) or b2.shape != (w2.shape[0],):
+                raise ValueError("projector head %d: inconsistent shapes" % i)
+            hid = torch.empty(B, w1.shape[0], device=dev)
+            raw = torch.empty(B, w2.shape[0], device=dev)
+            out = torch.empty(B, w2.shape[0], device=dev)
+            h = heads[i]
+            h.d_in, h.d_hid, h.d_out = w1.shape[1], w1.shape[0], w2.shape[0]
+            h.w1, h.b1, h.w2, h.b2 = N.ptr(w1), N.ptr(b1), N.ptr(w2), N.ptr(b2)
+            h.x, h.hid, h.raw, h.out = N.ptr(x), N.ptr(hid), N.ptr(raw), N.ptr(out)
+            outs.append(out)
+            saved += [x, w1, b1, w2, b2, hid, raw]
+        with torch.cuda.device(dev):
+            N.check(N.lib().cfm_projector_fwd(heads, n, B, float(eps), N.stream_ptr()))
+        ctx.save_for_backward(*saved)
+        ctx.eps, ctx.n = float(eps), n
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *g_outs):
+        n, saved = ctx.n, ctx.saved_tensors
+        B, dev = saved[0].shape[0], saved[0].device
+        heads, grads = (N.Projector * n)(), (N.ProjectorGrads * n)()
+        result, keep = [None], []
+        for i in range(n):
+            x, w1, b1, w2, b2, hid, raw = saved[7 * i:7 * i + 7]
+            g = g_outs[i]
+            g = torch.zeros_like(raw) if g is None else g.contiguous().float()
+            h, gr = heads[i], grads[i]
+            h.d_in, h.d_hid, h.d_out = w1.shape[1], w1.shape[0], w2.shape[0]
+            h.w1, h.b1, h.w2, h.b2 = N.ptr(w1), N.ptr(b1), N.ptr(w2), N.ptr(b2)
+            h.x, h.hid, h.raw, h.out = N.ptr(x), N.ptr(hid), N.ptr(raw), None
+            dx = torch.empty_like(x) if ctx.needs_input_grad[1 + 5 * i] else None
+            dw1, db1, dw2, db2 = (torch.empty_like(t) for t in (w1, b1, w2, b2))
+            scratch = torch.empty(int(N.lib().cfm_projector_scratch_floats(C.byref(h), B)), device=dev)
+            gr.g_out, gr.dx, gr.dw1, gr.db1, gr.dw2, gr.db2 = N.ptr(g), N.ptr(dx), N.ptr(dw1), N.ptr(db1), N.ptr(dw2), N.ptr(db2)
+            gr.scratch = N.ptr(scratch)
+            keep += [g, scratch]
+            result += [dx, dw1, db1, dw2, db2]
+        with torch.cuda.device(dev):
+            N.check(N.lib().cfm_projector_bwd(heads, grads, n, B, ctx.eps, N.stream_ptr()))
+        return tuple(result)
+
+
+def projector_heads(pairs, eps: float = 1e-12):
+    """``pairs``: [(x, nn.Sequential(Linear, ReLU, Linear)), ...] -> tuple of L2-normalised projections
+    (contrastive.py:41-50 applied at :88-97).  The sub-modules only hand over their parameters."""
+    flat = []
+    for x, seq in pairs:
+        lin1, lin2 = seq[0], seq[2]
+        flat += [x, lin1.weight, lin1.bias, lin2.weight, lin2.bias]
+    return ProjectorHeadsFunction.apply(eps, *flat)
+
+
+# ---------------------------------------------------------------------------------------
 # structural head (structural_model.py:130-141, structural_training.py:75-77)
 # ---------------------------------------------------------------------------------------
 class StructuralHeadFunction(torch.autograd.Function):

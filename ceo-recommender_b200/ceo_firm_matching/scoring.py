@@ -72,20 +72,12 @@ def score_topk(rows: torch.Tensor, cols: torch.Tensor, k: int, scale: float = 1.
             out_s64.fill_(float("-inf"))
         return result()
     # Filter operands: fp16 copies when the values fit fp16 comfortably (unit-norm tower outputs always do) — 11-bit
-    # mantissas make the filter 8x tighter than bf16 — otherwise bf16 copies (same exponent range as fp32).
-    # |16-bit-operand score - exact score| <= 2u |row||col| (Cauchy-Schwarz over the per-element roundings, u = 2^-11
-    # or 2^-8), twice that separates "certainly in" from "certainly out"; the extra covers fp32 accumulation and
-    # fp16 subnormals.
-    # (one host read for both statistics; the launch parameters below depend on them)
-    norm_bound, amax = torch.stack([rows.norm(dim=1).max() * cols.norm(dim=1).max(),
-                                    torch.maximum(rows.abs().max(), cols.abs().max())]).tolist()
-    use_f16 = 1e-2 < amax < 1e3
-    if use_f16:
-        rb, cb = ops.pack_f16(rows), ops.pack_f16(cols)
-        margin = (2.0 ** -10 + 2.0 ** -16) * norm_bound + 4e-6
-    else:
-        rb, cb = ops.pack_bf16(rows), ops.pack_bf16(cols)
-        margin = (2.0 ** -7 + 2.0 ** -16) * norm_bound
+    # significands make the filter 4x tighter than bf16 — otherwise bf16 copies (same exponent range as fp32).
+    # e = bound on |16-bit-operand score - exact score| (_score_error_bound); the k-th largest filter score and a
+    # candidate's filter score are both off by up to e, so 2e separates "certainly in" from "certainly out".
+    use_f16, err = _score_error_bound(rows, cols)
+    margin = 2.0 * err
+    rb, cb = (ops.pack_f16(rows), ops.pack_f16(cols)) if use_f16 else (ops.pack_bf16(rows), ops.pack_bf16(cols))
     chunks = N.lib().cfm_simtile_chunks(R, C)
     rpad = (R + 255) // 256 * 256
     cand = torch.empty(chunks * rpad * N.CFM_TOPK_CAP, 2, dtype=torch.int32, device=dev)    # (score bits, column)
@@ -135,7 +127,66 @@ def target_ranks(rows: torch.Tensor, cols: torch.Tensor, target: torch.Tensor) -
     return rank
 
 
-def diagonal_ranks(firm_emb: torch.Tensor, ceo_emb: torch.Tensor) -> torch.Tensor:
-    """Rank of the true CEO (the diagonal) for every firm — contrastive.py:306-322 without the full sort."""
-    n = firm_emb.shape[0]
-    return target_ranks(firm_emb, ceo_emb, torch.arange(n, device=firm_emb.device))
+_RANK_TC_MIN_PAIRS = 1 << 22      # below ~4M pairs the fp64 SIMT kernel is as fast as the filter + rescoring chain
+_RANK_BLOCK_ROWS = 65536
+_RANK_AMB_CAP = 1 << 25           # listed (row, column) pairs per row block: 256 MB
+
+
+def _score_error_bound(rows: torch.Tensor, cols: torch.Tensor) -> Tuple[bool, float]:
+    """(use fp16 operands?, bound on |16-bit-operand score - exact score|): 2u |row||col| by Cauchy-Schwarz over the
+    per-element roundings (u = 2^-11 fp16, 2^-9 bf16) plus the fp32 accumulation / fp16-subnormal allowance."""
+    norm_bound, amax = torch.stack([rows.norm(dim=1).max() * cols.norm(dim=1).max(),
+                                    torch.maximum(rows.abs().max(), cols.abs().max())]).tolist()
+    use_f16 = 1e-2 < amax < 1e3
+    err = (2.0 ** -10 + 2.0 ** -16) * norm_bound + 4e-6 if use_f16 else (2.0 ** -8 + 2.0 ** -16) * norm_bound
+    return use_f16, err
+
+
+def diagonal_ranks(firm_emb: torch.Tensor, ceo_emb: torch.Tensor, method: str = "auto") -> torch.Tensor:
+    """Rank of the true CEO (the diagonal) for every firm — contrastive.py:306-322 without the full sort.
+
+    ``method="tensor"`` (``"auto"`` from ~4M pairs on): the tcgen05 similarity kernel counts, in its epilogue, the
+    columns whose 16-bit-operand score lies certainly above the row's exact positive score and lists the few pairs
+    too close to call; those are compared exactly (fp64 of the fp32 operands).  ``method="exact"``: the fp64 SIMT
+    kernel over every pair.  Both give the same ranks (ties by column index)."""
+    ops._require_cuda(firm_emb, ceo_emb)
+    n, C = firm_emb.shape[0], ceo_emb.shape[0]
+    if method not in ("auto", "tensor", "exact"):
+        raise ValueError("method must be 'auto', 'tensor' or 'exact'")
+    D = firm_emb.shape[1]
+    if n == 0:
+        return torch.empty(0, dtype=torch.int64, device=firm_emb.device)
+    if method == "exact" or D > 128 or (method == "auto" and n * C < _RANK_TC_MIN_PAIRS):
+        return target_ranks(firm_emb, ceo_emb, torch.arange(n, device=firm_emb.device))
+    rows, cols = firm_emb.detach().float().contiguous(), ceo_emb.detach().float().contiguous()
+    dev = rows.device
+    use_f16, err = _score_error_bound(rows, cols)
+    pack = ops.pack_f16 if use_f16 else ops.pack_bf16
+    cb = pack(cols)
+    out = torch.empty(n, dtype=torch.int64, device=dev)
+    nb = min(n, _RANK_BLOCK_ROWS)
+    rpad = (nb + 255) // 256 * 256
+    part = torch.empty(N.lib().cfm_simtile_chunks(nb, C) * rpad, dtype=torch.int32, device=dev)
+    extra = torch.empty(nb, dtype=torch.int32, device=dev)
+    diag64 = torch.empty(nb, dtype=torch.float64, device=dev)
+    window = torch.empty(2 * nb, device=dev)
+    amb = torch.empty(_RANK_AMB_CAP, 2, dtype=torch.int32, device=dev)
+    amb_n = torch.zeros(1, dtype=torch.int32, device=dev)
+    statuses = []
+    with torch.cuda.device(dev):
+        for r0 in range(0, n, nb):
+            blk = rows[r0:r0 + nb]
+            status = torch.zeros(2, dtype=torch.int32, device=dev)
+            rbk = pack(blk)
+            N.check(N.lib().cfm_allpairs_diag_rank(N.ptr(blk), N.ptr(cols), N.ptr(rbk), N.ptr(cb), 1 if use_f16 else 0,
+                                                   blk.shape[0], C, D, cb.shape[1], r0, err, N.ptr(out[r0:r0 + nb]),
+                                                   N.ptr(status), N.ptr(part), N.ptr(extra), N.ptr(diag64), N.ptr(window),
+                                                   N.ptr(amb), _RANK_AMB_CAP, N.ptr(amb_n), N.stream_ptr()))
+            statuses.append(status)
+    over = torch.stack(statuses)[:, 0].tolist()          # one host read for all blocks
+    for i, flag in enumerate(over):                       # too many near-ties to list (degenerate inputs): exact kernel
+        if flag:
+            r0 = i * nb
+            blk = rows[r0:r0 + nb]
+            out[r0:r0 + nb] = target_ranks(blk, cols, torch.arange(r0, r0 + blk.shape[0], device=dev))
+    return out

@@ -27,7 +27,7 @@ __host__ __device__ constexpr int sim_threads(int mode) { return 64 + ((mode == 
 constexpr int KB_BYTES = ST_M * 128;                   // one [128 rows x 64 bf16] swizzled block = 16 KB
 constexpr float LOG2E = 1.4426950408889634f;
 
-enum SimMode { SIM_SCORES = 0, SIM_ROWSUM = 1, SIM_GRAD = 2, SIM_TOPK = 3 };
+enum SimMode { SIM_SCORES = 0, SIM_ROWSUM = 1, SIM_GRAD = 2, SIM_TOPK = 3, SIM_RANK = 4 };
 
 // streaming top-k: per (row, column chunk) candidate buffer of TK_CAP entries; when it fills the warp keeps the
 // TK_KEEP best and raises the row's admission threshold
@@ -142,7 +142,55 @@ struct SimArgs {
     float* cand_thr;              // top-k: [chunks * Rpad] final admission threshold (-inf: nothing was dropped)
     int Rpad;
     int poly;                     // InfoNCE: a quarter of the exponentials on the FMA pipe (needs 2*c1 <= 120)
+    // rank of the positive (SIM_RANK): per-row window [rk_lo, rk_hi] around the exact positive score; scores above it
+    // are counted, scores inside it are listed as (row, column) pairs for exact rescoring
+    const float *rk_lo, *rk_hi;   // [R]
+    uint2* amb;                   // [amb_cap]
+    unsigned* amb_n;              // pairs listed so far (may run past amb_cap: the caller then falls back)
+    unsigned amb_cap;
 };
+
+// SIM_RANK epilogue strip: 64 fresh scores v[] (columns j0 .. j0+63) of `row`.  Columns past C and the row's own
+// positive are taken out; scores above the window are counted in `cnt`, scores inside it go to the pair list (one
+// atomicAdd per warp and strip reserves the slots of all 32 rows).
+__device__ __forceinline__ void rank_strip(const SimArgs& a, float (&v)[64], int j0, long long row, float lo, float hi,
+                                           long long dcol, int lane, int& cnt) {
+    if (__any_sync(FULL, j0 + 64 > a.C || (dcol >= j0 && dcol < j0 + 64))) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i)
+            if (j0 + i >= a.C || j0 + i == dcol) v[i] = -INFINITY;
+    }
+    int c_hi = 0, c_lo = 0;
+#pragma unroll
+    for (int i = 0; i < 64; ++i) {
+        c_hi += v[i] > hi;
+        c_lo += v[i] >= lo;
+    }
+    cnt += c_hi;
+    const int h = c_lo - c_hi;
+    if (__any_sync(FULL, h > 0)) {
+        int scan = h;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(FULL, scan, o);
+            if (lane >= o) scan += t;
+        }
+        const int total = __shfl_sync(FULL, scan, 31);
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(a.amb_n, (unsigned)total);
+        base = __shfl_sync(FULL, base, 0);
+        unsigned pos = base + (unsigned)(scan - h);
+        if (h > 0) {
+#pragma unroll
+            for (int i = 0; i < 64; ++i) {
+                if (v[i] >= lo && !(v[i] > hi)) {
+                    if (pos < a.amb_cap) a.amb[pos] = make_uint2((uint32_t)row, (uint32_t)(j0 + i));
+                    ++pos;
+                }
+            }
+        }
+    }
+}
 
 // InfoNCE epilogue strips: N fresh scores of one row -> exponentials, in batches of 16 (see exp16)
 template <bool POLY, int N>
@@ -545,13 +593,15 @@ simtile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
             // per 128-row block state (RB <= 2)
             long long row[RB];
             bool row_ok[RB];
-            float thr[RB];
+            float thr[RB], rhi[RB];
             int cnt[RB];
 #pragma unroll
             for (int rb = 0; rb < RB; ++rb) {
                 row[rb] = (long long)row0 + rb * ST_M + r_loc;
                 row_ok[rb] = row[rb] < a.R;
                 thr[rb] = row_ok[rb] ? -INFINITY : INFINITY;       // rows past R admit nothing
+                rhi[rb] = INFINITY;
+                if (MODE == SIM_RANK && row_ok[rb]) { thr[rb] = a.rk_lo[row[rb]]; rhi[rb] = a.rk_hi[row[rb]]; }
                 cnt[rb] = 0;
             }
             for (int t = 0; t < n_tiles; ++t) {
@@ -567,6 +617,8 @@ simtile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
                         if (row_ok[rb])
                             for (int i = 0; i < 64; ++i)
                                 if (j0 + i < a.C) a.out_part[row[rb] * a.C + j0 + i] = v[i];
+                    } else if (MODE == SIM_RANK) {
+                        rank_strip(a, v, j0, row[rb], thr[rb], rhi[rb], row[rb] + a.diag_offset, lane, cnt[rb]);
                     } else {
                         if (j0 + 64 > a.C) {                             // ragged last tile: columns past C never qualify
 #pragma unroll
@@ -586,6 +638,10 @@ simtile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
                     a.cand_cnt[slot] = row_ok[rb] ? cnt[rb] : 0;
                     a.cand_thr[slot] = thr[rb];
                 }
+            }
+            if (MODE == SIM_RANK) {                                  // columns certainly above the positive, per list
+#pragma unroll
+                for (int rb = 0; rb < RB; ++rb) a.cand_cnt[list * a.Rpad + row[rb]] = row_ok[rb] ? cnt[rb] : 0;
             }
         }
     }
@@ -748,9 +804,11 @@ static int launch_sim(SimArgs a, const void* x, const void* y, int chunks, cudaS
         case SIM_GRAD * 2: fn = simtile_kernel<SIM_GRAD, 1>; break;
         case SIM_TOPK * 2: fn = simtile_kernel<SIM_TOPK, 1>; break;
         case SIM_TOPK * 2 + 1: fn = simtile_kernel<SIM_TOPK, 2>; break;
+        case SIM_RANK * 2: fn = simtile_kernel<SIM_RANK, 1>; break;
+        case SIM_RANK * 2 + 1: fn = simtile_kernel<SIM_RANK, 2>; break;
         default: set_error("unsupported similarity-kernel variant"); return CFM_ERR_UNSUPPORTED;
     }
-    static bool attr[8] = {false};
+    static bool attr[10] = {false};
     if (!attr[a.mode * 2 + (a.rb - 1)]) {
         CFM_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr[a.mode * 2 + (a.rb - 1)] = true;
@@ -1024,7 +1082,94 @@ __global__ void __launch_bounds__(128) allpairs_rank_kernel(const float* __restr
     if (lane == 0) rank[row] = (tcol >= 0 && tcol < C) ? cnt + 1 : C;
 }
 
+// ---- rank of the positive through the tensor-core filter (SIM_RANK) ----
+// thread per row: exact (fp64 of the fp32 operands, same summation order as allpairs_rank_kernel) score of the row's
+// positive, and the fp32 window [d - e, d + e] outside of which a 16-bit-operand score decides the comparison
+__global__ void rank_prepare_kernel(const float* __restrict__ rows_f32, const float* __restrict__ cols_f32, int R, int C, int D,
+                                    long long diag_offset, float err, double* __restrict__ diag64, float* __restrict__ lo,
+                                    float* __restrict__ hi, int* __restrict__ extra, unsigned* __restrict__ amb_n) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row == 0) *amb_n = 0u;
+    if (row >= R) return;
+    const long long tcol = row + diag_offset;
+    extra[row] = 0;
+    if (tcol < 0 || tcol >= C) {           // no positive among these columns: nothing is counted, rank = C (see finish)
+        diag64[row] = 0.0; lo[row] = INFINITY; hi[row] = INFINITY;
+        return;
+    }
+    const float* u = rows_f32 + (long long)row * D;
+    const float* v = cols_f32 + tcol * D;
+    double st = 0.0;
+    for (int d = 0; d < D; ++d) st = fma((double)u[d], (double)v[d], st);
+    diag64[row] = st;
+    lo[row] = __double2float_rd(st - (double)err);
+    hi[row] = __double2float_ru(st + (double)err);
+}
+// thread per listed pair: exact comparison against the row's positive, ties broken by column index
+__global__ void rank_resolve_kernel(const float* __restrict__ rows_f32, const float* __restrict__ cols_f32, int D,
+                                    long long diag_offset, const double* __restrict__ diag64, const uint2* __restrict__ amb,
+                                    const unsigned* __restrict__ amb_n, unsigned amb_cap, int* __restrict__ extra) {
+    const unsigned n = min(*amb_n, amb_cap);
+    for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+        const uint2 e = amb[p];
+        const float* u = rows_f32 + (long long)e.x * D;
+        const float* v = cols_f32 + (long long)e.y * D;
+        double acc = 0.0;
+        for (int d = 0; d < D; ++d) acc = fma((double)u[d], (double)v[d], acc);
+        const double st = diag64[e.x];
+        const long long tcol = (long long)e.x + diag_offset;
+        if (acc > st || (acc == st && (long long)e.y < tcol)) atomicAdd(extra + e.x, 1);
+    }
+}
+__global__ void rank_finish_kernel(const int* __restrict__ part, int lists, int Rpad, const int* __restrict__ extra, int R, int C,
+                                   long long diag_offset, const unsigned* __restrict__ amb_n, unsigned amb_cap,
+                                   long long* __restrict__ rank, int* __restrict__ status) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row == 0) { status[0] = *amb_n > amb_cap ? 1 : 0; status[1] = (int)min(*amb_n, 0x7fffffffu); }
+    if (row >= R) return;
+    const long long tcol = row + diag_offset;
+    long long c = extra[row];
+    for (int l = 0; l < lists; ++l) c += part[(long long)l * Rpad + row];
+    rank[row] = (tcol >= 0 && tcol < C) ? c + 1 : C;
+}
+
 }  // namespace cfm
+
+extern "C" int cfm_allpairs_diag_rank(const float* rows_f32, const float* cols_f32, const void* rows_16, const void* cols_16,
+                                      int64_t operands_f16, int64_t R, int64_t C, int64_t D, int64_t Dp, int64_t diag_offset,
+                                      double err_bound, int64_t* rank, int32_t* status, int32_t* part, int32_t* extra,
+                                      double* diag64, float* window, void* amb, int64_t amb_cap, uint32_t* amb_n,
+                                      void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CFM_REQUIRE(rows_f32 && cols_f32 && rows_16 && cols_16 && rank && status && part && extra && diag64 && window && amb && amb_n,
+                CFM_ERR_INVALID, "null pointer");
+    CFM_REQUIRE(R >= 1 && C >= 1 && D >= 1 && D <= Dp && err_bound >= 0 && amb_cap >= 1 && amb_cap <= 0x7fffffffLL,
+                CFM_ERR_INVALID, "bad diagonal-rank arguments");
+    const int rb = sim_rb(R);
+    const int chunks = sim_chunks(R, C, rb);
+    SimArgs a{};
+    a.rb = rb;
+    a.mode = SIM_RANK; a.R = (int)R; a.C = (int)C; a.D = (int)D; a.Dp = (int)Dp;
+    a.f16 = operands_f16 != 0;
+    a.diag_offset = diag_offset;
+    a.cand_cnt = part;
+    a.Rpad = (int)((R + 2 * ST_M - 1) / (2 * ST_M)) * 2 * ST_M;
+    a.rk_lo = window; a.rk_hi = window + R;
+    a.amb = (uint2*)amb; a.amb_n = amb_n; a.amb_cap = (unsigned)amb_cap;
+    ProfScope prof(PROF_TOPK, stream);
+    rank_prepare_kernel<<<(int)((R + 127) / 128), 128, 0, stream>>>(rows_f32, cols_f32, (int)R, (int)C, (int)D, diag_offset,
+                                                                  (float)err_bound, diag64, window, window + R, extra, amb_n);
+    CFM_LAUNCH_CHECK();
+    int rc = launch_sim(a, rows_16, cols_16, chunks, stream);
+    if (rc) return rc;
+    rank_resolve_kernel<<<sm_count() * 8, 256, 0, stream>>>(rows_f32, cols_f32, (int)D, diag_offset, diag64, (const uint2*)amb,
+                                                           amb_n, (unsigned)amb_cap, extra);
+    CFM_LAUNCH_CHECK();
+    rank_finish_kernel<<<(int)((R + 127) / 128), 128, 0, stream>>>(part, 2 * chunks, a.Rpad, extra, (int)R, (int)C, diag_offset,
+                                                                 amb_n, (unsigned)amb_cap, (long long*)rank, status);
+    CFM_LAUNCH_CHECK();
+    return CFM_OK;
+}
 
 extern "C" int cfm_allpairs_topk(const float* rows_f32, const float* cols_f32, const void* rows_bf16, const void* cols_bf16,
                                  int64_t operands_f16, int64_t R, int64_t C, int64_t D, int64_t Dp, int64_t k, double scale,

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define CFM_ABI_VERSION 2
+#define CFM_ABI_VERSION 3
 #define CFM_MAX_TABLES 16
 
 #define CFM_OK 0
@@ -266,6 +266,31 @@ int cfm_cosine_head_bwd(const float* u, const float* v, const float* logit_scale
                         float* d_logit_scale /* [1] */, float* partial /* >= 4096 floats */, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Projection heads of the contrastive model:  out = normalize(W2 . relu(W1 . x + b1) + b2).
+ * replaces: ceo_firm_matching/contrastive.py:41-50 (firm_projector / ceo_projector, nn.Sequential(Linear, ReLU,
+ *           Linear)), :96-97 (F.normalize(..., dim=1), eps = 1e-12) and their autograd (:244-260).
+ * fp32 FMA arithmetic, layers up to 64 wide; several heads (both sides of the model) share one launch.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct cfm_projector {
+    int64_t d_in, d_hid, d_out;
+    const float *w1, *b1, *w2, *b2;   /* torch layouts: w1 [d_hid,d_in], w2 [d_out,d_hid] */
+    const float *x;                   /* [B,d_in] */
+    float *hid;                       /* [B,d_hid] relu(W1 x + b1): written by fwd, read by bwd */
+    float *raw;                       /* [B,d_out] W2 hid + b2 before normalisation: written by fwd, read by bwd */
+    float *out;                       /* [B,d_out] raw / max(||raw||, eps) (unused by bwd) */
+} cfm_projector_t;
+typedef struct cfm_projector_grads {
+    const float* g_out;               /* [B,d_out] gradient w.r.t. out */
+    float *dx;                        /* [B,d_in] (nullable) */
+    float *dw1, *db1, *dw2, *db2;     /* parameter gradients (overwritten) */
+    float *scratch;                   /* cfm_projector_scratch_floats(head, B) floats: per-CTA partials, added in CTA order */
+} cfm_projector_grads_t;
+int64_t cfm_projector_scratch_floats(const cfm_projector_t* head, int64_t B);
+int cfm_projector_fwd(const cfm_projector_t* heads, int64_t n_heads /* 1..4 */, int64_t B, double eps, void* stream);
+int cfm_projector_bwd(const cfm_projector_t* heads, const cfm_projector_grads_t* grads, int64_t n_heads, int64_t B,
+                      double eps, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Structural head: softmax(c_logits) . A . softmax(f_logits) expected match, KL distillation loss and
  * the gradients w.r.t. both logit sets, one kernel.
  * replaces: structural_model.py:130-141 + structural_training.py:75-77 (+ autograd of both).
@@ -345,6 +370,20 @@ int cfm_topk_merge(const void* part_score, int64_t score_is_f64, const int64_t* 
  * (contrastive.py:312-320), scores formed in fp64 from the fp32 operands */
 int cfm_allpairs_rank(const float* rows_f32, const float* cols_f32, int64_t R, int64_t C, int64_t D,
                       const int64_t* target_col /* [R] */, int64_t* rank /* [R] */, void* stream);
+/* The same rank for the positive pair on a shifted diagonal, target column = i + diag_offset (retrieval metrics of
+ * contrastive.py:296-332 / run_deep_extensions.py:470-483), counted in the epilogue of the tcgen05 similarity kernel:
+ * every 16-bit-operand score outside the window [d_i - err_bound, d_i + err_bound] around the row's exact positive
+ * score d_i decides its comparison on the spot; the (row, column) pairs inside the window are listed and compared
+ * exactly (fp64 of the fp32 operands, ties by column index), so `rank` equals cfm_allpairs_rank's.  err_bound must
+ * bound |16-bit-operand score - exact score| (2u |row| |col| + the fp32 accumulation error; u = 2^-11 fp16, 2^-9 bf16).
+ *   status[0] = 1 when more than amb_cap pairs fell inside the windows (rank is then incomplete: use
+ *   cfm_allpairs_rank), status[1] = pairs listed.  Scratch: part [cfm_simtile_chunks(R,C) * Rpad] with Rpad = R rounded
+ *   up to 256, extra [R], diag64 [R], window [2R], amb [amb_cap] pairs of uint32, amb_n [1]. */
+int cfm_allpairs_diag_rank(const float* rows_f32, const float* cols_f32, const void* rows_16, const void* cols_16,
+                           int64_t operands_f16, int64_t R, int64_t C, int64_t D, int64_t Dp, int64_t diag_offset,
+                           double err_bound, int64_t* rank /* [R] */, int32_t* status /* [2] */, int32_t* part,
+                           int32_t* extra, double* diag64, float* window, void* amb, int64_t amb_cap, uint32_t* amb_n,
+                           void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Self-test of the tensor-core building blocks of the tower kernels (tcgen05 kind::tf32 on (hi, lo)-split fp32
