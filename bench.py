@@ -306,6 +306,24 @@ def secondary_metrics(device, world, rank, dist):
                               "roofline": {"bound": "tensor", "achieved": flops / (ms * 1e-3) / 1e12 / world,
                                            "peak": bf16_peak, "unit": "TFLOP/s",
                                            "frac": flops / (ms * 1e-3) / 1e12 / world / bf16_peak}}
+    if world == 1:
+        # ---- retrieval ranks: rank of the true partner of every row among all columns, counted in the
+        # epilogue of the same tensor-core kernel; positives correlated with their rows as after training ----
+        from ceo_firm_matching.scoring import diagonal_ranks
+        Nr = 262_144
+        fr = firms[:Nr]
+        cr = F.normalize(0.8 * fr + F.normalize(torch.randn(Nr, Dl, device=device, generator=g), dim=1), dim=1)
+        diagonal_ranks(fr[:8192], cr[:8192], method="tensor")
+        ms_t = _time_cuda(lambda: diagonal_ranks(fr, cr, method="tensor"), 2, None, device)
+        Ne = 16_384
+        ms_e = _time_cuda(lambda: diagonal_ranks(fr[:Ne], cr, method="exact"), 1, None, device)
+        out["retrieval_ranks"] = {"workload": "rank of the diagonal, 262144 firms x 262144 CEOs, D=60 (contrastive.py:296-332 "
+                                              "without its 5000-row cap), fp16 tensor-core filter + exact fp64 near-ties",
+                                  "ms": ms_t, "value": float(Nr) * Nr / (ms_t * 1e-3), "unit": "scores/s",
+                                  "exact_fp64_simt_kernel_ms_scaled": ms_e * (Nr / Ne),
+                                  "roofline": {"bound": "tensor", "achieved": 2.0 * Nr * Nr * Dl / (ms_t * 1e-3) / 1e12,
+                                               "peak": bf16_peak, "unit": "TFLOP/s",
+                                               "frac": 2.0 * Nr * Nr * Dl / (ms_t * 1e-3) / 1e12 / bf16_peak}}
     return out
 
 

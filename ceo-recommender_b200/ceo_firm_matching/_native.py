@@ -134,6 +134,8 @@ PROTOTYPES = {
     "cfm_simtile_set_poly": (C.c_int, [_I]),
     "cfm_pack_rows_bf16": (C.c_int, [_V, _I, _I, _I, _V, _V]),
     "cfm_infonce_rowsum": (C.c_int, [_V, _V, _I, _I, _I, _D, _I, _V, _V, _V, _V]),
+    "cfm_infonce_colpart_floats": (i64, [_I, _I]),
+    "cfm_infonce_rowcolsum": (C.c_int, [_V, _V, _I, _I, _I, _D, _I, _V, _V, _V, _V, _V, _V]),
     "cfm_infonce_loss": (C.c_int, [_V, _V, _V, _I, _D, _I, _V, _V]),
     "cfm_infonce_grad": (C.c_int, [_V, _V, _I, _I, _I, _I, _D, _I, _I, _V, _V, _V, _V, _V, _V, _V]),
     "cfm_simtile_scores": (C.c_int, [_V, _V, _I, _I, _I, _V, _V]),

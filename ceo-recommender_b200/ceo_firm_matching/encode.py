@@ -15,7 +15,6 @@ from typing import List, Optional, Sequence, Tuple
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from . import ops
 
@@ -65,7 +64,13 @@ def encode(module: nn.Module, f_numeric: torch.Tensor, f_cat: torch.Tensor, c_nu
     as the reference's ``encode`` methods do (``multitask_model.py:139,145``)."""
     u, v = ops.run_towers(tower_handles(module), [(f_numeric, f_cat), (c_numeric, c_cat)], module.training)
     if normalize:
-        u, v = F.normalize(u, dim=1), F.normalize(v, dim=1)
+        # F.normalize semantics (x / max(||x||, 1e-12)) from the cosine-head kernel's unit-latent outputs
+        zero = torch.zeros((), device=u.device)
+        if u.shape == v.shape:
+            _, u, v = ops.CosineHeadFunction.apply(u, v, zero, 1e-12, True)
+        else:                                   # towers of different widths: one launch per side
+            _, u, _ = ops.CosineHeadFunction.apply(u, u, zero, 1e-12, True)
+            _, v, _ = ops.CosineHeadFunction.apply(v, v, zero, 1e-12, True)
     return u, v
 
 

@@ -829,6 +829,22 @@ def infonce_rowsum(xb: torch.Tensor, yb: torch.Tensor, temperature: float, diag_
     return rowsum, diag
 
 
+def infonce_rowcolsum(xb: torch.Tensor, yb: torch.Tensor, temperature: float, diag_offset: int = 0):
+    """One pass over S = X.Y^T: rowsum[i] = sum_j exp((s_ij - 1)/T), colsum[j] = sum_i exp((s_ij - 1)/T) (the row sums
+    of S^T) and diag[i] = s_(i, i+diag_offset)."""
+    R, C, dp = xb.shape[0], yb.shape[0], xb.shape[1]
+    dev = xb.device
+    chunks = N.lib().cfm_simtile_chunks(R, C)
+    part = torch.empty(chunks * R, device=dev)
+    col_part = torch.empty(N.lib().cfm_infonce_colpart_floats(R, C), device=dev)
+    rowsum, colsum = torch.empty(R, device=dev), torch.empty(C, device=dev)
+    diag = torch.zeros(R, device=dev)
+    with torch.cuda.device(dev):
+        N.check(N.lib().cfm_infonce_rowcolsum(N.ptr(xb), N.ptr(yb), R, C, dp, temperature, diag_offset, N.ptr(rowsum),
+                                              N.ptr(colsum), N.ptr(diag), N.ptr(part), N.ptr(col_part), N.stream_ptr()))
+    return rowsum, colsum, diag
+
+
 def infonce_grad(xb, yb, D, temperature, diag_offset, B_total, rowsum_x, rowsum_y, diag, g_loss):
     R, C, dp = xb.shape[0], yb.shape[0], xb.shape[1]
     dev = xb.device
@@ -844,16 +860,16 @@ def infonce_grad(xb, yb, D, temperature, diag_offset, B_total, rowsum_x, rowsum_
 
 class InfoNCEFunction(torch.autograd.Function):
     """apply(firm_proj [B,D], ceo_proj [B,D], temperature) -> scalar symmetric InfoNCE loss.
-    Four passes of the similarity-tile kernel (row sums of S and of S^T, then dF and dC); the [B,B] matrix only
-    ever exists as 128x128 TMEM accumulators."""
+    Three passes of the similarity-tile kernel (row AND column sums of S in one, then dF and dC); the [B,B] matrix
+    only ever exists as 128x128 TMEM accumulators."""
 
     @staticmethod
     def forward(ctx, firm_proj, ceo_proj, temperature):
         _require_cuda(firm_proj, ceo_proj)
         B, D = firm_proj.shape
         fb, cb = pack_bf16(firm_proj), pack_bf16(ceo_proj)
-        rs_f, diag = infonce_rowsum(fb, cb, temperature)               # row sums of S  (firm -> ceo)
-        rs_c, _ = infonce_rowsum(cb, fb, temperature, want_diag=False)  # row sums of S^T (ceo -> firm)
+        # one pass over S: its row sums (firm -> ceo) and its column sums (= row sums of S^T, ceo -> firm)
+        rs_f, rs_c, diag = infonce_rowcolsum(fb, cb, temperature)
         loss = torch.empty((), device=firm_proj.device)
         with torch.cuda.device(firm_proj.device):
             N.check(N.lib().cfm_infonce_loss(N.ptr(rs_f), N.ptr(rs_c), N.ptr(diag), B, temperature, B, N.ptr(loss),

@@ -130,6 +130,24 @@ __host__ __device__ __forceinline__ bool drop_keep(const DropCtx& d, const Philo
     return v >= d.thresh;
 }
 
+// Column sums over the lanes of a warp by recursive halving: every step a lane keeps one half of its columns and
+// sends the other half to its partner (xor mask), so 32 lanes x NC columns cost NC - NC/32 shuffles instead of
+// 5 * NC.  After masks 16..1 lane l holds the sums of columns (NC/32)*l ... ; with masks 8..1 (16-lane groups, the
+// M = 64 accumulator layout) lane l < 16 holds columns (NC/16)*l ... of its group.
+template <int N, int MASK>
+struct Halve {
+    __device__ static __forceinline__ void run(float (&x)[N], int lane) {
+        const bool up = (lane & MASK) != 0;
+#pragma unroll
+        for (int i = 0; i < N / 2; ++i) {
+            const float keep = up ? x[i + N / 2] : x[i];
+            const float send = up ? x[i] : x[i + N / 2];
+            x[i] = keep + __shfl_xor_sync(FULL, send, MASK);
+        }
+        if constexpr (MASK > 1) Halve<N / 2, MASK / 2>::run(reinterpret_cast<float (&)[N / 2]>(x), lane);
+    }
+};
+
 __host__ __device__ __forceinline__ int pad_ld(int k) {   // leading dim: multiple of 4 floats, (ld/4) odd
     int ld = (k + 3) & ~3;
     if (((ld >> 2) & 1) == 0) ld += 4;

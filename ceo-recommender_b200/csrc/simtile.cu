@@ -23,11 +23,14 @@ constexpr int ST_STAGES = 3;
 // Y-tile ring: the gradient kernel keeps four tiles (tiles t .. t+2 are in use by GEMM 1 / GEMM 2, t+3 is in flight)
 __host__ __device__ constexpr int sim_stages(int mode) { return mode == 2 ? 4 : ST_STAGES; }
 // TMA warp, MMA warp, then 16 epilogue warps in the InfoNCE modes (row sums, gradients), 8 otherwise
-__host__ __device__ constexpr int sim_threads(int mode) { return 64 + ((mode == 1 || mode == 2) ? 16 : 8) * 32; }
+__host__ __device__ constexpr int sim_threads(int mode, int rb = 1) {
+    (void)rb;
+    return 64 + ((mode == 1 || mode == 2 || mode == 5) ? 16 : 8) * 32;
+}
 constexpr int KB_BYTES = ST_M * 128;                   // one [128 rows x 64 bf16] swizzled block = 16 KB
 constexpr float LOG2E = 1.4426950408889634f;
 
-enum SimMode { SIM_SCORES = 0, SIM_ROWSUM = 1, SIM_GRAD = 2, SIM_TOPK = 3, SIM_RANK = 4 };
+enum SimMode { SIM_SCORES = 0, SIM_ROWSUM = 1, SIM_GRAD = 2, SIM_TOPK = 3, SIM_RANK = 4, SIM_ROWCOL = 5 };
 
 // streaming top-k: per (row, column chunk) candidate buffer of TK_CAP entries; when it fills the warp keeps the
 // TK_KEEP best and raises the row's admission threshold
@@ -142,6 +145,8 @@ struct SimArgs {
     float* cand_thr;              // top-k: [chunks * Rpad] final admission threshold (-inf: nothing was dropped)
     int Rpad;
     int poly;                     // InfoNCE: a quarter of the exponentials on the FMA pipe (needs 2*c1 <= 120)
+    float* col_part;              // SIM_ROWCOL: [row blocks, Cpad] column sums of the same exponentials per 128-row block
+    int Cpad;
     // rank of the positive (SIM_RANK): per-row window [rk_lo, rk_hi] around the exact positive score; scores above it
     // are counted, scores inside it are listed as (row, column) pairs for exact rescoring
     const float *rk_lo, *rk_hi;   // [R]
@@ -203,6 +208,33 @@ __device__ __forceinline__ void rowsum_strip(const float (&v)[N], float c1, floa
         for (int i = 0; i < 16; ++i) acc[i & 3] += e[i];
     }
 }
+// SIM_ROWCOL: 32 fresh scores of one row (columns jp ..) -> exponentials, added to the row's sum AND summed over the
+// warp's 32 rows by recursive halving (one shuffle per column); lane l returns the column sum of column
+// jp + 16 * (l & 1) + (l >> 1).  Rows past R (`my_ok` false) and columns past C contribute nothing.
+template <bool POLY>
+__device__ __forceinline__ float rowcol_piece(const float (&v)[32], int jp, int C, float c1, float c2, bool my_ok, bool all_ok,
+                                              int lane, float (&acc)[4]) {
+    float cs[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        float e[16];
+        if (jp + 32 <= C) {
+            exp16<POLY>(v + 16 * h, c1, c2, e);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) e[i] = (jp + 16 * h + i < C) ? ex2_approx(fmaf(v[16 * h + i], c1, -c2)) : 0.f;
+        }
+        if (!all_ok) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) e[i] = my_ok ? e[i] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i & 3] += e[i];
+        Halve<16, 16>::run(e, lane);
+        cs[h] = e[0] + __shfl_xor_sync(FULL, e[0], 1);
+    }
+    return (lane & 1) ? cs[1] : cs[0];
+}
 // ry: alpha / column sums of the N columns (shared memory, 16-byte aligned); dst16(i0 / 8) receives eight bf16 values
 template <bool POLY, int N, class Store>
 __device__ __forceinline__ void grad_strip(const float (&v)[N], const float* ry, float rx, float c1, float c2, Store&& store16) {
@@ -247,7 +279,7 @@ __device__ __forceinline__ void topk_admit(const SimArgs& a, const float (&v)[64
 }
 
 struct SimSmem {                  // offsets from the 1024-aligned base
-    int x, y, g, ry, bars, tmem_slot, total;
+    int x, y, g, ry, cs, bars, tmem_slot, total;
 };
 __host__ __device__ inline SimSmem sim_smem(int Dp, int mode, int rb) {
     SimSmem s;
@@ -257,6 +289,7 @@ __host__ __device__ inline SimSmem sim_smem(int Dp, int mode, int rb) {
     s.y = o; o += sim_stages(mode) * nkb * KB_BYTES;
     s.g = o; o += mode == SIM_GRAD ? 2 * 2 * KB_BYTES : 0;
     s.ry = o; o += 4 * ST_N * 4;
+    s.cs = o; o += mode == SIM_ROWCOL ? 4 * 2 * 4 * 64 * 4 : 0;      // column sums: [group][tile parity][warp][64 columns]
     s.bars = o; o += 32 * 8;
     s.tmem_slot = o; o += 16;
     // slack for the manual 1024-byte alignment; the gradient kernel fills shared memory to the last kilobyte and
@@ -266,7 +299,7 @@ __host__ __device__ inline SimSmem sim_smem(int Dp, int mode, int rb) {
 }
 
 template <int MODE, int RB>
-__global__ void __launch_bounds__(sim_threads(MODE), 1)
+__global__ void __launch_bounds__(sim_threads(MODE, RB), 1)
 simtile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_y, const SimArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic on the __shared__ array: accesses compile to LDS/STS (a uintptr_t round trip makes them generic LD/ST)
@@ -288,7 +321,7 @@ simtile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
     const int tile0 = blockIdx.y * a.tiles_per_chunk;
     const int n_tiles = max(0, min(a.tiles_per_chunk, a.n_col_tiles - tile0));
     constexpr bool grad = MODE == SIM_GRAD;
-    constexpr bool NCE = MODE == SIM_ROWSUM || MODE == SIM_GRAD;      // 16 epilogue warps
+    constexpr bool NCE = MODE == SIM_ROWSUM || MODE == SIM_GRAD || MODE == SIM_ROWCOL;      // 16 epilogue warps
     constexpr int NSTG = sim_stages(MODE);
     // threads that hand an S buffer back: every buffer is drained by two four-warp groups (column halves), except in
     // the top-k variant with two row blocks, where one group walks a whole buffer (one candidate stream per row)
@@ -407,10 +440,14 @@ simtile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
         const long long myrow = (long long)row0 + rbo * ST_M + r_loc;
         const bool my_ok = myrow < a.R;
         const long long dcol = myrow + a.diag_offset;  // column of this row's positive pair
-        if constexpr (MODE == SIM_ROWSUM) {
+        if constexpr (MODE == SIM_ROWSUM || MODE == SIM_ROWCOL) {
+            constexpr bool COLS = MODE == SIM_ROWCOL;
             float acc[4] = {0.f, 0.f, 0.f, 0.f}, dv = 0.f;
             bool hd = false;
-            for (int t = t_first; t < n_tiles; t += t_step) {
+            const bool all_ok = __all_sync(FULL, my_ok);
+            float* sm_cs = reinterpret_cast<float*>(sm + L.cs) + g * (2 * 4 * 64);
+            int u = 0;                                 // tiles this group has walked (column-sum buffer parity)
+            for (int t = t_first; t < n_tiles; t += t_step, ++u) {
                 const int b = t & 1, sb = rbo * 2 + b;
                 const int j0 = (tile0 + t) * ST_N + 64 * ch;
                 const uint32_t taddr = tmem_s0 + sb * ST_N + 64 * ch + lane_addr;
@@ -432,17 +469,56 @@ simtile_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
                         hd = true;
                     }
                 };
-                {
-                    float va[32];
-                    tmem_ld32(taddr, va);
-                    piece(va, j0);
-                }
-                {
-                    float vb[32];
-                    tmem_ld32(taddr + 32, vb);
-                    tc_fence_before();
-                    mbar_arrive(s_empty + sb);         // the buffer is in registers: it may be refilled
-                    piece(vb, j0 + 32);
+                auto diag_pick = [&](const float (&v)[32], int jp) {
+                    if (diag_here && dcol >= jp && dcol < jp + 32) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (jp + i == dcol) dv = v[i];
+                        hd = true;
+                    }
+                };
+                if constexpr (!COLS) {
+                    {
+                        float va[32];
+                        tmem_ld32(taddr, va);
+                        piece(va, j0);
+                    }
+                    {
+                        float vb[32];
+                        tmem_ld32(taddr + 32, vb);
+                        tc_fence_before();
+                        mbar_arrive(s_empty + sb);         // the buffer is in registers: it may be refilled
+                        piece(vb, j0 + 32);
+                    }
+                } else {
+                    // the same exponentials feed the row sums and, summed over the 128 rows of the block, the column
+                    // sums (= the row sums of S^T: the second similarity pass of the loss is not needed)
+                    float csa, csb;
+                    {
+                        float va[32];
+                        tmem_ld32(taddr, va);
+                        csa = a.poly ? rowcol_piece<true>(va, j0, a.C, a.c1, a.c2, my_ok, all_ok, lane, acc)
+                                     : rowcol_piece<false>(va, j0, a.C, a.c1, a.c2, my_ok, all_ok, lane, acc);
+                        diag_pick(va, j0);
+                    }
+                    {
+                        float vb[32];
+                        tmem_ld32(taddr + 32, vb);
+                        tc_fence_before();
+                        mbar_arrive(s_empty + sb);
+                        csb = a.poly ? rowcol_piece<true>(vb, j0 + 32, a.C, a.c1, a.c2, my_ok, all_ok, lane, acc)
+                                     : rowcol_piece<false>(vb, j0 + 32, a.C, a.c1, a.c2, my_ok, all_ok, lane, acc);
+                        diag_pick(vb, j0 + 32);
+                    }
+                    float* buf = sm_cs + (u & 1) * (4 * 64);
+                    const int cl = 16 * (lane & 1) + (lane >> 1);
+                    buf[q * 64 + cl] = csa;
+                    buf[q * 64 + 32 + cl] = csb;
+                    named_bar_sync(4 + g, 128);        // the four row quadrants of this group have delivered
+                    if (r_loc < 64) {                  // fixed order over the quadrants: bitwise reproducible
+                        const float cs4 = (buf[r_loc] + buf[64 + r_loc]) + (buf[128 + r_loc] + buf[192 + r_loc]);
+                        a.col_part[((long long)blockIdx.x * RB + rbo) * a.Cpad + j0 + r_loc] = cs4;
+                    }
                 }
             }
             float sum = (acc[0] + acc[1]) + (acc[2] + acc[3]);
@@ -685,6 +761,20 @@ __global__ void rowsum_finalize_kernel(const float* __restrict__ part, int chunk
 
 // dX[r, d] = g_loss * ( sum_chunks part[c][r][d] + (g_rr - 1/(B T)) * y[r + off][d] ),
 // g_rr = alpha * exp((s_rr - 1)/T) * (1/rowsum_x[r] + 1/rowsum_y[r + off]) : the positive pair, kept in fp32
+// column sums: the per-row-block partials added in row-block order (four interleaved chains, fixed association)
+__global__ void colsum_finalize_kernel(const float* __restrict__ part, int nrb, int Cpad, int C, float* __restrict__ out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= C) return;
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    int b = 0;
+    for (; b + 4 <= nrb; b += 4) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s[k] += part[(long long)(b + k) * Cpad + j];
+    }
+    for (; b < nrb; ++b) s[b & 3] += part[(long long)b * Cpad + j];
+    out[j] = (s[0] + s[1]) + (s[2] + s[3]);
+}
+
 __global__ void grad_finalize_kernel(const float* __restrict__ part, int chunks, int R, int D, int Dp, int C,
                                      const __nv_bfloat16* __restrict__ y, long long diag_offset, float diag_coef,
                                      float alpha, float c1, const float* __restrict__ diag,
@@ -804,17 +894,19 @@ static int launch_sim(SimArgs a, const void* x, const void* y, int chunks, cudaS
         case SIM_GRAD * 2: fn = simtile_kernel<SIM_GRAD, 1>; break;
         case SIM_TOPK * 2: fn = simtile_kernel<SIM_TOPK, 1>; break;
         case SIM_TOPK * 2 + 1: fn = simtile_kernel<SIM_TOPK, 2>; break;
+        case SIM_ROWCOL * 2: fn = simtile_kernel<SIM_ROWCOL, 1>; break;
+        case SIM_ROWCOL * 2 + 1: fn = simtile_kernel<SIM_ROWCOL, 2>; break;
         case SIM_RANK * 2: fn = simtile_kernel<SIM_RANK, 1>; break;
         case SIM_RANK * 2 + 1: fn = simtile_kernel<SIM_RANK, 2>; break;
         default: set_error("unsupported similarity-kernel variant"); return CFM_ERR_UNSUPPORTED;
     }
-    static bool attr[10] = {false};
+    static bool attr[12] = {false};
     if (!attr[a.mode * 2 + (a.rb - 1)]) {
         CFM_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr[a.mode * 2 + (a.rb - 1)] = true;
     }
     dim3 grid((a.R + a.rb * ST_M - 1) / (a.rb * ST_M), chunks);
-    fn<<<grid, sim_threads(a.mode), L.total, stream>>>(tmx, tmy, a);
+    fn<<<grid, sim_threads(a.mode, a.rb), L.total, stream>>>(tmx, tmy, a);
     CFM_LAUNCH_CHECK();
     return CFM_OK;
 }
@@ -894,6 +986,39 @@ extern "C" int cfm_infonce_rowsum(const void* x_bf16, const void* y_bf16, int64_
     int rc = launch_sim(a, x_bf16, y_bf16, chunks, stream);
     if (rc) return rc;
     rowsum_finalize_kernel<<<(int)std::min<long long>((R + 255) / 256, 592), 256, 0, stream>>>(part, 2 * chunks, (int)R, rowsum);
+    CFM_LAUNCH_CHECK();
+    return CFM_OK;
+}
+
+static long long rowcol_blocks(long long R) { return ((R + 2 * ST_M - 1) / (2 * ST_M)) * 2; }   // even: CTAs may hold two
+static long long rowcol_cpad(long long C) { return ((C + ST_N - 1) / ST_N) * ST_N; }
+
+extern "C" int64_t cfm_infonce_colpart_floats(int64_t R, int64_t C) {
+    return (R < 1 || C < 1) ? 0 : rowcol_blocks(R) * rowcol_cpad(C);
+}
+
+extern "C" int cfm_infonce_rowcolsum(const void* x_bf16, const void* y_bf16, int64_t R, int64_t C, int64_t Dp,
+                                     double temperature, int64_t diag_offset, float* rowsum, float* colsum, float* diag,
+                                     float* part, float* col_part, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CFM_REQUIRE(x_bf16 && y_bf16 && rowsum && colsum && part && col_part && temperature > 0, CFM_ERR_INVALID,
+                "bad rowcolsum arguments");
+    const int rb = sim_rb(R);
+    const int chunks = sim_chunks(R, C, rb);
+    SimArgs a{};
+    a.rb = rb;
+    a.mode = SIM_ROWCOL; a.R = (int)R; a.C = (int)C; a.D = (int)Dp; a.Dp = (int)Dp;
+    a.c1 = (float)(LOG2E / temperature); a.c2 = (float)(LOG2E / temperature);
+    a.diag_offset = diag_offset; a.out_part = part; a.diag = diag;
+    a.col_part = col_part; a.Cpad = (int)rowcol_cpad(C);
+    a.poly = (g_poly_mask & 1) && 2.f * a.c1 <= 120.f;
+    ProfScope prof(PROF_NCE_ROWSUM, stream);
+    int rc = launch_sim(a, x_bf16, y_bf16, chunks, stream);
+    if (rc) return rc;
+    rowsum_finalize_kernel<<<(int)std::min<long long>((R + 255) / 256, 592), 256, 0, stream>>>(part, 2 * chunks, (int)R, rowsum);
+    CFM_LAUNCH_CHECK();
+    const int nrb = (int)(((R + rb * ST_M - 1) / (rb * ST_M)) * rb);      // row blocks the grid covered
+    colsum_finalize_kernel<<<(int)((C + 255) / 256), 256, 0, stream>>>(col_part, nrb, a.Cpad, (int)C, colsum);
     CFM_LAUNCH_CHECK();
     return CFM_OK;
 }

@@ -327,6 +327,15 @@ int cfm_pack_rows_bf16(const float* in /* [R,D] */, int64_t R, int64_t D, int64_
 int cfm_infonce_rowsum(const void* x_bf16, const void* y_bf16, int64_t R, int64_t C, int64_t Dp, double temperature,
                        int64_t diag_offset, float* rowsum /* [R] */, float* diag /* [R] nullable */, float* part,
                        void* stream);
+/* Row sums AND column sums of exp((S - 1/T)/T) from ONE pass over S = X . Y^T: the exponentials of every tile are
+ * added along the rows (as above) and, summed over the 128 rows of the tile by warp shuffles, along the columns.
+ * colsum[j] = sum_i exp((x_i.y_j - 1)/T) is the row sum of S^T, so the forward of the symmetric loss
+ * (contrastive.py:129-138) needs one similarity pass instead of two.  col_part: cfm_infonce_colpart_floats(R, C)
+ * floats of scratch (per-128-row-block column sums, added in block order: bitwise reproducible). */
+int64_t cfm_infonce_colpart_floats(int64_t R, int64_t C);
+int cfm_infonce_rowcolsum(const void* x_bf16, const void* y_bf16, int64_t R, int64_t C, int64_t Dp, double temperature,
+                          int64_t diag_offset, float* rowsum /* [R] */, float* colsum /* [C] */,
+                          float* diag /* [R] nullable */, float* part, float* col_part, void* stream);
 int cfm_infonce_loss(const float* rowsum_row, const float* rowsum_col, const float* diag, int64_t n,
                      double temperature, int64_t B_total, float* loss /* [1] */, void* stream);
 int cfm_infonce_grad(const void* x_bf16, const void* y_bf16, int64_t R, int64_t C, int64_t D, int64_t Dp,

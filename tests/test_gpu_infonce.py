@@ -119,3 +119,30 @@ def test_row_block_variants_agree_with_oracle(rb):
     assert float(loss) == pytest.approx(float(lo), rel=2e-5, abs=1e-5)
     assert_close_scaled(f.grad, fq.grad, 6e-3, "d_firm")
     assert_close_scaled(c.grad, cq.grad, 6e-3, "d_ceo")
+
+
+@pytest.mark.parametrize("rb", [1, 2])
+@pytest.mark.parametrize("poly", [0, 1])
+@pytest.mark.parametrize("shape", [(300, 1500, 600), (1500, 1100, 0), (129, 130, 1), (2048, 2048, 0)])
+def test_one_pass_row_and_column_sums(shape, poly, rb):
+    """cfm_infonce_rowcolsum: the column sums that come out of the row-sum pass (shuffle reduction over each tile's
+    128 rows, per-row-block partials added in block order) equal the row sums of the transposed problem; ragged row
+    and column tiles contribute nothing; both CTA shapes and both exponential variants."""
+    from ceo_firm_matching import _native as N
+    from ceo_firm_matching import ops
+    R, C, off = shape
+    x, y = _unit(R, 128, 7), _unit(C, 128, 8)
+    xb, yb = ops.pack_bf16(x.to(DEV)), ops.pack_bf16(y.to(DEV))
+    N.check(N.lib().cfm_simtile_set_rb(rb)); N.check(N.lib().cfm_simtile_set_poly(poly))
+    try:
+        rs, cs, diag = ops.infonce_rowcolsum(xb, yb, 0.07, diag_offset=off)
+        rs2, cs2, _ = ops.infonce_rowcolsum(xb, yb, 0.07, diag_offset=off)
+    finally:
+        N.check(N.lib().cfm_simtile_set_rb(0)); N.check(N.lib().cfm_simtile_set_poly(1))
+    s = xb.float().cpu().double() @ yb.float().cpu().double().t()
+    e = torch.exp((s - 1) / 0.07)
+    assert_close_scaled(rs, e.sum(1), 2e-5, "rowsum")
+    assert_close_scaled(cs, e.sum(0), 2e-5, "colsum")
+    n = min(R, C - off)
+    assert_close_scaled(diag[:n], s[torch.arange(n), torch.arange(n) + off], 2e-6, "diag", floor=1e-6)
+    assert torch.equal(rs, rs2) and torch.equal(cs, cs2)           # bitwise reproducible
