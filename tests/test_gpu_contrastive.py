@@ -121,3 +121,82 @@ def test_diagonal_ranks_match_a_full_sort():
     order = np.argsort(-sim, axis=1, kind="stable")
     want = np.array([int(np.where(order[i] == i)[0][0]) + 1 for i in range(700)])
     np.testing.assert_array_equal(ranks, want)
+
+
+def test_train_contrastive_follows_oracle_trajectory(monkeypatch, capsys):
+    """The whole loop of contrastive.py:197-272 (InfoNCE branch): 6 epochs over 512 synthetic rows in batches of 256,
+    dropout off, no shuffle; the printed losses of epochs 0 and 5 and the parameter movement must follow an oracle loop
+    (CPU autograd on oracle.contrastive_forward + oracle.info_nce, torch Adam) started from the same initial
+    parameters.  The InfoNCE part runs in bf16 on the tensor cores: printed losses 2e-3; Adam's normalised update turns
+    a flipped sign of a near-zero gradient entry into a +-lr step, so the movement of every tensor (trained minus
+    initial) is compared in relative L2 norm (30 %)."""
+    import contextlib
+    import io
+    import re
+    from torch.utils.data import DataLoader
+    import ceo_firm_matching as cfm
+    import oracle
+    from ceo_firm_matching import contrastive as cmod
+    from ceo_firm_matching import model as model_mod
+    from helpers import dead_bias_names
+    real_mlp = model_mod._mlp
+
+    def mlp_no_dropout(i, o):
+        seq = real_mlp(i, o)
+        for mod in seq:
+            if isinstance(mod, torch.nn.Dropout):
+                mod.p = 0.0
+        return seq
+
+    monkeypatch.setattr(model_mod, "_mlp", mlp_no_dropout)
+    cfg = cfm.Config()
+    cfg.EPOCHS, cfg.DEVICE = 6, torch.device(DEV)
+    proc = cfm.DataProcessor(cfg)
+    with contextlib.redirect_stdout(io.StringIO()):
+        df = proc.prepare_features(cfm.generate_synthetic_data(700)).iloc[:512]
+        proc.fit(df)
+        data = proc.transform(df)
+    loader = DataLoader(cfm.CEOFirmDataset(data), batch_size=256, shuffle=False)
+
+    torch.manual_seed(11)
+    model = cmod.train_contrastive(loader, loader, data, cfg, contrastive_weight=0.3, temperature=0.07)
+    printed = capsys.readouterr().out
+    m0 = re.search(r"Epoch 0: Loss=([0-9.]+) \(MSE=([0-9.]+), CL=([0-9.]+)\)", printed)
+    m5 = re.search(r"Epoch 5: Loss=([0-9.]+) \(MSE=([0-9.]+), CL=([0-9.]+)\)", printed)
+    assert m0 and m5, printed
+    assert "Loss type: InfoNCE" in printed and next(model.parameters()).device.type == "cuda"
+
+    torch.manual_seed(11)
+    init = cmod.ContrastiveCEOFirmMatcher(data, cfg).state_dict()
+    p = {k: v.clone() for k, v in init.items()}
+    names = [k for k, v in p.items() if v.is_floating_point() and "running" not in k]
+    for k in names:
+        p[k].requires_grad_(True)
+    opt = torch.optim.Adam([p[k] for k in names], lr=cfg.LEARNING_RATE)
+    keys = ("firm_numeric", "firm_cat", "ceo_numeric", "ceo_cat", "target", "weights")
+    per_epoch = []
+    for epoch in range(6):
+        tot = np.zeros(3)
+        for s in range(0, 512, 256):
+            f_num, f_cat, c_num, c_cat, tgt, w = [data[k][s:s + 256] for k in keys]
+            opt.zero_grad()
+            score, fp, cp = oracle.contrastive_forward(p, f_num, f_cat, c_num, c_cat, training=True)
+            mse = oracle.weighted_mse(score, tgt, w)
+            cl = oracle.info_nce(fp, cp, 0.07)
+            loss = 0.7 * mse + 0.3 * cl
+            loss.backward()
+            opt.step()
+            tot += np.array([float(loss), float(mse), float(cl)])
+        per_epoch.append(tot / 2)
+    for m, want3 in ((m0, per_epoch[0]), (m5, per_epoch[5])):
+        for got, want in zip(m.groups(), want3):
+            assert float(got) == pytest.approx(want, rel=2e-3, abs=2e-4)
+    assert per_epoch[5][0] < per_epoch[0][0]                       # and the objective went down
+    sd = model.state_dict()
+    dead = {"base_model." + k for k in dead_bias_names(model.base_model.train())}
+    for k in names:
+        if k in dead:
+            continue
+        moved_o = (p[k].detach() - init[k]).double()
+        moved_g = (sd[k].cpu() - init[k]).double()
+        assert float((moved_g - moved_o).norm()) <= 0.3 * float(moved_o.norm()) + 1e-6, k
