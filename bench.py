@@ -420,12 +420,14 @@ def small_config_legs(device, with_cpu):
     val_loader = DataLoader(CEOFirmDataset(val_data), batch_size=256, shuffle=False)
     with quiet:
         train_model(train_loader, val_loader, train_data, cfg)              # warm-up: library load, allocator, graphs
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    with quiet:
-        model = train_model(train_loader, val_loader, train_data, cfg)
-    torch.cuda.synchronize()
-    loop_s = time.perf_counter() - t0
+    loop_s = float("inf")
+    for _ in range(3):                                  # a host-bound loop of ~0.1 s: best of 3 guards against hiccups
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with quiet:
+            model = train_model(train_loader, val_loader, train_data, cfg)
+        torch.cuda.synchronize()
+        loop_s = min(loop_s, time.perf_counter() - t0)
     # one step (fwd + loss + bwd + Adam) at B = 256 as a graph replay
     batch = [train_data[k][:256].to(device) for k in BATCH_KEYS]
     model.train()
@@ -490,12 +492,14 @@ def small_config_legs(device, with_cpu):
     warm.EPOCHS, warm.BATCH_SIZE, warm.DATA_PATH = 2, 128, "SYNTHETIC_MODE"
     with quiet:
         train_structural_model(s_train, s_val, sproc.get_metadata(), warm)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    with quiet:
-        smodel = train_structural_model(s_train, s_val, sproc.get_metadata(), scfg)
-    torch.cuda.synchronize()
-    s_loop = time.perf_counter() - t0
+    s_loop = float("inf")
+    for _ in range(2):                                  # best of 2 (see config 1)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with quiet:
+            smodel = train_structural_model(s_train, s_val, sproc.get_metadata(), scfg)
+        torch.cuda.synchronize()
+        s_loop = min(s_loop, time.perf_counter() - t0)
     n_train_steps = scfg.EPOCHS * len(s_train)
     out["config2_structural_cli"] = {
         "workload": "config2: structural_cli --synthetic --epochs 100 --batch-size 128 (1600 train / 400 val rows, KL distillation, Adam)",
