@@ -1002,14 +1002,6 @@ static float* dw_region(const cfm_tower_t& t, int s) {
 static float* misc_region(const cfm_tower_t& t) {
     return t.scratch + max_ctas() * (dw_region_floats(t, 1) + dw_region_floats(t, 2) + dw_region_floats(t, 3));
 }
-// The BatchNorm partials alternate between the two halves of the misc region from stage to stage: a tcgen05 stage
-// kernel reads its producer's partials in its prologue (folded finalize) while its own CTAs write theirs at their end.
-static int64_t misc_half_floats(const cfm_tower_t& t) {
-    int64_t d = 0;
-    for (int s = 1; s <= 3; ++s) d = std::max<int64_t>(d, std::max<int64_t>(stage_N(t, s), stage_K(t, s)));
-    return 2 * d + 8;                                  // per CTA; cfm_tower_scratch_floats reserves 4 d + 16
-}
-static float* misc_region(const cfm_tower_t& t, int half) { return misc_region(t) + half * max_ctas() * misc_half_floats(t); }
 extern "C" int64_t cfm_tower_scratch_floats(const cfm_tower_t* t) {
     int64_t m = 0, d = 0;
     for (int s = 1; s <= 3; ++s) {
@@ -1064,8 +1056,6 @@ extern "C" int cfm_towers_fwd(const cfm_tower_t* towers, int64_t n_towers, int64
         for (int i = 0; i < n_towers; ++i) use_tc[s] = use_tc[s] && tc_fwd_supported(towers[i], s);
     }
     if (towers[0].wimg) { int rc = tc_prep_launch(towers, (int)n_towers, stream); if (rc) return rc; }
-    bool fold_prev[2] = {false, false};                  // the previous stage left its BatchNorm finalize to this one
-    int prev_ctas[2] = {0, 0};
     for (int s = 1; s <= 3; ++s) {
         FwdArgs a{};
         a.B = B; a.err = err_flag; a.exact = exact ? 1 : 0;
@@ -1094,15 +1084,8 @@ extern "C" int cfm_towers_fwd(const cfm_tower_t* towers, int64_t n_towers, int64
             S.bias = s == 1 ? t.b1 : s == 2 ? t.b2 : t.b3;
             S.hout = s == 1 ? t.h1_raw : s == 2 ? t.h2_raw : t.out;
             bool bn_after = s == 1 || (s == 2 && t.bn2);
-            S.stat_part = (training && bn_after) ? misc_region(t, s - 1) : nullptr;
+            S.stat_part = (training && bn_after) ? misc_region(t) : nullptr;
             any_stats |= S.stat_part != nullptr;
-            if (fold_prev[i]) {                          // statistics of the BatchNorm in front: still per-CTA partials
-                S.fin.part = misc_region(t, s - 2); S.fin.nparts = prev_ctas[i];
-                S.fin.stat = s == 2 ? t.bn1_stat : t.bn2_stat;
-                S.fin.rm = s == 2 ? t.bn1_rm : t.bn2_rm;
-                S.fin.rv = s == 2 ? t.bn1_rv : t.bn2_rv;
-                S.fin.nbt = (long long*)(s == 2 ? t.bn1_nbt : t.bn2_nbt);
-            }
             size_t need = fwd_smem_bytes(t, s, a.tm);
             CFM_REQUIRE(use_tc[s] || need <= (size_t)MAX_SMEM, CFM_ERR_UNSUPPORTED,
                         "tower stage %d needs %zu B shared memory (> %d): layer %dx%d too large", s, need, MAX_SMEM,
@@ -1118,19 +1101,13 @@ extern "C" int cfm_towers_fwd(const cfm_tower_t* towers, int64_t n_towers, int64
             else tower_fwd_stage<false, 64><<<dim3(ctas, (unsigned)n_towers), NT, smem, stream>>>(a);
             CFM_LAUNCH_CHECK();
         }
-        // the tcgen05 kernel of the next stage merges the partials in its prologue (no finalize launch in between)
-        const bool fold_next = any_stats && s < 3 && use_tc[s + 1];
-        for (int i = 0; i < n_towers; ++i) {
-            fold_prev[i] = fold_next && a.st[i].stat_part != nullptr;
-            prev_ctas[i] = ctas_t[i];
-        }
-        if (any_stats && !fold_next) {
+        if (any_stats) {
             BnFwdFinArgs f{};
             for (int i = 0; i < n_towers; ++i) {
                 const cfm_tower_t& t = towers[i];
                 bool bn_after = s == 1 || (s == 2 && t.bn2);
                 BnFwdFin& F = f.t[i];
-                F.part = misc_region(t, s - 1); F.nparts = ctas_t[i]; F.N = bn_after ? stage_N(t, s) : 0;
+                F.part = misc_region(t); F.nparts = ctas_t[i]; F.N = bn_after ? stage_N(t, s) : 0;
                 F.stat = s == 1 ? t.bn1_stat : t.bn2_stat;
                 F.rm = s == 1 ? t.bn1_rm : t.bn2_rm;
                 F.rv = s == 1 ? t.bn1_rv : t.bn2_rv;
@@ -1184,19 +1161,6 @@ extern "C" int cfm_towers_bwd(const cfm_tower_t* towers, const cfm_tower_grads_t
         CFM_REQUIRE(!towers[i].bn2 || (g.dbn2_w && g.dbn2_b), CFM_ERR_INVALID, "null bn2 gradient buffer");
     }
     SideStream* side = side_stream();
-    // stages the tcgen05 kernels cover (every tower of the call must qualify): such a stage merges the BatchNorm-backward
-    // sums of the stage above it in its own prologue, which saves the finalize launch in between
-    bool tc_stage[4] = {false, false, false, false};
-    for (int s = 1; s <= 3; ++s) {
-        tc_stage[s] = true;
-        for (int i = 0; i < n_towers; ++i) {
-            const bool a_bn_i = s >= 2 && (s == 2 || towers[i].bn2);
-            const bool need_dx_i = s > 1 || grads[i].dx_emb || grads[i].dx_num;
-            tc_stage[s] = tc_stage[s] && tc_bwd_supported(towers[i], s, a_bn_i, need_dx_i);
-        }
-    }
-    bool fold_prev[2] = {false, false};
-    int prev_ctas[2] = {0, 0};
     for (int s = 3; s >= 1; --s) {
         BwdArgs a{};
         a.B = B;
@@ -1246,13 +1210,7 @@ extern "C" int cfm_towers_bwd(const cfm_tower_t* towers, const cfm_tower_grads_t
             }
             S.dW_part = dw_region(t, s);
             S.dy_out = s == 3 ? g.dy2 : s == 2 ? g.dy1 : nullptr;
-            S.sum_part = misc_region(t, s == 3 ? 0 : 1);
-            if (fold_prev[i]) {                          // sums of this stage's BatchNorm: still the partials of stage s + 1
-                S.fin.part = misc_region(t, s == 2 ? 0 : 1); S.fin.nparts = prev_ctas[i]; S.fin.B = (float)B;
-                S.fin.dgamma = s == 2 ? g.dbn2_w : g.dbn1_w;
-                S.fin.dbeta = s == 2 ? g.dbn2_b : g.dbn1_b;
-                S.fin.stat = s == 2 ? t.bn2_stat : t.bn1_stat;
-            }
+            S.sum_part = misc_region(t);
             S.dx_emb = s == 1 ? g.dx_emb : nullptr;
             S.dx_num = s == 1 ? g.dx_num : nullptr;
             S.need_dx = s > 1 || g.dx_emb || g.dx_num;
@@ -1301,13 +1259,8 @@ extern "C" int cfm_towers_bwd(const cfm_tower_t* towers, const cfm_tower_grads_t
             reduce_dw<<<dim3(std::min(ceil_div(maxS, 32), 592), (unsigned)n_towers), 256, 0, rs>>>(r);
             CFM_LAUNCH_CHECK();
         }
-        const bool fold_next = any_sums && s > 1 && tc_stage[s - 1];
-        for (int i = 0; i < n_towers; ++i) {
-            fold_prev[i] = fold_next && a.st[i].a_bn != 0;
-            prev_ctas[i] = ctas_t[i];
-        }
         ProfScope prof_red(PROF_REDUCE, stream);
-        if (any_sums && !fold_next) {
+        if (any_sums) {
             BnBwdFinArgs f{};
             for (int i = 0; i < n_towers; ++i) {
                 const cfm_tower_t& t = towers[i];

@@ -173,113 +173,16 @@ __device__ __forceinline__ void act_decode(const float4& code, const float* sm_b
     xhat = make_float4(xv[0], xv[1], xv[2], xv[3]);
 }
 
-// `folded`: mean and 1/std of the real columns come from fold_bn_fwd (the global statistics do not exist yet)
-__device__ __forceinline__ void stage_bn_params_tc(const ActSrc& a, int K, float* sm_bn, int tid, int nthreads, bool folded = false) {
+__device__ __forceinline__ void stage_bn_params_tc(const ActSrc& a, int K, float* sm_bn, int tid, int nthreads) {
     const int Kp = (K + 3) & ~3;
     if (a.bn_mode == 0) return;
     for (int c = tid; c < Kp; c += nthreads) {
         const bool ok = c < K;
-        if (!(folded && ok)) {
-            const float s = ok ? a.var_or_istd[c] : 1.f;
-            sm_bn[c] = ok ? a.mean[c] : 0.f;
-            sm_bn[Kp + c] = a.bn_mode == 2 ? rsqrtf(s + BN_EPS) : s;
-        }
+        const float s = ok ? a.var_or_istd[c] : 1.f;
+        sm_bn[c] = ok ? a.mean[c] : 0.f;
+        sm_bn[Kp + c] = a.bn_mode == 2 ? rsqrtf(s + BN_EPS) : s;
         sm_bn[2 * Kp + c] = ok ? a.gamma[c] : 0.f;
         sm_bn[3 * Kp + c] = ok ? a.beta[c] : 0.f;
-    }
-}
-
-// BatchNorm forward finalize in the consumer's prologue (the arithmetic of bn_fwd_finalize, tower.cu: one warp per
-// column, lanes Chan-merge a strided subset of the per-CTA (count, mean, M2) partials, then a fixed shuffle tree).
-// Writes mean -> sm_mean[c], 1/std -> sm_istd[c]; `writer` (one CTA per tower) also stores them and the running
-// statistics for everyone else.
-__device__ __forceinline__ void fold_bn_fwd(const BnFold& F, int N, float* sm_mean, float* sm_istd, bool writer, int warp,
-                                            int lane, int nwarps) {
-    // eight lanes per column, four columns per warp: all columns of a layer (<= 64) are merged in ONE round by the
-    // first 16 warps - the prologue is a chain of L2 round trips, so rounds are what costs
-    const int grp = lane >> 3, sub = lane & 7;
-    for (int c = 4 * warp + grp; c < ((N + 3) & ~3); c += 4 * nwarps) {
-        const bool okc = c < N;
-        float n = 0.f, mean = 0.f, m2 = 0.f;
-        constexpr int PF = 5;
-        for (int p0 = sub; p0 < F.nparts; p0 += 8 * PF) {
-            float nbv[PF], mbv[PF], qbv[PF];
-#pragma unroll
-            for (int u = 0; u < PF; ++u) {
-                const int p = p0 + 8 * u;
-                nbv[u] = 0.f; mbv[u] = 0.f; qbv[u] = 0.f;
-                if (okc && p < F.nparts) {
-                    const float* P = F.part + (size_t)p * (2 * N + 4);
-                    nbv[u] = P[2 * N]; mbv[u] = P[c]; qbv[u] = P[N + c];
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < PF; ++u) {
-                const float nb = nbv[u];
-                if (nb <= 0.f) continue;
-                const float d = mbv[u] - mean, nn = n + nb;
-                mean += d * (nb / nn);
-                m2 += qbv[u] + d * d * (n * nb / nn);
-                n = nn;
-            }
-        }
-#pragma unroll
-        for (int o = 4; o > 0; o >>= 1) {
-            const float nb = __shfl_down_sync(FULL, n, o, 8), mb = __shfl_down_sync(FULL, mean, o, 8);
-            const float qb = __shfl_down_sync(FULL, m2, o, 8);
-            if (nb > 0.f) {
-                const float d = mb - mean, nn = n + nb;
-                mean += d * (nb / nn);
-                m2 += qb + d * d * (n * nb / nn);
-                n = nn;
-            }
-        }
-        if (sub == 0 && okc) {
-            const float var_b = m2 / n, istd = rsqrtf(var_b + BN_EPS);
-            sm_mean[c] = mean;
-            sm_istd[c] = istd;
-            if (writer) {
-                F.stat[c] = mean;
-                F.stat[N + c] = istd;
-                if (F.rm) {
-                    const float var_u = n > 1.f ? m2 / (n - 1.f) : var_b;
-                    F.rm[c] = 0.9f * F.rm[c] + 0.1f * mean;       // momentum 0.1 (nn.BatchNorm1d default)
-                    F.rv[c] = 0.9f * F.rv[c] + 0.1f * var_u;
-                }
-            }
-        }
-    }
-    if (writer && warp == 0 && lane == 0 && F.nbt && N > 0) *F.nbt += 1;
-}
-// BatchNorm backward finalize in the consumer's prologue (the arithmetic of bn_bwd_finalize, tower.cu): sums of dy and
-// dy * x-hat over the batch -> c1 = sum dy / B, c2 = sum dy x-hat / B; `writer` stores the affine gradients.
-__device__ __forceinline__ void fold_bn_bwd(const BnFold& F, int N, float* sm_c1, float* sm_c2, bool want_c, bool writer,
-                                            int warp, int lane, int nwarps) {
-    const int grp = lane >> 3, sub = lane & 7;           // eight lanes per column, one round (see fold_bn_fwd)
-    for (int c = 4 * warp + grp; c < ((N + 3) & ~3); c += 4 * nwarps) {
-        const bool okc = c < N;
-        float s1 = 0.f, s2 = 0.f;
-        if (okc) {
-            for (int p = sub; p < F.nparts; p += 8) {
-                s1 += F.part[(size_t)p * 2 * N + c];
-                s2 += F.part[(size_t)p * 2 * N + N + c];
-            }
-        }
-#pragma unroll
-        for (int o = 4; o > 0; o >>= 1) {
-            s1 += __shfl_down_sync(FULL, s1, o, 8);
-            s2 += __shfl_down_sync(FULL, s2, o, 8);
-        }
-        if (sub == 0 && okc) {
-            const float c1 = s1 / F.B, c2 = s2 / F.B;
-            if (want_c) { sm_c1[c] = c1; sm_c2[c] = c2; }
-            if (writer) {
-                if (F.dbeta) F.dbeta[c] = s1;
-                if (F.dgamma) F.dgamma[c] = s2;
-                F.stat[2 * N + c] = c1;
-                F.stat[3 * N + c] = c2;
-            }
-        }
     }
 }
 
@@ -461,11 +364,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tower_fwd_tc(const __grid_const
     }
     constexpr uint32_t TMEM_COLS = 2 * NC;
     if (warp == TC_MMA_WARP) tmem_alloc(tmem_slot, TMEM_COLS);
-    if (!STAGE1) {
-        const bool folded = S.fin.part != nullptr;
-        stage_bn_params_tc(S.in.a, K, sm_bn, tid, TC_THREADS, folded);
-        if (folded) fold_bn_fwd(S.fin, K, sm_bn, sm_bn + Kp, cta == 0, warp, lane, TC_THREADS / 32);
-    }
+    if (!STAGE1) stage_bn_params_tc(S.in.a, K, sm_bn, tid, TC_THREADS);
     for (int c = tid; c < 64; c += TC_THREADS) sm_bias[c] = c < N ? S.bias[c] : 0.f;
     tc_fence_before();
     __syncthreads();
@@ -869,7 +768,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tower_bwd_tc(const __grid_const
         }
     }
     if (!STAGE1) stage_bn_params_tc(S.in.a, K, sm_bna, tid, TC_THREADS);
-    const bool folded = S.fin.part != nullptr;           // the BatchNorm-backward sums of this stage's BatchNorm are still partials
     if (S.g_mode) {
         for (int c = tid; c < Np; c += TC_THREADS) {
             const bool ok = c < N;
@@ -878,13 +776,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tower_bwd_tc(const __grid_const
             sm_bng[c] = ok ? S.g_mean[c] : 0.f;
             sm_bng[Np + c] = istd;
             sm_bng[2 * Np + c] = ok ? S.g_gamma[c] * istd : 0.f;
-            if (!(folded && ok && S.g_mode == 1)) {
-                sm_bng[3 * Np + c] = (ok && S.g_mode == 1) ? S.g_c1[c] : 0.f;
-                sm_bng[4 * Np + c] = (ok && S.g_mode == 1) ? S.g_c2[c] : 0.f;
-            }
+            sm_bng[3 * Np + c] = (ok && S.g_mode == 1) ? S.g_c1[c] : 0.f;
+            sm_bng[4 * Np + c] = (ok && S.g_mode == 1) ? S.g_c2[c] : 0.f;
         }
     }
-    if (folded) fold_bn_bwd(S.fin, N, sm_bng + 3 * Np, sm_bng + 4 * Np, S.g_mode == 1, cta == 0, warp, lane, TC_THREADS / 32);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();

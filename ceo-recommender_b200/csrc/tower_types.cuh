@@ -55,19 +55,6 @@ __host__ __device__ inline int ceil8(int k) { return (k + 7) & ~7; }
 // leading dimension for "transposed" fragment loads (lanes walk rows with t, columns with g): ld == 8 (mod 32)
 __host__ __device__ inline int pad_ld_t(int k) { int ld = (ceil8(k) + 31) & ~31; return ld + 8; }
 
-// BatchNorm finalize folded into the prologue of the tcgen05 stage kernel that consumes its result (tower_tc.cu): every
-// CTA merges the producer's per-CTA partials in CTA order (identical arithmetic in every CTA, hence identical values),
-// CTA 0 of the tower also stores what the stand-alone finalize kernels store.  part == nullptr: not folded.
-struct BnFold {
-    const float* part;    // forward: per-CTA (mean[N], M2[N], count) partials; backward: per-CTA [2N] sums
-    int nparts;
-    float* stat;          // [4,N]: mean, istd (forward) / c1, c2 (backward)
-    float *rm, *rv;       // forward: running statistics (nullable)
-    long long* nbt;       // forward: num_batches_tracked (nullable)
-    float *dgamma, *dbeta;   // backward: affine gradients
-    float B;              // backward: batch rows
-};
-
 struct FwdStage {
     InputDesc in;
     int N;
@@ -78,7 +65,6 @@ struct FwdStage {
     const float* wimg;    // tcgen05 path: forward weight image of this layer (tower_tc.cuh)
     float* a_out;         // tcgen05 path, stage > 1: where the producers save the input activation a (nullable)
     float* x_out;         // tcgen05 path, stage 1: stash of the gathered input tiles (nullable; tower_tc.cu)
-    BnFold fin;           // tcgen05 path, stage > 1: statistics of the BatchNorm in front of this stage, still as partials
 };
 struct FwdArgs {
     FwdStage st[2];
@@ -106,7 +92,6 @@ struct BwdStage {
     int need_dx;          // run the dX GEMM
     const float* wtimg;   // tcgen05 path: transposed weight image of this layer (tower_tc.cuh)
     const float* x_in;    // tcgen05 path, stage 1: the forward's stash of input tiles (nullable: gather again)
-    BnFold fin;           // tcgen05 path: BatchNorm-backward sums of the BatchNorm behind this stage, still as partials
 };
 struct BwdArgs {
     BwdStage st[2];
