@@ -130,6 +130,7 @@ def target_ranks(rows: torch.Tensor, cols: torch.Tensor, target: torch.Tensor) -
 _RANK_TC_MIN_PAIRS = 1 << 22      # below ~4M pairs the fp64 SIMT kernel is as fast as the filter + rescoring chain
 _RANK_BLOCK_ROWS = 65536
 _RANK_AMB_CAP = 1 << 25           # listed (row, column) pairs per row block: 256 MB
+_RANK_MIN_BLOCK = 2048            # row blocks are split down to this size before the exact kernel takes over
 
 
 def _score_error_bound(rows: torch.Tensor, cols: torch.Tensor) -> Tuple[bool, float]:
@@ -165,28 +166,46 @@ def diagonal_ranks(firm_emb: torch.Tensor, ceo_emb: torch.Tensor, method: str = 
     cb = pack(cols)
     out = torch.empty(n, dtype=torch.int64, device=dev)
     nb = min(n, _RANK_BLOCK_ROWS)
-    rpad = (nb + 255) // 256 * 256
-    part = torch.empty(N.lib().cfm_simtile_chunks(nb, C) * rpad, dtype=torch.int32, device=dev)
-    extra = torch.empty(nb, dtype=torch.int32, device=dev)
-    diag64 = torch.empty(nb, dtype=torch.float64, device=dev)
-    window = torch.empty(2 * nb, device=dev)
     amb = torch.empty(_RANK_AMB_CAP, 2, dtype=torch.int32, device=dev)
     amb_n = torch.zeros(1, dtype=torch.int32, device=dev)
-    statuses = []
-    with torch.cuda.device(dev):
-        for r0 in range(0, n, nb):
-            blk = rows[r0:r0 + nb]
-            status = torch.zeros(2, dtype=torch.int32, device=dev)
-            rbk = pack(blk)
-            N.check(N.lib().cfm_allpairs_diag_rank(N.ptr(blk), N.ptr(cols), N.ptr(rbk), N.ptr(cb), 1 if use_f16 else 0,
-                                                   blk.shape[0], C, D, cb.shape[1], r0, err, N.ptr(out[r0:r0 + nb]),
-                                                   N.ptr(status), N.ptr(part), N.ptr(extra), N.ptr(diag64), N.ptr(window),
-                                                   N.ptr(amb), _RANK_AMB_CAP, N.ptr(amb_n), N.stream_ptr()))
-            statuses.append(status)
-    over = torch.stack(statuses)[:, 0].tolist()          # one host read for all blocks
-    for i, flag in enumerate(over):                       # too many near-ties to list (degenerate inputs): exact kernel
-        if flag:
-            r0 = i * nb
-            blk = rows[r0:r0 + nb]
-            out[r0:r0 + nb] = target_ranks(blk, cols, torch.arange(r0, r0 + blk.shape[0], device=dev))
+    scratch = {}
+
+    def scratch_for(rows_n):
+        if rows_n not in scratch:
+            rpad = (rows_n + 255) // 256 * 256
+            scratch[rows_n] = (torch.empty(N.lib().cfm_simtile_chunks(rows_n, C) * rpad, dtype=torch.int32, device=dev),
+                               torch.empty(rows_n, dtype=torch.int32, device=dev),
+                               torch.empty(rows_n, dtype=torch.float64, device=dev),
+                               torch.empty(2 * rows_n, device=dev))
+        return scratch[rows_n]
+
+    # Row blocks whose near-tie list overflows (untrained embeddings: the positive sits inside the bulk of the scores,
+    # ~0.5 % of all pairs fall into the window) are split in four and run again; below _RANK_MIN_BLOCK rows the exact
+    # kernel takes over.  One host read per round of blocks.
+    pending = [(r0, min(nb, n - r0)) for r0 in range(0, n, nb)]
+    while pending:
+        statuses = []
+        with torch.cuda.device(dev):
+            for r0, rows_n in pending:
+                blk = rows[r0:r0 + rows_n]
+                part, extra, diag64, window = scratch_for(rows_n)
+                status = torch.zeros(2, dtype=torch.int32, device=dev)
+                rbk = pack(blk)
+                N.check(N.lib().cfm_allpairs_diag_rank(N.ptr(blk), N.ptr(cols), N.ptr(rbk), N.ptr(cb), 1 if use_f16 else 0,
+                                                       rows_n, C, D, cb.shape[1], r0, err, N.ptr(out[r0:r0 + rows_n]),
+                                                       N.ptr(status), N.ptr(part), N.ptr(extra), N.ptr(diag64), N.ptr(window),
+                                                       N.ptr(amb), _RANK_AMB_CAP, N.ptr(amb_n), N.stream_ptr()))
+                statuses.append(status)
+        over = torch.stack(statuses)[:, 0].tolist()
+        nxt = []
+        for (r0, rows_n), flag in zip(pending, over):
+            if not flag:
+                continue
+            if rows_n <= _RANK_MIN_BLOCK:           # still too many near-ties to list (degenerate inputs): exact kernel
+                blk = rows[r0:r0 + rows_n]
+                out[r0:r0 + rows_n] = target_ranks(blk, cols, torch.arange(r0, r0 + rows_n, device=dev))
+            else:
+                q = (rows_n + 3) // 4
+                nxt += [(a, min(q, r0 + rows_n - a)) for a in range(r0, r0 + rows_n, q)]
+        pending = nxt
     return out

@@ -165,6 +165,17 @@ __device__ __forceinline__ void rank_strip(const SimArgs& a, float (&v)[64], int
         for (int i = 0; i < 64; ++i)
             if (j0 + i >= a.C || j0 + i == dcol) v[i] = -INFINITY;
     }
+    // With trained embeddings the positive outranks almost every column: first a max tree (half an instruction per
+    // score) and one warp vote - only strips in which some row has a score at or above its window are counted
+    {
+        float m8[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            m8[k] = fmax3(fmax3(v[8 * k], v[8 * k + 1], v[8 * k + 2]), fmax3(v[8 * k + 3], v[8 * k + 4], v[8 * k + 5]),
+                          fmaxf(v[8 * k + 6], v[8 * k + 7]));
+        const float m = fmax3(fmax3(m8[0], m8[1], m8[2]), fmax3(m8[3], m8[4], m8[5]), fmaxf(m8[6], m8[7]));
+        if (!__any_sync(FULL, m >= lo)) return;
+    }
     int c_hi = 0, c_lo = 0;
 #pragma unroll
     for (int i = 0; i < 64; ++i) {

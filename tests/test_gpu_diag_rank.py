@@ -70,6 +70,20 @@ def test_row_blocks_overflow_fallback_and_bf16_operands(monkeypatch):
     monkeypatch.setattr(scoring, "_RANK_AMB_CAP", 16)                 # pair list overflows -> exact kernel for the block
     np.testing.assert_array_equal(scoring.diagonal_ranks(u.to(DEV), v.to(DEV), method="tensor").cpu().numpy(), want)
     monkeypatch.undo()
+    # untrained embeddings (positives inside the bulk): a list too small for a 1024-row block, large enough for its
+    # quarters -> the blocks are split and run again on the tensor path, the exact kernel is never called
+    ur, vr = _unit(R, 60, 13), _unit(R, 60, 14)
+    monkeypatch.setattr(scoring, "_RANK_BLOCK_ROWS", 1024)
+    monkeypatch.setattr(scoring, "_RANK_AMB_CAP", 6000)
+    monkeypatch.setattr(scoring, "_RANK_MIN_BLOCK", 128)
+
+    def no_exact(*a, **k):
+        raise AssertionError("exact kernel called")
+
+    monkeypatch.setattr(scoring, "target_ranks", no_exact)
+    np.testing.assert_array_equal(scoring.diagonal_ranks(ur.to(DEV), vr.to(DEV), method="tensor").cpu().numpy(),
+                                  _sorted_ranks(ur, vr))
+    monkeypatch.undo()
     big = 4000.0                                                      # outside fp16's comfortable range -> bf16 copies
     np.testing.assert_array_equal(scoring.diagonal_ranks((big * u).to(DEV), v.to(DEV), method="tensor").cpu().numpy(),
                                   _sorted_ranks(big * u, v))
