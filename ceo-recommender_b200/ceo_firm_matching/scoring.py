@@ -167,7 +167,7 @@ def diagonal_ranks(firm_emb: torch.Tensor, ceo_emb: torch.Tensor, method: str = 
     out = torch.empty(n, dtype=torch.int64, device=dev)
     nb = min(n, _RANK_BLOCK_ROWS)
     amb = torch.empty(_RANK_AMB_CAP, 2, dtype=torch.int32, device=dev)
-    amb_n = torch.zeros(1, dtype=torch.int32, device=dev)
+    amb_n = torch.zeros(1, dtype=torch.int64, device=dev)
     scratch = {}
 
     def scratch_for(rows_n):

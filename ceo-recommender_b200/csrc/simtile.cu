@@ -151,7 +151,7 @@ struct SimArgs {
     // are counted, scores inside it are listed as (row, column) pairs for exact rescoring
     const float *rk_lo, *rk_hi;   // [R]
     uint2* amb;                   // [amb_cap]
-    unsigned* amb_n;              // pairs listed so far (may run past amb_cap: the caller then falls back)
+    unsigned long long* amb_n;    // pairs found so far, 64-bit: may run far past amb_cap (the caller then falls back)
     unsigned amb_cap;
 };
 
@@ -192,10 +192,10 @@ __device__ __forceinline__ void rank_strip(const SimArgs& a, float (&v)[64], int
             if (lane >= o) scan += t;
         }
         const int total = __shfl_sync(FULL, scan, 31);
-        unsigned base = 0;
-        if (lane == 0) base = atomicAdd(a.amb_n, (unsigned)total);
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(a.amb_n, (unsigned long long)total);
         base = __shfl_sync(FULL, base, 0);
-        unsigned pos = base + (unsigned)(scan - h);
+        unsigned long long pos = base + (unsigned long long)(scan - h);
         if (h > 0) {
 #pragma unroll
             for (int i = 0; i < 64; ++i) {
@@ -1223,9 +1223,9 @@ __global__ void __launch_bounds__(128) allpairs_rank_kernel(const float* __restr
 // positive, and the fp32 window [d - e, d + e] outside of which a 16-bit-operand score decides the comparison
 __global__ void rank_prepare_kernel(const float* __restrict__ rows_f32, const float* __restrict__ cols_f32, int R, int C, int D,
                                     long long diag_offset, float err, double* __restrict__ diag64, float* __restrict__ lo,
-                                    float* __restrict__ hi, int* __restrict__ extra, unsigned* __restrict__ amb_n) {
+                                    float* __restrict__ hi, int* __restrict__ extra, unsigned long long* __restrict__ amb_n) {
     const int row = blockIdx.x * blockDim.x + threadIdx.x;
-    if (row == 0) *amb_n = 0u;
+    if (row == 0) *amb_n = 0ull;
     if (row >= R) return;
     const long long tcol = row + diag_offset;
     extra[row] = 0;
@@ -1244,8 +1244,8 @@ __global__ void rank_prepare_kernel(const float* __restrict__ rows_f32, const fl
 // thread per listed pair: exact comparison against the row's positive, ties broken by column index
 __global__ void rank_resolve_kernel(const float* __restrict__ rows_f32, const float* __restrict__ cols_f32, int D,
                                     long long diag_offset, const double* __restrict__ diag64, const uint2* __restrict__ amb,
-                                    const unsigned* __restrict__ amb_n, unsigned amb_cap, int* __restrict__ extra) {
-    const unsigned n = min(*amb_n, amb_cap);
+                                    const unsigned long long* __restrict__ amb_n, unsigned amb_cap, int* __restrict__ extra) {
+    const unsigned n = (unsigned)min(*amb_n, (unsigned long long)amb_cap);
     for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
         const uint2 e = amb[p];
         const float* u = rows_f32 + (long long)e.x * D;
@@ -1258,10 +1258,10 @@ __global__ void rank_resolve_kernel(const float* __restrict__ rows_f32, const fl
     }
 }
 __global__ void rank_finish_kernel(const int* __restrict__ part, int lists, int Rpad, const int* __restrict__ extra, int R, int C,
-                                   long long diag_offset, const unsigned* __restrict__ amb_n, unsigned amb_cap,
+                                   long long diag_offset, const unsigned long long* __restrict__ amb_n, unsigned amb_cap,
                                    long long* __restrict__ rank, int* __restrict__ status) {
     const int row = blockIdx.x * blockDim.x + threadIdx.x;
-    if (row == 0) { status[0] = *amb_n > amb_cap ? 1 : 0; status[1] = (int)min(*amb_n, 0x7fffffffu); }
+    if (row == 0) { status[0] = *amb_n > (unsigned long long)amb_cap ? 1 : 0; status[1] = (int)min(*amb_n, 0x7fffffffull); }
     if (row >= R) return;
     const long long tcol = row + diag_offset;
     long long c = extra[row];
@@ -1274,7 +1274,7 @@ __global__ void rank_finish_kernel(const int* __restrict__ part, int lists, int 
 extern "C" int cfm_allpairs_diag_rank(const float* rows_f32, const float* cols_f32, const void* rows_16, const void* cols_16,
                                       int64_t operands_f16, int64_t R, int64_t C, int64_t D, int64_t Dp, int64_t diag_offset,
                                       double err_bound, int64_t* rank, int32_t* status, int32_t* part, int32_t* extra,
-                                      double* diag64, float* window, void* amb, int64_t amb_cap, uint32_t* amb_n,
+                                      double* diag64, float* window, void* amb, int64_t amb_cap, uint64_t* amb_n,
                                       void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     CFM_REQUIRE(rows_f32 && cols_f32 && rows_16 && cols_16 && rank && status && part && extra && diag64 && window && amb && amb_n,
@@ -1291,18 +1291,18 @@ extern "C" int cfm_allpairs_diag_rank(const float* rows_f32, const float* cols_f
     a.cand_cnt = part;
     a.Rpad = (int)((R + 2 * ST_M - 1) / (2 * ST_M)) * 2 * ST_M;
     a.rk_lo = window; a.rk_hi = window + R;
-    a.amb = (uint2*)amb; a.amb_n = amb_n; a.amb_cap = (unsigned)amb_cap;
+    a.amb = (uint2*)amb; a.amb_n = (unsigned long long*)amb_n; a.amb_cap = (unsigned)amb_cap;
     ProfScope prof(PROF_TOPK, stream);
     rank_prepare_kernel<<<(int)((R + 127) / 128), 128, 0, stream>>>(rows_f32, cols_f32, (int)R, (int)C, (int)D, diag_offset,
-                                                                  (float)err_bound, diag64, window, window + R, extra, amb_n);
+                                                                  (float)err_bound, diag64, window, window + R, extra, (unsigned long long*)amb_n);
     CFM_LAUNCH_CHECK();
     int rc = launch_sim(a, rows_16, cols_16, chunks, stream);
     if (rc) return rc;
     rank_resolve_kernel<<<sm_count() * 8, 256, 0, stream>>>(rows_f32, cols_f32, (int)D, diag_offset, diag64, (const uint2*)amb,
-                                                           amb_n, (unsigned)amb_cap, extra);
+                                                           (const unsigned long long*)amb_n, (unsigned)amb_cap, extra);
     CFM_LAUNCH_CHECK();
     rank_finish_kernel<<<(int)((R + 127) / 128), 128, 0, stream>>>(part, 2 * chunks, a.Rpad, extra, (int)R, (int)C, diag_offset,
-                                                                 amb_n, (unsigned)amb_cap, (long long*)rank, status);
+                                                                 (const unsigned long long*)amb_n, (unsigned)amb_cap, (long long*)rank, status);
     CFM_LAUNCH_CHECK();
     return CFM_OK;
 }

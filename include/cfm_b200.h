@@ -387,11 +387,12 @@ int cfm_allpairs_rank(const float* rows_f32, const float* cols_f32, int64_t R, i
  * bound |16-bit-operand score - exact score| (2u |row| |col| + the fp32 accumulation error; u = 2^-11 fp16, 2^-9 bf16).
  *   status[0] = 1 when more than amb_cap pairs fell inside the windows (rank is then incomplete: use
  *   cfm_allpairs_rank), status[1] = pairs listed.  Scratch: part [cfm_simtile_chunks(R,C) * Rpad] with Rpad = R rounded
- *   up to 256, extra [R], diag64 [R], window [2R], amb [amb_cap] pairs of uint32, amb_n [1]. */
+ *   up to 256, extra [R], diag64 [R], window [2R], amb [amb_cap] pairs of uint32, amb_n [1] (64-bit: the count
+ *   cannot wrap even when every pair of a degenerate input falls inside the windows). */
 int cfm_allpairs_diag_rank(const float* rows_f32, const float* cols_f32, const void* rows_16, const void* cols_16,
                            int64_t operands_f16, int64_t R, int64_t C, int64_t D, int64_t Dp, int64_t diag_offset,
                            double err_bound, int64_t* rank /* [R] */, int32_t* status /* [2] */, int32_t* part,
-                           int32_t* extra, double* diag64, float* window, void* amb, int64_t amb_cap, uint32_t* amb_n,
+                           int32_t* extra, double* diag64, float* window, void* amb, int64_t amb_cap, uint64_t* amb_n,
                            void* stream);
 
 /* ------------------------------------------------------------------------------------------

@@ -102,3 +102,14 @@ def test_auto_switches_to_the_tensor_path_and_metrics_agree():
     want = _sorted_ranks(u, v)
     np.testing.assert_array_equal(got, want)
     assert oracle.retrieval_metrics(got) == oracle.retrieval_metrics(want)
+
+
+def test_degenerate_inputs_every_pair_a_tie():
+    """All rows and all columns identical: every score ties with the positive, every pair falls inside the window (the
+    64-bit pair counter overflows the list by orders of magnitude), ranks are decided by the column index alone."""
+    from ceo_firm_matching.scoring import diagonal_ranks
+    R = 4300
+    one = F.normalize(torch.randn(1, 60, generator=torch.Generator().manual_seed(9)), dim=1)
+    u, v = one.repeat(R, 1), one.repeat(R, 1)
+    got = diagonal_ranks(u.to(DEV), v.to(DEV), method="tensor").cpu().numpy()
+    np.testing.assert_array_equal(got, np.arange(1, R + 1))
