@@ -1325,7 +1325,7 @@ extern "C" int cfm_allpairs_topk(const float* rows_f32, const float* cols_f32, c
     a.cand = (uint2*)cand; a.cand_cnt = cand_cnt; a.cand_thr = cand_thr;
     a.f16 = operands_f16 != 0;
     // survivors of the filter = k + the columns within `margin` of the k-th score: ~24 for bf16 operands on
-    // 1M unit-norm columns, ~3 for fp16; the rest of the slack absorbs clustering before the exact fallback kicks in
+    // 1M unit-norm columns, ~6 for fp16; the rest of the slack absorbs clustering before the exact fallback kicks in
     a.keep = (int)std::min<int64_t>(TK_KEEP, ((k + (a.f16 ? 28 : 60) + 31) / 32) * 32);
     a.Rpad = (int)((R + 2 * ST_M - 1) / (2 * ST_M)) * 2 * ST_M;
     {
