@@ -13,7 +13,7 @@ def test_library_exports_every_declared_symbol():
     from ceo_firm_matching import _native
     header = open(os.path.join(ROOT, "include", "cfm_b200.h")).read()
     declared = set(re.findall(r"\b(cfm_[a-z0-9_]+)\s*\(", header))
-    declared -= {"cfm_tower", "cfm_tower_grads"}
+    declared -= {"cfm_tower", "cfm_tower_grads", "cfm_projector", "cfm_projector_grads"}
     lib = _native.lib()                                    # binds every prototype; AttributeError if one is missing
     assert lib.cfm_abi_version() == _native.CFM_ABI_VERSION
     for name in declared:
@@ -47,6 +47,8 @@ def test_struct_mirrors_match_header_field_order():
     assert fields("cfm_emb_group") == [f[0] for f in _native.EmbGroup._fields_]
     assert fields("cfm_peer_group") == [f[0] for f in _native.PeerGroup._fields_]
     assert fields("cfm_adam_tensor") == [f[0] for f in _native.AdamTensor._fields_]
+    assert fields("cfm_projector") == [f[0] for f in _native.Projector._fields_]
+    assert fields("cfm_projector_grads") == [f[0] for f in _native.ProjectorGrads._fields_]
 
 
 def test_modules_construct_on_cpu_and_refuse_cpu_forward():
